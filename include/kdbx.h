@@ -1,0 +1,154 @@
+/*
+ * kdbx.h — C ABI of the B200-native common-k-mer counting path (libkdbx.so).
+ *
+ * This is the drop-in boundary for ONE path of refresh-bio/kmer-db (v2.3.1): the
+ * similarity engine `SimilarityCalculator` over `PrefixKmerDb`'s pattern trie.  The
+ * reference has no FFI; the seam it offers is the C++ class declared in
+ *     src/similarity_calculator.h:4-16
+ * whose methods the mode drivers call once per run
+ *     src/console_all2all.cpp:21,34      (all2all)
+ *     src/console_all2all_sparse.cpp:30,44 (all2all_sp)
+ *     src/console_new2all.cpp:26,78,82   (one2all / one2all_sp)
+ * Every entry point below names the reference interface it replaces.  Plain pointers and
+ * sizes only: no C++ types, no torch types.  All functions return 0 (KDBX_OK) or a negative
+ * error code and never throw; `kdbx_last_error` gives the text.  The host-side C++ mirror
+ * (kmer-db_b200/host/similarity_calculator.h) rethrows std::runtime_error so that the CLI
+ * keeps the reference's error behaviour (src/main.cpp:51-59).
+ *
+ * There is NO CPU fallback behind this ABI: every compute entry point fails with
+ * KDBX_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef KDBX_H
+#define KDBX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KDBX_ABI_VERSION 1
+
+enum {
+    KDBX_OK = 0,
+    KDBX_ERR_ARG = -1,    /* bad argument / malformed trie view            */
+    KDBX_ERR_CUDA = -2,   /* CUDA runtime error, or no usable device       */
+    KDBX_ERR_STATE = -3,  /* call order violated (e.g. no patterns loaded) */
+    KDBX_ERR_NOMEM = -4   /* device or pinned-host allocation failed       */
+};
+
+typedef struct kdbx_ctx kdbx_ctx;
+
+/* Replaces the constructor arguments of SimilarityCalculator(num_threads, cacheBufferMb)
+ * (src/similarity_calculator.h:6).  `-buffer` (the 8 MB CPU cache block,
+ * src/similarity_calculator.cpp:51) has no meaning on the GPU; its analogue is `chunk_ids`,
+ * the number of decoded sample ids expanded per pass (sized to stay L2-resident). */
+typedef struct kdbx_config {
+    int32_t device;        /* CUDA ordinal; -1 = current device                          */
+    uint32_t flags;        /* KDBX_FLAG_*                                                */
+    uint64_t chunk_ids;    /* decoded ids per chunk; 0 = default                         */
+    uint32_t tile_cols;    /* columns per warp-private accumulator tile; 0 = default     */
+    uint32_t unit_updates; /* target updates per work unit; 0 = default                  */
+    uint64_t reserved[4];
+} kdbx_config;
+
+#define KDBX_FLAG_NONE 0u
+
+/* Borrowed, read-only SoA view of `std::vector<pattern_t>` (src/pattern.h:42-55) as
+ * PrefixKmerDb::getPatterns() exposes it (src/prefix_kmer_db.h:87-175).  One entry per trie
+ * node, index = pattern id; entry 0 is the empty sentinel (src/prefix_kmer_db.cpp:24).
+ * parent_id[p] < p or -1.  `payload` holds the Elias-gamma coded deltas of each node's LOCAL
+ * sample ids (src/elias_gamma.h:104-128), MSB-first in 64-bit words, node p starting at word
+ * payload_off[p] and spanning ceil(num_bits[p]/128)*2 words (src/pattern.h:80-82).
+ * The library copies what it needs; the view is NOT mutated (the reference's all2all
+ * mutates num_kmers in place, src/similarity_calculator.cpp:64-72 — we do not). */
+typedef struct kdbx_trie_view {
+    uint64_t num_patterns;
+    uint32_t num_samples;
+    uint32_t _pad;
+    const int64_t* num_kmers;          /* pattern_t::num_kmers                          */
+    const int64_t* parent_id;          /* pattern_t::parent_id                          */
+    const uint32_t* num_samples_full;  /* pattern_t::num_samples (node + ancestors), n  */
+    const uint32_t* num_local_samples; /* pattern_t::num_local_samples, l               */
+    const uint32_t* last_sample_id;    /* pattern_t::last_sample_id                     */
+    const uint32_t* num_bits;          /* pattern_t::num_bits                           */
+    const uint64_t* payload_off;       /* word offset of pattern_t::data; NULL = densely
+                                          packed in pattern order                       */
+    const uint64_t* payload;           /* concatenated pattern_t::data                  */
+    uint64_t payload_words;
+} kdbx_trie_view;
+
+/* Counters and per-stage device times of the last compute call (CUDA events on the
+ * library's stream).  U is a property of the input trie:
+ * U = sum_p l_p (2 n_p - l_p - 1) / 2 = the number of `row[col] += w` executions of the
+ * reference's dense path (src/simd/row_add_avx2.cpp:57-72). */
+typedef struct kdbx_stats {
+    uint64_t updates;        /* U restricted to the requested rows                       */
+    uint64_t jobs;           /* (pattern, local position, tile) work items emitted       */
+    uint64_t flat_ids;       /* sum_p n_p expanded                                       */
+    uint64_t local_ids;      /* sum_p l_p decoded                                        */
+    uint64_t units;          /* work units scheduled on warps                            */
+    uint32_t chunks;
+    uint32_t kernel_launches;/* kernels of this library launched by the call             */
+    float ms_upload;         /* H2D of the trie view (kdbx_load_patterns)                */
+    float ms_prepare;        /* scans, node packing, W accumulation, gamma decode        */
+    float ms_expand;         /* full-list expansion, all chunks                          */
+    float ms_bucket;         /* job histogram + scan + scatter + unit build, all chunks  */
+    float ms_scatter;        /* the scatter-add kernel, all chunks                       */
+    float ms_total;          /* whole compute call on the device                         */
+    float ms_download;       /* D2H of the result                                        */
+    uint32_t scatter_launches;
+    uint32_t _pad;
+    uint64_t reserved[4];
+} kdbx_stats;
+
+/* Library / device management ---------------------------------------------------------- */
+int kdbx_abi_version(void);
+int kdbx_device_count(void);   /* number of sm_100 devices, <0 on CUDA error */
+int kdbx_open(const kdbx_config* cfg, kdbx_ctx** out);
+void kdbx_close(kdbx_ctx* ctx);
+/* Error text of the last failed call on ctx (ctx may be NULL for kdbx_open failures). */
+const char* kdbx_last_error(const kdbx_ctx* ctx);
+
+/* Page-locked host memory for the trie view / result so that H2D and D2H run at link rate. */
+int kdbx_host_alloc(void** out, size_t bytes);
+void kdbx_host_free(void* p);
+
+/* Stage the trie in HBM.  Replaces handing `PrefixKmerDb&` to the calculator
+ * (src/console_all2all.cpp:26,34).  Only copies; all decoding happens in the compute calls. */
+int kdbx_load_patterns(kdbx_ctx* ctx, const kdbx_trie_view* view);
+
+/* Number of `row[col] += w` updates per matrix row (length num_samples), the quantity
+ * row-block sharding is balanced on; sum = U.  Computed on the device. */
+int kdbx_row_updates(kdbx_ctx* ctx, uint64_t* out_updates_per_row);
+
+/* Replaces SimilarityCalculator::all2all (src/similarity_calculator.cpp:42-438) including
+ * its W accumulation (:64-72), decode (:110-163), counting sort by row (:166-203,244-280)
+ * and row_add loop (:206-241; src/simd/row_add.h:16).  Fills the packed lower-triangular
+ * matrix exactly as LowerTriangularMatrix<uint32_t> lays it out (src/array.h:140,156-159):
+ * row s starts at s(s-1)/2 and has s cells; out_tri has N(N-1)/2 cells.  Bit-exact
+ * (uint32 wrap-around included).  `out_tri` is HOST memory. */
+int kdbx_all2all_dense(kdbx_ctx* ctx, uint32_t* out_tri, kdbx_stats* stats);
+
+/* Row-block shard of the same matrix for multi-GPU runs: only rows [row_begin,row_end)
+ * are computed; out_rows receives their cells, i.e. the packed range
+ * [row_begin(row_begin-1)/2, row_end(row_end-1)/2).  Analogue of the reference's row
+ * ownership between threads (src/similarity_calculator.cpp:371-395). */
+int kdbx_all2all_dense_rows(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end,
+                            uint32_t* out_rows, kdbx_stats* stats);
+
+/* Same, result left in DEVICE memory (`d_out_rows` is a CUDA device pointer on ctx's
+ * device, e.g. a torch tensor's data_ptr); no D2H inside the call. */
+int kdbx_all2all_dense_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end,
+                                   void* d_out_rows, kdbx_stats* stats);
+
+/* Debug / test taps (not used by the product path): copy intermediate device arrays of the
+ * last compute call to the host.  what: 0 = W (uint32[P]), 1 = decoded local ids
+ * (uint32[sum l]), 2 = local offsets (uint64[P+1]).  Returns elements written or <0. */
+int64_t kdbx_debug_fetch(kdbx_ctx* ctx, int what, void* out, uint64_t max_elems);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KDBX_H */

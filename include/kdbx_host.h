@@ -1,0 +1,80 @@
+/*
+ * kdbx_host.h — C ABI of the host-side companion library (libkdbx_host.so, no CUDA code).
+ *
+ * It holds what sits either side of the GPU path in the reference's mode drivers and that a
+ * caller in another language needs in order to drive libkdbx.so end to end:
+ *   - the .db reader/writer          (PrefixKmerDb::deserialize / serialize,
+ *                                      src/prefix_kmer_db.cpp:578-748 / 438-574)
+ *   - the byte-exact CSV emitters    (All2AllConsole::run, src/console_all2all.cpp:40-78)
+ *   - the synthetic database generator used by bench.py and the tests (ours).
+ * Everything returns 0 or a negative code; kdbxh_last_error() gives the (thread-local) text.
+ */
+#ifndef KDBX_HOST_H
+#define KDBX_HOST_H
+
+#include "kdbx.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kdbxh_trie kdbxh_trie;
+
+typedef struct kdbxh_synth_params {
+    uint32_t num_samples;
+    uint32_t num_clusters;
+    uint64_t genome_kmers;   /* distinct k-mers per genome (~ length in bp) */
+    uint32_t k;
+    int32_t interleaved;     /* 0: clusters contiguous in sample order; 1: round-robin */
+    double mutation_rate;    /* substitutions per base vs the template genome */
+    uint64_t seed;
+    int32_t threads;         /* 0 = all host cores */
+    int32_t _pad;
+} kdbxh_synth_params;
+
+typedef struct kdbxh_totals {
+    uint64_t num_patterns;
+    uint64_t num_samples;
+    uint64_t updates;        /* U = sum l(2n-l-1)/2 */
+    uint64_t sum_n;
+    uint64_t sum_l;
+    uint64_t payload_bytes;
+    uint64_t kmers_count;
+    uint32_t kmer_length;
+    uint32_t _pad;
+    double fraction;
+} kdbxh_totals;
+
+const char* kdbxh_last_error(void);
+
+/* pinned != 0: arrays live in page-locked memory (needs libkdbx.so + a CUDA device). */
+kdbxh_trie* kdbxh_trie_new(int pinned);
+void kdbxh_trie_free(kdbxh_trie* t);
+
+int kdbxh_read_db(kdbxh_trie* t, const char* path);
+int kdbxh_write_db(const kdbxh_trie* t, const char* path);
+int kdbxh_synth(kdbxh_trie* t, const kdbxh_synth_params* params);
+
+/* Structural checks a valid kmer-db trie satisfies (parent < child, n = n_parent + l,
+ * ascending local lists that continue the parent's list, payload bounds).  0 = valid. */
+int kdbxh_validate(const kdbxh_trie* t);
+
+/* dst := the sub-database of the first `num_samples` samples.  Only defined when those samples
+ * share no pattern with later ones and their patterns form a prefix of the pattern order (true
+ * at cluster boundaries of cluster-contiguous generated databases); anything else is an error.
+ * Used to cut a bounded sample of a workload for the CPU baseline. */
+int kdbxh_prefix(const kdbxh_trie* src, uint32_t num_samples, kdbxh_trie* dst);
+
+int kdbxh_view(const kdbxh_trie* t, kdbx_trie_view* out);
+int kdbxh_totals_of(const kdbxh_trie* t, kdbxh_totals* out);
+/* name of sample i (NUL-terminated, owned by the trie) and its total-kmers count */
+const char* kdbxh_sample_name(const kdbxh_trie* t, uint32_t i);
+uint64_t kdbxh_sample_kmers(const kdbxh_trie* t, uint32_t i);
+
+/* tri: packed lower-triangular uint32 matrix, N(N-1)/2 cells (src/array.h:140). */
+int kdbxh_write_all2all_csv(const kdbxh_trie* t, const uint32_t* tri, const char* path, int sparse);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KDBX_HOST_H */

@@ -1,0 +1,883 @@
+// libkdbx.so — B200 (sm_100a) implementation of kmer-db's dense all2all common-k-mer counting.
+//
+// Replaces SimilarityCalculator::all2all (src/similarity_calculator.cpp:42-438) and what it
+// calls: the W accumulation up the trie (:64-72), pattern_t::decodeSamples + CEliasGamma
+// (src/pattern.cpp:99-109, src/elias_gamma.h:133-256), the counting sort of row-add jobs by
+// sample id (:166-203, :244-280) and the row_add inner loop (src/simd/row_add_avx2.cpp:31-124).
+// Nothing here is a translation: the CPU code streams 8 MB cache blocks through four thread
+// pools; this file keeps the whole trie in HBM, expands full sample-id lists in L2-sized
+// chunks and runs the scatter-add on warp-private shared-memory accumulator tiles.
+//
+// Pipeline of one kdbx_all2all_dense* call (all on one stream, two host syncs up front):
+//   prepare : scans of l / n / chunk cost (CUB), node packing, W accumulation, gamma decode
+//   per chunk of patterns [p0,p1):
+//     K_expand     full list of p = locals of its ancestors (root first) ++ locals of p
+//     K_job_hist   one job per (pattern, local position i, column tile t): row = full[i],
+//                  cols = full[0..i) restricted to tile t; histogram by key = row*T + t
+//     scan         bucket offsets
+//     K_job_fill   counting-sort scatter of 16-byte job records
+//     K_units      split every bucket into work units of ~unit_updates updates
+//     K_scatter    THE hot kernel: a warp owns a (row, tile) accumulator in shared memory,
+//                  streams its jobs' id runs with coalesced loads, does conflict-free
+//                  LDS/IADD/STS (ids inside a run are distinct), then flushes the tile into
+//                  the packed triangle with red.global.add.u32
+// Integer adds commute, so any schedule gives the reference's bits (uint32 wrap included).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include "../../include/kdbx.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// device-side records
+// ------------------------------------------------------------------------------------------
+struct __align__(32) Node {  // one 32-byte sector per chain step
+    int32_t parent;
+    uint32_t n;       // samples in node + ancestors
+    uint32_t l;       // local samples
+    uint32_t last;    // last local sample id
+    uint64_t loff;    // offset of the node's decoded local ids in d_loc
+    uint64_t pad;
+};
+
+struct __align__(16) Job {  // cols = flat[off .. off+len), weight w
+    uint32_t off;
+    uint32_t len;
+    uint32_t w;
+    uint32_t pad;
+};
+
+struct __align__(16) Unit {  // jobs [job_begin, job_end) all belong to one key = row*T + tile
+    uint32_t key;
+    uint32_t job_begin;
+    uint32_t job_end;
+    uint32_t pad;
+};
+
+constexpr int kScatterThreads = 256;
+constexpr int kWarpsPerBlock = kScatterThreads / 32;
+constexpr uint32_t kMaxTiles = 31;
+
+__device__ __forceinline__ uint64_t tri_offset(uint64_t row) { return row * (row - 1) / 2; }
+
+// ------------------------------------------------------------------------------------------
+// prepare kernels
+// ------------------------------------------------------------------------------------------
+struct U32AsU64 {
+    const uint32_t* p; uint64_t n;
+    __host__ __device__ uint64_t operator()(uint64_t i) const { return i < n ? (uint64_t)p[i] : 0ull; }
+};
+struct PayloadWords {
+    const uint32_t* bits; uint64_t n;
+    __host__ __device__ uint64_t operator()(uint64_t i) const {
+        if (i >= n) return 0ull;
+        const uint32_t b = bits[i];
+        return b == 0 ? 0ull : (uint64_t)((b + 127u) / 128u) * 2ull;
+    }
+};
+// chunking cost of a pattern: it needs n ids of flat space and at most l*(tiles its ids can
+// span) job slots; both buffers hold `chunk_ids` entries.
+struct ChunkCost {
+    const uint32_t* n; const uint32_t* l; const uint32_t* last; uint64_t cnt; uint32_t tile_cols;
+    __host__ __device__ uint64_t operator()(uint64_t i) const {
+        if (i >= cnt) return 0ull;
+        const uint64_t jobs = (uint64_t)l[i] * (uint64_t)(last[i] / tile_cols + 1u);
+        const uint64_t ids = n[i];
+        return jobs > ids ? jobs : ids;
+    }
+};
+
+__global__ void k_build_nodes(uint64_t P, const int64_t* __restrict__ parent, const int64_t* __restrict__ num_kmers,
+                              const uint32_t* __restrict__ n, const uint32_t* __restrict__ l,
+                              const uint32_t* __restrict__ last, const uint64_t* __restrict__ loff,
+                              Node* __restrict__ nodes, uint32_t* __restrict__ W) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    Node nd;
+    nd.parent = (int32_t)parent[p];
+    nd.n = n[p]; nd.l = l[p]; nd.last = last[p]; nd.loff = loff[p]; nd.pad = 0;
+    nodes[p] = nd;
+    W[p] = (uint32_t)num_kmers[p];  // the reference adds (uint32_t)num_kmers (similarity_calculator.cpp:222)
+}
+
+// W_p = sum of num_kmers over p's subtree, mod 2^32 (reference: serial reverse sweep,
+// similarity_calculator.cpp:64-72).  Every node pushes its own count to all its ancestors.
+__global__ void k_accumulate_w(uint64_t P, const int64_t* __restrict__ num_kmers, const Node* __restrict__ nodes,
+                               uint32_t* __restrict__ W) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const uint32_t v = (uint32_t)num_kmers[p];
+    if (v == 0) return;
+    int32_t q = nodes[p].parent;
+    while (q >= 0) {
+        atomicAdd(&W[q], v);
+        q = nodes[q].parent;
+    }
+}
+
+__device__ __forceinline__ uint32_t gamma_field(const uint64_t* __restrict__ w, uint32_t pos, uint32_t cnt) {
+    if (cnt == 0) return 0;
+    const uint32_t i = pos >> 6, off = pos & 63;
+    uint64_t x = w[i] << off;
+    if (off + cnt > 64) x |= w[i + 1] >> (64 - off);
+    return (uint32_t)(x >> (64 - cnt));
+}
+
+// One Elias-gamma value at bit `pos` (format: SURVEY.md §A.1); `limit` = num_bits guards
+// against malformed streams (returns 0 and leaves pos >= limit).
+__device__ __forceinline__ uint32_t gamma_next(const uint64_t* __restrict__ w, uint32_t& pos, uint32_t limit) {
+    uint32_t ones = 0;
+    while (pos < limit) {
+        const uint32_t i = pos >> 6, off = pos & 63;
+        const uint64_t x = ~(w[i] << off);
+        const uint32_t avail = 64 - off;
+        const uint32_t run = x ? (uint32_t)__clzll((long long)x) : 64u;
+        if (run >= avail) { ones += avail; pos += avail; continue; }
+        ones += run; pos += run + 1;
+        if (ones > 31 || pos + ones > limit) { pos = limit + 1; return 0; }
+        const uint32_t low = gamma_field(w, pos, ones);
+        pos += ones;
+        return (1u << ones) | low;
+    }
+    pos = limit + 1;
+    return 0;
+}
+
+// Decodes the LOCAL ids of every pattern into d_loc (ascending), one thread per pattern.
+__global__ void k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint32_t* __restrict__ bits,
+                                const uint64_t* __restrict__ poff, const uint64_t* __restrict__ payload,
+                                uint32_t* __restrict__ loc, uint32_t N, int* __restrict__ err) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const Node nd = nodes[p];
+    if (nd.l == 0) return;
+    uint32_t* out = loc + nd.loff;
+    if (nd.l == 1) { out[0] = nd.last; if (nd.last >= N) atomicExch(err, 2); return; }
+    const uint64_t* w = payload + poff[p];
+    const uint32_t nb = bits[p];
+    uint32_t pos = 0;
+    for (uint32_t i = 0; i + 1 < nd.l; ++i) out[i] = gamma_next(w, pos, nb);
+    if (pos != nb) { atomicExch(err, 1); }
+    uint32_t cur = nd.last;
+    for (uint32_t i = nd.l; i-- > 0;) {
+        const uint32_t d = i > 0 ? out[i - 1] : 0u;
+        out[i] = cur;
+        cur -= d;
+    }
+    if (nd.last >= N || out[0] > nd.last) atomicExch(err, 2);
+}
+
+// smallest p with off[p] >= c * chunk  (off is the exclusive scan of the chunk cost, P+1 long)
+__global__ void k_chunk_bounds(uint64_t P, const uint64_t* __restrict__ coff, uint64_t chunk, uint32_t nchunks,
+                               uint64_t* __restrict__ bounds) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > nchunks) return;
+    if (c == nchunks) { bounds[c] = P; return; }
+    const uint64_t target = (uint64_t)c * chunk;
+    uint64_t lo = 0, hi = P;  // first index with coff[idx] >= target
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (coff[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    bounds[c] = lo;
+}
+
+// per-row update counts (sum over jobs of the position i), for work-balanced row sharding
+__global__ void k_row_updates(uint64_t P, const Node* __restrict__ nodes, const uint32_t* __restrict__ loc,
+                              unsigned long long* __restrict__ upd) {
+    const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint64_t p = gw; p < P; p += nw) {
+        const Node nd = nodes[p];
+        const uint32_t first = nd.n - nd.l;
+        for (uint32_t j = lane; j < nd.l; j += 32) {
+            const uint32_t i = first + j;
+            if (i) atomicAdd(&upd[loc[nd.loff + j]], (unsigned long long)i);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-chunk kernels
+// ------------------------------------------------------------------------------------------
+
+// Full list of p = local lists of its ancestors (root first) followed by its own; node q's
+// locals land at positions [n_q - l_q, n_q).  One warp per pattern, walking the parent chain.
+__global__ void k_expand(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
+                         const uint32_t* __restrict__ loc, uint32_t* __restrict__ flat) {
+    const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t base0 = noff[p0];
+    for (uint64_t p = p0 + gw; p < p1; p += nw) {
+        Node nd = nodes[p];
+        if (nd.n == 0) continue;
+        uint32_t* dst = flat + (noff[p] - base0);
+        for (;;) {
+            const uint32_t* src = loc + nd.loff;
+            const uint32_t at = nd.n - nd.l;
+            for (uint32_t j = lane; j < nd.l; j += 32) dst[at + j] = src[j];
+            if (nd.parent < 0) break;
+            nd = nodes[nd.parent];
+        }
+    }
+}
+
+// Shared by the histogram and fill passes: enumerate the jobs of pattern p.
+// emit(key, off, len) is called by the lane that owns local position j.
+template <class Emit>
+__device__ __forceinline__ void for_each_job(const Node& nd, uint32_t base, const uint32_t* __restrict__ flat,
+                                             uint32_t T, uint32_t tile_cols, uint32_t row_begin, uint32_t row_end,
+                                             uint32_t lane, unsigned long long& updates, Emit emit) {
+    const uint32_t first = nd.n - nd.l;
+    // tile boundaries inside the (ascending) full list: bound_t = first index with id >= t*tile_cols
+    uint32_t my_bound = 0;
+    if (T > 1) {
+        if (lane <= T) {
+            const uint32_t target = lane * tile_cols;
+            uint32_t lo = 0, hi = nd.n;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (flat[base + mid] >= target) hi = mid; else lo = mid + 1;
+            }
+            my_bound = lo;
+        }
+    } else {
+        my_bound = (lane == 0) ? 0u : nd.n;
+    }
+    const uint32_t rounds = (nd.l + 31) / 32;
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t j = r * 32 + lane;
+        const bool have = j < nd.l;
+        const uint32_t i = first + j;
+        uint32_t row = 0;
+        bool active = false;
+        if (have && i > 0) {
+            row = flat[base + i];
+            active = row >= row_begin && row < row_end;
+        }
+        if (active) updates += i;
+        for (uint32_t t = 0; t < T; ++t) {
+            const uint32_t a = __shfl_sync(0xffffffffu, my_bound, t);
+            uint32_t b = __shfl_sync(0xffffffffu, my_bound, t + 1);
+            if (active) {
+                b = b < i ? b : i;
+                if (b > a) emit(row * T + t, base + a, b - a);
+            }
+        }
+    }
+}
+
+__global__ void k_job_hist(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
+                           const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T,
+                           uint32_t tile_cols, uint32_t row_begin, uint32_t row_end, uint32_t* __restrict__ hist,
+                           unsigned long long* __restrict__ work, unsigned long long* __restrict__ total_updates) {
+    const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t base0 = noff[p0];
+    unsigned long long updates = 0;
+    for (uint64_t p = p0 + gw; p < p1; p += nw) {
+        const Node nd = nodes[p];
+        if (nd.l == 0) continue;
+        const bool weightless = W[p] == 0;  // adds of 0 are skipped, but still counted in U
+        const uint32_t base = (uint32_t)(noff[p] - base0);
+        for_each_job(nd, base, flat, T, tile_cols, row_begin, row_end, lane, updates,
+                     [&](uint32_t key, uint32_t, uint32_t len) {
+                         if (weightless) return;
+                         atomicAdd(&hist[key], 1u);
+                         atomicAdd(&work[key], (unsigned long long)len);
+                     });
+    }
+    for (int o = 16; o; o >>= 1) updates += __shfl_xor_sync(0xffffffffu, updates, o);
+    if (lane == 0 && updates) atomicAdd(total_updates, updates);
+}
+
+__global__ void k_job_fill(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
+                           const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T,
+                           uint32_t tile_cols, uint32_t row_begin, uint32_t row_end, uint32_t* __restrict__ cursor,
+                           Job* __restrict__ jobs) {
+    const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t base0 = noff[p0];
+    unsigned long long updates = 0;
+    for (uint64_t p = p0 + gw; p < p1; p += nw) {
+        const Node nd = nodes[p];
+        if (nd.l == 0) continue;
+        const uint32_t w = W[p];
+        if (w == 0) continue;
+        const uint32_t base = (uint32_t)(noff[p] - base0);
+        for_each_job(nd, base, flat, T, tile_cols, row_begin, row_end, lane, updates,
+                     [&](uint32_t key, uint32_t off, uint32_t len) {
+                         const uint32_t slot = atomicAdd(&cursor[key], 1u);
+                         Job jb; jb.off = off; jb.len = len; jb.w = w; jb.pad = 0;
+                         jobs[slot] = jb;
+                     });
+    }
+}
+
+// units per key = ceil(work / unit_updates) (>= 1 when the bucket is non-empty)
+__global__ void k_unit_count(uint32_t nkeys, const uint32_t* __restrict__ hist, const unsigned long long* __restrict__ work,
+                             uint32_t unit_updates, uint32_t* __restrict__ ucount) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > nkeys) return;
+    uint32_t c = 0;
+    if (k < nkeys && hist[k]) {
+        const unsigned long long u = (work[k] + unit_updates - 1) / unit_updates;
+        c = (uint32_t)(u < 1 ? 1 : (u > hist[k] ? hist[k] : u));
+    }
+    ucount[k] = c;  // ucount[nkeys] = 0 so that the exclusive scan yields the total there
+}
+
+__global__ void k_unit_fill(uint32_t nkeys, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ bucket_off,
+                            const uint32_t* __restrict__ ucount, const uint32_t* __restrict__ uoff,
+                            Unit* __restrict__ units) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkeys) return;
+    const uint32_t c = ucount[k];
+    if (c == 0) return;
+    const uint32_t jobs = hist[k], b0 = bucket_off[k];
+    const uint32_t per = (jobs + c - 1) / c;
+    for (uint32_t u = 0; u < c; ++u) {
+        Unit un;
+        un.key = k;
+        un.job_begin = b0 + min(jobs, u * per);
+        un.job_end = b0 + min(jobs, (u + 1) * per);
+        un.pad = 0;
+        units[uoff[k] + u] = un;
+    }
+}
+
+// THE hot kernel.  Persistent warps pull work units from a global counter.  For its unit a
+// warp zeroes a private tile of `tile_cols` uint32 accumulators in shared memory, then for
+// every job adds w to tile[id - col0] for the ids of the job's run.  Ids inside one run are
+// distinct, so a warp-wide LDS / IADD / STS never collides with itself; runs of different
+// jobs are separated by __syncwarp().  Finally the tile is added into the packed
+// lower-triangular matrix (src/array.h:140) with red.global.add.u32.
+__global__ void __launch_bounds__(kScatterThreads)
+k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_units_ptr, const Job* __restrict__ jobs,
+              const uint32_t* __restrict__ flat, uint32_t* __restrict__ tri, uint64_t tri_base, uint32_t T,
+              uint32_t tile_cols, uint32_t* __restrict__ unit_counter) {
+    extern __shared__ uint32_t smem[];
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t* tile = smem + (threadIdx.x >> 5) * tile_cols;
+    const uint32_t n_units = *n_units_ptr;
+    for (;;) {
+        uint32_t u = 0;
+        if (lane == 0) u = atomicAdd(unit_counter, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= n_units) break;
+        const Unit un = units[u];
+        const uint32_t row = un.key / T, t = un.key - row * T;
+        const uint32_t col0 = t * tile_cols;
+        const uint32_t ncols = min(tile_cols, row - col0);  // only columns < row exist
+        for (uint32_t c = lane; c < ncols; c += 32) tile[c] = 0;
+        __syncwarp();
+        for (uint32_t jb = un.job_begin; jb < un.job_end; jb += 32) {
+            const uint32_t cnt = min(32u, un.job_end - jb);
+            Job mine; mine.off = 0; mine.len = 0; mine.w = 0; mine.pad = 0;
+            if (lane < cnt) mine = jobs[jb + lane];
+            for (uint32_t j = 0; j < cnt; ++j) {
+                const uint32_t off = __shfl_sync(0xffffffffu, mine.off, j);
+                const uint32_t len = __shfl_sync(0xffffffffu, mine.len, j);
+                const uint32_t w = __shfl_sync(0xffffffffu, mine.w, j);
+                const uint32_t* __restrict__ ids = flat + off;
+                uint32_t k = lane;
+                // 4 independent loads in flight per lane; all ids of a run are distinct
+                for (; k + 96 < len; k += 128) {
+                    const uint32_t i0 = ids[k] - col0, i1 = ids[k + 32] - col0;
+                    const uint32_t i2 = ids[k + 64] - col0, i3 = ids[k + 96] - col0;
+                    const uint32_t v0 = tile[i0], v1 = tile[i1], v2 = tile[i2], v3 = tile[i3];
+                    tile[i0] = v0 + w; tile[i1] = v1 + w; tile[i2] = v2 + w; tile[i3] = v3 + w;
+                }
+                for (; k < len; k += 32) {
+                    const uint32_t i0 = ids[k] - col0;
+                    tile[i0] += w;
+                }
+                __syncwarp();
+            }
+        }
+        const uint64_t out0 = tri_offset(row) - tri_base + col0;
+        for (uint32_t c = lane; c < ncols; c += 32) {
+            const uint32_t v = tile[c];
+            if (v) atomicAdd(&tri[out0 + c], v);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+        const size_t want = need + need / 16 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+std::string g_open_error;
+
+}  // namespace
+
+struct kdbx_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    kdbx_config cfg{};
+    std::string err;
+
+    // staged trie (raw, as uploaded)
+    uint64_t P = 0;
+    uint32_t N = 0;
+    uint64_t payload_words = 0;
+    bool loaded = false;
+    bool dense_payload = false;
+    DevBuf num_kmers, parent, n, l, last, bits, poff, payload;
+    float ms_upload = 0.f;
+
+    // prepared
+    DevBuf nodes, W, loc, loff, noff, coff, bounds, err_flag, cub_tmp;
+    // per chunk
+    DevBuf flat, jobs, hist, work, bucket_off, cursor, ucount, uoff, units, counters;
+    DevBuf tri, rowupd;
+    uint64_t sum_l = 0, sum_n = 0;
+
+    std::vector<cudaEvent_t> events;
+    size_t ev_used = 0;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        err = buf;
+        return code;
+    }
+    cudaEvent_t event() {
+        if (ev_used == events.size()) { cudaEvent_t e; cudaEventCreate(&e); events.push_back(e); }
+        cudaEvent_t e = events[ev_used++];
+        cudaEventRecord(e, stream);
+        return e;
+    }
+};
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return ctx->fail(e__ == cudaErrorMemoryAllocation ? KDBX_ERR_NOMEM : KDBX_ERR_CUDA, \
+                             "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+namespace {
+
+inline unsigned blocks_for(uint64_t items, unsigned threads) { return (unsigned)((items + threads - 1) / threads); }
+
+template <class InIt>
+int scan_exclusive(kdbx_ctx* ctx, InIt in, uint64_t* out, uint64_t count) {
+    size_t tmp = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, count, ctx->stream));
+    CK(ctx->cub_tmp.ensure(tmp));
+    CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, out, count, ctx->stream));
+    return KDBX_OK;
+}
+int scan_exclusive_u32(kdbx_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_t count) {
+    size_t tmp = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, count, ctx->stream));
+    CK(ctx->cub_tmp.ensure(tmp));
+    CK(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, out, count, ctx->stream));
+    return KDBX_OK;
+}
+
+struct Plan {
+    uint32_t tile_cols = 0, T = 0, unit_updates = 0;
+    uint64_t chunk = 0;
+};
+
+int make_plan(kdbx_ctx* ctx, Plan& pl) {
+    const uint32_t N = ctx->N;
+    uint32_t tc = ctx->cfg.tile_cols;
+    if (tc == 0) tc = N <= 1024 ? 1024 : 2048;
+    if (tc < 32 || (tc & 31)) return ctx->fail(KDBX_ERR_ARG, "tile_cols must be a multiple of 32");
+    if ((size_t)tc * 4 * kWarpsPerBlock > 227 * 1024) return ctx->fail(KDBX_ERR_ARG, "tile_cols too large for shared memory");
+    const uint32_t T = N == 0 ? 1 : (N + tc - 1) / tc;
+    if (T > kMaxTiles)
+        return ctx->fail(KDBX_ERR_ARG, "dense all2all supports at most %u samples with tile_cols=%u (got %u)",
+                         kMaxTiles * tc, tc, N);
+    pl.tile_cols = tc; pl.T = T;
+    pl.unit_updates = ctx->cfg.unit_updates ? ctx->cfg.unit_updates : 32768u;
+    pl.chunk = ctx->cfg.chunk_ids ? ctx->cfg.chunk_ids : ((uint64_t)12 << 20);
+    if (pl.chunk < 4096) pl.chunk = 4096;
+    if (pl.chunk > ((uint64_t)1 << 31)) pl.chunk = (uint64_t)1 << 31;
+    return KDBX_OK;
+}
+
+// scans + node packing + W + gamma decode.  Leaves sum_l / sum_n on the host (one sync).
+int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
+    const uint64_t P = ctx->P;
+    cudaStream_t st = ctx->stream;
+    CK(ctx->loff.ensure((P + 1) * 8)); CK(ctx->noff.ensure((P + 1) * 8)); CK(ctx->coff.ensure((P + 1) * 8));
+    CK(ctx->nodes.ensure(P * sizeof(Node))); CK(ctx->W.ensure(P * 4)); CK(ctx->err_flag.ensure(16));
+    cub::CountingInputIterator<uint64_t> idx(0);
+    {
+        cub::TransformInputIterator<uint64_t, U32AsU64, cub::CountingInputIterator<uint64_t>> it(idx, U32AsU64{ctx->l.as<uint32_t>(), P});
+        if (int rc = scan_exclusive(ctx, it, ctx->loff.as<uint64_t>(), P + 1)) return rc;
+    }
+    {
+        cub::TransformInputIterator<uint64_t, U32AsU64, cub::CountingInputIterator<uint64_t>> it(idx, U32AsU64{ctx->n.as<uint32_t>(), P});
+        if (int rc = scan_exclusive(ctx, it, ctx->noff.as<uint64_t>(), P + 1)) return rc;
+    }
+    {
+        ChunkCost cc{ctx->n.as<uint32_t>(), ctx->l.as<uint32_t>(), ctx->last.as<uint32_t>(), P, pl.tile_cols};
+        cub::TransformInputIterator<uint64_t, ChunkCost, cub::CountingInputIterator<uint64_t>> it(idx, cc);
+        if (int rc = scan_exclusive(ctx, it, ctx->coff.as<uint64_t>(), P + 1)) return rc;
+    }
+    launches += 3;
+    if (ctx->dense_payload) {
+        CK(ctx->poff.ensure((P + 1) * 8));
+        cub::TransformInputIterator<uint64_t, PayloadWords, cub::CountingInputIterator<uint64_t>> it(idx, PayloadWords{ctx->bits.as<uint32_t>(), P});
+        if (int rc = scan_exclusive(ctx, it, ctx->poff.as<uint64_t>(), P + 1)) return rc;
+        launches += 1;
+    }
+    CK(cudaMemsetAsync(ctx->err_flag.p, 0, 16, st));
+    k_build_nodes<<<blocks_for(P, 256), 256, 0, st>>>(P, ctx->parent.as<int64_t>(), ctx->num_kmers.as<int64_t>(),
+                                                       ctx->n.as<uint32_t>(), ctx->l.as<uint32_t>(), ctx->last.as<uint32_t>(),
+                                                       ctx->loff.as<uint64_t>(), ctx->nodes.as<Node>(), ctx->W.as<uint32_t>());
+    k_accumulate_w<<<blocks_for(P, 256), 256, 0, st>>>(P, ctx->num_kmers.as<int64_t>(), ctx->nodes.as<Node>(), ctx->W.as<uint32_t>());
+    launches += 2;
+    uint64_t sums[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(&sums[0], ctx->loff.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&sums[1], ctx->noff.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&sums[2], ctx->coff.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->sum_l = sums[0]; ctx->sum_n = sums[1];
+    CK(ctx->loc.ensure((ctx->sum_l + 32) * 4));
+    k_decode_locals<<<blocks_for(P, 128), 128, 0, st>>>(P, ctx->nodes.as<Node>(), ctx->bits.as<uint32_t>(), ctx->poff.as<uint64_t>(),
+                                                         ctx->payload.as<uint64_t>(), ctx->loc.as<uint32_t>(), ctx->N,
+                                                         ctx->err_flag.as<int>());
+    launches += 1;
+    CK(cudaGetLastError());
+    // chunk boundaries
+    const uint64_t total_cost = sums[2];
+    const uint32_t nchunks = (uint32_t)std::max<uint64_t>(1, (total_cost + pl.chunk - 1) / pl.chunk);
+    CK(ctx->bounds.ensure(((size_t)nchunks + 1) * 8));
+    k_chunk_bounds<<<blocks_for(nchunks + 1, 128), 128, 0, st>>>(P, ctx->coff.as<uint64_t>(), pl.chunk, nchunks, ctx->bounds.as<uint64_t>());
+    launches += 1;
+    CK(cudaGetLastError());
+    return (int)nchunks;
+}
+
+int check_device_error(kdbx_ctx* ctx) {
+    int flag = 0;
+    CK(cudaMemcpy(&flag, ctx->err_flag.p, sizeof flag, cudaMemcpyDeviceToHost));
+    if (flag == 1) return ctx->fail(KDBX_ERR_ARG, "malformed trie: Elias-gamma stream does not match num_bits");
+    if (flag == 2) return ctx->fail(KDBX_ERR_ARG, "malformed trie: sample id out of range");
+    return KDBX_OK;
+}
+
+float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uint32_t* d_out, kdbx_stats* stats) {
+    if (!ctx->loaded) return ctx->fail(KDBX_ERR_STATE, "no patterns loaded (call kdbx_load_patterns first)");
+    if (row_begin > row_end || row_end > ctx->N) return ctx->fail(KDBX_ERR_ARG, "bad row range [%u,%u) for %u samples", row_begin, row_end, ctx->N);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    Plan pl;
+    if (int rc = make_plan(ctx, pl)) return rc;
+    kdbx_stats s{};
+    s.ms_upload = ctx->ms_upload;
+    ctx->ev_used = 0;
+    uint32_t launches = 0;
+    auto tri_off = [](uint64_t r) { return r == 0 ? 0ull : r * (r - 1) / 2; };
+    const uint64_t tri_base = tri_off(row_begin);
+    const uint64_t cells = tri_off(row_end) - tri_base;
+
+    cudaEvent_t ev_start = ctx->event();
+    if (cells) CK(cudaMemsetAsync(d_out, 0, cells * 4, st));
+    const int nchunks_or_err = prepare(ctx, pl, launches);
+    if (nchunks_or_err < 0) return nchunks_or_err;
+    const uint32_t nchunks = (uint32_t)nchunks_or_err;
+    std::vector<uint64_t> bounds(nchunks + 1);
+    CK(cudaMemcpyAsync(bounds.data(), ctx->bounds.p, (nchunks + 1) * 8, cudaMemcpyDeviceToHost, st));
+    cudaEvent_t ev_prepared = ctx->event();
+    CK(cudaStreamSynchronize(st));
+    s.ms_prepare = elapsed(ev_start, ev_prepared);
+
+    const uint32_t nkeys = ctx->N * pl.T;
+    const uint64_t cap = pl.chunk + (uint64_t)ctx->N * (pl.T + 1) + 64;  // a chunk may overshoot by one pattern
+    CK(ctx->flat.ensure(cap * 4)); CK(ctx->jobs.ensure(cap * sizeof(Job)));
+    CK(ctx->hist.ensure(((size_t)nkeys + 1) * 4)); CK(ctx->work.ensure(((size_t)nkeys + 1) * 8));
+    CK(ctx->bucket_off.ensure(((size_t)nkeys + 1) * 4)); CK(ctx->cursor.ensure(((size_t)nkeys + 1) * 4));
+    CK(ctx->ucount.ensure(((size_t)nkeys + 1) * 4)); CK(ctx->uoff.ensure(((size_t)nkeys + 1) * 4));
+    CK(ctx->units.ensure(cap * sizeof(Unit)));
+    CK(ctx->counters.ensure(64));
+    unsigned long long* d_total_updates = ctx->counters.as<unsigned long long>();
+    uint32_t* d_unit_counter = ctx->counters.as<uint32_t>() + 4;
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+
+    const size_t smem = (size_t)pl.tile_cols * 4 * kWarpsPerBlock;
+    CK(cudaFuncSetAttribute(k_scatter_add, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks_per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_scatter_add, kScatterThreads, smem));
+    if (blocks_per_sm < 1) return ctx->fail(KDBX_ERR_CUDA, "scatter kernel does not fit on an SM");
+    const unsigned scatter_grid = (unsigned)(ctx->sm_count * blocks_per_sm);
+    const unsigned wide_grid = (unsigned)(ctx->sm_count * 8);
+
+    struct ChunkEv { cudaEvent_t a, b, c, d; };
+    std::vector<ChunkEv> cev;
+    cev.reserve(nchunks);
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const uint64_t p0 = bounds[c], p1 = bounds[c + 1];
+        if (p1 <= p0) continue;
+        ChunkEv e;
+        e.a = ctx->event();
+        k_expand<<<wide_grid, 256, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->loc.as<uint32_t>(), ctx->flat.as<uint32_t>());
+        e.b = ctx->event();
+        CK(cudaMemsetAsync(ctx->hist.p, 0, ((size_t)nkeys + 1) * 4, st));
+        CK(cudaMemsetAsync(ctx->work.p, 0, ((size_t)nkeys + 1) * 8, st));
+        k_job_hist<<<wide_grid, 256, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
+                                               ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, row_begin, row_end,
+                                               ctx->hist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates);
+        if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
+        CK(cudaMemcpyAsync(ctx->cursor.p, ctx->bucket_off.p, ((size_t)nkeys + 1) * 4, cudaMemcpyDeviceToDevice, st));
+        k_job_fill<<<wide_grid, 256, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
+                                               ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, row_begin, row_end,
+                                               ctx->cursor.as<uint32_t>(), ctx->jobs.as<Job>());
+        k_unit_count<<<blocks_for((uint64_t)nkeys + 1, 256), 256, 0, st>>>(nkeys, ctx->hist.as<uint32_t>(), ctx->work.as<unsigned long long>(),
+                                                                            pl.unit_updates, ctx->ucount.as<uint32_t>());
+        if (int rc = scan_exclusive_u32(ctx, ctx->ucount.as<uint32_t>(), ctx->uoff.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
+        k_unit_fill<<<blocks_for(nkeys, 256), 256, 0, st>>>(nkeys, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(),
+                                                             ctx->ucount.as<uint32_t>(), ctx->uoff.as<uint32_t>(), ctx->units.as<Unit>());
+        CK(cudaMemsetAsync(d_unit_counter, 0, 4, st));
+        e.c = ctx->event();
+        k_scatter_add<<<scatter_grid, kScatterThreads, smem, st>>>(ctx->units.as<Unit>(), ctx->uoff.as<uint32_t>() + nkeys, ctx->jobs.as<Job>(),
+                                                                   ctx->flat.as<uint32_t>(), d_out, tri_base, pl.T, pl.tile_cols, d_unit_counter);
+        e.d = ctx->event();
+        launches += 8;
+        s.scatter_launches += 1;
+        cev.push_back(e);
+    }
+    cudaEvent_t ev_end = ctx->event();
+    CK(cudaGetLastError());
+    unsigned long long total_updates = 0;
+    CK(cudaMemcpyAsync(&total_updates, d_total_updates, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (int rc = check_device_error(ctx)) return rc;
+    for (const ChunkEv& e : cev) {
+        s.ms_expand += elapsed(e.a, e.b);
+        s.ms_bucket += elapsed(e.b, e.c);
+        s.ms_scatter += elapsed(e.c, e.d);
+    }
+    s.ms_total = elapsed(ev_start, ev_end);
+    s.updates = total_updates;
+    s.flat_ids = ctx->sum_n; s.local_ids = ctx->sum_l;
+    s.chunks = nchunks; s.kernel_launches = launches;
+    if (stats) *stats = s;
+    return KDBX_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int kdbx_abi_version(void) { return KDBX_ABI_VERSION; }
+
+int kdbx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return -1; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        cudaDeviceProp pr;
+        if (cudaGetDeviceProperties(&pr, d) == cudaSuccess && pr.major == 10) ++ok;
+    }
+    return ok;
+}
+
+const char* kdbx_last_error(const kdbx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_open_error.c_str(); }
+
+int kdbx_open(const kdbx_config* cfg, kdbx_ctx** out) {
+    if (!out) { g_open_error = "kdbx_open: out is NULL"; return KDBX_ERR_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        g_open_error = std::string("kdbx_open: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback";
+        return KDBX_ERR_CUDA;
+    }
+    int dev = cfg ? cfg->device : -1;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    if (dev >= ndev) { g_open_error = "kdbx_open: device ordinal out of range"; return KDBX_ERR_ARG; }
+    cudaDeviceProp pr;
+    if ((e = cudaGetDeviceProperties(&pr, dev)) != cudaSuccess) { g_open_error = cudaGetErrorString(e); return KDBX_ERR_CUDA; }
+    if (pr.major != 10) {
+        g_open_error = "kdbx_open: device is sm_" + std::to_string(pr.major) + std::to_string(pr.minor) +
+                       "; this library carries sm_100a code only";
+        return KDBX_ERR_CUDA;
+    }
+    kdbx_ctx* ctx = new kdbx_ctx();
+    ctx->device = dev;
+    ctx->sm_count = pr.multiProcessorCount;
+    if (cfg) ctx->cfg = *cfg;
+    if ((e = cudaSetDevice(dev)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_open_error = std::string("kdbx_open: ") + cudaGetErrorString(e);
+        delete ctx;
+        return KDBX_ERR_CUDA;
+    }
+    *out = ctx;
+    return KDBX_OK;
+}
+
+void kdbx_close(kdbx_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (DevBuf* b : {&ctx->num_kmers, &ctx->parent, &ctx->n, &ctx->l, &ctx->last, &ctx->bits, &ctx->poff, &ctx->payload,
+                      &ctx->nodes, &ctx->W, &ctx->loc, &ctx->loff, &ctx->noff, &ctx->coff, &ctx->bounds, &ctx->err_flag,
+                      &ctx->cub_tmp, &ctx->flat, &ctx->jobs, &ctx->hist, &ctx->work, &ctx->bucket_off, &ctx->cursor,
+                      &ctx->ucount, &ctx->uoff, &ctx->units, &ctx->counters, &ctx->tri, &ctx->rowupd})
+        b->release();
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int kdbx_host_alloc(void** out, size_t bytes) {
+    if (!out) return KDBX_ERR_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return KDBX_ERR_NOMEM; }
+    return KDBX_OK;
+}
+void kdbx_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int kdbx_load_patterns(kdbx_ctx* ctx, const kdbx_trie_view* v) {
+    if (!ctx) return KDBX_ERR_ARG;
+    if (!v) return ctx->fail(KDBX_ERR_ARG, "kdbx_load_patterns: view is NULL");
+    const uint64_t P = v->num_patterns;
+    if (P == 0 || P >= ((uint64_t)1 << 31)) return ctx->fail(KDBX_ERR_ARG, "kdbx_load_patterns: num_patterns must be in [1, 2^31)");
+    if (!v->num_kmers || !v->parent_id || !v->num_samples_full || !v->num_local_samples || !v->last_sample_id || !v->num_bits)
+        return ctx->fail(KDBX_ERR_ARG, "kdbx_load_patterns: NULL array in view");
+    if (v->payload_words && !v->payload) return ctx->fail(KDBX_ERR_ARG, "kdbx_load_patterns: payload is NULL");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->loaded = false;
+    CK(ctx->num_kmers.ensure(P * 8)); CK(ctx->parent.ensure(P * 8)); CK(ctx->n.ensure(P * 4)); CK(ctx->l.ensure(P * 4));
+    CK(ctx->last.ensure(P * 4)); CK(ctx->bits.ensure(P * 4)); CK(ctx->payload.ensure((v->payload_words + 2) * 8));
+    ctx->ev_used = 0;
+    cudaEvent_t a = ctx->event();
+    CK(cudaMemcpyAsync(ctx->num_kmers.p, v->num_kmers, P * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->parent.p, v->parent_id, P * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->n.p, v->num_samples_full, P * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->l.p, v->num_local_samples, P * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->last.p, v->last_sample_id, P * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->bits.p, v->num_bits, P * 4, cudaMemcpyHostToDevice, st));
+    if (v->payload_words) CK(cudaMemcpyAsync(ctx->payload.p, v->payload, v->payload_words * 8, cudaMemcpyHostToDevice, st));
+    // two zero guard words: the decoder may touch word i+1 of a run that ends at a word edge
+    CK(cudaMemsetAsync(ctx->payload.as<uint64_t>() + v->payload_words, 0, 16, st));
+    ctx->dense_payload = (v->payload_off == nullptr);
+    if (!ctx->dense_payload) {
+        CK(ctx->poff.ensure((P + 1) * 8));
+        CK(cudaMemcpyAsync(ctx->poff.p, v->payload_off, P * 8, cudaMemcpyHostToDevice, st));
+    }
+    cudaEvent_t b = ctx->event();
+    CK(cudaStreamSynchronize(st));
+    ctx->ms_upload = elapsed(a, b);
+    ctx->P = P; ctx->N = v->num_samples; ctx->payload_words = v->payload_words;
+    ctx->loaded = true;
+    return KDBX_OK;
+}
+
+int kdbx_all2all_dense_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_out_rows, kdbx_stats* stats) {
+    if (!ctx) return KDBX_ERR_ARG;
+    if (!d_out_rows && row_end > row_begin && row_end > 1) return ctx->fail(KDBX_ERR_ARG, "output pointer is NULL");
+    return all2all_rows_device(ctx, row_begin, row_end, static_cast<uint32_t*>(d_out_rows), stats);
+}
+
+int kdbx_all2all_dense_rows(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uint32_t* out_rows, kdbx_stats* stats) {
+    if (!ctx) return KDBX_ERR_ARG;
+    if (!ctx->loaded) return ctx->fail(KDBX_ERR_STATE, "no patterns loaded (call kdbx_load_patterns first)");
+    if (row_begin > row_end || row_end > ctx->N) return ctx->fail(KDBX_ERR_ARG, "bad row range [%u,%u) for %u samples", row_begin, row_end, ctx->N);
+    auto tri_off = [](uint64_t r) { return r == 0 ? 0ull : r * (r - 1) / 2; };
+    const uint64_t cells = tri_off(row_end) - tri_off(row_begin);
+    if (cells && !out_rows) return ctx->fail(KDBX_ERR_ARG, "output pointer is NULL");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->tri.ensure((cells + 1) * 4));
+    kdbx_stats s{};
+    if (int rc = all2all_rows_device(ctx, row_begin, row_end, ctx->tri.as<uint32_t>(), &s)) return rc;
+    cudaEvent_t a = ctx->event();
+    if (cells) CK(cudaMemcpyAsync(out_rows, ctx->tri.p, cells * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEvent_t b = ctx->event();
+    CK(cudaStreamSynchronize(ctx->stream));
+    s.ms_download = elapsed(a, b);
+    if (stats) *stats = s;
+    return KDBX_OK;
+}
+
+int kdbx_all2all_dense(kdbx_ctx* ctx, uint32_t* out_tri, kdbx_stats* stats) {
+    if (!ctx) return KDBX_ERR_ARG;
+    return kdbx_all2all_dense_rows(ctx, 0, ctx->N, out_tri, stats);
+}
+
+int kdbx_row_updates(kdbx_ctx* ctx, uint64_t* out) {
+    if (!ctx) return KDBX_ERR_ARG;
+    if (!ctx->loaded) return ctx->fail(KDBX_ERR_STATE, "no patterns loaded (call kdbx_load_patterns first)");
+    if (!out) return ctx->fail(KDBX_ERR_ARG, "output pointer is NULL");
+    CK(cudaSetDevice(ctx->device));
+    Plan pl;
+    if (int rc = make_plan(ctx, pl)) return rc;
+    uint32_t launches = 0;
+    const int rc = prepare(ctx, pl, launches);
+    if (rc < 0) return rc;
+    CK(ctx->rowupd.ensure(((size_t)ctx->N + 1) * 8));
+    CK(cudaMemsetAsync(ctx->rowupd.p, 0, ((size_t)ctx->N + 1) * 8, ctx->stream));
+    k_row_updates<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->P, ctx->nodes.as<Node>(), ctx->loc.as<uint32_t>(),
+                                                              ctx->rowupd.as<unsigned long long>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->rowupd.p, (size_t)ctx->N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return check_device_error(ctx);
+}
+
+int64_t kdbx_debug_fetch(kdbx_ctx* ctx, int what, void* out, uint64_t max_elems) {
+    if (!ctx || !out) return KDBX_ERR_ARG;
+    if (!ctx->loaded || !ctx->nodes.p) return ctx->fail(KDBX_ERR_STATE, "nothing prepared yet");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return KDBX_ERR_CUDA;
+    cudaStreamSynchronize(ctx->stream);
+    const void* src = nullptr; uint64_t n = 0; size_t es = 4;
+    switch (what) {
+        case 0: src = ctx->W.p; n = ctx->P; es = 4; break;
+        case 1: src = ctx->loc.p; n = ctx->sum_l; es = 4; break;
+        case 2: src = ctx->loff.p; n = ctx->P + 1; es = 8; break;
+        default: return ctx->fail(KDBX_ERR_ARG, "unknown debug tap %d", what);
+    }
+    n = std::min(n, max_elems);
+    if (n && cudaMemcpy(out, src, n * es, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return ctx->fail(KDBX_ERR_CUDA, "debug fetch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return (int64_t)n;
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+// .db wire format reader / writer (little-endian, no magic).  Layout follows SURVEY.md §A.1,
+// i.e. what PrefixKmerDb::serialize emits (src/prefix_kmer_db.cpp:438-574) and
+// PrefixKmerDb::deserialize(SkipHashtables) consumes (src/prefix_kmer_db.cpp:578-748), with
+// packed patterns as in pattern_t::pack (src/pattern.cpp:15-47) and raw hashtables as in
+// hash_map_lp::serialize (src/hashmap_lp.h:481-528).  all2all never needs the hashtables
+// (src/console_all2all.cpp:26), so the reader seeks over them and the writer emits empty ones.
+#include <cstdio>
+#include <cstring>
+#include <memory>
+
+#include "trie.h"
+
+namespace kdbx {
+namespace {
+
+struct File {
+    FILE* f = nullptr;
+    std::string path;
+    File(const std::string& p, const char* mode) : f(std::fopen(p.c_str(), mode)), path(p) {
+        if (!f) throw std::runtime_error("Cannot open k-mer database " + p);
+    }
+    ~File() { if (f) std::fclose(f); }
+    void read(void* dst, size_t bytes) {
+        if (bytes && std::fread(dst, 1, bytes, f) != bytes)
+            throw std::runtime_error("Cannot open k-mer database " + path + " (truncated)");
+    }
+    template <class T> T get() { T v; read(&v, sizeof(T)); return v; }
+    void skip(uint64_t bytes) {
+        if (fseeko(f, (off_t)bytes, SEEK_CUR) != 0)
+            throw std::runtime_error("Cannot open k-mer database " + path + " (seek)");
+    }
+    void write(const void* src, size_t bytes) {
+        if (bytes && std::fwrite(src, 1, bytes, f) != bytes)
+            throw std::runtime_error("Cannot write k-mer database " + path);
+    }
+    template <class T> void put(const T& v) { write(&v, sizeof(T)); }
+};
+
+constexpr size_t kPatternHeaderBytes = 40;          // src/pattern.cpp:15-37
+constexpr size_t kIoBlockBytes = (size_t)64 << 20;  // reader's buffer (src/prefix_kmer_db.h:179)
+constexpr size_t kRefPatternStructBytes = 48;       // sizeof(pattern_t), used by the block cut
+
+}  // namespace
+
+void read_db(const std::string& path, Trie& t) {
+    File in(path, "rb");
+    DbHeader& h = t.hdr;
+    h.format_word = in.get<uint64_t>();
+    h.kmer_length = in.get<uint32_t>();
+    h.fraction = in.get<double>();
+    h.start_fraction = in.get<double>();
+    h.alphabet_type = in.get<int32_t>();
+    h.is_initialized = in.get<uint8_t>();
+    h.kmers_count = in.get<uint64_t>();
+
+    const uint64_t n_samples = in.get<uint64_t>();
+    t.sample_names.resize(n_samples);
+    t.sample_kmers.resize(n_samples);
+    for (uint64_t i = 0; i < n_samples; ++i) {
+        t.sample_kmers[i] = in.get<uint64_t>();
+        const uint64_t len = in.get<uint64_t>();
+        t.sample_names[i].resize(len);
+        in.read(t.sample_names[i].data(), len);
+    }
+
+    h.num_hashtables = in.get<uint64_t>();
+    const bool raw = (h.format_word & 1) != 0;
+    for (uint64_t i = 0; i < h.num_hashtables; ++i) {
+        if (raw) {
+            in.skip(sizeof(double));  // max_fill_factor
+            const uint64_t filled = in.get<uint64_t>();
+            const uint64_t allocated = in.get<uint64_t>();
+            in.skip(5 * sizeof(uint64_t));  // size_when_restruct, mask, ht_memory, ht_total, ht_match
+            in.skip(((allocated + 63) / 64) * sizeof(uint64_t) + filled * 8);
+        } else {  // portioned form (src/prefix_kmer_db.cpp:657-697)
+            const uint64_t total = in.get<uint64_t>();
+            uint64_t seen = 0;
+            while (seen < total) {
+                const uint64_t portion = in.get<uint64_t>();
+                // NB: the reference seeks `portion` BYTES here (src/prefix_kmer_db.cpp:676)
+                // although the portion holds 8-byte items; a correct reader skips the items.
+                in.skip(portion * 8);
+                seen += portion;
+            }
+        }
+    }
+
+    const uint64_t P = in.get<uint64_t>();
+    t.num_kmers.resize(P); t.parent_id.resize(P); t.n.resize(P); t.l.resize(P);
+    t.last.resize(P); t.bits.resize(P); t.payload_off.resize(P);
+    t.payload.clear();
+
+    std::unique_ptr<char[]> block(new char[kIoBlockBytes]);
+    uint64_t pid = 0;
+    while (pid < P) {
+        const uint64_t block_bytes = in.get<uint64_t>();
+        if (block_bytes > kIoBlockBytes) throw std::runtime_error("Corrupt k-mer database " + path);
+        in.read(block.get(), block_bytes);
+        const char* p = block.get();
+        const char* end = p + block_bytes;
+        while (p < end) {
+            if (pid >= P || p + kPatternHeaderBytes > end)
+                throw std::runtime_error("Corrupt k-mer database " + path);
+            int64_t nk, par; uint32_t ns, nl, ls, nb;
+            std::memcpy(&nk, p, 8); std::memcpy(&par, p + 8, 8);
+            std::memcpy(&ns, p + 16, 4); std::memcpy(&nl, p + 20, 4);
+            std::memcpy(&ls, p + 24, 4); std::memcpy(&nb, p + 28, 4);
+            p += kPatternHeaderBytes;  // bytes 32..39: is_parent (4 valid + 4 undefined bytes)
+            const uint64_t words = Trie::payload_words_for_bits(nb);
+            if (p + words * 8 > end) throw std::runtime_error("Corrupt k-mer database " + path);
+            t.num_kmers[pid] = nk; t.parent_id[pid] = par; t.n[pid] = ns; t.l[pid] = nl;
+            t.last[pid] = ls; t.bits[pid] = nb;
+            t.payload_off[pid] = t.payload.size();
+            if (words) {
+                const size_t at = t.payload.size();
+                t.payload.resize(at + words);
+                std::memcpy(t.payload.data() + at, p, words * 8);
+                p += words * 8;
+            }
+            ++pid;
+        }
+    }
+}
+
+void write_db(const std::string& path, const Trie& t) {
+    File out(path, "wb");
+    const DbHeader& h = t.hdr;
+    out.put<uint64_t>(1);  // raw hashtables
+    out.put(h.kmer_length); out.put(h.fraction); out.put(h.start_fraction);
+    out.put(h.alphabet_type); out.put(h.is_initialized); out.put(h.kmers_count);
+    out.put<uint64_t>(t.sample_names.size());
+    for (size_t i = 0; i < t.sample_names.size(); ++i) {
+        out.put<uint64_t>(t.sample_kmers[i]);
+        out.put<uint64_t>(t.sample_names[i].size());
+        out.write(t.sample_names[i].data(), t.sample_names[i].size());
+    }
+    // empty raw hashtables: capacity 16, nothing filled (SURVEY.md §8d cfg3 note)
+    out.put<uint64_t>(h.num_hashtables);
+    for (uint64_t i = 0; i < h.num_hashtables; ++i) {
+        out.put<double>(0.8);
+        out.put<uint64_t>(0);    // filled
+        out.put<uint64_t>(16);   // allocated
+        out.put<uint64_t>(12);   // size_when_restruct = allocated * max_fill
+        out.put<uint64_t>(15);   // allocated_mask
+        out.put<uint64_t>(0); out.put<uint64_t>(0); out.put<uint64_t>(0);
+        out.put<uint64_t>(0);    // one bit-vector word, no slot used
+    }
+    const uint64_t P = t.num_patterns();
+    out.put<uint64_t>(P);
+    std::vector<uint8_t> has_child(P, 0);  // pattern_t::is_parent (consulted by build -extend)
+    for (uint64_t p = 0; p < P; ++p)
+        if (t.parent_id[p] >= 0) has_child[(uint64_t)t.parent_id[p]] = 1;
+    std::unique_ptr<char[]> block(new char[kIoBlockBytes]);
+    char* cur = block.get();
+    auto flush = [&]() {
+        const uint64_t bytes = (uint64_t)(cur - block.get());
+        out.put<uint64_t>(bytes);
+        out.write(block.get(), bytes);
+        cur = block.get();
+    };
+    for (uint64_t p = 0; p < P; ++p) {
+        const uint64_t words = Trie::payload_words_for_bits(t.bits[p]);
+        if (cur + kRefPatternStructBytes + words * 8 > block.get() + kIoBlockBytes) flush();
+        std::memcpy(cur, &t.num_kmers[p], 8); std::memcpy(cur + 8, &t.parent_id[p], 8);
+        std::memcpy(cur + 16, &t.n[p], 4); std::memcpy(cur + 20, &t.l[p], 4);
+        std::memcpy(cur + 24, &t.last[p], 4); std::memcpy(cur + 28, &t.bits[p], 4);
+        const uint64_t is_parent = has_child[p];
+        std::memcpy(cur + 32, &is_parent, 8);
+        cur += kPatternHeaderBytes;
+        if (words) { std::memcpy(cur, t.payload.data() + t.payload_off[p], words * 8); cur += words * 8; }
+    }
+    flush();
+}
+
+}  // namespace kdbx

@@ -1,0 +1,161 @@
+// extern "C" surface of libkdbx_host.so (include/kdbx_host.h): thin wrappers that translate
+// exceptions into error codes.
+#include <cstring>
+#include <string>
+
+#include "../../include/kdbx_host.h"
+#include "gamma.h"
+#include "synth.h"
+#include "trie.h"
+
+struct kdbxh_trie { kdbx::Trie t; explicit kdbxh_trie(bool pinned) : t(pinned) {} };
+
+namespace {
+thread_local std::string g_err;
+template <class F> int guarded(F&& f) {
+    try { f(); return 0; }
+    catch (const std::exception& e) { g_err = e.what(); return -1; }
+    catch (...) { g_err = "unknown error"; return -1; }
+}
+}  // namespace
+
+namespace kdbx {
+// Structural validity of a trie (see kdbx_host.h).  Throws with the first violation.
+void validate_trie(const Trie& t) {
+    const uint64_t P = t.num_patterns();
+    const uint32_t N = t.num_samples();
+    if (P == 0) throw std::runtime_error("trie has no sentinel pattern");
+    std::vector<uint32_t> ids;
+    for (uint64_t p = 0; p < P; ++p) {
+        const int64_t par = t.parent_id[p];
+        const uint32_t n = t.n[p], l = t.l[p];
+        auto bad = [&](const char* what) {
+            throw std::runtime_error("invalid trie at pattern " + std::to_string(p) + ": " + what);
+        };
+        if (par >= (int64_t)p || par < -1) bad("parent_id must be -1 or < own id");
+        if (l > n) bad("num_local_samples > num_samples");
+        if (n > N) bad("num_samples > sample count");
+        const uint32_t n_par = par >= 0 ? t.n[par] : 0;
+        if (n != n_par + l) bad("num_samples != parent's num_samples + num_local_samples");
+        if (l == 0) { if (t.bits[p]) bad("payload without local samples"); continue; }
+        const uint64_t words = Trie::payload_words_for_bits(t.bits[p]);
+        if (t.payload_off[p] + words > t.payload.size()) bad("payload out of bounds");
+        if (t.last[p] >= N) bad("last_sample_id >= sample count");
+        ids.resize(l);
+        // decode with explicit bounds so that a corrupt stream cannot run away
+        uint32_t pos = 0; uint64_t sum = 0;
+        for (uint32_t i = 0; i + 1 < l; ++i) {
+            if (pos >= t.bits[p]) bad("Elias-gamma stream shorter than num_local_samples-1 codes");
+            const uint32_t d = gamma_get(t.payload.data() + t.payload_off[p], pos);
+            sum += d;
+        }
+        if (pos != t.bits[p]) bad("Elias-gamma stream length != num_bits");
+        if (sum > t.last[p]) bad("deltas exceed last_sample_id");
+        const uint32_t first = t.last[p] - (uint32_t)sum;
+        if (par >= 0 && first <= t.last[par]) bad("local list does not continue parent's list");
+    }
+}
+
+// Sub-database of the first k samples (see kdbx_host.h for the precondition).
+void prefix_trie(const Trie& src, uint32_t k, Trie& dst) {
+    if (k > src.num_samples()) throw std::runtime_error("prefix: more samples requested than the database has");
+    const uint64_t P = src.num_patterns();
+    uint64_t keep = 1;
+    bool tail = false;
+    for (uint64_t p = 1; p < P; ++p) {
+        // first id of the full list = first local id of the root of p's chain; last id = last[p]
+        const bool low = src.last[p] < k;
+        if (low) {
+            if (tail) throw std::runtime_error("prefix: patterns of the first samples do not form a prefix");
+            keep = p + 1;
+        } else {
+            tail = true;
+            int64_t q = (int64_t)p;
+            while (src.parent_id[q] >= 0) q = src.parent_id[q];
+            uint32_t pos = 0, sum = 0;
+            for (uint32_t i = 0; i + 1 < src.l[q]; ++i) sum += gamma_get(src.payload.data() + src.payload_off[q], pos);
+            if (src.last[q] - sum < k) throw std::runtime_error("prefix: a pattern spans the cut");
+        }
+    }
+    dst.hdr = src.hdr;
+    dst.sample_names.assign(src.sample_names.begin(), src.sample_names.begin() + k);
+    dst.sample_kmers.assign(src.sample_kmers.begin(), src.sample_kmers.begin() + k);
+    dst.num_kmers.resize(keep); dst.parent_id.resize(keep); dst.n.resize(keep); dst.l.resize(keep);
+    dst.last.resize(keep); dst.bits.resize(keep); dst.payload_off.resize(keep);
+    uint64_t words = 0;
+    for (uint64_t p = 0; p < keep; ++p) {
+        dst.num_kmers[p] = src.num_kmers[p]; dst.parent_id[p] = src.parent_id[p]; dst.n[p] = src.n[p];
+        dst.l[p] = src.l[p]; dst.last[p] = src.last[p]; dst.bits[p] = src.bits[p];
+        dst.payload_off[p] = words;
+        words += Trie::payload_words_for_bits(src.bits[p]);
+    }
+    dst.payload.resize(words, 0);
+    for (uint64_t p = 0; p < keep; ++p) {
+        const uint64_t w = Trie::payload_words_for_bits(src.bits[p]);
+        if (w) std::memcpy(dst.payload.data() + dst.payload_off[p], src.payload.data() + src.payload_off[p], w * 8);
+    }
+}
+}  // namespace kdbx
+
+extern "C" {
+
+const char* kdbxh_last_error(void) { return g_err.c_str(); }
+
+kdbxh_trie* kdbxh_trie_new(int pinned) {
+    try { return new kdbxh_trie(pinned != 0); } catch (...) { g_err = "allocation failed"; return nullptr; }
+}
+void kdbxh_trie_free(kdbxh_trie* t) { delete t; }
+
+int kdbxh_read_db(kdbxh_trie* t, const char* path) {
+    if (!t || !path) { g_err = "null argument"; return -1; }
+    return guarded([&] { kdbx::read_db(path, t->t); });
+}
+int kdbxh_write_db(const kdbxh_trie* t, const char* path) {
+    if (!t || !path) { g_err = "null argument"; return -1; }
+    return guarded([&] { kdbx::write_db(path, t->t); });
+}
+int kdbxh_synth(kdbxh_trie* t, const kdbxh_synth_params* p) {
+    if (!t || !p) { g_err = "null argument"; return -1; }
+    return guarded([&] {
+        kdbx::SynthParams sp;
+        sp.num_samples = p->num_samples; sp.num_clusters = p->num_clusters;
+        sp.genome_kmers = p->genome_kmers; sp.k = p->k; sp.mutation_rate = p->mutation_rate;
+        sp.seed = p->seed; sp.interleaved = p->interleaved; sp.threads = p->threads;
+        kdbx::synth_generate(sp, t->t);
+    });
+}
+int kdbxh_validate(const kdbxh_trie* t) {
+    if (!t) { g_err = "null argument"; return -1; }
+    return guarded([&] { kdbx::validate_trie(t->t); });
+}
+int kdbxh_prefix(const kdbxh_trie* src, uint32_t num_samples, kdbxh_trie* dst) {
+    if (!src || !dst || src == dst) { g_err = "bad argument"; return -1; }
+    return guarded([&] { kdbx::prefix_trie(src->t, num_samples, dst->t); });
+}
+int kdbxh_view(const kdbxh_trie* t, kdbx_trie_view* out) {
+    if (!t || !out) { g_err = "null argument"; return -1; }
+    *out = t->t.view();
+    return 0;
+}
+int kdbxh_totals_of(const kdbxh_trie* t, kdbxh_totals* out) {
+    if (!t || !out) { g_err = "null argument"; return -1; }
+    const auto tt = t->t.totals();
+    std::memset(out, 0, sizeof *out);
+    out->num_patterns = t->t.num_patterns(); out->num_samples = t->t.num_samples();
+    out->updates = tt.U; out->sum_n = tt.sum_n; out->sum_l = tt.sum_l;
+    out->payload_bytes = tt.payload_bytes; out->kmers_count = t->t.hdr.kmers_count;
+    out->kmer_length = t->t.hdr.kmer_length; out->fraction = t->t.hdr.fraction;
+    return 0;
+}
+const char* kdbxh_sample_name(const kdbxh_trie* t, uint32_t i) {
+    return (t && i < t->t.num_samples()) ? t->t.sample_names[i].c_str() : nullptr;
+}
+uint64_t kdbxh_sample_kmers(const kdbxh_trie* t, uint32_t i) {
+    return (t && i < t->t.num_samples()) ? t->t.sample_kmers[i] : 0;
+}
+int kdbxh_write_all2all_csv(const kdbxh_trie* t, const uint32_t* tri, const char* path, int sparse) {
+    if (!t || !path || (!tri && t->t.num_samples() > 1)) { g_err = "null argument"; return -1; }
+    return guarded([&] { kdbx::write_all2all_csv(path, t->t, tri, sparse != 0); });
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+// Host-side model of a kmer-db database as the all2all path needs it: database header,
+// sample table and the pattern trie in structure-of-arrays form (the layout kdbx_trie_view
+// borrows).  Mirrors the *fields* of the reference's pattern_t (src/pattern.h:42-55) and
+// AbstractKmerDb (src/kmer_db.h:27-45); storage is ours: one contiguous payload blob instead
+// of one heap block per pattern (src/pattern.cpp:84-90).
+#pragma once
+#include <cstdint>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/kdbx.h"
+
+namespace kdbx {
+
+// Minimal growable array that can live in page-locked memory (kdbx_host_alloc) so that the
+// trie goes to HBM at link rate.  Falls back to malloc only when pinning is not requested.
+template <class T>
+class Buf {
+public:
+    Buf() = default;
+    Buf(const Buf&) = delete;
+    Buf& operator=(const Buf&) = delete;
+    Buf(Buf&& o) noexcept { swap(o); }
+    Buf& operator=(Buf&& o) noexcept { if (this != &o) { release(); swap(o); } return *this; }
+    ~Buf() { release(); }
+
+    void set_pinned(bool p) { if (!ptr_) pinned_ = p; }
+    size_t size() const { return size_; }
+    T* data() { return ptr_; }
+    const T* data() const { return ptr_; }
+    T& operator[](size_t i) { return ptr_[i]; }
+    const T& operator[](size_t i) const { return ptr_[i]; }
+    T& back() { return ptr_[size_ - 1]; }
+
+    void reserve(size_t n) {
+        if (n <= cap_) return;
+        size_t ncap = cap_ ? cap_ : 1024;
+        while (ncap < n) ncap += ncap / 2 + 1;
+        T* np = nullptr;
+        if (pinned_) {
+            void* v = nullptr;
+            if (kdbx_host_alloc(&v, ncap * sizeof(T)) != KDBX_OK) throw std::bad_alloc();
+            np = static_cast<T*>(v);
+        } else {
+            np = static_cast<T*>(std::malloc(ncap * sizeof(T)));
+            if (!np) throw std::bad_alloc();
+        }
+        for (size_t i = 0; i < size_; ++i) np[i] = ptr_[i];
+        free_ptr();
+        ptr_ = np;
+        cap_ = ncap;
+    }
+    void resize(size_t n, T fill = T()) {
+        reserve(n);
+        for (size_t i = size_; i < n; ++i) ptr_[i] = fill;
+        size_ = n;
+    }
+    void push_back(const T& v) {
+        if (size_ == cap_) reserve(size_ + 1);
+        ptr_[size_++] = v;
+    }
+    void clear() { size_ = 0; }
+
+private:
+    void free_ptr() {
+        if (!ptr_) return;
+        if (pinned_) kdbx_host_free(ptr_); else std::free(ptr_);
+        ptr_ = nullptr;
+    }
+    void release() { free_ptr(); size_ = cap_ = 0; }
+    void swap(Buf& o) {
+        std::swap(ptr_, o.ptr_); std::swap(size_, o.size_); std::swap(cap_, o.cap_);
+        std::swap(pinned_, o.pinned_);
+    }
+    T* ptr_ = nullptr;
+    size_t size_ = 0, cap_ = 0;
+    bool pinned_ = false;
+};
+
+// Database header fields in file order (src/prefix_kmer_db.cpp:449-455).
+struct DbHeader {
+    uint64_t format_word = 1;  // bit0: raw hashtables (console_build.cpp:149 always sets it)
+    uint32_t kmer_length = 18;
+    double fraction = 1.0;
+    double start_fraction = 0.0;
+    int32_t alphabet_type = 0;  // enum AlphabetType (src/alphabet.h:10-18), 0 = nt
+    uint8_t is_initialized = 1;
+    uint64_t kmers_count = 0;
+    uint64_t num_hashtables = 256;
+};
+
+struct Trie {
+    DbHeader hdr;
+    std::vector<std::string> sample_names;
+    std::vector<uint64_t> sample_kmers;  // per-sample distinct k-mer count ("total-kmers")
+
+    // SoA over patterns, index = pattern id
+    Buf<int64_t> num_kmers;
+    Buf<int64_t> parent_id;
+    Buf<uint32_t> n;     // num_samples (node + ancestors)
+    Buf<uint32_t> l;     // num_local_samples
+    Buf<uint32_t> last;  // last_sample_id
+    Buf<uint32_t> bits;  // num_bits
+    Buf<uint64_t> payload_off;  // word offset into payload
+    Buf<uint64_t> payload;      // Elias-gamma words, ceil(bits/128)*2 words per pattern
+
+    explicit Trie(bool pinned = false) {
+        num_kmers.set_pinned(pinned); parent_id.set_pinned(pinned); n.set_pinned(pinned);
+        l.set_pinned(pinned); last.set_pinned(pinned); bits.set_pinned(pinned);
+        payload_off.set_pinned(pinned); payload.set_pinned(pinned);
+    }
+
+    uint64_t num_patterns() const { return n.size(); }
+    uint32_t num_samples() const { return (uint32_t)sample_names.size(); }
+
+    static uint64_t payload_words_for_bits(uint32_t nbits) {
+        return nbits == 0 ? 0 : (uint64_t)((nbits + 127) / 128) * 2;  // src/pattern.h:80-82
+    }
+
+    kdbx_trie_view view() const {
+        kdbx_trie_view v{};
+        v.num_patterns = num_patterns();
+        v.num_samples = num_samples();
+        v.num_kmers = num_kmers.data();
+        v.parent_id = parent_id.data();
+        v.num_samples_full = n.data();
+        v.num_local_samples = l.data();
+        v.last_sample_id = last.data();
+        v.num_bits = bits.data();
+        v.payload_off = payload_off.data();
+        v.payload = payload.data();
+        v.payload_words = payload.size();
+        return v;
+    }
+
+    // U = sum_p l(2n - l - 1)/2 and friends; pure host arithmetic.
+    struct Totals { uint64_t U = 0, sum_n = 0, sum_l = 0, payload_bytes = 0; };
+    Totals totals() const {
+        Totals t;
+        for (uint64_t p = 0; p < num_patterns(); ++p) {
+            uint64_t nn = n[p], ll = l[p];
+            t.sum_n += nn; t.sum_l += ll;
+            t.U += ll * (2 * nn - ll - 1) / 2;
+        }
+        t.payload_bytes = payload.size() * 8;
+        return t;
+    }
+};
+
+// db_io.cpp — .db wire format (src/prefix_kmer_db.cpp:438-574,578-748)
+void read_db(const std::string& path, Trie& out);   // hashtables are skipped (all2all needs none)
+void write_db(const std::string& path, const Trie& t);  // writes EMPTY raw hashtables
+
+// csv_out.cpp — byte-exact CSV emitters (src/console_all2all.cpp:40-78)
+void write_all2all_csv(const std::string& path, const Trie& t, const uint32_t* tri, bool sparse);
+
+}  // namespace kdbx

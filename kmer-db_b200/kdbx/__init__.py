@@ -1,0 +1,359 @@
+"""ctypes binding of the two C-ABI libraries of this repository (include/kdbx.h, include/kdbx_host.h).
+
+This is the Python-side mirror that bench.py and the tests use; the product itself is the C++
+host code in kmer-db_b200/host plus the CUDA library.  Nothing here computes anything: every
+function forwards to libkdbx.so (CUDA, sm_100a) or libkdbx_host.so and raises ``KdbxError`` on a
+non-zero return code — exactly as the C++ mirror rethrows ``std::runtime_error``
+(kmer-db_b200/host/similarity_calculator.h; reference behaviour: src/main.cpp:56-59).
+There is no CPU fallback: without the built libraries ``load()`` raises, and without a B200
+``Context()`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent.parent
+LIB_DIR = _PKG / "lib"
+
+
+class KdbxError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("chunk_ids", C.c_uint64),
+                ("tile_cols", C.c_uint32), ("unit_updates", C.c_uint32), ("reserved", C.c_uint64 * 4)]
+
+
+class TrieView(C.Structure):
+    _fields_ = [("num_patterns", C.c_uint64), ("num_samples", C.c_uint32), ("_pad", C.c_uint32),
+                ("num_kmers", C.c_void_p), ("parent_id", C.c_void_p), ("num_samples_full", C.c_void_p),
+                ("num_local_samples", C.c_void_p), ("last_sample_id", C.c_void_p), ("num_bits", C.c_void_p),
+                ("payload_off", C.c_void_p), ("payload", C.c_void_p), ("payload_words", C.c_uint64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("updates", C.c_uint64), ("jobs", C.c_uint64), ("flat_ids", C.c_uint64), ("local_ids", C.c_uint64),
+                ("units", C.c_uint64), ("chunks", C.c_uint32), ("kernel_launches", C.c_uint32),
+                ("ms_upload", C.c_float), ("ms_prepare", C.c_float), ("ms_expand", C.c_float), ("ms_bucket", C.c_float),
+                ("ms_scatter", C.c_float), ("ms_total", C.c_float), ("ms_download", C.c_float),
+                ("scatter_launches", C.c_uint32), ("_pad", C.c_uint32), ("reserved", C.c_uint64 * 4)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k not in ("_pad", "reserved")}
+
+
+class SynthParams(C.Structure):
+    _fields_ = [("num_samples", C.c_uint32), ("num_clusters", C.c_uint32), ("genome_kmers", C.c_uint64),
+                ("k", C.c_uint32), ("interleaved", C.c_int32), ("mutation_rate", C.c_double), ("seed", C.c_uint64),
+                ("threads", C.c_int32), ("_pad", C.c_int32)]
+
+
+class Totals(C.Structure):
+    _fields_ = [("num_patterns", C.c_uint64), ("num_samples", C.c_uint64), ("updates", C.c_uint64),
+                ("sum_n", C.c_uint64), ("sum_l", C.c_uint64), ("payload_bytes", C.c_uint64), ("kmers_count", C.c_uint64),
+                ("kmer_length", C.c_uint32), ("_pad", C.c_uint32), ("fraction", C.c_double)]
+
+
+# every symbol include/kdbx.h declares (tests check that the library exports all of them)
+KDBX_SYMBOLS = ["kdbx_abi_version", "kdbx_device_count", "kdbx_open", "kdbx_close", "kdbx_last_error",
+                "kdbx_host_alloc", "kdbx_host_free", "kdbx_load_patterns", "kdbx_row_updates", "kdbx_all2all_dense",
+                "kdbx_all2all_dense_rows", "kdbx_all2all_dense_rows_device", "kdbx_debug_fetch"]
+KDBXH_SYMBOLS = ["kdbxh_last_error", "kdbxh_trie_new", "kdbxh_trie_free", "kdbxh_read_db", "kdbxh_write_db",
+                 "kdbxh_synth", "kdbxh_validate", "kdbxh_prefix", "kdbxh_view", "kdbxh_totals_of", "kdbxh_sample_name",
+                 "kdbxh_sample_kmers", "kdbxh_write_all2all_csv"]
+
+_libs = None
+
+
+def load():
+    """dlopen libkdbx.so and libkdbx_host.so from kmer-db_b200/lib (built by `make`)."""
+    global _libs
+    if _libs is not None:
+        return _libs
+    so, hso = LIB_DIR / "libkdbx.so", LIB_DIR / "libkdbx_host.so"
+    if not so.exists() or not hso.exists():
+        raise KdbxError(f"{so} / {hso} not built: run `make -C {_PKG}` (or __graft_entry__.build()); "
+                        "there is no fallback implementation")
+    k = C.CDLL(str(so), mode=C.RTLD_GLOBAL)
+    h = C.CDLL(str(hso), mode=C.RTLD_GLOBAL)
+    P = C.POINTER
+    k.kdbx_abi_version.restype = C.c_int
+    k.kdbx_device_count.restype = C.c_int
+    k.kdbx_open.argtypes = [P(Config), P(C.c_void_p)]
+    k.kdbx_close.argtypes = [C.c_void_p]
+    k.kdbx_close.restype = None
+    k.kdbx_last_error.argtypes = [C.c_void_p]
+    k.kdbx_last_error.restype = C.c_char_p
+    k.kdbx_host_alloc.argtypes = [P(C.c_void_p), C.c_size_t]
+    k.kdbx_host_free.argtypes = [C.c_void_p]
+    k.kdbx_host_free.restype = None
+    k.kdbx_load_patterns.argtypes = [C.c_void_p, P(TrieView)]
+    k.kdbx_row_updates.argtypes = [C.c_void_p, C.c_void_p]
+    k.kdbx_all2all_dense.argtypes = [C.c_void_p, C.c_void_p, P(Stats)]
+    k.kdbx_all2all_dense_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, P(Stats)]
+    k.kdbx_all2all_dense_rows_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, P(Stats)]
+    k.kdbx_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
+    k.kdbx_debug_fetch.restype = C.c_int64
+    h.kdbxh_last_error.restype = C.c_char_p
+    h.kdbxh_trie_new.argtypes = [C.c_int]
+    h.kdbxh_trie_new.restype = C.c_void_p
+    h.kdbxh_trie_free.argtypes = [C.c_void_p]
+    h.kdbxh_trie_free.restype = None
+    h.kdbxh_read_db.argtypes = [C.c_void_p, C.c_char_p]
+    h.kdbxh_write_db.argtypes = [C.c_void_p, C.c_char_p]
+    h.kdbxh_synth.argtypes = [C.c_void_p, P(SynthParams)]
+    h.kdbxh_validate.argtypes = [C.c_void_p]
+    h.kdbxh_prefix.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    h.kdbxh_view.argtypes = [C.c_void_p, P(TrieView)]
+    h.kdbxh_totals_of.argtypes = [C.c_void_p, P(Totals)]
+    h.kdbxh_sample_name.argtypes = [C.c_void_p, C.c_uint32]
+    h.kdbxh_sample_name.restype = C.c_char_p
+    h.kdbxh_sample_kmers.argtypes = [C.c_void_p, C.c_uint32]
+    h.kdbxh_sample_kmers.restype = C.c_uint64
+    h.kdbxh_write_all2all_csv.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+    _libs = (k, h)
+    return _libs
+
+
+def tri_cells(n: int) -> int:
+    return n * (n - 1) // 2 if n > 0 else 0
+
+
+def _np_from(ptr, count, dtype):
+    if count == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=count)
+
+
+class Trie:
+    """A kmer-db database as the all2all path needs it (owned by libkdbx_host.so)."""
+
+    def __init__(self, pinned: bool = False):
+        _, h = load()
+        self._h = h
+        self._p = h.kdbxh_trie_new(1 if pinned else 0)
+        if not self._p:
+            raise KdbxError("kdbxh_trie_new failed")
+        self._keep = None
+
+    def close(self):
+        if self._p:
+            self._h.kdbxh_trie_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise KdbxError(self._h.kdbxh_last_error().decode())
+
+    @classmethod
+    def read_db(cls, path, pinned=False):
+        t = cls(pinned)
+        t._check(t._h.kdbxh_read_db(t._p, os.fsencode(str(path))))
+        return t
+
+    @classmethod
+    def synth(cls, num_samples, num_clusters=4, genome_kmers=5_000_000, k=18, mutation_rate=0.005, seed=2,
+              interleaved=False, threads=0, pinned=False):
+        t = cls(pinned)
+        sp = SynthParams(num_samples, num_clusters, genome_kmers, k, 1 if interleaved else 0, mutation_rate, seed, threads, 0)
+        t._check(t._h.kdbxh_synth(t._p, C.byref(sp)))
+        return t
+
+    def prefix(self, num_samples, pinned=False):
+        """Sub-database of the first `num_samples` samples (cluster boundary of a generated db)."""
+        t = Trie(pinned)
+        self._check(self._h.kdbxh_prefix(self._p, num_samples, t._p))
+        return t
+
+    def write_db(self, path):
+        self._check(self._h.kdbxh_write_db(self._p, os.fsencode(str(path))))
+
+    def validate(self):
+        self._check(self._h.kdbxh_validate(self._p))
+
+    def view(self) -> TrieView:
+        v = TrieView()
+        self._check(self._h.kdbxh_view(self._p, C.byref(v)))
+        return v
+
+    def totals(self) -> Totals:
+        t = Totals()
+        self._check(self._h.kdbxh_totals_of(self._p, C.byref(t)))
+        return t
+
+    @property
+    def num_samples(self):
+        return int(self.view().num_samples)
+
+    @property
+    def num_patterns(self):
+        return int(self.view().num_patterns)
+
+    def arrays(self):
+        """Zero-copy numpy views of the SoA arrays (valid while the Trie lives)."""
+        v = self.view()
+        P = int(v.num_patterns)
+        return {
+            "num_kmers": _np_from(v.num_kmers, P, np.int64), "parent_id": _np_from(v.parent_id, P, np.int64),
+            "n": _np_from(v.num_samples_full, P, np.uint32), "l": _np_from(v.num_local_samples, P, np.uint32),
+            "last": _np_from(v.last_sample_id, P, np.uint32), "bits": _np_from(v.num_bits, P, np.uint32),
+            "payload_off": _np_from(v.payload_off, P, np.uint64),
+            "payload": _np_from(v.payload, int(v.payload_words), np.uint64),
+        }
+
+    def sample_names(self):
+        return [self._h.kdbxh_sample_name(self._p, i).decode() for i in range(self.num_samples)]
+
+    def write_all2all_csv(self, tri: np.ndarray, path, sparse=False):
+        tri = np.ascontiguousarray(tri, dtype=np.uint32)
+        if tri.size != tri_cells(self.num_samples):
+            raise KdbxError("matrix size does not match the sample count")
+        self._check(self._h.kdbxh_write_all2all_csv(self._p, tri.ctypes.data, os.fsencode(str(path)), 1 if sparse else 0))
+
+
+def view_from_arrays(num_samples, num_kmers, parent_id, n, l, last, bits, payload_off, payload):
+    """TrieView over caller-owned numpy arrays (kept alive by the returned tuple)."""
+    arrs = [np.ascontiguousarray(num_kmers, np.int64), np.ascontiguousarray(parent_id, np.int64),
+            np.ascontiguousarray(n, np.uint32), np.ascontiguousarray(l, np.uint32),
+            np.ascontiguousarray(last, np.uint32), np.ascontiguousarray(bits, np.uint32),
+            None if payload_off is None else np.ascontiguousarray(payload_off, np.uint64),
+            np.ascontiguousarray(payload, np.uint64)]
+    v = TrieView()
+    v.num_patterns = len(arrs[0])
+    v.num_samples = num_samples
+    v.num_kmers, v.parent_id = arrs[0].ctypes.data, arrs[1].ctypes.data
+    v.num_samples_full, v.num_local_samples = arrs[2].ctypes.data, arrs[3].ctypes.data
+    v.last_sample_id, v.num_bits = arrs[4].ctypes.data, arrs[5].ctypes.data
+    v.payload_off = None if arrs[6] is None else arrs[6].ctypes.data
+    v.payload = arrs[7].ctypes.data if arrs[7].size else None
+    v.payload_words = arrs[7].size
+    return v, arrs
+
+
+class Context:
+    """One GPU context of libkdbx.so (mirror of SimilarityCalculator's lifetime)."""
+
+    def __init__(self, device: int = -1, chunk_ids: int = 0, tile_cols: int = 0, unit_updates: int = 0):
+        k, _ = load()
+        self._k = k
+        cfg = Config(device, 0, chunk_ids, tile_cols, unit_updates)
+        p = C.c_void_p()
+        rc = k.kdbx_open(C.byref(cfg), C.byref(p))
+        if rc != 0:
+            raise KdbxError(k.kdbx_last_error(None).decode())
+        self._p = p
+        self.num_samples = 0
+        self.num_patterns = 0
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self._k.kdbx_close(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise KdbxError(self._k.kdbx_last_error(self._p).decode())
+
+    def load_patterns(self, trie_or_view, keep=None):
+        v = trie_or_view.view() if isinstance(trie_or_view, Trie) else trie_or_view
+        self._keep = (trie_or_view, keep)
+        self._check(self._k.kdbx_load_patterns(self._p, C.byref(v)))
+        self.num_samples, self.num_patterns = int(v.num_samples), int(v.num_patterns)
+
+    def all2all_dense(self, out: np.ndarray | None = None):
+        n = self.num_samples
+        if out is None:
+            out = np.empty(tri_cells(n), dtype=np.uint32)
+        st = Stats()
+        self._check(self._k.kdbx_all2all_dense(self._p, out.ctypes.data if out.size else None, C.byref(st)))
+        return out, st
+
+    def all2all_dense_rows(self, row_begin, row_end, out: np.ndarray | None = None):
+        cells = tri_cells(row_end) - tri_cells(row_begin)
+        if out is None:
+            out = np.empty(cells, dtype=np.uint32)
+        st = Stats()
+        self._check(self._k.kdbx_all2all_dense_rows(self._p, row_begin, row_end, out.ctypes.data if out.size else None, C.byref(st)))
+        return out, st
+
+    def all2all_dense_rows_device(self, row_begin, row_end, device_ptr: int):
+        st = Stats()
+        self._check(self._k.kdbx_all2all_dense_rows_device(self._p, row_begin, row_end, C.c_void_p(device_ptr), C.byref(st)))
+        return st
+
+    def row_updates(self):
+        out = np.zeros(self.num_samples, dtype=np.uint64)
+        self._check(self._k.kdbx_row_updates(self._p, out.ctypes.data if out.size else None))
+        return out
+
+    def debug_fetch(self, what: int, count: int, dtype):
+        out = np.zeros(count, dtype=dtype)
+        got = self._k.kdbx_debug_fetch(self._p, what, out.ctypes.data, count)
+        if got < 0:
+            raise KdbxError(self._k.kdbx_last_error(self._p).decode())
+        return out[:got]
+
+
+def pinned_empty(count: int, dtype=np.uint32):
+    """numpy array over page-locked host memory from kdbx_host_alloc (freed with the array)."""
+    k, _ = load()
+    nbytes = max(1, count * np.dtype(dtype).itemsize)
+    p = C.c_void_p()
+    if k.kdbx_host_alloc(C.byref(p), nbytes) != 0:
+        raise KdbxError("kdbx_host_alloc failed")
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            k.kdbx_host_free(self.ptr)
+
+    owner = _Owner(p)
+    buf = (C.c_char * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=count)
+    _PINNED_OWNERS[id(buf)] = owner  # keep alive as long as the module; arrays are few and large
+    return arr
+
+
+_PINNED_OWNERS: dict = {}
+
+
+def shard_rows_by_work(row_updates: np.ndarray, world: int):
+    """Contiguous row blocks with (nearly) equal numbers of updates: returns
+    world+1 boundaries.  Deterministic, so every rank computes the same split."""
+    n = len(row_updates)
+    cum = np.concatenate([[0], np.cumsum(row_updates.astype(np.float64))])
+    total = cum[-1]
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r / world
+        b = int(np.searchsorted(cum, target, side="left"))
+        bounds.append(min(max(b, bounds[-1]), n))
+    bounds.append(n)
+    return bounds

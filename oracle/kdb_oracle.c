@@ -1,0 +1,263 @@
+/*
+ * kdb_oracle.c — CPU restatement of kmer-db's dense all2all path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this; the product (kmer-db_b200/) never links, imports or executes anything under
+ * oracle/.  Plain scalar C, O(U) time, written from the behaviour of refresh-bio/kmer-db v2.3.1:
+ *
+ *   .db parsing            PrefixKmerDb::deserialize(SkipHashtables)  src/prefix_kmer_db.cpp:578-748
+ *                          pattern_t::unpack                          src/pattern.cpp:50-94
+ *                          hash_map_lp::deserialize(skipData)         src/hashmap_lp.h:546-566
+ *   Elias-gamma decode     CEliasGamma::decode / Decode               src/elias_gamma.h:133-256,371-378
+ *   local ids of a node    pattern_t::decodeSamples                   src/pattern.cpp:99-109
+ *   W accumulation         SimilarityCalculator::all2all              src/similarity_calculator.cpp:64-72
+ *   full list of a node    decomp worker (ancestors' lists, root first) src/similarity_calculator.cpp:130-152
+ *   jobs and row updates   sample2pattern + matrix workers            src/similarity_calculator.cpp:154-157,191-196,214-231
+ *   row_add                row[ids[k]] += to_add                      src/simd/row_add_avx2.cpp:57-72
+ *   packed triangle        LowerTriangularMatrix::operator[]          src/array.h:140
+ *   CSV bytes              All2AllConsole::run                        src/console_all2all.cpp:40-78
+ *                          num2str / num2str_sparse                   src/conversion.h:248-299
+ *
+ * Parity is PINNED: tests/test_oracle.py checks this file against the reference's own golden
+ * CSVs (test/virus/k18.csv, k18.sparse.csv, k24.csv, k18.frac.csv, test/synth/a2a, a2a-sparse;
+ * committed under tests/golden/) and against the unmodified reference binary built by
+ * oracle/build_ref.sh (oracle/_ref/kmer-db) on generated databases.
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+    uint64_t num_patterns;
+    uint32_t num_samples;
+    uint32_t kmer_length;
+    double fraction;
+    int64_t* num_kmers;
+    int64_t* parent_id;
+    uint32_t* n;
+    uint32_t* l;
+    uint32_t* last;
+    uint32_t* bits;
+    uint64_t* payload_off; /* in 64-bit words */
+    uint64_t* payload;
+    uint64_t payload_words;
+    char** names;
+    uint64_t* sample_kmers;
+} oracle_db;
+
+/* ---- Elias-gamma: (b-1) ones, a zero, then b-1 low bits, MSB-first in u64 words -------- */
+static uint32_t get_bit(const uint64_t* w, uint32_t pos) { return (uint32_t)((w[pos >> 6] >> (63 - (pos & 63))) & 1u); }
+
+static uint32_t gamma_decode_one(const uint64_t* w, uint32_t* pos) {
+    uint32_t ones = 0, v = 1;
+    while (get_bit(w, *pos)) { ++ones; ++*pos; }
+    ++*pos; /* the zero */
+    for (uint32_t i = 0; i < ones; ++i) { v = (v << 1) | get_bit(w, *pos); ++*pos; }
+    return v;
+}
+
+/* local ids of one node, ascending (src/pattern.cpp:99-109) */
+void oracle_decode_local(const uint64_t* words, uint32_t l, uint32_t last, uint32_t* out) {
+    if (l == 0) return;
+    uint32_t pos = 0;
+    out[l - 1] = last;
+    for (uint32_t i = 0; i + 1 < l; ++i) out[i] = gamma_decode_one(words, &pos); /* deltas */
+    for (int64_t i = (int64_t)l - 2; i >= 0; --i) out[i] = out[i + 1] - out[i];
+}
+
+/* ---- dense all2all over SoA arrays -------------------------------------------------------
+ * tri: N(N-1)/2 uint32 cells, zeroed here.  Returns U (number of row[col] += w executions),
+ * or UINT64_MAX on allocation failure.  Does not modify its inputs. */
+uint64_t oracle_all2all(uint64_t P, uint32_t N, const int64_t* num_kmers, const int64_t* parent_id, const uint32_t* n,
+                        const uint32_t* l, const uint32_t* last, const uint32_t* bits, const uint64_t* payload_off,
+                        const uint64_t* payload, uint32_t* tri) {
+    (void)bits;
+    const uint64_t cells = N ? (uint64_t)N * (N - 1) / 2 : 0;
+    memset(tri, 0, cells * sizeof(uint32_t));
+    int64_t* W = (int64_t*)malloc(P * sizeof(int64_t));
+    uint32_t* full = (uint32_t*)malloc(((size_t)N + 1) * sizeof(uint32_t));
+    if (!W || !full) { free(W); free(full); return UINT64_MAX; }
+    memcpy(W, num_kmers, P * sizeof(int64_t));
+    for (uint64_t i = P; i-- > 1;) /* children before parents: parent_id < own id */
+        if (parent_id[i] >= 0) W[parent_id[i]] += W[i];
+    uint64_t U = 0;
+    for (uint64_t p = 0; p < P; ++p) {
+        if (l[p] == 0) continue;
+        /* full list, written back to front while walking to the root */
+        uint32_t* out = full + n[p];
+        for (int64_t q = (int64_t)p; q >= 0; q = parent_id[q]) {
+            out -= l[q];
+            oracle_decode_local(payload + payload_off[q], l[q], last[q], out);
+        }
+        const uint32_t to_add = (uint32_t)W[p];
+        for (uint32_t i = n[p] - l[p]; i < n[p]; ++i) { /* one job per LOCAL position */
+            const uint64_t s = full[i];
+            uint32_t* row = tri + s * (s - 1) / 2; /* i == 0 implies no columns; row unused */
+            for (uint32_t k = 0; k < i; ++k) row[full[k]] += to_add;
+            U += i;
+        }
+    }
+    free(W); free(full);
+    return U;
+}
+
+/* Independent second opinion used by the tests on small tries: M[s][t] = sum of num_kmers over
+ * nodes whose full list contains both s and t (a k-mer of node p lies in exactly the samples
+ * of p's full list).  O(sum n^2), no W accumulation, no job rule. */
+int oracle_all2all_bruteforce(uint64_t P, uint32_t N, const int64_t* num_kmers, const int64_t* parent_id, const uint32_t* n,
+                              const uint32_t* l, const uint32_t* last, const uint64_t* payload_off, const uint64_t* payload,
+                              uint32_t* tri) {
+    const uint64_t cells = N ? (uint64_t)N * (N - 1) / 2 : 0;
+    memset(tri, 0, cells * sizeof(uint32_t));
+    uint32_t* full = (uint32_t*)malloc(((size_t)N + 1) * sizeof(uint32_t));
+    if (!full) return -1;
+    for (uint64_t p = 0; p < P; ++p) {
+        if (n[p] == 0 || num_kmers[p] == 0) continue;
+        uint32_t* out = full + n[p];
+        for (int64_t q = (int64_t)p; q >= 0; q = parent_id[q]) {
+            out -= l[q];
+            oracle_decode_local(payload + payload_off[q], l[q], last[q], out);
+        }
+        for (uint32_t a = 1; a < n[p]; ++a)
+            for (uint32_t b = 0; b < a; ++b) {
+                const uint64_t s = full[a];
+                tri[s * (s - 1) / 2 + full[b]] += (uint32_t)num_kmers[p];
+            }
+    }
+    free(full);
+    return 0;
+}
+
+/* ---- .db reader (hashtables skipped) ---------------------------------------------------- */
+static int rd(FILE* f, void* dst, size_t bytes) { return bytes == 0 || fread(dst, 1, bytes, f) == bytes; }
+
+void oracle_db_free(oracle_db* db) {
+    if (!db) return;
+    free(db->num_kmers); free(db->parent_id); free(db->n); free(db->l); free(db->last); free(db->bits);
+    free(db->payload_off); free(db->payload); free(db->sample_kmers);
+    if (db->names) for (uint32_t i = 0; i < db->num_samples; ++i) free(db->names[i]);
+    free(db->names);
+    free(db);
+}
+
+oracle_db* oracle_db_read(const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return NULL;
+    oracle_db* db = (oracle_db*)calloc(1, sizeof(oracle_db));
+    uint64_t format_word, kmers_count, nsamples, ntables, P;
+    double start_fraction; int32_t alphabet; uint8_t inited;
+    int ok = rd(f, &format_word, 8) && rd(f, &db->kmer_length, 4) && rd(f, &db->fraction, 8) && rd(f, &start_fraction, 8) &&
+             rd(f, &alphabet, 4) && rd(f, &inited, 1) && rd(f, &kmers_count, 8) && rd(f, &nsamples, 8);
+    if (!ok) goto fail;
+    db->num_samples = (uint32_t)nsamples;
+    db->names = (char**)calloc(nsamples + 1, sizeof(char*));
+    db->sample_kmers = (uint64_t*)calloc(nsamples + 1, 8);
+    for (uint64_t i = 0; i < nsamples; ++i) {
+        uint64_t len;
+        if (!rd(f, &db->sample_kmers[i], 8) || !rd(f, &len, 8)) goto fail;
+        db->names[i] = (char*)calloc(len + 1, 1);
+        if (!rd(f, db->names[i], len)) goto fail;
+    }
+    if (!rd(f, &ntables, 8)) goto fail;
+    for (uint64_t i = 0; i < ntables; ++i) {
+        if (format_word & 1) { /* raw: f64 + 7 u64 header, bit-vector, filled slots */
+            uint64_t hdr[8];
+            if (!rd(f, hdr, sizeof hdr)) goto fail;
+            const uint64_t filled = hdr[1], allocated = hdr[2];
+            if (fseeko(f, (off_t)(((allocated + 63) / 64) * 8 + filled * 8), SEEK_CUR)) goto fail;
+        } else {
+            uint64_t total, seen = 0, portion;
+            if (!rd(f, &total, 8)) goto fail;
+            while (seen < total) {
+                if (!rd(f, &portion, 8) || fseeko(f, (off_t)(portion * 8), SEEK_CUR)) goto fail;
+                seen += portion;
+            }
+        }
+    }
+    if (!rd(f, &P, 8)) goto fail;
+    db->num_patterns = P;
+    db->num_kmers = (int64_t*)malloc((P + 1) * 8); db->parent_id = (int64_t*)malloc((P + 1) * 8);
+    db->n = (uint32_t*)malloc((P + 1) * 4); db->l = (uint32_t*)malloc((P + 1) * 4);
+    db->last = (uint32_t*)malloc((P + 1) * 4); db->bits = (uint32_t*)malloc((P + 1) * 4);
+    db->payload_off = (uint64_t*)malloc((P + 1) * 8);
+    {
+        uint64_t cap = 1024, used = 0, pid = 0;
+        db->payload = (uint64_t*)malloc(cap * 8);
+        while (pid < P) {
+            uint64_t block;
+            if (!rd(f, &block, 8)) goto fail;
+            unsigned char* buf = (unsigned char*)malloc(block + 1);
+            if (!rd(f, buf, block)) { free(buf); goto fail; }
+            uint64_t at = 0;
+            while (at < block && pid < P) { /* 40-byte header + ceil(bits/128)*16 payload bytes */
+                memcpy(&db->num_kmers[pid], buf + at, 8); memcpy(&db->parent_id[pid], buf + at + 8, 8);
+                memcpy(&db->n[pid], buf + at + 16, 4); memcpy(&db->l[pid], buf + at + 20, 4);
+                memcpy(&db->last[pid], buf + at + 24, 4); memcpy(&db->bits[pid], buf + at + 28, 4);
+                at += 40;
+                const uint64_t words = db->bits[pid] ? ((uint64_t)(db->bits[pid] + 127) / 128) * 2 : 0;
+                if (used + words + 2 > cap) { while (used + words + 2 > cap) cap *= 2; db->payload = (uint64_t*)realloc(db->payload, cap * 8); }
+                db->payload_off[pid] = used;
+                memcpy(db->payload + used, buf + at, words * 8);
+                used += words; at += words * 8;
+                ++pid;
+            }
+            free(buf);
+        }
+        db->payload[used] = 0; db->payload[used + 1] = 0;
+        db->payload_words = used;
+    }
+    fclose(f);
+    return db;
+fail:
+    fclose(f);
+    oracle_db_free(db);
+    return NULL;
+}
+
+/* ---- CSV (src/console_all2all.cpp:40-78) ------------------------------------------------- */
+int oracle_write_csv(const oracle_db* db, const uint32_t* tri, const char* path, int sparse) {
+    FILE* f = fopen(path, "wb");
+    if (!f) return -1;
+    fprintf(f, "kmer-length: %u fraction: %g ,db-samples ,", db->kmer_length, db->fraction);
+    for (uint32_t i = 0; i < db->num_samples; ++i) fprintf(f, "%s,", db->names[i]);
+    fprintf(f, "\nquery-samples,total-kmers,");
+    for (uint32_t i = 0; i < db->num_samples; ++i) fprintf(f, "%llu,", (unsigned long long)db->sample_kmers[i]);
+    fprintf(f, "\n");
+    for (uint64_t s = 0; s < db->num_samples; ++s) {
+        fprintf(f, "%s,%llu,", db->names[s], (unsigned long long)db->sample_kmers[s]);
+        const uint32_t* row = tri + s * (s - 1) / 2;
+        for (uint64_t c = 0; c < s; ++c) {
+            if (!sparse) fprintf(f, "%u,", row[c]);
+            else if (row[c]) fprintf(f, "%llu:%u,", (unsigned long long)(c + 1), row[c]);
+        }
+        fprintf(f, "\n");
+    }
+    return fclose(f);
+}
+
+/* whole path on a file: returns U or UINT64_MAX */
+uint64_t oracle_all2all_file(const char* db_path, const char* csv_path, int sparse) {
+    oracle_db* db = oracle_db_read(db_path);
+    if (!db) return UINT64_MAX;
+    const uint64_t N = db->num_samples;
+    uint32_t* tri = (uint32_t*)calloc(N * (N ? N - 1 : 0) / 2 + 1, 4);
+    uint64_t U = oracle_all2all(db->num_patterns, db->num_samples, db->num_kmers, db->parent_id, db->n, db->l, db->last, db->bits,
+                                db->payload_off, db->payload, tri);
+    if (U != UINT64_MAX && csv_path && oracle_write_csv(db, tri, csv_path, sparse)) U = UINT64_MAX;
+    free(tri);
+    oracle_db_free(db);
+    return U;
+}
+
+#ifdef ORACLE_MAIN
+int main(int argc, char** argv) {
+    int sparse = 0, a = 1;
+    if (argc > 1 && !strcmp(argv[1], "-sparse")) { sparse = 1; a = 2; }
+    if (argc - a != 2) { fprintf(stderr, "usage: kdb_oracle [-sparse] <db> <out.csv>\n"); return 2; }
+    const uint64_t U = oracle_all2all_file(argv[a], argv[a + 1], sparse);
+    if (U == UINT64_MAX) { fprintf(stderr, "oracle failed\n"); return 1; }
+    fprintf(stderr, "U=%llu\n", (unsigned long long)U);
+    return 0;
+}
+#endif

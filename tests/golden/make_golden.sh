@@ -1,0 +1,22 @@
+#!/usr/bin/env bash
+# Regenerates the fixtures in this directory from the reference checkout (run in the build
+# container only; /root/reference does not exist on the GPU box).  Databases are built by the
+# UNMODIFIED reference binary (oracle/_ref/kmer-db, see oracle/build_ref.sh) from the
+# reference's own test inputs; the *.csv / a2a* files are the reference's committed golden
+# outputs for those inputs (test/virus, test/synth), copied verbatim as test vectors.
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="${REF:-/root/reference}"
+BIN="$HERE/../../oracle/_ref/kmer-db"
+cd "$REF"
+"$BIN" build test/virus/seqs.list "$HERE/virus.k18.db"
+"$BIN" build -f 0.1 test/virus/seqs.list "$HERE/virus.k18.f01.db"
+"$BIN" build -k 24 test/virus/seqs.list "$HERE/virus.k24.db"
+gzip -9 -f "$HERE/virus.k24.db"      # 65536 mostly empty hashtables: 5 MB -> small
+"$BIN" build -multisample-fasta -k 21 test/synth/synth.fa "$HERE/synth.k21.db"
+cp test/virus/k18.csv "$HERE/virus.k18.csv"
+cp test/virus/k18.sparse.csv "$HERE/virus.k18.sparse.csv"
+cp test/virus/k18.frac.csv "$HERE/virus.k18.f01.csv"
+cp test/virus/k24.csv "$HERE/virus.k24.csv"
+cp test/synth/a2a "$HERE/synth.k21.csv"
+cp test/synth/a2a-sparse "$HERE/synth.k21.sparse.csv"

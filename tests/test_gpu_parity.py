@@ -1,0 +1,214 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle.  Needs a B200: -m gpu."""
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_util as ou
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(libs):
+    c = libs.Context(device=0)
+    yield c
+    c.close()
+
+
+def _run(libs, N, a, **cfg):
+    with libs.Context(device=0, **cfg) as c:
+        v, keep = libs.view_from_arrays(N, a["num_kmers"], a["parent_id"], a["n"], a["l"], a["last"], a["bits"], a["payload_off"],
+                                        a["payload"])
+        c.load_patterns(v, keep)
+        out, st = c.all2all_dense()
+        return out, st
+
+
+@pytest.mark.parametrize("name", ["virus.k18", "virus.k18.f01", "virus.k24", "synth.k21"])
+def test_golden_databases_csv_bytes(libs, ctx, golden_dbs, tmp_path, name):
+    db, dense, sparse = golden_dbs[name]
+    t = libs.Trie.read_db(db)
+    ctx.load_patterns(t)
+    tri, st = ctx.all2all_dense()
+    assert st.updates == t.totals().updates
+    out = tmp_path / "g.csv"
+    t.write_all2all_csv(tri, out)
+    assert ou.read_bytes(out) == ou.read_bytes(dense)
+    if sparse is not None:
+        t.write_all2all_csv(tri, out, sparse=True)
+        assert ou.read_bytes(out) == ou.read_bytes(sparse)
+
+
+def test_cli_reproduces_golden_csv(libs, golden_dbs, tmp_path):
+    db, dense, sparse = golden_dbs["virus.k18"]
+    exe = ou.ROOT / "kmer-db_b200" / "bin" / "kmer-db-b200"
+    subprocess.run([str(exe), "all2all", str(db), str(tmp_path / "a.csv")], check=True, stderr=subprocess.DEVNULL)
+    assert ou.read_bytes(tmp_path / "a.csv") == ou.read_bytes(dense)
+    subprocess.run([str(exe), "all2all", "-sparse", str(db), str(tmp_path / "s.csv")], check=True, stderr=subprocess.DEVNULL)
+    assert ou.read_bytes(tmp_path / "s.csv") == ou.read_bytes(sparse)
+    r = subprocess.run([str(exe), "all2all", str(tmp_path / "missing.db"), str(tmp_path / "x.csv")], capture_output=True, text=True)
+    assert r.returncode != 0 and "ERROR: Cannot open k-mer database" in r.stderr
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_tries_bit_exact(libs, oracle, seed):
+    rng = np.random.default_rng(100 + seed)
+    N = int(rng.integers(2, 400))
+    a, _ = ou.random_trie(rng, N, int(rng.integers(2, 1500)), max_local=int(rng.integers(1, 30)),
+                          big_weights=(seed % 2 == 0), dense_lists=(seed % 3 == 0))
+    want, U = ou.oracle_all2all(oracle, N, a)
+    got, st = _run(libs, N, a)
+    assert st.updates == U
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("cfg", [dict(tile_cols=32), dict(tile_cols=64, chunk_ids=4096), dict(tile_cols=128, unit_updates=64),
+                                 dict(chunk_ids=5000, unit_updates=1), dict(tile_cols=1024, unit_updates=1 << 30)])
+def test_schedule_knobs_do_not_change_results(libs, oracle, cfg):
+    """column tiles (T>1), many chunks, tiny / huge work units: same bits."""
+    rng = np.random.default_rng(7)
+    N = 900
+    a, _ = ou.random_trie(rng, N, 4000, max_local=25, big_weights=True)
+    want, U = ou.oracle_all2all(oracle, N, a)
+    got, st = _run(libs, N, a, **cfg)
+    assert st.updates == U
+    assert np.array_equal(got, want)
+    if "chunk_ids" in cfg:
+        assert st.chunks > 1
+
+
+def test_edge_cases(libs, oracle):
+    z = np.zeros
+    # only the sentinel pattern; N = 0, 1, 2
+    for N in (0, 1, 2):
+        a = {"num_kmers": z(1, np.int64), "parent_id": np.full(1, -1, np.int64), "n": z(1, np.uint32), "l": z(1, np.uint32),
+             "last": z(1, np.uint32), "bits": z(1, np.uint32), "payload_off": z(1, np.uint64), "payload": z(2, np.uint64)}
+        got, st = _run(libs, N, a)
+        assert got.size == ou.tri_cells(N) and not got.any() and st.updates == 0
+    # one pattern holding every sample (maximum list length), N not a multiple of 32
+    N = 1000
+    w, nb = ou.gamma_encode([1] * (N - 1))
+    a = {"num_kmers": np.array([0, 2**32 + 3], np.int64), "parent_id": np.array([-1, -1], np.int64),
+         "n": np.array([0, N], np.uint32), "l": np.array([0, N], np.uint32), "last": np.array([0, N - 1], np.uint32),
+         "bits": np.array([0, nb], np.uint32), "payload_off": z(2, np.uint64), "payload": np.concatenate([w, z(2, np.uint64)])}
+    got, st = _run(libs, N, a)
+    assert st.updates == N * (N - 1) // 2 and (got == 3).all()
+    # dense payload (payload_off = NULL) gives the same result
+    rng = np.random.default_rng(3)
+    a, _ = ou.random_trie(rng, 300, 800, max_local=20)
+    want, _ = ou.oracle_all2all(oracle, 300, a)
+    with libs.Context(device=0) as c:
+        v, keep = libs.view_from_arrays(300, a["num_kmers"], a["parent_id"], a["n"], a["l"], a["last"], a["bits"], None, a["payload"])
+        c.load_patterns(v, keep)
+        got, _ = c.all2all_dense()
+    assert np.array_equal(got, want)
+
+
+def test_malformed_and_misuse_are_errors(libs):
+    with libs.Context(device=0) as c:
+        with pytest.raises(libs.KdbxError, match="no patterns loaded"):
+            c.num_samples = 4
+            c.all2all_dense()
+    rng = np.random.default_rng(1)
+    a, _ = ou.random_trie(rng, 50, 60, max_local=8)
+    bad = dict(a)
+    bad["bits"] = a["bits"].copy()
+    idx = int(np.argmax(a["l"] > 1))
+    bad["bits"][idx] += 1
+    with pytest.raises(libs.KdbxError, match="malformed trie"):
+        _run(libs, 50, bad)
+    with libs.Context(device=0) as c:
+        v, keep = libs.view_from_arrays(50, a["num_kmers"], a["parent_id"], a["n"], a["l"], a["last"], a["bits"], a["payload_off"], a["payload"])
+        c.load_patterns(v, keep)
+        with pytest.raises(libs.KdbxError, match="bad row range"):
+            c.all2all_dense_rows(10, 60)
+
+
+def test_w_accumulation_and_decode_taps(libs, oracle):
+    rng = np.random.default_rng(9)
+    N = 200
+    a, lists = ou.random_trie(rng, N, 3000, max_local=12, big_weights=True)
+    with libs.Context(device=0) as c:
+        v, keep = libs.view_from_arrays(N, a["num_kmers"], a["parent_id"], a["n"], a["l"], a["last"], a["bits"], a["payload_off"], a["payload"])
+        c.load_patterns(v, keep)
+        c.all2all_dense()
+        W = c.debug_fetch(0, len(a["n"]), np.uint32)
+        loff = c.debug_fetch(2, len(a["n"]) + 1, np.uint64)
+        loc = c.debug_fetch(1, int(a["l"].sum()), np.uint32)
+    assert np.array_equal(W, ou.host_w(a))
+    assert np.array_equal(loff, np.concatenate([[0], np.cumsum(a["l"].astype(np.uint64))]))
+    assert loc.tolist() == [x for ids in lists for x in ids]
+
+
+def test_row_sharding_matches_full_matrix(libs, oracle):
+    t = libs.Trie.synth(num_samples=300, num_clusters=3, genome_kmers=40000, seed=5, interleaved=True)
+    N = t.num_samples
+    want, U = ou.oracle_all2all(oracle, N, t.arrays())
+    with libs.Context(device=0) as c:
+        c.load_patterns(t)
+        upd = c.row_updates()
+        assert int(upd.sum()) == U
+        for world in (2, 3, 8):
+            b = libs.shard_rows_by_work(upd, world)
+            parts, total = [], 0
+            for r in range(world):
+                out, st = c.all2all_dense_rows(b[r], b[r + 1])
+                assert st.updates == int(upd[b[r]:b[r + 1]].sum())
+                parts.append(out)
+                total += st.updates
+            assert total == U
+            assert np.array_equal(np.concatenate(parts), want)
+
+
+def test_generated_db_matches_reference_binary(libs, ref_bin, tmp_path):
+    """Same .db through the unmodified reference (all host cores) and through the GPU path: cmp."""
+    if ref_bin is None:
+        pytest.skip("reference binary not built (oracle/_ref)")
+    t = libs.Trie.synth(num_samples=400, num_clusters=4, genome_kmers=200000, seed=21)
+    db = tmp_path / "g.db"
+    t.write_db(db)
+    subprocess.run([str(ref_bin), "all2all", str(db), str(tmp_path / "ref.csv")], check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL)
+    with libs.Context(device=0) as c:
+        c.load_patterns(t)
+        tri, st = c.all2all_dense()
+    assert st.updates == t.totals().updates
+    t.write_all2all_csv(tri, tmp_path / "gpu.csv")
+    assert ou.read_bytes(tmp_path / "gpu.csv") == ou.read_bytes(tmp_path / "ref.csv")
+
+
+def test_large_n_uses_column_tiles(libs, oracle):
+    """N > tile width: the (row, tile) decomposition with the default 2048-column tiles."""
+    t = libs.Trie.synth(num_samples=5000, num_clusters=10, genome_kmers=3000, seed=8, mutation_rate=0.01)
+    N = t.num_samples
+    want, U = ou.oracle_all2all(oracle, N, t.arrays())
+    with libs.Context(device=0) as c:
+        c.load_patterns(t)
+        got, st = c.all2all_dense()
+    assert st.updates == U
+    assert np.array_equal(got, want)
+
+
+def test_full_size_properties(libs):
+    """A BASELINE-shaped cluster (250 genomes x 5 Mbp, one of config 2's four): results must not
+    depend on the schedule (chunking / unit size), every cell is bounded by the genome size,
+    row shards tile the matrix, and the update count equals U from the trie."""
+    t = libs.Trie.synth(num_samples=250, num_clusters=1, genome_kmers=5_000_000, seed=2, pinned=False)
+    tot = t.totals()
+    with libs.Context(device=0) as c:
+        c.load_patterns(t)
+        a, st = c.all2all_dense()
+        assert st.updates == tot.updates
+        upd = c.row_updates()
+        assert int(upd.sum()) == tot.updates
+        b = libs.shard_rows_by_work(upd, 4)
+        parts = [c.all2all_dense_rows(b[r], b[r + 1])[0] for r in range(4)]
+    assert np.array_equal(np.concatenate(parts), a)
+    assert int(a.max()) <= 5_000_000
+    with libs.Context(device=0, chunk_ids=1 << 26, unit_updates=4096) as c:
+        c.load_patterns(t)
+        b2, _ = c.all2all_dense()
+    assert np.array_equal(a, b2)
+    # checksum of checksums: sum of the matrix == sum over jobs of W*i, computed from the device taps
+    # (W, decoded locals) with numpy only

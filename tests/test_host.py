@@ -1,0 +1,150 @@
+"""Host logic and the C-ABI surface; no GPU needed."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_util as ou
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared(header):
+    text = (ROOT / "include" / header).read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kdbxh?_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_libraries_export_every_declared_symbol(libs):
+    k, h = libs.load()
+    for name in _declared("kdbx.h"):
+        assert hasattr(k, name), name
+    for name in _declared("kdbx_host.h"):
+        assert hasattr(h, name), name
+    assert set(_declared("kdbx.h")) == set(libs.KDBX_SYMBOLS)
+    assert set(_declared("kdbx_host.h")) == set(libs.KDBXH_SYMBOLS)
+    assert k.kdbx_abi_version() == 1
+
+
+def test_struct_sizes_match_header(libs, tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "kdbx_host.h"\nint main(){printf("%zu %zu %zu %zu %zu",sizeof(kdbx_config),'
+                   'sizeof(kdbx_trie_view),sizeof(kdbx_stats),sizeof(kdbxh_synth_params),sizeof(kdbxh_totals));return 0;}')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [C.sizeof(libs.Config), C.sizeof(libs.TrieView), C.sizeof(libs.Stats), C.sizeof(libs.SynthParams),
+                     C.sizeof(libs.Totals)]
+
+
+def test_no_gpu_means_loud_failure_not_fallback(libs):
+    k, _ = libs.load()
+    if k.kdbx_device_count() > 0:
+        pytest.skip("a B200 is present")
+    with pytest.raises(libs.KdbxError, match="no CPU fallback|sm_100a"):
+        libs.Context()
+
+
+def test_product_never_touches_the_oracle():
+    for p in (ROOT / "kmer-db_b200").rglob("*"):
+        if p.suffix in {".cpp", ".h", ".cu", ".py"} or p.name == "Makefile":
+            assert "oracle" not in p.read_text(), p
+
+
+@pytest.mark.parametrize("name", ["virus.k18", "virus.k18.f01", "virus.k24", "synth.k21"])
+def test_reader_agrees_with_oracle_reader_and_csv_writer_is_byte_exact(libs, oracle, golden_dbs, tmp_path, name):
+    db, dense, sparse = golden_dbs[name]
+    t = libs.Trie.read_db(db)
+    t.validate()
+    a = t.arrays()
+    tri, U = ou.oracle_all2all(oracle, t.num_samples, a)   # the checker computes the matrix ...
+    assert U == t.totals().updates
+    out = tmp_path / "h.csv"
+    t.write_all2all_csv(tri, out)                           # ... the product formats it
+    assert ou.read_bytes(out) == ou.read_bytes(dense)
+    if sparse is not None:
+        t.write_all2all_csv(tri, out, sparse=True)
+        assert ou.read_bytes(out) == ou.read_bytes(sparse)
+
+
+def test_db_writer_round_trip_and_reference_accepts_it(libs, golden_dbs, ref_bin, tmp_path):
+    db, dense, _ = golden_dbs["virus.k18"]
+    t = libs.Trie.read_db(db)
+    out = tmp_path / "copy.db"
+    t.write_db(out)
+    t2 = libs.Trie.read_db(out)
+    a, b = t.arrays(), t2.arrays()
+    for key in a:
+        assert np.array_equal(a[key], b[key]), key
+    assert t.sample_names() == t2.sample_names()
+    if ref_bin is not None:  # the unmodified reference computes the golden CSV from OUR file
+        subprocess.run([str(ref_bin), "all2all", "-t", "2", str(out), str(tmp_path / "r.csv")], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        assert ou.read_bytes(tmp_path / "r.csv") == ou.read_bytes(dense)
+
+
+def test_missing_db_is_an_error(libs, tmp_path):
+    with pytest.raises(libs.KdbxError, match="Cannot open k-mer database"):
+        libs.Trie.read_db(tmp_path / "nope.db")
+    (tmp_path / "short.db").write_bytes(b"\x01\x00\x00")
+    with pytest.raises(libs.KdbxError):
+        libs.Trie.read_db(tmp_path / "short.db")
+
+
+@pytest.mark.parametrize("interleaved", [False, True])
+def test_generator_makes_valid_tries_with_exact_kmer_accounting(libs, oracle, interleaved):
+    L = 20000
+    t = libs.Trie.synth(num_samples=40, num_clusters=3, genome_kmers=L, seed=3, interleaved=interleaved)
+    t.validate()
+    a = t.arrays()
+    N = t.num_samples
+    # every sample's k-mers are partitioned over the patterns whose full list contains it
+    per_sample = np.zeros(N, np.int64)
+    P = len(a["n"])
+    for p in range(1, P):
+        q = p
+        while q >= 0:
+            ids = np.zeros(int(a["l"][q]), np.uint32)
+            oracle.oracle_decode_local(a["payload"][int(a["payload_off"][q]):].ctypes.data, int(a["l"][q]), int(a["last"][q]),
+                                       ids.ctypes.data)
+            per_sample[ids] += int(a["num_kmers"][p])
+            q = int(a["parent_id"][q])
+    assert (per_sample == L).all()
+    # shared k-mers never exceed a genome, members of different clusters share nothing
+    tri, _ = ou.oracle_all2all(oracle, N, a)
+    assert tri.max() <= L
+    cl = (lambda s: s % 3) if interleaved else (lambda s: s * 3 // N)
+    for s in range(N):
+        for c in range(s):
+            if cl(s) != cl(c):
+                assert tri[s * (s - 1) // 2 + c] == 0
+    # determinism
+    t2 = libs.Trie.synth(num_samples=40, num_clusters=3, genome_kmers=L, seed=3, interleaved=interleaved, threads=1)
+    for key, v in t2.arrays().items():
+        assert np.array_equal(v, a[key]), key
+
+
+def test_shard_rows_by_work(libs):
+    w = np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 9] * 10, dtype=np.uint64)
+    for world in (1, 2, 4, 8):
+        b = libs.shard_rows_by_work(w, world)
+        assert b[0] == 0 and b[-1] == len(w) and all(x <= y for x, y in zip(b, b[1:]))
+        loads = [int(w[b[i]:b[i + 1]].sum()) for i in range(world)]
+        assert max(loads) - min(loads) <= 2 * int(w.max())
+
+
+def test_prefix_cuts_a_cluster_exactly(libs, oracle):
+    t = libs.Trie.synth(num_samples=60, num_clusters=3, genome_kmers=15000, seed=4)
+    sub = t.prefix(20)
+    sub.validate()
+    full, _ = ou.oracle_all2all(oracle, 60, t.arrays())
+    part, _ = ou.oracle_all2all(oracle, 20, sub.arrays())
+    assert np.array_equal(part, full[:ou.tri_cells(20)])
+    with pytest.raises(libs.KdbxError, match="prefix"):
+        t.prefix(30)  # inside a cluster
+    ti = libs.Trie.synth(num_samples=60, num_clusters=3, genome_kmers=15000, seed=4, interleaved=True)
+    with pytest.raises(libs.KdbxError, match="prefix"):
+        ti.prefix(20)
