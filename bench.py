@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the all2all common-k-mer counting path (BASELINE.json metric: k-mer-pair updates/s).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a kernels through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the UNMODIFIED reference binary on the host cores
+
+Workload (config.workload): BASELINE.json configs[1] — 1,000 synthetic 5 Mbp bacterial genomes,
+k=18, f=1.0, dense all2all — produced by the pattern-level generator (kmer-db_b200/host/synth.cpp:
+4 clusters x 250, every genome a copy of a random earlier cluster member with 0.5 % substitutions).
+A "step" is one full all2all over that database.  The unit of work U (updates) is a property of
+the database: U = sum_p l_p(2 n_p - l_p - 1)/2 = the number of `row[col] += w` executions of the
+reference's dense path.
+
+  value    K*U / device time of K steps, inputs (the raw trie) resident in HBM, result left in HBM;
+           device time = CUDA events on the library's stream around each step, summed, max over ranks.
+  e2e      same metric through the public C-ABI calls with HOST buffers: every step copies the trie
+           from pinned host memory (kdbx_load_patterns) and reads the matrix back (kdbx_all2all_dense_rows).
+  roofline the scatter-add kernel: 12 algorithmic bytes per update (4 B id + 4 B cell read + 4 B cell
+           write) x updates per launch / measured average launch duration, against the
+           measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the reference binary (oracle/_ref/kmer-db all2all -t <all cores>) on a bounded sample:
+           the first cluster (250 genomes x 5 Mbp = exactly a quarter of the workload's updates).
+With N>1 (torchrun, one rank per GPU) the matrix is sharded by contiguous row blocks balanced on
+per-row update counts; no collective on the data path; total work is fixed => "strong" scaling.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "kmer-db_b200"))
+
+ALGO_BYTES_PER_UPDATE = 12
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--samples", type=int, default=1000)
+    ap.add_argument("--clusters", type=int, default=4)
+    ap.add_argument("--genome-kmers", type=int, default=5_000_000)
+    ap.add_argument("--k", type=int, default=18)
+    ap.add_argument("--mu", type=float, default=0.005)
+    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--chunk-ids", type=int, default=0)
+    ap.add_argument("--tile-cols", type=int, default=0)
+    ap.add_argument("--unit-updates", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cache-dir", default=os.environ.get("KDBX_CACHE", "/tmp/kdbx_cache"))
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"{a.samples} synthetic {a.genome_kmers / 1e6:g} Mbp genomes, {a.clusters} clusters, mu={a.mu}, "
+            f"k={a.k}, f=1.0, dense all2all (BASELINE.json configs[1] shape)")
+
+
+def cache_path(a, samples, clusters):
+    return Path(a.cache_dir) / f"synth_n{samples}_c{clusters}_L{a.genome_kmers}_k{a.k}_mu{a.mu}_s{a.seed}.db"
+
+
+def get_workload(kdbx, a, samples, clusters, pinned, rank=0, barrier=None):
+    """Generate (rank 0) or read the cached database.  Same seed => cluster c is identical whether
+    generated alone or as part of the full workload, so the CPU sample is a true subset."""
+    path = cache_path(a, samples, clusters)
+    if rank == 0 and not path.exists():
+        path.parent.mkdir(parents=True, exist_ok=True)
+        t0 = time.time()
+        t = kdbx.Trie.synth(num_samples=samples, num_clusters=clusters, genome_kmers=a.genome_kmers, k=a.k,
+                            mutation_rate=a.mu, seed=a.seed)
+        tmp = path.with_suffix(".tmp%d" % os.getpid())
+        t.write_db(tmp)
+        os.replace(tmp, path)
+        t.close()
+        print(f"[bench] generated {path.name} in {time.time() - t0:.1f} s", file=sys.stderr)
+    if barrier:
+        barrier()
+    return kdbx.Trie.read_db(path, pinned=pinned), path
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines = []
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference_binary(db_path, threads):
+    """Times the reference's own all2all (the span it prints as 'OK (x seconds)' after
+    'Calculating matrix of common k-mers...', src/console_all2all.cpp:31-36)."""
+    exe = ROOT / "oracle" / "_ref" / "kmer-db"
+    if not exe.exists():
+        raise RuntimeError("oracle/_ref/kmer-db missing (run oracle/build_ref.sh where /root/reference is mounted)")
+    out = Path(db_path).with_suffix(".ref.csv")
+    r = subprocess.run([str(exe), "all2all", "-t", str(threads), str(db_path), str(out)], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("reference all2all failed: " + r.stderr[-300:])
+    txt = r.stdout + r.stderr
+    m = re.search(r"Calculating matrix of common k-mers\.\.\..*?OK \(([0-9.eE+-]+) seconds\)", txt, re.S)
+    if not m:
+        raise RuntimeError("could not parse the reference's timing line")
+    try:
+        out.unlink()
+    except OSError:
+        pass
+    return float(m.group(1))
+
+
+def ncu_traffic_per_launch():
+    """dram bytes per scatter launch from the committed ncu summary, if one exists."""
+    p = ROOT / "profiles" / "scatter_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def main():
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    sample_n = max(1, a.samples // a.clusters)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        import kdbx
+        t, path = get_workload(kdbx, a, sample_n, 1, pinned=False)
+        U = int(t.totals().updates)
+        t.close()
+        for _ in range(a.warmup):
+            run_reference_binary(path, cores)
+        secs = [run_reference_binary(path, cores) for _ in range(a.steps)]
+        total = sum(secs)
+        v = U * a.steps / total
+        sample = f"first cluster only: {sample_n} genomes x {a.genome_kmers / 1e6:g} Mbp, U={U:.4g} per step"
+        print(json.dumps({
+            "impl": "reference", "metric": "k-mer-pair updates/sec on all2all", "value": v, "unit": "updates/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "sample": sample, "threads": cores},
+            "cpu_baseline": {"value": v, "unit": "updates/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": v, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    import numpy as np
+    import torch
+    import kdbx
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    trie, db_path = get_workload(kdbx, a, a.samples, a.clusters, pinned=True, rank=rank, barrier=barrier if world > 1 else None)
+    tot = trie.totals()
+    N, P, U_total = int(tot.num_samples), int(tot.num_patterns), int(tot.updates)
+    ctx = kdbx.Context(device=local_rank, chunk_ids=a.chunk_ids, tile_cols=a.tile_cols, unit_updates=a.unit_updates)
+    ctx.load_patterns(trie)
+    upd = ctx.row_updates()
+    assert int(upd.sum()) == U_total, "device row-update counts disagree with U of the trie"
+    bounds = kdbx.shard_rows_by_work(upd, world)
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    U_rank = int(upd[r0:r1].sum())
+    cells = kdbx.tri_cells(r1) - kdbx.tri_cells(r0)
+    d_out = torch.zeros(max(1, cells), dtype=torch.int32, device="cuda")
+
+    # ---- device-resident leg -------------------------------------------------------------
+    for _ in range(a.warmup):
+        st = ctx.all2all_dense_rows_device(r0, r1, d_out.data_ptr())
+    assert st.updates == U_rank
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    wall0 = time.perf_counter()
+    dev_ms = scat_ms = 0.0
+    launches = scat_launches = 0
+    stage = {"prepare": 0.0, "expand": 0.0, "bucket": 0.0, "scatter": 0.0}
+    for _ in range(a.steps):
+        st = ctx.all2all_dense_rows_device(r0, r1, d_out.data_ptr())
+        dev_ms += st.ms_total
+        scat_ms += st.ms_scatter
+        launches += st.kernel_launches
+        scat_launches += st.scatter_launches
+        for k in stage:
+            stage[k] += getattr(st, "ms_" + k)
+    barrier()
+    wall_ms = (time.perf_counter() - wall0) * 1e3
+    clocks = sampler.stop() if sampler else None
+    T_ms = max_over_ranks(dev_ms)
+    value = U_total * a.steps / (T_ms / 1e3)
+    checksum = int(d_out[:cells].to(torch.int64).sum().item()) if cells else 0
+
+    # ---- end-to-end leg: host trie -> H2D -> compute -> D2H host matrix ----------------------
+    e2e = None
+    if not a.no_e2e:
+        out_host = kdbx.pinned_empty(max(1, cells), np.uint32)
+        ctx.load_patterns(trie)
+        ctx.all2all_dense_rows(r0, r1, out_host[:cells])
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            ctx.load_patterns(trie)
+            _, st2 = ctx.all2all_dense_rows(r0, r1, out_host[:cells])
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        assert int(out_host[:cells].astype(np.int64).sum()) == checksum, "e2e result differs from the device-resident result"
+        h2d = P * 40 + int(tot.payload_bytes)
+        e2e = {"value": U_total * a.steps / e2e_s, "unit": "updates/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": cells * 4, "ms_per_step": 1e3 * e2e_s / a.steps,
+               "ms_upload": st2.ms_upload, "ms_download": st2.ms_download}
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_hbm_peak()
+    achieved = ALGO_BYTES_PER_UPDATE * U_rank * a.steps / (scat_ms / 1e3) / 1e9 if scat_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_scatter_add", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
+                "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE,
+                "updates_per_launch": U_rank / max(1, scat_launches / a.steps),
+                "avg_launch_ms": scat_ms / max(1, scat_launches), "launches_per_step": scat_launches // max(1, a.steps),
+                "kernel_share_of_step": scat_ms / dev_ms if dev_ms else None}
+
+    cpu_baseline = None
+    if world == 1 and not a.no_cpu_baseline:
+        try:
+            sub = trie.prefix(sample_n)
+            sub_path = cache_path(a, sample_n, 1)
+            if not sub_path.exists():
+                sub.write_db(sub_path)
+            U_s = int(sub.totals().updates)
+            secs = run_reference_binary(sub_path, cores)
+            cpu_baseline = {"value": U_s / secs, "unit": "updates/s", "cores": cores, "kind": "reference",
+                            "sample": f"first cluster only: {sample_n} genomes x {a.genome_kmers / 1e6:g} Mbp, "
+                                      f"U={U_s:.4g}, {secs:.2f} s, kmer-db 2.3.1 all2all -t {cores}"}
+        except Exception as e:  # the baseline is a reported number, not a dependency of the GPU path
+            cpu_baseline = {"value": None, "unit": "updates/s", "cores": cores, "kind": "reference", "sample": f"failed: {e}"}
+
+    print(json.dumps({
+        "metric": "k-mer-pair updates/sec on all2all", "value": value, "unit": "updates/s", "n_gpus": world,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": T_ms / a.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "num_samples": N, "num_patterns": P, "updates_per_step": U_total,
+                   "sum_n": int(tot.sum_n), "sum_l": int(tot.sum_l), "parallelism": f"row-block x{world}",
+                   "l2_policy": "inputs (trie %.1f GB + per-chunk lists) exceed the 126 MB L2; no explicit flush" %
+                                ((P * 40 + int(tot.payload_bytes)) / 1e9),
+                   "chunk_ids": a.chunk_ids, "tile_cols": a.tile_cols, "unit_updates": a.unit_updates},
+        "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "stage_ms_per_step": {k: v / a.steps for k, v in stage.items()}, "wall_ms_per_step": wall_ms / a.steps,
+        "result_checksum": checksum,
+    }))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

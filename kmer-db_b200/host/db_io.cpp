@@ -89,6 +89,17 @@ void read_db(const std::string& path, Trie& t) {
     t.num_kmers.resize(P); t.parent_id.resize(P); t.n.resize(P); t.l.resize(P);
     t.last.resize(P); t.bits.resize(P); t.payload_off.resize(P);
     t.payload.clear();
+    {   // everything left in the file is pattern blocks: an upper bound for the payload, so that
+        // (possibly page-locked) storage is allocated once
+        const off_t here = ftello(in.f);
+        if (fseeko(in.f, 0, SEEK_END) == 0) {
+            const off_t end = ftello(in.f);
+            const uint64_t rest = end > here ? (uint64_t)(end - here) : 0;
+            const uint64_t headers = P * kPatternHeaderBytes;
+            if (rest > headers) t.payload.reserve((rest - headers) / 8 + 2);
+        }
+        fseeko(in.f, here, SEEK_SET);
+    }
 
     std::unique_ptr<char[]> block(new char[kIoBlockBytes]);
     uint64_t pid = 0;

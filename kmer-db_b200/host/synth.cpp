@@ -83,48 +83,74 @@ struct ClusterSim {
         last[q] = sid; ++n[q]; ++l[q];
     }
 
-    // Replace every run of a genome by its current leaves (in genomic order).
-    void refine(std::vector<uint32_t>& g, std::vector<uint32_t>& scratch, std::vector<uint32_t>& stack) {
-        scratch.clear();
-        for (uint32_t r : g) {
-            if (run_child[r] == kLeaf) { scratch.push_back(r); continue; }
-            stack.clear(); stack.push_back(r);
-            while (!stack.empty()) {
-                const uint32_t x = stack.back(); stack.pop_back();
-                if (run_child[x] == kLeaf) { scratch.push_back(x); continue; }
-                for (uint32_t c = run_nchild[x]; c-- > 0;) stack.push_back(run_child[x] + c);
-            }
-        }
-        g.swap(scratch);
+    unsigned team = 1;  // threads working on this cluster
+
+    // f(tid, begin, end) over [0,n) in `team` contiguous slices (slice t on thread t)
+    template <class F>
+    void par_for(size_t n, F&& f) const {
+        if (team <= 1 || n < 8192) { f(0u, (size_t)0, n); return; }
+        const size_t per = (n + team - 1) / team;
+        std::vector<std::thread> th;
+        th.reserve(team);
+        for (unsigned t = 0; t < team; ++t)
+            th.emplace_back([&f, t, per, n]() { const size_t b = std::min(n, t * per); f(t, b, std::min(n, b + per)); });
+        for (auto& x : th) x.join();
     }
+
+    // Replace every run of a genome by its current leaves (in genomic order).
+    void refine(std::vector<uint32_t>& g) {
+        std::vector<std::vector<uint32_t>> part(team);
+        par_for(g.size(), [&](unsigned tid, size_t b, size_t e) {
+            std::vector<uint32_t>& out = part[tid];
+            std::vector<uint32_t> stack;
+            out.reserve((e - b) + (e - b) / 8);
+            for (size_t i = b; i < e; ++i) {
+                const uint32_t r = g[i];
+                if (run_child[r] == kLeaf) { out.push_back(r); continue; }
+                stack.clear(); stack.push_back(r);
+                while (!stack.empty()) {
+                    const uint32_t x = stack.back(); stack.pop_back();
+                    if (run_child[x] == kLeaf) { out.push_back(x); continue; }
+                    for (uint32_t c = run_nchild[x]; c-- > 0;) stack.push_back(run_child[x] + c);
+                }
+            }
+        });
+        size_t total = 0;
+        for (auto& v : part) total += v.size();
+        g.clear(); g.reserve(total);
+        for (auto& v : part) g.insert(g.end(), v.begin(), v.end());
+    }
+
+    struct CutOut {  // what one slice of the cut phase produces
+        std::vector<uint32_t> list;      // run ids; new runs as kNewFlag | local index
+        std::vector<uint32_t> new_len;
+        std::vector<int32_t> new_pat;
+        std::vector<uint32_t> split_run, split_first, split_cnt;  // cut leaves and their children (local indices)
+        uint64_t len_sum = 0;
+    };
+    static constexpr uint32_t kNewFlag = 0x80000000u;
 
     void run(const SynthParams& sp, const std::vector<uint32_t>& sids, uint64_t seed) {
         Rng rng(seed);
         const uint64_t L = sp.genome_kmers;
         const uint32_t k = sp.k;
         genomes.resize(sids.size());
-        std::vector<uint32_t> scratch, stack, touched;
+        std::vector<uint32_t> touched;
         std::vector<uint32_t> cnt;       // k-mers of the current sample per pattern
         std::vector<int32_t> remap;
         std::vector<std::pair<uint64_t, uint64_t>> dead;  // destroyed k-mer intervals [s,e)
         const double log1m = std::log1p(-sp.mutation_rate);
+        const int32_t root_marker = -2;  // leaves that are novel in this sample
 
         for (size_t m = 0; m < sids.size(); ++m) {
             const uint32_t sid = sids[m];
             std::vector<uint32_t>& gi = genomes[m];
             uint64_t novel = 0;
-            const int32_t root_marker = -2;  // leaves that are novel in this sample
             if (m == 0) {
-                uint64_t left = L;
-                while (left) {  // run lengths are 32-bit
-                    const uint32_t len = (uint32_t)std::min<uint64_t>(left, 0x7FFFFFFFu);
-                    gi.push_back(new_run(len, root_marker));
-                    left -= len;
-                }
                 novel = L;
             } else {
                 const size_t j = (size_t)rng.below(m);
-                refine(genomes[j], scratch, stack);
+                refine(genomes[j]);
                 const std::vector<uint32_t>& gj = genomes[j];
                 // destroyed k-mer intervals from substitution positions (base coordinates)
                 dead.clear();
@@ -142,68 +168,112 @@ struct ClusterSim {
                     ++b;
                 }
                 // walk the leaves of genome j, cutting those a destroyed interval overlaps
-                gi.reserve(gj.size() + 2 * dead.size());
-                size_t di = 0;
-                uint64_t pos = 0;
-                for (size_t idx = 0; idx < gj.size(); ++idx) {
-                    const uint32_t r = gj[idx];
-                    const uint64_t len = run_len[r], end = pos + len;
-                    while (di < dead.size() && dead[di].second <= pos) ++di;
-                    if (di == dead.size() || dead[di].first >= end) {  // untouched leaf
-                        gi.push_back(r); pos = end; continue;
-                    }
-                    // pieces: alternate kept / destroyed inside [pos,end)
-                    const uint32_t first_child = (uint32_t)run_len.size();
-                    uint32_t nchild = 0;
-                    uint64_t cur = pos;
-                    size_t d = di;
-                    const int32_t pat = run_pat[r];
-                    while (cur < end) {
-                        if (d < dead.size() && dead[d].first < end) {
-                            const uint64_t ds = std::max(dead[d].first, cur), de = std::min(dead[d].second, end);
-                            if (ds > cur) {  // kept piece
-                                gi.push_back(new_run((uint32_t)(ds - cur), pat)); ++nchild;
+                std::vector<CutOut> outs(team);
+                par_for(gj.size(), [&](unsigned tid, size_t b0, size_t e0) {  // slice lengths
+                    uint64_t sum = 0;
+                    for (size_t i = b0; i < e0; ++i) sum += run_len[gj[i]];
+                    outs[tid].len_sum = sum;
+                });
+                std::vector<uint64_t> start(team + 1, 0);
+                for (unsigned t = 0; t < team; ++t) start[t + 1] = start[t] + outs[t].len_sum;
+                par_for(gj.size(), [&](unsigned tid, size_t b0, size_t e0) {
+                    CutOut& o = outs[tid];
+                    o.list.reserve((e0 - b0) + (e0 - b0) / 4);
+                    uint64_t pos = start[tid];
+                    size_t di = (size_t)(std::lower_bound(dead.begin(), dead.end(), pos,
+                                                          [](const std::pair<uint64_t, uint64_t>& iv, uint64_t p) { return iv.second <= p; }) -
+                                         dead.begin());
+                    auto add_run = [&](uint32_t len, int32_t pat) {
+                        o.new_len.push_back(len); o.new_pat.push_back(pat);
+                        return (uint32_t)o.new_len.size() - 1;
+                    };
+                    for (size_t idx = b0; idx < e0; ++idx) {
+                        const uint32_t r = gj[idx];
+                        const uint64_t len = run_len[r], end = pos + len;
+                        while (di < dead.size() && dead[di].second <= pos) ++di;
+                        if (di == dead.size() || dead[di].first >= end) {  // untouched leaf
+                            o.list.push_back(r); pos = end; continue;
+                        }
+                        // pieces: alternate kept / destroyed inside [pos,end); children contiguous
+                        const uint32_t first_child = (uint32_t)o.new_len.size();
+                        uint32_t nchild = 0;
+                        uint64_t cur = pos;
+                        size_t d = di;
+                        const int32_t pat = run_pat[r];
+                        while (cur < end) {
+                            if (d < dead.size() && dead[d].first < end) {
+                                const uint64_t ds = std::max(dead[d].first, cur), de = std::min(dead[d].second, end);
+                                if (ds > cur) { o.list.push_back(kNewFlag | add_run((uint32_t)(ds - cur), pat)); ++nchild; }  // kept
+                                add_run((uint32_t)(de - ds), pat); ++nchild;  // destroyed here, lives on elsewhere
+                                cur = de;
+                                if (dead[d].second <= end) ++d; else break;
+                            } else {
+                                o.list.push_back(kNewFlag | add_run((uint32_t)(end - cur), pat)); ++nchild;
+                                cur = end;
                             }
-                            new_run((uint32_t)(de - ds), pat); ++nchild;  // destroyed here, lives on elsewhere
-                            // children must stay contiguous: the novel run is created after the loop
-                            cur = de;
-                            if (dead[d].second <= end) ++d; else break;
-                        } else {
-                            gi.push_back(new_run((uint32_t)(end - cur), pat)); ++nchild;
-                            cur = end;
+                        }
+                        o.split_run.push_back(r); o.split_first.push_back(first_child); o.split_cnt.push_back(nchild);
+                        pos = end;
+                    }
+                });
+                // append the new runs slice by slice (== serial order), then patch ids
+                std::vector<uint32_t> base(team + 1, (uint32_t)run_len.size());
+                size_t list_total = 0;
+                std::vector<size_t> list_at(team + 1, 0);
+                for (unsigned t = 0; t < team; ++t) {
+                    base[t + 1] = base[t] + (uint32_t)outs[t].new_len.size();
+                    list_at[t + 1] = list_at[t] + outs[t].list.size();
+                }
+                list_total = list_at[team];
+                const size_t nruns = base[team];
+                run_len.resize(nruns); run_pat.resize(nruns); run_child.resize(nruns, kLeaf); run_nchild.resize(nruns, 0);
+                gi.resize(list_total);
+                par_for(team, [&](unsigned, size_t tb, size_t te) {
+                    for (size_t t = tb; t < te; ++t) {
+                        const CutOut& o = outs[t];
+                        std::copy(o.new_len.begin(), o.new_len.end(), run_len.begin() + base[t]);
+                        std::copy(o.new_pat.begin(), o.new_pat.end(), run_pat.begin() + base[t]);
+                        for (size_t i = 0; i < o.list.size(); ++i) {
+                            const uint32_t v = o.list[i];
+                            gi[list_at[t] + i] = (v & kNewFlag) ? base[t] + (v & ~kNewFlag) : v;
+                        }
+                        for (size_t i = 0; i < o.split_run.size(); ++i) {
+                            run_child[o.split_run[i]] = base[t] + o.split_first[i];
+                            run_nchild[o.split_run[i]] = o.split_cnt[i];
                         }
                     }
-                    run_child[r] = first_child; run_nchild[r] = nchild;
-                    pos = end;
-                }
-                // Novel k-mers replace every destroyed one (substitutions keep the length).
-                // They all share one pattern (this sample's root), so one run set suffices;
-                // position inside the genome does not matter to the build rule, append them.
-                uint64_t total_dead = 0;
-                for (auto& iv : dead) total_dead += iv.second - iv.first;
-                uint64_t left = total_dead;
-                while (left) {
-                    const uint32_t len = (uint32_t)std::min<uint64_t>(left, 0x7FFFFFFFu);
-                    gi.push_back(new_run(len, root_marker));
-                    left -= len;
-                }
-                novel = total_dead;
+                });
+                for (auto& iv : dead) novel += iv.second - iv.first;
+            }
+            // Novel k-mers (the whole first genome; afterwards one per destroyed k-mer, since
+            // substitutions keep the length).  They all share one pattern — this sample's root —
+            // and their position inside the genome does not matter to the build rule: append.
+            for (uint64_t left = novel; left;) {
+                const uint32_t len = (uint32_t)std::min<uint64_t>(left, 0x7FFFFFFFu);  // run lengths are 32-bit
+                gi.push_back(new_run(len, root_marker));
+                left -= len;
             }
 
             // ---- addKmers(sample sid): group by pattern, extend or split ----
-            if (cnt.size() < num_kmers.size() + 1) { cnt.resize(num_kmers.size() + 1024, 0); }
-            touched.clear();
-            for (uint32_t r : gi) {
-                const int32_t q = run_pat[r];
-                if (q < 0) continue;
-                if ((size_t)q >= cnt.size()) cnt.resize((size_t)q + 1024, 0);
-                if (cnt[q] == 0) touched.push_back((uint32_t)q);
-                cnt[q] += run_len[r];
+            if (cnt.size() < num_kmers.size() + 1) cnt.resize(num_kmers.size() + (num_kmers.size() >> 2) + 1024, 0);
+            {
+                std::vector<std::vector<uint32_t>> tl(team);
+                par_for(gi.size(), [&](unsigned tid, size_t b0, size_t e0) {
+                    for (size_t i = b0; i < e0; ++i) {
+                        const uint32_t r = gi[i];
+                        const int32_t q = run_pat[r];
+                        if (q < 0) continue;
+                        if (__atomic_fetch_add(&cnt[q], run_len[r], __ATOMIC_RELAXED) == 0) tl[tid].push_back((uint32_t)q);
+                    }
+                });
+                touched.clear();
+                for (auto& v : tl) touched.insert(touched.end(), v.begin(), v.end());
+                std::sort(touched.begin(), touched.end());  // pattern numbering independent of the team size
             }
             const size_t first_new = num_kmers.size();
             int32_t root = -1;
             if (novel) root = new_pattern((int64_t)novel, -1, 1, sid);
-            if (remap.size() < first_new) remap.resize(first_new + 1024, -1);
+            if (remap.size() < first_new) remap.resize(first_new + (first_new >> 2) + 1024, -1);
             for (uint32_t q : touched) {
                 const uint32_t c = cnt[q];
                 if ((int64_t)c == num_kmers[q] && !has_child[q]) {
@@ -215,10 +285,13 @@ struct ClusterSim {
                     remap[q] = r;
                 }
             }
-            for (uint32_t r : gi) {
-                const int32_t q = run_pat[r];
-                run_pat[r] = (q < 0) ? root : remap[q];
-            }
+            par_for(gi.size(), [&](unsigned, size_t b0, size_t e0) {
+                for (size_t i = b0; i < e0; ++i) {
+                    const uint32_t r = gi[i];
+                    const int32_t q = run_pat[r];
+                    run_pat[r] = (q < 0) ? root : remap[q];
+                }
+            });
             for (uint32_t q : touched) { cnt[q] = 0; remap[q] = -1; }
             novel_kmers += novel;
         }
@@ -248,12 +321,17 @@ void synth_generate(const SynthParams& sp_in, Trie& t) {
     }
     std::vector<ClusterSim> sims(C);
     {
-        unsigned nt = sp.threads > 0 ? (unsigned)sp.threads : std::max(1u, std::thread::hardware_concurrency());
-        nt = std::min<unsigned>(nt, C);
+        // clusters run side by side; spare cores form a team inside each cluster
+        const unsigned total = sp.threads > 0 ? (unsigned)sp.threads : std::max(1u, std::thread::hardware_concurrency());
+        const unsigned nt = std::min<unsigned>(total, C);
+        const unsigned team = std::max(1u, std::min(16u, total / nt));
         std::vector<std::thread> th;
         for (unsigned w = 0; w < nt; ++w)
             th.emplace_back([&, w]() {
-                for (uint32_t c = w; c < C; c += nt) sims[c].run(sp, members[c], sp.seed * 0x100000001B3ull + c + 1);
+                for (uint32_t c = w; c < C; c += nt) {
+                    sims[c].team = team;
+                    sims[c].run(sp, members[c], sp.seed * 0x100000001B3ull + c + 1);
+                }
             });
         for (auto& x : th) x.join();
     }

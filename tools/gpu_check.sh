@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# One gpurun call: GPU parity tests, microbenchmarks, a small and (optionally) the full bench.
+# Everything is logged under gpurun_out/<tag>/.
+set -u
+TAG="${1:-run}"; shift || true
+OUT="gpurun_out/$TAG"; mkdir -p "$OUT"
+{ nvidia-smi; nproc; free -g; } > "$OUT/box.txt" 2>&1
+for step in "$@"; do
+  case "$step" in
+    tests)  timeout 1500 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?" | tee -a "$OUT/summary.txt";;
+    tests_fast) timeout 900 python -m pytest tests -m gpu -x -q -k "not full_size" > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?" | tee -a "$OUT/summary.txt";;
+    micro)  timeout 300 kmer-db_b200/bin/microbench > "$OUT/microbench.txt" 2>&1; echo "micro rc=$?" | tee -a "$OUT/summary.txt";;
+    smoke)  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/smoke.log" 2>&1; echo "smoke rc=$?" | tee -a "$OUT/summary.txt";;
+    bench_small) timeout 600 python bench.py --samples 400 --genome-kmers 1000000 --steps 3 --warmup 2 > "$OUT/bench_small.json" 2> "$OUT/bench_small.err"; echo "bench_small rc=$?" | tee -a "$OUT/summary.txt";;
+    bench)  timeout 1500 python bench.py > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench rc=$?" | tee -a "$OUT/summary.txt";;
+    bench_ref) timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"; echo "bench_ref rc=$?" | tee -a "$OUT/summary.txt";;
+    *) echo "unknown step $step";;
+  esac
+done
+tail -n 30 "$OUT"/*.log "$OUT"/*.txt "$OUT"/*.json "$OUT"/*.err 2>/dev/null | tail -n 120
