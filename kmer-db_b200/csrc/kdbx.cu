@@ -6,7 +6,7 @@
 // sample id (:166-203, :244-280) and the row_add inner loop (src/simd/row_add_avx2.cpp:31-124).
 // Nothing here is a translation: the CPU code streams 8 MB cache blocks through four thread
 // pools; this file keeps the whole trie in HBM, expands full sample-id lists in L2-sized
-// chunks and runs the scatter-add on warp-private shared-memory accumulator tiles.
+// chunks and runs the scatter-add on CTA-shared shared-memory accumulator tiles.
 //
 // Pipeline of one kdbx_all2all_dense* call (all on one stream, two host syncs up front):
 //   prepare : scans of l / n / chunk cost (CUB), node packing, W accumulation, gamma decode
@@ -17,10 +17,9 @@
 //     scan         bucket offsets
 //     K_job_fill   counting-sort scatter of 16-byte job records
 //     K_units      split every bucket into work units of ~unit_updates updates
-//     K_scatter    THE hot kernel: a warp owns a (row, tile) accumulator in shared memory,
-//                  streams its jobs' id runs with coalesced loads, does conflict-free
-//                  LDS/IADD/STS (ids inside a run are distinct), then flushes the tile into
-//                  the packed triangle with red.global.add.u32
+//     K_scatter    THE hot kernel: a CTA owns a (row, tile) accumulator in shared memory, its
+//                  warps stream the jobs' id runs with coalesced loads and red.shared.add.u32,
+//                  then the tile is flushed into the packed triangle with red.global.add.u32
 // Integer adds commute, so any schedule gives the reference's bits (uint32 wrap included).
 #include <cuda_runtime.h>
 
@@ -214,23 +213,29 @@ __global__ void k_row_updates(uint64_t P, const Node* __restrict__ nodes, const 
 // ------------------------------------------------------------------------------------------
 
 // Full list of p = local lists of its ancestors (root first) followed by its own; node q's
-// locals land at positions [n_q - l_q, n_q).  One warp per pattern, walking the parent chain.
+// locals land at positions [n_q - l_q, n_q).  Eight lanes per pattern walk the parent chain
+// (most chain steps copy only a few ids, so a full warp per pattern would idle and — worse —
+// keep only one pointer chase in flight); the parent's node is requested before the copy.
+constexpr uint32_t kExpandLanes = 8;
 __global__ void k_expand(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
                          const uint32_t* __restrict__ loc, uint32_t* __restrict__ flat) {
-    const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t gid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kExpandLanes;
+    const uint64_t ng = ((uint64_t)gridDim.x * blockDim.x) / kExpandLanes;
+    const uint32_t sub = threadIdx.x & (kExpandLanes - 1);
     const uint64_t base0 = noff[p0];
-    for (uint64_t p = p0 + gw; p < p1; p += nw) {
+    for (uint64_t p = p0 + gid; p < p1; p += ng) {
         Node nd = nodes[p];
         if (nd.n == 0) continue;
         uint32_t* dst = flat + (noff[p] - base0);
         for (;;) {
+            Node up; up.parent = -1; up.n = 0; up.l = 0; up.last = 0; up.loff = 0; up.pad = 0;
+            const bool more = nd.parent >= 0;
+            if (more) up = nodes[nd.parent];
             const uint32_t* src = loc + nd.loff;
             const uint32_t at = nd.n - nd.l;
-            for (uint32_t j = lane; j < nd.l; j += 32) dst[at + j] = src[j];
-            if (nd.parent < 0) break;
-            nd = nodes[nd.parent];
+            for (uint32_t j = sub; j < nd.l; j += kExpandLanes) dst[at + j] = src[j];
+            if (!more) break;
+            nd = up;
         }
     }
 }
@@ -280,6 +285,109 @@ __device__ __forceinline__ void for_each_job(const Node& nd, uint32_t base, cons
     }
 }
 
+// ---- job bucketing, small key spaces: block-private histograms in shared memory ------------
+// With N*T <= kSmemKeys every block counts its contiguous slice of patterns into shared memory
+// and publishes one row of blockhist[block][key]; a per-key column scan then gives every
+// (block, key) pair its exact slot range, so the fill pass needs no global atomics at all.
+constexpr uint32_t kSmemKeys = 2048;
+constexpr int kBucketThreads = 256;
+
+__device__ __forceinline__ void block_slice(uint64_t p0, uint64_t p1, uint64_t& lo, uint64_t& hi) {
+    const uint64_t per = (p1 - p0 + gridDim.x - 1) / gridDim.x;
+    lo = p0 + (uint64_t)blockIdx.x * per;
+    hi = lo + per < p1 ? lo + per : p1;
+    if (lo > p1) lo = p1;
+}
+
+__global__ void __launch_bounds__(kBucketThreads)
+k_job_hist_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
+                const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T, uint32_t tile_cols,
+                uint32_t row_begin, uint32_t row_end, uint32_t nkeys, uint32_t* __restrict__ blockhist,
+                unsigned long long* __restrict__ work, unsigned long long* __restrict__ total_updates) {
+    __shared__ uint32_t s_hist[kSmemKeys];
+    __shared__ unsigned long long s_work[kSmemKeys];
+    for (uint32_t k = threadIdx.x; k < nkeys; k += blockDim.x) { s_hist[k] = 0; s_work[k] = 0; }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint64_t base0 = noff[p0];
+    uint64_t lo, hi;
+    block_slice(p0, p1, lo, hi);
+    unsigned long long updates = 0;
+    for (uint64_t p = lo + warp; p < hi; p += nwarps) {
+        const Node nd = nodes[p];
+        if (nd.l == 0) continue;
+        const bool weightless = W[p] == 0;
+        const uint32_t base = (uint32_t)(noff[p] - base0);
+        for_each_job(nd, base, flat, T, tile_cols, row_begin, row_end, lane, updates,
+                     [&](uint32_t key, uint32_t, uint32_t len) {
+                         if (weightless) return;
+                         atomicAdd(&s_hist[key], 1u);
+                         atomicAdd(&s_work[key], (unsigned long long)len);
+                     });
+    }
+    for (int o = 16; o; o >>= 1) updates += __shfl_xor_sync(0xffffffffu, updates, o);
+    if (lane == 0 && updates) atomicAdd(total_updates, updates);
+    __syncthreads();
+    uint32_t* out = blockhist + (size_t)blockIdx.x * nkeys;
+    for (uint32_t k = threadIdx.x; k < nkeys; k += blockDim.x) {
+        out[k] = s_hist[k];
+        if (s_work[k]) atomicAdd(&work[k], s_work[k]);
+    }
+}
+
+// hist[key] = sum over blocks (column sums of blockhist)
+__global__ void k_key_totals(uint32_t nkeys, uint32_t nblocks, const uint32_t* __restrict__ blockhist, uint32_t* __restrict__ hist) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > nkeys) return;
+    uint32_t sum = 0;
+    if (k < nkeys)
+        for (uint32_t b = 0; b < nblocks; ++b) sum += blockhist[(size_t)b * nkeys + k];
+    hist[k] = sum;
+}
+
+// blockhist[b][key] := bucket_off[key] + sum_{b' < b} blockhist[b'][key]   (first slot of the pair)
+__global__ void k_block_offsets(uint32_t nkeys, uint32_t nblocks, const uint32_t* __restrict__ bucket_off,
+                                uint32_t* __restrict__ blockhist) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nkeys) return;
+    uint32_t run = bucket_off[k];
+    for (uint32_t b = 0; b < nblocks; ++b) {
+        const uint32_t c = blockhist[(size_t)b * nkeys + k];
+        blockhist[(size_t)b * nkeys + k] = run;
+        run += c;
+    }
+}
+
+__global__ void __launch_bounds__(kBucketThreads)
+k_job_fill_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
+                const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T, uint32_t tile_cols,
+                uint32_t row_begin, uint32_t row_end, uint32_t nkeys, const uint32_t* __restrict__ blockbase,
+                Job* __restrict__ jobs) {
+    __shared__ uint32_t s_next[kSmemKeys];
+    const uint32_t* mine = blockbase + (size_t)blockIdx.x * nkeys;
+    for (uint32_t k = threadIdx.x; k < nkeys; k += blockDim.x) s_next[k] = mine[k];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint64_t base0 = noff[p0];
+    uint64_t lo, hi;
+    block_slice(p0, p1, lo, hi);
+    unsigned long long updates = 0;
+    for (uint64_t p = lo + warp; p < hi; p += nwarps) {
+        const Node nd = nodes[p];
+        if (nd.l == 0) continue;
+        const uint32_t w = W[p];
+        if (w == 0) continue;
+        const uint32_t base = (uint32_t)(noff[p] - base0);
+        for_each_job(nd, base, flat, T, tile_cols, row_begin, row_end, lane, updates,
+                     [&](uint32_t key, uint32_t off, uint32_t len) {
+                         const uint32_t slot = atomicAdd(&s_next[key], 1u);
+                         Job jb; jb.off = off; jb.len = len; jb.w = w; jb.pad = 0;
+                         jobs[slot] = jb;
+                     });
+    }
+}
+
+// ---- job bucketing, large key spaces: global atomics (contention is low when keys are many) --
 __global__ void k_job_hist(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
                            const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T,
                            uint32_t tile_cols, uint32_t row_begin, uint32_t row_end, uint32_t* __restrict__ hist,
@@ -361,32 +469,39 @@ __global__ void k_unit_fill(uint32_t nkeys, const uint32_t* __restrict__ hist, c
     }
 }
 
-// THE hot kernel.  Persistent warps pull work units from a global counter.  For its unit a
-// warp zeroes a private tile of `tile_cols` uint32 accumulators in shared memory, then for
-// every job adds w to tile[id - col0] for the ids of the job's run.  Ids inside one run are
-// distinct, so a warp-wide LDS / IADD / STS never collides with itself; runs of different
-// jobs are separated by __syncwarp().  Finally the tile is added into the packed
-// lower-triangular matrix (src/array.h:140) with red.global.add.u32.
+// THE hot kernel.  Persistent CTAs pull work units (one (row, column tile) key and a range of
+// its jobs) from a global counter.  The CTA zeroes a tile of `tile_cols` uint32 accumulators in
+// shared memory; its warps then grab batches of 32 jobs and, for every job, stream the job's
+// run of sample ids with coalesced 128-byte loads and do red.shared.add.u32 tile[id - col0] += w
+// (measured on B200: shared-memory reductions keep up with an id stream at full HBM bandwidth,
+// profiles/r01_microbench_atomics.txt — faster than LDS/IADD/STS on warp-private tiles).
+// Finally the tile is added into the packed lower-triangular matrix (src/array.h:140) with
+// red.global.add.u32, skipping zero cells.
 __global__ void __launch_bounds__(kScatterThreads)
 k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_units_ptr, const Job* __restrict__ jobs,
               const uint32_t* __restrict__ flat, uint32_t* __restrict__ tri, uint64_t tri_base, uint32_t T,
               uint32_t tile_cols, uint32_t* __restrict__ unit_counter) {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ uint32_t tile[];
+    __shared__ uint32_t s_unit, s_next_job;
     const uint32_t lane = threadIdx.x & 31;
-    uint32_t* tile = smem + (threadIdx.x >> 5) * tile_cols;
     const uint32_t n_units = *n_units_ptr;
     for (;;) {
-        uint32_t u = 0;
-        if (lane == 0) u = atomicAdd(unit_counter, 1u);
-        u = __shfl_sync(0xffffffffu, u, 0);
+        if (threadIdx.x == 0) s_unit = atomicAdd(unit_counter, 1u);
+        __syncthreads();
+        const uint32_t u = s_unit;
         if (u >= n_units) break;
         const Unit un = units[u];
         const uint32_t row = un.key / T, t = un.key - row * T;
         const uint32_t col0 = t * tile_cols;
         const uint32_t ncols = min(tile_cols, row - col0);  // only columns < row exist
-        for (uint32_t c = lane; c < ncols; c += 32) tile[c] = 0;
-        __syncwarp();
-        for (uint32_t jb = un.job_begin; jb < un.job_end; jb += 32) {
+        for (uint32_t c = threadIdx.x; c < ncols; c += kScatterThreads) tile[c] = 0;
+        if (threadIdx.x == 0) s_next_job = un.job_begin;
+        __syncthreads();
+        for (;;) {
+            uint32_t jb = 0;
+            if (lane == 0) jb = atomicAdd(&s_next_job, 32u);
+            jb = __shfl_sync(0xffffffffu, jb, 0);
+            if (jb >= un.job_end) break;
             const uint32_t cnt = min(32u, un.job_end - jb);
             Job mine; mine.off = 0; mine.len = 0; mine.w = 0; mine.pad = 0;
             if (lane < cnt) mine = jobs[jb + lane];
@@ -396,26 +511,21 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
                 const uint32_t w = __shfl_sync(0xffffffffu, mine.w, j);
                 const uint32_t* __restrict__ ids = flat + off;
                 uint32_t k = lane;
-                // 4 independent loads in flight per lane; all ids of a run are distinct
-                for (; k + 96 < len; k += 128) {
-                    const uint32_t i0 = ids[k] - col0, i1 = ids[k + 32] - col0;
-                    const uint32_t i2 = ids[k + 64] - col0, i3 = ids[k + 96] - col0;
-                    const uint32_t v0 = tile[i0], v1 = tile[i1], v2 = tile[i2], v3 = tile[i3];
-                    tile[i0] = v0 + w; tile[i1] = v1 + w; tile[i2] = v2 + w; tile[i3] = v3 + w;
+                for (; k + 96 < len; k += 128) {  // 4 independent coalesced loads in flight per lane
+                    const uint32_t i0 = ids[k], i1 = ids[k + 32], i2 = ids[k + 64], i3 = ids[k + 96];
+                    atomicAdd(&tile[i0 - col0], w); atomicAdd(&tile[i1 - col0], w);
+                    atomicAdd(&tile[i2 - col0], w); atomicAdd(&tile[i3 - col0], w);
                 }
-                for (; k < len; k += 32) {
-                    const uint32_t i0 = ids[k] - col0;
-                    tile[i0] += w;
-                }
-                __syncwarp();
+                for (; k < len; k += 32) atomicAdd(&tile[ids[k] - col0], w);
             }
         }
+        __syncthreads();
         const uint64_t out0 = tri_offset(row) - tri_base + col0;
-        for (uint32_t c = lane; c < ncols; c += 32) {
+        for (uint32_t c = threadIdx.x; c < ncols; c += kScatterThreads) {
             const uint32_t v = tile[c];
             if (v) atomicAdd(&tri[out0 + c], v);
         }
-        __syncwarp();
+        __syncthreads();
     }
 }
 
@@ -460,7 +570,7 @@ struct kdbx_ctx {
     // prepared
     DevBuf nodes, W, loc, loff, noff, coff, bounds, err_flag, cub_tmp;
     // per chunk
-    DevBuf flat, jobs, hist, work, bucket_off, cursor, ucount, uoff, units, counters;
+    DevBuf flat, jobs, hist, work, bucket_off, cursor, ucount, uoff, units, counters, blockhist;
     DevBuf tri, rowupd;
     uint64_t sum_l = 0, sum_n = 0;
 
@@ -517,16 +627,17 @@ struct Plan {
 int make_plan(kdbx_ctx* ctx, Plan& pl) {
     const uint32_t N = ctx->N;
     uint32_t tc = ctx->cfg.tile_cols;
-    if (tc == 0) tc = N <= 1024 ? 1024 : 2048;
+    // default: a whole row per CTA tile while 7-8 CTAs still fit an SM (7168 cols = 28 KB)
+    if (tc == 0) tc = std::min<uint32_t>(7168u, std::max<uint32_t>(32u, (N + 31u) & ~31u));
     if (tc < 32 || (tc & 31)) return ctx->fail(KDBX_ERR_ARG, "tile_cols must be a multiple of 32");
-    if ((size_t)tc * 4 * kWarpsPerBlock > 227 * 1024) return ctx->fail(KDBX_ERR_ARG, "tile_cols too large for shared memory");
+    if ((size_t)tc * 4 > 200 * 1024) return ctx->fail(KDBX_ERR_ARG, "tile_cols too large for shared memory");
     const uint32_t T = N == 0 ? 1 : (N + tc - 1) / tc;
     if (T > kMaxTiles)
         return ctx->fail(KDBX_ERR_ARG, "dense all2all supports at most %u samples with tile_cols=%u (got %u)",
                          kMaxTiles * tc, tc, N);
     pl.tile_cols = tc; pl.T = T;
-    pl.unit_updates = ctx->cfg.unit_updates ? ctx->cfg.unit_updates : 32768u;
-    pl.chunk = ctx->cfg.chunk_ids ? ctx->cfg.chunk_ids : ((uint64_t)12 << 20);
+    pl.unit_updates = ctx->cfg.unit_updates ? ctx->cfg.unit_updates : 131072u;
+    pl.chunk = ctx->cfg.chunk_ids ? ctx->cfg.chunk_ids : ((uint64_t)64 << 20);
     if (pl.chunk < 4096) pl.chunk = 4096;
     if (pl.chunk > ((uint64_t)1 << 31)) pl.chunk = (uint64_t)1 << 31;
     return KDBX_OK;
@@ -624,6 +735,13 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     s.ms_prepare = elapsed(ev_start, ev_prepared);
 
     const uint32_t nkeys = ctx->N * pl.T;
+    if (cells == 0 || nkeys == 0) {  // N <= 1 or an empty row range: no cell exists
+        s.ms_total = s.ms_prepare;
+        s.flat_ids = ctx->sum_n; s.local_ids = ctx->sum_l; s.kernel_launches = launches;
+        if (int rc = check_device_error(ctx)) return rc;
+        if (stats) *stats = s;
+        return KDBX_OK;
+    }
     const uint64_t cap = pl.chunk + (uint64_t)ctx->N * (pl.T + 1) + 64;  // a chunk may overshoot by one pattern
     CK(ctx->flat.ensure(cap * 4)); CK(ctx->jobs.ensure(cap * sizeof(Job)));
     CK(ctx->hist.ensure(((size_t)nkeys + 1) * 4)); CK(ctx->work.ensure(((size_t)nkeys + 1) * 8));
@@ -635,13 +753,15 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     uint32_t* d_unit_counter = ctx->counters.as<uint32_t>() + 4;
     CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
 
-    const size_t smem = (size_t)pl.tile_cols * 4 * kWarpsPerBlock;
+    const size_t smem = (size_t)pl.tile_cols * 4;
     CK(cudaFuncSetAttribute(k_scatter_add, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks_per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_scatter_add, kScatterThreads, smem));
     if (blocks_per_sm < 1) return ctx->fail(KDBX_ERR_CUDA, "scatter kernel does not fit on an SM");
     const unsigned scatter_grid = (unsigned)(ctx->sm_count * blocks_per_sm);
     const unsigned wide_grid = (unsigned)(ctx->sm_count * 8);
+    const bool smem_buckets = nkeys <= kSmemKeys;
+    if (smem_buckets) CK(ctx->blockhist.ensure((size_t)wide_grid * nkeys * 4 + 16));
 
     struct ChunkEv { cudaEvent_t a, b, c, d; };
     std::vector<ChunkEv> cev;
@@ -653,16 +773,29 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         e.a = ctx->event();
         k_expand<<<wide_grid, 256, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->loc.as<uint32_t>(), ctx->flat.as<uint32_t>());
         e.b = ctx->event();
-        CK(cudaMemsetAsync(ctx->hist.p, 0, ((size_t)nkeys + 1) * 4, st));
         CK(cudaMemsetAsync(ctx->work.p, 0, ((size_t)nkeys + 1) * 8, st));
-        k_job_hist<<<wide_grid, 256, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                               ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, row_begin, row_end,
-                                               ctx->hist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates);
-        if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
-        CK(cudaMemcpyAsync(ctx->cursor.p, ctx->bucket_off.p, ((size_t)nkeys + 1) * 4, cudaMemcpyDeviceToDevice, st));
-        k_job_fill<<<wide_grid, 256, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                               ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, row_begin, row_end,
-                                               ctx->cursor.as<uint32_t>(), ctx->jobs.as<Job>());
+        if (smem_buckets) {
+            k_job_hist_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
+                                                                  ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, row_begin, row_end, nkeys,
+                                                                  ctx->blockhist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates);
+            k_key_totals<<<blocks_for((uint64_t)nkeys + 1, 128), 128, 0, st>>>(nkeys, wide_grid, ctx->blockhist.as<uint32_t>(), ctx->hist.as<uint32_t>());
+            if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
+            k_block_offsets<<<blocks_for(nkeys, 128), 128, 0, st>>>(nkeys, wide_grid, ctx->bucket_off.as<uint32_t>(), ctx->blockhist.as<uint32_t>());
+            k_job_fill_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
+                                                                  ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, row_begin, row_end, nkeys,
+                                                                  ctx->blockhist.as<uint32_t>(), ctx->jobs.as<Job>());
+            launches += 2;
+        } else {
+            CK(cudaMemsetAsync(ctx->hist.p, 0, ((size_t)nkeys + 1) * 4, st));
+            k_job_hist<<<wide_grid, 256, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
+                                                   ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, row_begin, row_end,
+                                                   ctx->hist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates);
+            if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
+            CK(cudaMemcpyAsync(ctx->cursor.p, ctx->bucket_off.p, ((size_t)nkeys + 1) * 4, cudaMemcpyDeviceToDevice, st));
+            k_job_fill<<<wide_grid, 256, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
+                                                   ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, row_begin, row_end,
+                                                   ctx->cursor.as<uint32_t>(), ctx->jobs.as<Job>());
+        }
         k_unit_count<<<blocks_for((uint64_t)nkeys + 1, 256), 256, 0, st>>>(nkeys, ctx->hist.as<uint32_t>(), ctx->work.as<unsigned long long>(),
                                                                             pl.unit_updates, ctx->ucount.as<uint32_t>());
         if (int rc = scan_exclusive_u32(ctx, ctx->ucount.as<uint32_t>(), ctx->uoff.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
@@ -758,7 +891,7 @@ void kdbx_close(kdbx_ctx* ctx) {
     for (DevBuf* b : {&ctx->num_kmers, &ctx->parent, &ctx->n, &ctx->l, &ctx->last, &ctx->bits, &ctx->poff, &ctx->payload,
                       &ctx->nodes, &ctx->W, &ctx->loc, &ctx->loff, &ctx->noff, &ctx->coff, &ctx->bounds, &ctx->err_flag,
                       &ctx->cub_tmp, &ctx->flat, &ctx->jobs, &ctx->hist, &ctx->work, &ctx->bucket_off, &ctx->cursor,
-                      &ctx->ucount, &ctx->uoff, &ctx->units, &ctx->counters, &ctx->tri, &ctx->rowupd})
+                      &ctx->ucount, &ctx->uoff, &ctx->units, &ctx->counters, &ctx->blockhist, &ctx->tri, &ctx->rowupd})
         b->release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

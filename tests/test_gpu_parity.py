@@ -178,12 +178,14 @@ def test_generated_db_matches_reference_binary(libs, ref_bin, tmp_path):
     assert ou.read_bytes(tmp_path / "gpu.csv") == ou.read_bytes(tmp_path / "ref.csv")
 
 
-def test_large_n_uses_column_tiles(libs, oracle):
-    """N > tile width: the (row, tile) decomposition with the default 2048-column tiles."""
+@pytest.mark.parametrize("tile_cols", [0, 2048])
+def test_large_n(libs, oracle, tile_cols):
+    """N = 5000: one 5024-column tile per row by default; 2048-column tiles force the
+    (row, tile) decomposition and the global-atomics bucketing path (15000 keys)."""
     t = libs.Trie.synth(num_samples=5000, num_clusters=10, genome_kmers=3000, seed=8, mutation_rate=0.01)
     N = t.num_samples
     want, U = ou.oracle_all2all(oracle, N, t.arrays())
-    with libs.Context(device=0) as c:
+    with libs.Context(device=0, tile_cols=tile_cols) as c:
         c.load_patterns(t)
         got, st = c.all2all_dense()
     assert st.updates == U
