@@ -244,7 +244,7 @@ def main():
     # ---- device-resident leg -------------------------------------------------------------
     for _ in range(a.warmup):
         st = ctx.all2all_dense_rows_device(r0, r1, d_out.data_ptr())
-    assert st.updates == U_rank
+        assert st.updates == U_rank
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     wall0 = time.perf_counter()
@@ -253,6 +253,7 @@ def main():
     stage = {"prepare": 0.0, "expand": 0.0, "bucket": 0.0, "scatter": 0.0}
     for _ in range(a.steps):
         st = ctx.all2all_dense_rows_device(r0, r1, d_out.data_ptr())
+        assert st.updates == U_rank
         dev_ms += st.ms_total
         scat_ms += st.ms_scatter
         launches += st.kernel_launches

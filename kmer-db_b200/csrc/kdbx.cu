@@ -30,6 +30,7 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -110,19 +111,31 @@ __global__ void k_build_nodes(uint64_t P, const int64_t* __restrict__ parent, co
     W[p] = (uint32_t)num_kmers[p];  // the reference adds (uint32_t)num_kmers (similarity_calculator.cpp:222)
 }
 
-// W_p = sum of num_kmers over p's subtree, mod 2^32 (reference: serial reverse sweep,
-// similarity_calculator.cpp:64-72).  Every node pushes its own count to all its ancestors.
-__global__ void k_accumulate_w(uint64_t P, const int64_t* __restrict__ num_kmers, const Node* __restrict__ nodes,
-                               uint32_t* __restrict__ W) {
+// W_p = sum of num_kmers over p's subtree, mod 2^32 (reference: serial reverse sweep over the
+// pattern array, similarity_calculator.cpp:64-72).  num_samples is a topological key: a child
+// has strictly more samples than its parent (n_child = n_parent + l_child, l_child >= 1), so
+// patterns are radix-sorted by n (descending) and every level pushes its finished sums to the
+// parents in one launch.  (A per-node walk to the root with atomics was 80 % of the prepare
+// stage: the ancestors near the roots are hit by millions of serialized L2 atomics.)
+__global__ void k_iota(uint64_t P, uint32_t* __restrict__ out) {
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
-    const uint32_t v = (uint32_t)num_kmers[p];
-    if (v == 0) return;
-    int32_t q = nodes[p].parent;
-    while (q >= 0) {
-        atomicAdd(&W[q], v);
-        q = nodes[q].parent;
-    }
+    if (p < P) out[p] = (uint32_t)p;
+}
+// level_start[v] = first index of key v in the descending-sorted key array
+__global__ void k_level_starts(uint64_t P, const uint32_t* __restrict__ keys, uint32_t* __restrict__ level_start) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    if (i == 0 || keys[i] != keys[i - 1]) level_start[keys[i]] = (uint32_t)i;
+}
+__global__ void k_push_level(uint32_t count, const uint32_t* __restrict__ order, const int64_t* __restrict__ parent,
+                             uint32_t* __restrict__ W) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t p = order[i];
+    const int64_t q = parent[p];
+    if (q < 0) return;
+    const uint32_t v = W[p];
+    if (v) atomicAdd(&W[q], v);
 }
 
 __device__ __forceinline__ uint32_t gamma_field(const uint64_t* __restrict__ w, uint32_t pos, uint32_t cnt) {
@@ -153,7 +166,10 @@ __device__ __forceinline__ uint32_t gamma_next(const uint64_t* __restrict__ w, u
     return 0;
 }
 
-// Decodes the LOCAL ids of every pattern into d_loc (ascending), one thread per pattern.
+// Decodes the LOCAL ids of every pattern into d_loc (ascending), one thread per pattern.  The
+// stream holds the deltas in append order and only the LAST id is stored (src/pattern.cpp:
+// 99-109), so the bits are walked twice — first to sum the deltas (registers only), then to
+// emit ids front to back — which writes every id exactly once and never reads d_loc back.
 __global__ void k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint32_t* __restrict__ bits,
                                 const uint64_t* __restrict__ poff, const uint64_t* __restrict__ payload,
                                 uint32_t* __restrict__ loc, uint32_t N, int* __restrict__ err) {
@@ -162,19 +178,22 @@ __global__ void k_decode_locals(uint64_t P, const Node* __restrict__ nodes, cons
     const Node nd = nodes[p];
     if (nd.l == 0) return;
     uint32_t* out = loc + nd.loff;
-    if (nd.l == 1) { out[0] = nd.last; if (nd.last >= N) atomicExch(err, 2); return; }
+    if (nd.last >= N) { atomicExch(err, 2); return; }
+    if (nd.l == 1) { out[0] = nd.last; return; }
     const uint64_t* w = payload + poff[p];
     const uint32_t nb = bits[p];
     uint32_t pos = 0;
-    for (uint32_t i = 0; i + 1 < nd.l; ++i) out[i] = gamma_next(w, pos, nb);
-    if (pos != nb) { atomicExch(err, 1); }
-    uint32_t cur = nd.last;
-    for (uint32_t i = nd.l; i-- > 0;) {
-        const uint32_t d = i > 0 ? out[i - 1] : 0u;
+    uint64_t sum = 0;
+    for (uint32_t i = 0; i + 1 < nd.l; ++i) sum += gamma_next(w, pos, nb);
+    if (pos != nb) { atomicExch(err, 1); return; }
+    if (sum > nd.last) { atomicExch(err, 2); return; }
+    uint32_t cur = nd.last - (uint32_t)sum;
+    out[0] = cur;
+    pos = 0;
+    for (uint32_t i = 1; i < nd.l; ++i) {
+        cur += gamma_next(w, pos, nb);
         out[i] = cur;
-        cur -= d;
     }
-    if (nd.last >= N || out[0] > nd.last) atomicExch(err, 2);
 }
 
 // smallest p with off[p] >= c * chunk  (off is the exclusive scan of the chunk cost, P+1 long)
@@ -192,9 +211,17 @@ __global__ void k_chunk_bounds(uint64_t P, const uint64_t* __restrict__ coff, ui
     bounds[c] = lo;
 }
 
-// per-row update counts (sum over jobs of the position i), for work-balanced row sharding
-__global__ void k_row_updates(uint64_t P, const Node* __restrict__ nodes, const uint32_t* __restrict__ loc,
+// per-row update counts (sum over jobs of the position i), for work-balanced row sharding;
+// block-private shared-memory accumulators when the rows fit (global atomics otherwise).
+constexpr uint32_t kRowUpdSmemRows = 4096;
+__global__ void k_row_updates(uint64_t P, uint32_t N, const Node* __restrict__ nodes, const uint32_t* __restrict__ loc,
                               unsigned long long* __restrict__ upd) {
+    __shared__ unsigned long long s_upd[kRowUpdSmemRows];
+    const bool priv = N <= kRowUpdSmemRows;
+    if (priv) {
+        for (uint32_t r = threadIdx.x; r < N; r += blockDim.x) s_upd[r] = 0;
+        __syncthreads();
+    }
     const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
@@ -203,8 +230,16 @@ __global__ void k_row_updates(uint64_t P, const Node* __restrict__ nodes, const 
         const uint32_t first = nd.n - nd.l;
         for (uint32_t j = lane; j < nd.l; j += 32) {
             const uint32_t i = first + j;
-            if (i) atomicAdd(&upd[loc[nd.loff + j]], (unsigned long long)i);
+            if (!i) continue;
+            const uint32_t row = loc[nd.loff + j];
+            if (priv) atomicAdd(&s_upd[row], (unsigned long long)i);
+            else atomicAdd(&upd[row], (unsigned long long)i);
         }
+    }
+    if (priv) {
+        __syncthreads();
+        for (uint32_t r = threadIdx.x; r < N; r += blockDim.x)
+            if (s_upd[r]) atomicAdd(&upd[r], s_upd[r]);
     }
 }
 
@@ -568,7 +603,8 @@ struct kdbx_ctx {
     float ms_upload = 0.f;
 
     // prepared
-    DevBuf nodes, W, loc, loff, noff, coff, bounds, err_flag, cub_tmp;
+    DevBuf nodes, W, loc, loff, noff, coff, bounds, err_flag, cub_tmp, order_in, order, keys_sorted, level_start;
+    std::vector<uint32_t> h_level_start;
     // per chunk
     DevBuf flat, jobs, hist, work, bucket_off, cursor, ucount, uoff, units, counters, blockhist;
     DevBuf tri, rowupd;
@@ -674,14 +710,51 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
     k_build_nodes<<<blocks_for(P, 256), 256, 0, st>>>(P, ctx->parent.as<int64_t>(), ctx->num_kmers.as<int64_t>(),
                                                        ctx->n.as<uint32_t>(), ctx->l.as<uint32_t>(), ctx->last.as<uint32_t>(),
                                                        ctx->loff.as<uint64_t>(), ctx->nodes.as<Node>(), ctx->W.as<uint32_t>());
-    k_accumulate_w<<<blocks_for(P, 256), 256, 0, st>>>(P, ctx->num_kmers.as<int64_t>(), ctx->nodes.as<Node>(), ctx->W.as<uint32_t>());
-    launches += 2;
+    launches += 1;
+    // order patterns by num_samples, descending (levels of the W accumulation)
+    const uint32_t N = ctx->N;
+    CK(ctx->order_in.ensure(P * 4)); CK(ctx->order.ensure(P * 4)); CK(ctx->keys_sorted.ensure(P * 4));
+    CK(ctx->level_start.ensure(((size_t)N + 2) * 4));
+    ctx->h_level_start.resize((size_t)N + 2);
+    {
+        int end_bit = 1;
+        while (end_bit < 32 && (N >> end_bit)) ++end_bit;
+        k_iota<<<blocks_for(P, 256), 256, 0, st>>>(P, ctx->order_in.as<uint32_t>());
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, ctx->n.as<uint32_t>(), ctx->keys_sorted.as<uint32_t>(),
+                                                     ctx->order_in.as<uint32_t>(), ctx->order.as<uint32_t>(), P, 0, end_bit, st));
+        CK(ctx->cub_tmp.ensure(tmp));
+        CK(cub::DeviceRadixSort::SortPairsDescending(ctx->cub_tmp.p, tmp, ctx->n.as<uint32_t>(), ctx->keys_sorted.as<uint32_t>(),
+                                                     ctx->order_in.as<uint32_t>(), ctx->order.as<uint32_t>(), P, 0, end_bit, st));
+        CK(cudaMemsetAsync(ctx->level_start.p, 0xFF, ((size_t)N + 2) * 4, st));
+        k_level_starts<<<blocks_for(P, 256), 256, 0, st>>>(P, ctx->keys_sorted.as<uint32_t>(), ctx->level_start.as<uint32_t>());
+        launches += 4;
+    }
     uint64_t sums[3] = {0, 0, 0};
     CK(cudaMemcpyAsync(&sums[0], ctx->loff.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&sums[1], ctx->noff.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&sums[2], ctx->coff.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->h_level_start.data(), ctx->level_start.p, ((size_t)N + 2) * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     ctx->sum_l = sums[0]; ctx->sum_n = sums[1];
+    {   // deepest level first; level 0 (the sentinel, n = 0) has no parent to feed
+        uint32_t end = (uint32_t)P;
+        std::vector<std::pair<uint32_t, uint32_t>> levels;  // ascending n; ranges in `order`
+        for (uint32_t v = 0; v <= N; ++v) {
+            const uint32_t b = ctx->h_level_start[v];
+            if (b == 0xFFFFFFFFu) continue;
+            levels.emplace_back(b, end);   // keys are sorted descending: smaller n sits further back
+            end = b;
+        }
+        // levels[k] = (begin of key v_k, end); built for ascending v, so begin decreases
+        for (size_t k = levels.size(); k-- > 0;) {
+            const uint32_t b = levels[k].first, e = levels[k].second;
+            if (e <= b) continue;
+            k_push_level<<<blocks_for(e - b, 256), 256, 0, st>>>(e - b, ctx->order.as<uint32_t>() + b, ctx->parent.as<int64_t>(),
+                                                                  ctx->W.as<uint32_t>());
+            launches += 1;
+        }
+    }
     CK(ctx->loc.ensure((ctx->sum_l + 32) * 4));
     k_decode_locals<<<blocks_for(P, 128), 128, 0, st>>>(P, ctx->nodes.as<Node>(), ctx->bits.as<uint32_t>(), ctx->poff.as<uint64_t>(),
                                                          ctx->payload.as<uint64_t>(), ctx->loc.as<uint32_t>(), ctx->N,
@@ -890,7 +963,7 @@ void kdbx_close(kdbx_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->num_kmers, &ctx->parent, &ctx->n, &ctx->l, &ctx->last, &ctx->bits, &ctx->poff, &ctx->payload,
                       &ctx->nodes, &ctx->W, &ctx->loc, &ctx->loff, &ctx->noff, &ctx->coff, &ctx->bounds, &ctx->err_flag,
-                      &ctx->cub_tmp, &ctx->flat, &ctx->jobs, &ctx->hist, &ctx->work, &ctx->bucket_off, &ctx->cursor,
+                      &ctx->cub_tmp, &ctx->order_in, &ctx->order, &ctx->keys_sorted, &ctx->level_start, &ctx->flat, &ctx->jobs, &ctx->hist, &ctx->work, &ctx->bucket_off, &ctx->cursor,
                       &ctx->ucount, &ctx->uoff, &ctx->units, &ctx->counters, &ctx->blockhist, &ctx->tri, &ctx->rowupd})
         b->release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
@@ -987,7 +1060,7 @@ int kdbx_row_updates(kdbx_ctx* ctx, uint64_t* out) {
     if (rc < 0) return rc;
     CK(ctx->rowupd.ensure(((size_t)ctx->N + 1) * 8));
     CK(cudaMemsetAsync(ctx->rowupd.p, 0, ((size_t)ctx->N + 1) * 8, ctx->stream));
-    k_row_updates<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->P, ctx->nodes.as<Node>(), ctx->loc.as<uint32_t>(),
+    k_row_updates<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->P, ctx->N, ctx->nodes.as<Node>(), ctx->loc.as<uint32_t>(),
                                                               ctx->rowupd.as<unsigned long long>());
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, ctx->rowupd.p, (size_t)ctx->N * 8, cudaMemcpyDeviceToHost, ctx->stream));
