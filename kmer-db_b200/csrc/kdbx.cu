@@ -101,9 +101,15 @@ struct ChunkCost {
 __global__ void k_build_nodes(uint64_t P, const int64_t* __restrict__ parent, const int64_t* __restrict__ num_kmers,
                               const uint32_t* __restrict__ n, const uint32_t* __restrict__ l,
                               const uint32_t* __restrict__ last, const uint64_t* __restrict__ loff,
-                              Node* __restrict__ nodes, uint32_t* __restrict__ W) {
+                              Node* __restrict__ nodes, uint32_t* __restrict__ W, uint32_t N, int* __restrict__ err) {
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
+    {   // structure every later kernel relies on: parent before child, n = n_parent + l <= N
+        const int64_t q = parent[p];
+        const bool ok = q >= -1 && q < (int64_t)p && l[p] <= n[p] && n[p] <= N &&
+                        n[p] == (q >= 0 ? n[q] : 0u) + l[p] && (l[p] == 0 || last[p] < N);
+        if (!ok) atomicExch(err, 4);
+    }
     Node nd;
     nd.parent = (int32_t)parent[p];
     nd.n = n[p]; nd.l = l[p]; nd.last = last[p]; nd.loff = loff[p]; nd.pad = 0;
@@ -172,22 +178,30 @@ __device__ __forceinline__ uint32_t gamma_next(const uint64_t* __restrict__ w, u
 // emit ids front to back — which writes every id exactly once and never reads d_loc back.
 __global__ void k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint32_t* __restrict__ bits,
                                 const uint64_t* __restrict__ poff, const uint64_t* __restrict__ payload,
-                                uint32_t* __restrict__ loc, uint32_t N, int* __restrict__ err) {
+                                uint64_t payload_words, uint32_t* __restrict__ loc, uint32_t N, int* __restrict__ err) {
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
     const Node nd = nodes[p];
     if (nd.l == 0) return;
     uint32_t* out = loc + nd.loff;
-    if (nd.last >= N) { atomicExch(err, 2); return; }
-    if (nd.l == 1) { out[0] = nd.last; return; }
-    const uint64_t* w = payload + poff[p];
+    // the parent's list must end before this one starts, or full lists would not ascend
+    const uint32_t floor_id = nd.parent >= 0 && nodes[nd.parent].l ? nodes[nd.parent].last + 1u : 0u;
+    if (nd.l == 1) {
+        out[0] = nd.last;
+        if (nd.last < floor_id) atomicExch(err, 3);
+        return;
+    }
     const uint32_t nb = bits[p];
+    const uint64_t po = poff[p];
+    if (po + ((uint64_t)(nb + 127u) / 128u) * 2u > payload_words) { atomicExch(err, 5); return; }
+    const uint64_t* w = payload + po;
     uint32_t pos = 0;
     uint64_t sum = 0;
     for (uint32_t i = 0; i + 1 < nd.l; ++i) sum += gamma_next(w, pos, nb);
     if (pos != nb) { atomicExch(err, 1); return; }
     if (sum > nd.last) { atomicExch(err, 2); return; }
     uint32_t cur = nd.last - (uint32_t)sum;
+    if (cur < floor_id) atomicExch(err, 3);
     out[0] = cur;
     pos = 0;
     for (uint32_t i = 1; i < nd.l; ++i) {
@@ -381,15 +395,23 @@ __global__ void k_key_totals(uint32_t nkeys, uint32_t nblocks, const uint32_t* _
 }
 
 // blockhist[b][key] := bucket_off[key] + sum_{b' < b} blockhist[b'][key]   (first slot of the pair)
+// One warp per key: a running exclusive scan over the blocks, 32 at a time.
 __global__ void k_block_offsets(uint32_t nkeys, uint32_t nblocks, const uint32_t* __restrict__ bucket_off,
                                 uint32_t* __restrict__ blockhist) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
     if (k >= nkeys) return;
     uint32_t run = bucket_off[k];
-    for (uint32_t b = 0; b < nblocks; ++b) {
-        const uint32_t c = blockhist[(size_t)b * nkeys + k];
-        blockhist[(size_t)b * nkeys + k] = run;
-        run += c;
+    for (uint32_t b0 = 0; b0 < nblocks; b0 += 32) {
+        const uint32_t b = b0 + lane;
+        const uint32_t c = b < nblocks ? blockhist[(size_t)b * nkeys + k] : 0u;
+        uint32_t incl = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += up;
+        }
+        if (b < nblocks) blockhist[(size_t)b * nkeys + k] = run + incl - c;
+        run += __shfl_sync(0xffffffffu, incl, 31);
     }
 }
 
@@ -512,6 +534,15 @@ __global__ void k_unit_fill(uint32_t nkeys, const uint32_t* __restrict__ hist, c
 // profiles/r01_microbench_atomics.txt — faster than LDS/IADD/STS on warp-private tiles).
 // Finally the tile is added into the packed lower-triangular matrix (src/array.h:140) with
 // red.global.add.u32, skipping zero cells.
+__device__ __forceinline__ void red_shared_add(uint32_t saddr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ldg_nc_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 __global__ void __launch_bounds__(kScatterThreads)
 k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_units_ptr, const Job* __restrict__ jobs,
               const uint32_t* __restrict__ flat, uint32_t* __restrict__ tri, uint64_t tri_base, uint32_t T,
@@ -520,6 +551,7 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
     __shared__ uint32_t s_unit, s_next_job;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n_units = *n_units_ptr;
+    const uint32_t tile_saddr = (uint32_t)__cvta_generic_to_shared(tile);
     for (;;) {
         if (threadIdx.x == 0) s_unit = atomicAdd(unit_counter, 1u);
         __syncthreads();
@@ -532,6 +564,8 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
         for (uint32_t c = threadIdx.x; c < ncols; c += kScatterThreads) tile[c] = 0;
         if (threadIdx.x == 0) s_next_job = un.job_begin;
         __syncthreads();
+        // shared address of column 0 (may lie below the tile when col0 > 0; only in-tile ids occur)
+        const uint32_t base = tile_saddr - col0 * 4u;
         for (;;) {
             uint32_t jb = 0;
             if (lane == 0) jb = atomicAdd(&s_next_job, 32u);
@@ -540,18 +574,46 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
             const uint32_t cnt = min(32u, un.job_end - jb);
             Job mine; mine.off = 0; mine.len = 0; mine.w = 0; mine.pad = 0;
             if (lane < cnt) mine = jobs[jb + lane];
-            for (uint32_t j = 0; j < cnt; ++j) {
-                const uint32_t off = __shfl_sync(0xffffffffu, mine.off, j);
-                const uint32_t len = __shfl_sync(0xffffffffu, mine.len, j);
-                const uint32_t w = __shfl_sync(0xffffffffu, mine.w, j);
-                const uint32_t* __restrict__ ids = flat + off;
-                uint32_t k = lane;
-                for (; k + 96 < len; k += 128) {  // 4 independent coalesced loads in flight per lane
-                    const uint32_t i0 = ids[k], i1 = ids[k + 32], i2 = ids[k + 64], i3 = ids[k + 96];
-                    atomicAdd(&tile[i0 - col0], w); atomicAdd(&tile[i1 - col0], w);
-                    atomicAdd(&tile[i2 - col0], w); atomicAdd(&tile[i3 - col0], w);
+            // Software pipeline over 128-id slices: the loads of slice s+1 (possibly of the next
+            // job) are issued before the reductions of slice s, so a warp always has one slice
+            // of ids in flight.  kNone marks lanes beyond the end of a run.
+            constexpr uint32_t kNone = 0xFFFFFFFFu;
+            uint32_t j = 0;
+            uint32_t len = __shfl_sync(0xffffffffu, mine.len, 0);
+            uint32_t w = __shfl_sync(0xffffffffu, mine.w, 0);
+            const uint32_t* ptr = flat + __shfl_sync(0xffffffffu, mine.off, 0) + lane;
+            uint32_t rem = len;  // ids of the current job not yet loaded
+            uint32_t a0, a1, a2, a3;
+            a0 = lane < rem ? ldg_nc_u32(ptr) : kNone;
+            a1 = lane + 32 < rem ? ldg_nc_u32(ptr + 32) : kNone;
+            a2 = lane + 64 < rem ? ldg_nc_u32(ptr + 64) : kNone;
+            a3 = lane + 96 < rem ? ldg_nc_u32(ptr + 96) : kNone;
+            for (;;) {
+                const uint32_t cur_w = w;
+                bool more = true;
+                if (rem > 128) { rem -= 128; ptr += 128; }
+                else {
+                    ++j;
+                    more = j < cnt;
+                    if (more) {
+                        rem = __shfl_sync(0xffffffffu, mine.len, j);
+                        w = __shfl_sync(0xffffffffu, mine.w, j);
+                        ptr = flat + __shfl_sync(0xffffffffu, mine.off, j) + lane;
+                    }
                 }
-                for (; k < len; k += 32) atomicAdd(&tile[ids[k] - col0], w);
+                uint32_t b0 = kNone, b1 = kNone, b2 = kNone, b3 = kNone;
+                if (more) {
+                    if (lane < rem) b0 = ldg_nc_u32(ptr);
+                    if (lane + 32 < rem) b1 = ldg_nc_u32(ptr + 32);
+                    if (lane + 64 < rem) b2 = ldg_nc_u32(ptr + 64);
+                    if (lane + 96 < rem) b3 = ldg_nc_u32(ptr + 96);
+                }
+                if (a0 != kNone) red_shared_add(base + a0 * 4u, cur_w);
+                if (a1 != kNone) red_shared_add(base + a1 * 4u, cur_w);
+                if (a2 != kNone) red_shared_add(base + a2 * 4u, cur_w);
+                if (a3 != kNone) red_shared_add(base + a3 * 4u, cur_w);
+                if (!more) break;
+                a0 = b0; a1 = b1; a2 = b2; a3 = b3;
             }
         }
         __syncthreads();
@@ -679,6 +741,17 @@ int make_plan(kdbx_ctx* ctx, Plan& pl) {
     return KDBX_OK;
 }
 
+int check_device_error(kdbx_ctx* ctx) {
+    int flag = 0;
+    CK(cudaMemcpy(&flag, ctx->err_flag.p, sizeof flag, cudaMemcpyDeviceToHost));
+    if (flag == 1) return ctx->fail(KDBX_ERR_ARG, "malformed trie: Elias-gamma stream does not match num_bits");
+    if (flag == 2) return ctx->fail(KDBX_ERR_ARG, "malformed trie: sample id out of range");
+    if (flag == 3) return ctx->fail(KDBX_ERR_ARG, "malformed trie: a local list does not continue its parent's list");
+    if (flag == 4) return ctx->fail(KDBX_ERR_ARG, "malformed trie: parent_id / num_samples / num_local_samples inconsistent");
+    if (flag == 5) return ctx->fail(KDBX_ERR_ARG, "malformed trie: payload offset out of bounds");
+    return KDBX_OK;
+}
+
 // scans + node packing + W + gamma decode.  Leaves sum_l / sum_n on the host (one sync).
 int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
     const uint64_t P = ctx->P;
@@ -709,7 +782,8 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
     CK(cudaMemsetAsync(ctx->err_flag.p, 0, 16, st));
     k_build_nodes<<<blocks_for(P, 256), 256, 0, st>>>(P, ctx->parent.as<int64_t>(), ctx->num_kmers.as<int64_t>(),
                                                        ctx->n.as<uint32_t>(), ctx->l.as<uint32_t>(), ctx->last.as<uint32_t>(),
-                                                       ctx->loff.as<uint64_t>(), ctx->nodes.as<Node>(), ctx->W.as<uint32_t>());
+                                                       ctx->loff.as<uint64_t>(), ctx->nodes.as<Node>(), ctx->W.as<uint32_t>(), ctx->N,
+                                                       ctx->err_flag.as<int>());
     launches += 1;
     // order patterns by num_samples, descending (levels of the W accumulation)
     const uint32_t N = ctx->N;
@@ -736,6 +810,7 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
     CK(cudaMemcpyAsync(&sums[2], ctx->coff.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(ctx->h_level_start.data(), ctx->level_start.p, ((size_t)N + 2) * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (int rc = check_device_error(ctx)) return rc;  // structural errors stop here, before any id is chased
     ctx->sum_l = sums[0]; ctx->sum_n = sums[1];
     {   // deepest level first; level 0 (the sentinel, n = 0) has no parent to feed
         uint32_t end = (uint32_t)P;
@@ -757,7 +832,7 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
     }
     CK(ctx->loc.ensure((ctx->sum_l + 32) * 4));
     k_decode_locals<<<blocks_for(P, 128), 128, 0, st>>>(P, ctx->nodes.as<Node>(), ctx->bits.as<uint32_t>(), ctx->poff.as<uint64_t>(),
-                                                         ctx->payload.as<uint64_t>(), ctx->loc.as<uint32_t>(), ctx->N,
+                                                         ctx->payload.as<uint64_t>(), ctx->payload_words, ctx->loc.as<uint32_t>(), ctx->N,
                                                          ctx->err_flag.as<int>());
     launches += 1;
     CK(cudaGetLastError());
@@ -769,14 +844,6 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
     launches += 1;
     CK(cudaGetLastError());
     return (int)nchunks;
-}
-
-int check_device_error(kdbx_ctx* ctx) {
-    int flag = 0;
-    CK(cudaMemcpy(&flag, ctx->err_flag.p, sizeof flag, cudaMemcpyDeviceToHost));
-    if (flag == 1) return ctx->fail(KDBX_ERR_ARG, "malformed trie: Elias-gamma stream does not match num_bits");
-    if (flag == 2) return ctx->fail(KDBX_ERR_ARG, "malformed trie: sample id out of range");
-    return KDBX_OK;
 }
 
 float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
@@ -806,6 +873,7 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     cudaEvent_t ev_prepared = ctx->event();
     CK(cudaStreamSynchronize(st));
     s.ms_prepare = elapsed(ev_start, ev_prepared);
+    if (int rc = check_device_error(ctx)) return rc;  // decode errors: stop before lists are expanded
 
     const uint32_t nkeys = ctx->N * pl.T;
     if (cells == 0 || nkeys == 0) {  // N <= 1 or an empty row range: no cell exists
@@ -853,7 +921,7 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
                                                                   ctx->blockhist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates);
             k_key_totals<<<blocks_for((uint64_t)nkeys + 1, 128), 128, 0, st>>>(nkeys, wide_grid, ctx->blockhist.as<uint32_t>(), ctx->hist.as<uint32_t>());
             if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
-            k_block_offsets<<<blocks_for(nkeys, 128), 128, 0, st>>>(nkeys, wide_grid, ctx->bucket_off.as<uint32_t>(), ctx->blockhist.as<uint32_t>());
+            k_block_offsets<<<blocks_for((uint64_t)nkeys * 32, 256), 256, 0, st>>>(nkeys, wide_grid, ctx->bucket_off.as<uint32_t>(), ctx->blockhist.as<uint32_t>());
             k_job_fill_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
                                                                   ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, row_begin, row_end, nkeys,
                                                                   ctx->blockhist.as<uint32_t>(), ctx->jobs.as<Job>());

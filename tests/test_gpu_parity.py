@@ -116,7 +116,28 @@ def test_malformed_and_misuse_are_errors(libs):
     bad["bits"] = a["bits"].copy()
     idx = int(np.argmax(a["l"] > 1))
     bad["bits"][idx] += 1
+    with pytest.raises(libs.KdbxError, match="malformed trie: Elias-gamma"):
+        _run(libs, 50, bad)
+    bad = dict(a)
+    bad["parent_id"] = a["parent_id"].copy()
+    bad["parent_id"][5] = 40  # parent after child
+    with pytest.raises(libs.KdbxError, match="malformed trie: parent_id"):
+        _run(libs, 50, bad)
+    bad = dict(a)
+    bad["n"] = a["n"].copy()
+    bad["n"][7] += 1
+    with pytest.raises(libs.KdbxError, match="malformed trie: parent_id"):
+        _run(libs, 50, bad)
+    bad = dict(a)
+    bad["last"] = a["last"].copy()
+    child = int(np.argmax(a["parent_id"] > 0))
+    bad["last"][child] = a["last"][int(a["parent_id"][child])]  # child list no longer after the parent's
     with pytest.raises(libs.KdbxError, match="malformed trie"):
+        _run(libs, 50, bad)
+    bad = dict(a)
+    bad["payload_off"] = a["payload_off"].copy()
+    bad["payload_off"][idx] = 10**9
+    with pytest.raises(libs.KdbxError, match="malformed trie: payload offset"):
         _run(libs, 50, bad)
     with libs.Context(device=0) as c:
         v, keep = libs.view_from_arrays(50, a["num_kmers"], a["parent_id"], a["n"], a["l"], a["last"], a["bits"], a["payload_off"], a["payload"])
