@@ -44,6 +44,52 @@ __global__ void __launch_bounds__(256) k_bench(const uint32_t* __restrict__ ids,
     if (acc == 0xdeadbeef) sink[0] = acc;
 }
 
+// ids resident in registers (8 per lane = a 256-id list), reductions into many different rows
+// of a CTA-shared tile: the pure red.shared issue rate, no global traffic in the loop.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_regs(const uint32_t* __restrict__ ids, int rows, int reps, uint32_t* __restrict__ sink) {
+    extern __shared__ uint32_t smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cells = rows * 256;
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) smem[i] = 0;
+    __syncthreads();
+    const uint32_t* p = ids + ((size_t)blockIdx.x * WARPS + warp) * 256;
+    uint32_t c[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) c[m] = (p[lane + 32 * m] & 255u) * 4u;
+    const uint32_t base0 = (uint32_t)__cvta_generic_to_shared(smem);
+    uint32_t r = warp * 7 + blockIdx.x;
+    for (int it = 0; it < reps; ++it) {
+        r = (r * 13 + 5) % (uint32_t)rows;
+        const uint32_t base = base0 + r * 1024u;
+        const uint32_t lim = 200 + (it & 31);  // most of the 256 columns are live
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+            if (lane + 32 * m < lim) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(base + c[m]), "r"(3u) : "memory");
+    }
+    __syncthreads();
+    uint32_t acc = 0;
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) acc += smem[i];
+    if (acc == 0xdeadbeef) sink[0] = acc;
+}
+
+template <int WARPS>
+void run_regs(const char* name, const uint32_t* d_ids, int blocks, int rows, uint32_t* d_sink) {
+    const size_t smem = (size_t)rows * 1024;
+    CK(cudaFuncSetAttribute(k_regs<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int reps = 20000;
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    k_regs<WARPS><<<blocks, WARPS * 32, smem>>>(d_ids, rows, 100, d_sink);
+    CK(cudaEventRecord(a));
+    k_regs<WARPS><<<blocks, WARPS * 32, smem>>>(d_ids, rows, reps, d_sink);
+    CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    double upd = 0;
+    for (int it = 0; it < reps; ++it) upd += 200 + (it & 31);
+    upd *= (double)blocks * WARPS;
+    printf("%-60s %8.3f ms  %.3e updates/s\n", name, ms, upd / (ms / 1e3));
+}
+
 template <int MODE>
 void run(const char* name, const uint32_t* d_ids, size_t per_warp, int blocks, uint32_t* d_mat, uint32_t* d_sink) {
     const size_t smem = (MODE == 0) ? 8 * TILE * 4 : TILE * 4;
@@ -94,5 +140,15 @@ int main(int argc, char** argv) {
         snprintf(nm, sizeof nm, "CTA-shared red.shared.add.u32 [%s]", pn[pattern]); run<1>(nm, d_ids, per_warp, blocks, d_mat, d_sink);
         snprintf(nm, sizeof nm, "red.global.add.u32 (L2 matrix) [%s]", pn[pattern]); run<2>(nm, d_ids, per_warp, blocks, d_mat, d_sink);
     }
+    // pure shared-memory reduction rate, ids in registers
+    printf("-- ids in registers, red.shared.add.u32 only (last id pattern: stride-4 columns)\n");
+    run_regs<32>("1 CTA/SM x 32 warps, 128-row x 256-col tile (128 KB)", d_ids, pr.multiProcessorCount, 128, d_sink);
+    run_regs<16>("2 CTA/SM x 16 warps, 96-row x 256-col tile (96 KB)", d_ids, pr.multiProcessorCount * 2, 96, d_sink);
+    run_regs<8>("4 CTA/SM x 8 warps, 48-row x 256-col tile (48 KB)", d_ids, pr.multiProcessorCount * 4, 48, d_sink);
+    for (size_t i = 0; i < total && i < (1u << 24); ++i) h[i] = (uint32_t)(i & 255);  // consecutive columns
+    CK(cudaMemcpy(d_ids, h.data(), (1u << 24) * 4, cudaMemcpyHostToDevice));
+    printf("-- same, consecutive columns (conflict-free)\n");
+    run_regs<32>("1 CTA/SM x 32 warps, 128-row x 256-col tile (128 KB)", d_ids, pr.multiProcessorCount, 128, d_sink);
+    run_regs<16>("2 CTA/SM x 16 warps, 96-row x 256-col tile (96 KB)", d_ids, pr.multiProcessorCount * 2, 96, d_sink);
     return 0;
 }
