@@ -16,6 +16,8 @@ for step in "$@"; do
     bench_ref) timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"; echo "bench_ref rc=$?" | tee -a "$OUT/summary.txt";;
     ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file "$OUT/launches.csv" python bench.py --samples 400 --genome-kmers 1000000 --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_list.out" 2>&1; echo "ncu_list rc=$?" | tee -a "$OUT/summary.txt";;
     ncu_full) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_scatter_add -s 2 -c 2 -f -o "$OUT/scatter" python bench.py --samples 400 --genome-kmers 1000000 --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_full.out" 2>&1; echo "ncu_full rc=$?" | tee -a "$OUT/summary.txt";;
+    ncu_list_cfg2) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file "$OUT/launches_cfg2.csv" python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_list_cfg2.out" 2>&1; echo "ncu_list_cfg2 rc=$?" | tee -a "$OUT/summary.txt";;
+    ncu_full_cfg2) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_scatter_add -s 10 -c 2 -f -o "$OUT/scatter_cfg2" python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_full_cfg2.out" 2>&1; echo "ncu_full_cfg2 rc=$?" | tee -a "$OUT/summary.txt";;
     *) echo "unknown step $step";;
   esac
 done
