@@ -3,7 +3,8 @@
 // PrefixKmerDb::deserialize(SkipHashtables) consumes (src/prefix_kmer_db.cpp:578-748), with
 // packed patterns as in pattern_t::pack (src/pattern.cpp:15-47) and raw hashtables as in
 // hash_map_lp::serialize (src/hashmap_lp.h:481-528).  all2all never needs the hashtables
-// (src/console_all2all.cpp:26), so the reader seeks over them and the writer emits empty ones.
+// (src/console_all2all.cpp:26), so by default the reader seeks over them; new2all and build -extend
+// read them (DeserializationMode::Everything).
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -42,7 +43,7 @@ constexpr size_t kRefPatternStructBytes = 48;       // sizeof(pattern_t), used b
 
 }  // namespace
 
-void read_db(const std::string& path, Trie& t) {
+void read_db(const std::string& path, Trie& t, bool with_tables) {
     File in(path, "rb");
     DbHeader& h = t.hdr;
     h.format_word = in.get<uint64_t>();
@@ -65,13 +66,41 @@ void read_db(const std::string& path, Trie& t) {
 
     h.num_hashtables = in.get<uint64_t>();
     const bool raw = (h.format_word & 1) != 0;
+    t.tables.clear();
+    if (with_tables) {
+        if (!raw) throw std::runtime_error("Cannot open k-mer database " + path + " (non-raw hashtables are not supported)");
+        t.tables.resize(h.num_hashtables);
+    }
+    std::vector<uint64_t> bv, items;
     for (uint64_t i = 0; i < h.num_hashtables; ++i) {
         if (raw) {
-            in.skip(sizeof(double));  // max_fill_factor
+            const double max_fill = in.get<double>();
             const uint64_t filled = in.get<uint64_t>();
             const uint64_t allocated = in.get<uint64_t>();
-            in.skip(5 * sizeof(uint64_t));  // size_when_restruct, mask, ht_memory, ht_total, ht_match
-            in.skip(((allocated + 63) / 64) * sizeof(uint64_t) + filled * 8);
+            in.skip(2 * sizeof(uint64_t));  // size_when_restruct, allocated_mask (both derived)
+            in.skip(sizeof(uint64_t));      // ht_memory (derived)
+            const uint64_t ht_total = in.get<uint64_t>(), ht_match = in.get<uint64_t>();
+            const uint64_t bv_words = (allocated + 63) / 64;
+            if (!with_tables) { in.skip(bv_words * sizeof(uint64_t) + filled * 8); continue; }
+            if (allocated == 0 || (allocated & (allocated - 1)) || filled > allocated)
+                throw std::runtime_error("Corrupt k-mer database " + path);
+            HashTable& ht = t.tables[i];
+            ht.max_fill = max_fill; ht.filled = filled; ht.ht_total = ht_total; ht.ht_match = ht_match;
+            bv.resize(bv_words); items.resize(filled);
+            in.read(bv.data(), bv_words * 8);
+            in.read(items.data(), filled * 8);   // {u32 key; i32 val} in slot order
+            ht.slots.assign(allocated, HashTable::kEmptySlot);
+            uint64_t next = 0;
+            for (uint64_t w = 0; w < bv_words; ++w) {
+                uint64_t bits = bv[w];
+                while (bits) {
+                    const uint64_t slot = w * 64 + (uint64_t)__builtin_ctzll(bits);
+                    bits &= bits - 1;
+                    if (slot >= allocated || next >= filled) throw std::runtime_error("Corrupt k-mer database " + path);
+                    ht.slots[slot] = items[next++];
+                }
+            }
+            if (next != filled) throw std::runtime_error("Corrupt k-mer database " + path);
         } else {  // portioned form (src/prefix_kmer_db.cpp:657-697)
             const uint64_t total = in.get<uint64_t>();
             uint64_t seen = 0;
@@ -145,16 +174,37 @@ void write_db(const std::string& path, const Trie& t) {
         out.put<uint64_t>(t.sample_names[i].size());
         out.write(t.sample_names[i].data(), t.sample_names[i].size());
     }
-    // empty raw hashtables: capacity 16, nothing filled (SURVEY.md §8d cfg3 note)
-    out.put<uint64_t>(h.num_hashtables);
-    for (uint64_t i = 0; i < h.num_hashtables; ++i) {
-        out.put<double>(0.8);
-        out.put<uint64_t>(0);    // filled
-        out.put<uint64_t>(16);   // allocated
-        out.put<uint64_t>(12);   // size_when_restruct = allocated * max_fill
-        out.put<uint64_t>(15);   // allocated_mask
-        out.put<uint64_t>(0); out.put<uint64_t>(0); out.put<uint64_t>(0);
-        out.put<uint64_t>(0);    // one bit-vector word, no slot used
+    if (!t.tables.empty()) {   // raw form of every table (src/hashmap_lp.h:481-528)
+        out.put<uint64_t>(t.tables.size());
+        std::vector<uint64_t> bv, items;
+        for (const HashTable& ht : t.tables) {
+            const uint64_t allocated = ht.allocated();
+            out.put<double>(ht.max_fill);
+            out.put<uint64_t>(ht.filled);
+            out.put<uint64_t>(allocated);
+            out.put<uint64_t>((uint64_t)((double)allocated * ht.max_fill));  // size_when_restruct
+            out.put<uint64_t>(allocated - 1);                                // allocated_mask
+            out.put<uint64_t>(allocated * 8);                                // ht_memory
+            out.put<uint64_t>(ht.ht_total); out.put<uint64_t>(ht.ht_match);
+            bv.assign((allocated + 63) / 64, 0);
+            items.clear(); items.reserve(ht.filled);
+            for (uint64_t i = 0; i < allocated; ++i)
+                if (!HashTable::is_empty(ht.slots[i])) { bv[i >> 6] |= 1ull << (i & 63); items.push_back(ht.slots[i]); }
+            out.write(bv.data(), bv.size() * 8);
+            out.write(items.data(), items.size() * 8);
+        }
+    } else {
+        // empty raw hashtables: capacity 16, nothing filled (SURVEY.md §8d cfg3 note)
+        out.put<uint64_t>(h.num_hashtables);
+        for (uint64_t i = 0; i < h.num_hashtables; ++i) {
+            out.put<double>(0.8);
+            out.put<uint64_t>(0);    // filled
+            out.put<uint64_t>(16);   // allocated
+            out.put<uint64_t>(12);   // size_when_restruct = allocated * max_fill
+            out.put<uint64_t>(15);   // allocated_mask
+            out.put<uint64_t>(0); out.put<uint64_t>(0); out.put<uint64_t>(0);
+            out.put<uint64_t>(0);    // one bit-vector word, no slot used
+        }
     }
     const uint64_t P = t.num_patterns();
     out.put<uint64_t>(P);

@@ -1,0 +1,154 @@
+// FASTA ingest for `build` and `new2all` (host side; the GPU path starts at sorted k-mers).
+// Behaviour follows the reference's loader: the sample list is a file of
+// whitespace-separated names unless the argument itself ends in a FASTA extension
+// (src/loader_ex.cpp:89-116); each entry is opened as given or with one of the known
+// extensions appended, gzip detected by content (src/genome_input_file.h:82-95); records are
+// split at '>', line ends removed, headers cut at the first space (:287-337); the sample name
+// is the last path component of the list entry (src/loader_ex.cpp:165-169) or, in
+// -multisample-fasta mode, each record's header (:241-282).
+#include <zlib.h>
+
+#include <cstdio>
+#include <cstring>
+#include <filesystem>
+#include <algorithm>
+#include <fstream>
+
+#include "ingest.h"
+
+namespace kdbx {
+
+std::vector<std::string> read_sample_list(const std::string& arg) {
+    static const char* exts[] = {".fa", ".fna", ".fasta", ".fastq", ".gz", ".fa.gz", ".fna.gz", ".fasta.gz", ".fastq.gz"};
+    for (const char* e : exts) {
+        const size_t n = std::strlen(e);
+        if (arg.size() >= n && arg.compare(arg.size() - n, n, e) == 0) return {arg};
+    }
+    std::ifstream ifs(arg);
+    if (!ifs) throw std::runtime_error("Unable to open input file " + arg);
+    std::vector<std::string> names;
+    std::string s;
+    while (ifs >> s) names.push_back(s);
+    return names;
+}
+
+bool load_sequence_file(const std::string& entry, std::string& data) {
+    static const char* exts[] = {"", ".fa", ".fna", ".fasta", ".gz", ".fa.gz", ".fna.gz", ".fasta.gz"};
+    std::string path;
+    for (const char* e : exts) {
+        std::error_code ec;
+        if (std::filesystem::exists(entry + e, ec)) { path = entry + e; break; }
+    }
+    if (path.empty()) return false;
+    gzFile f = gzopen(path.c_str(), "rb");  // transparent for plain files
+    if (!f) return false;
+    gzbuffer(f, 1 << 20);
+    data.clear();
+    std::vector<char> buf(1 << 22);
+    for (;;) {
+        const int n = gzread(f, buf.data(), (unsigned)buf.size());
+        if (n < 0) { gzclose(f); return false; }
+        if (n == 0) break;
+        data.append(buf.data(), (size_t)n);
+    }
+    gzclose(f);
+    return true;
+}
+
+void split_fasta(std::string& data, std::vector<FastaRecord>& out) {
+    out.clear();
+    size_t pos = data.find('>');
+    while (pos != std::string::npos) {
+        const size_t head = pos + 1;
+        size_t eol = data.find('\n', head);
+        if (eol == std::string::npos) eol = data.size();
+        size_t head_end = eol;
+        if (head_end > head && data[head_end - 1] == '\r') --head_end;
+        const size_t space = data.find(' ', head);
+        if (space != std::string::npos && space < head_end) head_end = space;
+        FastaRecord r;
+        r.header.assign(data, head, head_end - head);
+        const size_t seq_begin = eol < data.size() ? eol + 1 : data.size();
+        size_t next = data.find('>', seq_begin);
+        const size_t seq_end = next == std::string::npos ? data.size() : next;
+        // squeeze line ends out in place
+        size_t w = seq_begin;
+        for (size_t i = seq_begin; i < seq_end; ++i) {
+            const char c = data[i];
+            if (c != '\n' && c != '\r') data[w++] = c;
+        }
+        r.seq = data.data() + seq_begin;
+        r.len = w - seq_begin;
+        out.push_back(r);
+        pos = next;
+    }
+}
+
+std::string sample_name_of(const std::string& entry) { return std::filesystem::path(entry).filename().string(); }
+
+}  // namespace kdbx
+
+namespace kdbx {
+
+SampleStream::SampleStream(const std::string& list_arg, const Alphabet& alphabet, const MinHash& filter, uint32_t k,
+                           bool multisample, int threads)
+    : files_(read_sample_list(list_arg)), alphabet_(alphabet), filter_(filter), k_(k), multisample_(multisample),
+      ahead_((size_t)std::max(1, threads)) {}
+
+std::vector<SampleKmers> SampleStream::load_file(size_t idx) const {
+    std::vector<SampleKmers> out;
+    std::string data;
+    if (!load_sequence_file(files_[idx], data)) {
+        std::fprintf(stderr, "failed:%s\n", files_[idx].c_str());
+        return out;
+    }
+    std::vector<FastaRecord> recs;
+    split_fasta(data, recs);
+    auto finish = [](SampleKmers& s) {
+        std::sort(s.kmers.begin(), s.kmers.end());
+        s.kmers.erase(std::unique(s.kmers.begin(), s.kmers.end()), s.kmers.end());
+    };
+    if (multisample_) {
+        for (const FastaRecord& r : recs) {
+            SampleKmers s;
+            s.name = r.header;
+            extract_kmers(r.seq, r.len, k_, alphabet_, filter_, s.kmers);
+            finish(s);
+            out.push_back(std::move(s));
+        }
+    } else {
+        SampleKmers s;
+        s.name = sample_name_of(files_[idx]);
+        size_t total = 0;
+        for (const FastaRecord& r : recs) total += r.len;
+        s.kmers.reserve(total);
+        for (const FastaRecord& r : recs) extract_kmers(r.seq, r.len, k_, alphabet_, filter_, s.kmers);
+        finish(s);
+        out.push_back(std::move(s));
+    }
+    return out;
+}
+
+void SampleStream::refill() {
+    while (inflight_.size() < ahead_ && next_file_ < files_.size()) {
+        const size_t idx = next_file_++;
+        inflight_.push_back(std::async(std::launch::async, [this, idx] { return load_file(idx); }));
+    }
+}
+
+bool SampleStream::next(SampleKmers& out) {
+    for (;;) {
+        if (!ready_.empty()) {
+            out = std::move(ready_.front());
+            ready_.pop_front();
+            return true;
+        }
+        refill();
+        if (inflight_.empty()) return false;
+        std::vector<SampleKmers> got = inflight_.front().get();
+        inflight_.pop_front();
+        for (auto& s : got) ready_.push_back(std::move(s));
+    }
+}
+
+}  // namespace kdbx

@@ -1,0 +1,56 @@
+// Sample ingest shared by `build` and `new2all`: sample list -> FASTA records -> sorted,
+// de-duplicated k-mers per sample, delivered strictly in list order (the reference's ordered
+// output queue, src/loader_ex.h:42-48).  Files are parsed and their k-mers extracted and
+// sorted by a small pool of reader threads running ahead of the consumer.
+#pragma once
+#include <condition_variable>
+#include <deque>
+#include <future>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "kmers.h"
+
+namespace kdbx {
+
+struct FastaRecord {
+    std::string header;  // up to the first space
+    const char* seq = nullptr;
+    size_t len = 0;
+};
+
+struct SampleKmers {
+    std::string name;
+    std::vector<uint64_t> kmers;  // ascending, unique
+};
+
+std::vector<std::string> read_sample_list(const std::string& arg);
+bool load_sequence_file(const std::string& entry, std::string& data);  // plain or gzip
+void split_fasta(std::string& data, std::vector<FastaRecord>& out);    // edits `data` in place
+std::string sample_name_of(const std::string& entry);
+
+class SampleStream {
+public:
+    SampleStream(const std::string& list_arg, const Alphabet& alphabet, const MinHash& filter, uint32_t k, bool multisample,
+                 int threads);
+    // Next sample in input order; false when the input is exhausted.
+    bool next(SampleKmers& out);
+    size_t num_files() const { return files_.size(); }
+
+private:
+    std::vector<SampleKmers> load_file(size_t idx) const;
+    void refill();
+    std::vector<std::string> files_;
+    Alphabet alphabet_;
+    MinHash filter_;
+    uint32_t k_;
+    bool multisample_;
+    size_t ahead_;
+    size_t next_file_ = 0;
+    std::deque<std::future<std::vector<SampleKmers>>> inflight_;
+    std::deque<SampleKmers> ready_;
+};
+
+}  // namespace kdbx

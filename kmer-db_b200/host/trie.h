@@ -91,8 +91,64 @@ struct DbHeader {
     uint64_t num_hashtables = 256;
 };
 
+// One prefix bucket: the raw form of the reference's hash_map_lp<uint32 suffix, int32 pattern id>
+// (src/hashmap_lp.h:69-99): open addressing, linear probing from fmix32(suffix) & mask, power-of-two
+// capacity, empty slots marked by val == INT32_MAX.  A slot is {u32 key; i32 val}, kept here as one
+// little-endian u64 (key in the low half) so that the array can go to HBM as it is.
+struct HashTable {
+    static constexpr uint64_t kEmptySlot = (uint64_t)0x7FFFFFFFu << 32;  // key 0, val INT32_MAX
+    double max_fill = 0.8;
+    uint64_t filled = 0;
+    uint64_t ht_total = 0, ht_match = 0;  // statistics words of the wire format, carried through
+    std::vector<uint64_t> slots = std::vector<uint64_t>(16, kEmptySlot);
+
+    uint64_t allocated() const { return slots.size(); }
+    uint64_t mask() const { return slots.size() - 1; }
+    static uint32_t hash(uint32_t h) {  // murmur3 fmix32 (src/hashmap_lp.h:52-64)
+        h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+        return h;
+    }
+    static bool is_empty(uint64_t slot) { return (uint32_t)(slot >> 32) == 0x7FFFFFFFu; }
+    // pattern id of `key`, or -1
+    int32_t find(uint32_t key) const {
+        const uint64_t m = mask();
+        for (uint64_t h = hash(key) & m;; h = (h + 1) & m) {
+            const uint64_t s = slots[h];
+            if (is_empty(s)) return -1;
+            if ((uint32_t)s == key) return (int32_t)(s >> 32);
+        }
+    }
+    // slot of `key`; a new key is inserted with pattern id 0 (src/prefix_kmer_db.cpp:159-162)
+    uint64_t* find_or_insert(uint32_t key) {
+        const uint64_t m = mask();
+        for (uint64_t h = hash(key) & m;; h = (h + 1) & m) {
+            uint64_t& s = slots[h];
+            if (is_empty(s)) { s = (uint64_t)key; ++filled; return &s; }
+            if ((uint32_t)s == key) return &s;
+        }
+    }
+    // capacity doubles until filled + incoming <= max_fill * capacity (src/hashmap_lp.h:427-464)
+    void reserve_additional(uint64_t incoming) {
+        uint64_t cap = slots.size();
+        while ((double)(filled + incoming) > (double)cap * max_fill) cap *= 2;
+        if (cap == slots.size()) return;
+        std::vector<uint64_t> old(cap, kEmptySlot);
+        old.swap(slots);
+        const uint64_t m = mask();
+        for (uint64_t s : old) {
+            if (is_empty(s)) continue;
+            uint64_t h = hash((uint32_t)s) & m;
+            while (!is_empty(slots[h])) h = (h + 1) & m;
+            slots[h] = s;
+        }
+    }
+};
+
 struct Trie {
     DbHeader hdr;
+    // prefix-bucketed k-mer -> pattern id tables (src/prefix_kmer_db.h:198); empty unless the
+    // database was read with hashtables or built here.  all2all never needs them.
+    std::vector<HashTable> tables;
     std::vector<std::string> sample_names;
     std::vector<uint64_t> sample_kmers;  // per-sample distinct k-mer count ("total-kmers")
 
@@ -150,8 +206,10 @@ struct Trie {
 };
 
 // db_io.cpp — .db wire format (src/prefix_kmer_db.cpp:438-574,578-748)
-void read_db(const std::string& path, Trie& out);   // hashtables are skipped (all2all needs none)
-void write_db(const std::string& path, const Trie& t);  // writes EMPTY raw hashtables
+// with_tables = false is the reference's DeserializationMode::SkipHashtables (all2all needs none)
+void read_db(const std::string& path, Trie& out, bool with_tables = false);
+// writes t.tables when present, otherwise hdr.num_hashtables EMPTY raw hashtables
+void write_db(const std::string& path, const Trie& t);
 
 // csv_out.cpp — byte-exact CSV emitters (src/console_all2all.cpp:40-78)
 void write_all2all_csv(const std::string& path, const Trie& t, const uint32_t* tri, bool sparse);
