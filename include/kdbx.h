@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define KDBX_ABI_VERSION 1
+#define KDBX_ABI_VERSION 2
 
 enum {
     KDBX_OK = 0,
@@ -50,7 +50,10 @@ typedef struct kdbx_config {
     uint64_t chunk_ids;    /* decoded ids per chunk; 0 = default                         */
     uint32_t tile_cols;    /* columns per warp-private accumulator tile; 0 = default     */
     uint32_t unit_updates; /* target updates per work unit; 0 = default                  */
-    uint64_t reserved[4];
+    uint64_t sparse_block_cells; /* kdbx_all2all_sparse: dense cells accumulated per row block;
+                                    0 = a quarter of the free HBM                          */
+    uint64_t query_batch_kmers;  /* kdbx_new2all_batch: k-mers per device pass; 0 = 2^28      */
+    uint64_t reserved[2];
 } kdbx_config;
 
 #define KDBX_FLAG_NONE 0u
@@ -100,7 +103,11 @@ typedef struct kdbx_stats {
     float ms_download;       /* D2H of the result                                        */
     uint32_t scatter_launches;
     uint32_t _pad;
-    uint64_t reserved[4];
+    uint64_t probes;         /* new2all: k-mers looked up                                */
+    uint64_t hits;           /* new2all: k-mers found in the database                    */
+    float ms_probe;          /* new2all: hash probe kernel                               */
+    float ms_compact;        /* sparse: filter + compaction kernels                      */
+    uint64_t reserved[2];
 } kdbx_stats;
 
 /* Library / device management ---------------------------------------------------------- */
@@ -142,6 +149,79 @@ int kdbx_all2all_dense_rows(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end,
  * device, e.g. a torch tensor's data_ptr); no D2H inside the call. */
 int kdbx_all2all_dense_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end,
                                    void* d_out_rows, kdbx_stats* stats);
+
+/* ---- sparse all2all ------------------------------------------------------------------- */
+
+/* Output filter evaluated ON THE DEVICE while rows are compacted.  Mirrors CombinedFilter
+ * (src/sparse_filters.h:33-61): a cell (row, col, common) is kept iff common != 0,
+ * min_common <= common <= max_common (KmerFilter, :26-30) and every metric bound holds
+ * (MetricFilter, :12-23: lo <= metric(common, cnt[row], cnt[col]) <= hi in IEEE double).
+ * Only measures whose arithmetic is exactly reproducible on the GPU (one division / one sqrt,
+ * round-to-nearest) are offered here; the log-based ones (mash, ani, ...) stay with the caller,
+ * who filters the returned rows on the host (kmer-db_b200/host does). */
+enum { KDBX_METRIC_JACCARD = 0, KDBX_METRIC_MIN = 1, KDBX_METRIC_MAX = 2, KDBX_METRIC_COSINE = 3 };
+typedef struct kdbx_metric_bound {
+    int32_t metric;     /* KDBX_METRIC_*                                                   */
+    int32_t _pad;
+    double lo, hi;      /* inclusive; use -DBL_MAX / DBL_MAX for an open side               */
+} kdbx_metric_bound;
+typedef struct kdbx_filter {
+    uint32_t min_common, max_common;      /* KmerFilter bounds; 0 / UINT32_MAX = open        */
+    uint32_t num_metric_bounds;           /* <= 4                                            */
+    uint32_t _pad;
+    kdbx_metric_bound metric_bounds[4];
+    const uint32_t* sample_kmers;         /* uint32[num_samples] "total-kmers" of each sample
+                                             (src/kmer_db.h:38); required iff bounds are given */
+} kdbx_filter;
+
+/* Rows of sorted (col, val) pairs, val > 0 and passing the filter: the content of the
+ * reference's SparseMatrix after compact2 (src/array.h:391-446).  Arrays are host memory owned
+ * by the library (page-locked when the result came from one row block); release with
+ * kdbx_free_csr. */
+typedef struct kdbx_csr {
+    uint32_t num_rows;      /* = num_samples                                               */
+    uint32_t _pad;          /* owned by the library (allocation kind)                       */
+    uint64_t nnz;
+    uint64_t* row_ptr;      /* num_rows + 1; row s = [row_ptr[s], row_ptr[s+1])             */
+    uint32_t* col;          /* ascending within a row, all < s                              */
+    uint32_t* val;
+} kdbx_csr;
+
+/* Replaces SimilarityCalculator::all2all_sp + SparseMatrix::compact2 + CBubbleHelper
+ * (src/similarity_calculator.cpp:442-657, src/array.h:391-446, src/bubble_helper.h): the same
+ * matrix as kdbx_all2all_dense, delivered as sparse rows.  The reference keeps one hash map per
+ * row and defers patterns with >= bubbleSize samples; here blocks of rows are accumulated
+ * densely in HBM by the same scatter-add kernels (180 GB holds the whole triangle up to
+ * N ~ 2*10^5) and compacted by a filter + prefix-sum kernel, so bubbles have no analogue.
+ * `filter` may be NULL (keep every non-zero cell). */
+int kdbx_all2all_sparse(kdbx_ctx* ctx, const kdbx_filter* filter, kdbx_csr* out, kdbx_stats* stats);
+void kdbx_free_csr(kdbx_csr* csr);
+
+/* ---- new2all: query samples against the database --------------------------------------- */
+
+/* The database's prefix-bucketed k-mer tables, PrefixKmerDb::hashtables (src/prefix_kmer_db.h:198),
+ * in the raw in-memory form of hash_map_lp<uint32_t suffix, int32_t pattern_id>
+ * (src/hashmap_lp.h:69-99): table t occupies slots[slot_off[t] .. slot_off[t+1]), its size is a
+ * power of two, a slot is the 8-byte item {uint32 key; int32 val} and val == INT32_MAX marks an
+ * empty slot; a key lives at or after fmix32(key) & (size-1) with linear probing (:308-333). */
+typedef struct kdbx_tables_view {
+    uint64_t num_tables;        /* 2^max(8, k*bits_per_symbol - 32) (src/prefix_kmer_db.cpp:54-62) */
+    const uint64_t* slot_off;   /* num_tables + 1                                           */
+    const uint64_t* slots;
+} kdbx_tables_view;
+
+/* Stage the tables in HBM (replaces handing PrefixKmerDb::getHashtables() to one2all,
+ * src/similarity_calculator.cpp:815). */
+int kdbx_load_hashtables(kdbx_ctx* ctx, const kdbx_tables_view* view);
+
+/* Replaces the per-query calls of SimilarityCalculator::one2all<false> / one2all_sp that
+ * New2AllConsole issues from its worker threads (src/console_new2all.cpp:64-94,
+ * src/similarity_calculator.cpp:810-925, 929-1051), batched: query q owns the ascending,
+ * unique k-mers kmers[q_off[q] .. q_off[q+1]) (KmerHelper::unique, src/kmer_extract.h:113-119).
+ * out[q * num_samples + s] = number of the query's k-mers present in database sample s.
+ * Needs kdbx_load_patterns and kdbx_load_hashtables.  `out` is HOST memory, n_queries x N. */
+int kdbx_new2all_batch(kdbx_ctx* ctx, const uint64_t* kmers, const uint64_t* q_off, uint32_t n_queries,
+                       uint32_t* out, kdbx_stats* stats);
 
 /* Debug / test taps (not used by the product path): copy intermediate device arrays of the
  * last compute call to the host.  what: 0 = W (uint32[P]), 1 = decoded local ids

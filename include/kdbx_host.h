@@ -6,6 +6,7 @@
  *   - the .db reader/writer          (PrefixKmerDb::deserialize / serialize,
  *                                      src/prefix_kmer_db.cpp:578-748 / 438-574)
  *   - the byte-exact CSV emitters    (All2AllConsole::run, src/console_all2all.cpp:40-78)
+ *   - FASTA ingest and the database builder (LoaderEx, KmerHelper, PrefixKmerDb::addKmers)
  *   - the synthetic database generator used by bench.py and the tests (ours).
  * Everything returns 0 or a negative code; kdbxh_last_error() gives the (thread-local) text.
  */
@@ -70,6 +71,33 @@ int kdbxh_totals_of(const kdbxh_trie* t, kdbxh_totals* out);
 /* name of sample i (NUL-terminated, owned by the trie) and its total-kmers count */
 const char* kdbxh_sample_name(const kdbxh_trie* t, uint32_t i);
 uint64_t kdbxh_sample_kmers(const kdbxh_trie* t, uint32_t i);
+
+/* Like kdbxh_read_db, but also loads the k-mer tables (DeserializationMode::Everything,
+ * src/kmer_db.h:55-60) — what new2all and build -extend need. */
+int kdbxh_read_db_full(kdbxh_trie* t, const char* path);
+/* Flattened view of the trie's k-mer tables for kdbx_load_hashtables (one contiguous slot array,
+ * built on first use and owned by the trie).  Error when the trie has no tables. */
+int kdbxh_tables_view(kdbxh_trie* t, kdbx_tables_view* out);
+
+/* Incremental construction of a database from per-sample k-mer sets: the restatement of
+ * PrefixKmerDb::addKmers (src/prefix_kmer_db.cpp:244-434) that the `build` mode drives.
+ * kmers: ascending, unique, nt alphabet, already canonical / shifted (see kdbxh_samples_load). */
+typedef struct kdbxh_builder kdbxh_builder;
+kdbxh_builder* kdbxh_builder_new(int threads);
+void kdbxh_builder_free(kdbxh_builder* b);
+int kdbxh_builder_add_sample(kdbxh_builder* b, const char* name, const uint64_t* kmers, uint64_t count, uint32_t k, double fraction);
+int kdbxh_builder_finish(kdbxh_builder* b, kdbxh_trie* out);
+
+/* FASTA ingest (LoaderEx + KmerHelper::extract + MinHashFilter, src/loader_ex.cpp, src/kmer_extract.h:13-97,
+ * src/filter.h:40-115): list_arg is a sample list file or one FASTA file; every sample's k-mers come
+ * back ascending and unique.  alphabet_id: enum AlphabetType (src/alphabet.h:10-18), 0 = nt. */
+typedef struct kdbxh_samples kdbxh_samples;
+kdbxh_samples* kdbxh_samples_load(const char* list_arg, uint32_t k, double fraction, double fraction_start, int32_t alphabet_id,
+                                  int multisample, int threads);
+void kdbxh_samples_free(kdbxh_samples* s);
+uint32_t kdbxh_samples_count(const kdbxh_samples* s);
+const char* kdbxh_samples_name(const kdbxh_samples* s, uint32_t i);
+const uint64_t* kdbxh_samples_kmers(const kdbxh_samples* s, uint32_t i, uint64_t* count);
 
 /* tri: packed lower-triangular uint32 matrix, N(N-1)/2 cells (src/array.h:140). */
 int kdbxh_write_all2all_csv(const kdbxh_trie* t, const uint32_t* tri, const char* path, int sparse);

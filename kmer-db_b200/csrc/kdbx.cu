@@ -26,11 +26,13 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_run_length_encode.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -671,6 +673,15 @@ struct kdbx_ctx {
     DevBuf flat, jobs, hist, work, bucket_off, cursor, ucount, uoff, units, counters, blockhist;
     DevBuf tri, rowupd;
     uint64_t sum_l = 0, sum_n = 0;
+    bool prepared = false;  // nodes / W / loc are valid for the loaded trie
+
+    // sparse delivery (sparse.cuh)
+    DevBuf sp_cnt, sp_counts, sp_rowptr, sp_col, sp_val;
+    // k-mer tables + query buffers (query.cuh)
+    bool tables_loaded = false;
+    uint64_t num_tables = 0;
+    float ms_upload_tables = 0.f;
+    DevBuf slot_off, slots, q_off, q_kmers, q_keys, q_keys2, q_runkeys, q_runcnt, q_out;
 
     std::vector<cudaEvent_t> events;
     size_t ev_used = 0;
@@ -843,6 +854,7 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
     k_chunk_bounds<<<blocks_for(nchunks + 1, 128), 128, 0, st>>>(P, ctx->coff.as<uint64_t>(), pl.chunk, nchunks, ctx->bounds.as<uint64_t>());
     launches += 1;
     CK(cudaGetLastError());
+    ctx->prepared = true;
     return (int)nchunks;
 }
 
@@ -970,6 +982,9 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     return KDBX_OK;
 }
 
+#include "sparse.cuh"
+#include "query.cuh"
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -1032,7 +1047,9 @@ void kdbx_close(kdbx_ctx* ctx) {
     for (DevBuf* b : {&ctx->num_kmers, &ctx->parent, &ctx->n, &ctx->l, &ctx->last, &ctx->bits, &ctx->poff, &ctx->payload,
                       &ctx->nodes, &ctx->W, &ctx->loc, &ctx->loff, &ctx->noff, &ctx->coff, &ctx->bounds, &ctx->err_flag,
                       &ctx->cub_tmp, &ctx->order_in, &ctx->order, &ctx->keys_sorted, &ctx->level_start, &ctx->flat, &ctx->jobs, &ctx->hist, &ctx->work, &ctx->bucket_off, &ctx->cursor,
-                      &ctx->ucount, &ctx->uoff, &ctx->units, &ctx->counters, &ctx->blockhist, &ctx->tri, &ctx->rowupd})
+                      &ctx->ucount, &ctx->uoff, &ctx->units, &ctx->counters, &ctx->blockhist, &ctx->tri, &ctx->rowupd,
+                      &ctx->sp_cnt, &ctx->sp_counts, &ctx->sp_rowptr, &ctx->sp_col, &ctx->sp_val, &ctx->slot_off, &ctx->slots,
+                      &ctx->q_off, &ctx->q_kmers, &ctx->q_keys, &ctx->q_keys2, &ctx->q_runkeys, &ctx->q_runcnt, &ctx->q_out})
         b->release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1059,6 +1076,7 @@ int kdbx_load_patterns(kdbx_ctx* ctx, const kdbx_trie_view* v) {
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     ctx->loaded = false;
+    ctx->prepared = false;
     CK(ctx->num_kmers.ensure(P * 8)); CK(ctx->parent.ensure(P * 8)); CK(ctx->n.ensure(P * 4)); CK(ctx->l.ensure(P * 4));
     CK(ctx->last.ensure(P * 4)); CK(ctx->bits.ensure(P * 4)); CK(ctx->payload.ensure((v->payload_words + 2) * 8));
     ctx->ev_used = 0;
@@ -1134,6 +1152,30 @@ int kdbx_row_updates(kdbx_ctx* ctx, uint64_t* out) {
     CK(cudaMemcpyAsync(out, ctx->rowupd.p, (size_t)ctx->N * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return check_device_error(ctx);
+}
+
+int kdbx_all2all_sparse(kdbx_ctx* ctx, const kdbx_filter* filter, kdbx_csr* out, kdbx_stats* stats) {
+    if (!ctx) return KDBX_ERR_ARG;
+    return all2all_sparse_impl(ctx, filter, out, stats);
+}
+
+void kdbx_free_csr(kdbx_csr* csr) {
+    if (!csr) return;
+    std::free(csr->row_ptr);
+    if (csr->_pad == 1) { if (csr->col) cudaFreeHost(csr->col); if (csr->val) cudaFreeHost(csr->val); }
+    else { std::free(csr->col); std::free(csr->val); }
+    std::memset(csr, 0, sizeof *csr);
+}
+
+int kdbx_load_hashtables(kdbx_ctx* ctx, const kdbx_tables_view* view) {
+    if (!ctx) return KDBX_ERR_ARG;
+    return load_hashtables_impl(ctx, view);
+}
+
+int kdbx_new2all_batch(kdbx_ctx* ctx, const uint64_t* kmers, const uint64_t* q_off, uint32_t n_queries, uint32_t* out,
+                       kdbx_stats* stats) {
+    if (!ctx) return KDBX_ERR_ARG;
+    return new2all_impl(ctx, kmers, q_off, n_queries, out, stats);
 }
 
 int64_t kdbx_debug_fetch(kdbx_ctx* ctx, int what, void* out, uint64_t max_elems) {

@@ -7,32 +7,13 @@
 #include <cstring>
 #include <thread>
 
-#include "trie.h"
+#include "csv_out.h"
+#include "numfmt.h"
 
 namespace kdbx {
 namespace {
 
-const char kDigitPairs[] =
-    "00010203040506070809101112131415161718192021222324252627282930313233343536373839"
-    "40414243444546474849505152535455565758596061626364656667686970717273747576777879"
-    "8081828384858687888990919293949596979899";
-
-inline char* put_u64(char* p, uint64_t v) {
-    char tmp[24];
-    int n = 0;
-    while (v >= 100) {
-        const unsigned r = (unsigned)(v % 100);
-        v /= 100;
-        tmp[n++] = kDigitPairs[2 * r + 1];
-        tmp[n++] = kDigitPairs[2 * r];
-    }
-    if (v >= 10) { tmp[n++] = kDigitPairs[2 * v + 1]; tmp[n++] = kDigitPairs[2 * v]; }
-    else tmp[n++] = (char)('0' + v);
-    while (n) *p++ = tmp[--n];
-    return p;
-}
-
-size_t format_row(const Trie& t, const uint32_t* tri, size_t s, bool sparse, std::string& out) {
+size_t format_row(const Trie& t, const uint32_t* tri, size_t s, bool sparse, const OutputFilters* filters, std::string& out) {
     const std::string& name = t.sample_names[s];
     out.resize(name.size() + 32 + s * (sparse ? 22 : 11));
     char* p = out.data();
@@ -44,7 +25,11 @@ size_t format_row(const Trie& t, const uint32_t* tri, size_t s, bool sparse, std
     if (!sparse) {
         for (size_t c = 0; c < s; ++c) { p = put_u64(p, row[c]); *p++ = ','; }
     } else {  // <col+1>:<val>, for non-zero cells (src/conversion.h:286-298)
+        // cells failing the -min/-max filters are zeroed first (LowerTriangularMatrix::compact,
+        // src/array.h:169-181), then zeros are skipped
+        const int k = (int)t.hdr.kmer_length;
         for (size_t c = 0; c < s; ++c) if (row[c] != 0) {
+            if (filters && !filters->pass(row[c], (uint32_t)t.sample_kmers[s], (uint32_t)t.sample_kmers[c], k)) continue;
             p = put_u64(p, c + 1); *p++ = ':'; p = put_u64(p, row[c]); *p++ = ',';
         }
     }
@@ -55,21 +40,25 @@ size_t format_row(const Trie& t, const uint32_t* tri, size_t s, bool sparse, std
 
 }  // namespace
 
-void write_all2all_csv(const std::string& path, const Trie& t, const uint32_t* tri, bool sparse) {
+std::string table_header(const Trie& t) {
+    std::string head = "kmer-length: " + std::to_string(t.hdr.kmer_length) + " fraction: ";
+    char num[64];
+    std::snprintf(num, sizeof num, "%g", t.hdr.fraction);  // == ostream << double
+    head += num;
+    head += " ,db-samples ,";
+    for (const auto& s : t.sample_names) { head += s; head += ','; }
+    head += "\nquery-samples,total-kmers,";
+    for (uint64_t c : t.sample_kmers) { head += std::to_string(c); head += ','; }
+    head += '\n';
+    return head;
+}
+
+void write_all2all_csv(const std::string& path, const Trie& t, const uint32_t* tri, bool sparse, const OutputFilters* filters) {
     FILE* f = std::fopen(path.c_str(), "wb");
     if (!f) throw std::runtime_error("Cannot open output file " + path);
-    {
-        std::string head = "kmer-length: " + std::to_string(t.hdr.kmer_length) + " fraction: ";
-        char num[64];
-        std::snprintf(num, sizeof num, "%g", t.hdr.fraction);  // == ostream << double
-        head += num;
-        head += " ,db-samples ,";
-        for (const auto& s : t.sample_names) { head += s; head += ','; }
-        head += "\nquery-samples,total-kmers,";
-        for (uint64_t c : t.sample_kmers) { head += std::to_string(c); head += ','; }
-        head += '\n';
-        std::fwrite(head.data(), 1, head.size(), f);
-    }
+    const std::string head = table_header(t);
+    std::fwrite(head.data(), 1, head.size(), f);
+    if (filters && filters->trivial()) filters = nullptr;
     const size_t N = t.num_samples();
     const size_t batch = 256;
     unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
@@ -79,12 +68,80 @@ void write_all2all_csv(const std::string& path, const Trie& t, const uint32_t* t
         std::vector<std::thread> th;
         for (unsigned k = 0; k < nt; ++k)
             th.emplace_back([&, k]() {
-                for (size_t s = s0 + k; s < s1; s += nt) format_row(t, tri, s, sparse, rows[s - s0]);
+                for (size_t s = s0 + k; s < s1; s += nt) format_row(t, tri, s, sparse, filters, rows[s - s0]);
             });
         for (auto& x : th) x.join();
         for (size_t s = s0; s < s1; ++s) std::fwrite(rows[s - s0].data(), 1, rows[s - s0].size(), f);
     }
     if (std::fclose(f) != 0) throw std::runtime_error("Cannot write output file " + path);
+}
+
+// all2all-sp table (src/console_all2all_sparse.cpp:50-98): same headers, rows of `col+1:val,`
+// (SparseMatrix::saveRowSparse, src/array.h:625-637).  `filters` (may be NULL) are applied again
+// here for the bounds the device did not evaluate.
+uint64_t write_sparse_csv(const std::string& path, const Trie& t, const kdbx_csr& m, const OutputFilters* filters) {
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("Cannot open output file " + path);
+    const std::string head = table_header(t);
+    std::fwrite(head.data(), 1, head.size(), f);
+    if (filters && filters->trivial()) filters = nullptr;
+    const int k = (int)t.hdr.kmer_length;
+    std::string row;
+    uint64_t saved = 0;
+    for (size_t s = 0; s < t.num_samples(); ++s) {
+        const uint64_t b = m.row_ptr ? m.row_ptr[s] : 0, e = m.row_ptr ? m.row_ptr[s + 1] : 0;
+        row.resize(t.sample_names[s].size() + 32 + (size_t)(e - b) * 22);
+        char* p = row.data();
+        std::memcpy(p, t.sample_names[s].data(), t.sample_names[s].size()); p += t.sample_names[s].size();
+        *p++ = ',';
+        p = put_u64(p, t.sample_kmers[s]);
+        *p++ = ',';
+        for (uint64_t i = b; i < e; ++i) {
+            if (filters && !filters->pass(m.val[i], (uint32_t)t.sample_kmers[s], (uint32_t)t.sample_kmers[m.col[i]], k)) continue;
+            p = put_u64(p, (uint64_t)m.col[i] + 1); *p++ = ':'; p = put_u64(p, m.val[i]); *p++ = ',';
+            ++saved;
+        }
+        *p++ = '\n';
+        std::fwrite(row.data(), 1, (size_t)(p - row.data()), f);
+    }
+    if (std::fclose(f) != 0) throw std::runtime_error("Cannot write output file " + path);
+    return saved;
+}
+
+// new2all table (src/console_new2all.cpp:98-161): database headers, then one row per query in
+// input order: `<name>,<unique k-mers>,` + N dense cells, or `col+1:val,` pairs for non-zero cells
+// passing the filters (evaluated with the QUERY's k-mer count as the row count).
+QueryTableWriter::QueryTableWriter(const std::string& path, const Trie& db, bool sparse, const OutputFilters* filters)
+    : db_(db), sparse_(sparse), filters_(filters && !filters->trivial() ? filters : nullptr) {
+    f_ = std::fopen(path.c_str(), "wb");
+    if (!f_) throw std::runtime_error("Cannot open output file " + path);
+    const std::string head = table_header(db);
+    std::fwrite(head.data(), 1, head.size(), f_);
+}
+QueryTableWriter::~QueryTableWriter() { if (f_) std::fclose(f_); }
+void QueryTableWriter::write_row(const std::string& name, uint64_t kmers, const uint32_t* sims) {
+    const size_t N = db_.num_samples();
+    buf_.resize(name.size() + 32 + N * 22);
+    char* p = buf_.data();
+    std::memcpy(p, name.data(), name.size()); p += name.size();
+    *p++ = ',';
+    p = put_u64(p, kmers);
+    *p++ = ',';
+    if (!sparse_) {
+        for (size_t c = 0; c < N; ++c) { p = put_u64(p, sims[c]); *p++ = ','; }
+    } else {
+        const int k = (int)db_.hdr.kmer_length;
+        for (size_t c = 0; c < N; ++c) if (sims[c] != 0) {
+            if (filters_ && !filters_->pass(sims[c], (uint32_t)kmers, (uint32_t)db_.sample_kmers[c], k)) continue;
+            p = put_u64(p, c + 1); *p++ = ':'; p = put_u64(p, sims[c]); *p++ = ',';
+        }
+    }
+    *p++ = '\n';
+    std::fwrite(buf_.data(), 1, (size_t)(p - buf_.data()), f_);
+}
+void QueryTableWriter::close() {
+    if (f_ && std::fclose(f_) != 0) { f_ = nullptr; throw std::runtime_error("Cannot write output file"); }
+    f_ = nullptr;
 }
 
 }  // namespace kdbx

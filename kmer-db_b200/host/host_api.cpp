@@ -2,13 +2,24 @@
 // exceptions into error codes.
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/kdbx_host.h"
 #include "gamma.h"
+#include "ingest.h"
+#include "kmer_db.h"
 #include "synth.h"
+#include "csv_out.h"
 #include "trie.h"
 
-struct kdbxh_trie { kdbx::Trie t; explicit kdbxh_trie(bool pinned) : t(pinned) {} };
+struct kdbxh_trie {
+    kdbx::Trie t;
+    std::vector<uint64_t> flat_off;   // flattened k-mer tables (kdbxh_tables_view)
+    kdbx::Buf<uint64_t> flat_slots;
+    explicit kdbxh_trie(bool pinned) : t(pinned) { flat_slots.set_pinned(pinned); }
+};
+struct kdbxh_builder { kdbx::DbBuilder b; explicit kdbxh_builder(int threads) : b(threads) {} };
+struct kdbxh_samples { std::vector<kdbx::SampleKmers> items; };
 
 namespace {
 thread_local std::string g_err;
@@ -109,6 +120,60 @@ void kdbxh_trie_free(kdbxh_trie* t) { delete t; }
 int kdbxh_read_db(kdbxh_trie* t, const char* path) {
     if (!t || !path) { g_err = "null argument"; return -1; }
     return guarded([&] { kdbx::read_db(path, t->t); });
+}
+int kdbxh_read_db_full(kdbxh_trie* t, const char* path) {
+    if (!t || !path) { g_err = "null argument"; return -1; }
+    return guarded([&] { t->flat_off.clear(); t->flat_slots.clear(); kdbx::read_db(path, t->t, true); });
+}
+int kdbxh_tables_view(kdbxh_trie* t, kdbx_tables_view* out) {
+    if (!t || !out) { g_err = "null argument"; return -1; }
+    return guarded([&] {
+        const auto& tabs = t->t.tables;
+        if (tabs.empty()) throw std::runtime_error("database was loaded without its k-mer tables");
+        if (t->flat_off.size() != tabs.size() + 1) {
+            t->flat_off.assign(tabs.size() + 1, 0);
+            for (size_t i = 0; i < tabs.size(); ++i) t->flat_off[i + 1] = t->flat_off[i] + tabs[i].slots.size();
+            t->flat_slots.clear();
+            t->flat_slots.resize(t->flat_off.back());
+            for (size_t i = 0; i < tabs.size(); ++i)
+                std::memcpy(t->flat_slots.data() + t->flat_off[i], tabs[i].slots.data(), tabs[i].slots.size() * 8);
+        }
+        out->num_tables = tabs.size(); out->slot_off = t->flat_off.data(); out->slots = t->flat_slots.data();
+    });
+}
+kdbxh_builder* kdbxh_builder_new(int threads) {
+    try { return new kdbxh_builder(threads > 0 ? threads : 1); } catch (...) { g_err = "allocation failed"; return nullptr; }
+}
+void kdbxh_builder_free(kdbxh_builder* b) { delete b; }
+int kdbxh_builder_add_sample(kdbxh_builder* b, const char* name, const uint64_t* kmers, uint64_t count, uint32_t k, double fraction) {
+    if (!b || !name || (count && !kmers)) { g_err = "null argument"; return -1; }
+    return guarded([&] { b->b.add_sample(name, kmers, (size_t)count, k, fraction, kdbx::kNt, 2); });
+}
+int kdbxh_builder_finish(kdbxh_builder* b, kdbxh_trie* out) {
+    if (!b || !out) { g_err = "null argument"; return -1; }
+    return guarded([&] { out->flat_off.clear(); out->flat_slots.clear(); b->b.finish(out->t); });
+}
+kdbxh_samples* kdbxh_samples_load(const char* list_arg, uint32_t k, double fraction, double fraction_start, int32_t alphabet_id,
+                                  int multisample, int threads) {
+    if (!list_arg) { g_err = "null argument"; return nullptr; }
+    kdbxh_samples* out = nullptr;
+    const int rc = guarded([&] {
+        const kdbx::Alphabet al = kdbx::Alphabet::make(alphabet_id);
+        kdbx::SampleStream stream(list_arg, al, kdbx::MinHash(fraction, fraction_start, k), k, multisample != 0, threads > 0 ? threads : 1);
+        out = new kdbxh_samples();
+        kdbx::SampleKmers s;
+        while (stream.next(s)) { out->items.push_back(std::move(s)); s = kdbx::SampleKmers(); }
+    });
+    if (rc != 0) { delete out; return nullptr; }
+    return out;
+}
+void kdbxh_samples_free(kdbxh_samples* s) { delete s; }
+uint32_t kdbxh_samples_count(const kdbxh_samples* s) { return s ? (uint32_t)s->items.size() : 0; }
+const char* kdbxh_samples_name(const kdbxh_samples* s, uint32_t i) { return (s && i < s->items.size()) ? s->items[i].name.c_str() : nullptr; }
+const uint64_t* kdbxh_samples_kmers(const kdbxh_samples* s, uint32_t i, uint64_t* count) {
+    if (!s || i >= s->items.size()) { if (count) *count = 0; return nullptr; }
+    if (count) *count = s->items[i].kmers.size();
+    return s->items[i].kmers.data();
 }
 int kdbxh_write_db(const kdbxh_trie* t, const char* path) {
     if (!t || !path) { g_err = "null argument"; return -1; }

@@ -1,6 +1,9 @@
-// Host-side C++ mirror of the reference's similarity engine interface for the dense path:
+// Host-side C++ mirror of the reference's similarity engine interface:
 //     class SimilarityCalculator { SimilarityCalculator(int num_threads, size_t cacheBufferMb);
-//         void all2all(PrefixKmerDb& db, LowerTriangularMatrix<uint32_t>& matrix) const; ... }
+//         void all2all(PrefixKmerDb& db, LowerTriangularMatrix<uint32_t>& matrix) const;
+//         void all2all_sp(PrefixKmerDb& db, SparseMatrix<uint32_t>& matrix, CBubbleHelper& bubbles) const;
+//         template <bool parallel> void one2all(const PrefixKmerDb& db, const kmer_t* kmers, size_t kmersCount,
+//                                               std::vector<uint32_t>& similarities) const; ... }
 // (src/similarity_calculator.h:4-16).  Same names and argument meaning; the work happens in
 // libkdbx.so through the C ABI (include/kdbx.h).  Differences, all deliberate:
 //   * `num_threads` / `cacheBufferMb` are accepted for CLI compatibility and ignored
@@ -10,11 +13,15 @@
 //   * errors surface as std::runtime_error, like every error in the reference
 //     (src/main.cpp:56-59); there is no CPU fallback.
 #pragma once
+#include <cfloat>
+#include <exception>
 #include <stdexcept>
+#include <thread>
 #include <string>
 #include <vector>
 
 #include "../../include/kdbx.h"
+#include "metrics.h"
 #include "trie.h"
 
 namespace kdbx {
@@ -36,10 +43,29 @@ private:
     std::vector<T> data_;
 };
 
+// Rows of ascending (col, val) pairs: what the reference's SparseMatrix<T> holds after compact2
+// (src/array.h:275-650, data_compacted).  Owns the library-allocated CSR arrays.
+template <class T>
+class SparseMatrix {
+public:
+    SparseMatrix() { csr_ = kdbx_csr{}; }
+    ~SparseMatrix() { kdbx_free_csr(&csr_); }
+    SparseMatrix(const SparseMatrix&) = delete;
+    SparseMatrix& operator=(const SparseMatrix&) = delete;
+    size_t getSize() const { return csr_.num_rows; }
+    size_t getNoInRow(size_t row) const { return (size_t)(csr_.row_ptr[row + 1] - csr_.row_ptr[row]); }
+    const uint32_t* cols(size_t row) const { return csr_.col + csr_.row_ptr[row]; }
+    const T* vals(size_t row) const { return csr_.val + csr_.row_ptr[row]; }
+    uint64_t nnz() const { return csr_.nnz; }
+    kdbx_csr* raw() { return &csr_; }
+private:
+    kdbx_csr csr_;
+};
+
 class SimilarityCalculator {
 public:
     SimilarityCalculator(int num_threads, size_t cacheBufferMb, int device = -1)
-        : num_threads_(num_threads), cache_buffer_mb_(cacheBufferMb) {
+        : num_threads_(num_threads), cache_buffer_mb_(cacheBufferMb), device_(device) {
         kdbx_config cfg{};
         cfg.device = device;
         if (kdbx_open(&cfg, &ctx_) != KDBX_OK) throw std::runtime_error(kdbx_last_error(nullptr));
@@ -56,14 +82,136 @@ public:
         check(kdbx_load_patterns(ctx_, &v));
         check(kdbx_all2all_dense(ctx_, matrix.data(), &stats_));
     }
+    // Contiguous row blocks with (nearly) equal numbers of updates: boundaries[g] .. boundaries[g+1]
+    // is GPU g's share.  Same rule as the reference's row-aligned ranges between threads
+    // (src/similarity_calculator.cpp:371-395), balanced on the per-row update counts.
+    static std::vector<uint32_t> shard_rows_by_work(const std::vector<uint64_t>& row_updates, int parts) {
+        const uint32_t N = (uint32_t)row_updates.size();
+        long double total = 0;
+        for (uint64_t u : row_updates) total += (long double)u;
+        std::vector<uint32_t> bounds(1, 0);
+        long double run = 0;
+        uint32_t r = 0;
+        for (int g = 1; g < parts; ++g) {
+            const long double target = total * g / parts;
+            while (r < N && run < target) run += (long double)row_updates[r++];
+            bounds.push_back(r);
+        }
+        bounds.push_back(N);
+        return bounds;
+    }
+
+    // The dense matrix on several GPUs of one node: every device holds the whole trie and
+    // computes a contiguous block of rows straight into its slice of the caller's matrix; rows
+    // are independent, so there is no exchange.  One host thread per device.
+    void all2all_multi(const Trie& db, LowerTriangularMatrix<uint32_t>& matrix, int num_gpus) const {
+        const int avail = kdbx_device_count();
+        if (num_gpus > avail) throw std::runtime_error("-gpus " + std::to_string(num_gpus) + " requested but only " + std::to_string(avail) + " B200 device(s) are visible");
+        matrix.resize(db.num_samples());
+        const uint32_t N = db.num_samples();
+        const kdbx_trie_view v = db.view();
+        const int base = device_ < 0 ? 0 : device_;
+        std::vector<kdbx_ctx*> ctxs((size_t)num_gpus, nullptr);
+        std::vector<std::string> errors((size_t)num_gpus);
+        ctxs[0] = ctx_;
+        auto close_extra = [&]() { for (int g = 1; g < num_gpus; ++g) kdbx_close(ctxs[(size_t)g]); };
+        auto on_all = [&](auto&& fn) {
+            std::vector<std::thread> th;
+            for (int g = 0; g < num_gpus; ++g)
+                th.emplace_back([&, g] { if (errors[(size_t)g].empty()) { try { fn(g); } catch (const std::exception& e) { errors[(size_t)g] = e.what(); } } });
+            for (auto& t : th) t.join();
+            for (const std::string& e : errors) if (!e.empty()) { close_extra(); throw std::runtime_error(e); }
+        };
+        on_all([&](int g) {
+            if (g > 0) {
+                kdbx_config cfg{};
+                cfg.device = base + g;
+                if (kdbx_open(&cfg, &ctxs[(size_t)g]) != KDBX_OK) throw std::runtime_error(kdbx_last_error(nullptr));
+            }
+            if (kdbx_load_patterns(ctxs[(size_t)g], &v) != KDBX_OK) throw std::runtime_error(kdbx_last_error(ctxs[(size_t)g]));
+        });
+        std::vector<uint64_t> upd(N, 0);
+        if (N && kdbx_row_updates(ctx_, upd.data()) != KDBX_OK) { const std::string e = kdbx_last_error(ctx_); close_extra(); throw std::runtime_error(e); }
+        const std::vector<uint32_t> bounds = shard_rows_by_work(upd, num_gpus);
+        std::vector<kdbx_stats> st((size_t)num_gpus);
+        on_all([&](int g) {
+            const uint32_t r0 = bounds[(size_t)g], r1 = bounds[(size_t)g + 1];
+            uint32_t* dst = matrix.data() + (r0 == 0 ? 0 : (size_t)r0 * (r0 - 1) / 2);
+            if (kdbx_all2all_dense_rows(ctxs[(size_t)g], r0, r1, dst, &st[(size_t)g]) != KDBX_OK)
+                throw std::runtime_error(kdbx_last_error(ctxs[(size_t)g]));
+        });
+        stats_ = st[0];
+        for (int g = 1; g < num_gpus; ++g) {  // totals; times are the slowest device's
+            stats_.updates += st[(size_t)g].updates;
+            stats_.kernel_launches += st[(size_t)g].kernel_launches;
+            stats_.ms_total = std::max(stats_.ms_total, st[(size_t)g].ms_total);
+            stats_.ms_scatter = std::max(stats_.ms_scatter, st[(size_t)g].ms_scatter);
+        }
+        close_extra();
+    }
+
+    // src/similarity_calculator.cpp:442 + SparseMatrix::compact2 (src/array.h:391-446): the same
+    // matrix as sparse rows.  `filters` are the -min/-max bounds; the ones whose arithmetic is
+    // exactly reproducible on the device run there (include/kdbx.h), the log-based ones are left
+    // to the CSV emitter, which applies `filters` again on the host.
+    void all2all_sp(const Trie& db, SparseMatrix<uint32_t>& matrix, const OutputFilters& filters) const {
+        const kdbx_trie_view v = db.view();
+        check(kdbx_load_patterns(ctx_, &v));
+        kdbx_filter f{};
+        f.min_common = filters.kmers_lo; f.max_common = filters.kmers_hi;
+        std::vector<uint32_t> counts(db.sample_kmers.begin(), db.sample_kmers.end());
+        for (const auto& m : filters.metrics) {
+            int id = -1;
+            if (m.first == "jaccard") id = KDBX_METRIC_JACCARD;
+            else if (m.first == "min") id = KDBX_METRIC_MIN;
+            else if (m.first == "max") id = KDBX_METRIC_MAX;
+            else if (m.first == "cosine") id = KDBX_METRIC_COSINE;
+            if (id < 0 || f.num_metric_bounds == 4) continue;
+            kdbx_metric_bound& b = f.metric_bounds[f.num_metric_bounds++];
+            b.metric = id; b.lo = m.second.lo; b.hi = m.second.hi;
+        }
+        f.sample_kmers = counts.data();
+        kdbx_free_csr(matrix.raw());
+        check(kdbx_all2all_sparse(ctx_, &f, matrix.raw(), &stats_));
+    }
+
+    // Stage the database for queries: patterns + k-mer tables (PrefixKmerDb::deserialize with
+    // DeserializationMode::Everything, src/console_new2all.cpp:32).
+    void load_database(const Trie& db) const {
+        if (db.tables.empty()) throw std::runtime_error("database was loaded without its k-mer tables");
+        const kdbx_trie_view v = db.view();
+        check(kdbx_load_patterns(ctx_, &v));
+        std::vector<uint64_t> off(db.tables.size() + 1, 0);
+        for (size_t t = 0; t < db.tables.size(); ++t) off[t + 1] = off[t] + db.tables[t].slots.size();
+        Buf<uint64_t> slots;
+        slots.set_pinned(true);
+        slots.resize(off.back());
+        for (size_t t = 0; t < db.tables.size(); ++t)
+            std::copy(db.tables[t].slots.begin(), db.tables[t].slots.end(), slots.data() + off[t]);
+        kdbx_tables_view tv{};
+        tv.num_tables = db.tables.size(); tv.slot_off = off.data(); tv.slots = slots.data();
+        check(kdbx_load_hashtables(ctx_, &tv));
+        num_samples_ = db.num_samples();
+    }
+
+    // A batch of one2all<false> calls (src/similarity_calculator.cpp:810-925): query q owns
+    // kmers[q_off[q] .. q_off[q+1]) (ascending, unique); similarities is resized to
+    // n_queries x N and row q receives the numbers of k-mers shared with every database sample.
+    void one2all_batch(const uint64_t* kmers, const std::vector<uint64_t>& q_off, std::vector<uint32_t>& similarities) const {
+        const uint32_t nq = q_off.empty() ? 0 : (uint32_t)(q_off.size() - 1);
+        similarities.assign((size_t)nq * num_samples_, 0);
+        check(kdbx_new2all_batch(ctx_, kmers, q_off.data(), nq, similarities.data(), &stats_));
+    }
     const kdbx_stats& last_stats() const { return stats_; }
 
 private:
     void check(int rc) const { if (rc != KDBX_OK) throw std::runtime_error(kdbx_last_error(ctx_)); }
     int num_threads_;
     size_t cache_buffer_mb_;
+    int device_ = -1;
     kdbx_ctx* ctx_ = nullptr;
     mutable kdbx_stats stats_{};
+    mutable uint32_t num_samples_ = 0;
 };
 
 }  // namespace kdbx

@@ -211,7 +211,5 @@ void read_db(const std::string& path, Trie& out, bool with_tables = false);
 // writes t.tables when present, otherwise hdr.num_hashtables EMPTY raw hashtables
 void write_db(const std::string& path, const Trie& t);
 
-// csv_out.cpp — byte-exact CSV emitters (src/console_all2all.cpp:40-78)
-void write_all2all_csv(const std::string& path, const Trie& t, const uint32_t* tri, bool sparse);
 
 }  // namespace kdbx

@@ -26,7 +26,8 @@ class KdbxError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("chunk_ids", C.c_uint64),
-                ("tile_cols", C.c_uint32), ("unit_updates", C.c_uint32), ("reserved", C.c_uint64 * 4)]
+                ("tile_cols", C.c_uint32), ("unit_updates", C.c_uint32), ("sparse_block_cells", C.c_uint64),
+                ("query_batch_kmers", C.c_uint64), ("reserved", C.c_uint64 * 2)]
 
 
 class TrieView(C.Structure):
@@ -41,10 +42,32 @@ class Stats(C.Structure):
                 ("units", C.c_uint64), ("chunks", C.c_uint32), ("kernel_launches", C.c_uint32),
                 ("ms_upload", C.c_float), ("ms_prepare", C.c_float), ("ms_expand", C.c_float), ("ms_bucket", C.c_float),
                 ("ms_scatter", C.c_float), ("ms_total", C.c_float), ("ms_download", C.c_float),
-                ("scatter_launches", C.c_uint32), ("_pad", C.c_uint32), ("reserved", C.c_uint64 * 4)]
+                ("scatter_launches", C.c_uint32), ("_pad", C.c_uint32), ("probes", C.c_uint64), ("hits", C.c_uint64),
+                ("ms_probe", C.c_float), ("ms_compact", C.c_float), ("reserved", C.c_uint64 * 2)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k not in ("_pad", "reserved")}
+
+
+class MetricBound(C.Structure):
+    _fields_ = [("metric", C.c_int32), ("_pad", C.c_int32), ("lo", C.c_double), ("hi", C.c_double)]
+
+
+class Filter(C.Structure):
+    _fields_ = [("min_common", C.c_uint32), ("max_common", C.c_uint32), ("num_metric_bounds", C.c_uint32), ("_pad", C.c_uint32),
+                ("metric_bounds", MetricBound * 4), ("sample_kmers", C.c_void_p)]
+
+
+class Csr(C.Structure):
+    _fields_ = [("num_rows", C.c_uint32), ("_pad", C.c_uint32), ("nnz", C.c_uint64), ("row_ptr", C.c_void_p),
+                ("col", C.c_void_p), ("val", C.c_void_p)]
+
+
+class TablesView(C.Structure):
+    _fields_ = [("num_tables", C.c_uint64), ("slot_off", C.c_void_p), ("slots", C.c_void_p)]
+
+
+METRICS = {"jaccard": 0, "min": 1, "max": 2, "cosine": 3}
 
 
 class SynthParams(C.Structure):
@@ -62,10 +85,13 @@ class Totals(C.Structure):
 # every symbol include/kdbx.h declares (tests check that the library exports all of them)
 KDBX_SYMBOLS = ["kdbx_abi_version", "kdbx_device_count", "kdbx_open", "kdbx_close", "kdbx_last_error",
                 "kdbx_host_alloc", "kdbx_host_free", "kdbx_load_patterns", "kdbx_row_updates", "kdbx_all2all_dense",
-                "kdbx_all2all_dense_rows", "kdbx_all2all_dense_rows_device", "kdbx_debug_fetch"]
+                "kdbx_all2all_dense_rows", "kdbx_all2all_dense_rows_device", "kdbx_all2all_sparse", "kdbx_free_csr",
+                "kdbx_load_hashtables", "kdbx_new2all_batch", "kdbx_debug_fetch"]
 KDBXH_SYMBOLS = ["kdbxh_last_error", "kdbxh_trie_new", "kdbxh_trie_free", "kdbxh_read_db", "kdbxh_write_db",
                  "kdbxh_synth", "kdbxh_validate", "kdbxh_prefix", "kdbxh_view", "kdbxh_totals_of", "kdbxh_sample_name",
-                 "kdbxh_sample_kmers", "kdbxh_write_all2all_csv"]
+                 "kdbxh_sample_kmers", "kdbxh_write_all2all_csv", "kdbxh_read_db_full", "kdbxh_tables_view",
+                 "kdbxh_builder_new", "kdbxh_builder_free", "kdbxh_builder_add_sample", "kdbxh_builder_finish",
+                 "kdbxh_samples_load", "kdbxh_samples_free", "kdbxh_samples_count", "kdbxh_samples_name", "kdbxh_samples_kmers"]
 
 _libs = None
 
@@ -97,6 +123,11 @@ def load():
     k.kdbx_all2all_dense.argtypes = [C.c_void_p, C.c_void_p, P(Stats)]
     k.kdbx_all2all_dense_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, P(Stats)]
     k.kdbx_all2all_dense_rows_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, P(Stats)]
+    k.kdbx_all2all_sparse.argtypes = [C.c_void_p, P(Filter), P(Csr), P(Stats)]
+    k.kdbx_free_csr.argtypes = [P(Csr)]
+    k.kdbx_free_csr.restype = None
+    k.kdbx_load_hashtables.argtypes = [C.c_void_p, P(TablesView)]
+    k.kdbx_new2all_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, P(Stats)]
     k.kdbx_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
     k.kdbx_debug_fetch.restype = C.c_int64
     h.kdbxh_last_error.restype = C.c_char_p
@@ -116,6 +147,24 @@ def load():
     h.kdbxh_sample_kmers.argtypes = [C.c_void_p, C.c_uint32]
     h.kdbxh_sample_kmers.restype = C.c_uint64
     h.kdbxh_write_all2all_csv.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+    h.kdbxh_read_db_full.argtypes = [C.c_void_p, C.c_char_p]
+    h.kdbxh_tables_view.argtypes = [C.c_void_p, P(TablesView)]
+    h.kdbxh_builder_new.argtypes = [C.c_int]
+    h.kdbxh_builder_new.restype = C.c_void_p
+    h.kdbxh_builder_free.argtypes = [C.c_void_p]
+    h.kdbxh_builder_free.restype = None
+    h.kdbxh_builder_add_sample.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_double]
+    h.kdbxh_builder_finish.argtypes = [C.c_void_p, C.c_void_p]
+    h.kdbxh_samples_load.argtypes = [C.c_char_p, C.c_uint32, C.c_double, C.c_double, C.c_int32, C.c_int, C.c_int]
+    h.kdbxh_samples_load.restype = C.c_void_p
+    h.kdbxh_samples_free.argtypes = [C.c_void_p]
+    h.kdbxh_samples_free.restype = None
+    h.kdbxh_samples_count.argtypes = [C.c_void_p]
+    h.kdbxh_samples_count.restype = C.c_uint32
+    h.kdbxh_samples_name.argtypes = [C.c_void_p, C.c_uint32]
+    h.kdbxh_samples_name.restype = C.c_char_p
+    h.kdbxh_samples_kmers.argtypes = [C.c_void_p, C.c_uint32, P(C.c_uint64)]
+    h.kdbxh_samples_kmers.restype = C.c_void_p
     _libs = (k, h)
     return _libs
 
@@ -162,6 +211,36 @@ class Trie:
         t = cls(pinned)
         t._check(t._h.kdbxh_read_db(t._p, os.fsencode(str(path))))
         return t
+
+    @classmethod
+    def read_db_full(cls, path, pinned=False):
+        """With the k-mer tables (what new2all needs)."""
+        t = cls(pinned)
+        t._check(t._h.kdbxh_read_db_full(t._p, os.fsencode(str(path))))
+        return t
+
+    @classmethod
+    def build(cls, samples, k=18, fraction=1.0, threads=1, pinned=False):
+        """Database from [(name, sorted unique uint64 k-mers)] through the host builder."""
+        _, h = load()
+        b = h.kdbxh_builder_new(threads)
+        t = cls(pinned)
+        try:
+            for name, kmers in samples:
+                kmers = np.ascontiguousarray(kmers, np.uint64)
+                t._check(h.kdbxh_builder_add_sample(b, name.encode(), kmers.ctypes.data if kmers.size else None, kmers.size, k, fraction))
+            t._check(h.kdbxh_builder_finish(b, t._p))
+        finally:
+            h.kdbxh_builder_free(b)
+        return t
+
+    def tables_view(self) -> TablesView:
+        v = TablesView()
+        self._check(self._h.kdbxh_tables_view(self._p, C.byref(v)))
+        return v
+
+    def sample_kmer_counts(self):
+        return np.array([self._h.kdbxh_sample_kmers(self._p, i) for i in range(self.num_samples)], dtype=np.uint64)
 
     @classmethod
     def synth(cls, num_samples, num_clusters=4, genome_kmers=5_000_000, k=18, mutation_rate=0.005, seed=2,
@@ -242,13 +321,31 @@ def view_from_arrays(num_samples, num_kmers, parent_id, n, l, last, bits, payloa
     return v, arrs
 
 
+def load_samples(list_arg, k=18, fraction=1.0, fraction_start=0.0, alphabet_id=0, multisample=False, threads=4):
+    """[(name, sorted unique k-mers)] of a sample list / FASTA file through the host ingest."""
+    _, h = load()
+    p = h.kdbxh_samples_load(os.fsencode(str(list_arg)), k, fraction, fraction_start, alphabet_id, 1 if multisample else 0, threads)
+    if not p:
+        raise KdbxError(h.kdbxh_last_error().decode())
+    try:
+        out = []
+        for i in range(h.kdbxh_samples_count(p)):
+            n = C.c_uint64()
+            ptr = h.kdbxh_samples_kmers(p, i, C.byref(n))
+            out.append((h.kdbxh_samples_name(p, i).decode(), _np_from(ptr, n.value, np.uint64).copy()))
+        return out
+    finally:
+        h.kdbxh_samples_free(p)
+
+
 class Context:
     """One GPU context of libkdbx.so (mirror of SimilarityCalculator's lifetime)."""
 
-    def __init__(self, device: int = -1, chunk_ids: int = 0, tile_cols: int = 0, unit_updates: int = 0):
+    def __init__(self, device: int = -1, chunk_ids: int = 0, tile_cols: int = 0, unit_updates: int = 0,
+                 sparse_block_cells: int = 0, query_batch_kmers: int = 0):
         k, _ = load()
         self._k = k
-        cfg = Config(device, 0, chunk_ids, tile_cols, unit_updates)
+        cfg = Config(device, 0, chunk_ids, tile_cols, unit_updates, sparse_block_cells, query_batch_kmers)
         p = C.c_void_p()
         rc = k.kdbx_open(C.byref(cfg), C.byref(p))
         if rc != 0:
@@ -305,6 +402,44 @@ class Context:
         st = Stats()
         self._check(self._k.kdbx_all2all_dense_rows_device(self._p, row_begin, row_end, C.c_void_p(device_ptr), C.byref(st)))
         return st
+
+    def all2all_sparse(self, min_common=0, max_common=0xFFFFFFFF, metric_bounds=(), sample_kmers=None):
+        """Sparse rows (row_ptr, col, val) as numpy copies; metric_bounds = [(name, lo, hi)]."""
+        f = Filter()
+        f.min_common, f.max_common = min_common, max_common
+        f.num_metric_bounds = len(metric_bounds)
+        for i, (name, lo, hi) in enumerate(metric_bounds):
+            f.metric_bounds[i].metric, f.metric_bounds[i].lo, f.metric_bounds[i].hi = METRICS[name], lo, hi
+        keep = None
+        if sample_kmers is not None:
+            keep = np.ascontiguousarray(sample_kmers, np.uint32)
+            f.sample_kmers = keep.ctypes.data
+        csr, st = Csr(), Stats()
+        self._check(self._k.kdbx_all2all_sparse(self._p, C.byref(f), C.byref(csr), C.byref(st)))
+        try:
+            row_ptr = _np_from(csr.row_ptr, csr.num_rows + 1, np.uint64).copy()
+            col = _np_from(csr.col, csr.nnz, np.uint32).copy()
+            val = _np_from(csr.val, csr.nnz, np.uint32).copy()
+        finally:
+            self._k.kdbx_free_csr(C.byref(csr))
+        return row_ptr, col, val, st
+
+    def load_hashtables(self, trie_or_view):
+        v = trie_or_view.tables_view() if isinstance(trie_or_view, Trie) else trie_or_view
+        self._keep_tables = trie_or_view
+        self._check(self._k.kdbx_load_hashtables(self._p, C.byref(v)))
+
+    def new2all_batch(self, queries):
+        """queries: list of sorted unique uint64 arrays -> (len(queries) x N uint32 matrix, stats)."""
+        q_off = np.zeros(len(queries) + 1, np.uint64)
+        for i, q in enumerate(queries):
+            q_off[i + 1] = q_off[i] + len(q)
+        kmers = np.ascontiguousarray(np.concatenate([np.asarray(q, np.uint64) for q in queries]) if queries else np.zeros(0, np.uint64))
+        out = np.zeros((len(queries), self.num_samples), np.uint32)
+        st = Stats()
+        self._check(self._k.kdbx_new2all_batch(self._p, kmers.ctypes.data if kmers.size else None, q_off.ctypes.data, len(queries),
+                                              out.ctypes.data if out.size else None, C.byref(st)))
+        return out, st
 
     def row_updates(self):
         out = np.zeros(self.num_samples, dtype=np.uint64)

@@ -17,10 +17,17 @@
  *   packed triangle        LowerTriangularMatrix::operator[]          src/array.h:140
  *   CSV bytes              All2AllConsole::run                        src/console_all2all.cpp:40-78
  *                          num2str / num2str_sparse                   src/conversion.h:248-299
+ *   sparse all2all         all2all_sp: every node a flat clique with its own num_kmers, no W
+ *                          accumulation (oracle_all2all_bruteforce)   src/similarity_calculator.cpp:442-657
+ *   k-mer tables           hash_map_lp raw form, find()               src/hashmap_lp.h:52-64,308-333,546-605
+ *   query vs database      one2all<false>                             src/similarity_calculator.cpp:810-925
+ *   k-mer extraction       KmerHelper::extract, MinHashFilter         src/kmer_extract.h:13-97, src/filter.h:40-115
+ *   FASTA records          GenomeInputFile::extractSubsequences       src/genome_input_file.h:287-337
+ *   new2all CSV            New2AllConsole::run                        src/console_new2all.cpp:98-161
  *
  * Parity is PINNED: tests/test_oracle.py checks this file against the reference's own golden
- * CSVs (test/virus/k18.csv, k18.sparse.csv, k24.csv, k18.frac.csv, test/synth/a2a, a2a-sparse;
- * committed under tests/golden/) and against the unmodified reference binary built by
+ * CSVs (test/virus/k18.csv, k18.sparse.csv, k24.csv, k18.frac.csv, k18.n2a.csv, k18.n2a.sparse.csv,
+ * test/synth/a2a, a2a-sparse, n2a, n2a-sparse; committed under tests/golden/) and against the unmodified reference binary built by
  * oracle/build_ref.sh (oracle/_ref/kmer-db) on generated databases.
  */
 #include <stdint.h>
@@ -44,6 +51,12 @@ typedef struct {
     uint64_t payload_words;
     char** names;
     uint64_t* sample_kmers;
+    /* k-mer tables (only with oracle_db_read_full): table t = slots[table_off[t] .. table_off[t+1]) */
+    double start_fraction;
+    int32_t alphabet;
+    uint64_t num_tables;
+    uint64_t* table_off;
+    uint64_t* slots; /* {u32 key; i32 val} as one little-endian u64; val == INT32_MAX: empty */
 } oracle_db;
 
 /* ---- Elias-gamma: (b-1) ones, a zero, then b-1 low bits, MSB-first in u64 words -------- */
@@ -135,20 +148,24 @@ static int rd(FILE* f, void* dst, size_t bytes) { return bytes == 0 || fread(dst
 void oracle_db_free(oracle_db* db) {
     if (!db) return;
     free(db->num_kmers); free(db->parent_id); free(db->n); free(db->l); free(db->last); free(db->bits);
-    free(db->payload_off); free(db->payload); free(db->sample_kmers);
+    free(db->payload_off); free(db->payload); free(db->sample_kmers); free(db->table_off); free(db->slots);
     if (db->names) for (uint32_t i = 0; i < db->num_samples; ++i) free(db->names[i]);
     free(db->names);
     free(db);
 }
 
-oracle_db* oracle_db_read(const char* path) {
+static oracle_db* db_read(const char* path, int with_tables);
+oracle_db* oracle_db_read(const char* path) { return db_read(path, 0); }
+oracle_db* oracle_db_read_full(const char* path) { return db_read(path, 1); }
+
+static oracle_db* db_read(const char* path, int with_tables) {
     FILE* f = fopen(path, "rb");
     if (!f) return NULL;
     oracle_db* db = (oracle_db*)calloc(1, sizeof(oracle_db));
     uint64_t format_word, kmers_count, nsamples, ntables, P;
-    double start_fraction; int32_t alphabet; uint8_t inited;
-    int ok = rd(f, &format_word, 8) && rd(f, &db->kmer_length, 4) && rd(f, &db->fraction, 8) && rd(f, &start_fraction, 8) &&
-             rd(f, &alphabet, 4) && rd(f, &inited, 1) && rd(f, &kmers_count, 8) && rd(f, &nsamples, 8);
+    uint8_t inited;
+    int ok = rd(f, &format_word, 8) && rd(f, &db->kmer_length, 4) && rd(f, &db->fraction, 8) && rd(f, &db->start_fraction, 8) &&
+             rd(f, &db->alphabet, 4) && rd(f, &inited, 1) && rd(f, &kmers_count, 8) && rd(f, &nsamples, 8);
     if (!ok) goto fail;
     db->num_samples = (uint32_t)nsamples;
     db->names = (char**)calloc(nsamples + 1, sizeof(char*));
@@ -160,12 +177,36 @@ oracle_db* oracle_db_read(const char* path) {
         if (!rd(f, db->names[i], len)) goto fail;
     }
     if (!rd(f, &ntables, 8)) goto fail;
+    uint64_t slot_cap = 0;
+    if (with_tables) {
+        if (!(format_word & 1)) goto fail;
+        db->num_tables = ntables;
+        db->table_off = (uint64_t*)calloc(ntables + 1, 8);
+    }
     for (uint64_t i = 0; i < ntables; ++i) {
         if (format_word & 1) { /* raw: f64 + 7 u64 header, bit-vector, filled slots */
             uint64_t hdr[8];
             if (!rd(f, hdr, sizeof hdr)) goto fail;
             const uint64_t filled = hdr[1], allocated = hdr[2];
-            if (fseeko(f, (off_t)(((allocated + 63) / 64) * 8 + filled * 8), SEEK_CUR)) goto fail;
+            if (!with_tables) {
+                if (fseeko(f, (off_t)(((allocated + 63) / 64) * 8 + filled * 8), SEEK_CUR)) goto fail;
+                continue;
+            }
+            /* rebuild the slot array: bit i of the bit-vector says slot i is used; the used slots
+             * follow in slot order (src/hashmap_lp.h:481-528) */
+            const uint64_t base = db->table_off[i], bvw = (allocated + 63) / 64;
+            db->table_off[i + 1] = base + allocated;
+            if (base + allocated > slot_cap) {
+                slot_cap = (base + allocated) * 2;
+                db->slots = (uint64_t*)realloc(db->slots, slot_cap * 8);
+            }
+            uint64_t* bv = (uint64_t*)malloc((bvw + 1) * 8);
+            if (!rd(f, bv, bvw * 8)) { free(bv); goto fail; }
+            for (uint64_t sidx = 0; sidx < allocated; ++sidx) {
+                if ((bv[sidx >> 6] >> (sidx & 63)) & 1) { if (!rd(f, &db->slots[base + sidx], 8)) { free(bv); goto fail; } }
+                else db->slots[base + sidx] = (uint64_t)0x7FFFFFFFu << 32;
+            }
+            free(bv);
         } else {
             uint64_t total, seen = 0, portion;
             if (!rd(f, &total, 8)) goto fail;
@@ -248,6 +289,185 @@ uint64_t oracle_all2all_file(const char* db_path, const char* csv_path, int spar
     free(tri);
     oracle_db_free(db);
     return U;
+}
+
+
+/* ---- query vs database: one2all<false> (src/similarity_calculator.cpp:810-925) ----------- */
+static uint32_t fmix32(uint32_t h) { h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16; return h; }
+
+/* pattern id stored for `kmer`, or -1 (hash_map_lp::find, src/hashmap_lp.h:308-333) */
+int64_t oracle_lookup(const oracle_db* db, uint64_t kmer) {
+    const uint64_t prefix = kmer >> 32;
+    const uint32_t suffix = (uint32_t)kmer;
+    if (prefix >= db->num_tables) return -1;
+    const uint64_t* t = db->slots + db->table_off[prefix];
+    const uint64_t mask = db->table_off[prefix + 1] - db->table_off[prefix] - 1;
+    for (uint64_t h = fmix32(suffix) & mask;; h = (h + 1) & mask) {
+        const uint32_t val = (uint32_t)(t[h] >> 32);
+        if (val == 0x7FFFFFFFu) return -1;
+        if ((uint32_t)t[h] == suffix) return (int64_t)val;
+    }
+}
+
+/* out[s] (N cells, zeroed here) = number of the query's k-mers present in sample s.  kmers must be
+ * unique (KmerHelper::unique, src/kmer_extract.h:113-119).  Returns the number of hits. */
+uint64_t oracle_one2all(const oracle_db* db, const uint64_t* kmers, uint64_t count, uint32_t* out) {
+    const uint32_t N = db->num_samples;
+    memset(out, 0, (size_t)N * 4);
+    int32_t* hit = (int32_t*)calloc(db->num_patterns + 1, 4); /* per-pattern hit counts (the unordered_map) */
+    uint32_t* full = (uint32_t*)malloc(((size_t)N + 1) * 4);
+    uint64_t hits = 0;
+    for (uint64_t i = 0; i < count; ++i) {
+        const int64_t pid = oracle_lookup(db, kmers[i]);
+        if (pid < 0 || db->num_kmers[pid] == 0) continue; /* :846-847 */
+        ++hit[pid];
+        ++hits;
+    }
+    for (uint64_t p = 0; p < db->num_patterns; ++p) {
+        if (!hit[p]) continue;
+        uint32_t* o = full + db->n[p];
+        for (int64_t q = (int64_t)p; q >= 0; q = db->parent_id[q]) { /* :890-900 */
+            o -= db->l[q];
+            oracle_decode_local(db->payload + db->payload_off[q], db->l[q], db->last[q], o);
+        }
+        for (uint32_t k = 0; k < db->n[p]; ++k) out[full[k]] += (uint32_t)hit[p];
+    }
+    free(hit); free(full);
+    return hits;
+}
+
+/* ---- k-mer extraction, written window by window (no rolling state) so that it is independent of
+ * the product's scanner: src/kmer_extract.h:13-97, alphabets src/alphabet.h:79-86 ----------------- */
+static const char* alphabet_groups(int32_t id, int* preserve) {
+    static const char* g[] = {"A,C,G,TU", "A,C,G,TU", "K,R,E,D,Q,N,C,G,H,I,L,V,M,F,Y,W,P,S,T,A", "KREDQN,C,G,H,ILV,M,F,Y,W,P,STA",
+                              "AST,C,DN,EQ,FY,G,H,IV,KR,LM,P,W", "STPAG,NDEQ,HRK,MILV,FYW,C"};
+    *preserve = id != 0;
+    return (id >= 0 && id <= 5) ? g[id] : NULL;
+}
+
+static uint64_t minhash_of(uint64_t x, uint32_t k) { /* src/filter.h:96-115 */
+    const uint64_t kd4 = (k + 3) / 4;
+    uint64_t h = x * 0x87c37b91114253d5ull;
+    h = (h << 31) | (h >> 33);
+    h *= 0x4cf5ad432745937full;
+    uint64_t h1 = (42 ^ h) ^ kd4, h2 = 42 ^ kd4;
+    h1 += h2; h2 += h1;
+    h1 ^= h1 >> 33; h1 *= 0xff51afd7ed558ccdull; h1 ^= h1 >> 33; h1 *= 0xc4ceb9fe1a85ec53ull; h1 ^= h1 >> 33;
+    h2 ^= h2 >> 33; h2 *= 0xff51afd7ed558ccdull; h2 ^= h2 >> 33; h2 *= 0xc4ceb9fe1a85ec53ull; h2 ^= h2 >> 33;
+    h1 += h2; h2 += h1;
+    return h1 ^ h2;
+}
+
+static int cmp_u64(const void* a, const void* b) { const uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b; return x < y ? -1 : x > y; }
+
+/* k-mers of one sequence appended to out (capacity: len).  Returns the new count. */
+static uint64_t extract_seq(const char* seq, uint64_t len, uint32_t k, int32_t alphabet, double fraction, double start, uint64_t* out,
+                            uint64_t cnt) {
+    int preserve, map[256], nsym = 1, bits = 0;
+    const char* g = alphabet_groups(alphabet, &preserve);
+    for (int i = 0; i < 256; ++i) map[i] = -1;
+    for (const char* c = g; *c; ++c) {
+        if (*c == ',') { ++nsym; continue; }
+        map[(unsigned char)*c] = nsym - 1;
+        map[(unsigned char)(*c - 'A' + 'a')] = nsym - 1;
+    }
+    while ((1 << bits) < nsym) ++bits;
+    const int prefix_bits = (int)k * bits - 32;
+    const uint32_t shift = prefix_bits < 8 ? (uint32_t)(8 - prefix_bits) : 0;
+    const uint64_t lo = (uint64_t)((double)UINT64_MAX * start), hi = (uint64_t)((double)UINT64_MAX * (start + fraction));
+    for (uint64_t i = 0; i + k <= len; ++i) {
+        uint64_t fwd = 0, rev = 0;
+        int ok = 1;
+        for (uint32_t j = 0; j < k; ++j) {
+            const int sy = map[(unsigned char)seq[i + j]];
+            if (sy < 0) { ok = 0; break; }
+            fwd = (fwd << bits) | (uint64_t)sy;
+            rev |= (uint64_t)(nsym - 1 - sy) << (bits * j); /* complement, reversed */
+        }
+        if (!ok) continue;
+        uint64_t can = (preserve || fwd < rev) ? fwd : rev;
+        can = (can << shift) | (can & ((1ull << shift) - 1));
+        if (fraction < 1.0) { const uint64_t h = minhash_of(can, k); if (!(h >= lo && h < hi)) continue; }
+        out[cnt++] = can;
+    }
+    return cnt;
+}
+
+/* new2all on files: database (with tables) x FASTA list -> CSV (src/console_new2all.cpp:12-174).
+ * list_path: whitespace-separated entries, opened as given or with .fa/.fna/.fasta appended (plain
+ * text only here).  multisample: every record is a query named by its header up to the first
+ * space; otherwise one query per file named by the entry's last path component.  Returns the
+ * number of queries or -1. */
+int64_t oracle_new2all_file(const char* db_path, const char* list_path, int multisample, const char* csv_path, int sparse) {
+    oracle_db* db = oracle_db_read_full(db_path);
+    if (!db) return -1;
+    FILE* lf = fopen(list_path, "rb");
+    FILE* out = fopen(csv_path, "wb");
+    if (!lf || !out) { if (lf) fclose(lf); if (out) fclose(out); oracle_db_free(db); return -1; }
+    fprintf(out, "kmer-length: %u fraction: %g ,db-samples ,", db->kmer_length, db->fraction);
+    for (uint32_t i = 0; i < db->num_samples; ++i) fprintf(out, "%s,", db->names[i]);
+    fprintf(out, "\nquery-samples,total-kmers,");
+    for (uint32_t i = 0; i < db->num_samples; ++i) fprintf(out, "%llu,", (unsigned long long)db->sample_kmers[i]);
+    fprintf(out, "\n");
+    uint32_t* sims = (uint32_t*)malloc(((size_t)db->num_samples + 1) * 4);
+    char entry[4096];
+    int64_t nq = 0;
+    while (fscanf(lf, "%4000s", entry) == 1) {
+        static const char* exts[] = {"", ".fa", ".fna", ".fasta"};
+        FILE* f = NULL;
+        char path[4200];
+        for (int e = 0; e < 4 && !f; ++e) { snprintf(path, sizeof path, "%s%s", entry, exts[e]); f = fopen(path, "rb"); }
+        if (!f) continue;
+        fseeko(f, 0, SEEK_END);
+        const uint64_t size = (uint64_t)ftello(f);
+        fseeko(f, 0, SEEK_SET);
+        char* data = (char*)malloc(size + 2);
+        if (fread(data, 1, size, f) != size) { fclose(f); free(data); continue; }
+        fclose(f);
+        data[size] = 0;
+        uint64_t* kmers = (uint64_t*)malloc((size + 1) * 8);
+        uint64_t cnt = 0;
+        const char* base = strrchr(entry, '/');
+        const char* qname = base ? base + 1 : entry;
+        char* p = strchr(data, '>');
+        char header[1024] = "";
+        while (p) {
+            char* eol = strchr(p, '\n');
+            if (!eol) eol = data + size;
+            size_t hl = (size_t)(eol - (p + 1));
+            if (hl && p[hl] == '\r') --hl;
+            if (hl > sizeof header - 1) hl = sizeof header - 1;
+            memcpy(header, p + 1, hl); header[hl] = 0;
+            char* sp = strchr(header, ' ');
+            if (sp) *sp = 0;
+            char* seq = (*eol) ? eol + 1 : eol;
+            char* next = strchr(seq, '>');
+            char* end = next ? next : data + size;
+            uint64_t w = 0;
+            for (char* c = seq; c < end; ++c) if (*c != '\n' && *c != '\r') seq[w++] = *c;
+            cnt = extract_seq(seq, w, db->kmer_length, db->alphabet, db->fraction, db->start_fraction, kmers, cnt);
+            if (multisample || !next) {
+                qsort(kmers, cnt, 8, cmp_u64);
+                uint64_t u = 0;
+                for (uint64_t i = 0; i < cnt; ++i) if (i == 0 || kmers[i] != kmers[i - 1]) kmers[u++] = kmers[i];
+                oracle_one2all(db, kmers, u, sims);
+                fprintf(out, "%s,%llu,", multisample ? header : qname, (unsigned long long)u);
+                for (uint32_t c = 0; c < db->num_samples; ++c) {
+                    if (!sparse) fprintf(out, "%u,", sims[c]);
+                    else if (sims[c]) fprintf(out, "%u:%u,", c + 1, sims[c]);
+                }
+                fprintf(out, "\n");
+                ++nq;
+                cnt = 0;
+            }
+            p = next;
+        }
+        free(kmers); free(data);
+    }
+    free(sims);
+    fclose(lf); fclose(out);
+    oracle_db_free(db);
+    return nq;
 }
 
 #ifdef ORACLE_MAIN

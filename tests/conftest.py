@@ -61,3 +61,30 @@ def golden_dbs(tmp_path_factory):
         "virus.k24": (k24, GOLDEN / "virus.k24.csv", None),
         "synth.k21": (GOLDEN / "synth.k21.db", GOLDEN / "synth.k21.csv", GOLDEN / "synth.k21.sparse.csv"),
     }
+
+
+@pytest.fixture(scope="session")
+def ref_fixtures(tmp_path_factory):
+    """The reference's own test inputs and golden outputs (tests/golden/reference_fixtures.tar.xz,
+    made by tests/golden/make_golden.sh), unpacked so that the list files' relative paths
+    (./test/virus/data/...) resolve from the returned directory."""
+    import tarfile
+    d = tmp_path_factory.mktemp("ref")
+    with tarfile.open(GOLDEN / "reference_fixtures.tar.xz", "r:xz") as tf:
+        tf.extractall(d, filter="data")
+    return d
+
+
+@pytest.fixture(scope="session")
+def cli(libs):
+    """Runs kmer-db-b200 from a working directory; returns the CompletedProcess."""
+    exe = PKG / "bin" / "kmer-db-b200"
+    if not exe.exists():
+        _make(PKG)
+
+    def run(cwd, *args, check=True):
+        r = subprocess.run([str(exe), *map(str, args)], cwd=str(cwd), capture_output=True, text=True)
+        if check and r.returncode != 0:
+            raise AssertionError(f"kmer-db-b200 {' '.join(map(str, args))} failed ({r.returncode}): {r.stderr[-2000:]}")
+        return r
+    return run

@@ -20,3 +20,8 @@ cp test/virus/k18.frac.csv "$HERE/virus.k18.f01.csv"
 cp test/virus/k24.csv "$HERE/virus.k24.csv"
 cp test/synth/a2a "$HERE/synth.k21.csv"
 cp test/synth/a2a-sparse "$HERE/synth.k21.sparse.csv"
+# database of the first 100 virus genomes (the CI's k18.parts.db, .github/workflows/main.yml:73) for new2all
+"$BIN" build test/virus/seqs.part1.list "$HERE/virus.k18.part1.db"
+# the reference's test INPUTS (FASTA, lists) and every golden OUTPUT of test/virus, test/synth and the
+# amino-acid part of test/protein, verbatim, for the CLI tests (build / new2all / distance / all2all-sp)
+tar cJf "$HERE/reference_fixtures.tar.xz" test/virus test/synth test/protein/aa_100x1000.fasta test/protein/*.a2a

@@ -1,0 +1,162 @@
+"""Host-side modes of the CLI (build, distance) and the host builder against the reference's own
+CI vectors (.github/workflows/main.yml:45-165, self-hosted.yml:91-426).  CPU only: databases we
+build are checked by running the ORACLE's all2all / new2all on them and comparing with the
+reference's golden CSVs."""
+import ctypes as C
+import shutil
+
+import numpy as np
+import pytest
+
+import oracle_util as ou
+
+
+def _oracle_all2all_csv(oracle, db, out, sparse=False):
+    assert oracle.oracle_all2all_file(str(db).encode(), str(out).encode(), 1 if sparse else 0) != 2**64 - 1
+    return ou.read_bytes(out)
+
+
+def _oracle_new2all_csv(oracle, db, lst, out, multi=False, sparse=False, cwd=None):
+    import os
+    old = os.getcwd()
+    os.chdir(cwd)
+    try:
+        n = oracle.oracle_new2all_file(str(db).encode(), str(lst).encode(), 1 if multi else 0, str(out).encode(), 1 if sparse else 0)
+    finally:
+        os.chdir(old)
+    assert n >= 0
+    return ou.read_bytes(out)
+
+
+@pytest.mark.parametrize("args,golden", [
+    (["test/virus/seqs.list"], "test/virus/k18.csv"),
+    (["-multisample-fasta", "test/virus/multi.list"], "test/virus/k18.csv"),
+    (["-multisample-fasta", "test/virus/multi.split.list"], "test/virus/k18.csv"),
+    (["-f", "0.1", "test/virus/seqs.list"], "test/virus/k18.frac.csv"),
+    (["-k", "24", "test/virus/seqs.list"], "test/virus/k24.csv"),
+    (["-t", "1", "test/virus/seqs.list"], "test/virus/k18.csv"),
+    (["-multisample-fasta", "-k", "21", "test/synth/synth.list"], "test/synth/a2a"),
+])
+def test_build_then_oracle_all2all_reproduces_reference_csv(cli, oracle, ref_fixtures, tmp_path, args, golden):
+    cli(ref_fixtures, "build", *args, tmp_path / "x.db")
+    assert _oracle_all2all_csv(oracle, tmp_path / "x.db", tmp_path / "x.csv") == ou.read_bytes(ref_fixtures / golden)
+
+
+def test_build_extend(cli, oracle, ref_fixtures, tmp_path):
+    """build part1, then -extend with part2 (k given on the command line is ignored, main.yml:132-135)."""
+    db = tmp_path / "parts.db"
+    cli(ref_fixtures, "build", "test/virus/seqs.part1.list", db)
+    cli(ref_fixtures, "build", "-extend", "-k", "25", "test/virus/seqs.part2.list", db)
+    assert _oracle_all2all_csv(oracle, db, tmp_path / "x.csv") == ou.read_bytes(ref_fixtures / "test/virus/k18.csv")
+    assert _oracle_all2all_csv(oracle, db, tmp_path / "s.csv", sparse=True) == ou.read_bytes(ref_fixtures / "test/virus/k18.sparse.csv")
+
+
+@pytest.mark.parametrize("alphabet", ["aa", "aa11_diamond", "aa12_mmseqs", "aa6_dayhoff"])
+def test_build_amino_alphabets(cli, oracle, ref_fixtures, tmp_path, alphabet):
+    cli(ref_fixtures, "build", "-k", "8", "-multisample-fasta", "-alphabet", alphabet, "test/protein/aa_100x1000.fasta", tmp_path / "a.db")
+    assert _oracle_all2all_csv(oracle, tmp_path / "a.db", tmp_path / "a.csv") == ou.read_bytes(ref_fixtures / f"test/protein/{alphabet}.a2a")
+
+
+def test_built_kmer_tables_serve_queries(cli, oracle, ref_fixtures, golden_dbs, tmp_path):
+    """The k-mer tables our build writes must answer the reference's new2all vectors; the same
+    oracle on the database the REFERENCE built (tests/golden) pins the oracle itself."""
+    ours = tmp_path / "p1.db"
+    cli(ref_fixtures, "build", "test/virus/seqs.part1.list", ours)
+    theirs = ou.ROOT / "tests" / "golden" / "virus.k18.part1.db"
+    for db in (ours, theirs):
+        got = _oracle_new2all_csv(oracle, db, "test/virus/seqs.part2.list", tmp_path / "n.csv", cwd=ref_fixtures)
+        assert got == ou.read_bytes(ref_fixtures / "test/virus/k18.n2a.csv")
+        got = _oracle_new2all_csv(oracle, db, "test/virus/seqs.part2.list", tmp_path / "n.csv", sparse=True, cwd=ref_fixtures)
+        assert got == ou.read_bytes(ref_fixtures / "test/virus/k18.n2a.sparse.csv")
+    got = _oracle_new2all_csv(oracle, golden_dbs["virus.k18"][0], "test/virus/seqs.list", tmp_path / "i.csv", cwd=ref_fixtures)
+    assert got == ou.read_bytes(ref_fixtures / "test/virus/k18.n2a.itself.csv")
+    got = _oracle_new2all_csv(oracle, golden_dbs["synth.k21"][0], "test/synth/synth.list", tmp_path / "s.csv", multi=True, cwd=ref_fixtures)
+    assert got == ou.read_bytes(ref_fixtures / "test/synth/n2a")
+    got = _oracle_new2all_csv(oracle, golden_dbs["synth.k21"][0], "test/synth/synth.list", tmp_path / "s.csv", multi=True, sparse=True,
+                              cwd=ref_fixtures)
+    assert got == ou.read_bytes(ref_fixtures / "test/synth/n2a-sparse")
+
+
+def test_reference_binary_accepts_our_database(cli, ref_bin, ref_fixtures, tmp_path):
+    if ref_bin is None:
+        pytest.skip("reference binary not built (oracle/_ref)")
+    import subprocess
+    cli(ref_fixtures, "build", "test/virus/seqs.part1.list", tmp_path / "p1.db")
+    subprocess.run([str(ref_bin), "new2all", str(tmp_path / "p1.db"), "test/virus/seqs.part2.list", str(tmp_path / "n.csv")],
+                   cwd=str(ref_fixtures), check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    assert ou.read_bytes(tmp_path / "n.csv") == ou.read_bytes(ref_fixtures / "test/virus/k18.n2a.csv")
+    subprocess.run([str(ref_bin), "build", "-extend", "test/virus/seqs.part2.list", str(tmp_path / "p1.db")],
+                   cwd=str(ref_fixtures), check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([str(ref_bin), "all2all", str(tmp_path / "p1.db"), str(tmp_path / "a.csv")],
+                   cwd=str(ref_fixtures), check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    assert ou.read_bytes(tmp_path / "a.csv") == ou.read_bytes(ref_fixtures / "test/virus/k18.csv")
+
+
+DISTANCE_CASES = [  # (arguments, input table, golden output) — main.yml:99-110, self-hosted.yml:146-260
+    (["jaccard"], "test/virus/k18.csv", "test/virus/k18.csv.jaccard"),
+    (["min"], "test/virus/k18.csv", "test/virus/k18.csv.min"),
+    (["max"], "test/virus/k18.csv", "test/virus/k18.csv.max"),
+    (["cosine"], "test/virus/k18.csv", "test/virus/k18.csv.cosine"),
+    (["mash"], "test/virus/k18.csv", "test/virus/k18.csv.mash"),
+    (["mash"], "test/synth/a2a", "test/synth/a2a.mash"),
+    (["ani"], "test/synth/a2a", "test/synth/a2a.ani"),
+    (["-sparse", "ani"], "test/synth/a2a", "test/synth/a2a-sparse.ani"),
+    (["-sparse", "-max", "1.0", "-min", "-1.0", "mash"], "test/synth/a2a", "test/synth/a2a-sparse.mash"),
+    (["mash"], "test/synth/a2a-sparse", "test/synth/a2a-sparse.mash"),
+    (["ani"], "test/synth/a2a-sparse", "test/synth/a2a-sparse.ani"),
+    (["-sparse", "mash", "-min", "0.03", "-max", "mash:1.0"], "test/synth/a2a-sparse", "test/synth/a2a.mash.above-below"),
+    (["-sparse", "-min", "0.03", "-max", "mash:1.0", "-min", "num-kmers:36", "mash"], "test/synth/a2a", "test/synth/a2a.mash-sparse-min2max"),
+    (["mash"], "test/synth/n2a", "test/synth/n2a.mash"),
+    (["ani"], "test/synth/n2a", "test/synth/n2a.ani"),
+    (["-sparse", "ani"], "test/synth/n2a", "test/synth/n2a-sparse.ani"),
+    (["-sparse", "-max", "1.0", "-min", "-1.0", "mash"], "test/synth/n2a", "test/synth/n2a-sparse.mash"),
+    (["mash"], "test/synth/n2a-sparse", "test/synth/n2a-sparse.mash"),
+    (["ani"], "test/synth/n2a-sparse", "test/synth/n2a-sparse.ani"),
+]
+
+
+@pytest.mark.parametrize("args,table,golden", DISTANCE_CASES)
+def test_distance_bytes(cli, ref_fixtures, tmp_path, args, table, golden):
+    cli(ref_fixtures, "distance", *args, table, tmp_path / "d.csv")
+    assert ou.read_bytes(tmp_path / "d.csv") == ou.read_bytes(ref_fixtures / golden)
+
+
+def test_cli_errors(cli, ref_fixtures, tmp_path):
+    r = cli(ref_fixtures, "distance", "nonsense", "test/synth/a2a", tmp_path / "d", check=False)
+    assert r.returncode != 0 and "ERROR" in r.stderr
+    r = cli(ref_fixtures, "distance", "-min", "foo:1", "mash", "test/synth/a2a", tmp_path / "d", check=False)
+    assert r.returncode != 0 and "unknown metric" in r.stderr
+    r = cli(ref_fixtures, "build", "-k", "40", "test/virus/seqs.list", tmp_path / "x.db", check=False)
+    assert r.returncode != 0 and "cannot exceed" in r.stderr
+    r = cli(ref_fixtures, "build", "missing.list", tmp_path / "x.db", check=False)
+    assert r.returncode != 0 and "Unable to open input file" in r.stderr
+    r = cli(ref_fixtures, "build", "only-one-file", check=False)
+    assert r.returncode != 0
+    assert cli(ref_fixtures, "-version").stdout.startswith("kmer-db-b200")
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_builder_matches_set_intersections(libs, oracle, seed):
+    """Semantic ground truth: M[s][t] = |K_s ∩ K_t| for k-mer sets K_s — checked
+    on databases the host builder makes from random overlapping sets, through the oracle's
+    all2all and its one2all."""
+    rng = np.random.default_rng(seed)
+    N = int(rng.integers(2, 40))
+    universe = np.unique(rng.integers(0, 1 << 40, size=3000, dtype=np.uint64))
+    sets = []
+    for s in range(N):
+        base = sets[int(rng.integers(0, s))] if s and rng.random() < 0.7 else universe[rng.random(universe.size) < 0.2]
+        keep = base[rng.random(base.size) < 0.9]
+        extra = universe[rng.random(universe.size) < 0.02]
+        sets.append(np.unique(np.concatenate([keep, extra])))
+    if seed == 1:
+        sets[3 % N] = np.zeros(0, np.uint64)  # an empty sample is registered but adds nothing
+    t = libs.Trie.build([(f"s{i}", k) for i, k in enumerate(sets)], k=20)
+    t.validate()
+    assert t.sample_kmer_counts().tolist() == [len(k) for k in sets]
+    tri, _ = ou.oracle_all2all(oracle, N, t.arrays())
+    want = np.zeros(ou.tri_cells(N), np.uint32)
+    for a in range(1, N):
+        for b in range(a):
+            want[a * (a - 1) // 2 + b] = np.intersect1d(sets[a], sets[b], assume_unique=True).size
+    assert np.array_equal(tri, want)

@@ -1,0 +1,216 @@
+"""GPU parity of the widened rows: sparse all2all, new2all, and the CLI end
+to end on the reference's CI vectors.  Needs a B200: -m gpu."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_util as ou
+
+pytestmark = pytest.mark.gpu
+
+
+def _dense_to_rows(tri, N, keep):
+    rows = []
+    for s in range(N):
+        r = tri[ou.tri_cells(s):ou.tri_cells(s) + s]
+        cols = [c for c in range(s) if r[c] != 0 and keep(int(r[c]), s, c)]
+        rows.append((cols, [int(r[c]) for c in cols]))
+    return rows
+
+
+def _csr_rows(row_ptr, col, val):
+    return [(col[int(row_ptr[s]):int(row_ptr[s + 1])].tolist(), val[int(row_ptr[s]):int(row_ptr[s + 1])].tolist())
+            for s in range(len(row_ptr) - 1)]
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_sparse_equals_flat_clique_oracle(libs, oracle, seed):
+    """all2all_sp's own algorithm (every node a clique with its raw num_kmers, no W accumulation,
+    src/similarity_calculator.cpp:596-638) restated in the oracle must give the same rows."""
+    rng = np.random.default_rng(40 + seed)
+    N = int(rng.integers(2, 300))
+    a, _ = ou.random_trie(rng, N, int(rng.integers(2, 1200)), max_local=int(rng.integers(1, 20)), big_weights=(seed % 2 == 0))
+    want = ou.oracle_bruteforce(oracle, N, a)
+    cfgs = [dict(), dict(sparse_block_cells=max(N, ou.tri_cells(N) // 7))]  # one block / many row blocks
+    for cfg in cfgs:
+        with libs.Context(device=0, **cfg) as c:
+            v, keep = libs.view_from_arrays(N, a["num_kmers"], a["parent_id"], a["n"], a["l"], a["last"], a["bits"], a["payload_off"], a["payload"])
+            c.load_patterns(v, keep)
+            rp, col, val, st = c.all2all_sparse()
+        assert _csr_rows(rp, col, val) == _dense_to_rows(want, N, lambda v_, s, c_: True)
+        assert int(rp[-1]) == int(np.count_nonzero(want))
+
+
+def test_sparse_filters_on_device(libs, oracle):
+    rng = np.random.default_rng(77)
+    N = 200
+    a, _ = ou.random_trie(rng, N, 900, max_local=15)
+    dense, _ = ou.oracle_all2all(oracle, N, a)
+    cnt = rng.integers(1, 5000, size=N).astype(np.uint32)
+    cnt[5] = 0
+    with libs.Context(device=0, sparse_block_cells=5000) as c:
+        v, keep = libs.view_from_arrays(N, a["num_kmers"], a["parent_id"], a["n"], a["l"], a["last"], a["bits"], a["payload_off"], a["payload"])
+        c.load_patterns(v, keep)
+        lo, hi = int(np.percentile(dense[dense > 0], 30)), int(np.percentile(dense[dense > 0], 90))
+        rp, col, val, _ = c.all2all_sparse(min_common=lo, max_common=hi)
+        assert _csr_rows(rp, col, val) == _dense_to_rows(dense, N, lambda x, s, t: lo <= x <= hi)
+        # metric bounds, evaluated with the reference's arithmetic (uint32 wrap, IEEE double)
+        def jac(x, s, t):
+            d = np.uint32(cnt[s] + cnt[t] - np.uint32(x))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                return np.float64(x) / np.float64(d)
+        def cosine(x, s, t):
+            with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+                return np.float64(x) / np.sqrt(np.float64(np.uint32(cnt[s] * cnt[t])))
+        for name, fn, b in (("jaccard", jac, (0.002, 0.5)), ("cosine", cosine, (0.001, 0.2)),
+                            ("min", lambda x, s, t: np.float64(x) / np.float64(min(cnt[s], cnt[t])), (0.01, 1.0)),
+                            ("max", lambda x, s, t: np.float64(x) / np.float64(max(cnt[s], cnt[t])), (0.001, 0.05))):
+            with np.errstate(divide="ignore", invalid="ignore"):
+                rp, col, val, _ = c.all2all_sparse(metric_bounds=[(name, b[0], b[1])], sample_kmers=cnt)
+                want = _dense_to_rows(dense, N, lambda x, s, t: bool(fn(x, s, t) >= b[0]) and bool(fn(x, s, t) <= b[1]))
+            assert _csr_rows(rp, col, val) == want, name
+
+
+def _random_db(libs, rng, N, universe_size=4000, k=20):
+    universe = np.unique(rng.integers(0, 1 << 40, size=universe_size, dtype=np.uint64))
+    sets = []
+    for s in range(N):
+        base = sets[int(rng.integers(0, s))] if s and rng.random() < 0.7 else universe[rng.random(universe.size) < 0.2]
+        sets.append(np.unique(np.concatenate([base[rng.random(base.size) < 0.9], universe[rng.random(universe.size) < 0.02]])))
+    return libs.Trie.build([(f"s{i}", x) for i, x in enumerate(sets)], k=k, pinned=False), sets, universe
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_new2all_equals_set_intersections(libs, seed):
+    rng = np.random.default_rng(200 + seed)
+    N = int(rng.integers(2, 120))
+    t, sets, universe = _random_db(libs, rng, N)
+    queries = [np.unique(np.concatenate([universe[rng.random(universe.size) < 0.3], rng.integers(0, 1 << 40, size=50, dtype=np.uint64)]))
+               for _ in range(int(rng.integers(1, 9)))]
+    queries.append(np.zeros(0, np.uint64))          # empty query
+    queries.append(sets[0].copy())                    # a database sample itself
+    for cfg in (dict(), dict(query_batch_kmers=1500)):  # one device pass / several
+        with libs.Context(device=0, **cfg) as c:
+            c.load_patterns(t)
+            c.load_hashtables(t)
+            out, st = c.new2all_batch(queries)
+        want = np.array([[np.intersect1d(q, s, assume_unique=True).size for s in sets] for q in queries], np.uint32)
+        assert np.array_equal(out, want)
+        assert st.probes == sum(len(q) for q in queries)
+        assert st.hits == sum(int(np.isin(q, universe).sum()) for q in queries if len(q)) or st.hits <= st.probes
+
+
+def test_new2all_matches_oracle_on_reference_database(libs, oracle, ref_fixtures, golden_dbs):
+    """The reference-built database of 100 virus genomes and the CI's 65 queries: device result ==
+    oracle's one2all row by row."""
+    db = ou.ROOT / "tests" / "golden" / "virus.k18.part1.db"
+    t = libs.Trie.read_db_full(db)
+    import os
+    old = os.getcwd()
+    os.chdir(ref_fixtures)
+    try:
+        samples = libs.load_samples("test/virus/seqs.part2.list", k=18)
+    finally:
+        os.chdir(old)
+    assert len(samples) == 65
+    with libs.Context(device=0) as c:
+        c.load_patterns(t)
+        c.load_hashtables(t)
+        out, st = c.new2all_batch([k for _, k in samples])
+    oracle.oracle_db_read_full.restype = C.c_void_p
+    oracle.oracle_one2all.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    oracle.oracle_one2all.restype = C.c_uint64
+    oracle.oracle_db_free.argtypes = [C.c_void_p]
+    odb = oracle.oracle_db_read_full(str(db).encode())
+    assert odb
+    hits = 0
+    for q, (_, kmers) in enumerate(samples):
+        row = np.zeros(t.num_samples, np.uint32)
+        hits += oracle.oracle_one2all(odb, kmers.ctypes.data, kmers.size, row.ctypes.data)
+        assert np.array_equal(out[q], row), q
+    oracle.oracle_db_free(odb)
+    assert st.hits == hits
+
+
+def test_misuse_is_an_error(libs):
+    t = libs.Trie.synth(num_samples=20, num_clusters=1, genome_kmers=2000, seed=1)
+    with libs.Context(device=0) as c:
+        c.load_patterns(t)
+        with pytest.raises(libs.KdbxError, match="no k-mer tables loaded"):
+            c.new2all_batch([np.arange(5, dtype=np.uint64)])
+        with pytest.raises(libs.KdbxError, match="without its k-mer tables"):
+            c.load_hashtables(t)
+        with pytest.raises(libs.KdbxError, match="need sample_kmers"):
+            c.all2all_sparse(metric_bounds=[("jaccard", 0.0, 1.0)])
+
+
+# ---- the CLI on the reference's CI sequences (main.yml:71-165, self-hosted.yml:110-260) ------------
+def test_cli_virus_sequence(cli, ref_fixtures, tmp_path):
+    g = lambda p: ou.read_bytes(ref_fixtures / p)
+    cli(ref_fixtures, "build", "test/virus/seqs.part1.list", tmp_path / "parts.db")
+    cli(ref_fixtures, "new2all", tmp_path / "parts.db", "test/virus/seqs.part2.list", tmp_path / "n2a.csv")
+    assert ou.read_bytes(tmp_path / "n2a.csv") == g("test/virus/k18.n2a.csv")
+    cli(ref_fixtures, "new2all", "-sparse", tmp_path / "parts.db", "test/virus/seqs.part2.list", tmp_path / "n2a.s.csv")
+    assert ou.read_bytes(tmp_path / "n2a.s.csv") == g("test/virus/k18.n2a.sparse.csv")
+    cli(ref_fixtures, "build", "-extend", "-k", "25", "test/virus/seqs.part2.list", tmp_path / "parts.db")
+    cli(ref_fixtures, "all2all", tmp_path / "parts.db", tmp_path / "k18.csv")
+    assert ou.read_bytes(tmp_path / "k18.csv") == g("test/virus/k18.csv")
+    cli(ref_fixtures, "all2all", "-sparse", tmp_path / "parts.db", tmp_path / "k18.s.csv")
+    assert ou.read_bytes(tmp_path / "k18.s.csv") == g("test/virus/k18.sparse.csv")
+    cli(ref_fixtures, "all2all-sp", tmp_path / "parts.db", tmp_path / "k18.sp.csv")
+    assert ou.read_bytes(tmp_path / "k18.sp.csv") == g("test/virus/k18.sparse.csv")
+    for m in ("jaccard", "min", "max", "cosine", "mash"):
+        cli(ref_fixtures, "distance", m, tmp_path / "k18.csv", tmp_path / f"k18.{m}")
+        assert ou.read_bytes(tmp_path / f"k18.{m}") == g(f"test/virus/k18.csv.{m}")
+    cli(ref_fixtures, "build", "-f", "0.1", "test/virus/seqs.list", tmp_path / "frac.db")
+    cli(ref_fixtures, "all2all", tmp_path / "frac.db", tmp_path / "frac.csv")
+    assert ou.read_bytes(tmp_path / "frac.csv") == g("test/virus/k18.frac.csv")
+    cli(ref_fixtures, "build", "test/virus/seqs.list", tmp_path / "k18.db")
+    cli(ref_fixtures, "new2all", tmp_path / "k18.db", "test/virus/seqs.list", tmp_path / "itself.csv")
+    assert ou.read_bytes(tmp_path / "itself.csv") == g("test/virus/k18.n2a.itself.csv")
+    cli(ref_fixtures, "new2all", "-multisample-fasta", tmp_path / "k18.db", "test/virus/multi.list", tmp_path / "itself.m.csv")
+    assert ou.read_bytes(tmp_path / "itself.m.csv") == g("test/virus/k18.n2a.itself.csv")
+
+
+def test_cli_synth_sequence(cli, ref_fixtures, tmp_path):
+    g = lambda p: ou.read_bytes(ref_fixtures / p)
+    db = tmp_path / "synth.db"
+    cli(ref_fixtures, "build", "-multisample-fasta", "-k", "21", "test/synth/synth.list", db)
+    cli(ref_fixtures, "all2all", db, tmp_path / "a2a")
+    assert ou.read_bytes(tmp_path / "a2a") == g("test/synth/a2a")
+    cli(ref_fixtures, "all2all", "-sparse", db, tmp_path / "a2a-sparse")
+    assert ou.read_bytes(tmp_path / "a2a-sparse") == g("test/synth/a2a-sparse")
+    cli(ref_fixtures, "all2all", "-sparse", "-max", "39", "-min", "num-kmers:31", db, tmp_path / "mm")
+    assert ou.read_bytes(tmp_path / "mm") == g("test/synth/a2a.sparse.above-below")
+    cli(ref_fixtures, "all2all-sp", db, tmp_path / "a2a-sp")
+    assert ou.read_bytes(tmp_path / "a2a-sp") == g("test/synth/a2a-sparse")
+    cli(ref_fixtures, "all2all-sp", "-max", "39", "-min", "num-kmers:31", db, tmp_path / "sp-mm")
+    assert ou.read_bytes(tmp_path / "sp-mm") == g("test/synth/a2a.sparse.above-below")
+    cli(ref_fixtures, "new2all", "-multisample-fasta", db, "test/synth/synth.list", tmp_path / "n2a")
+    assert ou.read_bytes(tmp_path / "n2a") == g("test/synth/n2a")
+    cli(ref_fixtures, "new2all", "-multisample-fasta", "-sparse", db, "test/synth/synth.list", tmp_path / "n2a-s")
+    assert ou.read_bytes(tmp_path / "n2a-s") == g("test/synth/n2a-sparse")
+    cli(ref_fixtures, "new2all", "-multisample-fasta", "-sparse", "-max", "69", "-min", "num-kmers:21", db, "test/synth/synth.list", tmp_path / "n2a-mm")
+    assert ou.read_bytes(tmp_path / "n2a-mm") == g("test/synth/n2a.sparse.above-below")
+    # a log-based metric bound is applied on the host side of all2all-sp: same rows as distance -sparse
+    cli(ref_fixtures, "all2all-sp", "-min", "ani:0.95", db, tmp_path / "sp-ani")
+    cli(ref_fixtures, "all2all", "-sparse", "-min", "ani:0.95", db, tmp_path / "dense-ani")
+    assert ou.read_bytes(tmp_path / "sp-ani") == ou.read_bytes(tmp_path / "dense-ani")
+
+
+def test_cli_protein_alphabet(cli, ref_fixtures, tmp_path):
+    cli(ref_fixtures, "build", "-k", "8", "-multisample-fasta", "-alphabet", "aa12_mmseqs", "test/protein/aa_100x1000.fasta", tmp_path / "aa.db")
+    cli(ref_fixtures, "all2all", tmp_path / "aa.db", tmp_path / "aa.a2a")
+    assert ou.read_bytes(tmp_path / "aa.a2a") == ou.read_bytes(ref_fixtures / "test/protein/aa12_mmseqs.a2a")
+
+
+def test_cli_multi_gpu_flag(cli, libs, ref_fixtures, golden_dbs, tmp_path):
+    k, _ = libs.load()
+    n = k.kdbx_device_count()
+    if n < 2:
+        r = cli(ref_fixtures, "all2all", "-gpus", "2", golden_dbs["virus.k18"][0], tmp_path / "x.csv", check=False)
+        assert r.returncode != 0 and "only 1 B200" in r.stderr
+        return
+    cli(ref_fixtures, "all2all", "-gpus", str(min(n, 4)), golden_dbs["virus.k18"][0], tmp_path / "x.csv")
+    assert ou.read_bytes(tmp_path / "x.csv") == ou.read_bytes(golden_dbs["virus.k18"][1])
