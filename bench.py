@@ -20,8 +20,11 @@ reference's dense path.
            measured HBM copy bandwidth in MEASURED_PEAKS.json.
   cpu_baseline  the reference binary (oracle/_ref/kmer-db all2all -t <all cores>) on a bounded sample:
            the first cluster (250 genomes x 5 Mbp = exactly a quarter of the workload's updates).
-With N>1 (torchrun, one rank per GPU) the matrix is sharded by contiguous row blocks balanced on
-per-row update counts; no collective on the data path; total work is fixed => "strong" scaling.
+With N>1 (torchrun, one rank per GPU) total work is fixed => "strong" scaling.  Default sharding: every rank
+holds the whole trie, executes the pattern chunks c with c % N == rank into a partial matrix, and ONE NCCL
+all-reduce (uint32 sum over NVLink) adds the partial matrices — the exchange step BASELINE.json's north_star
+names.  `--shard rows` instead gives every rank a contiguous block of matrix rows balanced on per-row update
+counts (no collective, but the decode/expand/bucketing stages are then replicated on every rank).
 """
 import argparse
 import json
@@ -54,6 +57,11 @@ def parse_args():
     ap.add_argument("--chunk-ids", type=int, default=0)
     ap.add_argument("--tile-cols", type=int, default=0)
     ap.add_argument("--unit-updates", type=int, default=0)
+    ap.add_argument("--tile-rows", type=int, default=0)
+    ap.add_argument("--scatter-threads", type=int, default=0)
+    ap.add_argument("--shard", choices=["patterns", "rows"], default="patterns",
+                    help="N>1: 'patterns' = every rank runs its share of pattern chunks into a partial matrix, one NCCL "
+                         "all-reduce adds them; 'rows' = contiguous row blocks balanced on per-row updates, no collective")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cache-dir", default=os.environ.get("KDBX_CACHE", "/tmp/kdbx_cache"))
@@ -231,28 +239,55 @@ def main():
     trie, db_path = get_workload(kdbx, a, a.samples, a.clusters, pinned=True, rank=rank, barrier=barrier if world > 1 else None)
     tot = trie.totals()
     N, P, U_total = int(tot.num_samples), int(tot.num_patterns), int(tot.updates)
-    ctx = kdbx.Context(device=local_rank, chunk_ids=a.chunk_ids, tile_cols=a.tile_cols, unit_updates=a.unit_updates)
+    by_patterns = world > 1 and a.shard == "patterns"
+    chunk_ids = a.chunk_ids
+    if by_patterns and chunk_ids == 0:
+        chunk_ids = max(1 << 22, (64 << 20) // world)  # finer chunks: ~62 per rank, balanced round-robin
+    ctx = kdbx.Context(device=local_rank, chunk_ids=chunk_ids, tile_cols=a.tile_cols, unit_updates=a.unit_updates,
+                       tile_rows=a.tile_rows, scatter_threads=a.scatter_threads)
     ctx.load_patterns(trie)
-    upd = ctx.row_updates()
-    assert int(upd.sum()) == U_total, "device row-update counts disagree with U of the trie"
-    bounds = kdbx.shard_rows_by_work(upd, world)
-    r0, r1 = bounds[rank], bounds[rank + 1]
-    U_rank = int(upd[r0:r1].sum())
+    if by_patterns:
+        r0, r1 = 0, N
+    else:
+        upd = ctx.row_updates()
+        assert int(upd.sum()) == U_total, "device row-update counts disagree with U of the trie"
+        bounds = kdbx.shard_rows_by_work(upd, world)
+        r0, r1 = bounds[rank], bounds[rank + 1]
     cells = kdbx.tri_cells(r1) - kdbx.tri_cells(r0)
     d_out = torch.zeros(max(1, cells), dtype=torch.int32, device="cuda")
 
+    def step():
+        """One all2all over the resident trie; returns the library's stats."""
+        if by_patterns:
+            st = ctx.all2all_dense_part_device(rank, world, d_out.data_ptr())
+            dist.all_reduce(d_out)  # uint32 sums wrap like int32 sums: same bits
+        else:
+            st = ctx.all2all_dense_rows_device(r0, r1, d_out.data_ptr())
+        return st
+
+    def total_updates(st_updates):
+        if dist is None:
+            return st_updates
+        t = torch.tensor([st_updates], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        return int(t.item())
+
     # ---- device-resident leg -------------------------------------------------------------
     for _ in range(a.warmup):
-        st = ctx.all2all_dense_rows_device(r0, r1, d_out.data_ptr())
-        assert st.updates == U_rank
+        st = step()
+    assert total_updates(int(st.updates)) == U_total, "updates executed by all ranks != U of the trie"
+    U_rank = int(st.updates)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     wall0 = time.perf_counter()
     dev_ms = scat_ms = 0.0
     launches = scat_launches = 0
     stage = {"prepare": 0.0, "expand": 0.0, "bucket": 0.0, "scatter": 0.0}
-    for _ in range(a.steps):
-        st = ctx.all2all_dense_rows_device(r0, r1, d_out.data_ptr())
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    for i in range(a.steps):
+        ev[i][0].record()
+        st = step()
+        ev[i][1].record()
         assert st.updates == U_rank
         dev_ms += st.ms_total
         scat_ms += st.ms_scatter
@@ -263,21 +298,34 @@ def main():
     barrier()
     wall_ms = (time.perf_counter() - wall0) * 1e3
     clocks = sampler.stop() if sampler else None
+    if dist is not None:
+        # with a collective in the step, time the whole step: CUDA events on torch's stream bracket the
+        # (synchronous) library call and the NCCL all-reduce that follows it
+        dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
     T_ms = max_over_ranks(dev_ms)
     value = U_total * a.steps / (T_ms / 1e3)
     checksum = int(d_out[:cells].to(torch.int64).sum().item()) if cells else 0
 
-    # ---- end-to-end leg: host trie -> H2D -> compute -> D2H host matrix ----------------------
+    # ---- end-to-end leg: host trie -> H2D -> compute (-> all-reduce) -> D2H host matrix ----------
     e2e = None
     if not a.no_e2e:
         out_host = kdbx.pinned_empty(max(1, cells), np.uint32)
-        ctx.load_patterns(trie)
-        ctx.all2all_dense_rows(r0, r1, out_host[:cells])
+        out_t = torch.from_numpy(out_host.view(np.int32))
+
+        def e2e_step():
+            ctx.load_patterns(trie)
+            if by_patterns:
+                st2 = step()
+                out_t.copy_(d_out, non_blocking=False)
+            else:
+                _, st2 = ctx.all2all_dense_rows(r0, r1, out_host[:cells])
+            return st2
+        e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(a.steps):
-            ctx.load_patterns(trie)
-            _, st2 = ctx.all2all_dense_rows(r0, r1, out_host[:cells])
+            st2 = e2e_step()
+        torch.cuda.synchronize()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         barrier()
         assert int(out_host[:cells].astype(np.int64).sum()) == checksum, "e2e result differs from the device-resident result"
@@ -317,10 +365,12 @@ def main():
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": T_ms / a.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload_name(a), "num_samples": N, "num_patterns": P, "updates_per_step": U_total,
-                   "sum_n": int(tot.sum_n), "sum_l": int(tot.sum_l), "parallelism": f"row-block x{world}",
+                   "sum_n": int(tot.sum_n), "sum_l": int(tot.sum_l), "parallelism": (f"pattern chunks round-robin x{world} + one NCCL all-reduce of the matrix" if by_patterns
+                                   else f"row-block x{world}, no collective"),
                    "l2_policy": "inputs (trie %.1f GB + per-chunk lists) exceed the 126 MB L2; no explicit flush" %
                                 ((P * 40 + int(tot.payload_bytes)) / 1e9),
-                   "chunk_ids": a.chunk_ids, "tile_cols": a.tile_cols, "unit_updates": a.unit_updates},
+                   "chunk_ids": chunk_ids, "tile_cols": a.tile_cols, "unit_updates": a.unit_updates,
+                   "tile_rows": a.tile_rows, "scatter_threads": a.scatter_threads},
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "stage_ms_per_step": {k: v / a.steps for k, v in stage.items()}, "wall_ms_per_step": wall_ms / a.steps,
         "result_checksum": checksum,

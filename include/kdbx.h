@@ -48,12 +48,15 @@ typedef struct kdbx_config {
     int32_t device;        /* CUDA ordinal; -1 = current device                          */
     uint32_t flags;        /* KDBX_FLAG_*                                                */
     uint64_t chunk_ids;    /* decoded ids per chunk; 0 = default                         */
-    uint32_t tile_cols;    /* columns per warp-private accumulator tile; 0 = default     */
+    uint32_t tile_cols;    /* columns of a CTA's shared-memory accumulator tile (multiple
+                              of 32); 0 = default                                        */
     uint32_t unit_updates; /* target updates per work unit; 0 = default                  */
     uint64_t sparse_block_cells; /* kdbx_all2all_sparse: dense cells accumulated per row block;
                                     0 = a quarter of the free HBM                          */
     uint64_t query_batch_kmers;  /* kdbx_new2all_batch: k-mers per device pass; 0 = 2^28      */
-    uint64_t reserved[2];
+    uint32_t tile_rows;          /* matrix rows per accumulator tile (power of two <= 32); 0 = default */
+    uint32_t scatter_threads;    /* threads per CTA of the scatter-add kernel; 0 = default     */
+    uint64_t reserved[1];
 } kdbx_config;
 
 #define KDBX_FLAG_NONE 0u
@@ -222,6 +225,17 @@ int kdbx_load_hashtables(kdbx_ctx* ctx, const kdbx_tables_view* view);
  * Needs kdbx_load_patterns and kdbx_load_hashtables.  `out` is HOST memory, n_queries x N. */
 int kdbx_new2all_batch(kdbx_ctx* ctx, const uint64_t* kmers, const uint64_t* q_off, uint32_t n_queries,
                        uint32_t* out, kdbx_stats* stats);
+
+/* Pattern-sharded variant for multi-GPU runs: the trie is cut into chunks of patterns (the
+ * library's unit of streaming, kdbx_config::chunk_ids); this call executes the chunks c with
+ * c % num_parts == part and leaves a PARTIAL matrix (whole packed triangle, N(N-1)/2 cells) in
+ * device memory.  The element-wise uint32 sum of the partial matrices of all parts is the matrix
+ * of kdbx_all2all_dense — the caller adds them with one collective (bench.py: NCCL all-reduce /
+ * reduce-scatter over NVLink).  stats->updates counts the executed chunks only.  The reference's
+ * nearest analogue is the per-thread partition of each cache block, src/similarity_calculator.cpp:
+ * 302-327. */
+int kdbx_all2all_dense_part_device(kdbx_ctx* ctx, uint32_t part, uint32_t num_parts, void* d_out_tri,
+                                   kdbx_stats* stats);
 
 /* Debug / test taps (not used by the product path): copy intermediate device arrays of the
  * last compute call to the host.  what: 0 = W (uint32[P]), 1 = decoded local ids

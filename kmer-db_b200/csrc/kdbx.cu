@@ -53,23 +53,13 @@ struct __align__(32) Node {  // one 32-byte sector per chain step
     uint64_t pad;
 };
 
-struct __align__(16) Job {  // cols = flat[off .. off+len), weight w
-    uint32_t off;
-    uint32_t len;
-    uint32_t w;
-    uint32_t pad;
-};
-
-struct __align__(16) Unit {  // jobs [job_begin, job_end) all belong to one key = row*T + tile
+struct __align__(16) Unit {  // jobs [job_begin, job_end) all belong to one key = row_block*T + tile
     uint32_t key;
     uint32_t job_begin;
     uint32_t job_end;
     uint32_t pad;
 };
 
-constexpr int kScatterThreads = 256;
-constexpr int kWarpsPerBlock = kScatterThreads / 32;
-constexpr uint32_t kMaxTiles = 31;
 
 __device__ __forceinline__ uint64_t tri_offset(uint64_t row) { return row * (row - 1) / 2; }
 
@@ -291,53 +281,97 @@ __global__ void k_expand(uint64_t p0, uint64_t p1, const Node* __restrict__ node
     }
 }
 
-// Shared by the histogram and fill passes: enumerate the jobs of pattern p.
-// emit(key, off, len) is called by the lane that owns local position j.
+// A job = one pattern x one block of matrix rows x one column tile: rows full[A0 .. A0+k) (k local
+// samples of the pattern that fall into the same block of `tile_rows` consecutive matrix rows) and,
+// for row j, the columns full[a .. min(b, A0+j)) — [a,b) being the part of the (ascending) list that
+// lies inside the column tile.  All k rows share the ids full[a .. min(b,A0)): one pass over them
+// feeds k accumulator rows, which is what makes the scatter kernel shared-memory-bound instead
+// of id-stream-bound (the reference re-reads the list once per row, src/similarity_calculator.cpp:
+// 214-231; so did the first three versions of this file).
+struct __align__(32) Job {
+    uint32_t off;  // start of the pattern's full list in the chunk's flat id array
+    uint32_t a, b;
+    uint32_t A0;
+    uint32_t k;
+    uint32_t w;    // (uint32_t) W_p
+    uint32_t pad[2];
+};
+
+// sum over rows j < k of max(0, min(b, A0 + j) - a): the number of row[col] += w updates of a job
+__device__ __forceinline__ unsigned long long job_updates(uint32_t a, uint32_t b, uint32_t A0, uint32_t k) {
+    if (b <= a) return 0;
+    long long lo = (long long)a + 1 - (long long)A0;  // first row that sees any id of [a,b)
+    if (lo < 0) lo = 0;
+    if (lo >= (long long)k) return 0;
+    long long sat = (long long)b - (long long)A0;     // first row that sees all of [a,b)
+    if (sat < lo) sat = lo;
+    if (sat > (long long)k) sat = k;
+    const long long cnt = sat - lo;
+    long long s = cnt * ((long long)A0 - (long long)a) + (lo + sat - 1) * cnt / 2;
+    s += ((long long)k - sat) * (long long)(b - a);
+    return (unsigned long long)s;
+}
+
+__device__ __forceinline__ uint32_t lower_bound_ids(const uint32_t* __restrict__ ids, uint32_t n, uint32_t target) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (ids[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// Shared by the histogram and fill passes: enumerate the jobs of pattern p (one warp per pattern,
+// lanes over the pattern's local positions).  emit(key, job, updates) is called by the lane that
+// owns the first row of a run of rows falling into one row block.
 template <class Emit>
 __device__ __forceinline__ void for_each_job(const Node& nd, uint32_t base, const uint32_t* __restrict__ flat,
-                                             uint32_t T, uint32_t tile_cols, uint32_t row_begin, uint32_t row_end,
-                                             uint32_t lane, unsigned long long& updates, Emit emit) {
+                                             uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin,
+                                             uint32_t row_end, uint32_t lane, unsigned long long& updates, Emit emit) {
     const uint32_t first = nd.n - nd.l;
-    // tile boundaries inside the (ascending) full list: bound_t = first index with id >= t*tile_cols
-    uint32_t my_bound = 0;
-    if (T > 1) {
-        if (lane <= T) {
-            const uint32_t target = lane * tile_cols;
-            uint32_t lo = 0, hi = nd.n;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (flat[base + mid] >= target) hi = mid; else lo = mid + 1;
-            }
-            my_bound = lo;
-        }
-    } else {
-        my_bound = (lane == 0) ? 0u : nd.n;
-    }
     const uint32_t rounds = (nd.l + 31) / 32;
+    const uint32_t* list = flat + base;
     for (uint32_t r = 0; r < rounds; ++r) {
         const uint32_t j = r * 32 + lane;
         const bool have = j < nd.l;
         const uint32_t i = first + j;
-        uint32_t row = 0;
+        uint32_t row = 0xFFFFFFFFu;
         bool active = false;
-        if (have && i > 0) {
-            row = flat[base + i];
+        if (have) {
+            row = list[i];
             active = row >= row_begin && row < row_end;
         }
         if (active) updates += i;
-        for (uint32_t t = 0; t < T; ++t) {
-            const uint32_t a = __shfl_sync(0xffffffffu, my_bound, t);
-            uint32_t b = __shfl_sync(0xffffffffu, my_bound, t + 1);
-            if (active) {
-                b = b < i ? b : i;
-                if (b > a) emit(row * T + t, base + a, b - a);
-            }
+        const uint32_t rb = row >> rb_shift;
+        const uint32_t prev_rb = __shfl_up_sync(0xffffffffu, rb, 1);
+        const uint32_t amask = __ballot_sync(0xffffffffu, active);
+        const bool start = active && (lane == 0 || !((amask >> (lane - 1)) & 1u) || prev_rb != rb);
+        const uint32_t smask = __ballot_sync(0xffffffffu, start);
+        if (!start) continue;
+        // the run ends at the next start or after the last active lane (active lanes are contiguous:
+        // rows ascend and [row_begin,row_end) is an interval)
+        const uint32_t above = lane == 31 ? 0u : ((smask >> (lane + 1)) << (lane + 1));
+        const uint32_t next_start = above ? (uint32_t)__ffs((int)above) - 1u : 32u;
+        const uint32_t last_active = 32u - (uint32_t)__clz((int)amask);
+        const uint32_t k = min(next_start, last_active) - lane;
+        const uint32_t reach = i + k - 1;  // the last row of the run sees the ids [0, reach)
+        Job jb;
+        jb.off = base; jb.A0 = i; jb.k = k; jb.w = 0; jb.pad[0] = jb.pad[1] = 0;
+        if (T == 1) {
+            if (reach > 0) { jb.a = 0; jb.b = nd.n; emit(rb, jb, job_updates(0, nd.n, i, k)); }
+            continue;
+        }
+        uint32_t a = 0;
+        for (uint32_t t = 0; t < T && a < reach; ++t) {
+            const uint32_t b = (t + 1 == T) ? nd.n : lower_bound_ids(list, nd.n, (t + 1) * tile_cols);
+            if (b > a) { jb.a = a; jb.b = b; emit(rb * T + t, jb, job_updates(a, b, i, k)); }
+            a = b;
         }
     }
 }
 
 // ---- job bucketing, small key spaces: block-private histograms in shared memory ------------
-// With N*T <= kSmemKeys every block counts its contiguous slice of patterns into shared memory
+// With nkeys <= kSmemKeys every block counts its contiguous slice of patterns into shared memory
 // and publishes one row of blockhist[block][key]; a per-key column scan then gives every
 // (block, key) pair its exact slot range, so the fill pass needs no global atomics at all.
 constexpr uint32_t kSmemKeys = 2048;
@@ -353,7 +387,7 @@ __device__ __forceinline__ void block_slice(uint64_t p0, uint64_t p1, uint64_t& 
 __global__ void __launch_bounds__(kBucketThreads)
 k_job_hist_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
                 const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T, uint32_t tile_cols,
-                uint32_t row_begin, uint32_t row_end, uint32_t nkeys, uint32_t* __restrict__ blockhist,
+                uint32_t rb_shift, uint32_t row_begin, uint32_t row_end, uint32_t nkeys, uint32_t* __restrict__ blockhist,
                 unsigned long long* __restrict__ work, unsigned long long* __restrict__ total_updates) {
     __shared__ uint32_t s_hist[kSmemKeys];
     __shared__ unsigned long long s_work[kSmemKeys];
@@ -367,13 +401,13 @@ k_job_hist_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const 
     for (uint64_t p = lo + warp; p < hi; p += nwarps) {
         const Node nd = nodes[p];
         if (nd.l == 0) continue;
-        const bool weightless = W[p] == 0;
+        const bool weightless = W[p] == 0;  // adds of 0 are skipped, but still counted in U
         const uint32_t base = (uint32_t)(noff[p] - base0);
-        for_each_job(nd, base, flat, T, tile_cols, row_begin, row_end, lane, updates,
-                     [&](uint32_t key, uint32_t, uint32_t len) {
-                         if (weightless) return;
+        for_each_job(nd, base, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+                     [&](uint32_t key, const Job&, unsigned long long upd) {
+                         if (weightless || upd == 0) return;
                          atomicAdd(&s_hist[key], 1u);
-                         atomicAdd(&s_work[key], (unsigned long long)len);
+                         atomicAdd(&s_work[key], upd);
                      });
     }
     for (int o = 16; o; o >>= 1) updates += __shfl_xor_sync(0xffffffffu, updates, o);
@@ -420,7 +454,7 @@ __global__ void k_block_offsets(uint32_t nkeys, uint32_t nblocks, const uint32_t
 __global__ void __launch_bounds__(kBucketThreads)
 k_job_fill_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
                 const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T, uint32_t tile_cols,
-                uint32_t row_begin, uint32_t row_end, uint32_t nkeys, const uint32_t* __restrict__ blockbase,
+                uint32_t rb_shift, uint32_t row_begin, uint32_t row_end, uint32_t nkeys, const uint32_t* __restrict__ blockbase,
                 Job* __restrict__ jobs) {
     __shared__ uint32_t s_next[kSmemKeys];
     const uint32_t* mine = blockbase + (size_t)blockIdx.x * nkeys;
@@ -437,10 +471,11 @@ k_job_fill_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const 
         const uint32_t w = W[p];
         if (w == 0) continue;
         const uint32_t base = (uint32_t)(noff[p] - base0);
-        for_each_job(nd, base, flat, T, tile_cols, row_begin, row_end, lane, updates,
-                     [&](uint32_t key, uint32_t off, uint32_t len) {
+        for_each_job(nd, base, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+                     [&](uint32_t key, Job jb, unsigned long long upd) {
+                         if (upd == 0) return;
                          const uint32_t slot = atomicAdd(&s_next[key], 1u);
-                         Job jb; jb.off = off; jb.len = len; jb.w = w; jb.pad = 0;
+                         jb.w = w;
                          jobs[slot] = jb;
                      });
     }
@@ -449,8 +484,9 @@ k_job_fill_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const 
 // ---- job bucketing, large key spaces: global atomics (contention is low when keys are many) --
 __global__ void k_job_hist(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
                            const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T,
-                           uint32_t tile_cols, uint32_t row_begin, uint32_t row_end, uint32_t* __restrict__ hist,
-                           unsigned long long* __restrict__ work, unsigned long long* __restrict__ total_updates) {
+                           uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin, uint32_t row_end,
+                           uint32_t* __restrict__ hist, unsigned long long* __restrict__ work,
+                           unsigned long long* __restrict__ total_updates) {
     const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
@@ -459,13 +495,13 @@ __global__ void k_job_hist(uint64_t p0, uint64_t p1, const Node* __restrict__ no
     for (uint64_t p = p0 + gw; p < p1; p += nw) {
         const Node nd = nodes[p];
         if (nd.l == 0) continue;
-        const bool weightless = W[p] == 0;  // adds of 0 are skipped, but still counted in U
+        const bool weightless = W[p] == 0;
         const uint32_t base = (uint32_t)(noff[p] - base0);
-        for_each_job(nd, base, flat, T, tile_cols, row_begin, row_end, lane, updates,
-                     [&](uint32_t key, uint32_t, uint32_t len) {
-                         if (weightless) return;
+        for_each_job(nd, base, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+                     [&](uint32_t key, const Job&, unsigned long long upd) {
+                         if (weightless || upd == 0) return;
                          atomicAdd(&hist[key], 1u);
-                         atomicAdd(&work[key], (unsigned long long)len);
+                         atomicAdd(&work[key], upd);
                      });
     }
     for (int o = 16; o; o >>= 1) updates += __shfl_xor_sync(0xffffffffu, updates, o);
@@ -474,8 +510,8 @@ __global__ void k_job_hist(uint64_t p0, uint64_t p1, const Node* __restrict__ no
 
 __global__ void k_job_fill(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
                            const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T,
-                           uint32_t tile_cols, uint32_t row_begin, uint32_t row_end, uint32_t* __restrict__ cursor,
-                           Job* __restrict__ jobs) {
+                           uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin, uint32_t row_end,
+                           uint32_t* __restrict__ cursor, Job* __restrict__ jobs) {
     const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
@@ -487,10 +523,11 @@ __global__ void k_job_fill(uint64_t p0, uint64_t p1, const Node* __restrict__ no
         const uint32_t w = W[p];
         if (w == 0) continue;
         const uint32_t base = (uint32_t)(noff[p] - base0);
-        for_each_job(nd, base, flat, T, tile_cols, row_begin, row_end, lane, updates,
-                     [&](uint32_t key, uint32_t off, uint32_t len) {
+        for_each_job(nd, base, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+                     [&](uint32_t key, Job jb, unsigned long long upd) {
+                         if (upd == 0) return;
                          const uint32_t slot = atomicAdd(&cursor[key], 1u);
-                         Job jb; jb.off = off; jb.len = len; jb.w = w; jb.pad = 0;
+                         jb.w = w;
                          jobs[slot] = jb;
                      });
     }
@@ -528,14 +565,16 @@ __global__ void k_unit_fill(uint32_t nkeys, const uint32_t* __restrict__ hist, c
     }
 }
 
-// THE hot kernel.  Persistent CTAs pull work units (one (row, column tile) key and a range of
-// its jobs) from a global counter.  The CTA zeroes a tile of `tile_cols` uint32 accumulators in
-// shared memory; its warps then grab batches of 32 jobs and, for every job, stream the job's
-// run of sample ids with coalesced 128-byte loads and do red.shared.add.u32 tile[id - col0] += w
-// (measured on B200: shared-memory reductions keep up with an id stream at full HBM bandwidth,
-// profiles/r01_microbench_atomics.txt — faster than LDS/IADD/STS on warp-private tiles).
-// Finally the tile is added into the packed lower-triangular matrix (src/array.h:140) with
-// red.global.add.u32, skipping zero cells.
+// THE hot kernel.  Persistent CTAs pull work units (one (row block, column tile) key and a range
+// of its jobs) from a global counter.  The CTA owns a tile of tile_rows x tile_cols uint32
+// accumulators in shared memory.  A warp takes a small batch of jobs; for each job it loads the
+// job's k row ids once, then streams the ids shared by all k rows in 128-id slices (coalesced
+// 128-byte loads) and, for every row, issues red.shared.add.u32 tile[row][id] += w — one id load
+// feeds k reductions.  The short triangular tail (row j also receives the rows before it) follows.
+// Measured on B200 (profiles/r01_microbench_atomics.txt): shared-memory reductions run at 2.3-5.1e12
+// updates/s when ids come from registers, i.e. the shared-memory pipe — not HBM — is the bound.
+// When a unit ends the tile is added into the packed lower-triangular matrix (src/array.h:140)
+// with red.global.add.u32, skipping zero cells; consecutive units of one key keep the tile.
 __device__ __forceinline__ void red_shared_add(uint32_t saddr, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
@@ -544,85 +583,120 @@ __device__ __forceinline__ uint32_t ldg_nc_u32(const uint32_t* p) {
     asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ uint4 ldg_nc_v4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 
-__global__ void __launch_bounds__(kScatterThreads)
+constexpr uint32_t kJobBatch = 8;  // jobs a warp claims at once (16 lanes load them as uint4 halves)
+
+__global__ void __launch_bounds__(1024)
 k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_units_ptr, const Job* __restrict__ jobs,
               const uint32_t* __restrict__ flat, uint32_t* __restrict__ tri, uint64_t tri_base, uint32_t T,
-              uint32_t tile_cols, uint32_t* __restrict__ unit_counter) {
-    extern __shared__ uint32_t tile[];
+              uint32_t tile_cols, uint32_t rb_shift, uint32_t* __restrict__ unit_counter) {
+    extern __shared__ uint4 tile4[];
+    uint32_t* tile = reinterpret_cast<uint32_t*>(tile4);
     __shared__ uint32_t s_unit, s_next_job;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n_units = *n_units_ptr;
+    const uint32_t R = 1u << rb_shift;
+    // every accumulator row is followed by 32 padding words: lanes beyond the end of an id slice
+    // reduce into them (one bank each), which keeps the inner loop free of branches
+    const uint32_t stride = tile_cols + 32u;
     const uint32_t tile_saddr = (uint32_t)__cvta_generic_to_shared(tile);
+    constexpr uint32_t kNone = 0xFFFFFFFFu;
+    uint32_t cur_key = kNone;  // key whose partial sums the tile holds
     for (;;) {
         if (threadIdx.x == 0) s_unit = atomicAdd(unit_counter, 1u);
         __syncthreads();
         const uint32_t u = s_unit;
-        if (u >= n_units) break;
-        const Unit un = units[u];
-        const uint32_t row = un.key / T, t = un.key - row * T;
-        const uint32_t col0 = t * tile_cols;
-        const uint32_t ncols = min(tile_cols, row - col0);  // only columns < row exist
-        for (uint32_t c = threadIdx.x; c < ncols; c += kScatterThreads) tile[c] = 0;
-        if (threadIdx.x == 0) s_next_job = un.job_begin;
-        __syncthreads();
-        // shared address of column 0 (may lie below the tile when col0 > 0; only in-tile ids occur)
-        const uint32_t base = tile_saddr - col0 * 4u;
-        for (;;) {
-            uint32_t jb = 0;
-            if (lane == 0) jb = atomicAdd(&s_next_job, 32u);
-            jb = __shfl_sync(0xffffffffu, jb, 0);
-            if (jb >= un.job_end) break;
-            const uint32_t cnt = min(32u, un.job_end - jb);
-            Job mine; mine.off = 0; mine.len = 0; mine.w = 0; mine.pad = 0;
-            if (lane < cnt) mine = jobs[jb + lane];
-            // Software pipeline over 128-id slices: the loads of slice s+1 (possibly of the next
-            // job) are issued before the reductions of slice s, so a warp always has one slice
-            // of ids in flight.  kNone marks lanes beyond the end of a run.
-            constexpr uint32_t kNone = 0xFFFFFFFFu;
-            uint32_t j = 0;
-            uint32_t len = __shfl_sync(0xffffffffu, mine.len, 0);
-            uint32_t w = __shfl_sync(0xffffffffu, mine.w, 0);
-            const uint32_t* ptr = flat + __shfl_sync(0xffffffffu, mine.off, 0) + lane;
-            uint32_t rem = len;  // ids of the current job not yet loaded
-            uint32_t a0, a1, a2, a3;
-            a0 = lane < rem ? ldg_nc_u32(ptr) : kNone;
-            a1 = lane + 32 < rem ? ldg_nc_u32(ptr + 32) : kNone;
-            a2 = lane + 64 < rem ? ldg_nc_u32(ptr + 64) : kNone;
-            a3 = lane + 96 < rem ? ldg_nc_u32(ptr + 96) : kNone;
-            for (;;) {
-                const uint32_t cur_w = w;
-                bool more = true;
-                if (rem > 128) { rem -= 128; ptr += 128; }
-                else {
-                    ++j;
-                    more = j < cnt;
-                    if (more) {
-                        rem = __shfl_sync(0xffffffffu, mine.len, j);
-                        w = __shfl_sync(0xffffffffu, mine.w, j);
-                        ptr = flat + __shfl_sync(0xffffffffu, mine.off, j) + lane;
+        const bool done = u >= n_units;
+        Unit un; un.key = kNone; un.job_begin = un.job_end = 0; un.pad = 0;
+        if (!done) un = units[u];
+        if (un.key != cur_key) {
+            if (cur_key != kNone) {  // flush the finished tile
+                const uint32_t rb = cur_key / T, t = cur_key - rb * T;
+                const uint32_t row0 = rb << rb_shift, col0 = t * tile_cols;
+                for (uint32_t r = 0; r < R; ++r) {
+                    const uint32_t row = row0 + r;
+                    if (row <= col0) continue;
+                    const uint32_t nc = min(tile_cols, row - col0);  // only columns < row exist
+                    const uint64_t out0 = tri_offset(row) - tri_base + col0;
+                    const uint32_t* src = tile + r * stride;
+                    for (uint32_t c = threadIdx.x; c < nc; c += blockDim.x) {
+                        const uint32_t v = src[c];
+                        if (v) atomicAdd(&tri[out0 + c], v);
                     }
                 }
-                uint32_t b0 = kNone, b1 = kNone, b2 = kNone, b3 = kNone;
-                if (more) {
-                    if (lane < rem) b0 = ldg_nc_u32(ptr);
-                    if (lane + 32 < rem) b1 = ldg_nc_u32(ptr + 32);
-                    if (lane + 64 < rem) b2 = ldg_nc_u32(ptr + 64);
-                    if (lane + 96 < rem) b3 = ldg_nc_u32(ptr + 96);
-                }
-                if (a0 != kNone) red_shared_add(base + a0 * 4u, cur_w);
-                if (a1 != kNone) red_shared_add(base + a1 * 4u, cur_w);
-                if (a2 != kNone) red_shared_add(base + a2 * 4u, cur_w);
-                if (a3 != kNone) red_shared_add(base + a3 * 4u, cur_w);
-                if (!more) break;
-                a0 = b0; a1 = b1; a2 = b2; a3 = b3;
+                __syncthreads();
             }
+            if (!done) {
+                const uint32_t n4 = (R * stride) >> 2;
+                for (uint32_t c = threadIdx.x; c < n4; c += blockDim.x) tile4[c] = make_uint4(0, 0, 0, 0);
+            }
+            cur_key = un.key;
         }
+        if (done) break;
+        if (threadIdx.x == 0) s_next_job = un.job_begin;
         __syncthreads();
-        const uint64_t out0 = tri_offset(row) - tri_base + col0;
-        for (uint32_t c = threadIdx.x; c < ncols; c += kScatterThreads) {
-            const uint32_t v = tile[c];
-            if (v) atomicAdd(&tri[out0 + c], v);
+        const uint32_t rb = un.key / T, t = un.key - rb * T;
+        const uint32_t row0 = rb << rb_shift, col0 = t * tile_cols;
+        // shared address of (row0, column 0); may lie below the tile when col0 > 0 — only in-tile ids occur
+        const uint32_t base = tile_saddr - col0 * 4u;
+        const uint32_t pad4 = (col0 + tile_cols + lane) * 4u;  // this lane's padding word, relative to `base`
+        for (;;) {
+            uint32_t jb = 0;
+            if (lane == 0) jb = atomicAdd(&s_next_job, kJobBatch);
+            jb = __shfl_sync(0xffffffffu, jb, 0);
+            if (jb >= un.job_end) break;
+            const uint32_t cnt = min(kJobBatch, un.job_end - jb);
+            uint4 part = make_uint4(0, 0, 0, 0);  // lane 2q: (off, a, b, A0) of job q; lane 2q+1: (k, w, -, -)
+            if (lane < 2 * cnt) part = ldg_nc_v4(reinterpret_cast<const uint4*>(jobs + jb) + lane);
+            for (uint32_t q = 0; q < cnt; ++q) {
+                const uint32_t off = __shfl_sync(0xffffffffu, part.x, 2 * q), a = __shfl_sync(0xffffffffu, part.y, 2 * q);
+                const uint32_t b = __shfl_sync(0xffffffffu, part.z, 2 * q), A0 = __shfl_sync(0xffffffffu, part.w, 2 * q);
+                const uint32_t k = __shfl_sync(0xffffffffu, part.x, 2 * q + 1), w = __shfl_sync(0xffffffffu, part.y, 2 * q + 1);
+                const uint32_t* list = flat + off;
+                uint32_t my_id4 = 0, rowoff = 0;  // lane j < k: 4 * id of row j, shared address of its accumulator row
+                if (lane < k) {
+                    const uint32_t my_row = ldg_nc_u32(list + A0 + lane);
+                    my_id4 = my_row * 4u;
+                    rowoff = base + (my_row - row0) * stride * 4u;
+                }
+                // ids seen by every row of the job: [a, min(b, A0))
+                const uint32_t bc = min(b, A0);
+                for (uint32_t c = a; c < bc; c += 128) {
+                    const uint32_t rem = bc - c;
+                    const uint32_t* p = list + c + lane;
+                    uint32_t x0 = pad4, x1 = pad4, x2 = pad4, x3 = pad4;
+                    if (lane < rem) x0 = ldg_nc_u32(p) * 4u;
+                    if (lane + 32 < rem) x1 = ldg_nc_u32(p + 32) * 4u;
+                    if (lane + 64 < rem) x2 = ldg_nc_u32(p + 64) * 4u;
+                    if (lane + 96 < rem) x3 = ldg_nc_u32(p + 96) * 4u;
+                    if (rem > 96) {
+                        for (uint32_t j = 0; j < k; ++j) {
+                            const uint32_t ro = __shfl_sync(0xffffffffu, rowoff, j);
+                            red_shared_add(ro + x0, w); red_shared_add(ro + x1, w);
+                            red_shared_add(ro + x2, w); red_shared_add(ro + x3, w);
+                        }
+                    } else if (rem > 32) {
+                        for (uint32_t j = 0; j < k; ++j) {
+                            const uint32_t ro = __shfl_sync(0xffffffffu, rowoff, j);
+                            red_shared_add(ro + x0, w); red_shared_add(ro + x1, w);
+                            if (rem > 64) red_shared_add(ro + x2, w);
+                        }
+                    } else {
+                        for (uint32_t j = 0; j < k; ++j) red_shared_add(__shfl_sync(0xffffffffu, rowoff, j) + x0, w);
+                    }
+                }
+                // triangular tail: row j also receives the rows before it that lie in [a, b)
+                const bool tv = lane < k && A0 + lane >= a && A0 + lane < b;
+                for (uint32_t j = 1; j < k; ++j) {
+                    const uint32_t ro = __shfl_sync(0xffffffffu, rowoff, j);
+                    if (tv && lane < j) red_shared_add(ro + my_id4, w);
+                }
+            }
         }
         __syncthreads();
     }
@@ -729,23 +803,37 @@ int scan_exclusive_u32(kdbx_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_
 }
 
 struct Plan {
-    uint32_t tile_cols = 0, T = 0, unit_updates = 0;
+    uint32_t tile_cols = 0, tile_rows = 0, rb_shift = 0, T = 0, RB = 0, unit_updates = 0, threads = 0;
     uint64_t chunk = 0;
+    size_t smem = 0;
 };
+
+constexpr size_t kMaxTileBytes = 200 * 1024;  // of the 227 KB a CTA may use
 
 int make_plan(kdbx_ctx* ctx, Plan& pl) {
     const uint32_t N = ctx->N;
     uint32_t tc = ctx->cfg.tile_cols;
-    // default: a whole row per CTA tile while 7-8 CTAs still fit an SM (7168 cols = 28 KB)
-    if (tc == 0) tc = std::min<uint32_t>(7168u, std::max<uint32_t>(32u, (N + 31u) & ~31u));
+    // default: whole rows up to 1024 samples (a 32 x 1024 tile is 128 KB: one 1024-thread CTA per SM)
+    if (tc == 0) tc = std::min<uint32_t>(1024u, std::max<uint32_t>(32u, (N + 31u) & ~31u));
     if (tc < 32 || (tc & 31)) return ctx->fail(KDBX_ERR_ARG, "tile_cols must be a multiple of 32");
-    if ((size_t)tc * 4 > 200 * 1024) return ctx->fail(KDBX_ERR_ARG, "tile_cols too large for shared memory");
-    const uint32_t T = N == 0 ? 1 : (N + tc - 1) / tc;
-    if (T > kMaxTiles)
-        return ctx->fail(KDBX_ERR_ARG, "dense all2all supports at most %u samples with tile_cols=%u (got %u)",
-                         kMaxTiles * tc, tc, N);
-    pl.tile_cols = tc; pl.T = T;
-    pl.unit_updates = ctx->cfg.unit_updates ? ctx->cfg.unit_updates : 131072u;
+    uint32_t tr = ctx->cfg.tile_rows;
+    if (tr == 0) {
+        tr = 32;
+        while (tr > 1 && (size_t)tr * (tc + 32) * 4 > kMaxTileBytes) tr >>= 1;
+    }
+    if (tr == 0 || tr > 32 || (tr & (tr - 1))) return ctx->fail(KDBX_ERR_ARG, "tile_rows must be a power of two <= 32");
+    if ((size_t)tr * (tc + 32) * 4 > kMaxTileBytes) return ctx->fail(KDBX_ERR_ARG, "tile_rows x tile_cols too large for shared memory");
+    pl.tile_cols = tc; pl.tile_rows = tr;
+    pl.rb_shift = 0;
+    while ((1u << pl.rb_shift) < tr) ++pl.rb_shift;
+    pl.T = N == 0 ? 1 : (N + tc - 1) / tc;
+    pl.RB = N == 0 ? 1 : (N + tr - 1) / tr;
+    if ((uint64_t)pl.T * pl.RB >= ((uint64_t)1 << 31)) return ctx->fail(KDBX_ERR_ARG, "too many (row block, column tile) keys");
+    pl.smem = (size_t)tr * (tc + 32) * 4;  // 32 padding words per row, see k_scatter_add
+    pl.threads = ctx->cfg.scatter_threads ? ctx->cfg.scatter_threads : (pl.smem > 100 * 1024 ? 1024u : pl.smem > 48 * 1024 ? 512u : 256u);
+    if (pl.threads < 32 || pl.threads > 1024 || (pl.threads & 31)) return ctx->fail(KDBX_ERR_ARG, "scatter_threads must be a multiple of 32 in [32, 1024]");
+    // a unit flushes at most tile_rows x tile_cols cells with global reductions: keep >= 64 updates per cell
+    pl.unit_updates = ctx->cfg.unit_updates ? ctx->cfg.unit_updates : std::max<uint32_t>(131072u, 64u * tr * tc);
     pl.chunk = ctx->cfg.chunk_ids ? ctx->cfg.chunk_ids : ((uint64_t)64 << 20);
     if (pl.chunk < 4096) pl.chunk = 4096;
     if (pl.chunk > ((uint64_t)1 << 31)) pl.chunk = (uint64_t)1 << 31;
@@ -860,7 +948,10 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
 
 float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 
-int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uint32_t* d_out, kdbx_stats* stats) {
+// part / num_parts: only the chunks c with c % num_parts == part are executed (pattern sharding for
+// multi-GPU runs: the partial matrices of all parts sum to the full one).
+int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uint32_t* d_out, kdbx_stats* stats,
+                        uint32_t part = 0, uint32_t num_parts = 1) {
     if (!ctx->loaded) return ctx->fail(KDBX_ERR_STATE, "no patterns loaded (call kdbx_load_patterns first)");
     if (row_begin > row_end || row_end > ctx->N) return ctx->fail(KDBX_ERR_ARG, "bad row range [%u,%u) for %u samples", row_begin, row_end, ctx->N);
     CK(cudaSetDevice(ctx->device));
@@ -887,7 +978,7 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     s.ms_prepare = elapsed(ev_start, ev_prepared);
     if (int rc = check_device_error(ctx)) return rc;  // decode errors: stop before lists are expanded
 
-    const uint32_t nkeys = ctx->N * pl.T;
+    const uint32_t nkeys = pl.RB * pl.T;
     if (cells == 0 || nkeys == 0) {  // N <= 1 or an empty row range: no cell exists
         s.ms_total = s.ms_prepare;
         s.flat_ids = ctx->sum_n; s.local_ids = ctx->sum_l; s.kernel_launches = launches;
@@ -906,10 +997,10 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     uint32_t* d_unit_counter = ctx->counters.as<uint32_t>() + 4;
     CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
 
-    const size_t smem = (size_t)pl.tile_cols * 4;
+    const size_t smem = pl.smem;
     CK(cudaFuncSetAttribute(k_scatter_add, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks_per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_scatter_add, kScatterThreads, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_scatter_add, (int)pl.threads, smem));
     if (blocks_per_sm < 1) return ctx->fail(KDBX_ERR_CUDA, "scatter kernel does not fit on an SM");
     const unsigned scatter_grid = (unsigned)(ctx->sm_count * blocks_per_sm);
     const unsigned wide_grid = (unsigned)(ctx->sm_count * 8);
@@ -921,7 +1012,7 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     cev.reserve(nchunks);
     for (uint32_t c = 0; c < nchunks; ++c) {
         const uint64_t p0 = bounds[c], p1 = bounds[c + 1];
-        if (p1 <= p0) continue;
+        if (p1 <= p0 || c % num_parts != part) continue;
         ChunkEv e;
         e.a = ctx->event();
         k_expand<<<wide_grid, 256, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->loc.as<uint32_t>(), ctx->flat.as<uint32_t>());
@@ -929,24 +1020,24 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         CK(cudaMemsetAsync(ctx->work.p, 0, ((size_t)nkeys + 1) * 8, st));
         if (smem_buckets) {
             k_job_hist_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                                  ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, row_begin, row_end, nkeys,
+                                                                  ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
                                                                   ctx->blockhist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates);
             k_key_totals<<<blocks_for((uint64_t)nkeys + 1, 128), 128, 0, st>>>(nkeys, wide_grid, ctx->blockhist.as<uint32_t>(), ctx->hist.as<uint32_t>());
             if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
             k_block_offsets<<<blocks_for((uint64_t)nkeys * 32, 256), 256, 0, st>>>(nkeys, wide_grid, ctx->bucket_off.as<uint32_t>(), ctx->blockhist.as<uint32_t>());
             k_job_fill_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                                  ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, row_begin, row_end, nkeys,
+                                                                  ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
                                                                   ctx->blockhist.as<uint32_t>(), ctx->jobs.as<Job>());
             launches += 2;
         } else {
             CK(cudaMemsetAsync(ctx->hist.p, 0, ((size_t)nkeys + 1) * 4, st));
             k_job_hist<<<wide_grid, 256, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                   ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, row_begin, row_end,
+                                                   ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
                                                    ctx->hist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates);
             if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
             CK(cudaMemcpyAsync(ctx->cursor.p, ctx->bucket_off.p, ((size_t)nkeys + 1) * 4, cudaMemcpyDeviceToDevice, st));
             k_job_fill<<<wide_grid, 256, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                   ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, row_begin, row_end,
+                                                   ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
                                                    ctx->cursor.as<uint32_t>(), ctx->jobs.as<Job>());
         }
         k_unit_count<<<blocks_for((uint64_t)nkeys + 1, 256), 256, 0, st>>>(nkeys, ctx->hist.as<uint32_t>(), ctx->work.as<unsigned long long>(),
@@ -956,8 +1047,8 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
                                                              ctx->ucount.as<uint32_t>(), ctx->uoff.as<uint32_t>(), ctx->units.as<Unit>());
         CK(cudaMemsetAsync(d_unit_counter, 0, 4, st));
         e.c = ctx->event();
-        k_scatter_add<<<scatter_grid, kScatterThreads, smem, st>>>(ctx->units.as<Unit>(), ctx->uoff.as<uint32_t>() + nkeys, ctx->jobs.as<Job>(),
-                                                                   ctx->flat.as<uint32_t>(), d_out, tri_base, pl.T, pl.tile_cols, d_unit_counter);
+        k_scatter_add<<<scatter_grid, pl.threads, smem, st>>>(ctx->units.as<Unit>(), ctx->uoff.as<uint32_t>() + nkeys, ctx->jobs.as<Job>(),
+                                                              ctx->flat.as<uint32_t>(), d_out, tri_base, pl.T, pl.tile_cols, pl.rb_shift, d_unit_counter);
         e.d = ctx->event();
         launches += 8;
         s.scatter_launches += 1;
@@ -1107,6 +1198,13 @@ int kdbx_all2all_dense_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t r
     if (!ctx) return KDBX_ERR_ARG;
     if (!d_out_rows && row_end > row_begin && row_end > 1) return ctx->fail(KDBX_ERR_ARG, "output pointer is NULL");
     return all2all_rows_device(ctx, row_begin, row_end, static_cast<uint32_t*>(d_out_rows), stats);
+}
+
+int kdbx_all2all_dense_part_device(kdbx_ctx* ctx, uint32_t part, uint32_t num_parts, void* d_out_tri, kdbx_stats* stats) {
+    if (!ctx) return KDBX_ERR_ARG;
+    if (num_parts == 0 || part >= num_parts) return ctx->fail(KDBX_ERR_ARG, "bad part %u of %u", part, num_parts);
+    if (!d_out_tri && ctx->N > 1) return ctx->fail(KDBX_ERR_ARG, "output pointer is NULL");
+    return all2all_rows_device(ctx, 0, ctx->N, static_cast<uint32_t*>(d_out_tri), stats, part, num_parts);
 }
 
 int kdbx_all2all_dense_rows(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uint32_t* out_rows, kdbx_stats* stats) {

@@ -27,7 +27,8 @@ class KdbxError(RuntimeError):
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("chunk_ids", C.c_uint64),
                 ("tile_cols", C.c_uint32), ("unit_updates", C.c_uint32), ("sparse_block_cells", C.c_uint64),
-                ("query_batch_kmers", C.c_uint64), ("reserved", C.c_uint64 * 2)]
+                ("query_batch_kmers", C.c_uint64), ("tile_rows", C.c_uint32), ("scatter_threads", C.c_uint32),
+                ("reserved", C.c_uint64 * 1)]
 
 
 class TrieView(C.Structure):
@@ -85,7 +86,7 @@ class Totals(C.Structure):
 # every symbol include/kdbx.h declares (tests check that the library exports all of them)
 KDBX_SYMBOLS = ["kdbx_abi_version", "kdbx_device_count", "kdbx_open", "kdbx_close", "kdbx_last_error",
                 "kdbx_host_alloc", "kdbx_host_free", "kdbx_load_patterns", "kdbx_row_updates", "kdbx_all2all_dense",
-                "kdbx_all2all_dense_rows", "kdbx_all2all_dense_rows_device", "kdbx_all2all_sparse", "kdbx_free_csr",
+                "kdbx_all2all_dense_rows", "kdbx_all2all_dense_rows_device", "kdbx_all2all_dense_part_device", "kdbx_all2all_sparse", "kdbx_free_csr",
                 "kdbx_load_hashtables", "kdbx_new2all_batch", "kdbx_debug_fetch"]
 KDBXH_SYMBOLS = ["kdbxh_last_error", "kdbxh_trie_new", "kdbxh_trie_free", "kdbxh_read_db", "kdbxh_write_db",
                  "kdbxh_synth", "kdbxh_validate", "kdbxh_prefix", "kdbxh_view", "kdbxh_totals_of", "kdbxh_sample_name",
@@ -123,6 +124,7 @@ def load():
     k.kdbx_all2all_dense.argtypes = [C.c_void_p, C.c_void_p, P(Stats)]
     k.kdbx_all2all_dense_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, P(Stats)]
     k.kdbx_all2all_dense_rows_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, P(Stats)]
+    k.kdbx_all2all_dense_part_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, P(Stats)]
     k.kdbx_all2all_sparse.argtypes = [C.c_void_p, P(Filter), P(Csr), P(Stats)]
     k.kdbx_free_csr.argtypes = [P(Csr)]
     k.kdbx_free_csr.restype = None
@@ -342,10 +344,10 @@ class Context:
     """One GPU context of libkdbx.so (mirror of SimilarityCalculator's lifetime)."""
 
     def __init__(self, device: int = -1, chunk_ids: int = 0, tile_cols: int = 0, unit_updates: int = 0,
-                 sparse_block_cells: int = 0, query_batch_kmers: int = 0):
+                 sparse_block_cells: int = 0, query_batch_kmers: int = 0, tile_rows: int = 0, scatter_threads: int = 0):
         k, _ = load()
         self._k = k
-        cfg = Config(device, 0, chunk_ids, tile_cols, unit_updates, sparse_block_cells, query_batch_kmers)
+        cfg = Config(device, 0, chunk_ids, tile_cols, unit_updates, sparse_block_cells, query_batch_kmers, tile_rows, scatter_threads)
         p = C.c_void_p()
         rc = k.kdbx_open(C.byref(cfg), C.byref(p))
         if rc != 0:
@@ -401,6 +403,11 @@ class Context:
     def all2all_dense_rows_device(self, row_begin, row_end, device_ptr: int):
         st = Stats()
         self._check(self._k.kdbx_all2all_dense_rows_device(self._p, row_begin, row_end, C.c_void_p(device_ptr), C.byref(st)))
+        return st
+
+    def all2all_dense_part_device(self, part, num_parts, device_ptr: int):
+        st = Stats()
+        self._check(self._k.kdbx_all2all_dense_part_device(self._p, part, num_parts, C.c_void_p(device_ptr), C.byref(st)))
         return st
 
     def all2all_sparse(self, min_common=0, max_common=0xFFFFFFFF, metric_bounds=(), sample_kmers=None):

@@ -115,6 +115,38 @@ uint64_t oracle_all2all(uint64_t P, uint32_t N, const int64_t* num_kmers, const 
     return U;
 }
 
+/* Pattern-sharded variant (multi-GPU tests): only the jobs of patterns p with (p / chunk) % parts == part
+ * are executed, with W from the WHOLE trie; the partial matrices of all parts sum to oracle_all2all's. */
+uint64_t oracle_all2all_part(uint64_t P, uint32_t N, const int64_t* num_kmers, const int64_t* parent_id, const uint32_t* n,
+                             const uint32_t* l, const uint32_t* last, const uint64_t* payload_off, const uint64_t* payload,
+                             uint64_t chunk, uint32_t part, uint32_t parts, uint32_t* tri) {
+    const uint64_t cells = N ? (uint64_t)N * (N - 1) / 2 : 0;
+    memset(tri, 0, cells * sizeof(uint32_t));
+    int64_t* W = (int64_t*)malloc(P * sizeof(int64_t));
+    uint32_t* full = (uint32_t*)malloc(((size_t)N + 1) * sizeof(uint32_t));
+    if (!W || !full) { free(W); free(full); return UINT64_MAX; }
+    memcpy(W, num_kmers, P * sizeof(int64_t));
+    for (uint64_t i = P; i-- > 1;)
+        if (parent_id[i] >= 0) W[parent_id[i]] += W[i];
+    uint64_t U = 0;
+    for (uint64_t p = 0; p < P; ++p) {
+        if (l[p] == 0 || (p / chunk) % parts != part) continue;
+        uint32_t* out = full + n[p];
+        for (int64_t q = (int64_t)p; q >= 0; q = parent_id[q]) {
+            out -= l[q];
+            oracle_decode_local(payload + payload_off[q], l[q], last[q], out);
+        }
+        for (uint32_t i = n[p] - l[p]; i < n[p]; ++i) {
+            const uint64_t s = full[i];
+            uint32_t* row = tri + s * (s - 1) / 2;
+            for (uint32_t k = 0; k < i; ++k) row[full[k]] += (uint32_t)W[p];
+            U += i;
+        }
+    }
+    free(W); free(full);
+    return U;
+}
+
 /* Independent second opinion used by the tests on small tries: M[s][t] = sum of num_kmers over
  * nodes whose full list contains both s and t (a k-mer of node p lies in exactly the samples
  * of p's full list).  O(sum n^2), no W accumulation, no job rule. */

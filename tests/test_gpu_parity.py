@@ -64,9 +64,11 @@ def test_random_tries_bit_exact(libs, oracle, seed):
 
 
 @pytest.mark.parametrize("cfg", [dict(tile_cols=32), dict(tile_cols=64, chunk_ids=4096), dict(tile_cols=128, unit_updates=64),
-                                 dict(chunk_ids=5000, unit_updates=1), dict(tile_cols=1024, unit_updates=1 << 30)])
+                                 dict(chunk_ids=5000, unit_updates=1), dict(tile_cols=1024, unit_updates=1 << 30),
+                                 dict(tile_rows=1), dict(tile_rows=8, tile_cols=64), dict(tile_rows=16, scatter_threads=128),
+                                 dict(tile_rows=2, tile_cols=160, scatter_threads=1024, chunk_ids=9000)])
 def test_schedule_knobs_do_not_change_results(libs, oracle, cfg):
-    """column tiles (T>1), many chunks, tiny / huge work units: same bits."""
+    """column tiles (T>1), row blocks of 1..32 rows, many chunks, tiny / huge work units: same bits."""
     rng = np.random.default_rng(7)
     N = 900
     a, _ = ou.random_trie(rng, N, 4000, max_local=25, big_weights=True)

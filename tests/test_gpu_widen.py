@@ -57,12 +57,12 @@ def test_sparse_filters_on_device(libs, oracle):
         assert _csr_rows(rp, col, val) == _dense_to_rows(dense, N, lambda x, s, t: lo <= x <= hi)
         # metric bounds, evaluated with the reference's arithmetic (uint32 wrap, IEEE double)
         def jac(x, s, t):
-            d = np.uint32(cnt[s] + cnt[t] - np.uint32(x))
+            d = (int(cnt[s]) + int(cnt[t]) - int(x)) & 0xFFFFFFFF
             with np.errstate(divide="ignore", invalid="ignore"):
                 return np.float64(x) / np.float64(d)
         def cosine(x, s, t):
             with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
-                return np.float64(x) / np.sqrt(np.float64(np.uint32(cnt[s] * cnt[t])))
+                return np.float64(x) / np.sqrt(np.float64((int(cnt[s]) * int(cnt[t])) & 0xFFFFFFFF))
         for name, fn, b in (("jaccard", jac, (0.002, 0.5)), ("cosine", cosine, (0.001, 0.2)),
                             ("min", lambda x, s, t: np.float64(x) / np.float64(min(cnt[s], cnt[t])), (0.01, 1.0)),
                             ("max", lambda x, s, t: np.float64(x) / np.float64(max(cnt[s], cnt[t])), (0.001, 0.05))):

@@ -1,0 +1,99 @@
+"""Host-side logic of the N>1 paths on CPU: two `gloo` ranks shard the work the way bench.py does
+(pattern chunks round-robin + one all-reduce of uint32 partial matrices; row blocks balanced on
+per-row updates + gather), with the ORACLE standing in for the device kernels."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_util as ou
+
+torch = pytest.importorskip("torch")
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, str(ou.ROOT / "kmer-db_b200"))
+    sys.path.insert(0, str(ou.ROOT / "tests"))
+    import ctypes as C
+    import kdbx
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        oracle = ou.load_oracle()
+        rng = np.random.default_rng(123)  # same trie on every rank (the trie is replicated)
+        N = 150
+        a, lists = ou.random_trie(rng, N, 2500, max_local=12, big_weights=True)
+        full, U = ou.oracle_all2all(oracle, N, a)
+        # (1) pattern chunks round-robin + all-reduce; uint32 sums wrap like int32 sums
+        part = np.zeros(ou.tri_cells(N), np.uint32)
+        oracle.oracle_all2all_part.restype = C.c_uint64
+        u = oracle.oracle_all2all_part(C.c_uint64(len(a["n"])), C.c_uint32(N), a["num_kmers"].ctypes.data_as(C.c_void_p),
+                                       a["parent_id"].ctypes.data_as(C.c_void_p), a["n"].ctypes.data_as(C.c_void_p),
+                                       a["l"].ctypes.data_as(C.c_void_p), a["last"].ctypes.data_as(C.c_void_p),
+                                       a["payload_off"].ctypes.data_as(C.c_void_p), a["payload"].ctypes.data_as(C.c_void_p),
+                                       C.c_uint64(64), C.c_uint32(rank), C.c_uint32(world), part.ctypes.data_as(C.c_void_p))
+        t = torch.from_numpy(part.view(np.int32).copy())
+        dist.all_reduce(t)
+        ut = torch.tensor([u], dtype=torch.int64)
+        dist.all_reduce(ut)
+        ok1 = bool(np.array_equal(t.numpy().view(np.uint32), full)) and int(ut.item()) == U
+        # (2) row blocks balanced on per-row updates, gathered in rank order
+        upd = np.zeros(N, np.uint64)
+        nn, ll = a["n"].astype(np.int64), a["l"].astype(np.int64)
+        for p, ids in enumerate(lists):
+            first = int(nn[p] - ll[p])
+            for j, row in enumerate(ids):
+                upd[row] += first + j
+        assert int(upd.sum()) == U
+        b = kdbx.shard_rows_by_work(upd, world)
+        mine = full[ou.tri_cells(b[rank]):ou.tri_cells(b[rank + 1])]
+        sizes = [ou.tri_cells(b[r + 1]) - ou.tri_cells(b[r]) for r in range(world)]
+        bufs = [torch.zeros(sz, dtype=torch.int32) for sz in sizes]
+        # gloo all_gather needs equal sizes: pad to the largest share
+        m = max(sizes)
+        padded = torch.zeros(m, dtype=torch.int32)
+        padded[:mine.size] = torch.from_numpy(mine.view(np.int32).copy())
+        out = [torch.zeros(m, dtype=torch.int32) for _ in range(world)]
+        dist.all_gather(out, padded)
+        got = np.concatenate([out[r][:sizes[r]].numpy().view(np.uint32) for r in range(world)])
+        ok2 = bool(np.array_equal(got, full)) and b[0] == 0 and b[-1] == N and all(b[i] <= b[i + 1] for i in range(world))
+        # shares are balanced: no rank has more than ~1.5x the mean work on this input
+        work = [int(upd[b[r]:b[r + 1]].sum()) for r in range(world)]
+        ok3 = max(work) <= 1.5 * (U / world) + int(upd.max())
+        # max over ranks of a per-rank time, as bench.py reports it
+        tt = torch.tensor([float(rank + 1)], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ok4 = tt.item() == float(world)
+        q.put((rank, ok1, ok2, ok3, ok4))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_two_rank_sharding_over_gloo(libs, oracle, world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok1, ok2, ok3, ok4 in sorted(res):
+        assert ok1, f"rank {rank}: all-reduced partial matrices differ from the full matrix"
+        assert ok2, f"rank {rank}: gathered row blocks differ from the full matrix"
+        assert ok3, f"rank {rank}: row shares are unbalanced"
+        assert ok4
