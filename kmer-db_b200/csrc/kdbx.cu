@@ -50,7 +50,8 @@ struct __align__(32) Node {  // one 32-byte sector per chain step
     uint32_t l;       // local samples
     uint32_t last;    // last local sample id
     uint64_t loff;    // offset of the node's decoded local ids in d_loc
-    uint64_t pad;
+    int32_t up2;      // grandparent and great-grandparent (-1: none): skip pointers that let the
+    int32_t up3;      // expansion keep three chain steps in flight per round trip
 };
 
 struct __align__(16) Unit {  // jobs [job_begin, job_end) all belong to one key = row_block*T + tile
@@ -104,7 +105,11 @@ __global__ void k_build_nodes(uint64_t P, const int64_t* __restrict__ parent, co
     }
     Node nd;
     nd.parent = (int32_t)parent[p];
-    nd.n = n[p]; nd.l = l[p]; nd.last = last[p]; nd.loff = loff[p]; nd.pad = 0;
+    nd.n = n[p]; nd.l = l[p]; nd.last = last[p]; nd.loff = loff[p];
+    const int64_t q1 = parent[p];
+    const int64_t q2 = (q1 >= 0 && q1 < (int64_t)p) ? parent[q1] : -1;
+    const int64_t q3 = (q2 >= 0 && q2 < q1) ? parent[q2] : -1;
+    nd.up2 = (int32_t)q2; nd.up3 = (q3 < q2) ? (int32_t)q3 : -1;
     nodes[p] = nd;
     W[p] = (uint32_t)num_kmers[p];  // the reference adds (uint32_t)num_kmers (similarity_calculator.cpp:222)
 }
@@ -265,18 +270,29 @@ __global__ void k_expand(uint64_t p0, uint64_t p1, const Node* __restrict__ node
     const uint32_t sub = threadIdx.x & (kExpandLanes - 1);
     const uint64_t base0 = noff[p0];
     for (uint64_t p = p0 + gid; p < p1; p += ng) {
-        Node nd = nodes[p];
+        const Node nd = nodes[p];
         if (nd.n == 0) continue;
         uint32_t* dst = flat + (noff[p] - base0);
-        for (;;) {
-            Node up; up.parent = -1; up.n = 0; up.l = 0; up.last = 0; up.loff = 0; up.pad = 0;
-            const bool more = nd.parent >= 0;
-            if (more) up = nodes[nd.parent];
-            const uint32_t* src = loc + nd.loff;
-            const uint32_t at = nd.n - nd.l;
-            for (uint32_t j = sub; j < nd.l; j += kExpandLanes) dst[at + j] = src[j];
-            if (!more) break;
-            nd = up;
+        auto copy_locals = [&](const Node& q) {
+            const uint32_t* src = loc + q.loff;
+            const uint32_t at = q.n - q.l;
+            for (uint32_t j = sub; j < q.l; j += kExpandLanes) dst[at + j] = src[j];
+        };
+        copy_locals(nd);
+        // three ancestors per round trip: parent, grandparent and great-grandparent are known from
+        // the node (skip pointers), so their records are requested together
+        int32_t a1 = nd.parent, a2 = nd.up2, a3 = nd.up3;
+        while (a1 >= 0) {
+            const Node n1 = nodes[a1];
+            Node n2 = n1, n3 = n1;
+            if (a2 >= 0) n2 = nodes[a2];
+            if (a3 >= 0) n3 = nodes[a3];
+            copy_locals(n1);
+            if (a2 < 0) break;
+            copy_locals(n2);
+            if (a3 < 0) break;
+            copy_locals(n3);
+            a1 = n3.parent; a2 = n3.up2; a3 = n3.up3;
         }
     }
 }
@@ -321,13 +337,33 @@ __device__ __forceinline__ uint32_t lower_bound_ids(const uint32_t* __restrict__
     return lo;
 }
 
-// Shared by the histogram and fill passes: enumerate the jobs of pattern p (one warp per pattern,
-// lanes over the pattern's local positions).  emit(key, job, updates) is called by the lane that
-// owns the first row of a run of rows falling into one row block.
+// One run of k rows of pattern `nd` (list positions i .. i+k, all in row block rb): one job per
+// column tile the run's ids reach.  emit(key, job, updates).
 template <class Emit>
-__device__ __forceinline__ void for_each_job(const Node& nd, uint32_t base, const uint32_t* __restrict__ flat,
-                                             uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin,
-                                             uint32_t row_end, uint32_t lane, unsigned long long& updates, Emit emit) {
+__device__ __forceinline__ void emit_run(const Node& nd, uint32_t base, const uint32_t* __restrict__ list, uint32_t T,
+                                         uint32_t tile_cols, uint32_t rb, uint32_t i, uint32_t k, Emit& emit) {
+    const uint32_t reach = i + k - 1;  // the last row of the run sees the ids [0, reach)
+    if (reach == 0) return;
+    Job jb;
+    jb.off = base; jb.A0 = i; jb.k = k; jb.w = 0; jb.pad[0] = jb.pad[1] = 0;
+    if (T == 1) {
+        jb.a = 0; jb.b = nd.n;
+        emit(rb, jb, job_updates(0, nd.n, i, k));
+        return;
+    }
+    uint32_t a = 0;
+    for (uint32_t t = 0; t < T && a < reach; ++t) {
+        const uint32_t b = (t + 1 == T) ? nd.n : lower_bound_ids(list, nd.n, (t + 1) * tile_cols);
+        if (b > a) { jb.a = a; jb.b = b; emit(rb * T + t, jb, job_updates(a, b, i, k)); }
+        a = b;
+    }
+}
+
+// Warp-cooperative enumeration of one (long) pattern: lanes over the pattern's local positions.
+template <class Emit>
+__device__ __forceinline__ void jobs_of_pattern_warp(const Node& nd, uint32_t base, const uint32_t* __restrict__ flat,
+                                                     uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin,
+                                                     uint32_t row_end, uint32_t lane, unsigned long long& updates, Emit& emit) {
     const uint32_t first = nd.n - nd.l;
     const uint32_t rounds = (nd.l + 31) / 32;
     const uint32_t* list = flat + base;
@@ -353,19 +389,61 @@ __device__ __forceinline__ void for_each_job(const Node& nd, uint32_t base, cons
         const uint32_t above = lane == 31 ? 0u : ((smask >> (lane + 1)) << (lane + 1));
         const uint32_t next_start = above ? (uint32_t)__ffs((int)above) - 1u : 32u;
         const uint32_t last_active = 32u - (uint32_t)__clz((int)amask);
-        const uint32_t k = min(next_start, last_active) - lane;
-        const uint32_t reach = i + k - 1;  // the last row of the run sees the ids [0, reach)
-        Job jb;
-        jb.off = base; jb.A0 = i; jb.k = k; jb.w = 0; jb.pad[0] = jb.pad[1] = 0;
-        if (T == 1) {
-            if (reach > 0) { jb.a = 0; jb.b = nd.n; emit(rb, jb, job_updates(0, nd.n, i, k)); }
-            continue;
+        emit_run(nd, base, list, T, tile_cols, rb, i, min(next_start, last_active) - lane, emit);
+    }
+}
+
+// Enumerates the jobs of the patterns [lo, hi) handled by this warp (`warp` of `nwarps`, 32 patterns
+// per step).  Most patterns hold a handful of local samples (a split creates a node with one), so a
+// lane walks the rows of its own pattern when there are at most kSmallL of them — 32 patterns in
+// flight per warp instead of one; longer local lists are then taken one by one by the whole warp.
+// emit(key, job, updates, w) may be called by any lane; `updates` accumulates U per lane.
+constexpr uint32_t kSmallL = 8;
+template <class Emit>
+__device__ __forceinline__ void enumerate_jobs(uint64_t lo, uint64_t hi, uint32_t warp, uint32_t nwarps,
+                                               const Node* __restrict__ nodes, const uint64_t* __restrict__ noff, uint64_t base0,
+                                               const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T,
+                                               uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin, uint32_t row_end,
+                                               uint32_t lane, unsigned long long& updates, Emit emit) {
+    for (uint64_t b = lo + (uint64_t)warp * 32; b < hi; b += (uint64_t)nwarps * 32) {
+        const uint64_t p = b + lane;
+        Node nd; nd.parent = -1; nd.n = 0; nd.l = 0; nd.last = 0; nd.loff = 0; nd.up2 = nd.up3 = -1;
+        uint32_t w = 0, base = 0;
+        if (p < hi) {
+            nd = nodes[p];
+            if (nd.l) { w = W[p]; base = (uint32_t)(noff[p] - base0); }
         }
-        uint32_t a = 0;
-        for (uint32_t t = 0; t < T && a < reach; ++t) {
-            const uint32_t b = (t + 1 == T) ? nd.n : lower_bound_ids(list, nd.n, (t + 1) * tile_cols);
-            if (b > a) { jb.a = a; jb.b = b; emit(rb * T + t, jb, job_updates(a, b, i, k)); }
-            a = b;
+        auto emit_w = [&](uint32_t key, const Job& jb, unsigned long long upd) { emit(key, jb, upd, w); };
+        if (nd.l && nd.l <= kSmallL) {
+            const uint32_t first = nd.n - nd.l;
+            const uint32_t* list = flat + base;
+            uint32_t run_i = 0, run_k = 0, run_rb = 0;
+            for (uint32_t j = 0; j < nd.l; ++j) {
+                const uint32_t row = list[first + j];
+                const bool active = row >= row_begin && row < row_end;
+                const uint32_t rb = row >> rb_shift;
+                if (active) updates += first + j;
+                if (run_k && (!active || rb != run_rb)) { emit_run(nd, base, list, T, tile_cols, run_rb, run_i, run_k, emit_w); run_k = 0; }
+                if (active) {
+                    if (!run_k) { run_i = first + j; run_rb = rb; }
+                    ++run_k;
+                }
+            }
+            if (run_k) emit_run(nd, base, list, T, tile_cols, run_rb, run_i, run_k, emit_w);
+        }
+        uint32_t big = __ballot_sync(0xffffffffu, nd.l > kSmallL);
+        while (big) {
+            const int src = __ffs((int)big) - 1;
+            big &= big - 1;
+            Node bn;
+            bn.parent = __shfl_sync(0xffffffffu, nd.parent, src);
+            bn.n = __shfl_sync(0xffffffffu, nd.n, src);
+            bn.l = __shfl_sync(0xffffffffu, nd.l, src);
+            bn.last = 0; bn.loff = 0; bn.up2 = bn.up3 = -1;
+            const uint32_t bw = __shfl_sync(0xffffffffu, w, src);
+            const uint32_t bbase = __shfl_sync(0xffffffffu, base, src);
+            auto emit_b = [&](uint32_t key, const Job& jb, unsigned long long upd) { emit(key, jb, upd, bw); };
+            jobs_of_pattern_warp(bn, bbase, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates, emit_b);
         }
     }
 }
@@ -394,22 +472,15 @@ k_job_hist_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const 
     for (uint32_t k = threadIdx.x; k < nkeys; k += blockDim.x) { s_hist[k] = 0; s_work[k] = 0; }
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const uint64_t base0 = noff[p0];
     uint64_t lo, hi;
     block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
-    for (uint64_t p = lo + warp; p < hi; p += nwarps) {
-        const Node nd = nodes[p];
-        if (nd.l == 0) continue;
-        const bool weightless = W[p] == 0;  // adds of 0 are skipped, but still counted in U
-        const uint32_t base = (uint32_t)(noff[p] - base0);
-        for_each_job(nd, base, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
-                     [&](uint32_t key, const Job&, unsigned long long upd) {
-                         if (weightless || upd == 0) return;
-                         atomicAdd(&s_hist[key], 1u);
-                         atomicAdd(&s_work[key], upd);
-                     });
-    }
+    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+                   [&](uint32_t key, const Job&, unsigned long long upd, uint32_t w) {
+                       if (w == 0 || upd == 0) return;  // adds of 0 are skipped, but still counted in U
+                       atomicAdd(&s_hist[key], 1u);
+                       atomicAdd(&s_work[key], upd);
+                   });
     for (int o = 16; o; o >>= 1) updates += __shfl_xor_sync(0xffffffffu, updates, o);
     if (lane == 0 && updates) atomicAdd(total_updates, updates);
     __syncthreads();
@@ -461,76 +532,53 @@ k_job_fill_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const 
     for (uint32_t k = threadIdx.x; k < nkeys; k += blockDim.x) s_next[k] = mine[k];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const uint64_t base0 = noff[p0];
     uint64_t lo, hi;
     block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
-    for (uint64_t p = lo + warp; p < hi; p += nwarps) {
-        const Node nd = nodes[p];
-        if (nd.l == 0) continue;
-        const uint32_t w = W[p];
-        if (w == 0) continue;
-        const uint32_t base = (uint32_t)(noff[p] - base0);
-        for_each_job(nd, base, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
-                     [&](uint32_t key, Job jb, unsigned long long upd) {
-                         if (upd == 0) return;
-                         const uint32_t slot = atomicAdd(&s_next[key], 1u);
-                         jb.w = w;
-                         jobs[slot] = jb;
-                     });
-    }
+    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+                   [&](uint32_t key, Job jb, unsigned long long upd, uint32_t w) {
+                       if (w == 0 || upd == 0) return;
+                       const uint32_t slot = atomicAdd(&s_next[key], 1u);
+                       jb.w = w;
+                       jobs[slot] = jb;
+                   });
 }
 
 // ---- job bucketing, large key spaces: global atomics (contention is low when keys are many) --
-__global__ void k_job_hist(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
-                           const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T,
-                           uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin, uint32_t row_end,
-                           uint32_t* __restrict__ hist, unsigned long long* __restrict__ work,
-                           unsigned long long* __restrict__ total_updates) {
-    const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t base0 = noff[p0];
+__global__ void __launch_bounds__(kBucketThreads)
+k_job_hist(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
+           const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T, uint32_t tile_cols, uint32_t rb_shift,
+           uint32_t row_begin, uint32_t row_end, uint32_t* __restrict__ hist, unsigned long long* __restrict__ work,
+           unsigned long long* __restrict__ total_updates) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint64_t lo, hi;
+    block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
-    for (uint64_t p = p0 + gw; p < p1; p += nw) {
-        const Node nd = nodes[p];
-        if (nd.l == 0) continue;
-        const bool weightless = W[p] == 0;
-        const uint32_t base = (uint32_t)(noff[p] - base0);
-        for_each_job(nd, base, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
-                     [&](uint32_t key, const Job&, unsigned long long upd) {
-                         if (weightless || upd == 0) return;
-                         atomicAdd(&hist[key], 1u);
-                         atomicAdd(&work[key], upd);
-                     });
-    }
+    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+                   [&](uint32_t key, const Job&, unsigned long long upd, uint32_t w) {
+                       if (w == 0 || upd == 0) return;
+                       atomicAdd(&hist[key], 1u);
+                       atomicAdd(&work[key], upd);
+                   });
     for (int o = 16; o; o >>= 1) updates += __shfl_xor_sync(0xffffffffu, updates, o);
     if (lane == 0 && updates) atomicAdd(total_updates, updates);
 }
 
-__global__ void k_job_fill(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
-                           const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T,
-                           uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin, uint32_t row_end,
-                           uint32_t* __restrict__ cursor, Job* __restrict__ jobs) {
-    const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t base0 = noff[p0];
+__global__ void __launch_bounds__(kBucketThreads)
+k_job_fill(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
+           const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T, uint32_t tile_cols, uint32_t rb_shift,
+           uint32_t row_begin, uint32_t row_end, uint32_t* __restrict__ cursor, Job* __restrict__ jobs) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint64_t lo, hi;
+    block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
-    for (uint64_t p = p0 + gw; p < p1; p += nw) {
-        const Node nd = nodes[p];
-        if (nd.l == 0) continue;
-        const uint32_t w = W[p];
-        if (w == 0) continue;
-        const uint32_t base = (uint32_t)(noff[p] - base0);
-        for_each_job(nd, base, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
-                     [&](uint32_t key, Job jb, unsigned long long upd) {
-                         if (upd == 0) return;
-                         const uint32_t slot = atomicAdd(&cursor[key], 1u);
-                         jb.w = w;
-                         jobs[slot] = jb;
-                     });
-    }
+    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+                   [&](uint32_t key, Job jb, unsigned long long upd, uint32_t w) {
+                       if (w == 0 || upd == 0) return;
+                       const uint32_t slot = atomicAdd(&cursor[key], 1u);
+                       jb.w = w;
+                       jobs[slot] = jb;
+                   });
 }
 
 // units per key = ceil(work / unit_updates) (>= 1 when the bucket is non-empty)
@@ -1031,12 +1079,12 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
             launches += 2;
         } else {
             CK(cudaMemsetAsync(ctx->hist.p, 0, ((size_t)nkeys + 1) * 4, st));
-            k_job_hist<<<wide_grid, 256, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
+            k_job_hist<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
                                                    ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
                                                    ctx->hist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates);
             if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
             CK(cudaMemcpyAsync(ctx->cursor.p, ctx->bucket_off.p, ((size_t)nkeys + 1) * 4, cudaMemcpyDeviceToDevice, st));
-            k_job_fill<<<wide_grid, 256, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
+            k_job_fill<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
                                                    ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
                                                    ctx->cursor.as<uint32_t>(), ctx->jobs.as<Job>());
         }
