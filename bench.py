@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--unit-updates", type=int, default=0)
     ap.add_argument("--tile-rows", type=int, default=0)
     ap.add_argument("--scatter-threads", type=int, default=0)
+    ap.add_argument("--chunked-lists", action="store_true", help="force the chunked parent-chain expansion")
     ap.add_argument("--shard", choices=["patterns", "rows"], default="patterns",
                     help="N>1: 'patterns' = every rank runs its share of pattern chunks into a partial matrix, one NCCL "
                          "all-reduce adds them; 'rows' = contiguous row blocks balanced on per-row updates, no collective")
@@ -222,7 +223,19 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout at communicator creation; keep stdout for the JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     def barrier():
         if dist is not None:
@@ -244,7 +257,7 @@ def main():
     if by_patterns and chunk_ids == 0:
         chunk_ids = max(1 << 22, (64 << 20) // world)  # finer chunks: ~62 per rank, balanced round-robin
     ctx = kdbx.Context(device=local_rank, chunk_ids=chunk_ids, tile_cols=a.tile_cols, unit_updates=a.unit_updates,
-                       tile_rows=a.tile_rows, scatter_threads=a.scatter_threads)
+                       tile_rows=a.tile_rows, scatter_threads=a.scatter_threads, flags=1 if a.chunked_lists else 0)
     ctx.load_patterns(trie)
     if by_patterns:
         r0, r1 = 0, N
@@ -261,6 +274,9 @@ def main():
         if by_patterns:
             st = ctx.all2all_dense_part_device(rank, world, d_out.data_ptr())
             dist.all_reduce(d_out)  # uint32 sums wrap like int32 sums: same bits
+            # the library works on its own stream: the next step must not start (and zero d_out)
+            # while this all-reduce is still in flight on NCCL's stream
+            torch.cuda.current_stream().synchronize()
         else:
             st = ctx.all2all_dense_rows_device(r0, r1, d_out.data_ptr())
         return st

@@ -60,6 +60,10 @@ typedef struct kdbx_config {
 } kdbx_config;
 
 #define KDBX_FLAG_NONE 0u
+/* Expand full sample-id lists chunk by chunk (parent-chain walk) even when the lists of all
+ * patterns would fit in HBM at once; the default picks the resident, level-ordered expansion
+ * whenever 4 * sum(num_samples) bytes take at most 40 % of the free device memory. */
+#define KDBX_FLAG_CHUNKED_LISTS 1u
 
 /* Borrowed, read-only SoA view of `std::vector<pattern_t>` (src/pattern.h:42-55) as
  * PrefixKmerDb::getPatterns() exposes it (src/prefix_kmer_db.h:87-175).  One entry per trie

@@ -173,11 +173,15 @@ __device__ __forceinline__ uint32_t gamma_next(const uint64_t* __restrict__ w, u
 // stream holds the deltas in append order and only the LAST id is stored (src/pattern.cpp:
 // 99-109), so the bits are walked twice — first to sum the deltas (registers only), then to
 // emit ids front to back — which writes every id exactly once and never reads d_loc back.
-__global__ void k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint32_t* __restrict__ bits,
-                                const uint64_t* __restrict__ poff, const uint64_t* __restrict__ payload,
-                                uint64_t payload_words, uint32_t* __restrict__ loc, uint32_t N, int* __restrict__ err) {
-    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
+// `by_len` lists the patterns by descending num_local_samples, so that the 32 threads of a warp walk
+// bit streams of (nearly) equal length instead of waiting for the longest of 32 arbitrary ones.
+__global__ void k_decode_locals(uint64_t P, const uint32_t* __restrict__ by_len, const Node* __restrict__ nodes,
+                                const uint32_t* __restrict__ bits, const uint64_t* __restrict__ poff,
+                                const uint64_t* __restrict__ payload, uint64_t payload_words, uint32_t* __restrict__ loc, uint32_t N,
+                                int* __restrict__ err) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const uint64_t p = by_len[idx];
     const Node nd = nodes[p];
     if (nd.l == 0) return;
     uint32_t* out = loc + nd.loff;
@@ -297,6 +301,28 @@ __global__ void k_expand(uint64_t p0, uint64_t p1, const Node* __restrict__ node
     }
 }
 
+// Resident expansion (used when the full lists of ALL patterns fit in HBM, 4 * sum n bytes): a
+// pattern's full list is its parent's full list followed by its own local ids, so the patterns of
+// one num_samples level — whose parents all sit on earlier levels, n_parent < n — are expanded by
+// two contiguous copies each.  One launch per level, ascending; no pointer chasing at all.
+constexpr uint32_t kLevelLanes = 16;
+__global__ void k_expand_level(uint32_t count, const uint32_t* __restrict__ order, const Node* __restrict__ nodes,
+                               const uint64_t* __restrict__ noff, const uint32_t* __restrict__ loc, uint32_t* flat) {
+    const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / kLevelLanes;
+    const uint32_t sub = threadIdx.x & (kLevelLanes - 1);
+    if (gid >= count) return;
+    const uint32_t p = order[gid];
+    const Node nd = nodes[p];
+    uint32_t* dst = flat + noff[p];
+    const uint32_t npar = nd.n - nd.l;
+    if (nd.parent >= 0) {
+        const uint32_t* src = flat + noff[nd.parent];
+        for (uint32_t j = sub; j < npar; j += kLevelLanes) dst[j] = src[j];
+    }
+    const uint32_t* own = loc + nd.loff;
+    for (uint32_t j = sub; j < nd.l; j += kLevelLanes) dst[npar + j] = own[j];
+}
+
 // A job = one pattern x one block of matrix rows x one column tile: rows full[A0 .. A0+k) (k local
 // samples of the pattern that fall into the same block of `tile_rows` consecutive matrix rows) and,
 // for row j, the columns full[a .. min(b, A0+j)) — [a,b) being the part of the (ascending) list that
@@ -305,12 +331,13 @@ __global__ void k_expand(uint64_t p0, uint64_t p1, const Node* __restrict__ node
 // of id-stream-bound (the reference re-reads the list once per row, src/similarity_calculator.cpp:
 // 214-231; so did the first three versions of this file).
 struct __align__(32) Job {
-    uint32_t off;  // start of the pattern's full list in the chunk's flat id array
+    uint32_t off;  // start of the pattern's full list in the chunk's flat id array (low 32 bits)
     uint32_t a, b;
     uint32_t A0;
     uint32_t k;
     uint32_t w;    // (uint32_t) W_p
-    uint32_t pad[2];
+    uint32_t off_hi;
+    uint32_t pad;
 };
 
 // sum over rows j < k of max(0, min(b, A0 + j) - a): the number of row[col] += w updates of a job
@@ -340,15 +367,15 @@ __device__ __forceinline__ uint32_t lower_bound_ids(const uint32_t* __restrict__
 // One run of k rows of pattern `nd` (list positions i .. i+k, all in row block rb): one job per
 // column tile the run's ids reach.  emit(key, job, updates).
 template <class Emit>
-__device__ __forceinline__ void emit_run(const Node& nd, uint32_t base, const uint32_t* __restrict__ list, uint32_t T,
+__device__ __forceinline__ void emit_run(const Node& nd, uint64_t base, const uint32_t* __restrict__ list, uint32_t T,
                                          uint32_t tile_cols, uint32_t rb, uint32_t i, uint32_t k, Emit& emit) {
     const uint32_t reach = i + k - 1;  // the last row of the run sees the ids [0, reach)
     if (reach == 0) return;
     Job jb;
-    jb.off = base; jb.A0 = i; jb.k = k; jb.w = 0; jb.pad[0] = jb.pad[1] = 0;
-    if (T == 1) {
+    jb.off = (uint32_t)base; jb.off_hi = (uint32_t)(base >> 32); jb.A0 = i; jb.k = k; jb.w = 0; jb.pad = 0;
+    if (T == 1) {  // one tile: every row j of the run sees the ids [0, i + j)
         jb.a = 0; jb.b = nd.n;
-        emit(rb, jb, job_updates(0, nd.n, i, k));
+        emit(rb, jb, (unsigned long long)k * i + (unsigned long long)(k * (k - 1u) / 2u));
         return;
     }
     uint32_t a = 0;
@@ -361,7 +388,7 @@ __device__ __forceinline__ void emit_run(const Node& nd, uint32_t base, const ui
 
 // Warp-cooperative enumeration of one (long) pattern: lanes over the pattern's local positions.
 template <class Emit>
-__device__ __forceinline__ void jobs_of_pattern_warp(const Node& nd, uint32_t base, const uint32_t* __restrict__ flat,
+__device__ __forceinline__ void jobs_of_pattern_warp(const Node& nd, uint64_t base, const uint32_t* __restrict__ flat,
                                                      uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin,
                                                      uint32_t row_end, uint32_t lane, unsigned long long& updates, Emit& emit) {
     const uint32_t first = nd.n - nd.l;
@@ -408,10 +435,11 @@ __device__ __forceinline__ void enumerate_jobs(uint64_t lo, uint64_t hi, uint32_
     for (uint64_t b = lo + (uint64_t)warp * 32; b < hi; b += (uint64_t)nwarps * 32) {
         const uint64_t p = b + lane;
         Node nd; nd.parent = -1; nd.n = 0; nd.l = 0; nd.last = 0; nd.loff = 0; nd.up2 = nd.up3 = -1;
-        uint32_t w = 0, base = 0;
+        uint32_t w = 0;
+        uint64_t base = 0;
         if (p < hi) {
             nd = nodes[p];
-            if (nd.l) { w = W[p]; base = (uint32_t)(noff[p] - base0); }
+            if (nd.l) { w = W[p]; base = noff[p] - base0; }
         }
         auto emit_w = [&](uint32_t key, const Job& jb, unsigned long long upd) { emit(key, jb, upd, w); };
         if (nd.l && nd.l <= kSmallL) {
@@ -441,7 +469,7 @@ __device__ __forceinline__ void enumerate_jobs(uint64_t lo, uint64_t hi, uint32_
             bn.l = __shfl_sync(0xffffffffu, nd.l, src);
             bn.last = 0; bn.loff = 0; bn.up2 = bn.up3 = -1;
             const uint32_t bw = __shfl_sync(0xffffffffu, w, src);
-            const uint32_t bbase = __shfl_sync(0xffffffffu, base, src);
+            const uint64_t bbase = __shfl_sync(0xffffffffu, base, src);
             auto emit_b = [&](uint32_t key, const Job& jb, unsigned long long upd) { emit(key, jb, upd, bw); };
             jobs_of_pattern_warp(bn, bbase, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates, emit_b);
         }
@@ -464,7 +492,7 @@ __device__ __forceinline__ void block_slice(uint64_t p0, uint64_t p1, uint64_t& 
 
 __global__ void __launch_bounds__(kBucketThreads)
 k_job_hist_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
-                const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T, uint32_t tile_cols,
+                const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, uint32_t resident, uint32_t T, uint32_t tile_cols,
                 uint32_t rb_shift, uint32_t row_begin, uint32_t row_end, uint32_t nkeys, uint32_t* __restrict__ blockhist,
                 unsigned long long* __restrict__ work, unsigned long long* __restrict__ total_updates) {
     __shared__ uint32_t s_hist[kSmemKeys];
@@ -475,6 +503,7 @@ k_job_hist_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const 
     uint64_t lo, hi;
     block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
+    const uint32_t* flat = flat_all + (resident ? noff[p0] : 0ull);  // the chunk's lists start at its first pattern
     enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
                    [&](uint32_t key, const Job&, unsigned long long upd, uint32_t w) {
                        if (w == 0 || upd == 0) return;  // adds of 0 are skipped, but still counted in U
@@ -524,7 +553,7 @@ __global__ void k_block_offsets(uint32_t nkeys, uint32_t nblocks, const uint32_t
 
 __global__ void __launch_bounds__(kBucketThreads)
 k_job_fill_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
-                const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T, uint32_t tile_cols,
+                const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, uint32_t resident, uint32_t T, uint32_t tile_cols,
                 uint32_t rb_shift, uint32_t row_begin, uint32_t row_end, uint32_t nkeys, const uint32_t* __restrict__ blockbase,
                 Job* __restrict__ jobs) {
     __shared__ uint32_t s_next[kSmemKeys];
@@ -535,6 +564,7 @@ k_job_fill_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const 
     uint64_t lo, hi;
     block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
+    const uint32_t* flat = flat_all + (resident ? noff[p0] : 0ull);  // the chunk's lists start at its first pattern
     enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
                    [&](uint32_t key, Job jb, unsigned long long upd, uint32_t w) {
                        if (w == 0 || upd == 0) return;
@@ -547,13 +577,14 @@ k_job_fill_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const 
 // ---- job bucketing, large key spaces: global atomics (contention is low when keys are many) --
 __global__ void __launch_bounds__(kBucketThreads)
 k_job_hist(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
-           const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T, uint32_t tile_cols, uint32_t rb_shift,
+           const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, uint32_t resident, uint32_t T, uint32_t tile_cols, uint32_t rb_shift,
            uint32_t row_begin, uint32_t row_end, uint32_t* __restrict__ hist, unsigned long long* __restrict__ work,
            unsigned long long* __restrict__ total_updates) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     uint64_t lo, hi;
     block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
+    const uint32_t* flat = flat_all + (resident ? noff[p0] : 0ull);  // the chunk's lists start at its first pattern
     enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
                    [&](uint32_t key, const Job&, unsigned long long upd, uint32_t w) {
                        if (w == 0 || upd == 0) return;
@@ -566,12 +597,13 @@ k_job_hist(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint6
 
 __global__ void __launch_bounds__(kBucketThreads)
 k_job_fill(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
-           const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T, uint32_t tile_cols, uint32_t rb_shift,
+           const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, uint32_t resident, uint32_t T, uint32_t tile_cols, uint32_t rb_shift,
            uint32_t row_begin, uint32_t row_end, uint32_t* __restrict__ cursor, Job* __restrict__ jobs) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     uint64_t lo, hi;
     block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
+    const uint32_t* flat = flat_all + (resident ? noff[p0] : 0ull);  // the chunk's lists start at its first pattern
     enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
                    [&](uint32_t key, Job jb, unsigned long long upd, uint32_t w) {
                        if (w == 0 || upd == 0) return;
@@ -641,9 +673,10 @@ constexpr uint32_t kJobBatch = 8;  // jobs a warp claims at once (16 lanes load 
 
 __global__ void __launch_bounds__(1024)
 k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_units_ptr, const Job* __restrict__ jobs,
-              const uint32_t* __restrict__ flat, uint32_t* __restrict__ tri, uint64_t tri_base, uint32_t T,
-              uint32_t tile_cols, uint32_t rb_shift, uint32_t* __restrict__ unit_counter) {
+              const uint32_t* __restrict__ flat_all, const uint64_t* __restrict__ flat_shift, uint32_t* __restrict__ tri,
+              uint64_t tri_base, uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t* __restrict__ unit_counter) {
     extern __shared__ uint4 tile4[];
+    const uint32_t* flat = flat_all + (flat_shift ? *flat_shift : 0ull);
     uint32_t* tile = reinterpret_cast<uint32_t*>(tile4);
     __shared__ uint32_t s_unit, s_next_job;
     const uint32_t lane = threadIdx.x & 31;
@@ -699,13 +732,14 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
             jb = __shfl_sync(0xffffffffu, jb, 0);
             if (jb >= un.job_end) break;
             const uint32_t cnt = min(kJobBatch, un.job_end - jb);
-            uint4 part = make_uint4(0, 0, 0, 0);  // lane 2q: (off, a, b, A0) of job q; lane 2q+1: (k, w, -, -)
+            uint4 part = make_uint4(0, 0, 0, 0);  // lane 2q: (off, a, b, A0) of job q; lane 2q+1: (k, w, off_hi, -)
             if (lane < 2 * cnt) part = ldg_nc_v4(reinterpret_cast<const uint4*>(jobs + jb) + lane);
             for (uint32_t q = 0; q < cnt; ++q) {
                 const uint32_t off = __shfl_sync(0xffffffffu, part.x, 2 * q), a = __shfl_sync(0xffffffffu, part.y, 2 * q);
                 const uint32_t b = __shfl_sync(0xffffffffu, part.z, 2 * q), A0 = __shfl_sync(0xffffffffu, part.w, 2 * q);
                 const uint32_t k = __shfl_sync(0xffffffffu, part.x, 2 * q + 1), w = __shfl_sync(0xffffffffu, part.y, 2 * q + 1);
-                const uint32_t* list = flat + off;
+                const uint32_t off_hi = __shfl_sync(0xffffffffu, part.z, 2 * q + 1);
+                const uint32_t* list = flat + (((uint64_t)off_hi << 32) | off);
                 uint32_t my_id4 = 0, rowoff = 0;  // lane j < k: 4 * id of row j, shared address of its accumulator row
                 if (lane < k) {
                     const uint32_t my_row = ldg_nc_u32(list + A0 + lane);
@@ -789,8 +823,9 @@ struct kdbx_ctx {
     float ms_upload = 0.f;
 
     // prepared
-    DevBuf nodes, W, loc, loff, noff, coff, bounds, err_flag, cub_tmp, order_in, order, keys_sorted, level_start;
+    DevBuf nodes, W, loc, loff, noff, coff, bounds, err_flag, cub_tmp, order_in, order, keys_sorted, level_start, by_len;
     std::vector<uint32_t> h_level_start;
+    std::vector<std::pair<uint32_t, uint32_t>> levels;  // ranges of `order` per distinct num_samples, ascending
     // per chunk
     DevBuf flat, jobs, hist, work, bucket_off, cursor, ucount, uoff, units, counters, blockhist;
     DevBuf tri, rowupd;
@@ -961,7 +996,8 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
     ctx->sum_l = sums[0]; ctx->sum_n = sums[1];
     {   // deepest level first; level 0 (the sentinel, n = 0) has no parent to feed
         uint32_t end = (uint32_t)P;
-        std::vector<std::pair<uint32_t, uint32_t>> levels;  // ascending n; ranges in `order`
+        std::vector<std::pair<uint32_t, uint32_t>>& levels = ctx->levels;  // ascending n; ranges in `order`
+        levels.clear();
         for (uint32_t v = 0; v <= N; ++v) {
             const uint32_t b = ctx->h_level_start[v];
             if (b == 0xFFFFFFFFu) continue;
@@ -978,7 +1014,19 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
         }
     }
     CK(ctx->loc.ensure((ctx->sum_l + 32) * 4));
-    k_decode_locals<<<blocks_for(P, 128), 128, 0, st>>>(P, ctx->nodes.as<Node>(), ctx->bits.as<uint32_t>(), ctx->poff.as<uint64_t>(),
+    {   // patterns by descending local-list length (keys_sorted is free again: the level starts are on the host)
+        int end_bit = 1;
+        while (end_bit < 32 && (N >> end_bit)) ++end_bit;
+        CK(ctx->by_len.ensure(P * 4));
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, ctx->l.as<uint32_t>(), ctx->keys_sorted.as<uint32_t>(),
+                                                     ctx->order_in.as<uint32_t>(), ctx->by_len.as<uint32_t>(), P, 0, end_bit, st));
+        CK(ctx->cub_tmp.ensure(tmp));
+        CK(cub::DeviceRadixSort::SortPairsDescending(ctx->cub_tmp.p, tmp, ctx->l.as<uint32_t>(), ctx->keys_sorted.as<uint32_t>(),
+                                                     ctx->order_in.as<uint32_t>(), ctx->by_len.as<uint32_t>(), P, 0, end_bit, st));
+        launches += 2;
+    }
+    k_decode_locals<<<blocks_for(P, 128), 128, 0, st>>>(P, ctx->by_len.as<uint32_t>(), ctx->nodes.as<Node>(), ctx->bits.as<uint32_t>(), ctx->poff.as<uint64_t>(),
                                                          ctx->payload.as<uint64_t>(), ctx->payload_words, ctx->loc.as<uint32_t>(), ctx->N,
                                                          ctx->err_flag.as<int>());
     launches += 1;
@@ -995,6 +1043,22 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
 }
 
 float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+// With resident lists a pass may cover far more patterns than the chunk planner's worst-case bound
+// provides slots for: read the exact number of jobs of this pass (bucket_off[nkeys], just scanned)
+// and grow the job / unit arrays to it.  The chunked mode stays within its precomputed bound.
+int ensure_job_slots(kdbx_ctx* ctx, bool resident, uint32_t nkeys, uint64_t& jobs_cap) {
+    if (!resident) return KDBX_OK;
+    uint32_t total = 0;
+    CK(cudaMemcpyAsync(&total, ctx->bucket_off.as<uint32_t>() + nkeys, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if ((uint64_t)total + 64 > jobs_cap) {
+        jobs_cap = (uint64_t)total + 64;
+        CK(ctx->jobs.ensure(jobs_cap * sizeof(Job)));
+        CK(ctx->units.ensure(jobs_cap * sizeof(Unit)));
+    }
+    return KDBX_OK;
+}
 
 // part / num_parts: only the chunks c with c % num_parts == part are executed (pattern sharding for
 // multi-GPU runs: the partial matrices of all parts sum to the full one).
@@ -1035,16 +1099,43 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         return KDBX_OK;
     }
     const uint64_t cap = pl.chunk + (uint64_t)ctx->N * (pl.T + 1) + 64;  // a chunk may overshoot by one pattern
-    CK(ctx->flat.ensure(cap * 4)); CK(ctx->jobs.ensure(cap * sizeof(Job)));
+    // full lists of all patterns resident (level-order expansion) when they take at most 40 % of the
+    // free HBM; otherwise they are expanded chunk by chunk by walking parent chains
+    // (a pattern-sharded part needs only its own chunks' lists: walking their chains is cheaper than
+    // expanding everything on every GPU)
+    bool resident = !(ctx->cfg.flags & KDBX_FLAG_CHUNKED_LISTS) && num_parts == 1;
+    if (resident) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t have = (uint64_t)free_b + ctx->flat.bytes;
+        resident = (ctx->sum_n + 64) * 4 <= have / 5 * 2;
+    }
+    CK(ctx->flat.ensure(resident ? (ctx->sum_n + 64) * 4 : cap * 4));
+    if (!resident) CK(ctx->jobs.ensure(cap * sizeof(Job)));
     CK(ctx->hist.ensure(((size_t)nkeys + 1) * 4)); CK(ctx->work.ensure(((size_t)nkeys + 1) * 8));
     CK(ctx->bucket_off.ensure(((size_t)nkeys + 1) * 4)); CK(ctx->cursor.ensure(((size_t)nkeys + 1) * 4));
     CK(ctx->ucount.ensure(((size_t)nkeys + 1) * 4)); CK(ctx->uoff.ensure(((size_t)nkeys + 1) * 4));
-    CK(ctx->units.ensure(cap * sizeof(Unit)));
+    if (!resident) CK(ctx->units.ensure(cap * sizeof(Unit)));
     CK(ctx->counters.ensure(64));
     unsigned long long* d_total_updates = ctx->counters.as<unsigned long long>();
     uint32_t* d_unit_counter = ctx->counters.as<uint32_t>() + 4;
     CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
 
+    float ms_expand_all = 0.f;
+    if (resident) {
+        cudaEvent_t a = ctx->event();
+        for (size_t k = 0; k < ctx->levels.size(); ++k) {  // ascending num_samples: parents first
+            const uint32_t b = ctx->levels[k].first, e = ctx->levels[k].second;
+            if (e <= b) continue;
+            k_expand_level<<<blocks_for((uint64_t)(e - b) * kLevelLanes, 256), 256, 0, st>>>(e - b, ctx->order.as<uint32_t>() + b, ctx->nodes.as<Node>(),
+                                                                                              ctx->noff.as<uint64_t>(), ctx->loc.as<uint32_t>(),
+                                                                                              ctx->flat.as<uint32_t>());
+            launches += 1;
+        }
+        cudaEvent_t b = ctx->event();
+        CK(cudaStreamSynchronize(st));
+        ms_expand_all = elapsed(a, b);
+    }
     const size_t smem = pl.smem;
     CK(cudaFuncSetAttribute(k_scatter_add, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks_per_sm = 0;
@@ -1058,34 +1149,43 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     struct ChunkEv { cudaEvent_t a, b, c, d; };
     std::vector<ChunkEv> cev;
     cev.reserve(nchunks);
-    for (uint32_t c = 0; c < nchunks; ++c) {
+    if (resident && num_parts == 1) {  // nothing is streamed: one pass over all patterns
+        bounds.assign(2, 0);
+        bounds[1] = ctx->P;
+    }
+    const uint32_t nloops = (uint32_t)bounds.size() - 1;
+    uint64_t jobs_cap = resident ? std::min<uint64_t>(ctx->jobs.bytes / sizeof(Job), ctx->units.bytes / sizeof(Unit)) : cap;  // slots allocated
+    for (uint32_t c = 0; c < nloops; ++c) {
         const uint64_t p0 = bounds[c], p1 = bounds[c + 1];
         if (p1 <= p0 || c % num_parts != part) continue;
         ChunkEv e;
         e.a = ctx->event();
-        k_expand<<<wide_grid, 256, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->loc.as<uint32_t>(), ctx->flat.as<uint32_t>());
+        if (!resident)
+            k_expand<<<wide_grid, 256, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->loc.as<uint32_t>(), ctx->flat.as<uint32_t>());
         e.b = ctx->event();
         CK(cudaMemsetAsync(ctx->work.p, 0, ((size_t)nkeys + 1) * 8, st));
         if (smem_buckets) {
             k_job_hist_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                                  ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
+                                                                  ctx->flat.as<uint32_t>(), resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
                                                                   ctx->blockhist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates);
             k_key_totals<<<blocks_for((uint64_t)nkeys + 1, 128), 128, 0, st>>>(nkeys, wide_grid, ctx->blockhist.as<uint32_t>(), ctx->hist.as<uint32_t>());
             if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
+            if (int rc = ensure_job_slots(ctx, resident, nkeys, jobs_cap)) return rc;
             k_block_offsets<<<blocks_for((uint64_t)nkeys * 32, 256), 256, 0, st>>>(nkeys, wide_grid, ctx->bucket_off.as<uint32_t>(), ctx->blockhist.as<uint32_t>());
             k_job_fill_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                                  ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
+                                                                  ctx->flat.as<uint32_t>(), resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
                                                                   ctx->blockhist.as<uint32_t>(), ctx->jobs.as<Job>());
             launches += 2;
         } else {
             CK(cudaMemsetAsync(ctx->hist.p, 0, ((size_t)nkeys + 1) * 4, st));
             k_job_hist<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                   ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
+                                                   ctx->flat.as<uint32_t>(), resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
                                                    ctx->hist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates);
             if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
+            if (int rc = ensure_job_slots(ctx, resident, nkeys, jobs_cap)) return rc;
             CK(cudaMemcpyAsync(ctx->cursor.p, ctx->bucket_off.p, ((size_t)nkeys + 1) * 4, cudaMemcpyDeviceToDevice, st));
             k_job_fill<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                   ctx->flat.as<uint32_t>(), pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
+                                                   ctx->flat.as<uint32_t>(), resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
                                                    ctx->cursor.as<uint32_t>(), ctx->jobs.as<Job>());
         }
         k_unit_count<<<blocks_for((uint64_t)nkeys + 1, 256), 256, 0, st>>>(nkeys, ctx->hist.as<uint32_t>(), ctx->work.as<unsigned long long>(),
@@ -1096,7 +1196,8 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         CK(cudaMemsetAsync(d_unit_counter, 0, 4, st));
         e.c = ctx->event();
         k_scatter_add<<<scatter_grid, pl.threads, smem, st>>>(ctx->units.as<Unit>(), ctx->uoff.as<uint32_t>() + nkeys, ctx->jobs.as<Job>(),
-                                                              ctx->flat.as<uint32_t>(), d_out, tri_base, pl.T, pl.tile_cols, pl.rb_shift, d_unit_counter);
+                                                              ctx->flat.as<uint32_t>(), resident ? ctx->noff.as<uint64_t>() + p0 : nullptr, d_out, tri_base,
+                                                              pl.T, pl.tile_cols, pl.rb_shift, d_unit_counter);
         e.d = ctx->event();
         launches += 8;
         s.scatter_launches += 1;
@@ -1113,10 +1214,11 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         s.ms_bucket += elapsed(e.b, e.c);
         s.ms_scatter += elapsed(e.c, e.d);
     }
+    s.ms_expand += ms_expand_all;
     s.ms_total = elapsed(ev_start, ev_end);
     s.updates = total_updates;
     s.flat_ids = ctx->sum_n; s.local_ids = ctx->sum_l;
-    s.chunks = nchunks; s.kernel_launches = launches;
+    s.chunks = nloops; s.kernel_launches = launches;
     if (stats) *stats = s;
     return KDBX_OK;
 }
@@ -1185,7 +1287,7 @@ void kdbx_close(kdbx_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->num_kmers, &ctx->parent, &ctx->n, &ctx->l, &ctx->last, &ctx->bits, &ctx->poff, &ctx->payload,
                       &ctx->nodes, &ctx->W, &ctx->loc, &ctx->loff, &ctx->noff, &ctx->coff, &ctx->bounds, &ctx->err_flag,
-                      &ctx->cub_tmp, &ctx->order_in, &ctx->order, &ctx->keys_sorted, &ctx->level_start, &ctx->flat, &ctx->jobs, &ctx->hist, &ctx->work, &ctx->bucket_off, &ctx->cursor,
+                      &ctx->cub_tmp, &ctx->order_in, &ctx->order, &ctx->keys_sorted, &ctx->level_start, &ctx->by_len, &ctx->flat, &ctx->jobs, &ctx->hist, &ctx->work, &ctx->bucket_off, &ctx->cursor,
                       &ctx->ucount, &ctx->uoff, &ctx->units, &ctx->counters, &ctx->blockhist, &ctx->tri, &ctx->rowupd,
                       &ctx->sp_cnt, &ctx->sp_counts, &ctx->sp_rowptr, &ctx->sp_col, &ctx->sp_val, &ctx->slot_off, &ctx->slots,
                       &ctx->q_off, &ctx->q_kmers, &ctx->q_keys, &ctx->q_keys2, &ctx->q_runkeys, &ctx->q_runcnt, &ctx->q_out})

@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <cstring>
+#include <chrono>
+#include <cstdio>
 #include <thread>
 
 #include "gamma.h"
@@ -86,6 +88,10 @@ uint32_t DbBuilder::add_sample(const std::string& name, const uint64_t* kmers, s
     sample_kmers_.push_back((uint32_t)count);  // the reference keeps uint32 counts (src/kmer_db.h:38)
     if (count == 0) return sample;
 
+    static const bool trace = std::getenv("KDBX_TRACE") != nullptr;
+    static double t_tab = 0, t_sort = 0, t_pat = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     // ---- k-mer tables: find-or-insert, parallel over prefix-aligned blocks -----------------------
     sample_patterns_.resize(count);
     const int T = (int)std::min<size_t>((size_t)threads_, std::max<size_t>(1, count / 4096));
@@ -127,9 +133,30 @@ uint32_t DbBuilder::add_sample(const std::string& name, const uint64_t* kmers, s
     }
     for (uint64_t a : added) hdr_.kmers_count += a;
 
+    const double t1 = now();
     // ---- group by pattern, then extend or split (src/prefix_kmer_db.cpp:181-240) ----------------------
-    std::sort(sample_patterns_.begin(), sample_patterns_.end(),
-              [](const auto& a, const auto& b) { return a.first < b.first; });
+    {   // LSD radix sort of (pattern id << 32 | k-mer index): three 11-bit passes over the id bits in use
+        std::vector<uint64_t>& a = sort_a_;
+        std::vector<uint64_t>& b = sort_b_;
+        a.resize(count); b.resize(count);
+        uint32_t max_pid = 0;
+        for (size_t i = 0; i < count; ++i) {
+            const uint32_t pid = (uint32_t)sample_patterns_[i].first;
+            a[i] = ((uint64_t)pid << 32) | (uint32_t)i;
+            max_pid = std::max(max_pid, pid);
+        }
+        for (int shift = 32; shift < 64 && (shift == 32 || (max_pid >> (shift - 32))); shift += 11) {
+            size_t hist[2049] = {0};
+            for (size_t i = 0; i < count; ++i) ++hist[((a[i] >> shift) & 2047) + 1];
+            for (int d = 0; d < 2048; ++d) hist[d + 1] += hist[d];
+            for (size_t i = 0; i < count; ++i) b[hist[(a[i] >> shift) & 2047]++] = a[i];
+            a.swap(b);
+        }
+        sorted_.resize(count);
+        for (size_t i = 0; i < count; ++i) sorted_[i] = sample_patterns_[(uint32_t)a[i]];
+        sorted_.swap(sample_patterns_);
+    }
+    const double t2 = now();
     for (size_t i = 0; i < count;) {
         const int32_t pid = sample_patterns_[i].first;
         size_t j = i + 1;
@@ -153,6 +180,10 @@ uint32_t DbBuilder::add_sample(const std::string& name, const uint64_t* kmers, s
             }
         }
         i = j;
+    }
+    if (trace) {
+        t_tab += t1 - t0; t_sort += t2 - t1; t_pat += now() - t2;
+        std::fprintf(stderr, "[build] sample %u: tables %.3f s, sort %.3f s, patterns %.3f s (cumulative)\n", sample, t_tab, t_sort, t_pat);
     }
     return sample;
 }

@@ -49,7 +49,8 @@ private:
     std::vector<uint64_t> sample_kmers_;
     std::vector<HashTable> tables_;
     std::vector<Pattern> pats_;
-    std::vector<std::pair<int32_t, uint64_t*>> sample_patterns_;  // (pattern id, table slot) per k-mer
+    std::vector<std::pair<int32_t, uint64_t*>> sample_patterns_, sorted_;  // (pattern id, table slot) per k-mer
+    std::vector<uint64_t> sort_a_, sort_b_;
 };
 
 }  // namespace kdbx

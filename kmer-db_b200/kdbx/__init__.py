@@ -69,6 +69,7 @@ class TablesView(C.Structure):
 
 
 METRICS = {"jaccard": 0, "min": 1, "max": 2, "cosine": 3}
+FLAG_CHUNKED_LISTS = 1
 
 
 class SynthParams(C.Structure):
@@ -344,10 +345,11 @@ class Context:
     """One GPU context of libkdbx.so (mirror of SimilarityCalculator's lifetime)."""
 
     def __init__(self, device: int = -1, chunk_ids: int = 0, tile_cols: int = 0, unit_updates: int = 0,
-                 sparse_block_cells: int = 0, query_batch_kmers: int = 0, tile_rows: int = 0, scatter_threads: int = 0):
+                 sparse_block_cells: int = 0, query_batch_kmers: int = 0, tile_rows: int = 0, scatter_threads: int = 0,
+                 flags: int = 0):
         k, _ = load()
         self._k = k
-        cfg = Config(device, 0, chunk_ids, tile_cols, unit_updates, sparse_block_cells, query_batch_kmers, tile_rows, scatter_threads)
+        cfg = Config(device, flags, chunk_ids, tile_cols, unit_updates, sparse_block_cells, query_batch_kmers, tile_rows, scatter_threads)
         p = C.c_void_p()
         rc = k.kdbx_open(C.byref(cfg), C.byref(p))
         if rc != 0:

@@ -66,7 +66,8 @@ def test_random_tries_bit_exact(libs, oracle, seed):
 @pytest.mark.parametrize("cfg", [dict(tile_cols=32), dict(tile_cols=64, chunk_ids=4096), dict(tile_cols=128, unit_updates=64),
                                  dict(chunk_ids=5000, unit_updates=1), dict(tile_cols=1024, unit_updates=1 << 30),
                                  dict(tile_rows=1), dict(tile_rows=8, tile_cols=64), dict(tile_rows=16, scatter_threads=128),
-                                 dict(tile_rows=2, tile_cols=160, scatter_threads=1024, chunk_ids=9000)])
+                                 dict(tile_rows=2, tile_cols=160, scatter_threads=1024, chunk_ids=9000),
+                                 dict(flags=1), dict(flags=1, chunk_ids=4096, tile_cols=96), dict(flags=1, tile_rows=4, unit_updates=50)])
 def test_schedule_knobs_do_not_change_results(libs, oracle, cfg):
     """column tiles (T>1), row blocks of 1..32 rows, many chunks, tiny / huge work units: same bits."""
     rng = np.random.default_rng(7)
@@ -76,8 +77,10 @@ def test_schedule_knobs_do_not_change_results(libs, oracle, cfg):
     got, st = _run(libs, N, a, **cfg)
     assert st.updates == U
     assert np.array_equal(got, want)
-    if "chunk_ids" in cfg:
+    if "chunk_ids" in cfg and cfg.get("flags"):
         assert st.chunks > 1
+    # flags=1 (KDBX_FLAG_CHUNKED_LISTS) forces the chunked parent-chain expansion; the default here is
+    # the resident level-ordered one
 
 
 def test_edge_cases(libs, oracle):
@@ -182,6 +185,32 @@ def test_row_sharding_matches_full_matrix(libs, oracle):
                 total += st.updates
             assert total == U
             assert np.array_equal(np.concatenate(parts), want)
+
+
+@pytest.mark.parametrize("flags", [0, 1])
+def test_pattern_parts_sum_to_full_matrix(libs, oracle, flags):
+    """kdbx_all2all_dense_part_device: the partial matrices of all parts add up (uint32) to the full one."""
+    import torch
+    t = libs.Trie.synth(num_samples=300, num_clusters=3, genome_kmers=40000, seed=6)
+    N = t.num_samples
+    want, U = ou.oracle_all2all(oracle, N, t.arrays())
+    with libs.Context(device=0, chunk_ids=200000, flags=flags) as c:
+        c.load_patterns(t)
+        for parts in (1, 2, 5):
+            acc = torch.zeros(ou.tri_cells(N), dtype=torch.int64, device="cuda:0")
+            buf = torch.zeros(ou.tri_cells(N), dtype=torch.int32, device="cuda:0")
+            total = 0
+            for part in range(parts):
+                st = c.all2all_dense_part_device(part, parts, buf.data_ptr())
+                torch.cuda.synchronize()
+                acc += buf.to(torch.int64) & 0xFFFFFFFF
+                total += st.updates
+                if parts > 1:
+                    assert st.chunks > parts  # pattern parts always stream chunk by chunk
+            assert total == U
+            assert np.array_equal((acc & 0xFFFFFFFF).cpu().numpy().astype(np.uint32), want)
+        with pytest.raises(libs.KdbxError, match="bad part"):
+            c.all2all_dense_part_device(3, 3, buf.data_ptr())
 
 
 def test_generated_db_matches_reference_binary(libs, ref_bin, tmp_path):
