@@ -257,7 +257,7 @@ def main():
     if by_patterns and chunk_ids == 0:
         chunk_ids = max(1 << 22, (64 << 20) // world)  # finer chunks: ~62 per rank, balanced round-robin
     ctx = kdbx.Context(device=local_rank, chunk_ids=chunk_ids, tile_cols=a.tile_cols, unit_updates=a.unit_updates,
-                       tile_rows=a.tile_rows, scatter_threads=a.scatter_threads, flags=1 if a.chunked_lists else 0)
+                       tile_rows=a.tile_rows, scatter_threads=a.scatter_threads, flags=(kdbx.FLAG_CHUNKED_LISTS if a.chunked_lists else 0) | kdbx.FLAG_ASYNC_UPLOAD)
     ctx.load_patterns(trie)
     if by_patterns:
         r0, r1 = 0, N

@@ -64,6 +64,11 @@ typedef struct kdbx_config {
  * patterns would fit in HBM at once; the default picks the resident, level-ordered expansion
  * whenever 4 * sum(num_samples) bytes take at most 40 % of the free device memory. */
 #define KDBX_FLAG_CHUNKED_LISTS 1u
+/* kdbx_load_patterns returns as soon as the copies are enqueued (headers on the compute stream, the
+ * Elias-gamma payload on a second stream) instead of waiting for them, so that the first stages of
+ * the next compute call overlap the tail of the transfer.  The caller's arrays must then stay
+ * valid and unchanged until that compute call has returned. */
+#define KDBX_FLAG_ASYNC_UPLOAD 2u
 
 /* Borrowed, read-only SoA view of `std::vector<pattern_t>` (src/pattern.h:42-55) as
  * PrefixKmerDb::getPatterns() exposes it (src/prefix_kmer_db.h:87-175).  One entry per trie

@@ -71,6 +71,12 @@ struct U32AsU64 {
     const uint32_t* p; uint64_t n;
     __host__ __device__ uint64_t operator()(uint64_t i) const { return i < n ? (uint64_t)p[i] : 0ull; }
 };
+// slots of a pattern's full list in `flat`: lists start on 16-byte boundaries so that the level-order
+// expansion can copy a parent's list with 128-bit loads and stores
+struct ListSlots {
+    const uint32_t* p; uint64_t n;
+    __host__ __device__ uint64_t operator()(uint64_t i) const { return i < n ? (uint64_t)((p[i] + 3u) & ~3u) : 0ull; }
+};
 struct PayloadWords {
     const uint32_t* bits; uint64_t n;
     __host__ __device__ uint64_t operator()(uint64_t i) const {
@@ -86,7 +92,7 @@ struct ChunkCost {
     __host__ __device__ uint64_t operator()(uint64_t i) const {
         if (i >= cnt) return 0ull;
         const uint64_t jobs = (uint64_t)l[i] * (uint64_t)(last[i] / tile_cols + 1u);
-        const uint64_t ids = n[i];
+        const uint64_t ids = (n[i] + 3u) & ~3u;
         return jobs > ids ? jobs : ids;
     }
 };
@@ -170,44 +176,77 @@ __device__ __forceinline__ uint32_t gamma_next(const uint64_t* __restrict__ w, u
 }
 
 // Decodes the LOCAL ids of every pattern into d_loc (ascending), one thread per pattern.  The
-// stream holds the deltas in append order and only the LAST id is stored (src/pattern.cpp:
-// 99-109), so the bits are walked twice — first to sum the deltas (registers only), then to
-// emit ids front to back — which writes every id exactly once and never reads d_loc back.
-// `by_len` lists the patterns by descending num_local_samples, so that the 32 threads of a warp walk
-// bit streams of (nearly) equal length instead of waiting for the longest of 32 arbitrary ones.
-__global__ void k_decode_locals(uint64_t P, const uint32_t* __restrict__ by_len, const Node* __restrict__ nodes,
-                                const uint32_t* __restrict__ bits, const uint64_t* __restrict__ poff,
-                                const uint64_t* __restrict__ payload, uint64_t payload_words, uint32_t* __restrict__ loc, uint32_t N,
-                                int* __restrict__ err) {
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    const uint64_t p = by_len[idx];
-    const Node nd = nodes[p];
-    if (nd.l == 0) return;
-    uint32_t* out = loc + nd.loff;
-    // the parent's list must end before this one starts, or full lists would not ascend
-    const uint32_t floor_id = nd.parent >= 0 && nodes[nd.parent].l ? nodes[nd.parent].last + 1u : 0u;
-    if (nd.l == 1) {
-        out[0] = nd.last;
-        if (nd.last < floor_id) atomicExch(err, 3);
-        return;
+// stream holds the deltas in append order and only the LAST id is stored (src/pattern.cpp:99-109):
+// a thread walks its bits once, parking the deltas, then turns them into ids front to back.
+// The local lists of the 128 consecutive patterns of a block are contiguous in d_loc, so they are
+// staged in shared memory and written out with coalesced stores (a thread writing its own list
+// straight to HBM costs one 32-byte sector per 4-byte id); blocks whose lists do not fit the stage
+// write directly.
+constexpr int kDecodeThreads = 128;
+constexpr uint32_t kDecodeStage = 10240;  // ids (40 KB)
+__global__ void __launch_bounds__(kDecodeThreads)
+k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __restrict__ loff,
+                const uint32_t* __restrict__ bits, const uint64_t* __restrict__ poff, const uint64_t* __restrict__ payload,
+                uint64_t payload_words, uint32_t* __restrict__ loc, uint32_t N, int* __restrict__ err) {
+    __shared__ uint32_t s_ids[kDecodeStage];
+    const uint64_t p0 = (uint64_t)blockIdx.x * kDecodeThreads;
+    const uint64_t p = p0 + threadIdx.x;
+    const uint64_t p_end = p0 + kDecodeThreads < P ? p0 + kDecodeThreads : P;
+    const uint64_t base = loff[p0];
+    const uint64_t total = loff[p_end] - base;
+    const bool staged = total <= kDecodeStage;
+    if (p < P) {
+        const Node nd = nodes[p];
+        if (nd.l) {
+            uint32_t* out = staged ? s_ids + (nd.loff - base) : loc + nd.loff;
+            // the parent's list must end before this one starts, or full lists would not ascend
+            const uint32_t floor_id = nd.parent >= 0 && nodes[nd.parent].l ? nodes[nd.parent].last + 1u : 0u;
+            if (nd.l == 1) {
+                out[0] = nd.last;
+                if (nd.last < floor_id) atomicExch(err, 3);
+            } else {
+                const uint32_t nb = bits[p];
+                const uint64_t po = poff[p];
+                bool ok = po + ((uint64_t)(nb + 127u) / 128u) * 2u <= payload_words;
+                if (!ok) atomicExch(err, 5);
+                uint32_t pos = 0;
+                uint64_t sum = 0;
+                if (ok) {
+                    const uint64_t* w = payload + po;
+                    uint32_t i = 1;
+                    while (i < nd.l && pos < nb) {
+                        // a delta of 1 is the single bit 0 (consecutive sample ids): take a whole run of
+                        // zero bits at once — most of a cluster's lists are such runs
+                        const uint32_t off = pos & 63;
+                        const uint64_t x = w[pos >> 6] << off;
+                        uint32_t z = x ? (uint32_t)__clzll((long long)x) : 64u;
+                        z = min(min(z, 64u - off), min(nb - pos, nd.l - i));
+                        if (z) {
+                            for (uint32_t t = 0; t < z; ++t) out[i + t] = 1u;
+                            i += z; pos += z; sum += z;
+                            continue;
+                        }
+                        const uint32_t d = gamma_next(w, pos, nb);
+                        out[i++] = d;
+                        sum += d;
+                    }
+                    if (i != nd.l || pos != nb) { atomicExch(err, 1); ok = false; }
+                    else if (sum > nd.last) { atomicExch(err, 2); ok = false; }
+                }
+                if (ok) {
+                    uint32_t cur = nd.last - (uint32_t)sum;
+                    if (cur < floor_id) atomicExch(err, 3);
+                    out[0] = cur;
+                    for (uint32_t i = 1; i < nd.l; ++i) { cur += out[i]; out[i] = cur; }
+                } else {
+                    for (uint32_t i = 0; i < nd.l; ++i) out[i] = 0;  // never chased: the call fails on the error flag
+                }
+            }
+        }
     }
-    const uint32_t nb = bits[p];
-    const uint64_t po = poff[p];
-    if (po + ((uint64_t)(nb + 127u) / 128u) * 2u > payload_words) { atomicExch(err, 5); return; }
-    const uint64_t* w = payload + po;
-    uint32_t pos = 0;
-    uint64_t sum = 0;
-    for (uint32_t i = 0; i + 1 < nd.l; ++i) sum += gamma_next(w, pos, nb);
-    if (pos != nb) { atomicExch(err, 1); return; }
-    if (sum > nd.last) { atomicExch(err, 2); return; }
-    uint32_t cur = nd.last - (uint32_t)sum;
-    if (cur < floor_id) atomicExch(err, 3);
-    out[0] = cur;
-    pos = 0;
-    for (uint32_t i = 1; i < nd.l; ++i) {
-        cur += gamma_next(w, pos, nb);
-        out[i] = cur;
+    if (staged) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < (uint32_t)total; i += kDecodeThreads) loc[base + i] = s_ids[i];
     }
 }
 
@@ -305,22 +344,33 @@ __global__ void k_expand(uint64_t p0, uint64_t p1, const Node* __restrict__ node
 // pattern's full list is its parent's full list followed by its own local ids, so the patterns of
 // one num_samples level — whose parents all sit on earlier levels, n_parent < n — are expanded by
 // two contiguous copies each.  One launch per level, ascending; no pointer chasing at all.
-constexpr uint32_t kLevelLanes = 16;
+constexpr uint32_t kLevelLanes = 8;
 __global__ void k_expand_level(uint32_t count, const uint32_t* __restrict__ order, const Node* __restrict__ nodes,
                                const uint64_t* __restrict__ noff, const uint32_t* __restrict__ loc, uint32_t* flat) {
     const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / kLevelLanes;
     const uint32_t sub = threadIdx.x & (kLevelLanes - 1);
-    if (gid >= count) return;
-    const uint32_t p = order[gid];
-    const Node nd = nodes[p];
-    uint32_t* dst = flat + noff[p];
-    const uint32_t npar = nd.n - nd.l;
-    if (nd.parent >= 0) {
-        const uint32_t* src = flat + noff[nd.parent];
-        for (uint32_t j = sub; j < npar; j += kLevelLanes) dst[j] = src[j];
+    const bool have = gid < count;
+    Node nd; nd.parent = -1; nd.n = 0; nd.l = 0; nd.last = 0; nd.loff = 0; nd.up2 = nd.up3 = -1;
+    uint32_t* dst = flat;
+    if (have) {
+        const uint32_t p = order[gid];
+        nd = nodes[p];
+        dst = flat + noff[p];
     }
-    const uint32_t* own = loc + nd.loff;
-    for (uint32_t j = sub; j < nd.l; j += kLevelLanes) dst[npar + j] = own[j];
+    const uint32_t npar = nd.n - nd.l;
+    if (have && nd.parent >= 0) {
+        // both lists start 16-byte aligned (ListSlots); the copy may run up to 3 ids past the parent's
+        // list — still inside this pattern's slots, overwritten by its own ids below
+        const uint4* src = reinterpret_cast<const uint4*>(flat + noff[nd.parent]);
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        const uint32_t n4 = (npar + 3u) >> 2;
+        for (uint32_t j = sub; j < n4; j += kLevelLanes) d4[j] = src[j];
+    }
+    __syncwarp();  // the tail of the 128-bit copy must land before the own ids that overwrite it
+    if (have) {
+        const uint32_t* own = loc + nd.loff;
+        for (uint32_t j = sub; j < nd.l; j += kLevelLanes) dst[npar + j] = own[j];
+    }
 }
 
 // A job = one pattern x one block of matrix rows x one column tile: rows full[A0 .. A0+k) (k local
@@ -389,7 +439,7 @@ __device__ __forceinline__ void emit_run(const Node& nd, uint64_t base, const ui
 // Warp-cooperative enumeration of one (long) pattern: lanes over the pattern's local positions.
 template <class Emit>
 __device__ __forceinline__ void jobs_of_pattern_warp(const Node& nd, uint64_t base, const uint32_t* __restrict__ flat,
-                                                     uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin,
+                                                     const uint32_t* __restrict__ loc, uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin,
                                                      uint32_t row_end, uint32_t lane, unsigned long long& updates, Emit& emit) {
     const uint32_t first = nd.n - nd.l;
     const uint32_t rounds = (nd.l + 31) / 32;
@@ -401,7 +451,7 @@ __device__ __forceinline__ void jobs_of_pattern_warp(const Node& nd, uint64_t ba
         uint32_t row = 0xFFFFFFFFu;
         bool active = false;
         if (have) {
-            row = list[i];
+            row = loc[nd.loff + j];  // the rows are the node's own local ids: contiguous in d_loc
             active = row >= row_begin && row < row_end;
         }
         if (active) updates += i;
@@ -429,9 +479,10 @@ constexpr uint32_t kSmallL = 8;
 template <class Emit>
 __device__ __forceinline__ void enumerate_jobs(uint64_t lo, uint64_t hi, uint32_t warp, uint32_t nwarps,
                                                const Node* __restrict__ nodes, const uint64_t* __restrict__ noff, uint64_t base0,
-                                               const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat, uint32_t T,
-                                               uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin, uint32_t row_end,
-                                               uint32_t lane, unsigned long long& updates, Emit emit) {
+                                               const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat,
+                                               const uint32_t* __restrict__ loc, uint32_t T, uint32_t tile_cols, uint32_t rb_shift,
+                                               uint32_t row_begin, uint32_t row_end, uint32_t lane, unsigned long long& updates,
+                                               Emit emit) {
     for (uint64_t b = lo + (uint64_t)warp * 32; b < hi; b += (uint64_t)nwarps * 32) {
         const uint64_t p = b + lane;
         Node nd; nd.parent = -1; nd.n = 0; nd.l = 0; nd.last = 0; nd.loff = 0; nd.up2 = nd.up3 = -1;
@@ -445,9 +496,10 @@ __device__ __forceinline__ void enumerate_jobs(uint64_t lo, uint64_t hi, uint32_
         if (nd.l && nd.l <= kSmallL) {
             const uint32_t first = nd.n - nd.l;
             const uint32_t* list = flat + base;
+            const uint32_t* rows = loc + nd.loff;
             uint32_t run_i = 0, run_k = 0, run_rb = 0;
             for (uint32_t j = 0; j < nd.l; ++j) {
-                const uint32_t row = list[first + j];
+                const uint32_t row = rows[j];
                 const bool active = row >= row_begin && row < row_end;
                 const uint32_t rb = row >> rb_shift;
                 if (active) updates += first + j;
@@ -467,11 +519,11 @@ __device__ __forceinline__ void enumerate_jobs(uint64_t lo, uint64_t hi, uint32_
             bn.parent = __shfl_sync(0xffffffffu, nd.parent, src);
             bn.n = __shfl_sync(0xffffffffu, nd.n, src);
             bn.l = __shfl_sync(0xffffffffu, nd.l, src);
-            bn.last = 0; bn.loff = 0; bn.up2 = bn.up3 = -1;
+            bn.last = 0; bn.loff = __shfl_sync(0xffffffffu, nd.loff, src); bn.up2 = bn.up3 = -1;
             const uint32_t bw = __shfl_sync(0xffffffffu, w, src);
             const uint64_t bbase = __shfl_sync(0xffffffffu, base, src);
             auto emit_b = [&](uint32_t key, const Job& jb, unsigned long long upd) { emit(key, jb, upd, bw); };
-            jobs_of_pattern_warp(bn, bbase, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates, emit_b);
+            jobs_of_pattern_warp(bn, bbase, flat, loc, T, tile_cols, rb_shift, row_begin, row_end, lane, updates, emit_b);
         }
     }
 }
@@ -492,8 +544,8 @@ __device__ __forceinline__ void block_slice(uint64_t p0, uint64_t p1, uint64_t& 
 
 __global__ void __launch_bounds__(kBucketThreads)
 k_job_hist_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
-                const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, uint32_t resident, uint32_t T, uint32_t tile_cols,
-                uint32_t rb_shift, uint32_t row_begin, uint32_t row_end, uint32_t nkeys, uint32_t* __restrict__ blockhist,
+                const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, const uint32_t* __restrict__ loc, uint32_t resident,
+                uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin, uint32_t row_end, uint32_t nkeys, uint32_t* __restrict__ blockhist,
                 unsigned long long* __restrict__ work, unsigned long long* __restrict__ total_updates) {
     __shared__ uint32_t s_hist[kSmemKeys];
     __shared__ unsigned long long s_work[kSmemKeys];
@@ -504,7 +556,7 @@ k_job_hist_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const 
     block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
     const uint32_t* flat = flat_all + (resident ? noff[p0] : 0ull);  // the chunk's lists start at its first pattern
-    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, loc, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
                    [&](uint32_t key, const Job&, unsigned long long upd, uint32_t w) {
                        if (w == 0 || upd == 0) return;  // adds of 0 are skipped, but still counted in U
                        atomicAdd(&s_hist[key], 1u);
@@ -553,8 +605,8 @@ __global__ void k_block_offsets(uint32_t nkeys, uint32_t nblocks, const uint32_t
 
 __global__ void __launch_bounds__(kBucketThreads)
 k_job_fill_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
-                const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, uint32_t resident, uint32_t T, uint32_t tile_cols,
-                uint32_t rb_shift, uint32_t row_begin, uint32_t row_end, uint32_t nkeys, const uint32_t* __restrict__ blockbase,
+                const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, const uint32_t* __restrict__ loc, uint32_t resident,
+                uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin, uint32_t row_end, uint32_t nkeys, const uint32_t* __restrict__ blockbase,
                 Job* __restrict__ jobs) {
     __shared__ uint32_t s_next[kSmemKeys];
     const uint32_t* mine = blockbase + (size_t)blockIdx.x * nkeys;
@@ -565,7 +617,7 @@ k_job_fill_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const 
     block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
     const uint32_t* flat = flat_all + (resident ? noff[p0] : 0ull);  // the chunk's lists start at its first pattern
-    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, loc, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
                    [&](uint32_t key, Job jb, unsigned long long upd, uint32_t w) {
                        if (w == 0 || upd == 0) return;
                        const uint32_t slot = atomicAdd(&s_next[key], 1u);
@@ -577,7 +629,8 @@ k_job_fill_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const 
 // ---- job bucketing, large key spaces: global atomics (contention is low when keys are many) --
 __global__ void __launch_bounds__(kBucketThreads)
 k_job_hist(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
-           const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, uint32_t resident, uint32_t T, uint32_t tile_cols, uint32_t rb_shift,
+           const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, const uint32_t* __restrict__ loc, uint32_t resident,
+           uint32_t T, uint32_t tile_cols, uint32_t rb_shift,
            uint32_t row_begin, uint32_t row_end, uint32_t* __restrict__ hist, unsigned long long* __restrict__ work,
            unsigned long long* __restrict__ total_updates) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -585,7 +638,7 @@ k_job_hist(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint6
     block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
     const uint32_t* flat = flat_all + (resident ? noff[p0] : 0ull);  // the chunk's lists start at its first pattern
-    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, loc, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
                    [&](uint32_t key, const Job&, unsigned long long upd, uint32_t w) {
                        if (w == 0 || upd == 0) return;
                        atomicAdd(&hist[key], 1u);
@@ -597,14 +650,15 @@ k_job_hist(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint6
 
 __global__ void __launch_bounds__(kBucketThreads)
 k_job_fill(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
-           const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, uint32_t resident, uint32_t T, uint32_t tile_cols, uint32_t rb_shift,
+           const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, const uint32_t* __restrict__ loc, uint32_t resident,
+           uint32_t T, uint32_t tile_cols, uint32_t rb_shift,
            uint32_t row_begin, uint32_t row_end, uint32_t* __restrict__ cursor, Job* __restrict__ jobs) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     uint64_t lo, hi;
     block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
     const uint32_t* flat = flat_all + (resident ? noff[p0] : 0ull);  // the chunk's lists start at its first pattern
-    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, loc, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
                    [&](uint32_t key, Job jb, unsigned long long upd, uint32_t w) {
                        if (w == 0 || upd == 0) return;
                        const uint32_t slot = atomicAdd(&cursor[key], 1u);
@@ -751,25 +805,33 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
                 for (uint32_t c = a; c < bc; c += 128) {
                     const uint32_t rem = bc - c;
                     const uint32_t* p = list + c + lane;
-                    uint32_t x0 = pad4, x1 = pad4, x2 = pad4, x3 = pad4;
-                    if (lane < rem) x0 = ldg_nc_u32(p) * 4u;
-                    if (lane + 32 < rem) x1 = ldg_nc_u32(p + 32) * 4u;
-                    if (lane + 64 < rem) x2 = ldg_nc_u32(p + 64) * 4u;
-                    if (lane + 96 < rem) x3 = ldg_nc_u32(p + 96) * 4u;
-                    if (rem > 96) {
+                    if (rem >= 128) {  // full slice: no lane is idle, no predicates
+                        const uint32_t x0 = ldg_nc_u32(p) * 4u, x1 = ldg_nc_u32(p + 32) * 4u;
+                        const uint32_t x2 = ldg_nc_u32(p + 64) * 4u, x3 = ldg_nc_u32(p + 96) * 4u;
                         for (uint32_t j = 0; j < k; ++j) {
                             const uint32_t ro = __shfl_sync(0xffffffffu, rowoff, j);
                             red_shared_add(ro + x0, w); red_shared_add(ro + x1, w);
                             red_shared_add(ro + x2, w); red_shared_add(ro + x3, w);
                         }
-                    } else if (rem > 32) {
-                        for (uint32_t j = 0; j < k; ++j) {
-                            const uint32_t ro = __shfl_sync(0xffffffffu, rowoff, j);
-                            red_shared_add(ro + x0, w); red_shared_add(ro + x1, w);
-                            if (rem > 64) red_shared_add(ro + x2, w);
-                        }
-                    } else {
-                        for (uint32_t j = 0; j < k; ++j) red_shared_add(__shfl_sync(0xffffffffu, rowoff, j) + x0, w);
+                        continue;
+                    }
+                    // last, ragged slice: full 32-id groups reduce unconditionally, the final partial group
+                    // under a lane predicate (an idle lane parked on a padding word would still occupy
+                    // a bank and cost the group a second wavefront)
+                    const uint32_t full = rem >> 5;          // complete 32-id groups (0..3)
+                    const bool tail = lane < (rem & 31u);     // this lane has an id in the partial group
+                    uint32_t x0 = pad4, x1 = pad4, x2 = pad4, x3 = pad4;
+                    if (lane < rem) x0 = ldg_nc_u32(p) * 4u;
+                    if (lane + 32 < rem) x1 = ldg_nc_u32(p + 32) * 4u;
+                    if (lane + 64 < rem) x2 = ldg_nc_u32(p + 64) * 4u;
+                    if (lane + 96 < rem) x3 = ldg_nc_u32(p + 96) * 4u;
+                    const uint32_t xt = full == 0 ? x0 : full == 1 ? x1 : full == 2 ? x2 : x3;
+                    for (uint32_t j = 0; j < k; ++j) {
+                        const uint32_t ro = __shfl_sync(0xffffffffu, rowoff, j);
+                        if (full > 0) red_shared_add(ro + x0, w);
+                        if (full > 1) red_shared_add(ro + x1, w);
+                        if (full > 2) red_shared_add(ro + x2, w);
+                        if (tail) red_shared_add(ro + xt, w);
                     }
                 }
                 // triangular tail: row j also receives the rows before it that lie in [a, b)
@@ -810,6 +872,9 @@ struct kdbx_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t up_stream = nullptr;     // second H2D stream: the payload travels while the scans run
+    cudaEvent_t ev_up_begin = nullptr, ev_up_hdr = nullptr, ev_up_payload = nullptr;
+    bool upload_pending = false;          // KDBX_FLAG_ASYNC_UPLOAD: copies may still be in flight
     kdbx_config cfg{};
     std::string err;
 
@@ -823,7 +888,7 @@ struct kdbx_ctx {
     float ms_upload = 0.f;
 
     // prepared
-    DevBuf nodes, W, loc, loff, noff, coff, bounds, err_flag, cub_tmp, order_in, order, keys_sorted, level_start, by_len;
+    DevBuf nodes, W, loc, loff, noff, coff, bounds, err_flag, cub_tmp, order_in, order, keys_sorted, level_start;
     std::vector<uint32_t> h_level_start;
     std::vector<std::pair<uint32_t, uint32_t>> levels;  // ranges of `order` per distinct num_samples, ascending
     // per chunk
@@ -946,7 +1011,7 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
         if (int rc = scan_exclusive(ctx, it, ctx->loff.as<uint64_t>(), P + 1)) return rc;
     }
     {
-        cub::TransformInputIterator<uint64_t, U32AsU64, cub::CountingInputIterator<uint64_t>> it(idx, U32AsU64{ctx->n.as<uint32_t>(), P});
+        cub::TransformInputIterator<uint64_t, ListSlots, cub::CountingInputIterator<uint64_t>> it(idx, ListSlots{ctx->n.as<uint32_t>(), P});
         if (int rc = scan_exclusive(ctx, it, ctx->noff.as<uint64_t>(), P + 1)) return rc;
     }
     {
@@ -1014,19 +1079,8 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
         }
     }
     CK(ctx->loc.ensure((ctx->sum_l + 32) * 4));
-    {   // patterns by descending local-list length (keys_sorted is free again: the level starts are on the host)
-        int end_bit = 1;
-        while (end_bit < 32 && (N >> end_bit)) ++end_bit;
-        CK(ctx->by_len.ensure(P * 4));
-        size_t tmp = 0;
-        CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, ctx->l.as<uint32_t>(), ctx->keys_sorted.as<uint32_t>(),
-                                                     ctx->order_in.as<uint32_t>(), ctx->by_len.as<uint32_t>(), P, 0, end_bit, st));
-        CK(ctx->cub_tmp.ensure(tmp));
-        CK(cub::DeviceRadixSort::SortPairsDescending(ctx->cub_tmp.p, tmp, ctx->l.as<uint32_t>(), ctx->keys_sorted.as<uint32_t>(),
-                                                     ctx->order_in.as<uint32_t>(), ctx->by_len.as<uint32_t>(), P, 0, end_bit, st));
-        launches += 2;
-    }
-    k_decode_locals<<<blocks_for(P, 128), 128, 0, st>>>(P, ctx->by_len.as<uint32_t>(), ctx->nodes.as<Node>(), ctx->bits.as<uint32_t>(), ctx->poff.as<uint64_t>(),
+    CK(cudaStreamWaitEvent(st, ctx->ev_up_payload, 0));  // the payload may still be on its way (second H2D stream)
+    k_decode_locals<<<blocks_for(P, kDecodeThreads), kDecodeThreads, 0, st>>>(P, ctx->nodes.as<Node>(), ctx->loff.as<uint64_t>(), ctx->bits.as<uint32_t>(), ctx->poff.as<uint64_t>(),
                                                          ctx->payload.as<uint64_t>(), ctx->payload_words, ctx->loc.as<uint32_t>(), ctx->N,
                                                          ctx->err_flag.as<int>());
     launches += 1;
@@ -1062,6 +1116,19 @@ int ensure_job_slots(kdbx_ctx* ctx, bool resident, uint32_t nkeys, uint64_t& job
 
 // part / num_parts: only the chunks c with c % num_parts == part are executed (pattern sharding for
 // multi-GPU runs: the partial matrices of all parts sum to the full one).
+// Waits for the copies of kdbx_load_patterns and records their duration.
+int finish_upload(kdbx_ctx* ctx) {
+    if (!ctx->upload_pending) return KDBX_OK;
+    CK(cudaEventSynchronize(ctx->ev_up_hdr));
+    CK(cudaEventSynchronize(ctx->ev_up_payload));
+    float hdr = 0.f, all = 0.f;
+    cudaEventElapsedTime(&hdr, ctx->ev_up_begin, ctx->ev_up_hdr);
+    cudaEventElapsedTime(&all, ctx->ev_up_begin, ctx->ev_up_payload);
+    ctx->ms_upload = std::max(hdr, all);
+    ctx->upload_pending = false;
+    return KDBX_OK;
+}
+
 int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uint32_t* d_out, kdbx_stats* stats,
                         uint32_t part = 0, uint32_t num_parts = 1) {
     if (!ctx->loaded) return ctx->fail(KDBX_ERR_STATE, "no patterns loaded (call kdbx_load_patterns first)");
@@ -1166,26 +1233,26 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         CK(cudaMemsetAsync(ctx->work.p, 0, ((size_t)nkeys + 1) * 8, st));
         if (smem_buckets) {
             k_job_hist_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                                  ctx->flat.as<uint32_t>(), resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
+                                                                  ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
                                                                   ctx->blockhist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates);
             k_key_totals<<<blocks_for((uint64_t)nkeys + 1, 128), 128, 0, st>>>(nkeys, wide_grid, ctx->blockhist.as<uint32_t>(), ctx->hist.as<uint32_t>());
             if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
             if (int rc = ensure_job_slots(ctx, resident, nkeys, jobs_cap)) return rc;
             k_block_offsets<<<blocks_for((uint64_t)nkeys * 32, 256), 256, 0, st>>>(nkeys, wide_grid, ctx->bucket_off.as<uint32_t>(), ctx->blockhist.as<uint32_t>());
             k_job_fill_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                                  ctx->flat.as<uint32_t>(), resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
+                                                                  ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
                                                                   ctx->blockhist.as<uint32_t>(), ctx->jobs.as<Job>());
             launches += 2;
         } else {
             CK(cudaMemsetAsync(ctx->hist.p, 0, ((size_t)nkeys + 1) * 4, st));
             k_job_hist<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                   ctx->flat.as<uint32_t>(), resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
+                                                   ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
                                                    ctx->hist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates);
             if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
             if (int rc = ensure_job_slots(ctx, resident, nkeys, jobs_cap)) return rc;
             CK(cudaMemcpyAsync(ctx->cursor.p, ctx->bucket_off.p, ((size_t)nkeys + 1) * 4, cudaMemcpyDeviceToDevice, st));
             k_job_fill<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                   ctx->flat.as<uint32_t>(), resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
+                                                   ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
                                                    ctx->cursor.as<uint32_t>(), ctx->jobs.as<Job>());
         }
         k_unit_count<<<blocks_for((uint64_t)nkeys + 1, 256), 256, 0, st>>>(nkeys, ctx->hist.as<uint32_t>(), ctx->work.as<unsigned long long>(),
@@ -1214,6 +1281,8 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         s.ms_bucket += elapsed(e.b, e.c);
         s.ms_scatter += elapsed(e.c, e.d);
     }
+    if (int rc = finish_upload(ctx)) return rc;
+    s.ms_upload = ctx->ms_upload;
     s.ms_expand += ms_expand_all;
     s.ms_total = elapsed(ev_start, ev_end);
     s.updates = total_updates;
@@ -1272,7 +1341,10 @@ int kdbx_open(const kdbx_config* cfg, kdbx_ctx** out) {
     ctx->device = dev;
     ctx->sm_count = pr.multiProcessorCount;
     if (cfg) ctx->cfg = *cfg;
-    if ((e = cudaSetDevice(dev)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    if ((e = cudaSetDevice(dev)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev_up_begin)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_up_hdr)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev_up_payload)) != cudaSuccess) {
         g_open_error = std::string("kdbx_open: ") + cudaGetErrorString(e);
         delete ctx;
         return KDBX_ERR_CUDA;
@@ -1287,12 +1359,14 @@ void kdbx_close(kdbx_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->num_kmers, &ctx->parent, &ctx->n, &ctx->l, &ctx->last, &ctx->bits, &ctx->poff, &ctx->payload,
                       &ctx->nodes, &ctx->W, &ctx->loc, &ctx->loff, &ctx->noff, &ctx->coff, &ctx->bounds, &ctx->err_flag,
-                      &ctx->cub_tmp, &ctx->order_in, &ctx->order, &ctx->keys_sorted, &ctx->level_start, &ctx->by_len, &ctx->flat, &ctx->jobs, &ctx->hist, &ctx->work, &ctx->bucket_off, &ctx->cursor,
+                      &ctx->cub_tmp, &ctx->order_in, &ctx->order, &ctx->keys_sorted, &ctx->level_start, &ctx->flat, &ctx->jobs, &ctx->hist, &ctx->work, &ctx->bucket_off, &ctx->cursor,
                       &ctx->ucount, &ctx->uoff, &ctx->units, &ctx->counters, &ctx->blockhist, &ctx->tri, &ctx->rowupd,
                       &ctx->sp_cnt, &ctx->sp_counts, &ctx->sp_rowptr, &ctx->sp_col, &ctx->sp_val, &ctx->slot_off, &ctx->slots,
                       &ctx->q_off, &ctx->q_kmers, &ctx->q_keys, &ctx->q_keys2, &ctx->q_runkeys, &ctx->q_runcnt, &ctx->q_out})
         b->release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    if (ctx->up_stream) { cudaStreamSynchronize(ctx->up_stream); cudaStreamDestroy(ctx->up_stream); }
+    for (cudaEvent_t e : {ctx->ev_up_begin, ctx->ev_up_hdr, ctx->ev_up_payload}) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1320,25 +1394,31 @@ int kdbx_load_patterns(kdbx_ctx* ctx, const kdbx_trie_view* v) {
     ctx->prepared = false;
     CK(ctx->num_kmers.ensure(P * 8)); CK(ctx->parent.ensure(P * 8)); CK(ctx->n.ensure(P * 4)); CK(ctx->l.ensure(P * 4));
     CK(ctx->last.ensure(P * 4)); CK(ctx->bits.ensure(P * 4)); CK(ctx->payload.ensure((v->payload_words + 2) * 8));
-    ctx->ev_used = 0;
-    cudaEvent_t a = ctx->event();
-    CK(cudaMemcpyAsync(ctx->num_kmers.p, v->num_kmers, P * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->parent.p, v->parent_id, P * 8, cudaMemcpyHostToDevice, st));
+    // headers on the compute stream (the scans need them first), the Elias-gamma payload on a second
+    // stream: only the decode kernel waits for it (prepare())
+    CK(cudaStreamSynchronize(ctx->up_stream));
+    CK(cudaEventRecord(ctx->ev_up_begin, st));
     CK(cudaMemcpyAsync(ctx->n.p, v->num_samples_full, P * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->l.p, v->num_local_samples, P * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->last.p, v->last_sample_id, P * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->bits.p, v->num_bits, P * 4, cudaMemcpyHostToDevice, st));
-    if (v->payload_words) CK(cudaMemcpyAsync(ctx->payload.p, v->payload, v->payload_words * 8, cudaMemcpyHostToDevice, st));
-    // two zero guard words: the decoder may touch word i+1 of a run that ends at a word edge
-    CK(cudaMemsetAsync(ctx->payload.as<uint64_t>() + v->payload_words, 0, 16, st));
+    CK(cudaMemcpyAsync(ctx->parent.p, v->parent_id, P * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->num_kmers.p, v->num_kmers, P * 8, cudaMemcpyHostToDevice, st));
     ctx->dense_payload = (v->payload_off == nullptr);
     if (!ctx->dense_payload) {
         CK(ctx->poff.ensure((P + 1) * 8));
         CK(cudaMemcpyAsync(ctx->poff.p, v->payload_off, P * 8, cudaMemcpyHostToDevice, st));
     }
-    cudaEvent_t b = ctx->event();
-    CK(cudaStreamSynchronize(st));
-    ctx->ms_upload = elapsed(a, b);
+    CK(cudaEventRecord(ctx->ev_up_hdr, st));
+    CK(cudaStreamWaitEvent(ctx->up_stream, ctx->ev_up_begin, 0));  // not before earlier work on the buffers is done
+    if (v->payload_words) CK(cudaMemcpyAsync(ctx->payload.p, v->payload, v->payload_words * 8, cudaMemcpyHostToDevice, ctx->up_stream));
+    // two zero guard words: the decoder may touch word i+1 of a run that ends at a word edge
+    CK(cudaMemsetAsync(ctx->payload.as<uint64_t>() + v->payload_words, 0, 16, ctx->up_stream));
+    CK(cudaEventRecord(ctx->ev_up_payload, ctx->up_stream));
+    ctx->upload_pending = true;
+    if (!(ctx->cfg.flags & KDBX_FLAG_ASYNC_UPLOAD)) {
+        if (int rc = finish_upload(ctx)) return rc;
+    }
     ctx->P = P; ctx->N = v->num_samples; ctx->payload_words = v->payload_words;
     ctx->loaded = true;
     return KDBX_OK;

@@ -177,6 +177,7 @@ int new2all_impl(kdbx_ctx* ctx, const uint64_t* kmers, const uint64_t* q_off, ui
     cudaEvent_t ev2 = ctx->event();
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    if (int rc = finish_upload(ctx)) return rc;
     s.ms_prepare = elapsed(ev0, ev1);
     s.ms_probe = ms_probe; s.ms_scatter = ms_scatter; s.ms_download = ms_download;
     s.ms_total = elapsed(ev0, ev2);

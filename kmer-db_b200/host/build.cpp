@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <functional>
 #include <chrono>
 #include <cstdio>
 #include <thread>
@@ -135,51 +136,110 @@ uint32_t DbBuilder::add_sample(const std::string& name, const uint64_t* kmers, s
 
     const double t1 = now();
     // ---- group by pattern, then extend or split (src/prefix_kmer_db.cpp:181-240) ----------------------
-    {   // LSD radix sort of (pattern id << 32 | k-mer index): three 11-bit passes over the id bits in use
+    auto run_parallel = [&](int n, const std::function<void(int)>& fn) {
+        if (n <= 1) { fn(0); return; }
+        std::vector<std::thread> th;
+        std::exception_ptr err;
+        for (int t = 0; t < n; ++t) th.emplace_back([&, t] { try { fn(t); } catch (...) { err = std::current_exception(); } });
+        for (auto& x : th) x.join();
+        if (err) std::rethrow_exception(err);
+    };
+    const int TS = (int)std::min<size_t>((size_t)threads_, std::max<size_t>(1, count / 65536));
+    auto slice = [&](int t, int n) { return std::make_pair(count * (size_t)t / (size_t)n, count * (size_t)(t + 1) / (size_t)n); };
+    {   // LSD radix sort of (pattern id << 32 | k-mer index): 11-bit passes over the id bits in use,
+        // every thread histograms and scatters its own slice
         std::vector<uint64_t>& a = sort_a_;
         std::vector<uint64_t>& b = sort_b_;
         a.resize(count); b.resize(count);
+        std::vector<uint32_t> tmax((size_t)TS, 0);
+        run_parallel(TS, [&](int t) {
+            auto [lo, hi] = slice(t, TS);
+            uint32_t m = 0;
+            for (size_t i = lo; i < hi; ++i) {
+                const uint32_t pid = (uint32_t)sample_patterns_[i].first;
+                a[i] = ((uint64_t)pid << 32) | (uint32_t)i;
+                m = std::max(m, pid);
+            }
+            tmax[(size_t)t] = m;
+        });
         uint32_t max_pid = 0;
-        for (size_t i = 0; i < count; ++i) {
-            const uint32_t pid = (uint32_t)sample_patterns_[i].first;
-            a[i] = ((uint64_t)pid << 32) | (uint32_t)i;
-            max_pid = std::max(max_pid, pid);
-        }
+        for (uint32_t m : tmax) max_pid = std::max(max_pid, m);
+        std::vector<std::vector<size_t>> hist((size_t)TS, std::vector<size_t>(2048));
         for (int shift = 32; shift < 64 && (shift == 32 || (max_pid >> (shift - 32))); shift += 11) {
-            size_t hist[2049] = {0};
-            for (size_t i = 0; i < count; ++i) ++hist[((a[i] >> shift) & 2047) + 1];
-            for (int d = 0; d < 2048; ++d) hist[d + 1] += hist[d];
-            for (size_t i = 0; i < count; ++i) b[hist[(a[i] >> shift) & 2047]++] = a[i];
+            run_parallel(TS, [&](int t) {
+                auto [lo, hi] = slice(t, TS);
+                std::vector<size_t>& h = hist[(size_t)t];
+                std::fill(h.begin(), h.end(), 0);
+                for (size_t i = lo; i < hi; ++i) ++h[(a[i] >> shift) & 2047];
+            });
+            size_t run = 0;  // digit-major, thread-minor exclusive offsets keep the pass stable
+            for (int d = 0; d < 2048; ++d)
+                for (int t = 0; t < TS; ++t) { const size_t c = hist[(size_t)t][(size_t)d]; hist[(size_t)t][(size_t)d] = run; run += c; }
+            run_parallel(TS, [&](int t) {
+                auto [lo, hi] = slice(t, TS);
+                std::vector<size_t>& h = hist[(size_t)t];
+                for (size_t i = lo; i < hi; ++i) b[h[(a[i] >> shift) & 2047]++] = a[i];
+            });
             a.swap(b);
         }
         sorted_.resize(count);
-        for (size_t i = 0; i < count; ++i) sorted_[i] = sample_patterns_[(uint32_t)a[i]];
+        run_parallel(TS, [&](int t) {
+            auto [lo, hi] = slice(t, TS);
+            for (size_t i = lo; i < hi; ++i) sorted_[i] = sample_patterns_[(uint32_t)a[i]];
+        });
         sorted_.swap(sample_patterns_);
     }
     const double t2 = now();
-    for (size_t i = 0; i < count;) {
-        const int32_t pid = sample_patterns_[i].first;
-        size_t j = i + 1;
-        while (j < count && sample_patterns_[j].first == pid) ++j;
-        const int64_t c = (int64_t)(j - i);
-        Pattern& q = pats_[(size_t)pid];
-        if (q.num_kmers == c && !q.is_parent) {
-            append_sample(q, sample);
-        } else {
-            Pattern child;
-            child.num_kmers = c;
-            child.n = q.n + 1; child.l = 1; child.last = sample;
-            if (q.n > 0) { q.is_parent = true; child.parent = pid; }  // children of pattern 0 are roots
-            if (pid) q.num_kmers -= c;
-            const uint64_t new_pid = pats_.size();
-            if (new_pid >= 0x7FFFFFFFull) throw std::runtime_error("too many patterns");
-            pats_.push_back(child);   // NB: invalidates q
-            for (size_t x = i; x < j; ++x) {
-                uint64_t* slot = sample_patterns_[x].second;
-                *slot = (*slot & 0xFFFFFFFFull) | (new_pid << 32);
-            }
+    {   // groups of equal pattern id are independent: threads take group-aligned slices, first decide
+        // extend-or-split and count the new patterns, then (after one resize) create them
+        std::vector<size_t> gcut((size_t)TS + 1, count);
+        gcut[0] = 0;
+        for (int t = 1; t < TS; ++t) {
+            size_t c = std::max(gcut[(size_t)t - 1], slice(t, TS).first);
+            while (c < count && c > 0 && sample_patterns_[c].first == sample_patterns_[c - 1].first) ++c;
+            gcut[(size_t)t] = c;
         }
-        i = j;
+        std::vector<uint64_t> new_count((size_t)TS, 0);
+        auto for_groups = [&](int t, auto&& fn) {
+            for (size_t i = gcut[(size_t)t]; i < gcut[(size_t)t + 1];) {
+                const int32_t pid = sample_patterns_[i].first;
+                size_t j = i + 1;
+                while (j < count && sample_patterns_[j].first == pid) ++j;
+                fn(pid, i, j);
+                i = j;
+            }
+        };
+        run_parallel(TS, [&](int t) {
+            uint64_t n = 0;
+            for_groups(t, [&](int32_t pid, size_t i, size_t j) {
+                const Pattern& q = pats_[(size_t)pid];
+                if (!(q.num_kmers == (int64_t)(j - i) && !q.is_parent)) ++n;
+            });
+            new_count[(size_t)t] = n;
+        });
+        uint64_t next = pats_.size();
+        std::vector<uint64_t> first_new((size_t)TS, 0);
+        for (int t = 0; t < TS; ++t) { first_new[(size_t)t] = next; next += new_count[(size_t)t]; }
+        if (next >= 0x7FFFFFFFull) throw std::runtime_error("too many patterns");
+        pats_.resize(next);
+        run_parallel(TS, [&](int t) {
+            uint64_t new_pid = first_new[(size_t)t];
+            for_groups(t, [&](int32_t pid, size_t i, size_t j) {
+                const int64_t c = (int64_t)(j - i);
+                Pattern& q = pats_[(size_t)pid];
+                if (q.num_kmers == c && !q.is_parent) { append_sample(q, sample); return; }
+                Pattern& child = pats_[new_pid];
+                child.num_kmers = c;
+                child.n = q.n + 1; child.l = 1; child.last = sample;
+                if (q.n > 0) { q.is_parent = true; child.parent = pid; }  // children of pattern 0 are roots
+                if (pid) q.num_kmers -= c;
+                for (size_t x = i; x < j; ++x) {
+                    uint64_t* slot = sample_patterns_[x].second;
+                    *slot = (*slot & 0xFFFFFFFFull) | (new_pid << 32);
+                }
+                ++new_pid;
+            });
+        });
     }
     if (trace) {
         t_tab += t1 - t0; t_sort += t2 - t1; t_pat += now() - t2;

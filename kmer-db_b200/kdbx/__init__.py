@@ -70,6 +70,7 @@ class TablesView(C.Structure):
 
 METRICS = {"jaccard": 0, "min": 1, "max": 2, "cosine": 3}
 FLAG_CHUNKED_LISTS = 1
+FLAG_ASYNC_UPLOAD = 2
 
 
 class SynthParams(C.Structure):
