@@ -20,11 +20,18 @@ reference's dense path.
            measured HBM copy bandwidth in MEASURED_PEAKS.json.
   cpu_baseline  the reference binary (oracle/_ref/kmer-db all2all -t <all cores>) on a bounded sample:
            the first cluster (250 genomes x 5 Mbp = exactly a quarter of the workload's updates).
-With N>1 (torchrun, one rank per GPU) total work is fixed => "strong" scaling.  Default sharding: every rank
-holds the whole trie, executes the pattern chunks c with c % N == rank into a partial matrix, and ONE NCCL
-all-reduce (uint32 sum over NVLink) adds the partial matrices — the exchange step BASELINE.json's north_star
-names.  `--shard rows` instead gives every rank a contiguous block of matrix rows balanced on per-row update
-counts (no collective, but the decode/expand/bucketing stages are then replicated on every rank).
+With N>1 (torchrun, one rank per GPU) the database is SHARDED: every rank holds, uploads and processes only its
+own sub-trie (kdbxh_partition: a piece of the trie's depth-first preorder plus the ancestors of that piece with
+num_kmers = 0; the matrix is linear in num_kmers, so the parts' matrices add up), runs the complete single-GPU
+pipeline on it into a partial matrix, and ONE NCCL all-reduce (uint32 sum over NVLink) adds the partial matrices —
+the exchange step BASELINE.json's north_star names.  Nothing is replicated but the few ancestor chains.
+  --scaling weak  (default)  per-GPU work fixed: N GPUs process a database of N x 1000 genomes (4N clusters, the
+                  shape of BASELINE.json configs[2]); rank r's shard is the configs[1] database laid onto the sample
+                  ids [1000 r, 1000 (r+1)) (kdbxh_relabel) — what the partitioner yields for a database whose clusters
+                  are disjoint subtrees.  U = N x U(configs[1]); the matrix is (1000 N)^2 / 2 cells.
+  --scaling strong           total work fixed: the configs[1] database is cut into N parts by kdbxh_partition
+                  (host, untimed: it is the layout of the sharded database); rank 0 also computes the unsharded
+                  matrix once and the all-reduced result must equal it bit for bit.
 """
 import argparse
 import json
@@ -60,9 +67,9 @@ def parse_args():
     ap.add_argument("--tile-rows", type=int, default=0)
     ap.add_argument("--scatter-threads", type=int, default=0)
     ap.add_argument("--chunked-lists", action="store_true", help="force the chunked parent-chain expansion")
-    ap.add_argument("--shard", choices=["patterns", "rows"], default="patterns",
-                    help="N>1: 'patterns' = every rank runs its share of pattern chunks into a partial matrix, one NCCL "
-                         "all-reduce adds them; 'rows' = contiguous row blocks balanced on per-row updates, no collective")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="N>1: 'weak' = every rank owns a configs[1]-sized shard of an N-times larger database; "
+                         "'strong' = the configs[1] database cut into N sub-tries; both end in one NCCL all-reduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cache-dir", default=os.environ.get("KDBX_CACHE", "/tmp/kdbx_cache"))
@@ -208,7 +215,7 @@ def main():
         print(json.dumps({
             "impl": "reference", "metric": "k-mer-pair updates/sec on all2all", "value": v, "unit": "updates/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(a), "sample": sample, "threads": cores},
             "cpu_baseline": {"value": v, "unit": "updates/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -251,34 +258,46 @@ def main():
 
     trie, db_path = get_workload(kdbx, a, a.samples, a.clusters, pinned=True, rank=rank, barrier=barrier if world > 1 else None)
     tot = trie.totals()
-    N, P, U_total = int(tot.num_samples), int(tot.num_patterns), int(tot.updates)
-    by_patterns = world > 1 and a.shard == "patterns"
+    N0, P0, U0 = int(tot.num_samples), int(tot.num_patterns), int(tot.updates)
     chunk_ids = a.chunk_ids
-    if by_patterns and chunk_ids == 0:
-        chunk_ids = max(1 << 22, (64 << 20) // world)  # finer chunks: ~62 per rank, balanced round-robin
     ctx = kdbx.Context(device=local_rank, chunk_ids=chunk_ids, tile_cols=a.tile_cols, unit_updates=a.unit_updates,
                        tile_rows=a.tile_rows, scatter_threads=a.scatter_threads, flags=(kdbx.FLAG_CHUNKED_LISTS if a.chunked_lists else 0) | kdbx.FLAG_ASYNC_UPLOAD)
-    ctx.load_patterns(trie)
-    if by_patterns:
-        r0, r1 = 0, N
+    scaling = a.scaling
+    full_ref = None
+    t_shard = 0.0
+    if world == 1:
+        N, U_total = N0, U0
+    elif scaling == "weak":
+        t0 = time.perf_counter()
+        trie.relabel(rank * N0, N0 * world)   # this rank's shard of the N0*world-sample database
+        t_shard = time.perf_counter() - t0
+        N, U_total = N0 * world, U0 * world
     else:
-        upd = ctx.row_updates()
-        assert int(upd.sum()) == U_total, "device row-update counts disagree with U of the trie"
-        bounds = kdbx.shard_rows_by_work(upd, world)
-        r0, r1 = bounds[rank], bounds[rank + 1]
-    cells = kdbx.tri_cells(r1) - kdbx.tri_cells(r0)
+        if rank == 0:  # the unsharded matrix, once, as the bit-exact check of the sharded path
+            ctx.load_patterns(trie)
+            full_ref = torch.zeros(max(1, kdbx.tri_cells(N0)), dtype=torch.int32, device="cuda")
+            ctx.all2all_dense_rows_device(0, N0, full_ref.data_ptr())
+        t0 = time.perf_counter()
+        part, _owned = trie.partition(world, rank, pinned=True)
+        t_shard = time.perf_counter() - t0
+        trie.close()
+        trie = part
+        N, U_total = N0, U0
+    tot = trie.totals()
+    P = int(tot.num_patterns)
+    ctx.load_patterns(trie)
+    r0, r1 = 0, N
+    cells = kdbx.tri_cells(N)
     d_out = torch.zeros(max(1, cells), dtype=torch.int32, device="cuda")
 
     def step():
-        """One all2all over the resident trie; returns the library's stats."""
-        if by_patterns:
-            st = ctx.all2all_dense_part_device(rank, world, d_out.data_ptr())
+        """One all2all over this rank's resident (sub-)trie (+ the all-reduce); returns the library's stats."""
+        st = ctx.all2all_dense_rows_device(r0, r1, d_out.data_ptr())
+        if dist is not None:
             dist.all_reduce(d_out)  # uint32 sums wrap like int32 sums: same bits
             # the library works on its own stream: the next step must not start (and zero d_out)
             # while this all-reduce is still in flight on NCCL's stream
             torch.cuda.current_stream().synchronize()
-        else:
-            st = ctx.all2all_dense_rows_device(r0, r1, d_out.data_ptr())
         return st
 
     def total_updates(st_updates):
@@ -292,8 +311,21 @@ def main():
     st = step()  # one untimed call establishes this rank's share of U (and warms the allocator)
     for _ in range(max(0, a.warmup - 1)):
         st = step()
-    assert total_updates(int(st.updates)) == U_total, "updates executed by all ranks != U of the trie"
     U_rank = int(st.updates)
+    assert U_rank == int(tot.updates), "updates executed on this rank != U of its (sub-)trie"
+    U_exec = total_updates(U_rank)
+    # sharding replicates only ancestor chains (num_kmers = 0 there, but their rows are still visited)
+    assert U_total <= U_exec <= U_total * 1.001, "updates executed by all ranks != U of the database"
+    if full_ref is not None:
+        assert torch.equal(d_out[:cells], full_ref[:cells]), "all-reduced matrix of the sharded run != unsharded matrix"
+        full_ref = None
+    if dist is not None and scaling == "weak":
+        # ranks own disjoint diagonal blocks: this rank's block must hold exactly its own partial result
+        mine = torch.zeros_like(d_out)
+        ctx.all2all_dense_rows_device(r0, r1, mine.data_ptr())
+        lo, hi = kdbx.tri_cells(rank * N0), kdbx.tri_cells((rank + 1) * N0)
+        assert torch.equal(mine[lo:hi], d_out[lo:hi]) and int(mine.to(torch.int64).sum().item()) == int(mine[lo:hi].to(torch.int64).sum().item())
+        del mine
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     wall0 = time.perf_counter()
@@ -331,7 +363,7 @@ def main():
 
         def e2e_step():
             ctx.load_patterns(trie)
-            if by_patterns:
+            if dist is not None:
                 st2 = step()
                 out_t.copy_(d_out, non_blocking=False)
             else:
@@ -346,9 +378,9 @@ def main():
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         barrier()
         assert int(out_host[:cells].astype(np.int64).sum()) == checksum, "e2e result differs from the device-resident result"
-        h2d = P * 40 + int(tot.payload_bytes)
+        h2d = total_updates(P * 40 + int(tot.payload_bytes))  # summed over the ranks (every rank copies its own shard)
         e2e = {"value": U_total * a.steps / e2e_s, "unit": "updates/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": cells * 4, "ms_per_step": 1e3 * e2e_s / a.steps,
+               "d2h_bytes_per_step": cells * 4 * world, "ms_per_step": 1e3 * e2e_s / a.steps,
                "ms_upload": st2.ms_upload, "ms_download": st2.ms_download}
 
     if rank != 0:
@@ -380,10 +412,16 @@ def main():
     print(json.dumps({
         "metric": "k-mer-pair updates/sec on all2all", "value": value, "unit": "updates/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": T_ms / a.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "num_samples": N, "num_patterns": P, "updates_per_step": U_total,
-                   "sum_n": int(tot.sum_n), "sum_l": int(tot.sum_l), "parallelism": (f"pattern chunks round-robin x{world} + one NCCL all-reduce of the matrix" if by_patterns
-                                   else f"row-block x{world}, no collective"),
+        "scaling": scaling, "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": workload_name(a) + ("" if world == 1 else
+                               f"; x{world} shards laid side by side = {N} genomes ({a.clusters * world} clusters)" if scaling == "weak"
+                               else f"; cut into {world} sub-tries"),
+                   "num_samples": N, "num_patterns": P if world == 1 else None, "patterns_on_rank0": P, "updates_per_step": U_total,
+                   "sum_n": int(tot.sum_n), "sum_l": int(tot.sum_l),
+                   "parallelism": ("1 GPU, no collective" if world == 1 else
+                                   f"trie sharded into {world} sub-tries (preorder pieces + ancestor chains), one per GPU, "
+                                   f"+ one NCCL all-reduce of the {cells * 4 / 1e6:.0f} MB matrix per step"),
+                   "shard_seconds_host": t_shard,
                    "l2_policy": "inputs (trie %.1f GB + per-chunk lists) exceed the 126 MB L2; no explicit flush" %
                                 ((P * 40 + int(tot.payload_bytes)) / 1e9),
                    "chunk_ids": chunk_ids, "tile_cols": a.tile_cols, "unit_updates": a.unit_updates,

@@ -66,6 +66,17 @@ int kdbxh_validate(const kdbxh_trie* t);
  * Used to cut a bounded sample of a workload for the CPU baseline. */
 int kdbxh_prefix(const kdbxh_trie* src, uint32_t num_samples, kdbxh_trie* dst);
 
+/* Sharding for multi-GPU runs (ours; the reference is single-process).  dst := part `part` of
+ * `num_parts`: a valid database over the same samples that holds a contiguous piece of the trie's
+ * depth-first preorder (balanced on the GPU pipeline's cost model) plus the ancestors of that piece
+ * with num_kmers = 0.  The shared-k-mer matrix is linear in num_kmers, so the matrices of the parts
+ * sum (uint32, wrapping) to the matrix of src: one GPU per part + one NCCL all-reduce.
+ * owned_updates (may be NULL) receives U of the patterns the part owns. */
+int kdbxh_partition(const kdbxh_trie* src, uint32_t num_parts, uint32_t part, kdbxh_trie* dst, uint64_t* owned_updates);
+/* Shifts every sample id of t by `offset` inside a sample table of `new_total` entries (the other
+ * entries are empty samples); the trie keeps its shape.  Lays shards of a workload side by side. */
+int kdbxh_relabel(kdbxh_trie* t, uint32_t offset, uint32_t new_total);
+
 int kdbxh_view(const kdbxh_trie* t, kdbx_trie_view* out);
 int kdbxh_totals_of(const kdbxh_trie* t, kdbxh_totals* out);
 /* name of sample i (NUL-terminated, owned by the trie) and its total-kmers count */

@@ -197,6 +197,14 @@ int kdbxh_prefix(const kdbxh_trie* src, uint32_t num_samples, kdbxh_trie* dst) {
     if (!src || !dst || src == dst) { g_err = "bad argument"; return -1; }
     return guarded([&] { kdbx::prefix_trie(src->t, num_samples, dst->t); });
 }
+int kdbxh_partition(const kdbxh_trie* src, uint32_t num_parts, uint32_t part, kdbxh_trie* dst, uint64_t* owned_updates) {
+    if (!src || !dst || src == dst) { g_err = "bad argument"; return -1; }
+    return guarded([&] { dst->flat_off.clear(); dst->flat_slots.clear(); kdbx::partition_trie(src->t, num_parts, part, dst->t, owned_updates); });
+}
+int kdbxh_relabel(kdbxh_trie* t, uint32_t offset, uint32_t new_total) {
+    if (!t) { g_err = "null argument"; return -1; }
+    return guarded([&] { t->flat_off.clear(); t->flat_slots.clear(); kdbx::relabel_samples(t->t, offset, new_total); });
+}
 int kdbxh_view(const kdbxh_trie* t, kdbx_trie_view* out) {
     if (!t || !out) { g_err = "null argument"; return -1; }
     *out = t->t.view();

@@ -211,5 +211,13 @@ void read_db(const std::string& path, Trie& out, bool with_tables = false);
 // writes t.tables when present, otherwise hdr.num_hashtables EMPTY raw hashtables
 void write_db(const std::string& path, const Trie& t);
 
+// partition.cpp — sharding the trie across GPUs: part `part` of `num_parts` as a valid trie of its own
+// (owned patterns = a piece of the depth-first preorder, plus their ancestors with num_kmers = 0); the
+// parts' all2all matrices add up to the whole database's.
+std::vector<uint32_t> trie_preorder(const Trie& t);
+void partition_trie(const Trie& src, uint32_t num_parts, uint32_t part, Trie& dst, uint64_t* owned_updates = nullptr);
+// shifts all sample ids by `offset` inside a sample table of `new_total` entries
+void relabel_samples(Trie& t, uint32_t offset, uint32_t new_total);
+
 
 }  // namespace kdbx

@@ -91,7 +91,7 @@ KDBX_SYMBOLS = ["kdbx_abi_version", "kdbx_device_count", "kdbx_open", "kdbx_clos
                 "kdbx_all2all_dense_rows", "kdbx_all2all_dense_rows_device", "kdbx_all2all_dense_part_device", "kdbx_all2all_sparse", "kdbx_free_csr",
                 "kdbx_load_hashtables", "kdbx_new2all_batch", "kdbx_debug_fetch"]
 KDBXH_SYMBOLS = ["kdbxh_last_error", "kdbxh_trie_new", "kdbxh_trie_free", "kdbxh_read_db", "kdbxh_write_db",
-                 "kdbxh_synth", "kdbxh_validate", "kdbxh_prefix", "kdbxh_view", "kdbxh_totals_of", "kdbxh_sample_name",
+                 "kdbxh_synth", "kdbxh_validate", "kdbxh_prefix", "kdbxh_partition", "kdbxh_relabel", "kdbxh_view", "kdbxh_totals_of", "kdbxh_sample_name",
                  "kdbxh_sample_kmers", "kdbxh_write_all2all_csv", "kdbxh_read_db_full", "kdbxh_tables_view",
                  "kdbxh_builder_new", "kdbxh_builder_free", "kdbxh_builder_add_sample", "kdbxh_builder_finish",
                  "kdbxh_samples_load", "kdbxh_samples_free", "kdbxh_samples_count", "kdbxh_samples_name", "kdbxh_samples_kmers"]
@@ -144,6 +144,8 @@ def load():
     h.kdbxh_synth.argtypes = [C.c_void_p, P(SynthParams)]
     h.kdbxh_validate.argtypes = [C.c_void_p]
     h.kdbxh_prefix.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    h.kdbxh_partition.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, P(C.c_uint64)]
+    h.kdbxh_relabel.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
     h.kdbxh_view.argtypes = [C.c_void_p, P(TrieView)]
     h.kdbxh_totals_of.argtypes = [C.c_void_p, P(Totals)]
     h.kdbxh_sample_name.argtypes = [C.c_void_p, C.c_uint32]
@@ -259,6 +261,17 @@ class Trie:
         t = Trie(pinned)
         self._check(self._h.kdbxh_prefix(self._p, num_samples, t._p))
         return t
+
+    def partition(self, num_parts, part, pinned=False):
+        """(sub-database of part `part`, U of the patterns it owns): see kdbxh_partition."""
+        t = Trie(pinned)
+        u = C.c_uint64()
+        self._check(self._h.kdbxh_partition(self._p, num_parts, part, t._p, C.byref(u)))
+        return t, int(u.value)
+
+    def relabel(self, offset, new_total):
+        """Shift all sample ids by `offset` inside a table of `new_total` samples (in place)."""
+        self._check(self._h.kdbxh_relabel(self._p, offset, new_total))
 
     def write_db(self, path):
         self._check(self._h.kdbxh_write_db(self._p, os.fsencode(str(path))))

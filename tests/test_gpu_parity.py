@@ -214,6 +214,37 @@ def test_pattern_parts_sum_to_full_matrix(libs, oracle, flags):
             c.all2all_dense_part_device(3, 3, buf.data_ptr())
 
 
+@pytest.mark.parametrize("parts", [2, 3, 8])
+def test_sub_tries_sum_to_full_matrix(libs, oracle, parts):
+    """The multi-GPU sharding of bench.py on one device: every sub-trie of kdbxh_partition runs through the
+    whole pipeline; the partial matrices add up (uint32) to the oracle's matrix of the whole database.
+    The relabelled shard (weak scaling) fills exactly its diagonal block of the larger matrix."""
+    t = libs.Trie.synth(num_samples=300, num_clusters=3, genome_kmers=40000, seed=6)
+    N = t.num_samples
+    want, U = ou.oracle_all2all(oracle, N, t.arrays())
+    acc = np.zeros_like(want)
+    owned_total = 0
+    with libs.Context(device=0) as c:
+        for r in range(parts):
+            sub, owned = t.partition(parts, r)
+            c.load_patterns(sub)
+            tri, st = c.all2all_dense()
+            assert st.updates == sub.totals().updates
+            acc += tri
+            owned_total += owned
+        assert owned_total == U and np.array_equal(acc, want)
+        off, total = 300 * (parts - 1), 300 * parts
+        t.relabel(off, total)
+        c.load_patterns(t)
+        big, st = c.all2all_dense()
+        assert st.updates == U
+        for s in (1, 2, 150, 299):
+            o = ou.tri_cells(s + off)
+            assert np.array_equal(big[o + off:o + off + s], want[ou.tri_cells(s):ou.tri_cells(s) + s])
+            assert not big[o:o + off].any()
+        assert int(big.astype(np.int64).sum()) == int(want.astype(np.int64).sum())
+
+
 def test_generated_db_matches_reference_binary(libs, ref_bin, tmp_path):
     """Same .db through the unmodified reference (all host cores) and through the GPU path: cmp."""
     if ref_bin is None:

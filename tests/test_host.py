@@ -149,3 +149,63 @@ def test_prefix_cuts_a_cluster_exactly(libs, oracle):
     ti = libs.Trie.synth(num_samples=60, num_clusters=3, genome_kmers=15000, seed=4, interleaved=True)
     with pytest.raises(libs.KdbxError, match="prefix"):
         ti.prefix(20)
+
+
+@pytest.mark.parametrize("source", ["synth", "synth-interleaved", "virus.k18", "synth.k21"])
+@pytest.mark.parametrize("parts", [1, 2, 3, 7])
+def test_partition_parts_sum_to_the_whole_matrix(libs, oracle, golden_dbs, source, parts):
+    """Sharding for multi-GPU runs: every part is a valid trie, the parts own disjoint patterns that
+    cover the trie, and their matrices add up (uint32) to the matrix of the whole database."""
+    if source.startswith("synth") and "." not in source:
+        t = libs.Trie.synth(num_samples=48, num_clusters=3, genome_kmers=12000, seed=9, interleaved=source.endswith("interleaved"))
+    else:
+        t = libs.Trie.read_db(golden_dbs[source][0])
+    N = t.num_samples
+    a = t.arrays()
+    full, U = ou.oracle_all2all(oracle, N, a)
+    acc = np.zeros_like(full)
+    owned_u, owned_patterns, kmers = 0, 0, 0
+    costs = []
+    for r in range(parts):
+        sub, u = t.partition(parts, r)
+        sub.validate()
+        assert sub.num_samples == N and sub.sample_names() == t.sample_names()
+        b = sub.arrays()
+        tri, _ = ou.oracle_all2all(oracle, N, b)
+        acc += tri  # uint32, wraps like the device all-reduce
+        owned_u += u
+        owned_patterns += int((b["num_kmers"] != 0).sum())
+        kmers += int(b["num_kmers"].sum())
+        costs.append(int((b["l"].astype(np.int64) * (2 * b["n"].astype(np.int64) - b["l"] - 1) // 2 + 34 * b["n"].astype(np.int64) + 200).sum()))
+    assert np.array_equal(acc, full)
+    assert owned_u == U
+    assert kmers == int(a["num_kmers"].sum())
+    assert owned_patterns == int((a["num_kmers"] != 0).sum())
+    if parts > 1 and len(a["n"]) > 2000:  # balanced on the cost model (one pattern of slack + the replicated chain)
+        assert max(costs) <= 1.25 * (sum(costs) / parts)
+
+
+def test_partition_rejects_bad_arguments(libs):
+    t = libs.Trie.synth(num_samples=8, num_clusters=2, genome_kmers=500, seed=1)
+    with pytest.raises(libs.KdbxError, match="partition"):
+        t.partition(0, 0)
+    with pytest.raises(libs.KdbxError, match="partition"):
+        t.partition(2, 2)
+
+
+def test_relabel_moves_the_matrix_block(libs, oracle):
+    t = libs.Trie.synth(num_samples=20, num_clusters=2, genome_kmers=3000, seed=5)
+    base, U = ou.oracle_all2all(oracle, 20, t.arrays())
+    t.relabel(30, 64)
+    t.validate()
+    assert t.num_samples == 64 and t.totals().updates == U
+    moved, U2 = ou.oracle_all2all(oracle, 64, t.arrays())
+    assert U2 == U
+    want = np.zeros(ou.tri_cells(64), np.uint32)
+    for s in range(1, 20):
+        src = base[ou.tri_cells(s):ou.tri_cells(s) + s]
+        o = ou.tri_cells(s + 30) + 30
+        want[o:o + s] = src
+    assert np.array_equal(moved, want)
+    with pytest.raises(libs.KdbxError, match="relabel"):
+        t.relabel(1, 64)

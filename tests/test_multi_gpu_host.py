@@ -1,6 +1,6 @@
 """Host-side logic of the N>1 paths on CPU: two `gloo` ranks shard the work the way bench.py does
-(pattern chunks round-robin + one all-reduce of uint32 partial matrices; row blocks balanced on
-per-row updates + gather), with the ORACLE standing in for the device kernels."""
+(sub-tries from kdbxh_partition / relabelled shards + one all-reduce of uint32 partial matrices, as
+bench.py does; also pattern chunks round-robin + all-reduce and row blocks balanced on per-row updates + gather), with the ORACLE standing in for the device kernels."""
 import os
 import socket
 import sys
@@ -75,7 +75,30 @@ def _worker(rank, world, port, q):
         tt = torch.tensor([float(rank + 1)], dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ok4 = tt.item() == float(world)
-        q.put((rank, ok1, ok2, ok3, ok4))
+        # (3) what bench.py does: the trie is cut into one sub-trie per rank (kdbxh_partition), each rank runs the
+        # whole pipeline on its own part (here: the oracle) and one all-reduce adds the partial matrices
+        t = kdbx.Trie.synth(num_samples=64, num_clusters=4, genome_kmers=8000, seed=11)
+        whole, U3 = ou.oracle_all2all(oracle, 64, t.arrays())
+        sub, owned = t.partition(world, rank)
+        mine3, u3 = ou.oracle_all2all(oracle, 64, sub.arrays())
+        t3 = torch.from_numpy(mine3.view(np.int32).copy())
+        dist.all_reduce(t3)
+        ut3 = torch.tensor([owned, u3], dtype=torch.int64)
+        dist.all_reduce(ut3)
+        ok5 = bool(np.array_equal(t3.numpy().view(np.uint32), whole)) and int(ut3[0]) == U3 and U3 <= int(ut3[1]) <= 1.05 * U3
+        # (4) weak scaling: every rank lays its own copy of the database onto its own sample ids (kdbxh_relabel)
+        t.relabel(rank * 64, world * 64)
+        mine4, u4 = ou.oracle_all2all(oracle, world * 64, t.arrays())
+        t4 = torch.from_numpy(mine4.view(np.int32).copy())
+        dist.all_reduce(t4)
+        got4 = t4.numpy().view(np.uint32)
+        ok6 = u4 == U3
+        for r in range(world):  # block r of the big matrix is the small matrix; everything else is zero
+            for srow in range(1, 64):
+                o = ou.tri_cells(srow + r * 64)
+                ok6 = ok6 and bool(np.array_equal(got4[o + r * 64:o + r * 64 + srow], whole[ou.tri_cells(srow):ou.tri_cells(srow) + srow]))
+                ok6 = ok6 and not got4[o:o + r * 64].any()
+        q.put((rank, ok1, ok2, ok3, ok4, ok5, ok6))
     finally:
         dist.destroy_process_group()
 
@@ -92,8 +115,10 @@ def test_two_rank_sharding_over_gloo(libs, oracle, world):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, ok1, ok2, ok3, ok4 in sorted(res):
+    for rank, ok1, ok2, ok3, ok4, ok5, ok6 in sorted(res):
         assert ok1, f"rank {rank}: all-reduced partial matrices differ from the full matrix"
         assert ok2, f"rank {rank}: gathered row blocks differ from the full matrix"
         assert ok3, f"rank {rank}: row shares are unbalanced"
         assert ok4
+        assert ok5, f"rank {rank}: all-reduced matrices of the sub-tries differ from the matrix of the whole trie"
+        assert ok6, f"rank {rank}: relabelled shards do not form the block-diagonal matrix"
