@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define KDBX_ABI_VERSION 2
+#define KDBX_ABI_VERSION 3
 
 enum {
     KDBX_OK = 0,
@@ -245,6 +245,75 @@ int kdbx_new2all_batch(kdbx_ctx* ctx, const uint64_t* kmers, const uint64_t* q_o
  * 302-327. */
 int kdbx_all2all_dense_part_device(kdbx_ctx* ctx, uint32_t part, uint32_t num_parts, void* d_out_tri,
                                    kdbx_stats* stats);
+
+/* ---- build: database construction on the device --------------------------------------------- */
+
+/* Replaces, per sample, what BuildConsole::run drives on host threads (src/console_build.cpp:91-118):
+ * KmerHelper::extract + MinHashFilter (src/kmer_extract.h:13-97, src/filter.h:40-115), sort + unique of
+ * the sample's k-mers (src/kmer_extract.h:101-119), and PrefixKmerDb::addKmers (src/prefix_kmer_db.cpp:
+ * 244-434): prefix histogram / hashtable find-or-insert (:67-178) and the pattern extend-or-split
+ * (:181-240).  Semantics: SURVEY.md §A.4.  New pattern ids are handed out in ascending order of the
+ * pattern they split from (the reference's order within one sample depends on its thread timing, :219). */
+typedef struct kdbx_builder kdbx_builder;
+
+typedef struct kdbx_build_params {
+    uint32_t kmer_length;        /* -k                                                            */
+    uint32_t bits_per_symbol;    /* Alphabet::bitsPerSymbol (src/alphabet.h:32-58)                */
+    uint32_t alphabet_size;      /* symbols; the complement of symbol s is size-1-s               */
+    uint32_t preserve_strand;    /* non-zero: no canonical form (-preserve-strand, amino acids)   */
+    double fraction;             /* -f: minhash fraction, >= 1 keeps every k-mer                  */
+    double fraction_start;       /* -f-start                                                      */
+    int8_t symbol_map[256];      /* byte -> symbol, < 0 = not in the alphabet                     */
+    uint64_t table_capacity_hint;/* expected number of distinct k-mers; 0 = grow on demand        */
+} kdbx_build_params;
+
+typedef struct kdbx_build_result {
+    uint64_t num_patterns;       /* trie nodes, sentinel included                                 */
+    uint64_t payload_words;      /* 64-bit words of Elias-gamma payload                           */
+    uint64_t num_tables;         /* 2^max(8, k*bits - 32)                                         */
+    uint64_t total_slots;        /* slots of all raw prefix tables                                */
+    uint64_t kmers_count;        /* distinct k-mers in the database                               */
+    uint64_t sum_local_samples;  /* sum of num_local_samples                                      */
+    uint64_t table_capacity;     /* slots of the device-side k-mer table                          */
+    uint32_t num_samples;
+    uint32_t kernel_launches;
+    uint32_t table_growths;
+    float ms_finish;             /* gamma coding + table export on the device                     */
+    uint64_t reserved[2];
+} kdbx_build_result;
+
+/* Caller-owned HOST arrays kdbx_builder_export fills (sizes from kdbx_build_result; NULL = skip):
+ * the trie in the layout of kdbx_trie_view and the k-mer tables in the layout of kdbx_tables_view,
+ * i.e. exactly what PrefixKmerDb::serialize writes (src/prefix_kmer_db.cpp:438-574). */
+typedef struct kdbx_build_arrays {
+    int64_t* num_kmers;           /* [num_patterns]      */
+    int64_t* parent_id;           /* [num_patterns]      */
+    uint32_t* num_samples_full;   /* [num_patterns]      */
+    uint32_t* num_local_samples;  /* [num_patterns]      */
+    uint32_t* last_sample_id;     /* [num_patterns]      */
+    uint32_t* num_bits;           /* [num_patterns]      */
+    uint64_t* payload_off;        /* [num_patterns]      */
+    uint64_t* payload;            /* [payload_words]     */
+    uint64_t* slot_off;           /* [num_tables + 1]    */
+    uint64_t* slots;              /* [total_slots]       */
+    uint64_t* table_filled;       /* [num_tables]        */
+} kdbx_build_arrays;
+
+int kdbx_builder_open(kdbx_ctx* ctx, const kdbx_build_params* params, kdbx_builder** out);
+void kdbx_builder_close(kdbx_builder* b);
+/* `build -extend` (src/console_build.cpp:48-57): continue the database staged on the context with
+ * kdbx_load_patterns + kdbx_load_hashtables.  Must precede the first sample. */
+int kdbx_builder_adopt(kdbx_builder* b);
+/* One sample from its sequence: `symbols` are the sample's records back to back, separated by any
+ * byte outside the alphabet (k-mers never span records).  unique_kmers (may be NULL) receives the
+ * sample's "total-kmers" (src/kmer_db.h:127-129).  Samples get consecutive ids in call order. */
+int kdbx_builder_add_sequence(kdbx_builder* b, const char* symbols, uint64_t len, uint64_t* unique_kmers);
+/* One sample from k-mers that are already canonical, shifted, filtered, ascending and unique. */
+int kdbx_builder_add_kmers(kdbx_builder* b, const uint64_t* kmers, uint64_t count);
+/* Elias-gamma coding of the local sample lists and conversion of the k-mer table into the
+ * reference's prefix-bucketed raw tables, on the device; reports the sizes to allocate. */
+int kdbx_builder_finish(kdbx_builder* b, kdbx_build_result* out);
+int kdbx_builder_export(kdbx_builder* b, const kdbx_build_arrays* arrays);
 
 /* Debug / test taps (not used by the product path): copy intermediate device arrays of the
  * last compute call to the host.  what: 0 = W (uint32[P]), 1 = decoded local ids

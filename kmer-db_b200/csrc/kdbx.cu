@@ -34,6 +34,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_run_length_encode.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
@@ -1294,7 +1295,41 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
 
 #include "sparse.cuh"
 #include "query.cuh"
+#include "build.cuh"
 
+}  // namespace
+
+// Device-side database builder (build.cuh / build_host.cuh); lives on a context's device and stream.
+struct kdbx_builder {
+    kdbx_ctx* ctx = nullptr;
+    BuildAlphabet alpha{};          // host copy of the extraction parameters
+    DevBuf d_alpha;
+    uint32_t sentinel_bit = 0;
+    uint64_t num_tables = 0;
+    // k-mer -> pattern id: open addressing over the whole 64-bit k-mer
+    DevBuf keys, vals;
+    uint64_t cap = 0, filled = 0;
+    uint32_t table_growths = 0;
+    // patterns (SoA, index = pattern id) and the log of in-place extensions
+    DevBuf num_kmers, parent, n, l, last, born, is_parent;
+    uint64_t P = 0, pat_cap = 0;
+    DevBuf ev_pat, ev_sample;
+    uint64_t ev_count = 0, ev_cap = 0;
+    // per-sample scratch
+    DevBuf seq, raw, sorted, uniq, nsel, slot_of, pid, pid2, idx, idx2, head, head_incl, run_start, split, split_incl, run_tag, ps;
+    BuildPerSample* h_ps = nullptr;   // pinned
+    uint32_t num_samples = 0;
+    uint64_t total_kmers = 0;
+    uint32_t launches = 0;
+    // finish
+    bool finished = false;
+    DevBuf bits, eoff, poff, payload, ev_pat2, ev_sample2, tfilled, slot_off, slots;
+    uint64_t payload_words = 0, total_slots = 0;
+    float ms_finish = 0.f;
+};
+
+namespace {
+#include "build_host.cuh"
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -1505,6 +1540,82 @@ int kdbx_new2all_batch(kdbx_ctx* ctx, const uint64_t* kmers, const uint64_t* q_o
     if (!ctx) return KDBX_ERR_ARG;
     return new2all_impl(ctx, kmers, q_off, n_queries, out, stats);
 }
+
+int kdbx_builder_open(kdbx_ctx* ctx, const kdbx_build_params* p, kdbx_builder** out) {
+    if (!ctx) return KDBX_ERR_ARG;
+    if (!p || !out) return ctx->fail(KDBX_ERR_ARG, "kdbx_builder_open: NULL argument");
+    *out = nullptr;
+    if (p->kmer_length == 0 || p->bits_per_symbol == 0 || p->bits_per_symbol > 8 || p->alphabet_size < 2 ||
+        p->alphabet_size > (1u << p->bits_per_symbol))
+        return ctx->fail(KDBX_ERR_ARG, "kdbx_builder_open: bad alphabet / k-mer length");
+    const int kb = (int)p->kmer_length * (int)p->bits_per_symbol;
+    const int prefix_bits = kb - 32;
+    const uint32_t shift = prefix_bits < 8 ? (uint32_t)(8 - prefix_bits) : 0u;   // src/kmer_extract.h:36-45
+    if (kb > 62 || kb + (int)shift > 62) return ctx->fail(KDBX_ERR_ARG, "kdbx_builder_open: k-mer does not fit 62 bits");
+    const int table_bits = prefix_bits < 8 ? 8 : prefix_bits;                     // src/prefix_kmer_db.cpp:54-62
+    if (table_bits > 24) return ctx->fail(KDBX_ERR_ARG, "kdbx_builder_open: 2^%d prefix tables are not supported on the device", table_bits);
+    if (!(p->fraction > 0.0)) return ctx->fail(KDBX_ERR_ARG, "kdbx_builder_open: fraction must be positive");
+    CK(cudaSetDevice(ctx->device));
+    kdbx_builder* b = new kdbx_builder();
+    b->ctx = ctx;
+    std::memcpy(b->alpha.map, p->symbol_map, 256);
+    b->alpha.k = p->kmer_length; b->alpha.bits = p->bits_per_symbol; b->alpha.size = p->alphabet_size;
+    b->alpha.preserve = p->preserve_strand ? 1u : 0u; b->alpha.shift = shift;
+    b->alpha.accept_all = !(p->fraction < 1.0) ? 1u : 0u;                         // NullFilter, src/filter.h:120-145
+    b->alpha.lo = 0; b->alpha.hi = ~0ull;
+    if (!b->alpha.accept_all) {                                                   // src/filter.h:40-51
+        const double top = (double)UINT64_MAX;
+        b->alpha.lo = (unsigned long long)(top * p->fraction_start);
+        const double hi = top * (p->fraction_start + p->fraction);
+        b->alpha.hi = hi >= top ? ~0ull : (unsigned long long)hi;
+    }
+    b->alpha.k_div_4 = (p->kmer_length + 3) / 4;
+    b->sentinel_bit = (uint32_t)kb + shift;
+    b->alpha.sentinel = 1ull << b->sentinel_bit;
+    b->num_tables = 1ull << table_bits;
+    auto fail = [&](int code, const char* what) { kdbx_builder_close(b); return ctx->fail(code, "kdbx_builder_open: %s", what); };
+    if (b->d_alpha.ensure(sizeof(BuildAlphabet)) != cudaSuccess || b->ps.ensure(sizeof(BuildPerSample)) != cudaSuccess ||
+        b->nsel.ensure(16) != cudaSuccess)
+        return fail(KDBX_ERR_NOMEM, "device allocation failed");
+    if (cudaHostAlloc(reinterpret_cast<void**>(&b->h_ps), sizeof(BuildPerSample), cudaHostAllocDefault) != cudaSuccess)
+        return fail(KDBX_ERR_NOMEM, "pinned allocation failed");
+    if (cudaMemcpyAsync(b->d_alpha.p, &b->alpha, sizeof(BuildAlphabet), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+        cudaMemsetAsync(b->ps.p, 0, sizeof(BuildPerSample), ctx->stream) != cudaSuccess)
+        return fail(KDBX_ERR_CUDA, "staging the parameters failed");
+    if (builder_reserve_patterns(b, 4096) != KDBX_OK || builder_reserve_events(b, 4096) != KDBX_OK) { kdbx_builder_close(b); return KDBX_ERR_NOMEM; }
+    // pattern 0: the empty sentinel every database starts with (src/prefix_kmer_db.cpp:24)
+    const long long minus1 = -1;
+    for (DevBuf* d : {&b->num_kmers, &b->n, &b->l, &b->last, &b->born, &b->is_parent}) cudaMemsetAsync(d->p, 0, 64, ctx->stream);
+    cudaMemcpyAsync(b->parent.p, &minus1, 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(KDBX_ERR_CUDA, "initialisation failed");
+    b->P = 1;
+    if (p->table_capacity_hint) {
+        if (int rc = builder_reserve_table(b, p->table_capacity_hint / 2)) { kdbx_builder_close(b); return rc; }
+    }
+    *out = b;
+    return KDBX_OK;
+}
+
+void kdbx_builder_close(kdbx_builder* b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    for (DevBuf* d : {&b->d_alpha, &b->keys, &b->vals, &b->num_kmers, &b->parent, &b->n, &b->l, &b->last, &b->born, &b->is_parent,
+                      &b->ev_pat, &b->ev_sample, &b->seq, &b->raw, &b->sorted, &b->uniq, &b->nsel, &b->slot_of, &b->pid, &b->pid2,
+                      &b->idx, &b->idx2, &b->head, &b->head_incl, &b->run_start, &b->split, &b->split_incl, &b->run_tag, &b->ps,
+                      &b->bits, &b->eoff, &b->poff, &b->payload, &b->ev_pat2, &b->ev_sample2, &b->tfilled, &b->slot_off, &b->slots})
+        d->release();
+    if (b->h_ps) cudaFreeHost(b->h_ps);
+    delete b;
+}
+
+int kdbx_builder_adopt(kdbx_builder* b) { return b ? builder_adopt(b) : KDBX_ERR_ARG; }
+int kdbx_builder_add_sequence(kdbx_builder* b, const char* symbols, uint64_t len, uint64_t* unique_kmers) {
+    return b ? builder_add_sequence(b, symbols, len, unique_kmers) : KDBX_ERR_ARG;
+}
+int kdbx_builder_add_kmers(kdbx_builder* b, const uint64_t* kmers, uint64_t count) { return b ? builder_add_kmers(b, kmers, count) : KDBX_ERR_ARG; }
+int kdbx_builder_finish(kdbx_builder* b, kdbx_build_result* out) { return b ? builder_finish(b, out) : KDBX_ERR_ARG; }
+int kdbx_builder_export(kdbx_builder* b, const kdbx_build_arrays* arrays) { return b ? builder_export(b, arrays) : KDBX_ERR_ARG; }
 
 int64_t kdbx_debug_fetch(kdbx_ctx* ctx, int what, void* out, uint64_t max_elems) {
     if (!ctx || !out) return KDBX_ERR_ARG;

@@ -21,7 +21,7 @@ for step in "$@"; do
     bench_chunks) for c in 16777216 33554432; do timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --chunk-ids $c > "$OUT/bench_chunk_$c.json" 2> "$OUT/bench_chunk_$c.err"; echo "bench_chunk $c rc=$?" | tee -a "$OUT/summary.txt"; done;;
     bench_tiles) for cfg in "32 1024 1024" "16 1024 512" "16 1024 1024" "8 1024 256" "32 1024 512"; do set -- $cfg; timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --tile-rows $1 --tile-cols $2 --scatter-threads $3 > "$OUT/bench_tile_$1_$2_$3.json" 2> "$OUT/bench_tile_$1_$2_$3.err"; echo "bench_tile $cfg rc=$?" | tee -a "$OUT/summary.txt"; done;;
     ncu_stages) timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:k_expand|k_job_hist|k_job_fill|k_scatter_add|k_decode_locals" -s 41 -c 5 -f -o "$OUT/stages_cfg2" python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_stages.out" 2>&1; echo "ncu_stages rc=$?" | tee -a "$OUT/summary.txt";;
-    scale) for n in ${SCALE_NS:-2 4}; do timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 5 --warmup 3 > "$OUT/scale_$n.json" 2> "$OUT/scale_$n.err"; echo "scale $n rc=$?" | tee -a "$OUT/summary.txt"; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n --steps 5 --warmup 3 --shard rows --no-e2e > "$OUT/scale_rows_$n.json" 2> "$OUT/scale_rows_$n.err"; echo "scale_rows $n rc=$?" | tee -a "$OUT/summary.txt"; done;;
+    scale) for n in ${SCALE_NS:-2}; do for mode in weak strong; do timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 5 --warmup 3 --scaling $mode > "$OUT/scale_${mode}_$n.json" 2> "$OUT/scale_${mode}_$n.err"; echo "scale $mode $n rc=$?" | tee -a "$OUT/summary.txt"; done; done;;
     test_multi) timeout 600 python -m pytest tests -m gpu -x -q -k "multi_gpu or sharding" > "$OUT/pytest_multi.log" 2>&1; echo "pytest_multi rc=$?" | tee -a "$OUT/summary.txt";;
     modes) timeout 1500 python tools/bench_modes.py --out-dir /tmp/kdbx_modes > "$OUT/modes.jsonl" 2> "$OUT/modes.err"; echo "modes rc=$?" | tee -a "$OUT/summary.txt";;
     *) echo "unknown step $step";;
