@@ -70,6 +70,8 @@ def parse_args():
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
                     help="N>1: 'weak' = every rank owns a configs[1]-sized shard of an N-times larger database; "
                          "'strong' = the configs[1] database cut into N sub-tries; both end in one NCCL all-reduce")
+    ap.add_argument("--emulate-shard", default="", help="debug, N=1 only: 'r/w' = run the weak-scaling shard of rank r of w "
+                    "ranks alone (no collective): what that rank would execute in a w-GPU run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cache-dir", default=os.environ.get("KDBX_CACHE", "/tmp/kdbx_cache"))
@@ -265,7 +267,11 @@ def main():
     scaling = a.scaling
     full_ref = None
     t_shard = 0.0
-    if world == 1:
+    if world == 1 and a.emulate_shard:
+        r_, w_ = (int(x) for x in a.emulate_shard.split("/"))
+        trie.relabel(r_ * N0, N0 * w_)
+        N, U_total = N0 * w_, U0
+    elif world == 1:
         N, U_total = N0, U0
     elif scaling == "weak":
         t0 = time.perf_counter()

@@ -417,21 +417,29 @@ __device__ __forceinline__ uint32_t lower_bound_ids(const uint32_t* __restrict__
 
 // One run of k rows of pattern `nd` (list positions i .. i+k, all in row block rb): one job per
 // column tile the run's ids reach.  emit(key, job, updates).
+// The ids a run sees are list[0 .. reach): they ascend from `first_id` = list[0] and stay below
+// `row_last`, the id of the run's last row, so only the tiles first_id/tile_cols .. (row_last-1)/tile_cols
+// can receive anything.  When that is one tile (always when T == 1; nearly always for clustered
+// samples) the job is known without touching the list; otherwise the list is cut at the tile
+// boundaries by binary search.
 template <class Emit>
 __device__ __forceinline__ void emit_run(const Node& nd, uint64_t base, const uint32_t* __restrict__ list, uint32_t T,
-                                         uint32_t tile_cols, uint32_t rb, uint32_t i, uint32_t k, Emit& emit) {
+                                         uint32_t tile_cols, uint32_t rb, uint32_t i, uint32_t k, uint32_t first_id,
+                                         uint32_t row_last, Emit& emit) {
     const uint32_t reach = i + k - 1;  // the last row of the run sees the ids [0, reach)
     if (reach == 0) return;
     Job jb;
     jb.off = (uint32_t)base; jb.off_hi = (uint32_t)(base >> 32); jb.A0 = i; jb.k = k; jb.w = 0; jb.pad = 0;
-    if (T == 1) {  // one tile: every row j of the run sees the ids [0, i + j)
+    const uint32_t t_lo = T == 1 ? 0u : first_id / tile_cols;
+    const uint32_t t_hi = T == 1 ? 0u : (row_last - 1u) / tile_cols;   // row_last > list[reach-1] >= first_id >= 0
+    if (t_lo == t_hi) {  // one tile: every row j of the run sees the ids [0, i + j)
         jb.a = 0; jb.b = nd.n;
-        emit(rb, jb, (unsigned long long)k * i + (unsigned long long)(k * (k - 1u) / 2u));
+        emit(rb * T + t_lo, jb, (unsigned long long)k * i + (unsigned long long)(k * (k - 1u) / 2u));
         return;
     }
     uint32_t a = 0;
-    for (uint32_t t = 0; t < T && a < reach; ++t) {
-        const uint32_t b = (t + 1 == T) ? nd.n : lower_bound_ids(list, nd.n, (t + 1) * tile_cols);
+    for (uint32_t t = t_lo; t <= t_hi && a < reach; ++t) {
+        const uint32_t b = (t == t_hi) ? nd.n : a + lower_bound_ids(list + a, reach - a, (t + 1) * tile_cols);
         if (b > a) { jb.a = a; jb.b = b; emit(rb * T + t, jb, job_updates(a, b, i, k)); }
         a = b;
     }
@@ -445,6 +453,7 @@ __device__ __forceinline__ void jobs_of_pattern_warp(const Node& nd, uint64_t ba
     const uint32_t first = nd.n - nd.l;
     const uint32_t rounds = (nd.l + 31) / 32;
     const uint32_t* list = flat + base;
+    const uint32_t first_id = T > 1 ? list[0] : 0u;
     for (uint32_t r = 0; r < rounds; ++r) {
         const uint32_t j = r * 32 + lane;
         const bool have = j < nd.l;
@@ -461,13 +470,15 @@ __device__ __forceinline__ void jobs_of_pattern_warp(const Node& nd, uint64_t ba
         const uint32_t amask = __ballot_sync(0xffffffffu, active);
         const bool start = active && (lane == 0 || !((amask >> (lane - 1)) & 1u) || prev_rb != rb);
         const uint32_t smask = __ballot_sync(0xffffffffu, start);
-        if (!start) continue;
         // the run ends at the next start or after the last active lane (active lanes are contiguous:
         // rows ascend and [row_begin,row_end) is an interval)
         const uint32_t above = lane == 31 ? 0u : ((smask >> (lane + 1)) << (lane + 1));
         const uint32_t next_start = above ? (uint32_t)__ffs((int)above) - 1u : 32u;
-        const uint32_t last_active = 32u - (uint32_t)__clz((int)amask);
-        emit_run(nd, base, list, T, tile_cols, rb, i, min(next_start, last_active) - lane, emit);
+        const uint32_t last_active = amask ? 32u - (uint32_t)__clz((int)amask) : 0u;
+        const uint32_t run_end = min(next_start, last_active);           // one past the run's last lane
+        const uint32_t row_last = __shfl_sync(0xffffffffu, row, (run_end > lane ? run_end : lane + 1u) - 1u);
+        if (!start) continue;
+        emit_run(nd, base, list, T, tile_cols, rb, i, run_end - lane, first_id, row_last, emit);
     }
 }
 
@@ -498,19 +509,21 @@ __device__ __forceinline__ void enumerate_jobs(uint64_t lo, uint64_t hi, uint32_
             const uint32_t first = nd.n - nd.l;
             const uint32_t* list = flat + base;
             const uint32_t* rows = loc + nd.loff;
-            uint32_t run_i = 0, run_k = 0, run_rb = 0;
+            const uint32_t first_id = T > 1 ? list[0] : 0u;
+            uint32_t run_i = 0, run_k = 0, run_rb = 0, run_last = 0;
             for (uint32_t j = 0; j < nd.l; ++j) {
                 const uint32_t row = rows[j];
                 const bool active = row >= row_begin && row < row_end;
                 const uint32_t rb = row >> rb_shift;
                 if (active) updates += first + j;
-                if (run_k && (!active || rb != run_rb)) { emit_run(nd, base, list, T, tile_cols, run_rb, run_i, run_k, emit_w); run_k = 0; }
+                if (run_k && (!active || rb != run_rb)) { emit_run(nd, base, list, T, tile_cols, run_rb, run_i, run_k, first_id, run_last, emit_w); run_k = 0; }
                 if (active) {
                     if (!run_k) { run_i = first + j; run_rb = rb; }
                     ++run_k;
+                    run_last = row;
                 }
             }
-            if (run_k) emit_run(nd, base, list, T, tile_cols, run_rb, run_i, run_k, emit_w);
+            if (run_k) emit_run(nd, base, list, T, tile_cols, run_rb, run_i, run_k, first_id, run_last, emit_w);
         }
         uint32_t big = __ballot_sync(0xffffffffu, nd.l > kSmallL);
         while (big) {

@@ -26,6 +26,7 @@ struct Params {
     bool multisample_fasta = false, sparse_out = false, extend_db = false, phylip_out = false;
     int gpu = -1;              // -gpu <ordinal> (ours)
     int num_gpus = 1;          // -gpus <n> (ours): row-block sharding over n devices
+    bool host_build = false;   // build -host-build (ours): run the host builder explicitly (machines without a GPU)
     Alphabet alphabet = Alphabet::make(kNt);
     OutputFilters filters;
     std::string metric_name;

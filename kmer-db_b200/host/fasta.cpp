@@ -152,3 +152,60 @@ bool SampleStream::next(SampleKmers& out) {
 }
 
 }  // namespace kdbx
+
+namespace kdbx {
+
+SequenceStream::SequenceStream(const std::string& list_arg, bool multisample, int threads)
+    : files_(read_sample_list(list_arg)), multisample_(multisample), ahead_((size_t)std::max(1, threads)) {}
+
+std::vector<SampleSeq> SequenceStream::load_file(size_t idx) const {
+    std::vector<SampleSeq> out;
+    std::string data;
+    if (!load_sequence_file(files_[idx], data)) {
+        std::fprintf(stderr, "failed:%s\n", files_[idx].c_str());
+        return out;
+    }
+    std::vector<FastaRecord> recs;
+    split_fasta(data, recs);
+    if (multisample_) {
+        for (const FastaRecord& r : recs) {
+            SampleSeq s;
+            s.name = r.header;
+            s.symbols.assign(r.seq, r.len);
+            out.push_back(std::move(s));
+        }
+    } else {
+        SampleSeq s;
+        s.name = sample_name_of(files_[idx]);
+        size_t total = 0;
+        for (const FastaRecord& r : recs) total += r.len + 1;
+        s.symbols.reserve(total);
+        for (const FastaRecord& r : recs) { s.symbols.append(r.seq, r.len); s.symbols.push_back('\0'); }
+        out.push_back(std::move(s));
+    }
+    return out;
+}
+
+void SequenceStream::refill() {
+    while (inflight_.size() < ahead_ && next_file_ < files_.size()) {
+        const size_t idx = next_file_++;
+        inflight_.push_back(std::async(std::launch::async, [this, idx] { return load_file(idx); }));
+    }
+}
+
+bool SequenceStream::next(SampleSeq& out) {
+    for (;;) {
+        if (!ready_.empty()) {
+            out = std::move(ready_.front());
+            ready_.pop_front();
+            return true;
+        }
+        refill();
+        if (inflight_.empty()) return false;
+        std::vector<SampleSeq> got = inflight_.front().get();
+        inflight_.pop_front();
+        for (auto& s : got) ready_.push_back(std::move(s));
+    }
+}
+
+}  // namespace kdbx

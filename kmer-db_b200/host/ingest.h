@@ -31,6 +31,32 @@ bool load_sequence_file(const std::string& entry, std::string& data);  // plain 
 void split_fasta(std::string& data, std::vector<FastaRecord>& out);    // edits `data` in place
 std::string sample_name_of(const std::string& entry);
 
+// One sample as the device builder takes it: the symbols of its records back to back, each record
+// followed by a NUL byte (outside every alphabet, so no k-mer spans two records).
+struct SampleSeq {
+    std::string name;
+    std::string symbols;
+};
+
+// Like SampleStream, but stops before k-mer extraction: the sequences go to the GPU
+// (kdbx_builder_add_sequence).  Reader threads load, gunzip and split the files ahead of the consumer.
+class SequenceStream {
+public:
+    SequenceStream(const std::string& list_arg, bool multisample, int threads);
+    bool next(SampleSeq& out);
+    size_t num_files() const { return files_.size(); }
+
+private:
+    std::vector<SampleSeq> load_file(size_t idx) const;
+    void refill();
+    std::vector<std::string> files_;
+    bool multisample_;
+    size_t ahead_;
+    size_t next_file_ = 0;
+    std::deque<std::future<std::vector<SampleSeq>>> inflight_;
+    std::deque<SampleSeq> ready_;
+};
+
 class SampleStream {
 public:
     SampleStream(const std::string& list_arg, const Alphabet& alphabet, const MinHash& filter, uint32_t k, bool multisample,

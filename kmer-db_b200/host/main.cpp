@@ -13,6 +13,7 @@
 #include <cstring>
 #include <iostream>
 
+#include "build_device.h"
 #include "cli.h"
 #include "csv_out.h"
 #include "ingest.h"
@@ -35,9 +36,51 @@ void print_stats_json(const kdbx_stats& s, double dt) {
 }
 }  // namespace
 
+// build on the device (the default): the host only reads, gunzips and splits the FASTA files; k-mer
+// extraction, minhash, sort/unique, the k-mer table and the pattern trie live on the GPU (csrc/build.cuh)
+static void run_build_device(const Params& p) {
+    Alphabet alphabet = p.alphabet;
+    uint32_t k = p.kmer_length;
+    double fraction = p.fraction, start = p.fraction_start;
+    Trie old;
+    if (p.extend_db) {
+        std::cerr << "Loading k-mer database " << p.files[1] << "..." << std::endl;
+        read_db(p.files[1], old, true);
+        alphabet = Alphabet::make(old.hdr.alphabet_type);
+        k = old.hdr.kmer_length;
+        fraction = old.hdr.fraction; start = old.hdr.start_fraction;
+        // the alphabet recorded with every sample is the command line's one (src/console_build.cpp:117)
+        if (old.hdr.alphabet_type != p.alphabet.id)
+            throw std::runtime_error("Error in AbstractKmerDb::addKmers(): adding samples from different alphabet");
+    }
+    DeviceDbBuilder builder(p.gpu, alphabet, k, fraction, start);
+    if (p.extend_db) { builder.adopt(old); old = Trie(); }
+    std::cerr << "Processing samples..." << std::endl;
+    const double t0 = now();
+    SequenceStream stream(p.files[0], p.multisample_fasta, p.num_reader_threads);
+    SampleSeq s;
+    size_t n = 0;
+    while (stream.next(s)) {
+        if (builder.add_sample(s.name, s.symbols.data(), s.symbols.size()) == 0) std::cerr << "Empty sample: " << s.name << std::endl;
+        if (++n % 10 == 0) std::cerr << "\r" << n << "/" << stream.num_files() << "..." << std::flush;
+    }
+    std::cerr << "\r" << n << "/" << n << "                      " << std::endl;
+    std::cerr << "Database update time: " << now() - t0 << std::endl;
+    std::cerr << "Serializing database..." << std::endl;
+    Trie db;
+    builder.finish(db);
+    const kdbx_build_result& r = builder.result();
+    std::fprintf(stderr, "{\"samples\": %u, \"patterns\": %llu, \"kmers\": %llu, \"table_slots\": %llu, \"table_growths\": %u, "
+                         "\"kernel_launches\": %u, \"ms_finish\": %.3f, \"seconds\": %.6f}\n",
+                 r.num_samples, (unsigned long long)r.num_patterns, (unsigned long long)r.kmers_count,
+                 (unsigned long long)r.table_capacity, r.table_growths, r.kernel_launches, r.ms_finish, now() - t0);
+    write_db(p.files[1], db);
+}
+
 void run_build(const Params& p) {
     if (p.files.size() != 2) throw usage_error(p.mode);
     std::cerr << "Building database (from genomes)" << std::endl;
+    if (!p.host_build) { run_build_device(p); return; }
     DbBuilder builder(p.num_threads);
     Alphabet alphabet = p.alphabet;
     MinHash filter(p.fraction, p.fraction_start, p.kmer_length);

@@ -97,6 +97,7 @@ bool parse_params(int argc, char** argv, Params& p) {
         if ((int)p.kmer_length > p.alphabet.max_kmer_len)
             throw std::runtime_error("K-mer length for the given alphabet cannot exceed " + std::to_string(p.alphabet.max_kmer_len));
         p.extend_db = find_switch(a, "-extend");
+        p.host_build = find_switch(a, "-host-build");
     } else if (p.mode == "all2all" || p.mode == "all2all-sp") {
         find_option(a, "-buffer", p.cache_buffer_mb);
         if (p.cache_buffer_mb <= 0) p.cache_buffer_mb = 8;

@@ -68,6 +68,24 @@ class TablesView(C.Structure):
     _fields_ = [("num_tables", C.c_uint64), ("slot_off", C.c_void_p), ("slots", C.c_void_p)]
 
 
+class BuildParams(C.Structure):
+    _fields_ = [("kmer_length", C.c_uint32), ("bits_per_symbol", C.c_uint32), ("alphabet_size", C.c_uint32),
+                ("preserve_strand", C.c_uint32), ("fraction", C.c_double), ("fraction_start", C.c_double),
+                ("symbol_map", C.c_int8 * 256), ("table_capacity_hint", C.c_uint64)]
+
+
+class BuildResult(C.Structure):
+    _fields_ = [("num_patterns", C.c_uint64), ("payload_words", C.c_uint64), ("num_tables", C.c_uint64),
+                ("total_slots", C.c_uint64), ("kmers_count", C.c_uint64), ("sum_local_samples", C.c_uint64),
+                ("table_capacity", C.c_uint64), ("num_samples", C.c_uint32), ("kernel_launches", C.c_uint32),
+                ("table_growths", C.c_uint32), ("ms_finish", C.c_float), ("reserved", C.c_uint64 * 2)]
+
+
+class BuildArrays(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("num_kmers", "parent_id", "num_samples_full", "num_local_samples", "last_sample_id",
+                                          "num_bits", "payload_off", "payload", "slot_off", "slots", "table_filled")]
+
+
 METRICS = {"jaccard": 0, "min": 1, "max": 2, "cosine": 3}
 FLAG_CHUNKED_LISTS = 1
 FLAG_ASYNC_UPLOAD = 2
@@ -89,7 +107,9 @@ class Totals(C.Structure):
 KDBX_SYMBOLS = ["kdbx_abi_version", "kdbx_device_count", "kdbx_open", "kdbx_close", "kdbx_last_error",
                 "kdbx_host_alloc", "kdbx_host_free", "kdbx_load_patterns", "kdbx_row_updates", "kdbx_all2all_dense",
                 "kdbx_all2all_dense_rows", "kdbx_all2all_dense_rows_device", "kdbx_all2all_dense_part_device", "kdbx_all2all_sparse", "kdbx_free_csr",
-                "kdbx_load_hashtables", "kdbx_new2all_batch", "kdbx_debug_fetch"]
+                "kdbx_load_hashtables", "kdbx_new2all_batch", "kdbx_debug_fetch",
+                "kdbx_builder_open", "kdbx_builder_close", "kdbx_builder_adopt", "kdbx_builder_add_sequence", "kdbx_builder_add_kmers",
+                "kdbx_builder_finish", "kdbx_builder_export"]
 KDBXH_SYMBOLS = ["kdbxh_last_error", "kdbxh_trie_new", "kdbxh_trie_free", "kdbxh_read_db", "kdbxh_write_db",
                  "kdbxh_synth", "kdbxh_validate", "kdbxh_prefix", "kdbxh_partition", "kdbxh_relabel", "kdbxh_view", "kdbxh_totals_of", "kdbxh_sample_name",
                  "kdbxh_sample_kmers", "kdbxh_write_all2all_csv", "kdbxh_read_db_full", "kdbxh_tables_view",
@@ -132,6 +152,14 @@ def load():
     k.kdbx_free_csr.restype = None
     k.kdbx_load_hashtables.argtypes = [C.c_void_p, P(TablesView)]
     k.kdbx_new2all_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, P(Stats)]
+    k.kdbx_builder_open.argtypes = [C.c_void_p, P(BuildParams), P(C.c_void_p)]
+    k.kdbx_builder_close.argtypes = [C.c_void_p]
+    k.kdbx_builder_close.restype = None
+    k.kdbx_builder_adopt.argtypes = [C.c_void_p]
+    k.kdbx_builder_add_sequence.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, P(C.c_uint64)]
+    k.kdbx_builder_add_kmers.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    k.kdbx_builder_finish.argtypes = [C.c_void_p, P(BuildResult)]
+    k.kdbx_builder_export.argtypes = [C.c_void_p, P(BuildArrays)]
     k.kdbx_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
     k.kdbx_debug_fetch.restype = C.c_int64
     h.kdbxh_last_error.restype = C.c_char_p
@@ -475,6 +503,73 @@ class Context:
         if got < 0:
             raise KdbxError(self._k.kdbx_last_error(self._p).decode())
         return out[:got]
+
+
+NT_MAP = {"A": 0, "C": 1, "G": 2, "T": 3, "U": 3}
+
+
+class DeviceBuilder:
+    """kdbx_builder_* on a Context (the device-side `build`).  alphabet: dict symbol -> code (upper case;
+    lower case is added), default nucleotides."""
+
+    def __init__(self, ctx: "Context", k=18, fraction=1.0, fraction_start=0.0, alphabet=None, preserve_strand=False,
+                 table_capacity_hint=0):
+        self._ctx = ctx
+        self._k = ctx._k
+        alphabet = alphabet or NT_MAP
+        size = max(alphabet.values()) + 1
+        bits = max(1, (size - 1).bit_length())
+        bp = BuildParams(k, bits, size, 1 if preserve_strand else 0, fraction, fraction_start)
+        for i in range(256):
+            bp.symbol_map[i] = -1
+        for ch, code in alphabet.items():
+            bp.symbol_map[ord(ch.upper())] = code
+            bp.symbol_map[ord(ch.lower())] = code
+        bp.table_capacity_hint = table_capacity_hint
+        p = C.c_void_p()
+        ctx._check(self._k.kdbx_builder_open(ctx._p, C.byref(bp), C.byref(p)))
+        self._p = p
+        self.k, self.bits = k, bits
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self._k.kdbx_builder_close(self._p)
+            self._p = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def adopt(self):
+        self._ctx._check(self._k.kdbx_builder_adopt(self._p))
+
+    def add_sequence(self, symbols: bytes) -> int:
+        n = C.c_uint64()
+        self._ctx._check(self._k.kdbx_builder_add_sequence(self._p, symbols, len(symbols), C.byref(n)))
+        return int(n.value)
+
+    def add_kmers(self, kmers):
+        kmers = np.ascontiguousarray(kmers, np.uint64)
+        self._ctx._check(self._k.kdbx_builder_add_kmers(self._p, kmers.ctypes.data if kmers.size else None, kmers.size))
+
+    def finish(self):
+        """-> (dict of SoA arrays like Trie.arrays(), slot_off, slots, table_filled, BuildResult)"""
+        r = BuildResult()
+        self._ctx._check(self._k.kdbx_builder_finish(self._p, C.byref(r)))
+        P, T = int(r.num_patterns), int(r.num_tables)
+        a = {"num_kmers": np.zeros(P, np.int64), "parent_id": np.zeros(P, np.int64), "n": np.zeros(P, np.uint32),
+             "l": np.zeros(P, np.uint32), "last": np.zeros(P, np.uint32), "bits": np.zeros(P, np.uint32),
+             "payload_off": np.zeros(P, np.uint64), "payload": np.zeros(int(r.payload_words) + 2, np.uint64)}
+        slot_off = np.zeros(T + 1, np.uint64)
+        slots = np.zeros(int(r.total_slots), np.uint64)
+        filled = np.zeros(T, np.uint64)
+        ba = BuildArrays(a["num_kmers"].ctypes.data, a["parent_id"].ctypes.data, a["n"].ctypes.data, a["l"].ctypes.data,
+                         a["last"].ctypes.data, a["bits"].ctypes.data, a["payload_off"].ctypes.data, a["payload"].ctypes.data,
+                         slot_off.ctypes.data, slots.ctypes.data if slots.size else None, filled.ctypes.data)
+        self._ctx._check(self._k.kdbx_builder_export(self._p, C.byref(ba)))
+        return a, slot_off, slots, filled, r
 
 
 def pinned_empty(count: int, dtype=np.uint32):

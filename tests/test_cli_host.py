@@ -1,4 +1,4 @@
-"""Host-side modes of the CLI (build, distance) and the host builder against the reference's own
+"""Host-side modes of the CLI (build -host-build, distance) and the host builder against the reference's own
 CI vectors (.github/workflows/main.yml:45-165, self-hosted.yml:91-426).  CPU only: databases we
 build are checked by running the ORACLE's all2all / new2all on them and comparing with the
 reference's golden CSVs."""
@@ -38,22 +38,22 @@ def _oracle_new2all_csv(oracle, db, lst, out, multi=False, sparse=False, cwd=Non
     (["-multisample-fasta", "-k", "21", "test/synth/synth.list"], "test/synth/a2a"),
 ])
 def test_build_then_oracle_all2all_reproduces_reference_csv(cli, oracle, ref_fixtures, tmp_path, args, golden):
-    cli(ref_fixtures, "build", *args, tmp_path / "x.db")
+    cli(ref_fixtures, "build", "-host-build", *args, tmp_path / "x.db")
     assert _oracle_all2all_csv(oracle, tmp_path / "x.db", tmp_path / "x.csv") == ou.read_bytes(ref_fixtures / golden)
 
 
 def test_build_extend(cli, oracle, ref_fixtures, tmp_path):
     """build part1, then -extend with part2 (k given on the command line is ignored, main.yml:132-135)."""
     db = tmp_path / "parts.db"
-    cli(ref_fixtures, "build", "test/virus/seqs.part1.list", db)
-    cli(ref_fixtures, "build", "-extend", "-k", "25", "test/virus/seqs.part2.list", db)
+    cli(ref_fixtures, "build", "-host-build", "test/virus/seqs.part1.list", db)
+    cli(ref_fixtures, "build", "-host-build", "-extend", "-k", "25", "test/virus/seqs.part2.list", db)
     assert _oracle_all2all_csv(oracle, db, tmp_path / "x.csv") == ou.read_bytes(ref_fixtures / "test/virus/k18.csv")
     assert _oracle_all2all_csv(oracle, db, tmp_path / "s.csv", sparse=True) == ou.read_bytes(ref_fixtures / "test/virus/k18.sparse.csv")
 
 
 @pytest.mark.parametrize("alphabet", ["aa", "aa11_diamond", "aa12_mmseqs", "aa6_dayhoff"])
 def test_build_amino_alphabets(cli, oracle, ref_fixtures, tmp_path, alphabet):
-    cli(ref_fixtures, "build", "-k", "8", "-multisample-fasta", "-alphabet", alphabet, "test/protein/aa_100x1000.fasta", tmp_path / "a.db")
+    cli(ref_fixtures, "build", "-host-build", "-k", "8", "-multisample-fasta", "-alphabet", alphabet, "test/protein/aa_100x1000.fasta", tmp_path / "a.db")
     assert _oracle_all2all_csv(oracle, tmp_path / "a.db", tmp_path / "a.csv") == ou.read_bytes(ref_fixtures / f"test/protein/{alphabet}.a2a")
 
 
@@ -61,7 +61,7 @@ def test_built_kmer_tables_serve_queries(cli, oracle, ref_fixtures, golden_dbs, 
     """The k-mer tables our build writes must answer the reference's new2all vectors; the same
     oracle on the database the REFERENCE built (tests/golden) pins the oracle itself."""
     ours = tmp_path / "p1.db"
-    cli(ref_fixtures, "build", "test/virus/seqs.part1.list", ours)
+    cli(ref_fixtures, "build", "-host-build", "test/virus/seqs.part1.list", ours)
     theirs = ou.ROOT / "tests" / "golden" / "virus.k18.part1.db"
     for db in (ours, theirs):
         got = _oracle_new2all_csv(oracle, db, "test/virus/seqs.part2.list", tmp_path / "n.csv", cwd=ref_fixtures)
@@ -81,7 +81,7 @@ def test_reference_binary_accepts_our_database(cli, ref_bin, ref_fixtures, tmp_p
     if ref_bin is None:
         pytest.skip("reference binary not built (oracle/_ref)")
     import subprocess
-    cli(ref_fixtures, "build", "test/virus/seqs.part1.list", tmp_path / "p1.db")
+    cli(ref_fixtures, "build", "-host-build", "test/virus/seqs.part1.list", tmp_path / "p1.db")
     subprocess.run([str(ref_bin), "new2all", str(tmp_path / "p1.db"), "test/virus/seqs.part2.list", str(tmp_path / "n.csv")],
                    cwd=str(ref_fixtures), check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     assert ou.read_bytes(tmp_path / "n.csv") == ou.read_bytes(ref_fixtures / "test/virus/k18.n2a.csv")
@@ -128,7 +128,7 @@ def test_cli_errors(cli, ref_fixtures, tmp_path):
     assert r.returncode != 0 and "unknown metric" in r.stderr
     r = cli(ref_fixtures, "build", "-k", "40", "test/virus/seqs.list", tmp_path / "x.db", check=False)
     assert r.returncode != 0 and "cannot exceed" in r.stderr
-    r = cli(ref_fixtures, "build", "missing.list", tmp_path / "x.db", check=False)
+    r = cli(ref_fixtures, "build", "-host-build", "missing.list", tmp_path / "x.db", check=False)
     assert r.returncode != 0 and "Unable to open input file" in r.stderr
     r = cli(ref_fixtures, "build", "only-one-file", check=False)
     assert r.returncode != 0

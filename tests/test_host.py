@@ -26,19 +26,21 @@ def test_libraries_export_every_declared_symbol(libs):
         assert hasattr(h, name), name
     assert set(_declared("kdbx.h")) == set(libs.KDBX_SYMBOLS)
     assert set(_declared("kdbx_host.h")) == set(libs.KDBXH_SYMBOLS)
-    assert k.kdbx_abi_version() == 2
+    assert k.kdbx_abi_version() == 3
 
 
 def test_struct_sizes_match_header(libs, tmp_path):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include "kdbx_host.h"\nint main(){printf("%zu %zu %zu %zu %zu",sizeof(kdbx_config),'
                    'sizeof(kdbx_trie_view),sizeof(kdbx_stats),sizeof(kdbxh_synth_params),sizeof(kdbxh_totals));'
-                   'printf(" %zu %zu %zu",sizeof(kdbx_filter),sizeof(kdbx_csr),sizeof(kdbx_tables_view));return 0;}')
+                   'printf(" %zu %zu %zu",sizeof(kdbx_filter),sizeof(kdbx_csr),sizeof(kdbx_tables_view));'
+                   'printf(" %zu %zu %zu",sizeof(kdbx_build_params),sizeof(kdbx_build_result),sizeof(kdbx_build_arrays));return 0;}')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
     sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [C.sizeof(libs.Config), C.sizeof(libs.TrieView), C.sizeof(libs.Stats), C.sizeof(libs.SynthParams),
-                     C.sizeof(libs.Totals), C.sizeof(libs.Filter), C.sizeof(libs.Csr), C.sizeof(libs.TablesView)]
+                     C.sizeof(libs.Totals), C.sizeof(libs.Filter), C.sizeof(libs.Csr), C.sizeof(libs.TablesView),
+                     C.sizeof(libs.BuildParams), C.sizeof(libs.BuildResult), C.sizeof(libs.BuildArrays)]
 
 
 def test_no_gpu_means_loud_failure_not_fallback(libs):
