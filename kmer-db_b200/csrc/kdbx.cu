@@ -92,7 +92,7 @@ struct ChunkCost {
     const uint32_t* n; const uint32_t* l; const uint32_t* last; uint64_t cnt; uint32_t tile_cols;
     __host__ __device__ uint64_t operator()(uint64_t i) const {
         if (i >= cnt) return 0ull;
-        const uint64_t jobs = (uint64_t)l[i] * (uint64_t)(last[i] / tile_cols + 1u);
+        const uint64_t jobs = (uint64_t)l[i] * (uint64_t)(last[i] / tile_cols + 2u);  // windows a row of p can reach
         const uint64_t ids = (n[i] + 3u) & ~3u;
         return jobs > ids ? jobs : ids;
     }
@@ -347,7 +347,7 @@ __global__ void k_expand(uint64_t p0, uint64_t p1, const Node* __restrict__ node
 // two contiguous copies each.  One launch per level, ascending; no pointer chasing at all.
 constexpr uint32_t kLevelLanes = 8;
 __global__ void k_expand_level(uint32_t count, const uint32_t* __restrict__ order, const Node* __restrict__ nodes,
-                               const uint64_t* __restrict__ noff, const uint32_t* __restrict__ loc, uint32_t* flat) {
+                               const uint64_t* __restrict__ noff, const uint32_t* __restrict__ loc, uint32_t* flat, uint32_t* first_id) {
     const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / kLevelLanes;
     const uint32_t sub = threadIdx.x & (kLevelLanes - 1);
     const bool have = gid < count;
@@ -357,6 +357,8 @@ __global__ void k_expand_level(uint32_t count, const uint32_t* __restrict__ orde
         const uint32_t p = order[gid];
         nd = nodes[p];
         dst = flat + noff[p];
+        // first id of the full list (the job enumeration places a pattern's columns with it)
+        if (sub == 0 && nd.n) first_id[p] = nd.parent >= 0 ? first_id[nd.parent] : loc[nd.loff];
     }
     const uint32_t npar = nd.n - nd.l;
     if (have && nd.parent >= 0) {
@@ -415,33 +417,51 @@ __device__ __forceinline__ uint32_t lower_bound_ids(const uint32_t* __restrict__
     return lo;
 }
 
+// Column windows.  The accumulator tile of row block rb does not sit on a fixed column grid: its
+// window 0 ends right above the block's rows (at win_hi(rb), the 32-aligned end of the block) and
+// window t covers the tile_cols columns [win_hi - (t+1) tile_cols, win_hi - t tile_cols) below it,
+// clipped at column 0.  Samples that entered the database close together (a clade, a cluster, a
+// shard of a larger database) have their ids within a few hundred places below the row, so all of
+// a pattern's columns fall into window 0 whatever N is; with N <= tile_cols there is one window and
+// it starts at column 0.  key = rb * T + t.
+__device__ __forceinline__ uint32_t win_hi(uint32_t rb, uint32_t rb_shift) { return (((rb + 1u) << rb_shift) + 31u) & ~31u; }
+__device__ __forceinline__ uint32_t win_col0(uint32_t hi, uint32_t t, uint32_t tile_cols) {
+    const uint64_t span = (uint64_t)(t + 1u) * tile_cols;
+    return span >= hi ? 0u : hi - (uint32_t)span;
+}
+
 // One run of k rows of pattern `nd` (list positions i .. i+k, all in row block rb): one job per
-// column tile the run's ids reach.  emit(key, job, updates).
+// column window the run's ids reach.  emit(key, job, updates).
 // The ids a run sees are list[0 .. reach): they ascend from `first_id` = list[0] and stay below
-// `row_last`, the id of the run's last row, so only the tiles first_id/tile_cols .. (row_last-1)/tile_cols
-// can receive anything.  When that is one tile (always when T == 1; nearly always for clustered
-// samples) the job is known without touching the list; otherwise the list is cut at the tile
-// boundaries by binary search.
+// `row_last`, the id of the run's last row.  When both ends lie in one window (always when T == 1)
+// the job is known without touching the list; otherwise the list is cut at the window boundaries by
+// binary search, far window first.
 template <class Emit>
 __device__ __forceinline__ void emit_run(const Node& nd, uint64_t base, const uint32_t* __restrict__ list, uint32_t T,
-                                         uint32_t tile_cols, uint32_t rb, uint32_t i, uint32_t k, uint32_t first_id,
+                                         uint32_t tile_cols, uint32_t rb_shift, uint32_t rb, uint32_t i, uint32_t k, uint32_t first_id,
                                          uint32_t row_last, Emit& emit) {
     const uint32_t reach = i + k - 1;  // the last row of the run sees the ids [0, reach)
     if (reach == 0) return;
     Job jb;
     jb.off = (uint32_t)base; jb.off_hi = (uint32_t)(base >> 32); jb.A0 = i; jb.k = k; jb.w = 0; jb.pad = 0;
-    const uint32_t t_lo = T == 1 ? 0u : first_id / tile_cols;
-    const uint32_t t_hi = T == 1 ? 0u : (row_last - 1u) / tile_cols;   // row_last > list[reach-1] >= first_id >= 0
-    if (t_lo == t_hi) {  // one tile: every row j of the run sees the ids [0, i + j)
+    uint32_t t_near = 0, t_far = 0, hi = 0;
+    if (T > 1) {
+        hi = win_hi(rb, rb_shift);               // row_last < hi, and first_id <= list[reach-1] < row_last
+        t_near = (hi - row_last) / tile_cols;     // window of the id row_last - 1
+        t_far = (hi - 1u - first_id) / tile_cols;
+    }
+    if (t_near == t_far) {  // one window: every row j of the run sees the ids [0, i + j)
         jb.a = 0; jb.b = nd.n;
-        emit(rb * T + t_lo, jb, (unsigned long long)k * i + (unsigned long long)(k * (k - 1u) / 2u));
+        emit(rb * T + t_near, jb, (unsigned long long)k * i + (unsigned long long)(k * (k - 1u) / 2u));
         return;
     }
     uint32_t a = 0;
-    for (uint32_t t = t_lo; t <= t_hi && a < reach; ++t) {
-        const uint32_t b = (t == t_hi) ? nd.n : a + lower_bound_ids(list + a, reach - a, (t + 1) * tile_cols);
+    for (uint32_t t = t_far; a < reach; --t) {
+        // ids below the upper end of window t belong to it (lower windows were cut off before)
+        const uint32_t b = (t == t_near) ? nd.n : a + lower_bound_ids(list + a, reach - a, hi - t * tile_cols);
         if (b > a) { jb.a = a; jb.b = b; emit(rb * T + t, jb, job_updates(a, b, i, k)); }
         a = b;
+        if (t == t_near) break;
     }
 }
 
@@ -449,11 +469,10 @@ __device__ __forceinline__ void emit_run(const Node& nd, uint64_t base, const ui
 template <class Emit>
 __device__ __forceinline__ void jobs_of_pattern_warp(const Node& nd, uint64_t base, const uint32_t* __restrict__ flat,
                                                      const uint32_t* __restrict__ loc, uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin,
-                                                     uint32_t row_end, uint32_t lane, unsigned long long& updates, Emit& emit) {
+                                                     uint32_t row_end, uint32_t lane, uint32_t first_id, unsigned long long& updates, Emit& emit) {
     const uint32_t first = nd.n - nd.l;
     const uint32_t rounds = (nd.l + 31) / 32;
     const uint32_t* list = flat + base;
-    const uint32_t first_id = T > 1 ? list[0] : 0u;
     for (uint32_t r = 0; r < rounds; ++r) {
         const uint32_t j = r * 32 + lane;
         const bool have = j < nd.l;
@@ -478,7 +497,7 @@ __device__ __forceinline__ void jobs_of_pattern_warp(const Node& nd, uint64_t ba
         const uint32_t run_end = min(next_start, last_active);           // one past the run's last lane
         const uint32_t row_last = __shfl_sync(0xffffffffu, row, (run_end > lane ? run_end : lane + 1u) - 1u);
         if (!start) continue;
-        emit_run(nd, base, list, T, tile_cols, rb, i, run_end - lane, first_id, row_last, emit);
+        emit_run(nd, base, list, T, tile_cols, rb_shift, rb, i, run_end - lane, first_id, row_last, emit);
     }
 }
 
@@ -492,38 +511,42 @@ template <class Emit>
 __device__ __forceinline__ void enumerate_jobs(uint64_t lo, uint64_t hi, uint32_t warp, uint32_t nwarps,
                                                const Node* __restrict__ nodes, const uint64_t* __restrict__ noff, uint64_t base0,
                                                const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat,
-                                               const uint32_t* __restrict__ loc, uint32_t T, uint32_t tile_cols, uint32_t rb_shift,
-                                               uint32_t row_begin, uint32_t row_end, uint32_t lane, unsigned long long& updates,
-                                               Emit emit) {
+                                               const uint32_t* __restrict__ loc, const uint32_t* __restrict__ first_ids, uint32_t T,
+                                               uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin, uint32_t row_end, uint32_t lane,
+                                               unsigned long long& updates, Emit emit) {
     for (uint64_t b = lo + (uint64_t)warp * 32; b < hi; b += (uint64_t)nwarps * 32) {
         const uint64_t p = b + lane;
         Node nd; nd.parent = -1; nd.n = 0; nd.l = 0; nd.last = 0; nd.loff = 0; nd.up2 = nd.up3 = -1;
-        uint32_t w = 0;
+        uint32_t w = 0, fid = 0;
         uint64_t base = 0;
         if (p < hi) {
             nd = nodes[p];
-            if (nd.l) { w = W[p]; base = noff[p] - base0; }
+            if (nd.l) {
+                w = W[p]; base = noff[p] - base0;
+                // first id of the full list: kept per pattern by the level-order expansion, else read from the list
+                if (T > 1) fid = first_ids ? first_ids[p] : flat[base];
+            }
         }
         auto emit_w = [&](uint32_t key, const Job& jb, unsigned long long upd) { emit(key, jb, upd, w); };
         if (nd.l && nd.l <= kSmallL) {
             const uint32_t first = nd.n - nd.l;
             const uint32_t* list = flat + base;
             const uint32_t* rows = loc + nd.loff;
-            const uint32_t first_id = T > 1 ? list[0] : 0u;
+            const uint32_t first_id = fid;
             uint32_t run_i = 0, run_k = 0, run_rb = 0, run_last = 0;
             for (uint32_t j = 0; j < nd.l; ++j) {
                 const uint32_t row = rows[j];
                 const bool active = row >= row_begin && row < row_end;
                 const uint32_t rb = row >> rb_shift;
                 if (active) updates += first + j;
-                if (run_k && (!active || rb != run_rb)) { emit_run(nd, base, list, T, tile_cols, run_rb, run_i, run_k, first_id, run_last, emit_w); run_k = 0; }
+                if (run_k && (!active || rb != run_rb)) { emit_run(nd, base, list, T, tile_cols, rb_shift, run_rb, run_i, run_k, first_id, run_last, emit_w); run_k = 0; }
                 if (active) {
                     if (!run_k) { run_i = first + j; run_rb = rb; }
                     ++run_k;
                     run_last = row;
                 }
             }
-            if (run_k) emit_run(nd, base, list, T, tile_cols, run_rb, run_i, run_k, first_id, run_last, emit_w);
+            if (run_k) emit_run(nd, base, list, T, tile_cols, rb_shift, run_rb, run_i, run_k, first_id, run_last, emit_w);
         }
         uint32_t big = __ballot_sync(0xffffffffu, nd.l > kSmallL);
         while (big) {
@@ -536,8 +559,9 @@ __device__ __forceinline__ void enumerate_jobs(uint64_t lo, uint64_t hi, uint32_
             bn.last = 0; bn.loff = __shfl_sync(0xffffffffu, nd.loff, src); bn.up2 = bn.up3 = -1;
             const uint32_t bw = __shfl_sync(0xffffffffu, w, src);
             const uint64_t bbase = __shfl_sync(0xffffffffu, base, src);
+            const uint32_t bfid = __shfl_sync(0xffffffffu, fid, src);
             auto emit_b = [&](uint32_t key, const Job& jb, unsigned long long upd) { emit(key, jb, upd, bw); };
-            jobs_of_pattern_warp(bn, bbase, flat, loc, T, tile_cols, rb_shift, row_begin, row_end, lane, updates, emit_b);
+            jobs_of_pattern_warp(bn, bbase, flat, loc, T, tile_cols, rb_shift, row_begin, row_end, lane, bfid, updates, emit_b);
         }
     }
 }
@@ -558,7 +582,7 @@ __device__ __forceinline__ void block_slice(uint64_t p0, uint64_t p1, uint64_t& 
 
 __global__ void __launch_bounds__(kBucketThreads)
 k_job_hist_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
-                const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, const uint32_t* __restrict__ loc, uint32_t resident,
+                const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, const uint32_t* __restrict__ loc, const uint32_t* __restrict__ first_ids, uint32_t resident,
                 uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin, uint32_t row_end, uint32_t nkeys, uint32_t* __restrict__ blockhist,
                 unsigned long long* __restrict__ work, unsigned long long* __restrict__ total_updates) {
     __shared__ uint32_t s_hist[kSmemKeys];
@@ -570,7 +594,7 @@ k_job_hist_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const 
     block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
     const uint32_t* flat = flat_all + (resident ? noff[p0] : 0ull);  // the chunk's lists start at its first pattern
-    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, loc, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, loc, first_ids, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
                    [&](uint32_t key, const Job&, unsigned long long upd, uint32_t w) {
                        if (w == 0 || upd == 0) return;  // adds of 0 are skipped, but still counted in U
                        atomicAdd(&s_hist[key], 1u);
@@ -619,7 +643,7 @@ __global__ void k_block_offsets(uint32_t nkeys, uint32_t nblocks, const uint32_t
 
 __global__ void __launch_bounds__(kBucketThreads)
 k_job_fill_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
-                const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, const uint32_t* __restrict__ loc, uint32_t resident,
+                const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, const uint32_t* __restrict__ loc, const uint32_t* __restrict__ first_ids, uint32_t resident,
                 uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin, uint32_t row_end, uint32_t nkeys, const uint32_t* __restrict__ blockbase,
                 Job* __restrict__ jobs) {
     __shared__ uint32_t s_next[kSmemKeys];
@@ -631,7 +655,7 @@ k_job_fill_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const 
     block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
     const uint32_t* flat = flat_all + (resident ? noff[p0] : 0ull);  // the chunk's lists start at its first pattern
-    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, loc, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, loc, first_ids, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
                    [&](uint32_t key, Job jb, unsigned long long upd, uint32_t w) {
                        if (w == 0 || upd == 0) return;
                        const uint32_t slot = atomicAdd(&s_next[key], 1u);
@@ -643,7 +667,7 @@ k_job_fill_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const 
 // ---- job bucketing, large key spaces: global atomics (contention is low when keys are many) --
 __global__ void __launch_bounds__(kBucketThreads)
 k_job_hist(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
-           const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, const uint32_t* __restrict__ loc, uint32_t resident,
+           const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, const uint32_t* __restrict__ loc, const uint32_t* __restrict__ first_ids, uint32_t resident,
            uint32_t T, uint32_t tile_cols, uint32_t rb_shift,
            uint32_t row_begin, uint32_t row_end, uint32_t* __restrict__ hist, unsigned long long* __restrict__ work,
            unsigned long long* __restrict__ total_updates) {
@@ -652,7 +676,7 @@ k_job_hist(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint6
     block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
     const uint32_t* flat = flat_all + (resident ? noff[p0] : 0ull);  // the chunk's lists start at its first pattern
-    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, loc, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, loc, first_ids, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
                    [&](uint32_t key, const Job&, unsigned long long upd, uint32_t w) {
                        if (w == 0 || upd == 0) return;
                        atomicAdd(&hist[key], 1u);
@@ -664,7 +688,7 @@ k_job_hist(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint6
 
 __global__ void __launch_bounds__(kBucketThreads)
 k_job_fill(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
-           const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, const uint32_t* __restrict__ loc, uint32_t resident,
+           const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, const uint32_t* __restrict__ loc, const uint32_t* __restrict__ first_ids, uint32_t resident,
            uint32_t T, uint32_t tile_cols, uint32_t rb_shift,
            uint32_t row_begin, uint32_t row_end, uint32_t* __restrict__ cursor, Job* __restrict__ jobs) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -672,7 +696,7 @@ k_job_fill(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint6
     block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
     const uint32_t* flat = flat_all + (resident ? noff[p0] : 0ull);  // the chunk's lists start at its first pattern
-    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, loc, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, loc, first_ids, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
                    [&](uint32_t key, Job jb, unsigned long long upd, uint32_t w) {
                        if (w == 0 || upd == 0) return;
                        const uint32_t slot = atomicAdd(&cursor[key], 1u);
@@ -766,7 +790,7 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
         if (un.key != cur_key) {
             if (cur_key != kNone) {  // flush the finished tile
                 const uint32_t rb = cur_key / T, t = cur_key - rb * T;
-                const uint32_t row0 = rb << rb_shift, col0 = t * tile_cols;
+                const uint32_t row0 = rb << rb_shift, col0 = win_col0(win_hi(rb, rb_shift), t, tile_cols);
                 for (uint32_t r = 0; r < R; ++r) {
                     const uint32_t row = row0 + r;
                     if (row <= col0) continue;
@@ -790,7 +814,7 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
         if (threadIdx.x == 0) s_next_job = un.job_begin;
         __syncthreads();
         const uint32_t rb = un.key / T, t = un.key - rb * T;
-        const uint32_t row0 = rb << rb_shift, col0 = t * tile_cols;
+        const uint32_t row0 = rb << rb_shift, col0 = win_col0(win_hi(rb, rb_shift), t, tile_cols);
         // shared address of (row0, column 0); may lie below the tile when col0 > 0 — only in-tile ids occur
         const uint32_t base = tile_saddr - col0 * 4u;
         const uint32_t pad4 = (col0 + tile_cols + lane) * 4u;  // this lane's padding word, relative to `base`
@@ -907,7 +931,7 @@ struct kdbx_ctx {
     std::vector<std::pair<uint32_t, uint32_t>> levels;  // ranges of `order` per distinct num_samples, ascending
     // per chunk
     DevBuf flat, jobs, hist, work, bucket_off, cursor, ucount, uoff, units, counters, blockhist;
-    DevBuf tri, rowupd;
+    DevBuf tri, rowupd, first_id;
     uint64_t sum_l = 0, sum_n = 0;
     bool prepared = false;  // nodes / W / loc are valid for the loaded trie
 
@@ -988,8 +1012,11 @@ int make_plan(kdbx_ctx* ctx, Plan& pl) {
     pl.tile_cols = tc; pl.tile_rows = tr;
     pl.rb_shift = 0;
     while ((1u << pl.rb_shift) < tr) ++pl.rb_shift;
-    pl.T = N == 0 ? 1 : (N + tc - 1) / tc;
     pl.RB = N == 0 ? 1 : (N + tr - 1) / tr;
+    {   // windows per row block: enough to reach column 0 from the end of the last block (see win_hi)
+        const uint64_t hi_max = ((uint64_t)pl.RB * tr + 31u) & ~(uint64_t)31u;
+        pl.T = (uint32_t)std::max<uint64_t>(1, (hi_max + tc - 1) / tc);
+    }
     if ((uint64_t)pl.T * pl.RB >= ((uint64_t)1 << 31)) return ctx->fail(KDBX_ERR_ARG, "too many (row block, column tile) keys");
     pl.smem = (size_t)tr * (tc + 32) * 4;  // 32 padding words per row, see k_scatter_add
     pl.threads = ctx->cfg.scatter_threads ? ctx->cfg.scatter_threads : (pl.smem > 100 * 1024 ? 1024u : pl.smem > 48 * 1024 ? 512u : 256u);
@@ -1192,6 +1219,7 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         resident = (ctx->sum_n + 64) * 4 <= have / 5 * 2;
     }
     CK(ctx->flat.ensure(resident ? (ctx->sum_n + 64) * 4 : cap * 4));
+    if (resident) CK(ctx->first_id.ensure(ctx->P * 4));
     if (!resident) CK(ctx->jobs.ensure(cap * sizeof(Job)));
     CK(ctx->hist.ensure(((size_t)nkeys + 1) * 4)); CK(ctx->work.ensure(((size_t)nkeys + 1) * 8));
     CK(ctx->bucket_off.ensure(((size_t)nkeys + 1) * 4)); CK(ctx->cursor.ensure(((size_t)nkeys + 1) * 4));
@@ -1210,7 +1238,7 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
             if (e <= b) continue;
             k_expand_level<<<blocks_for((uint64_t)(e - b) * kLevelLanes, 256), 256, 0, st>>>(e - b, ctx->order.as<uint32_t>() + b, ctx->nodes.as<Node>(),
                                                                                               ctx->noff.as<uint64_t>(), ctx->loc.as<uint32_t>(),
-                                                                                              ctx->flat.as<uint32_t>());
+                                                                                              ctx->flat.as<uint32_t>(), ctx->first_id.as<uint32_t>());
             launches += 1;
         }
         cudaEvent_t b = ctx->event();
@@ -1247,26 +1275,26 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         CK(cudaMemsetAsync(ctx->work.p, 0, ((size_t)nkeys + 1) * 8, st));
         if (smem_buckets) {
             k_job_hist_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                                  ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
+                                                                  ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
                                                                   ctx->blockhist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates);
             k_key_totals<<<blocks_for((uint64_t)nkeys + 1, 128), 128, 0, st>>>(nkeys, wide_grid, ctx->blockhist.as<uint32_t>(), ctx->hist.as<uint32_t>());
             if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
             if (int rc = ensure_job_slots(ctx, resident, nkeys, jobs_cap)) return rc;
             k_block_offsets<<<blocks_for((uint64_t)nkeys * 32, 256), 256, 0, st>>>(nkeys, wide_grid, ctx->bucket_off.as<uint32_t>(), ctx->blockhist.as<uint32_t>());
             k_job_fill_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                                  ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
+                                                                  ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
                                                                   ctx->blockhist.as<uint32_t>(), ctx->jobs.as<Job>());
             launches += 2;
         } else {
             CK(cudaMemsetAsync(ctx->hist.p, 0, ((size_t)nkeys + 1) * 4, st));
             k_job_hist<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                   ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
+                                                   ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
                                                    ctx->hist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates);
             if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
             if (int rc = ensure_job_slots(ctx, resident, nkeys, jobs_cap)) return rc;
             CK(cudaMemcpyAsync(ctx->cursor.p, ctx->bucket_off.p, ((size_t)nkeys + 1) * 4, cudaMemcpyDeviceToDevice, st));
             k_job_fill<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                   ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
+                                                   ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
                                                    ctx->cursor.as<uint32_t>(), ctx->jobs.as<Job>());
         }
         k_unit_count<<<blocks_for((uint64_t)nkeys + 1, 256), 256, 0, st>>>(nkeys, ctx->hist.as<uint32_t>(), ctx->work.as<unsigned long long>(),
@@ -1408,7 +1436,7 @@ void kdbx_close(kdbx_ctx* ctx) {
     for (DevBuf* b : {&ctx->num_kmers, &ctx->parent, &ctx->n, &ctx->l, &ctx->last, &ctx->bits, &ctx->poff, &ctx->payload,
                       &ctx->nodes, &ctx->W, &ctx->loc, &ctx->loff, &ctx->noff, &ctx->coff, &ctx->bounds, &ctx->err_flag,
                       &ctx->cub_tmp, &ctx->order_in, &ctx->order, &ctx->keys_sorted, &ctx->level_start, &ctx->flat, &ctx->jobs, &ctx->hist, &ctx->work, &ctx->bucket_off, &ctx->cursor,
-                      &ctx->ucount, &ctx->uoff, &ctx->units, &ctx->counters, &ctx->blockhist, &ctx->tri, &ctx->rowupd,
+                      &ctx->ucount, &ctx->uoff, &ctx->units, &ctx->counters, &ctx->blockhist, &ctx->tri, &ctx->rowupd, &ctx->first_id,
                       &ctx->sp_cnt, &ctx->sp_counts, &ctx->sp_rowptr, &ctx->sp_col, &ctx->sp_val, &ctx->slot_off, &ctx->slots,
                       &ctx->q_off, &ctx->q_kmers, &ctx->q_keys, &ctx->q_keys2, &ctx->q_runkeys, &ctx->q_runcnt, &ctx->q_out})
         b->release();
