@@ -336,6 +336,7 @@ def main():
     barrier()
     wall0 = time.perf_counter()
     dev_ms = scat_ms = 0.0
+    per_step_ms = []
     launches = scat_launches = 0
     stage = {"prepare": 0.0, "expand": 0.0, "bucket": 0.0, "scatter": 0.0}
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
@@ -345,6 +346,7 @@ def main():
         ev[i][1].record()
         assert st.updates == U_rank
         dev_ms += st.ms_total
+        per_step_ms.append(round(st.ms_total, 3))
         scat_ms += st.ms_scatter
         launches += st.kernel_launches
         scat_launches += st.scatter_launches
@@ -434,6 +436,7 @@ def main():
                    "tile_rows": a.tile_rows, "scatter_threads": a.scatter_threads},
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "stage_ms_per_step": {k: v / a.steps for k, v in stage.items()}, "wall_ms_per_step": wall_ms / a.steps,
+        "library_ms_per_step": per_step_ms,
         "result_checksum": checksum,
     }))
     if dist is not None:

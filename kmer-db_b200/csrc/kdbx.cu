@@ -946,6 +946,16 @@ struct kdbx_ctx {
     std::vector<cudaEvent_t> events;
     size_t ev_used = 0;
 
+    // The W accumulation and the level-order expansion are one tiny launch per num_samples level
+    // (hundreds per step): they are captured once per staged trie into CUDA graphs and replayed, so
+    // the step does not depend on how fast the host can issue launches.
+    struct LevelGraph {
+        cudaGraphExec_t exec = nullptr;
+        const void* ptr[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        uint64_t P = 0, levels_hash = 0;
+        size_t nlevels = 0;
+    } g_push, g_expand;
+
     int fail(int code, const char* fmt, ...) {
         char buf[512];
         va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
@@ -1040,6 +1050,39 @@ int check_device_error(kdbx_ctx* ctx) {
     return KDBX_OK;
 }
 
+uint64_t levels_hash_of(const std::vector<std::pair<uint32_t, uint32_t>>& levels) {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (const auto& lv : levels) { h ^= ((uint64_t)lv.first << 32) | lv.second; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 29; }
+    return h;
+}
+
+// Replays `record` (kernel launches on ctx->stream only) from a graph; re-captures when the staged trie,
+// its levels or any of the buffers the launches point at have changed.
+template <class Record>
+int launch_level_graph(kdbx_ctx* ctx, kdbx_ctx::LevelGraph& g, std::initializer_list<const void*> ptrs, Record&& record) {
+    kdbx_ctx::LevelGraph want;
+    size_t i = 0;
+    for (const void* p : ptrs) want.ptr[i++] = p;
+    want.P = ctx->P; want.nlevels = ctx->levels.size(); want.levels_hash = levels_hash_of(ctx->levels);
+    const bool same = g.exec && g.P == want.P && g.nlevels == want.nlevels && g.levels_hash == want.levels_hash &&
+                      std::memcmp(g.ptr, want.ptr, sizeof want.ptr) == 0;
+    if (!same) {
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        record();
+        CK(cudaStreamEndCapture(ctx->stream, &graph));
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return ctx->fail(KDBX_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+        want.exec = exec;
+        g = want;
+    }
+    CK(cudaGraphLaunch(g.exec, ctx->stream));
+    return KDBX_OK;
+}
+
 // scans + node packing + W + gamma decode.  Leaves sum_l / sum_n on the host (one sync).
 int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
     const uint64_t P = ctx->P;
@@ -1111,13 +1154,19 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
             end = b;
         }
         // levels[k] = (begin of key v_k, end); built for ascending v, so begin decreases
-        for (size_t k = levels.size(); k-- > 0;) {
-            const uint32_t b = levels[k].first, e = levels[k].second;
-            if (e <= b) continue;
-            k_push_level<<<blocks_for(e - b, 256), 256, 0, st>>>(e - b, ctx->order.as<uint32_t>() + b, ctx->parent.as<int64_t>(),
-                                                                  ctx->W.as<uint32_t>());
-            launches += 1;
+        uint32_t n_launch = 0;
+        for (size_t k = levels.size(); k-- > 0;) if (levels[k].second > levels[k].first) ++n_launch;
+        if (n_launch) {
+            if (int rc = launch_level_graph(ctx, ctx->g_push, {ctx->order.p, ctx->parent.p, ctx->W.p}, [&] {
+                    for (size_t k = levels.size(); k-- > 0;) {
+                        const uint32_t b = levels[k].first, e = levels[k].second;
+                        if (e <= b) continue;
+                        k_push_level<<<blocks_for(e - b, 256), 256, 0, st>>>(e - b, ctx->order.as<uint32_t>() + b, ctx->parent.as<int64_t>(),
+                                                                              ctx->W.as<uint32_t>());
+                    }
+                })) return rc;
         }
+        launches += n_launch;
     }
     CK(ctx->loc.ensure((ctx->sum_l + 32) * 4));
     CK(cudaStreamWaitEvent(st, ctx->ev_up_payload, 0));  // the payload may still be on its way (second H2D stream)
@@ -1233,14 +1282,20 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     float ms_expand_all = 0.f;
     if (resident) {
         cudaEvent_t a = ctx->event();
-        for (size_t k = 0; k < ctx->levels.size(); ++k) {  // ascending num_samples: parents first
-            const uint32_t b = ctx->levels[k].first, e = ctx->levels[k].second;
-            if (e <= b) continue;
-            k_expand_level<<<blocks_for((uint64_t)(e - b) * kLevelLanes, 256), 256, 0, st>>>(e - b, ctx->order.as<uint32_t>() + b, ctx->nodes.as<Node>(),
-                                                                                              ctx->noff.as<uint64_t>(), ctx->loc.as<uint32_t>(),
-                                                                                              ctx->flat.as<uint32_t>(), ctx->first_id.as<uint32_t>());
-            launches += 1;
+        uint32_t n_launch = 0;
+        for (const auto& lv : ctx->levels) if (lv.second > lv.first) ++n_launch;
+        if (n_launch) {
+            if (int rc = launch_level_graph(ctx, ctx->g_expand, {ctx->order.p, ctx->nodes.p, ctx->noff.p, ctx->loc.p, ctx->flat.p, ctx->first_id.p}, [&] {
+                    for (size_t k = 0; k < ctx->levels.size(); ++k) {  // ascending num_samples: parents first
+                        const uint32_t b = ctx->levels[k].first, e = ctx->levels[k].second;
+                        if (e <= b) continue;
+                        k_expand_level<<<blocks_for((uint64_t)(e - b) * kLevelLanes, 256), 256, 0, st>>>(e - b, ctx->order.as<uint32_t>() + b, ctx->nodes.as<Node>(),
+                                                                                                          ctx->noff.as<uint64_t>(), ctx->loc.as<uint32_t>(),
+                                                                                                          ctx->flat.as<uint32_t>(), ctx->first_id.as<uint32_t>());
+                    }
+                })) return rc;
         }
+        launches += n_launch;
         cudaEvent_t b = ctx->event();
         CK(cudaStreamSynchronize(st));
         ms_expand_all = elapsed(a, b);
@@ -1441,6 +1496,8 @@ void kdbx_close(kdbx_ctx* ctx) {
                       &ctx->q_off, &ctx->q_kmers, &ctx->q_keys, &ctx->q_keys2, &ctx->q_runkeys, &ctx->q_runcnt, &ctx->q_out})
         b->release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    if (ctx->g_push.exec) cudaGraphExecDestroy(ctx->g_push.exec);
+    if (ctx->g_expand.exec) cudaGraphExecDestroy(ctx->g_expand.exec);
     if (ctx->up_stream) { cudaStreamSynchronize(ctx->up_stream); cudaStreamDestroy(ctx->up_stream); }
     for (cudaEvent_t e : {ctx->ev_up_begin, ctx->ev_up_hdr, ctx->ev_up_payload}) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -24,6 +24,8 @@ for step in "$@"; do
     scale) for n in ${SCALE_NS:-2}; do for mode in weak strong; do timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 5 --warmup 3 --scaling $mode > "$OUT/scale_${mode}_$n.json" 2> "$OUT/scale_${mode}_$n.err"; echo "scale $mode $n rc=$?" | tee -a "$OUT/summary.txt"; done; done;;
     tests_build) timeout 900 python -m pytest tests/test_gpu_build.py -m gpu -x -q > "$OUT/pytest_build.log" 2>&1; echo "pytest_build rc=$?" | tee -a "$OUT/summary.txt";;
     bench_shard) for sh in ${SHARDS:-1/2 7/8}; do tag=$(echo $sh | tr / _); timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --emulate-shard $sh > "$OUT/bench_shard_$tag.json" 2> "$OUT/bench_shard_$tag.err"; echo "bench_shard $sh rc=$?" | tee -a "$OUT/summary.txt"; done;;
+    ncu_stages2) timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:k_job_hist|k_job_fill|k_decode_locals" -s 3 -c 3 -f -o "$OUT/stages2_cfg2" python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_stages2.out" 2>&1; echo "ncu_stages2 rc=$?" | tee -a "$OUT/summary.txt";;
+    bench2) timeout 900 python bench.py --no-cpu-baseline > "$OUT/bench2.json" 2> "$OUT/bench2.err"; echo "bench2 rc=$?" | tee -a "$OUT/summary.txt";;
     test_multi) timeout 600 python -m pytest tests -m gpu -x -q -k "multi_gpu or sharding" > "$OUT/pytest_multi.log" 2>&1; echo "pytest_multi rc=$?" | tee -a "$OUT/summary.txt";;
     modes) timeout 1500 python tools/bench_modes.py --out-dir /tmp/kdbx_modes > "$OUT/modes.jsonl" 2> "$OUT/modes.err"; echo "modes rc=$?" | tee -a "$OUT/summary.txt";;
     *) echo "unknown step $step";;
