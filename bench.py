@@ -66,6 +66,7 @@ def parse_args():
     ap.add_argument("--unit-updates", type=int, default=0)
     ap.add_argument("--tile-rows", type=int, default=0)
     ap.add_argument("--scatter-threads", type=int, default=0)
+    ap.add_argument("--rows-as-lanes", type=int, default=0, help="kdbx_config::rows_as_lanes (0 = default, 33 = never)")
     ap.add_argument("--chunked-lists", action="store_true", help="force the chunked parent-chain expansion")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
                     help="N>1: 'weak' = every rank owns a configs[1]-sized shard of an N-times larger database; "
@@ -263,7 +264,7 @@ def main():
     N0, P0, U0 = int(tot.num_samples), int(tot.num_patterns), int(tot.updates)
     chunk_ids = a.chunk_ids
     ctx = kdbx.Context(device=local_rank, chunk_ids=chunk_ids, tile_cols=a.tile_cols, unit_updates=a.unit_updates,
-                       tile_rows=a.tile_rows, scatter_threads=a.scatter_threads, flags=(kdbx.FLAG_CHUNKED_LISTS if a.chunked_lists else 0) | kdbx.FLAG_ASYNC_UPLOAD)
+                       tile_rows=a.tile_rows, scatter_threads=a.scatter_threads, rows_as_lanes=a.rows_as_lanes, flags=(kdbx.FLAG_CHUNKED_LISTS if a.chunked_lists else 0) | kdbx.FLAG_ASYNC_UPLOAD)
     scaling = a.scaling
     full_ref = None
     t_shard = 0.0
@@ -433,7 +434,7 @@ def main():
                    "l2_policy": "inputs (trie %.1f GB + per-chunk lists) exceed the 126 MB L2; no explicit flush" %
                                 ((P * 40 + int(tot.payload_bytes)) / 1e9),
                    "chunk_ids": chunk_ids, "tile_cols": a.tile_cols, "unit_updates": a.unit_updates,
-                   "tile_rows": a.tile_rows, "scatter_threads": a.scatter_threads},
+                   "tile_rows": a.tile_rows, "scatter_threads": a.scatter_threads, "rows_as_lanes": a.rows_as_lanes},
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "stage_ms_per_step": {k: v / a.steps for k, v in stage.items()}, "wall_ms_per_step": wall_ms / a.steps,
         "library_ms_per_step": per_step_ms,

@@ -762,11 +762,18 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const uint4* p) {
 }
 
 constexpr uint32_t kJobBatch = 8;  // jobs a warp claims at once (16 lanes load them as uint4 halves)
+constexpr uint32_t kRowPad = 33;   // padding words after every accumulator row (see k_scatter_add)
+// A job whose run has at least this many rows takes its shared ids one at a time with the ROWS on
+// the lanes (one conflict-free wavefront per id, k of 32 lanes busy) instead of 32 ids at a time with
+// one instruction per row (k instructions per 32 ids, 1.9 wavefronts each on gappy sorted ids: the
+// same residue modulo 32 recurs within a slice).  Break-even is k = 32 / 1.9 (profiles/r01_scatter_modes.txt).
+constexpr uint32_t kRowsAsLanes = 18;
 
 __global__ void __launch_bounds__(1024)
 k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_units_ptr, const Job* __restrict__ jobs,
               const uint32_t* __restrict__ flat_all, const uint64_t* __restrict__ flat_shift, uint32_t* __restrict__ tri,
-              uint64_t tri_base, uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t* __restrict__ unit_counter) {
+              uint64_t tri_base, uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t rows_as_lanes,
+              uint32_t* __restrict__ unit_counter) {
     extern __shared__ uint4 tile4[];
     const uint32_t* flat = flat_all + (flat_shift ? *flat_shift : 0ull);
     uint32_t* tile = reinterpret_cast<uint32_t*>(tile4);
@@ -775,8 +782,11 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
     const uint32_t n_units = *n_units_ptr;
     const uint32_t R = 1u << rb_shift;
     // every accumulator row is followed by 32 padding words: lanes beyond the end of an id slice
-    // reduce into them (one bank each), which keeps the inner loop free of branches
-    const uint32_t stride = tile_cols + 32u;
+    // reduce into them (one bank each), which keeps the inner loop free of branches.  One more word
+    // makes the row stride odd modulo the 32 banks: cell (row, col) lives in bank (row + col) mod 32, so
+    // 32 lanes hitting 32 different ROWS at one column are as conflict-free as 32 consecutive columns
+    // of one row — which the rows-as-lanes pass below relies on.
+    const uint32_t stride = tile_cols + kRowPad;
     const uint32_t tile_saddr = (uint32_t)__cvta_generic_to_shared(tile);
     constexpr uint32_t kNone = 0xFFFFFFFFu;
     uint32_t cur_key = kNone;  // key whose partial sums the tile holds
@@ -805,7 +815,7 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
                 __syncthreads();
             }
             if (!done) {
-                const uint32_t n4 = (R * stride) >> 2;
+                const uint32_t n4 = (R * stride + 3u) >> 2;
                 for (uint32_t c = threadIdx.x; c < n4; c += blockDim.x) tile4[c] = make_uint4(0, 0, 0, 0);
             }
             cur_key = un.key;
@@ -840,6 +850,31 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
                 }
                 // ids seen by every row of the job: [a, min(b, A0))
                 const uint32_t bc = min(b, A0);
+                if (k >= rows_as_lanes) {
+                    // rows on the lanes: lane j < k owns row j; every shared id is broadcast and all rows
+                    // reduce at once into distinct banks
+                    const bool mine = lane < k;
+                    uint32_t x = 0;
+                    if (a < bc && lane < bc - a) x = ldg_nc_u32(list + a + lane) * 4u;
+                    for (uint32_t c = a; c < bc; c += 32) {
+                        const uint32_t rem = min(32u, bc - c);
+                        uint32_t nx = 0;   // next slice in flight while this one is reduced
+                        if (c + 32 < bc && lane < bc - (c + 32)) nx = ldg_nc_u32(list + c + 32 + lane) * 4u;
+                        if (rem == 32) {
+#pragma unroll
+                            for (uint32_t i = 0; i < 32; ++i) {
+                                const uint32_t xi = __shfl_sync(0xffffffffu, x, i);
+                                if (mine) red_shared_add(rowoff + xi, w);
+                            }
+                        } else {
+                            for (uint32_t i = 0; i < rem; ++i) {
+                                const uint32_t xi = __shfl_sync(0xffffffffu, x, i);
+                                if (mine) red_shared_add(rowoff + xi, w);
+                            }
+                        }
+                        x = nx;
+                    }
+                } else
                 for (uint32_t c = a; c < bc; c += 128) {
                     const uint32_t rem = bc - c;
                     const uint32_t* p = list + c + lane;
@@ -1015,10 +1050,10 @@ int make_plan(kdbx_ctx* ctx, Plan& pl) {
     uint32_t tr = ctx->cfg.tile_rows;
     if (tr == 0) {
         tr = 32;
-        while (tr > 1 && (size_t)tr * (tc + 32) * 4 > kMaxTileBytes) tr >>= 1;
+        while (tr > 1 && (size_t)tr * (tc + kRowPad) * 4 > kMaxTileBytes) tr >>= 1;
     }
     if (tr == 0 || tr > 32 || (tr & (tr - 1))) return ctx->fail(KDBX_ERR_ARG, "tile_rows must be a power of two <= 32");
-    if ((size_t)tr * (tc + 32) * 4 > kMaxTileBytes) return ctx->fail(KDBX_ERR_ARG, "tile_rows x tile_cols too large for shared memory");
+    if ((size_t)tr * (tc + kRowPad) * 4 > kMaxTileBytes) return ctx->fail(KDBX_ERR_ARG, "tile_rows x tile_cols too large for shared memory");
     pl.tile_cols = tc; pl.tile_rows = tr;
     pl.rb_shift = 0;
     while ((1u << pl.rb_shift) < tr) ++pl.rb_shift;
@@ -1028,7 +1063,7 @@ int make_plan(kdbx_ctx* ctx, Plan& pl) {
         pl.T = (uint32_t)std::max<uint64_t>(1, (hi_max + tc - 1) / tc);
     }
     if ((uint64_t)pl.T * pl.RB >= ((uint64_t)1 << 31)) return ctx->fail(KDBX_ERR_ARG, "too many (row block, column tile) keys");
-    pl.smem = (size_t)tr * (tc + 32) * 4;  // 32 padding words per row, see k_scatter_add
+    pl.smem = ((size_t)tr * (tc + kRowPad) * 4 + 15) & ~(size_t)15;  // padding words per row, see k_scatter_add
     pl.threads = ctx->cfg.scatter_threads ? ctx->cfg.scatter_threads : (pl.smem > 100 * 1024 ? 1024u : pl.smem > 48 * 1024 ? 512u : 256u);
     if (pl.threads < 32 || pl.threads > 1024 || (pl.threads & 31)) return ctx->fail(KDBX_ERR_ARG, "scatter_threads must be a multiple of 32 in [32, 1024]");
     // a unit flushes at most tile_rows x tile_cols cells with global reductions: keep >= 64 updates per cell
@@ -1361,7 +1396,8 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         e.c = ctx->event();
         k_scatter_add<<<scatter_grid, pl.threads, smem, st>>>(ctx->units.as<Unit>(), ctx->uoff.as<uint32_t>() + nkeys, ctx->jobs.as<Job>(),
                                                               ctx->flat.as<uint32_t>(), resident ? ctx->noff.as<uint64_t>() + p0 : nullptr, d_out, tri_base,
-                                                              pl.T, pl.tile_cols, pl.rb_shift, d_unit_counter);
+                                                              pl.T, pl.tile_cols, pl.rb_shift, ctx->cfg.rows_as_lanes ? ctx->cfg.rows_as_lanes : kRowsAsLanes,
+                                                              d_unit_counter);
         e.d = ctx->event();
         launches += 8;
         s.scatter_launches += 1;
