@@ -66,7 +66,6 @@ def parse_args():
     ap.add_argument("--unit-updates", type=int, default=0)
     ap.add_argument("--tile-rows", type=int, default=0)
     ap.add_argument("--scatter-threads", type=int, default=0)
-    ap.add_argument("--rows-as-lanes", type=int, default=0, help="kdbx_config::rows_as_lanes (0 = default, 33 = never)")
     ap.add_argument("--chunked-lists", action="store_true", help="force the chunked parent-chain expansion")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
                     help="N>1: 'weak' = every rank owns a configs[1]-sized shard of an N-times larger database; "
@@ -108,12 +107,16 @@ def get_workload(kdbx, a, samples, clusters, pinned, rank=0, barrier=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).
+    nvidia-smi is started well before the timed region (its NVML start-up holds driver locks for tens of
+    milliseconds and stalled whole steps when it began inside the region); only samples taken between
+    begin() and stop() are reported."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.lines = []
+        self.t_begin = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                        "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -124,11 +127,21 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def wait_first_sample(self, timeout=20.0):
+        t0 = time.perf_counter()
+        while self.p and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
+    def begin(self):
+        self.t_begin = time.perf_counter()
 
     def stop(self):
+        t_end = time.perf_counter()
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)  # one more period, so that a short region still gets its closing sample
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -136,7 +149,10 @@ class ClockSampler:
             self.p.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        for ts, ln in self.lines:
+            if ts < t0 or ts > t_end + 0.12:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -264,7 +280,7 @@ def main():
     N0, P0, U0 = int(tot.num_samples), int(tot.num_patterns), int(tot.updates)
     chunk_ids = a.chunk_ids
     ctx = kdbx.Context(device=local_rank, chunk_ids=chunk_ids, tile_cols=a.tile_cols, unit_updates=a.unit_updates,
-                       tile_rows=a.tile_rows, scatter_threads=a.scatter_threads, rows_as_lanes=a.rows_as_lanes, flags=(kdbx.FLAG_CHUNKED_LISTS if a.chunked_lists else 0) | kdbx.FLAG_ASYNC_UPLOAD)
+                       tile_rows=a.tile_rows, scatter_threads=a.scatter_threads, flags=(kdbx.FLAG_CHUNKED_LISTS if a.chunked_lists else 0) | kdbx.FLAG_ASYNC_UPLOAD)
     scaling = a.scaling
     full_ref = None
     t_shard = 0.0
@@ -315,6 +331,7 @@ def main():
         return int(t.item())
 
     # ---- device-resident leg -------------------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # started now, so that it is settled before the timed steps
     st = step()  # one untimed call establishes this rank's share of U (and warms the allocator)
     for _ in range(max(0, a.warmup - 1)):
         st = step()
@@ -333,8 +350,11 @@ def main():
         lo, hi = kdbx.tri_cells(rank * N0), kdbx.tri_cells((rank + 1) * N0)
         assert torch.equal(mine[lo:hi], d_out[lo:hi]) and int(mine.to(torch.int64).sum().item()) == int(mine[lo:hi].to(torch.int64).sum().item())
         del mine
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.wait_first_sample()
     barrier()
+    if sampler:
+        sampler.begin()
     wall0 = time.perf_counter()
     dev_ms = scat_ms = 0.0
     per_step_ms = []
@@ -434,7 +454,7 @@ def main():
                    "l2_policy": "inputs (trie %.1f GB + per-chunk lists) exceed the 126 MB L2; no explicit flush" %
                                 ((P * 40 + int(tot.payload_bytes)) / 1e9),
                    "chunk_ids": chunk_ids, "tile_cols": a.tile_cols, "unit_updates": a.unit_updates,
-                   "tile_rows": a.tile_rows, "scatter_threads": a.scatter_threads, "rows_as_lanes": a.rows_as_lanes},
+                   "tile_rows": a.tile_rows, "scatter_threads": a.scatter_threads},
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "stage_ms_per_step": {k: v / a.steps for k, v in stage.items()}, "wall_ms_per_step": wall_ms / a.steps,
         "library_ms_per_step": per_step_ms,

@@ -56,9 +56,7 @@ typedef struct kdbx_config {
     uint64_t query_batch_kmers;  /* kdbx_new2all_batch: k-mers per device pass; 0 = 2^28      */
     uint32_t tile_rows;          /* matrix rows per accumulator tile (power of two <= 32); 0 = default */
     uint32_t scatter_threads;    /* threads per CTA of the scatter-add kernel; 0 = default     */
-    uint32_t rows_as_lanes;      /* a job with at least this many rows reduces with its rows on the
-                                    lanes (one id per instruction); 0 = default (18), 33 = never  */
-    uint32_t reserved;
+    uint64_t reserved[1];
 } kdbx_config;
 
 #define KDBX_FLAG_NONE 0u

@@ -762,18 +762,17 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const uint4* p) {
 }
 
 constexpr uint32_t kJobBatch = 8;  // jobs a warp claims at once (16 lanes load them as uint4 halves)
-constexpr uint32_t kRowPad = 33;   // padding words after every accumulator row (see k_scatter_add)
-// A job whose run has at least this many rows takes its shared ids one at a time with the ROWS on
-// the lanes (one conflict-free wavefront per id, k of 32 lanes busy) instead of 32 ids at a time with
-// one instruction per row (k instructions per 32 ids, 1.9 wavefronts each on gappy sorted ids: the
-// same residue modulo 32 recurs within a slice).  Break-even is k = 32 / 1.9 (profiles/r01_scatter_modes.txt).
-constexpr uint32_t kRowsAsLanes = 18;
+constexpr uint32_t kRowPad = 32;   // padding words after every accumulator row (see k_scatter_add)
+// Tried and dropped (profiles/r01_scatter_rows_as_lanes.txt): taking the shared ids one at a time with the
+// job's ROWS on the lanes (row stride odd modulo 32, so every instruction is one conflict-free wavefront with
+// k of 32 lanes busy).  The wavefront count falls by a third on config 2, the time rises (84 -> 112 ms at
+// k >= 18): a shared-memory reduction costs ~1 clock per INSTRUCTION plus ~0.7 per wavefront, and this
+// form issues 32/k times more instructions.
 
 __global__ void __launch_bounds__(1024)
 k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_units_ptr, const Job* __restrict__ jobs,
               const uint32_t* __restrict__ flat_all, const uint64_t* __restrict__ flat_shift, uint32_t* __restrict__ tri,
-              uint64_t tri_base, uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t rows_as_lanes,
-              uint32_t* __restrict__ unit_counter) {
+              uint64_t tri_base, uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t* __restrict__ unit_counter) {
     extern __shared__ uint4 tile4[];
     const uint32_t* flat = flat_all + (flat_shift ? *flat_shift : 0ull);
     uint32_t* tile = reinterpret_cast<uint32_t*>(tile4);
@@ -782,10 +781,7 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
     const uint32_t n_units = *n_units_ptr;
     const uint32_t R = 1u << rb_shift;
     // every accumulator row is followed by 32 padding words: lanes beyond the end of an id slice
-    // reduce into them (one bank each), which keeps the inner loop free of branches.  One more word
-    // makes the row stride odd modulo the 32 banks: cell (row, col) lives in bank (row + col) mod 32, so
-    // 32 lanes hitting 32 different ROWS at one column are as conflict-free as 32 consecutive columns
-    // of one row — which the rows-as-lanes pass below relies on.
+    // reduce into them (one bank each), which keeps the inner loop free of branches
     const uint32_t stride = tile_cols + kRowPad;
     const uint32_t tile_saddr = (uint32_t)__cvta_generic_to_shared(tile);
     constexpr uint32_t kNone = 0xFFFFFFFFu;
@@ -850,31 +846,6 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
                 }
                 // ids seen by every row of the job: [a, min(b, A0))
                 const uint32_t bc = min(b, A0);
-                if (k >= rows_as_lanes) {
-                    // rows on the lanes: lane j < k owns row j; every shared id is broadcast and all rows
-                    // reduce at once into distinct banks
-                    const bool mine = lane < k;
-                    uint32_t x = 0;
-                    if (a < bc && lane < bc - a) x = ldg_nc_u32(list + a + lane) * 4u;
-                    for (uint32_t c = a; c < bc; c += 32) {
-                        const uint32_t rem = min(32u, bc - c);
-                        uint32_t nx = 0;   // next slice in flight while this one is reduced
-                        if (c + 32 < bc && lane < bc - (c + 32)) nx = ldg_nc_u32(list + c + 32 + lane) * 4u;
-                        if (rem == 32) {
-#pragma unroll
-                            for (uint32_t i = 0; i < 32; ++i) {
-                                const uint32_t xi = __shfl_sync(0xffffffffu, x, i);
-                                if (mine) red_shared_add(rowoff + xi, w);
-                            }
-                        } else {
-                            for (uint32_t i = 0; i < rem; ++i) {
-                                const uint32_t xi = __shfl_sync(0xffffffffu, x, i);
-                                if (mine) red_shared_add(rowoff + xi, w);
-                            }
-                        }
-                        x = nx;
-                    }
-                } else
                 for (uint32_t c = a; c < bc; c += 128) {
                     const uint32_t rem = bc - c;
                     const uint32_t* p = list + c + lane;
@@ -1396,8 +1367,7 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         e.c = ctx->event();
         k_scatter_add<<<scatter_grid, pl.threads, smem, st>>>(ctx->units.as<Unit>(), ctx->uoff.as<uint32_t>() + nkeys, ctx->jobs.as<Job>(),
                                                               ctx->flat.as<uint32_t>(), resident ? ctx->noff.as<uint64_t>() + p0 : nullptr, d_out, tri_base,
-                                                              pl.T, pl.tile_cols, pl.rb_shift, ctx->cfg.rows_as_lanes ? ctx->cfg.rows_as_lanes : kRowsAsLanes,
-                                                              d_unit_counter);
+                                                              pl.T, pl.tile_cols, pl.rb_shift, d_unit_counter);
         e.d = ctx->event();
         launches += 8;
         s.scatter_launches += 1;

@@ -68,9 +68,7 @@ def test_random_tries_bit_exact(libs, oracle, seed):
                                  dict(tile_rows=1), dict(tile_rows=8, tile_cols=64), dict(tile_rows=16, scatter_threads=128),
                                  dict(tile_rows=2, tile_cols=160, scatter_threads=1024, chunk_ids=9000),
                                  dict(flags=1), dict(flags=1, chunk_ids=4096, tile_cols=96), dict(flags=1, tile_rows=4, unit_updates=50),
-                                 dict(flags=2), dict(flags=3, chunk_ids=4096),
-                                 dict(rows_as_lanes=33), dict(rows_as_lanes=1), dict(rows_as_lanes=2, tile_cols=64, tile_rows=8),
-                                 dict(rows_as_lanes=5, tile_rows=16, scatter_threads=128)])
+                                 dict(flags=2), dict(flags=3, chunk_ids=4096)])
 def test_schedule_knobs_do_not_change_results(libs, oracle, cfg):
     """column tiles (T>1), row blocks of 1..32 rows, many chunks, tiny / huge work units: same bits."""
     rng = np.random.default_rng(7)

@@ -26,7 +26,6 @@ for step in "$@"; do
     bench_shard) for sh in ${SHARDS:-1/2 7/8}; do tag=$(echo $sh | tr / _); timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --emulate-shard $sh > "$OUT/bench_shard_$tag.json" 2> "$OUT/bench_shard_$tag.err"; echo "bench_shard $sh rc=$?" | tee -a "$OUT/summary.txt"; done;;
     ncu_stages2) timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:k_job_hist|k_job_fill|k_decode_locals" -s 3 -c 3 -f -o "$OUT/stages2_cfg2" python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_stages2.out" 2>&1; echo "ncu_stages2 rc=$?" | tee -a "$OUT/summary.txt";;
     bench2) timeout 900 python bench.py --no-cpu-baseline > "$OUT/bench2.json" 2> "$OUT/bench2.err"; echo "bench2 rc=$?" | tee -a "$OUT/summary.txt";;
-    bench_modes_ab) for ral in ${RALS:-33 12 16 20 24}; do timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --rows-as-lanes $ral > "$OUT/bench_ral_$ral.json" 2> "$OUT/bench_ral_$ral.err"; echo "bench_ral $ral rc=$?" | tee -a "$OUT/summary.txt"; done;;
     test_multi) timeout 600 python -m pytest tests -m gpu -x -q -k "multi_gpu or sharding" > "$OUT/pytest_multi.log" 2>&1; echo "pytest_multi rc=$?" | tee -a "$OUT/summary.txt";;
     modes) timeout 1500 python tools/bench_modes.py --out-dir /tmp/kdbx_modes > "$OUT/modes.jsonl" 2> "$OUT/modes.err"; echo "modes rc=$?" | tee -a "$OUT/summary.txt";;
     *) echo "unknown step $step";;
