@@ -76,10 +76,7 @@ struct U32AsU64 {
 // expansion can copy a parent's list with 128-bit loads and stores
 struct ListSlots {
     const uint32_t* p; uint64_t n;
-    const uint32_t* only;  // when set: slots only for the patterns flagged here (those with children)
-    __host__ __device__ uint64_t operator()(uint64_t i) const {
-        return (i < n && (!only || only[i])) ? (uint64_t)((p[i] + 3u) & ~3u) : 0ull;
-    }
+    __host__ __device__ uint64_t operator()(uint64_t i) const { return i < n ? (uint64_t)((p[i] + 3u) & ~3u) : 0ull; }
 };
 struct PayloadWords {
     const uint32_t* bits; uint64_t n;
@@ -130,12 +127,6 @@ __global__ void k_build_nodes(uint64_t P, const int64_t* __restrict__ parent, co
 // patterns are radix-sorted by n (descending) and every level pushes its finished sums to the
 // parents in one launch.  (A per-node walk to the root with atomics was 80 % of the prepare
 // stage: the ancestors near the roots are hit by millions of serialized L2 atomics.)
-__global__ void k_mark_parents(uint64_t P, const int64_t* __restrict__ parent, uint32_t* __restrict__ has_child) {
-    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
-    const int64_t q = parent[p];
-    if (q >= 0 && q < (int64_t)p) has_child[q] = 1u;   // benign race: everyone writes 1
-}
 __global__ void k_iota(uint64_t P, uint32_t* __restrict__ out) {
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < P) out[p] = (uint32_t)p;
@@ -350,33 +341,30 @@ __global__ void k_expand(uint64_t p0, uint64_t p1, const Node* __restrict__ node
     }
 }
 
-// Resident expansion (used when the lists fit in HBM).  A pattern's full list is its parent's full
-// list followed by its own local ids, and a job only ever reads list(parent) and the pattern's own
-// locals (see Job) — so full lists are materialised ONLY for patterns that have children (30 % of
-// the ids at config 2), each by two contiguous copies.  The patterns of one num_samples level have
-// their parents on earlier levels (n_parent < n): one launch per level, ascending; no pointer chasing.
-// Every pattern also gets the first id of its full list (the job enumeration places columns with it).
+// Resident expansion (used when the full lists of ALL patterns fit in HBM, 4 * sum n bytes): a
+// pattern's full list is its parent's full list followed by its own local ids, so the patterns of
+// one num_samples level — whose parents all sit on earlier levels, n_parent < n — are expanded by
+// two contiguous copies each.  One launch per level, ascending; no pointer chasing at all.
 constexpr uint32_t kLevelLanes = 8;
 __global__ void k_expand_level(uint32_t count, const uint32_t* __restrict__ order, const Node* __restrict__ nodes,
-                               const uint64_t* __restrict__ ioff, const uint32_t* __restrict__ has_child,
-                               const uint32_t* __restrict__ loc, uint32_t* flat, uint32_t* first_id) {
+                               const uint64_t* __restrict__ noff, const uint32_t* __restrict__ loc, uint32_t* flat, uint32_t* first_id) {
     const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / kLevelLanes;
     const uint32_t sub = threadIdx.x & (kLevelLanes - 1);
-    bool have = gid < count;
+    const bool have = gid < count;
     Node nd; nd.parent = -1; nd.n = 0; nd.l = 0; nd.last = 0; nd.loff = 0; nd.up2 = nd.up3 = -1;
     uint32_t* dst = flat;
     if (have) {
         const uint32_t p = order[gid];
         nd = nodes[p];
+        dst = flat + noff[p];
+        // first id of the full list (the job enumeration places a pattern's columns with it)
         if (sub == 0 && nd.n) first_id[p] = nd.parent >= 0 ? first_id[nd.parent] : loc[nd.loff];
-        have = has_child[p] != 0;
-        dst = flat + ioff[p];
     }
     const uint32_t npar = nd.n - nd.l;
     if (have && nd.parent >= 0) {
         // both lists start 16-byte aligned (ListSlots); the copy may run up to 3 ids past the parent's
         // list — still inside this pattern's slots, overwritten by its own ids below
-        const uint4* src = reinterpret_cast<const uint4*>(flat + ioff[nd.parent]);
+        const uint4* src = reinterpret_cast<const uint4*>(flat + noff[nd.parent]);
         uint4* d4 = reinterpret_cast<uint4*>(dst);
         const uint32_t n4 = (npar + 3u) >> 2;
         for (uint32_t j = sub; j < n4; j += kLevelLanes) d4[j] = src[j];
@@ -395,25 +383,14 @@ __global__ void k_expand_level(uint32_t count, const uint32_t* __restrict__ orde
 // feeds k accumulator rows, which is what makes the scatter kernel shared-memory-bound instead
 // of id-stream-bound (the reference re-reads the list once per row, src/similarity_calculator.cpp:
 // 214-231; so did the first three versions of this file).
-// The pattern's full list is read as two segments: positions [0, n_split) from the flat array at offA,
-// positions [n_split, n) from the decoded local ids at offB.  Resident mode: offA = list(parent),
-// n_split = n - l, offB = the pattern's own locals.  Chunked mode: offA = the pattern's own expanded
-// list, n_split = n.
 struct __align__(32) Job {
-    uint32_t offA;     // low 32 bits of the offset into the flat id array
+    uint32_t off;  // start of the pattern's full list in the chunk's flat id array (low 32 bits)
     uint32_t a, b;
     uint32_t A0;
-    uint32_t k_hi;     // k | offA_hi << 8 | offB_hi << 20   (offsets < 2^44 ids)
-    uint32_t w;        // (uint32_t) W_p
-    uint32_t offB;     // low 32 bits of the offset into the local-id array
-    uint32_t n_split;
-};
-struct Seg2 {   // the two segments of one pattern's list
-    const uint32_t* pA;   // flat + offA
-    const uint32_t* pB;   // loc + offB - n_split (so that pB[pos] is position pos)
-    uint32_t n_split;
-    uint64_t offA, offB;
-    __device__ __forceinline__ uint32_t at(uint32_t pos) const { return pos < n_split ? pA[pos] : pB[pos]; }
+    uint32_t k;
+    uint32_t w;    // (uint32_t) W_p
+    uint32_t off_hi;
+    uint32_t pad;
 };
 
 // sum over rows j < k of max(0, min(b, A0 + j) - a): the number of row[col] += w updates of a job
@@ -431,11 +408,11 @@ __device__ __forceinline__ unsigned long long job_updates(uint32_t a, uint32_t b
     return (unsigned long long)s;
 }
 
-// first position in [lo, hi) of the (ascending) list whose id is >= target
-__device__ __forceinline__ uint32_t lower_bound_ids(const Seg2& list, uint32_t lo, uint32_t hi, uint32_t target) {
+__device__ __forceinline__ uint32_t lower_bound_ids(const uint32_t* __restrict__ ids, uint32_t n, uint32_t target) {
+    uint32_t lo = 0, hi = n;
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (list.at(mid) >= target) hi = mid; else lo = mid + 1;
+        if (ids[mid] >= target) hi = mid; else lo = mid + 1;
     }
     return lo;
 }
@@ -460,15 +437,13 @@ __device__ __forceinline__ uint32_t win_col0(uint32_t hi, uint32_t t, uint32_t t
 // the job is known without touching the list; otherwise the list is cut at the window boundaries by
 // binary search, far window first.
 template <class Emit>
-__device__ __forceinline__ void emit_run(const Node& nd, const Seg2& list, uint32_t T,
+__device__ __forceinline__ void emit_run(const Node& nd, uint64_t base, const uint32_t* __restrict__ list, uint32_t T,
                                          uint32_t tile_cols, uint32_t rb_shift, uint32_t rb, uint32_t i, uint32_t k, uint32_t first_id,
                                          uint32_t row_last, Emit& emit) {
     const uint32_t reach = i + k - 1;  // the last row of the run sees the ids [0, reach)
     if (reach == 0) return;
     Job jb;
-    jb.offA = (uint32_t)list.offA; jb.offB = (uint32_t)list.offB; jb.n_split = list.n_split;
-    jb.k_hi = k | ((uint32_t)(list.offA >> 32) << 8) | ((uint32_t)(list.offB >> 32) << 20);
-    jb.A0 = i; jb.w = 0;
+    jb.off = (uint32_t)base; jb.off_hi = (uint32_t)(base >> 32); jb.A0 = i; jb.k = k; jb.w = 0; jb.pad = 0;
     uint32_t t_near = 0, t_far = 0, hi = 0;
     if (T > 1) {
         hi = win_hi(rb, rb_shift);               // row_last < hi, and first_id <= list[reach-1] < row_last
@@ -483,7 +458,7 @@ __device__ __forceinline__ void emit_run(const Node& nd, const Seg2& list, uint3
     uint32_t a = 0;
     for (uint32_t t = t_far; a < reach; --t) {
         // ids below the upper end of window t belong to it (lower windows were cut off before)
-        const uint32_t b = (t == t_near) ? nd.n : lower_bound_ids(list, a, reach, hi - t * tile_cols);
+        const uint32_t b = (t == t_near) ? nd.n : a + lower_bound_ids(list + a, reach - a, hi - t * tile_cols);
         if (b > a) { jb.a = a; jb.b = b; emit(rb * T + t, jb, job_updates(a, b, i, k)); }
         a = b;
         if (t == t_near) break;
@@ -492,11 +467,12 @@ __device__ __forceinline__ void emit_run(const Node& nd, const Seg2& list, uint3
 
 // Warp-cooperative enumeration of one (long) pattern: lanes over the pattern's local positions.
 template <class Emit>
-__device__ __forceinline__ void jobs_of_pattern_warp(const Node& nd, const Seg2& list,
+__device__ __forceinline__ void jobs_of_pattern_warp(const Node& nd, uint64_t base, const uint32_t* __restrict__ flat,
                                                      const uint32_t* __restrict__ loc, uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin,
                                                      uint32_t row_end, uint32_t lane, uint32_t first_id, unsigned long long& updates, Emit& emit) {
     const uint32_t first = nd.n - nd.l;
     const uint32_t rounds = (nd.l + 31) / 32;
+    const uint32_t* list = flat + base;
     for (uint32_t r = 0; r < rounds; ++r) {
         const uint32_t j = r * 32 + lane;
         const bool have = j < nd.l;
@@ -521,7 +497,7 @@ __device__ __forceinline__ void jobs_of_pattern_warp(const Node& nd, const Seg2&
         const uint32_t run_end = min(next_start, last_active);           // one past the run's last lane
         const uint32_t row_last = __shfl_sync(0xffffffffu, row, (run_end > lane ? run_end : lane + 1u) - 1u);
         if (!start) continue;
-        emit_run(nd, list, T, tile_cols, rb_shift, rb, i, run_end - lane, first_id, row_last, emit);
+        emit_run(nd, base, list, T, tile_cols, rb_shift, rb, i, run_end - lane, first_id, row_last, emit);
     }
 }
 
@@ -533,36 +509,28 @@ __device__ __forceinline__ void jobs_of_pattern_warp(const Node& nd, const Seg2&
 constexpr uint32_t kSmallL = 8;
 template <class Emit>
 __device__ __forceinline__ void enumerate_jobs(uint64_t lo, uint64_t hi, uint32_t warp, uint32_t nwarps,
-                                               const Node* __restrict__ nodes, const uint64_t* __restrict__ lists, uint64_t base0,
-                                               uint32_t resident, const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat,
+                                               const Node* __restrict__ nodes, const uint64_t* __restrict__ noff, uint64_t base0,
+                                               const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat,
                                                const uint32_t* __restrict__ loc, const uint32_t* __restrict__ first_ids, uint32_t T,
                                                uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin, uint32_t row_end, uint32_t lane,
                                                unsigned long long& updates, Emit emit) {
-    // `lists`: resident mode = offsets of the lists of patterns with children (ioff), a job reads
-    // list(parent) ++ own locals; chunked mode = offsets of every pattern's own expanded list (noff)
     for (uint64_t b = lo + (uint64_t)warp * 32; b < hi; b += (uint64_t)nwarps * 32) {
         const uint64_t p = b + lane;
         Node nd; nd.parent = -1; nd.n = 0; nd.l = 0; nd.last = 0; nd.loff = 0; nd.up2 = nd.up3 = -1;
-        uint32_t w = 0, fid = 0, n_split = 0;
-        uint64_t offA = 0, offB = 0;
+        uint32_t w = 0, fid = 0;
+        uint64_t base = 0;
         if (p < hi) {
             nd = nodes[p];
             if (nd.l) {
-                w = W[p];
-                if (resident) { n_split = nd.n - nd.l; offA = nd.parent >= 0 ? lists[nd.parent] : 0ull; offB = nd.loff; }
-                else { n_split = nd.n; offA = lists[p] - base0; }
+                w = W[p]; base = noff[p] - base0;
                 // first id of the full list: kept per pattern by the level-order expansion, else read from the list
-                if (T > 1) fid = first_ids ? first_ids[p] : flat[offA];
+                if (T > 1) fid = first_ids ? first_ids[p] : flat[base];
             }
         }
-        auto seg_of = [&](uint64_t oa, uint64_t ob, uint32_t ns) {
-            Seg2 sg; sg.pA = flat + oa; sg.pB = loc + ob - ns; sg.n_split = ns; sg.offA = oa; sg.offB = ob;
-            return sg;
-        };
         auto emit_w = [&](uint32_t key, const Job& jb, unsigned long long upd) { emit(key, jb, upd, w); };
         if (nd.l && nd.l <= kSmallL) {
             const uint32_t first = nd.n - nd.l;
-            const Seg2 list = seg_of(offA, offB, n_split);
+            const uint32_t* list = flat + base;
             const uint32_t* rows = loc + nd.loff;
             const uint32_t first_id = fid;
             uint32_t run_i = 0, run_k = 0, run_rb = 0, run_last = 0;
@@ -571,14 +539,14 @@ __device__ __forceinline__ void enumerate_jobs(uint64_t lo, uint64_t hi, uint32_
                 const bool active = row >= row_begin && row < row_end;
                 const uint32_t rb = row >> rb_shift;
                 if (active) updates += first + j;
-                if (run_k && (!active || rb != run_rb)) { emit_run(nd, list, T, tile_cols, rb_shift, run_rb, run_i, run_k, first_id, run_last, emit_w); run_k = 0; }
+                if (run_k && (!active || rb != run_rb)) { emit_run(nd, base, list, T, tile_cols, rb_shift, run_rb, run_i, run_k, first_id, run_last, emit_w); run_k = 0; }
                 if (active) {
                     if (!run_k) { run_i = first + j; run_rb = rb; }
                     ++run_k;
                     run_last = row;
                 }
             }
-            if (run_k) emit_run(nd, list, T, tile_cols, rb_shift, run_rb, run_i, run_k, first_id, run_last, emit_w);
+            if (run_k) emit_run(nd, base, list, T, tile_cols, rb_shift, run_rb, run_i, run_k, first_id, run_last, emit_w);
         }
         uint32_t big = __ballot_sync(0xffffffffu, nd.l > kSmallL);
         while (big) {
@@ -590,11 +558,10 @@ __device__ __forceinline__ void enumerate_jobs(uint64_t lo, uint64_t hi, uint32_
             bn.l = __shfl_sync(0xffffffffu, nd.l, src);
             bn.last = 0; bn.loff = __shfl_sync(0xffffffffu, nd.loff, src); bn.up2 = bn.up3 = -1;
             const uint32_t bw = __shfl_sync(0xffffffffu, w, src);
-            const uint64_t boffA = __shfl_sync(0xffffffffu, offA, src), boffB = __shfl_sync(0xffffffffu, offB, src);
-            const uint32_t bsplit = __shfl_sync(0xffffffffu, n_split, src);
+            const uint64_t bbase = __shfl_sync(0xffffffffu, base, src);
             const uint32_t bfid = __shfl_sync(0xffffffffu, fid, src);
             auto emit_b = [&](uint32_t key, const Job& jb, unsigned long long upd) { emit(key, jb, upd, bw); };
-            jobs_of_pattern_warp(bn, seg_of(boffA, boffB, bsplit), loc, T, tile_cols, rb_shift, row_begin, row_end, lane, bfid, updates, emit_b);
+            jobs_of_pattern_warp(bn, bbase, flat, loc, T, tile_cols, rb_shift, row_begin, row_end, lane, bfid, updates, emit_b);
         }
     }
 }
@@ -626,8 +593,8 @@ k_job_hist_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const 
     uint64_t lo, hi;
     block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
-    const uint32_t* flat = flat_all;
-    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, resident ? 0ull : noff[p0], resident, W, flat, loc, first_ids, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+    const uint32_t* flat = flat_all + (resident ? noff[p0] : 0ull);  // the chunk's lists start at its first pattern
+    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, loc, first_ids, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
                    [&](uint32_t key, const Job&, unsigned long long upd, uint32_t w) {
                        if (w == 0 || upd == 0) return;  // adds of 0 are skipped, but still counted in U
                        atomicAdd(&s_hist[key], 1u);
@@ -687,8 +654,8 @@ k_job_fill_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const 
     uint64_t lo, hi;
     block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
-    const uint32_t* flat = flat_all;
-    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, resident ? 0ull : noff[p0], resident, W, flat, loc, first_ids, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+    const uint32_t* flat = flat_all + (resident ? noff[p0] : 0ull);  // the chunk's lists start at its first pattern
+    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, loc, first_ids, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
                    [&](uint32_t key, Job jb, unsigned long long upd, uint32_t w) {
                        if (w == 0 || upd == 0) return;
                        const uint32_t slot = atomicAdd(&s_next[key], 1u);
@@ -708,8 +675,8 @@ k_job_hist(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint6
     uint64_t lo, hi;
     block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
-    const uint32_t* flat = flat_all;
-    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, resident ? 0ull : noff[p0], resident, W, flat, loc, first_ids, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+    const uint32_t* flat = flat_all + (resident ? noff[p0] : 0ull);  // the chunk's lists start at its first pattern
+    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, loc, first_ids, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
                    [&](uint32_t key, const Job&, unsigned long long upd, uint32_t w) {
                        if (w == 0 || upd == 0) return;
                        atomicAdd(&hist[key], 1u);
@@ -728,8 +695,8 @@ k_job_fill(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint6
     uint64_t lo, hi;
     block_slice(p0, p1, lo, hi);
     unsigned long long updates = 0;
-    const uint32_t* flat = flat_all;
-    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, resident ? 0ull : noff[p0], resident, W, flat, loc, first_ids, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
+    const uint32_t* flat = flat_all + (resident ? noff[p0] : 0ull);  // the chunk's lists start at its first pattern
+    enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, loc, first_ids, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
                    [&](uint32_t key, Job jb, unsigned long long upd, uint32_t w) {
                        if (w == 0 || upd == 0) return;
                        const uint32_t slot = atomicAdd(&cursor[key], 1u);
@@ -804,9 +771,10 @@ constexpr uint32_t kRowPad = 32;   // padding words after every accumulator row 
 
 __global__ void __launch_bounds__(1024)
 k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_units_ptr, const Job* __restrict__ jobs,
-              const uint32_t* __restrict__ flat, const uint32_t* __restrict__ loc, uint32_t* __restrict__ tri,
+              const uint32_t* __restrict__ flat_all, const uint64_t* __restrict__ flat_shift, uint32_t* __restrict__ tri,
               uint64_t tri_base, uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t* __restrict__ unit_counter) {
     extern __shared__ uint4 tile4[];
+    const uint32_t* flat = flat_all + (flat_shift ? *flat_shift : 0ull);
     uint32_t* tile = reinterpret_cast<uint32_t*>(tile4);
     __shared__ uint32_t s_unit, s_next_job;
     const uint32_t lane = threadIdx.x & 31;
@@ -862,21 +830,17 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
             jb = __shfl_sync(0xffffffffu, jb, 0);
             if (jb >= un.job_end) break;
             const uint32_t cnt = min(kJobBatch, un.job_end - jb);
-            uint4 part = make_uint4(0, 0, 0, 0);  // lane 2q: (offA, a, b, A0) of job q; lane 2q+1: (k_hi, w, offB, n_split)
+            uint4 part = make_uint4(0, 0, 0, 0);  // lane 2q: (off, a, b, A0) of job q; lane 2q+1: (k, w, off_hi, -)
             if (lane < 2 * cnt) part = ldg_nc_v4(reinterpret_cast<const uint4*>(jobs + jb) + lane);
             for (uint32_t q = 0; q < cnt; ++q) {
                 const uint32_t off = __shfl_sync(0xffffffffu, part.x, 2 * q), a = __shfl_sync(0xffffffffu, part.y, 2 * q);
                 const uint32_t b = __shfl_sync(0xffffffffu, part.z, 2 * q), A0 = __shfl_sync(0xffffffffu, part.w, 2 * q);
-                const uint32_t k_hi = __shfl_sync(0xffffffffu, part.x, 2 * q + 1), w = __shfl_sync(0xffffffffu, part.y, 2 * q + 1);
-                const uint32_t offB = __shfl_sync(0xffffffffu, part.z, 2 * q + 1), n_split = __shfl_sync(0xffffffffu, part.w, 2 * q + 1);
-                const uint32_t k = k_hi & 0xFFu;
-                // the list in two segments: positions below n_split from the flat array, the rest from the local ids
-                const uint32_t* pA = flat + (((uint64_t)((k_hi >> 8) & 0xFFFu) << 32) | off);
-                const uint32_t* pB = loc + (((uint64_t)(k_hi >> 20) << 32) | offB) - n_split;
-                auto ld_id = [&](uint32_t pos) { return ldg_nc_u32(pos < n_split ? pA + pos : pB + pos); };
+                const uint32_t k = __shfl_sync(0xffffffffu, part.x, 2 * q + 1), w = __shfl_sync(0xffffffffu, part.y, 2 * q + 1);
+                const uint32_t off_hi = __shfl_sync(0xffffffffu, part.z, 2 * q + 1);
+                const uint32_t* list = flat + (((uint64_t)off_hi << 32) | off);
                 uint32_t my_id4 = 0, rowoff = 0;  // lane j < k: 4 * id of row j, shared address of its accumulator row
                 if (lane < k) {
-                    const uint32_t my_row = ld_id(A0 + lane);
+                    const uint32_t my_row = ldg_nc_u32(list + A0 + lane);
                     my_id4 = my_row * 4u;
                     rowoff = base + (my_row - row0) * stride * 4u;
                 }
@@ -884,10 +848,10 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
                 const uint32_t bc = min(b, A0);
                 for (uint32_t c = a; c < bc; c += 128) {
                     const uint32_t rem = bc - c;
-                    const uint32_t p = c + lane;
+                    const uint32_t* p = list + c + lane;
                     if (rem >= 128) {  // full slice: no lane is idle, no predicates
-                        const uint32_t x0 = ld_id(p) * 4u, x1 = ld_id(p + 32) * 4u;
-                        const uint32_t x2 = ld_id(p + 64) * 4u, x3 = ld_id(p + 96) * 4u;
+                        const uint32_t x0 = ldg_nc_u32(p) * 4u, x1 = ldg_nc_u32(p + 32) * 4u;
+                        const uint32_t x2 = ldg_nc_u32(p + 64) * 4u, x3 = ldg_nc_u32(p + 96) * 4u;
                         for (uint32_t j = 0; j < k; ++j) {
                             const uint32_t ro = __shfl_sync(0xffffffffu, rowoff, j);
                             red_shared_add(ro + x0, w); red_shared_add(ro + x1, w);
@@ -901,10 +865,10 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
                     const uint32_t full = rem >> 5;          // complete 32-id groups (0..3)
                     const bool tail = lane < (rem & 31u);     // this lane has an id in the partial group
                     uint32_t x0 = pad4, x1 = pad4, x2 = pad4, x3 = pad4;
-                    if (lane < rem) x0 = ld_id(p) * 4u;
-                    if (lane + 32 < rem) x1 = ld_id(p + 32) * 4u;
-                    if (lane + 64 < rem) x2 = ld_id(p + 64) * 4u;
-                    if (lane + 96 < rem) x3 = ld_id(p + 96) * 4u;
+                    if (lane < rem) x0 = ldg_nc_u32(p) * 4u;
+                    if (lane + 32 < rem) x1 = ldg_nc_u32(p + 32) * 4u;
+                    if (lane + 64 < rem) x2 = ldg_nc_u32(p + 64) * 4u;
+                    if (lane + 96 < rem) x3 = ldg_nc_u32(p + 96) * 4u;
                     const uint32_t xt = full == 0 ? x0 : full == 1 ? x1 : full == 2 ? x2 : x3;
                     for (uint32_t j = 0; j < k; ++j) {
                         const uint32_t ro = __shfl_sync(0xffffffffu, rowoff, j);
@@ -973,8 +937,8 @@ struct kdbx_ctx {
     std::vector<std::pair<uint32_t, uint32_t>> levels;  // ranges of `order` per distinct num_samples, ascending
     // per chunk
     DevBuf flat, jobs, hist, work, bucket_off, cursor, ucount, uoff, units, counters, blockhist;
-    DevBuf tri, rowupd, first_id, has_child, ioff;
-    uint64_t sum_l = 0, sum_n = 0, sum_n_parents = 0;
+    DevBuf tri, rowupd, first_id;
+    uint64_t sum_l = 0, sum_n = 0;
     bool prepared = false;  // nodes / W / loc are valid for the loaded trie
 
     // sparse delivery (sparse.cuh)
@@ -1081,15 +1045,19 @@ int make_plan(kdbx_ctx* ctx, Plan& pl) {
     return KDBX_OK;
 }
 
-int check_device_error(kdbx_ctx* ctx) {
-    int flag = 0;
-    CK(cudaMemcpy(&flag, ctx->err_flag.p, sizeof flag, cudaMemcpyDeviceToHost));
+int error_from_flag(kdbx_ctx* ctx, int flag) {
     if (flag == 1) return ctx->fail(KDBX_ERR_ARG, "malformed trie: Elias-gamma stream does not match num_bits");
     if (flag == 2) return ctx->fail(KDBX_ERR_ARG, "malformed trie: sample id out of range");
     if (flag == 3) return ctx->fail(KDBX_ERR_ARG, "malformed trie: a local list does not continue its parent's list");
     if (flag == 4) return ctx->fail(KDBX_ERR_ARG, "malformed trie: parent_id / num_samples / num_local_samples inconsistent");
     if (flag == 5) return ctx->fail(KDBX_ERR_ARG, "malformed trie: payload offset out of bounds");
+    if (flag == 6) return ctx->fail(KDBX_ERR_ARG, "k-mer table points at a pattern that does not exist");
     return KDBX_OK;
+}
+int check_device_error(kdbx_ctx* ctx) {
+    int flag = 0;
+    CK(cudaMemcpy(&flag, ctx->err_flag.p, sizeof flag, cudaMemcpyDeviceToHost));
+    return error_from_flag(ctx, flag);
 }
 
 uint64_t levels_hash_of(const std::vector<std::pair<uint32_t, uint32_t>>& levels) {
@@ -1137,16 +1105,8 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
         if (int rc = scan_exclusive(ctx, it, ctx->loff.as<uint64_t>(), P + 1)) return rc;
     }
     {
-        cub::TransformInputIterator<uint64_t, ListSlots, cub::CountingInputIterator<uint64_t>> it(idx, ListSlots{ctx->n.as<uint32_t>(), P, nullptr});
+        cub::TransformInputIterator<uint64_t, ListSlots, cub::CountingInputIterator<uint64_t>> it(idx, ListSlots{ctx->n.as<uint32_t>(), P});
         if (int rc = scan_exclusive(ctx, it, ctx->noff.as<uint64_t>(), P + 1)) return rc;
-    }
-    {   // lists that other lists are built from: only patterns with children get one in resident mode
-        CK(ctx->has_child.ensure(P * 4)); CK(ctx->ioff.ensure((P + 1) * 8));
-        CK(cudaMemsetAsync(ctx->has_child.p, 0, P * 4, st));
-        k_mark_parents<<<blocks_for(P, 256), 256, 0, st>>>(P, ctx->parent.as<int64_t>(), ctx->has_child.as<uint32_t>());
-        cub::TransformInputIterator<uint64_t, ListSlots, cub::CountingInputIterator<uint64_t>> it(idx, ListSlots{ctx->n.as<uint32_t>(), P, ctx->has_child.as<uint32_t>()});
-        if (int rc = scan_exclusive(ctx, it, ctx->ioff.as<uint64_t>(), P + 1)) return rc;
-        launches += 2;
     }
     {
         ChunkCost cc{ctx->n.as<uint32_t>(), ctx->l.as<uint32_t>(), ctx->last.as<uint32_t>(), P, pl.tile_cols};
@@ -1186,13 +1146,14 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
         launches += 4;
     }
     uint64_t sums[3] = {0, 0, 0};
-    CK(cudaMemcpyAsync(&ctx->sum_n_parents, ctx->ioff.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&sums[0], ctx->loff.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&sums[1], ctx->noff.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&sums[2], ctx->coff.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(ctx->h_level_start.data(), ctx->level_start.p, ((size_t)N + 2) * 4, cudaMemcpyDeviceToHost, st));
+    int h_flag = 0;
+    CK(cudaMemcpyAsync(&h_flag, ctx->err_flag.p, sizeof h_flag, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (int rc = check_device_error(ctx)) return rc;  // structural errors stop here, before any id is chased
+    if (int rc = error_from_flag(ctx, h_flag)) return rc;  // structural errors stop here, before any id is chased
     ctx->sum_l = sums[0]; ctx->sum_n = sums[1];
     {   // deepest level first; level 0 (the sentinel, n = 0) has no parent to feed
         uint32_t end = (uint32_t)P;
@@ -1245,8 +1206,11 @@ float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime
 int ensure_job_slots(kdbx_ctx* ctx, bool resident, uint32_t nkeys, uint64_t& jobs_cap) {
     if (!resident) return KDBX_OK;
     uint32_t total = 0;
+    int h_flag = 0;   // decode errors surface here: before any job is filled in or executed
     CK(cudaMemcpyAsync(&total, ctx->bucket_off.as<uint32_t>() + nkeys, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&h_flag, ctx->err_flag.p, sizeof h_flag, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (int rc = error_from_flag(ctx, h_flag)) return rc;
     if ((uint64_t)total + 64 > jobs_cap) {
         jobs_cap = (uint64_t)total + 64;
         CK(ctx->jobs.ensure(jobs_cap * sizeof(Job)));
@@ -1292,14 +1256,12 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     if (nchunks_or_err < 0) return nchunks_or_err;
     const uint32_t nchunks = (uint32_t)nchunks_or_err;
     std::vector<uint64_t> bounds(nchunks + 1);
-    CK(cudaMemcpyAsync(bounds.data(), ctx->bounds.p, (nchunks + 1) * 8, cudaMemcpyDeviceToHost, st));
     cudaEvent_t ev_prepared = ctx->event();
-    CK(cudaStreamSynchronize(st));
-    s.ms_prepare = elapsed(ev_start, ev_prepared);
-    if (int rc = check_device_error(ctx)) return rc;  // decode errors: stop before lists are expanded
 
     const uint32_t nkeys = pl.RB * pl.T;
     if (cells == 0 || nkeys == 0) {  // N <= 1 or an empty row range: no cell exists
+        CK(cudaStreamSynchronize(st));
+        s.ms_prepare = elapsed(ev_start, ev_prepared);
         s.ms_total = s.ms_prepare;
         s.flat_ids = ctx->sum_n; s.local_ids = ctx->sum_l; s.kernel_launches = launches;
         if (int rc = check_device_error(ctx)) return rc;
@@ -1316,9 +1278,14 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
         const uint64_t have = (uint64_t)free_b + ctx->flat.bytes;
-        resident = (ctx->sum_n_parents + 64) * 4 <= have / 5 * 2;
+        resident = (ctx->sum_n + 64) * 4 <= have / 5 * 2;
     }
-    CK(ctx->flat.ensure(resident ? (ctx->sum_n_parents + 64) * 4 : cap * 4));
+    if (!resident) {   // chunk boundaries come from the device; decode errors stop the call before any chain is walked
+        CK(cudaMemcpyAsync(bounds.data(), ctx->bounds.p, (nchunks + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (int rc = check_device_error(ctx)) return rc;
+    }   // (resident mode: the expansion only copies by the validated sizes; the flag is read before the jobs are filled in)
+    CK(ctx->flat.ensure(resident ? (ctx->sum_n + 64) * 4 : cap * 4));
     if (resident) CK(ctx->first_id.ensure(ctx->P * 4));
     if (!resident) CK(ctx->jobs.ensure(cap * sizeof(Job)));
     CK(ctx->hist.ensure(((size_t)nkeys + 1) * 4)); CK(ctx->work.ensure(((size_t)nkeys + 1) * 8));
@@ -1330,26 +1297,25 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     uint32_t* d_unit_counter = ctx->counters.as<uint32_t>() + 4;
     CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
 
-    float ms_expand_all = 0.f;
+    cudaEvent_t ev_expand_a = nullptr, ev_expand_b = nullptr;
     if (resident) {
         cudaEvent_t a = ctx->event();
         uint32_t n_launch = 0;
         for (const auto& lv : ctx->levels) if (lv.second > lv.first) ++n_launch;
         if (n_launch) {
-            if (int rc = launch_level_graph(ctx, ctx->g_expand, {ctx->order.p, ctx->nodes.p, ctx->ioff.p, ctx->loc.p, ctx->flat.p, ctx->first_id.p}, [&] {
+            if (int rc = launch_level_graph(ctx, ctx->g_expand, {ctx->order.p, ctx->nodes.p, ctx->noff.p, ctx->loc.p, ctx->flat.p, ctx->first_id.p}, [&] {
                     for (size_t k = 0; k < ctx->levels.size(); ++k) {  // ascending num_samples: parents first
                         const uint32_t b = ctx->levels[k].first, e = ctx->levels[k].second;
                         if (e <= b) continue;
                         k_expand_level<<<blocks_for((uint64_t)(e - b) * kLevelLanes, 256), 256, 0, st>>>(e - b, ctx->order.as<uint32_t>() + b, ctx->nodes.as<Node>(),
-                                                                                                          ctx->ioff.as<uint64_t>(), ctx->has_child.as<uint32_t>(), ctx->loc.as<uint32_t>(),
+                                                                                                          ctx->noff.as<uint64_t>(), ctx->loc.as<uint32_t>(),
                                                                                                           ctx->flat.as<uint32_t>(), ctx->first_id.as<uint32_t>());
                     }
                 })) return rc;
         }
         launches += n_launch;
-        cudaEvent_t b = ctx->event();
-        CK(cudaStreamSynchronize(st));
-        ms_expand_all = elapsed(a, b);
+        ev_expand_a = a;
+        ev_expand_b = ctx->event();
     }
     const size_t smem = pl.smem;
     CK(cudaFuncSetAttribute(k_scatter_add, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1380,26 +1346,26 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         e.b = ctx->event();
         CK(cudaMemsetAsync(ctx->work.p, 0, ((size_t)nkeys + 1) * 8, st));
         if (smem_buckets) {
-            k_job_hist_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), (resident ? ctx->ioff : ctx->noff).as<uint64_t>(), ctx->W.as<uint32_t>(),
+            k_job_hist_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
                                                                   ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
                                                                   ctx->blockhist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates);
             k_key_totals<<<blocks_for((uint64_t)nkeys + 1, 128), 128, 0, st>>>(nkeys, wide_grid, ctx->blockhist.as<uint32_t>(), ctx->hist.as<uint32_t>());
             if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
             if (int rc = ensure_job_slots(ctx, resident, nkeys, jobs_cap)) return rc;
             k_block_offsets<<<blocks_for((uint64_t)nkeys * 32, 256), 256, 0, st>>>(nkeys, wide_grid, ctx->bucket_off.as<uint32_t>(), ctx->blockhist.as<uint32_t>());
-            k_job_fill_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), (resident ? ctx->ioff : ctx->noff).as<uint64_t>(), ctx->W.as<uint32_t>(),
+            k_job_fill_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
                                                                   ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
                                                                   ctx->blockhist.as<uint32_t>(), ctx->jobs.as<Job>());
             launches += 2;
         } else {
             CK(cudaMemsetAsync(ctx->hist.p, 0, ((size_t)nkeys + 1) * 4, st));
-            k_job_hist<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), (resident ? ctx->ioff : ctx->noff).as<uint64_t>(), ctx->W.as<uint32_t>(),
+            k_job_hist<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
                                                    ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
                                                    ctx->hist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates);
             if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
             if (int rc = ensure_job_slots(ctx, resident, nkeys, jobs_cap)) return rc;
             CK(cudaMemcpyAsync(ctx->cursor.p, ctx->bucket_off.p, ((size_t)nkeys + 1) * 4, cudaMemcpyDeviceToDevice, st));
-            k_job_fill<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), (resident ? ctx->ioff : ctx->noff).as<uint64_t>(), ctx->W.as<uint32_t>(),
+            k_job_fill<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
                                                    ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
                                                    ctx->cursor.as<uint32_t>(), ctx->jobs.as<Job>());
         }
@@ -1411,7 +1377,7 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         CK(cudaMemsetAsync(d_unit_counter, 0, 4, st));
         e.c = ctx->event();
         k_scatter_add<<<scatter_grid, pl.threads, smem, st>>>(ctx->units.as<Unit>(), ctx->uoff.as<uint32_t>() + nkeys, ctx->jobs.as<Job>(),
-                                                              ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), d_out, tri_base,
+                                                              ctx->flat.as<uint32_t>(), resident ? ctx->noff.as<uint64_t>() + p0 : nullptr, d_out, tri_base,
                                                               pl.T, pl.tile_cols, pl.rb_shift, d_unit_counter);
         e.d = ctx->event();
         launches += 8;
@@ -1421,9 +1387,12 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     cudaEvent_t ev_end = ctx->event();
     CK(cudaGetLastError());
     unsigned long long total_updates = 0;
+    int h_flag = 0;
     CK(cudaMemcpyAsync(&total_updates, d_total_updates, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h_flag, ctx->err_flag.p, sizeof h_flag, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (int rc = check_device_error(ctx)) return rc;
+    if (int rc = error_from_flag(ctx, h_flag)) return rc;
+    s.ms_prepare = elapsed(ev_start, ev_prepared);
     for (const ChunkEv& e : cev) {
         s.ms_expand += elapsed(e.a, e.b);
         s.ms_bucket += elapsed(e.b, e.c);
@@ -1431,7 +1400,7 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     }
     if (int rc = finish_upload(ctx)) return rc;
     s.ms_upload = ctx->ms_upload;
-    s.ms_expand += ms_expand_all;
+    if (ev_expand_a) s.ms_expand += elapsed(ev_expand_a, ev_expand_b);
     s.ms_total = elapsed(ev_start, ev_end);
     s.updates = total_updates;
     s.flat_ids = ctx->sum_n; s.local_ids = ctx->sum_l;
@@ -1542,7 +1511,7 @@ void kdbx_close(kdbx_ctx* ctx) {
     for (DevBuf* b : {&ctx->num_kmers, &ctx->parent, &ctx->n, &ctx->l, &ctx->last, &ctx->bits, &ctx->poff, &ctx->payload,
                       &ctx->nodes, &ctx->W, &ctx->loc, &ctx->loff, &ctx->noff, &ctx->coff, &ctx->bounds, &ctx->err_flag,
                       &ctx->cub_tmp, &ctx->order_in, &ctx->order, &ctx->keys_sorted, &ctx->level_start, &ctx->flat, &ctx->jobs, &ctx->hist, &ctx->work, &ctx->bucket_off, &ctx->cursor,
-                      &ctx->ucount, &ctx->uoff, &ctx->units, &ctx->counters, &ctx->blockhist, &ctx->tri, &ctx->rowupd, &ctx->first_id, &ctx->has_child, &ctx->ioff,
+                      &ctx->ucount, &ctx->uoff, &ctx->units, &ctx->counters, &ctx->blockhist, &ctx->tri, &ctx->rowupd, &ctx->first_id,
                       &ctx->sp_cnt, &ctx->sp_counts, &ctx->sp_rowptr, &ctx->sp_col, &ctx->sp_val, &ctx->slot_off, &ctx->slots,
                       &ctx->q_off, &ctx->q_kmers, &ctx->q_keys, &ctx->q_keys2, &ctx->q_runkeys, &ctx->q_runcnt, &ctx->q_out})
         b->release();

@@ -131,12 +131,27 @@ def main():
             write_fasta(out / "fa" / f"q{q:05d}.fasta", seq, f"q{q:05d}")
             qnames.append(str(out / "fa" / f"q{q:05d}"))
         (out / "q.list").write_text("\n".join(qnames) + "\n")
-        text, bwall = run([EXE, "build", "-t", a.threads, out / "db.list", out / "n2a.ours.db"])
+        def update_time(text):
+            m = re.search(r"Database update time:\s*([0-9.eE+-]+)", text)
+            return float(m.group(1)) if m else None
+        text, bwall = run([EXE, "build", "-t", a.threads, out / "db.list", out / "n2a.ours.db"])   # on the device
+        dev = {}
+        for ln in text.splitlines():
+            if ln.startswith("{\"samples\""):
+                dev = json.loads(ln)
         line = {"mode": "build", "workload": f"{a.db_genomes} genomes x {a.len} bp, {a.db_clusters} clusters, k=18 (FASTA-level synthetic)",
-                "ours_wall_seconds": bwall, "threads": a.threads}
+                "ours_device_wall_seconds": bwall, "ours_device_update_seconds": update_time(text), "ours_device_stats": dev,
+                "host_threads": a.threads}
+        text, hwall = run([EXE, "build", "-host-build", "-t", a.threads, out / "db.list", out / "n2a.host.db"])
+        line.update({"ours_host_builder_wall_seconds": hwall, "ours_host_builder_update_seconds": update_time(text)})
+        run([EXE, "all2all", out / "n2a.ours.db", out / "b.dev.csv"])
+        run([EXE, "all2all", out / "n2a.host.db", out / "b.host.csv"])
+        line["device_and_host_builder_give_identical_all2all"] = same(out / "b.dev.csv", out / "b.host.csv")
         if have_ref:
             text, rbwall = run([REF, "build", "-t", a.threads, out / "db.list", out / "n2a.ref.db"])
-            line.update({"reference_wall_seconds": rbwall})
+            line.update({"reference_wall_seconds": rbwall, "reference_update_seconds": update_time(text)})
+            run([EXE, "all2all", out / "n2a.ref.db", out / "b.ref.csv"])
+            line["all2all_identical_to_reference_built_db"] = same(out / "b.dev.csv", out / "b.ref.csv")
         print(json.dumps(line), flush=True)
         text, wall = run([EXE, "new2all", "-t", a.threads, out / "n2a.ours.db", out / "q.list", out / "n2a.ours.csv"])
         st = stats_json(text)
