@@ -762,6 +762,22 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const uint4* p) {
 }
 
 constexpr uint32_t kJobBatch = 8;  // jobs a warp claims at once (16 lanes load them as uint4 halves)
+
+// Last pass of a job over its k rows (see k_scatter_add): F complete 32-id groups (x0..x2), the partial
+// group xt under `tail`, and the triangular part (lanes below j hold the ids of the rows before row j).
+template <uint32_t F>
+__device__ __forceinline__ void last_rows(uint32_t k, uint32_t rowoff, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t xt, bool tail,
+                                          bool tv, uint32_t my_id4, uint32_t lane, uint32_t w) {
+#pragma unroll 2
+    for (uint32_t j = 0; j < k; ++j) {
+        const uint32_t ro = __shfl_sync(0xffffffffu, rowoff, j);
+        if (F > 0) red_shared_add(ro + x0, w);
+        if (F > 1) red_shared_add(ro + x1, w);
+        if (F > 2) red_shared_add(ro + x2, w);
+        if (tail) red_shared_add(ro + xt, w);
+        if (tv && lane < j) red_shared_add(ro + my_id4, w);
+    }
+}
 constexpr uint32_t kRowPad = 32;   // padding words after every accumulator row (see k_scatter_add)
 // Tried and dropped (profiles/r01_scatter_rows_as_lanes.txt): taking the shared ids one at a time with the
 // job's ROWS on the lanes (row stride odd modulo 32, so every instruction is one conflict-free wavefront with
@@ -844,45 +860,41 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
                     my_id4 = my_row * 4u;
                     rowoff = base + (my_row - row0) * stride * 4u;
                 }
-                // ids seen by every row of the job: [a, min(b, A0))
+                // ids seen by every row of the job: [a, min(b, A0)).  Whole 128-id slices first ...
                 const uint32_t bc = min(b, A0);
-                for (uint32_t c = a; c < bc; c += 128) {
-                    const uint32_t rem = bc - c;
+                const uint32_t c_last = a < bc ? a + ((bc - a) & ~127u) : a;
+                for (uint32_t c = a; c < c_last; c += 128) {  // full slice: no lane is idle, no predicates
                     const uint32_t* p = list + c + lane;
-                    if (rem >= 128) {  // full slice: no lane is idle, no predicates
-                        const uint32_t x0 = ldg_nc_u32(p) * 4u, x1 = ldg_nc_u32(p + 32) * 4u;
-                        const uint32_t x2 = ldg_nc_u32(p + 64) * 4u, x3 = ldg_nc_u32(p + 96) * 4u;
-                        for (uint32_t j = 0; j < k; ++j) {
-                            const uint32_t ro = __shfl_sync(0xffffffffu, rowoff, j);
-                            red_shared_add(ro + x0, w); red_shared_add(ro + x1, w);
-                            red_shared_add(ro + x2, w); red_shared_add(ro + x3, w);
-                        }
-                        continue;
+                    const uint32_t x0 = ldg_nc_u32(p) * 4u, x1 = ldg_nc_u32(p + 32) * 4u;
+                    const uint32_t x2 = ldg_nc_u32(p + 64) * 4u, x3 = ldg_nc_u32(p + 96) * 4u;
+                    for (uint32_t j = 0; j < k; ++j) {
+                        const uint32_t ro = __shfl_sync(0xffffffffu, rowoff, j);
+                        red_shared_add(ro + x0, w); red_shared_add(ro + x1, w);
+                        red_shared_add(ro + x2, w); red_shared_add(ro + x3, w);
                     }
-                    // last, ragged slice: full 32-id groups reduce unconditionally, the final partial group
-                    // under a lane predicate (an idle lane parked on a padding word would still occupy
-                    // a bank and cost the group a second wavefront)
-                    const uint32_t full = rem >> 5;          // complete 32-id groups (0..3)
-                    const bool tail = lane < (rem & 31u);     // this lane has an id in the partial group
+                }
+                // ... then ONE pass over the rows for what is left: the ragged last slice (0..127 ids: complete
+                // 32-id groups reduce unconditionally, the partial group under a lane predicate — an idle lane
+                // parked on a padding word would still occupy a bank) together with the triangular part (row j
+                // also receives the rows before it that lie in [a, b)).  Most jobs are nothing but this pass
+                // (a parent's list is ~70 ids), so it is specialised on the number of complete groups.
+                {
+                    const uint32_t rem = a < bc ? bc - c_last : 0u;
+                    const uint32_t* p = list + c_last + lane;
+                    const uint32_t full = rem >> 5;           // complete 32-id groups (0..3)
+                    const bool tail = lane < (rem & 31u);      // this lane has an id in the partial group
                     uint32_t x0 = pad4, x1 = pad4, x2 = pad4, x3 = pad4;
                     if (lane < rem) x0 = ldg_nc_u32(p) * 4u;
                     if (lane + 32 < rem) x1 = ldg_nc_u32(p + 32) * 4u;
                     if (lane + 64 < rem) x2 = ldg_nc_u32(p + 64) * 4u;
                     if (lane + 96 < rem) x3 = ldg_nc_u32(p + 96) * 4u;
-                    const uint32_t xt = full == 0 ? x0 : full == 1 ? x1 : full == 2 ? x2 : x3;
-                    for (uint32_t j = 0; j < k; ++j) {
-                        const uint32_t ro = __shfl_sync(0xffffffffu, rowoff, j);
-                        if (full > 0) red_shared_add(ro + x0, w);
-                        if (full > 1) red_shared_add(ro + x1, w);
-                        if (full > 2) red_shared_add(ro + x2, w);
-                        if (tail) red_shared_add(ro + xt, w);
+                    const bool tv = lane < k && A0 + lane >= a && A0 + lane < b;
+                    switch (full) {
+                        case 0: last_rows<0>(k, rowoff, x0, x1, x2, x0, tail, tv, my_id4, lane, w); break;
+                        case 1: last_rows<1>(k, rowoff, x0, x1, x2, x1, tail, tv, my_id4, lane, w); break;
+                        case 2: last_rows<2>(k, rowoff, x0, x1, x2, x2, tail, tv, my_id4, lane, w); break;
+                        default: last_rows<3>(k, rowoff, x0, x1, x2, x3, tail, tv, my_id4, lane, w); break;
                     }
-                }
-                // triangular tail: row j also receives the rows before it that lie in [a, b)
-                const bool tv = lane < k && A0 + lane >= a && A0 + lane < b;
-                for (uint32_t j = 1; j < k; ++j) {
-                    const uint32_t ro = __shfl_sync(0xffffffffu, rowoff, j);
-                    if (tv && lane < j) red_shared_add(ro + my_id4, w);
                 }
             }
         }
@@ -1066,18 +1078,25 @@ uint64_t levels_hash_of(const std::vector<std::pair<uint32_t, uint32_t>>& levels
     return h;
 }
 
-// Replays `record` (kernel launches on ctx->stream only) from a graph; re-captures when the staged trie,
-// its levels or any of the buffers the launches point at have changed.
+// Replays `record` (kernel launches on ctx->stream only) from a graph.  The first call for a given
+// staged trie launches directly (a one-shot CLI run should not pay for capture and instantiation); the
+// second call with the same trie, levels and buffers captures the graph, later calls replay it.
 template <class Record>
 int launch_level_graph(kdbx_ctx* ctx, kdbx_ctx::LevelGraph& g, std::initializer_list<const void*> ptrs, Record&& record) {
     kdbx_ctx::LevelGraph want;
     size_t i = 0;
     for (const void* p : ptrs) want.ptr[i++] = p;
     want.P = ctx->P; want.nlevels = ctx->levels.size(); want.levels_hash = levels_hash_of(ctx->levels);
-    const bool same = g.exec && g.P == want.P && g.nlevels == want.nlevels && g.levels_hash == want.levels_hash &&
+    const bool same = g.P == want.P && g.nlevels == want.nlevels && g.levels_hash == want.levels_hash &&
                       std::memcmp(g.ptr, want.ptr, sizeof want.ptr) == 0;
     if (!same) {
         if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        g = want;          // remember what was launched; exec stays empty
+        record();
+        CK(cudaGetLastError());
+        return KDBX_OK;
+    }
+    if (!g.exec) {
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
         record();
@@ -1086,8 +1105,7 @@ int launch_level_graph(kdbx_ctx* ctx, kdbx_ctx::LevelGraph& g, std::initializer_
         const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) return ctx->fail(KDBX_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
-        want.exec = exec;
-        g = want;
+        g.exec = exec;
     }
     CK(cudaGraphLaunch(g.exec, ctx->stream));
     return KDBX_OK;
