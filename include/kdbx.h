@@ -315,6 +315,15 @@ int kdbx_builder_add_kmers(kdbx_builder* b, const uint64_t* kmers, uint64_t coun
 int kdbx_builder_finish(kdbx_builder* b, kdbx_build_result* out);
 int kdbx_builder_export(kdbx_builder* b, const kdbx_build_arrays* arrays);
 
+/* new2all from the queries' sequences: the k-mer extraction, minhash, sort and unique that New2AllConsole's
+ * loader threads run per query on the host (src/console_new2all.cpp:64-94, src/kmer_extract.h:13-119) happen on
+ * the device with `params` (the database's k, alphabet and fraction — as for kdbx_builder_open), then the same
+ * probe / count / scatter as kdbx_new2all_batch.  Query q = symbols[q_off[q] .. q_off[q+1]) (records separated by
+ * a byte outside the alphabet); unique_kmers[q] (may be NULL) receives its number of distinct k-mers, the
+ * "total-kmers" column of the reference's table.  `out` is HOST memory, n_queries x N. */
+int kdbx_new2all_sequences(kdbx_ctx* ctx, const kdbx_build_params* params, const char* symbols, const uint64_t* q_off,
+                           uint32_t n_queries, uint32_t* out, uint64_t* unique_kmers, kdbx_stats* stats);
+
 /* Debug / test taps (not used by the product path): copy intermediate device arrays of the
  * last compute call to the host.  what: 0 = W (uint32[P]), 1 = decoded local ids
  * (uint32[sum l]), 2 = local offsets (uint64[P+1]).  Returns elements written or <0. */

@@ -356,3 +356,145 @@ __global__ void k_adopt_tables(uint64_t total_slots, uint64_t num_tables, const 
     const unsigned m = __ballot_sync(0xffffffffu, inserted);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&ps->inserted, (unsigned long long)__popc(m));
 }
+
+// ---- extraction parameters from the caller's description (shared by the builder and the query path) ----
+int make_build_alphabet(kdbx_ctx* ctx, const kdbx_build_params* p, const char* who, BuildAlphabet& a, uint32_t& sentinel_bit,
+                        uint64_t& num_tables) {
+    if (!p) return ctx->fail(KDBX_ERR_ARG, "%s: parameters are NULL", who);
+    if (p->kmer_length == 0 || p->bits_per_symbol == 0 || p->bits_per_symbol > 8 || p->alphabet_size < 2 ||
+        p->alphabet_size > (1u << p->bits_per_symbol))
+        return ctx->fail(KDBX_ERR_ARG, "%s: bad alphabet / k-mer length", who);
+    const int kb = (int)p->kmer_length * (int)p->bits_per_symbol;
+    const int prefix_bits = kb - 32;
+    const uint32_t shift = prefix_bits < 8 ? (uint32_t)(8 - prefix_bits) : 0u;   // src/kmer_extract.h:36-45
+    if (kb > 62 || kb + (int)shift > 62) return ctx->fail(KDBX_ERR_ARG, "%s: k-mer does not fit 62 bits", who);
+    const int table_bits = prefix_bits < 8 ? 8 : prefix_bits;                     // src/prefix_kmer_db.cpp:54-62
+    if (table_bits > 24) return ctx->fail(KDBX_ERR_ARG, "%s: 2^%d prefix tables are not supported on the device", who, table_bits);
+    if (!(p->fraction > 0.0)) return ctx->fail(KDBX_ERR_ARG, "%s: fraction must be positive", who);
+    std::memcpy(a.map, p->symbol_map, 256);
+    a.k = p->kmer_length; a.bits = p->bits_per_symbol; a.size = p->alphabet_size;
+    a.preserve = p->preserve_strand ? 1u : 0u; a.shift = shift;
+    a.accept_all = !(p->fraction < 1.0) ? 1u : 0u;                                // NullFilter, src/filter.h:120-145
+    a.lo = 0; a.hi = ~0ull;
+    if (!a.accept_all) {                                                          // src/filter.h:40-51
+        const double top = (double)UINT64_MAX;
+        a.lo = (unsigned long long)(top * p->fraction_start);
+        const double hi = top * (p->fraction_start + p->fraction);
+        a.hi = hi >= top ? ~0ull : (unsigned long long)hi;
+    }
+    a.k_div_4 = (p->kmer_length + 3) / 4;
+    sentinel_bit = (uint32_t)kb + shift;
+    a.sentinel = 1ull << sentinel_bit;
+    num_tables = 1ull << table_bits;
+    return KDBX_OK;
+}
+
+__global__ void k_unique_count(const unsigned long long* __restrict__ uniq, const unsigned long long* __restrict__ nsel,
+                               unsigned long long sentinel, unsigned long long* __restrict__ out) {
+    unsigned long long c = *nsel;
+    if (c && uniq[c - 1] >= sentinel) --c;
+    *out = c;
+}
+
+// new2all from the queries' SEQUENCES: what New2AllConsole's loader threads do per query on the host
+// (KmerHelper::extract + MinHashFilter + sort + unique, src/console_new2all.cpp:64-94, src/kmer_extract.h:13-119)
+// happens here on the device, straight into the k-mer buffer the probe kernel reads: the host uploads
+// 1 byte per base instead of 8 bytes per k-mer and does no sorting.  Queries are taken in sub-batches
+// bounded by the k-mer budget of the probe pipeline.
+int new2all_sequences_impl(kdbx_ctx* ctx, const kdbx_build_params* params, const char* symbols, const uint64_t* q_off,
+                           uint32_t n_queries, uint32_t* out, uint64_t* unique_kmers, kdbx_stats* stats) {
+    if (!ctx->loaded) return ctx->fail(KDBX_ERR_STATE, "no patterns loaded (call kdbx_load_patterns first)");
+    if (!ctx->tables_loaded) return ctx->fail(KDBX_ERR_STATE, "no k-mer tables loaded (call kdbx_load_hashtables first)");
+    if (n_queries && (!q_off || !out)) return ctx->fail(KDBX_ERR_ARG, "kdbx_new2all_sequences: NULL argument");
+    for (uint32_t q = 0; q < n_queries; ++q)
+        if (q_off[q + 1] < q_off[q]) return ctx->fail(KDBX_ERR_ARG, "kdbx_new2all_sequences: q_off must be non-decreasing");
+    if (n_queries && q_off[n_queries] > q_off[0] && !symbols) return ctx->fail(KDBX_ERR_ARG, "kdbx_new2all_sequences: symbols is NULL");
+    BuildAlphabet alpha{};
+    uint32_t sentinel_bit = 0;
+    uint64_t num_tables = 0;
+    if (int rc = make_build_alphabet(ctx, params, "kdbx_new2all_sequences", alpha, sentinel_bit, num_tables)) return rc;
+    if (num_tables != ctx->num_tables)
+        return ctx->fail(KDBX_ERR_ARG, "kdbx_new2all_sequences: the database has %llu k-mer tables, these parameters imply %llu",
+                         (unsigned long long)ctx->num_tables, (unsigned long long)num_tables);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t N = ctx->N;
+    kdbx_stats s{};
+    uint32_t launches = 0;
+    ctx->ev_used = 0;
+    cudaEvent_t ev0 = ctx->event();
+    if (!ctx->prepared) {  // decoded local lists + nodes, shared with all2all
+        Plan pl;
+        if (int rc = make_plan(ctx, pl)) return rc;
+        const int rc = prepare(ctx, pl, launches);
+        if (rc < 0) return rc;
+        if (int rc2 = check_device_error(ctx)) return rc2;
+    }
+    cudaEvent_t ev1 = ctx->event();
+    if (n_queries == 0 || N == 0) { if (stats) *stats = s; return KDBX_OK; }
+    CK(ctx->counters.ensure(64));
+    CK(ctx->qx_alpha.ensure(sizeof(BuildAlphabet))); CK(ctx->qx_count.ensure(16));
+    CK(cudaMemcpyAsync(ctx->qx_alpha.p, &alpha, sizeof alpha, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // `alpha` lives on this stack frame
+
+    const uint64_t max_kmers = ctx->cfg.query_batch_kmers ? ctx->cfg.query_batch_kmers : ((uint64_t)1 << 28);
+    const uint64_t max_rows = std::max<uint64_t>(1, ((uint64_t)1 << 30) / std::max<uint32_t>(1, N));
+    float ms_probe = 0.f, ms_scatter = 0.f, ms_download = 0.f, ms_extract = 0.f;
+    std::vector<uint64_t> koff;   // k-mer offsets of the sub-batch's queries
+    uint32_t q0 = 0;
+    while (q0 < n_queries) {
+        // a sub-batch: whole queries while their WINDOWS (an upper bound of their k-mers) fit the budget
+        uint32_t q1 = q0 + 1;
+        while (q1 < n_queries && q_off[q1 + 1] - q_off[q0] <= max_kmers && (uint64_t)(q1 + 1 - q0) <= max_rows) ++q1;
+        const uint64_t sym0 = q_off[q0], nsym = q_off[q1] - sym0;
+        CK(ctx->qx_seq.ensure(nsym + 16)); CK(ctx->q_kmers.ensure((nsym + 1) * 8));
+        if (nsym) CK(cudaMemcpyAsync(ctx->qx_seq.p, symbols + sym0, nsym, cudaMemcpyHostToDevice, st));
+        koff.assign(1, 0);
+        cudaEvent_t xa = ctx->event();
+        for (uint32_t q = q0; q < q1; ++q) {
+            const uint64_t len = q_off[q + 1] - q_off[q];
+            unsigned long long cnt = 0;
+            if (len >= alpha.k) {
+                CK(ctx->qx_raw.ensure(len * 8)); CK(ctx->qx_sorted.ensure(len * 8));
+                k_extract_kmers<<<blocks_for(len, 256), 256, 0, st>>>(ctx->qx_seq.as<uint8_t>() + (q_off[q] - sym0), len,
+                                                                      ctx->qx_alpha.as<BuildAlphabet>(), ctx->qx_raw.as<unsigned long long>());
+                size_t tmp = 0;
+                const int end_bit = (int)sentinel_bit + 1;
+                CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, ctx->qx_raw.as<unsigned long long>(), ctx->qx_sorted.as<unsigned long long>(), len, 0, end_bit, st));
+                CK(ctx->cub_tmp.ensure(tmp));
+                CK(cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tmp, ctx->qx_raw.as<unsigned long long>(), ctx->qx_sorted.as<unsigned long long>(), len, 0, end_bit, st));
+                // the query's distinct k-mers land behind those of the queries before it (<= their windows, so they fit)
+                unsigned long long* dst = ctx->q_kmers.as<unsigned long long>() + koff.back();
+                unsigned long long* nsel = ctx->qx_count.as<unsigned long long>();
+                CK(cub::DeviceSelect::Unique(nullptr, tmp, ctx->qx_sorted.as<unsigned long long>(), dst, nsel, len, st));
+                CK(ctx->cub_tmp.ensure(tmp));
+                CK(cub::DeviceSelect::Unique(ctx->cub_tmp.p, tmp, ctx->qx_sorted.as<unsigned long long>(), dst, nsel, len, st));
+                k_unique_count<<<1, 1, 0, st>>>(dst, nsel, alpha.sentinel, nsel + 1);
+                CK(cudaMemcpyAsync(&cnt, nsel + 1, 8, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                launches += 5;
+            }
+            if (unique_kmers) unique_kmers[q] = cnt;
+            koff.push_back(koff.back() + cnt);
+        }
+        cudaEvent_t xb = ctx->event();
+        const uint32_t nq = q1 - q0;
+        CK(ctx->q_off.ensure(((size_t)nq + 1) * 8));
+        CK(cudaMemcpyAsync(ctx->q_off.p, koff.data(), ((size_t)nq + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (int rc = new2all_core(ctx, koff.back(), 0, 0, nq, out + (size_t)q0 * N, s, ms_probe, ms_scatter, ms_download, launches)) return rc;
+        ms_extract += elapsed(xa, xb);
+        q0 = q1;
+    }
+    cudaEvent_t ev2 = ctx->event();
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (int rc = finish_upload(ctx)) return rc;
+    s.ms_prepare = elapsed(ev0, ev1);
+    s.ms_probe = ms_probe; s.ms_scatter = ms_scatter; s.ms_download = ms_download;
+    s.ms_expand = ms_extract;   // reported in the "expand" slot: k-mer extraction + sort + unique of the queries
+    s.ms_total = elapsed(ev0, ev2);
+    s.kernel_launches = launches;
+    s.local_ids = ctx->sum_l; s.flat_ids = ctx->sum_n;
+    if (stats) *stats = s;
+    return KDBX_OK;
+}

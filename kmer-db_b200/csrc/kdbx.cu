@@ -960,6 +960,7 @@ struct kdbx_ctx {
     uint64_t num_tables = 0;
     float ms_upload_tables = 0.f;
     DevBuf slot_off, slots, q_off, q_kmers, q_keys, q_keys2, q_runkeys, q_runcnt, q_out;
+    DevBuf qx_alpha, qx_seq, qx_raw, qx_sorted, qx_count;   // queries from sequences (build.cuh)
 
     std::vector<cudaEvent_t> events;
     size_t ev_used = 0;
@@ -1531,7 +1532,8 @@ void kdbx_close(kdbx_ctx* ctx) {
                       &ctx->cub_tmp, &ctx->order_in, &ctx->order, &ctx->keys_sorted, &ctx->level_start, &ctx->flat, &ctx->jobs, &ctx->hist, &ctx->work, &ctx->bucket_off, &ctx->cursor,
                       &ctx->ucount, &ctx->uoff, &ctx->units, &ctx->counters, &ctx->blockhist, &ctx->tri, &ctx->rowupd, &ctx->first_id,
                       &ctx->sp_cnt, &ctx->sp_counts, &ctx->sp_rowptr, &ctx->sp_col, &ctx->sp_val, &ctx->slot_off, &ctx->slots,
-                      &ctx->q_off, &ctx->q_kmers, &ctx->q_keys, &ctx->q_keys2, &ctx->q_runkeys, &ctx->q_runcnt, &ctx->q_out})
+                      &ctx->q_off, &ctx->q_kmers, &ctx->q_keys, &ctx->q_keys2, &ctx->q_runkeys, &ctx->q_runcnt, &ctx->q_out,
+                      &ctx->qx_alpha, &ctx->qx_seq, &ctx->qx_raw, &ctx->qx_sorted, &ctx->qx_count})
         b->release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->g_push.exec) cudaGraphExecDestroy(ctx->g_push.exec);
@@ -1677,38 +1679,26 @@ int kdbx_new2all_batch(kdbx_ctx* ctx, const uint64_t* kmers, const uint64_t* q_o
     return new2all_impl(ctx, kmers, q_off, n_queries, out, stats);
 }
 
+int kdbx_new2all_sequences(kdbx_ctx* ctx, const kdbx_build_params* params, const char* symbols, const uint64_t* q_off,
+                           uint32_t n_queries, uint32_t* out, uint64_t* unique_kmers, kdbx_stats* stats) {
+    if (!ctx) return KDBX_ERR_ARG;
+    return new2all_sequences_impl(ctx, params, symbols, q_off, n_queries, out, unique_kmers, stats);
+}
+
 int kdbx_builder_open(kdbx_ctx* ctx, const kdbx_build_params* p, kdbx_builder** out) {
     if (!ctx) return KDBX_ERR_ARG;
     if (!p || !out) return ctx->fail(KDBX_ERR_ARG, "kdbx_builder_open: NULL argument");
     *out = nullptr;
-    if (p->kmer_length == 0 || p->bits_per_symbol == 0 || p->bits_per_symbol > 8 || p->alphabet_size < 2 ||
-        p->alphabet_size > (1u << p->bits_per_symbol))
-        return ctx->fail(KDBX_ERR_ARG, "kdbx_builder_open: bad alphabet / k-mer length");
-    const int kb = (int)p->kmer_length * (int)p->bits_per_symbol;
-    const int prefix_bits = kb - 32;
-    const uint32_t shift = prefix_bits < 8 ? (uint32_t)(8 - prefix_bits) : 0u;   // src/kmer_extract.h:36-45
-    if (kb > 62 || kb + (int)shift > 62) return ctx->fail(KDBX_ERR_ARG, "kdbx_builder_open: k-mer does not fit 62 bits");
-    const int table_bits = prefix_bits < 8 ? 8 : prefix_bits;                     // src/prefix_kmer_db.cpp:54-62
-    if (table_bits > 24) return ctx->fail(KDBX_ERR_ARG, "kdbx_builder_open: 2^%d prefix tables are not supported on the device", table_bits);
-    if (!(p->fraction > 0.0)) return ctx->fail(KDBX_ERR_ARG, "kdbx_builder_open: fraction must be positive");
+    BuildAlphabet alpha{};
+    uint32_t sentinel_bit = 0;
+    uint64_t num_tables = 0;
+    if (int rc = make_build_alphabet(ctx, p, "kdbx_builder_open", alpha, sentinel_bit, num_tables)) return rc;
     CK(cudaSetDevice(ctx->device));
     kdbx_builder* b = new kdbx_builder();
     b->ctx = ctx;
-    std::memcpy(b->alpha.map, p->symbol_map, 256);
-    b->alpha.k = p->kmer_length; b->alpha.bits = p->bits_per_symbol; b->alpha.size = p->alphabet_size;
-    b->alpha.preserve = p->preserve_strand ? 1u : 0u; b->alpha.shift = shift;
-    b->alpha.accept_all = !(p->fraction < 1.0) ? 1u : 0u;                         // NullFilter, src/filter.h:120-145
-    b->alpha.lo = 0; b->alpha.hi = ~0ull;
-    if (!b->alpha.accept_all) {                                                   // src/filter.h:40-51
-        const double top = (double)UINT64_MAX;
-        b->alpha.lo = (unsigned long long)(top * p->fraction_start);
-        const double hi = top * (p->fraction_start + p->fraction);
-        b->alpha.hi = hi >= top ? ~0ull : (unsigned long long)hi;
-    }
-    b->alpha.k_div_4 = (p->kmer_length + 3) / 4;
-    b->sentinel_bit = (uint32_t)kb + shift;
-    b->alpha.sentinel = 1ull << b->sentinel_bit;
-    b->num_tables = 1ull << table_bits;
+    b->alpha = alpha;
+    b->sentinel_bit = sentinel_bit;
+    b->num_tables = num_tables;
     auto fail = [&](int code, const char* what) { kdbx_builder_close(b); return ctx->fail(code, "kdbx_builder_open: %s", what); };
     if (b->d_alpha.ensure(sizeof(BuildAlphabet)) != cudaSuccess || b->ps.ensure(sizeof(BuildPerSample)) != cudaSuccess ||
         b->nsel.ensure(16) != cudaSuccess)

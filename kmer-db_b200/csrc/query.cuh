@@ -89,6 +89,65 @@ __global__ void k_query_scatter(const int* __restrict__ num_runs, const unsigned
     }
 }
 
+// Probe, count and scatter the k-mers ctx->q_kmers[0 .. count) of the queries [q_begin, q_end): query q owns the
+// k-mers with global index in [q_off[q], q_off[q+1]) (ctx->q_off, device), the first of the batch being kmer_base.
+// The rows of the batch go to out_rows (HOST memory, (q_end - q_begin) x N).
+int new2all_core(kdbx_ctx* ctx, uint64_t count, uint64_t kmer_base, uint32_t q_begin, uint32_t q_end, uint32_t* out_rows,
+                 kdbx_stats& s, float& ms_probe, float& ms_scatter, float& ms_download, uint32_t& launches) {
+    cudaStream_t st = ctx->stream;
+    const uint32_t N = ctx->N;
+    const uint32_t nq = q_end - q_begin;
+    const uint64_t base = kmer_base;
+    const uint32_t q0 = q_begin, q1 = q_end;
+    {
+        CK(ctx->q_out.ensure((size_t)nq * N * 4 + 16));
+        CK(cudaMemsetAsync(ctx->q_out.p, 0, (size_t)nq * N * 4, st));
+        if (count) {
+            CK(ctx->q_keys.ensure(count * 8)); CK(ctx->q_keys2.ensure(count * 8));
+            CK(ctx->q_runkeys.ensure(count * 8)); CK(ctx->q_runcnt.ensure(count * 4));
+            CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+            unsigned long long* d_hits = ctx->counters.as<unsigned long long>();
+            int* d_runs = ctx->counters.as<int>() + 4;
+            cudaEvent_t a = ctx->event();
+            k_probe<<<blocks_for(count, 256), 256, 0, st>>>(count, ctx->q_kmers.as<uint64_t>(), base, ctx->q_off.as<uint64_t>(), q0, q1,
+                                                             ctx->num_tables, ctx->slot_off.as<uint64_t>(), ctx->slots.as<uint64_t>(),
+                                                             ctx->num_kmers.as<int64_t>(), ctx->P, ctx->q_keys.as<unsigned long long>(), d_hits,
+                                                             ctx->err_flag.as<int>());
+            cudaEvent_t b = ctx->event();
+            int pid_bits = 1; while (pid_bits < 32 && (ctx->P >> pid_bits)) ++pid_bits;
+            int q_bits = 1; while (q_bits < 32 && (nq >> q_bits)) ++q_bits;
+            // keys of misses are all ones: sorting the low 32+q_bits bits still puts them last within
+            // their (truncated) query, and k_query_scatter skips them by value
+            size_t tmp = 0;
+            CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, ctx->q_keys.as<unsigned long long>(), ctx->q_keys2.as<unsigned long long>(), count, 0, 64, st));
+            CK(ctx->cub_tmp.ensure(tmp));
+            CK(cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tmp, ctx->q_keys.as<unsigned long long>(), ctx->q_keys2.as<unsigned long long>(), count, 0, 64, st));
+            (void)pid_bits; (void)q_bits;
+            CK(cub::DeviceRunLengthEncode::Encode(nullptr, tmp, ctx->q_keys2.as<unsigned long long>(), ctx->q_runkeys.as<unsigned long long>(),
+                                                  ctx->q_runcnt.as<uint32_t>(), d_runs, count, st));
+            CK(ctx->cub_tmp.ensure(tmp));
+            CK(cub::DeviceRunLengthEncode::Encode(ctx->cub_tmp.p, tmp, ctx->q_keys2.as<unsigned long long>(), ctx->q_runkeys.as<unsigned long long>(),
+                                                  ctx->q_runcnt.as<uint32_t>(), d_runs, count, st));
+            k_query_scatter<<<ctx->sm_count * 16, 256, 0, st>>>(d_runs, ctx->q_runkeys.as<unsigned long long>(), ctx->q_runcnt.as<uint32_t>(),
+                                                                 ctx->nodes.as<Node>(), ctx->loc.as<uint32_t>(), N, ctx->q_out.as<uint32_t>());
+            cudaEvent_t c = ctx->event();
+            launches += 8;
+            unsigned long long h_hits = 0;
+            CK(cudaMemcpyAsync(&h_hits, d_hits, 8, cudaMemcpyDeviceToHost, st));
+            cudaEvent_t d0 = ctx->event();
+            CK(cudaMemcpyAsync(out_rows, ctx->q_out.p, (size_t)nq * N * 4, cudaMemcpyDeviceToHost, st));
+            cudaEvent_t d1 = ctx->event();
+            CK(cudaStreamSynchronize(st));
+            ms_probe += elapsed(a, b); ms_scatter += elapsed(b, c); ms_download += elapsed(d0, d1);
+            s.hits += h_hits; s.probes += count;
+        } else {
+            CK(cudaMemcpyAsync(out_rows, ctx->q_out.p, (size_t)nq * N * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+    }
+    return check_device_error(ctx);
+}
+
 int new2all_impl(kdbx_ctx* ctx, const uint64_t* kmers, const uint64_t* q_off, uint32_t n_queries, uint32_t* out, kdbx_stats* stats) {
     if (!ctx->loaded) return ctx->fail(KDBX_ERR_STATE, "no patterns loaded (call kdbx_load_patterns first)");
     if (!ctx->tables_loaded) return ctx->fail(KDBX_ERR_STATE, "no k-mer tables loaded (call kdbx_load_hashtables first)");
@@ -125,53 +184,11 @@ int new2all_impl(kdbx_ctx* ctx, const uint64_t* kmers, const uint64_t* q_off, ui
         uint32_t q1 = q0 + 1;
         while (q1 < n_queries && q_off[q1 + 1] - q_off[q0] <= max_kmers && (uint64_t)(q1 + 1 - q0) <= max_rows) ++q1;
         const uint64_t base = q_off[q0], count = q_off[q1] - base;
-        const uint32_t nq = q1 - q0;
-        CK(ctx->q_out.ensure((size_t)nq * N * 4 + 16));
-        CK(cudaMemsetAsync(ctx->q_out.p, 0, (size_t)nq * N * 4, st));
         if (count) {
-            CK(ctx->q_kmers.ensure(count * 8)); CK(ctx->q_keys.ensure(count * 8)); CK(ctx->q_keys2.ensure(count * 8));
-            CK(ctx->q_runkeys.ensure(count * 8)); CK(ctx->q_runcnt.ensure(count * 4));
+            CK(ctx->q_kmers.ensure(count * 8));
             CK(cudaMemcpyAsync(ctx->q_kmers.p, kmers + base, count * 8, cudaMemcpyHostToDevice, st));
-            CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
-            unsigned long long* d_hits = ctx->counters.as<unsigned long long>();
-            int* d_runs = ctx->counters.as<int>() + 4;
-            cudaEvent_t a = ctx->event();
-            k_probe<<<blocks_for(count, 256), 256, 0, st>>>(count, ctx->q_kmers.as<uint64_t>(), base, ctx->q_off.as<uint64_t>(), q0, q1,
-                                                             ctx->num_tables, ctx->slot_off.as<uint64_t>(), ctx->slots.as<uint64_t>(),
-                                                             ctx->num_kmers.as<int64_t>(), ctx->P, ctx->q_keys.as<unsigned long long>(), d_hits,
-                                                             ctx->err_flag.as<int>());
-            cudaEvent_t b = ctx->event();
-            int pid_bits = 1; while (pid_bits < 32 && (ctx->P >> pid_bits)) ++pid_bits;
-            int q_bits = 1; while (q_bits < 32 && (nq >> q_bits)) ++q_bits;
-            // keys of misses are all ones: sorting the low 32+q_bits bits still puts them last within
-            // their (truncated) query, and k_query_scatter skips them by value
-            size_t tmp = 0;
-            CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, ctx->q_keys.as<unsigned long long>(), ctx->q_keys2.as<unsigned long long>(), count, 0, 64, st));
-            CK(ctx->cub_tmp.ensure(tmp));
-            CK(cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tmp, ctx->q_keys.as<unsigned long long>(), ctx->q_keys2.as<unsigned long long>(), count, 0, 64, st));
-            (void)pid_bits; (void)q_bits;
-            CK(cub::DeviceRunLengthEncode::Encode(nullptr, tmp, ctx->q_keys2.as<unsigned long long>(), ctx->q_runkeys.as<unsigned long long>(),
-                                                  ctx->q_runcnt.as<uint32_t>(), d_runs, count, st));
-            CK(ctx->cub_tmp.ensure(tmp));
-            CK(cub::DeviceRunLengthEncode::Encode(ctx->cub_tmp.p, tmp, ctx->q_keys2.as<unsigned long long>(), ctx->q_runkeys.as<unsigned long long>(),
-                                                  ctx->q_runcnt.as<uint32_t>(), d_runs, count, st));
-            k_query_scatter<<<ctx->sm_count * 16, 256, 0, st>>>(d_runs, ctx->q_runkeys.as<unsigned long long>(), ctx->q_runcnt.as<uint32_t>(),
-                                                                 ctx->nodes.as<Node>(), ctx->loc.as<uint32_t>(), N, ctx->q_out.as<uint32_t>());
-            cudaEvent_t c = ctx->event();
-            launches += 8;
-            unsigned long long h_hits = 0;
-            CK(cudaMemcpyAsync(&h_hits, d_hits, 8, cudaMemcpyDeviceToHost, st));
-            cudaEvent_t d0 = ctx->event();
-            CK(cudaMemcpyAsync(out + (size_t)q0 * N, ctx->q_out.p, (size_t)nq * N * 4, cudaMemcpyDeviceToHost, st));
-            cudaEvent_t d1 = ctx->event();
-            CK(cudaStreamSynchronize(st));
-            ms_probe += elapsed(a, b); ms_scatter += elapsed(b, c); ms_download += elapsed(d0, d1);
-            s.hits += h_hits; s.probes += count;
-        } else {
-            CK(cudaMemcpyAsync(out + (size_t)q0 * N, ctx->q_out.p, (size_t)nq * N * 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
         }
-        if (int rc = check_device_error(ctx)) return rc;
+        if (int rc = new2all_core(ctx, count, base, q0, q1, out + (size_t)q0 * N, s, ms_probe, ms_scatter, ms_download, launches)) return rc;
         q0 = q1;
     }
     cudaEvent_t ev2 = ctx->event();

@@ -172,42 +172,45 @@ void run_new2all(const Params& p) {
     read_db(p.files[0], db, true);
     std::cerr << "OK (" << now() - t0 << " seconds)" << std::endl;
     calculator.load_database(db);
-    const Alphabet alphabet = Alphabet::make(db.hdr.alphabet_type);
-    const MinHash filter(db.hdr.fraction, db.hdr.start_fraction, db.hdr.kmer_length);
-    SampleStream stream(p.files[1], alphabet, filter, db.hdr.kmer_length, p.multisample_fasta, p.num_reader_threads);
+    SequenceStream stream(p.files[1], p.multisample_fasta, p.num_reader_threads);
     std::cerr << "Processing queries..." << std::endl;
     t0 = now();
     QueryTableWriter writer(p.files[2], db, p.sparse_out, &p.filters);
-    // queries go to the device in batches (bounded k-mers), rows are written in input order
-    const uint64_t batch_kmers = (uint64_t)1 << 27;
+    // the queries' SEQUENCES go to the device in batches (bounded symbols); k-mer extraction, sort and unique
+    // happen there; rows are written in input order
+    const uint64_t batch_symbols = (uint64_t)1 << 27;
     const size_t N = db.num_samples();
-    std::vector<SampleKmers> batch;
-    Buf<uint64_t> kmers;
-    kmers.set_pinned(true);
-    std::vector<uint64_t> q_off;
+    std::vector<std::string> names;
+    Buf<char> symbols;
+    symbols.set_pinned(true);
+    symbols.reserve(batch_symbols + ((uint64_t)1 << 24));
+    std::vector<uint64_t> q_off, unique;
     std::vector<uint32_t> sims;
     kdbx_stats total{};
     size_t done = 0;
     bool more = true;
-    while (more) {
-        batch.clear(); kmers.clear(); q_off.assign(1, 0);
-        SampleKmers s;
-        while (kmers.size() < batch_kmers && batch.size() < 4096 && (more = stream.next(s))) {
-            const size_t at = kmers.size();
-            kmers.resize(at + s.kmers.size());
-            std::copy(s.kmers.begin(), s.kmers.end(), kmers.data() + at);
-            q_off.push_back(kmers.size());
-            s.kmers.clear(); s.kmers.shrink_to_fit();
-            batch.push_back(std::move(s));
-            s = SampleKmers();
+    SampleSeq s;
+    bool pending = false;   // `s` holds a query that did not fit the previous batch
+    while (more || pending) {
+        names.clear(); symbols.clear(); q_off.assign(1, 0);
+        while (names.size() < 4096) {
+            if (!pending) { more = stream.next(s); if (!more) break; }
+            pending = false;
+            if (!names.empty() && symbols.size() + s.symbols.size() > batch_symbols) { pending = true; break; }
+            const size_t at = symbols.size();
+            symbols.resize(at + s.symbols.size());
+            std::copy(s.symbols.begin(), s.symbols.end(), symbols.data() + at);
+            q_off.push_back(symbols.size());
+            names.push_back(std::move(s.name));
+            s = SampleSeq();
         }
-        if (batch.empty()) break;
-        calculator.one2all_batch(kmers.data(), q_off, sims);
+        if (names.empty()) break;
+        calculator.one2all_sequences(db.hdr, symbols.data(), q_off, sims, unique);
         const kdbx_stats& st = calculator.last_stats();
         total.probes += st.probes; total.hits += st.hits; total.ms_probe += st.ms_probe; total.ms_scatter += st.ms_scatter;
-        total.ms_total += st.ms_total; total.ms_prepare += st.ms_prepare; total.ms_download += st.ms_download;
-        for (size_t q = 0; q < batch.size(); ++q) writer.write_row(batch[q].name, q_off[q + 1] - q_off[q], sims.data() + q * N);
-        done += batch.size();
+        total.ms_total += st.ms_total; total.ms_prepare += st.ms_prepare; total.ms_download += st.ms_download; total.ms_expand += st.ms_expand;
+        for (size_t q = 0; q < names.size(); ++q) writer.write_row(names[q], unique[q], sims.data() + q * N);
+        done += names.size();
         if (done % 10 == 0) std::cerr << "\r" << done << "...                      " << std::flush;
     }
     writer.close();

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "../../include/kdbx.h"
+#include "kmers.h"
 #include "metrics.h"
 #include "trie.h"
 
@@ -201,6 +202,22 @@ public:
         const uint32_t nq = q_off.empty() ? 0 : (uint32_t)(q_off.size() - 1);
         similarities.assign((size_t)nq * num_samples_, 0);
         check(kdbx_new2all_batch(ctx_, kmers, q_off.data(), nq, similarities.data(), &stats_));
+    }
+    // The same from the queries' sequences: k-mer extraction, minhash, sort and unique run on the device with
+    // the database's own parameters (what the reference's loader threads do per query on the host,
+    // src/console_new2all.cpp:64-94).  Query q = symbols[q_off[q] .. q_off[q+1]) (ingest.h: SampleSeq);
+    // unique_kmers receives each query's number of distinct k-mers.
+    void one2all_sequences(const DbHeader& hdr, const char* symbols, const std::vector<uint64_t>& q_off,
+                           std::vector<uint32_t>& similarities, std::vector<uint64_t>& unique_kmers) const {
+        const uint32_t nq = q_off.empty() ? 0 : (uint32_t)(q_off.size() - 1);
+        const Alphabet al = Alphabet::make(hdr.alphabet_type);
+        kdbx_build_params bp{};
+        bp.kmer_length = hdr.kmer_length; bp.bits_per_symbol = (uint32_t)al.bits_per_symbol; bp.alphabet_size = (uint32_t)al.size;
+        bp.preserve_strand = al.preserve_strand ? 1u : 0u; bp.fraction = hdr.fraction; bp.fraction_start = hdr.start_fraction;
+        for (int i = 0; i < 256; ++i) bp.symbol_map[i] = al.map[i];
+        similarities.assign((size_t)nq * num_samples_, 0);
+        unique_kmers.assign(nq, 0);
+        check(kdbx_new2all_sequences(ctx_, &bp, symbols, q_off.data(), nq, similarities.data(), unique_kmers.data(), &stats_));
     }
     const kdbx_stats& last_stats() const { return stats_; }
 

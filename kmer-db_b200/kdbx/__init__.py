@@ -109,7 +109,7 @@ KDBX_SYMBOLS = ["kdbx_abi_version", "kdbx_device_count", "kdbx_open", "kdbx_clos
                 "kdbx_all2all_dense_rows", "kdbx_all2all_dense_rows_device", "kdbx_all2all_dense_part_device", "kdbx_all2all_sparse", "kdbx_free_csr",
                 "kdbx_load_hashtables", "kdbx_new2all_batch", "kdbx_debug_fetch",
                 "kdbx_builder_open", "kdbx_builder_close", "kdbx_builder_adopt", "kdbx_builder_add_sequence", "kdbx_builder_add_kmers",
-                "kdbx_builder_finish", "kdbx_builder_export"]
+                "kdbx_builder_finish", "kdbx_builder_export", "kdbx_new2all_sequences"]
 KDBXH_SYMBOLS = ["kdbxh_last_error", "kdbxh_trie_new", "kdbxh_trie_free", "kdbxh_read_db", "kdbxh_write_db",
                  "kdbxh_synth", "kdbxh_validate", "kdbxh_prefix", "kdbxh_partition", "kdbxh_relabel", "kdbxh_view", "kdbxh_totals_of", "kdbxh_sample_name",
                  "kdbxh_sample_kmers", "kdbxh_write_all2all_csv", "kdbxh_read_db_full", "kdbxh_tables_view",
@@ -160,6 +160,7 @@ def load():
     k.kdbx_builder_add_kmers.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     k.kdbx_builder_finish.argtypes = [C.c_void_p, P(BuildResult)]
     k.kdbx_builder_export.argtypes = [C.c_void_p, P(BuildArrays)]
+    k.kdbx_new2all_sequences.argtypes = [C.c_void_p, P(BuildParams), C.c_char_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, P(Stats)]
     k.kdbx_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
     k.kdbx_debug_fetch.restype = C.c_int64
     h.kdbxh_last_error.restype = C.c_char_p
@@ -492,6 +493,21 @@ class Context:
                                               out.ctypes.data if out.size else None, C.byref(st)))
         return out, st
 
+    def new2all_sequences(self, sequences, k=18, fraction=1.0, fraction_start=0.0, alphabet=None, preserve_strand=False):
+        """sequences: list of bytes (records separated by a byte outside the alphabet) ->
+        (len(sequences) x N uint32 matrix, distinct k-mers per query, stats)."""
+        bp = build_params(k, fraction, fraction_start, alphabet, preserve_strand)
+        q_off = np.zeros(len(sequences) + 1, np.uint64)
+        for i, q in enumerate(sequences):
+            q_off[i + 1] = q_off[i] + len(q)
+        blob = b"".join(sequences)
+        out = np.zeros((len(sequences), self.num_samples), np.uint32)
+        uniq = np.zeros(len(sequences), np.uint64)
+        st = Stats()
+        self._check(self._k.kdbx_new2all_sequences(self._p, C.byref(bp), blob if blob else None, q_off.ctypes.data, len(sequences),
+                                                   out.ctypes.data if out.size else None, uniq.ctypes.data if uniq.size else None, C.byref(st)))
+        return out, uniq, st
+
     def row_updates(self):
         out = np.zeros(self.num_samples, dtype=np.uint64)
         self._check(self._k.kdbx_row_updates(self._p, out.ctypes.data if out.size else None))
@@ -508,6 +524,21 @@ class Context:
 NT_MAP = {"A": 0, "C": 1, "G": 2, "T": 3, "U": 3}
 
 
+def build_params(k=18, fraction=1.0, fraction_start=0.0, alphabet=None, preserve_strand=False, table_capacity_hint=0):
+    """kdbx_build_params for an alphabet given as dict symbol -> code (upper case; lower case is added)."""
+    alphabet = alphabet or NT_MAP
+    size = max(alphabet.values()) + 1
+    bits = max(1, (size - 1).bit_length())
+    bp = BuildParams(k, bits, size, 1 if preserve_strand else 0, fraction, fraction_start)
+    for i in range(256):
+        bp.symbol_map[i] = -1
+    for ch, code in alphabet.items():
+        bp.symbol_map[ord(ch.upper())] = code
+        bp.symbol_map[ord(ch.lower())] = code
+    bp.table_capacity_hint = table_capacity_hint
+    return bp
+
+
 class DeviceBuilder:
     """kdbx_builder_* on a Context (the device-side `build`).  alphabet: dict symbol -> code (upper case;
     lower case is added), default nucleotides."""
@@ -516,16 +547,8 @@ class DeviceBuilder:
                  table_capacity_hint=0):
         self._ctx = ctx
         self._k = ctx._k
-        alphabet = alphabet or NT_MAP
-        size = max(alphabet.values()) + 1
-        bits = max(1, (size - 1).bit_length())
-        bp = BuildParams(k, bits, size, 1 if preserve_strand else 0, fraction, fraction_start)
-        for i in range(256):
-            bp.symbol_map[i] = -1
-        for ch, code in alphabet.items():
-            bp.symbol_map[ord(ch.upper())] = code
-            bp.symbol_map[ord(ch.lower())] = code
-        bp.table_capacity_hint = table_capacity_hint
+        bp = build_params(k, fraction, fraction_start, alphabet, preserve_strand, table_capacity_hint)
+        bits = bp.bits_per_symbol
         p = C.c_void_p()
         ctx._check(self._k.kdbx_builder_open(ctx._p, C.byref(bp), C.byref(p)))
         self._p = p

@@ -164,3 +164,40 @@ def test_device_builder_misuse(libs):
         with libs.DeviceBuilder(ctx, k=18) as b:
             with pytest.raises(libs.KdbxError, match="stage the database"):
                 b.adopt()
+
+
+@pytest.mark.parametrize("k,fraction", [(18, 1.0), (21, 0.4)])
+def test_new2all_from_sequences_equals_new2all_from_host_kmers(libs, tmp_path, k, fraction):
+    """kdbx_new2all_sequences (extraction, minhash, sort, unique on the device) gives the rows and the k-mer counts
+    of kdbx_new2all_batch fed with the host's extraction of the same files; sub-batching does not change them."""
+    rng = np.random.default_rng(77 + k)
+    base = "".join(rng.choice(list("ACGT"), size=8000))
+    files, seqs = [], []
+    for s_ in range(14):
+        x = list(base)
+        for pos in rng.integers(0, len(x), size=60 * (s_ + 1)):
+            x[pos] = "ACGT"[int(rng.integers(0, 4))]
+        x = "".join(x)
+        recs = [(f"q{s_}a", x[:5000]), (f"q{s_}b", x[5000:] + "NN" + x[:200].lower())]
+        _write_fasta(tmp_path / f"q{s_}.fa", recs)
+        files.append(str(tmp_path / f"q{s_}.fa"))
+        seqs.append(b"".join(r.encode() + b"\0" for _, r in recs))
+    seqs.append(b"ACGT")     # shorter than k: no k-mers
+    (tmp_path / "list.txt").write_text("\n".join(files) + "\n")
+    samples = libs.load_samples(tmp_path / "list.txt", k=k, fraction=fraction)
+    db = libs.Trie.build(samples[:10], k=k, fraction=fraction)
+    want_sets = [s[1] for s in samples] + [np.zeros(0, np.uint64)]
+    for batch in (0, 4000):
+        with libs.Context(device=0, query_batch_kmers=batch) as ctx:
+            ctx.load_patterns(db)
+            ctx.load_hashtables(db)
+            want, _ = ctx.new2all_batch(want_sets)
+            got, uniq, st = ctx.new2all_sequences(seqs, k=k, fraction=fraction)
+        assert uniq.tolist() == [len(s) for s in want_sets]
+        assert np.array_equal(got, want)
+        assert st.probes == sum(len(s) for s in want_sets)
+    with libs.Context(device=0) as ctx:
+        ctx.load_patterns(db)
+        ctx.load_hashtables(db)
+        with pytest.raises(libs.KdbxError, match="k-mer tables"):
+            ctx.new2all_sequences(seqs, k=22 if k != 22 else 23)     # another number of prefix tables than the database has
