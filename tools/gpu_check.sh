@@ -21,7 +21,7 @@ for step in "$@"; do
     bench_chunks) for c in 16777216 33554432; do timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --chunk-ids $c > "$OUT/bench_chunk_$c.json" 2> "$OUT/bench_chunk_$c.err"; echo "bench_chunk $c rc=$?" | tee -a "$OUT/summary.txt"; done;;
     bench_tiles) for cfg in "32 1024 1024" "16 1024 512" "16 1024 1024" "8 1024 256" "32 1024 512"; do set -- $cfg; timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --tile-rows $1 --tile-cols $2 --scatter-threads $3 > "$OUT/bench_tile_$1_$2_$3.json" 2> "$OUT/bench_tile_$1_$2_$3.err"; echo "bench_tile $cfg rc=$?" | tee -a "$OUT/summary.txt"; done;;
     ncu_stages) timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:k_expand|k_job_hist|k_job_fill|k_scatter_add|k_decode_locals" -s 41 -c 5 -f -o "$OUT/stages_cfg2" python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_stages.out" 2>&1; echo "ncu_stages rc=$?" | tee -a "$OUT/summary.txt";;
-    scale) for n in ${SCALE_NS:-2}; do for mode in weak strong; do timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 5 --warmup 3 --scaling $mode > "$OUT/scale_${mode}_$n.json" 2> "$OUT/scale_${mode}_$n.err"; echo "scale $mode $n rc=$?" | tee -a "$OUT/summary.txt"; done; done;;
+    scale) for n in ${SCALE_NS:-2}; do for mode in ${SCALE_MODES:-weak strong}; do timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 5 --warmup 3 --scaling $mode > "$OUT/scale_${mode}_$n.json" 2> "$OUT/scale_${mode}_$n.err"; echo "scale $mode $n rc=$?" | tee -a "$OUT/summary.txt"; done; done;;
     tests_build) timeout 900 python -m pytest tests/test_gpu_build.py -m gpu -x -q > "$OUT/pytest_build.log" 2>&1; echo "pytest_build rc=$?" | tee -a "$OUT/summary.txt";;
     bench_shard) for sh in ${SHARDS:-1/2 7/8}; do tag=$(echo $sh | tr / _); timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --emulate-shard $sh > "$OUT/bench_shard_$tag.json" 2> "$OUT/bench_shard_$tag.err"; echo "bench_shard $sh rc=$?" | tee -a "$OUT/summary.txt"; done;;
     ncu_stages2) timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:k_job_hist|k_job_fill|k_decode_locals" -s 3 -c 3 -f -o "$OUT/stages2_cfg2" python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_stages2.out" 2>&1; echo "ncu_stages2 rc=$?" | tee -a "$OUT/summary.txt";;
