@@ -345,11 +345,14 @@ __global__ void k_expand(uint64_t p0, uint64_t p1, const Node* __restrict__ node
 // pattern's full list is its parent's full list followed by its own local ids, so the patterns of
 // one num_samples level — whose parents all sit on earlier levels, n_parent < n — are expanded by
 // two contiguous copies each.  One launch per level, ascending; no pointer chasing at all.
-template <uint32_t kLevelLanes>
+// (8 lanes per pattern measured best: 17.1 ms per step at config 2 against 18.4 with 16 and 24.2 with 32,
+// profiles/r01_small_ab.txt)
+constexpr uint32_t kLevelLanes = 8;
+template <uint32_t kLanes>
 __global__ void k_expand_level(uint32_t count, const uint32_t* __restrict__ order, const Node* __restrict__ nodes,
                                const uint64_t* __restrict__ noff, const uint32_t* __restrict__ loc, uint32_t* flat, uint32_t* first_id) {
-    const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / kLevelLanes;
-    const uint32_t sub = threadIdx.x & (kLevelLanes - 1);
+    const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
+    const uint32_t sub = threadIdx.x & (kLanes - 1);
     const bool have = gid < count;
     Node nd; nd.parent = -1; nd.n = 0; nd.l = 0; nd.last = 0; nd.loff = 0; nd.up2 = nd.up3 = -1;
     uint32_t* dst = flat;
@@ -367,12 +370,12 @@ __global__ void k_expand_level(uint32_t count, const uint32_t* __restrict__ orde
         const uint4* src = reinterpret_cast<const uint4*>(flat + noff[nd.parent]);
         uint4* d4 = reinterpret_cast<uint4*>(dst);
         const uint32_t n4 = (npar + 3u) >> 2;
-        for (uint32_t j = sub; j < n4; j += kLevelLanes) d4[j] = src[j];
+        for (uint32_t j = sub; j < n4; j += kLanes) d4[j] = src[j];
     }
     __syncwarp();  // the tail of the 128-bit copy must land before the own ids that overwrite it
     if (have) {
         const uint32_t* own = loc + nd.loff;
-        for (uint32_t j = sub; j < nd.l; j += kLevelLanes) dst[npar + j] = own[j];
+        for (uint32_t j = sub; j < nd.l; j += kLanes) dst[npar + j] = own[j];
     }
 }
 
@@ -534,19 +537,8 @@ __device__ __forceinline__ void enumerate_jobs(uint64_t lo, uint64_t hi, uint32_
             const uint32_t* rows = loc + nd.loff;
             const uint32_t first_id = fid;
             uint32_t run_i = 0, run_k = 0, run_rb = 0, run_last = 0;
-#ifdef KDBX_ALT
-            uint32_t rr[kSmallL];   // all the pattern's rows in flight at once instead of one dependent load per turn
-#pragma unroll
-            for (uint32_t j = 0; j < kSmallL; ++j) rr[j] = j < nd.l ? rows[j] : 0u;
-#endif
-#pragma unroll
-            for (uint32_t j = 0; j < kSmallL; ++j) {
-                if (j >= nd.l) break;
-#ifdef KDBX_ALT
-                const uint32_t row = rr[j];
-#else
+            for (uint32_t j = 0; j < nd.l; ++j) {
                 const uint32_t row = rows[j];
-#endif
                 const bool active = row >= row_begin && row < row_end;
                 const uint32_t rb = row >> rb_shift;
                 if (active) updates += first + j;
@@ -583,11 +575,7 @@ __device__ __forceinline__ void enumerate_jobs(uint64_t lo, uint64_t hi, uint32_
 // (block, key) pair its exact slot range, so the fill pass needs no global atomics at all.
 constexpr uint32_t kSmemKeys = 2048;
 constexpr int kBucketThreads = 256;
-#ifdef KDBX_ALT
-#define KDBX_BUCKET_BOUNDS __launch_bounds__(kBucketThreads, 5)
-#else
 #define KDBX_BUCKET_BOUNDS __launch_bounds__(kBucketThreads)
-#endif
 
 __device__ __forceinline__ void block_slice(uint64_t p0, uint64_t p1, uint64_t& lo, uint64_t& hi) {
     const uint64_t per = (p1 - p0 + gridDim.x - 1) / gridDim.x;
@@ -949,7 +937,6 @@ struct kdbx_ctx {
     bool upload_pending = false;          // KDBX_FLAG_ASYNC_UPLOAD: copies may still be in flight
     kdbx_config cfg{};
     std::string err;
-    uint32_t level_lanes = 8;   // lanes per pattern in the level-order expansion (KDBX_LEVEL_LANES: 8, 16 or 32)
 
     // staged trie (raw, as uploaded)
     uint64_t P = 0;
@@ -1343,16 +1330,9 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
                     for (size_t k = 0; k < ctx->levels.size(); ++k) {  // ascending num_samples: parents first
                         const uint32_t b = ctx->levels[k].first, e = ctx->levels[k].second;
                         if (e <= b) continue;
-                        const uint32_t* ord = ctx->order.as<uint32_t>() + b;
-                        if (ctx->level_lanes == 16)
-                            k_expand_level<16><<<blocks_for((uint64_t)(e - b) * 16, 256), 256, 0, st>>>(e - b, ord, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(),
-                                                                                                     ctx->loc.as<uint32_t>(), ctx->flat.as<uint32_t>(), ctx->first_id.as<uint32_t>());
-                        else if (ctx->level_lanes == 32)
-                            k_expand_level<32><<<blocks_for((uint64_t)(e - b) * 32, 256), 256, 0, st>>>(e - b, ord, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(),
-                                                                                                     ctx->loc.as<uint32_t>(), ctx->flat.as<uint32_t>(), ctx->first_id.as<uint32_t>());
-                        else
-                            k_expand_level<8><<<blocks_for((uint64_t)(e - b) * 8, 256), 256, 0, st>>>(e - b, ord, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(),
-                                                                                                   ctx->loc.as<uint32_t>(), ctx->flat.as<uint32_t>(), ctx->first_id.as<uint32_t>());
+                        k_expand_level<kLevelLanes><<<blocks_for((uint64_t)(e - b) * kLevelLanes, 256), 256, 0, st>>>(
+                            e - b, ctx->order.as<uint32_t>() + b, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->loc.as<uint32_t>(),
+                            ctx->flat.as<uint32_t>(), ctx->first_id.as<uint32_t>());
                     }
                 })) return rc;
         }
@@ -1535,7 +1515,6 @@ int kdbx_open(const kdbx_config* cfg, kdbx_ctx** out) {
     ctx->device = dev;
     ctx->sm_count = pr.multiProcessorCount;
     if (cfg) ctx->cfg = *cfg;
-    if (const char* e = std::getenv("KDBX_LEVEL_LANES")) { const int v = std::atoi(e); if (v == 16 || v == 32) ctx->level_lanes = (uint32_t)v; }
     if ((e = cudaSetDevice(dev)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev_up_begin)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_up_hdr)) != cudaSuccess ||

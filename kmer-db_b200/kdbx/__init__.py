@@ -124,7 +124,7 @@ def load():
     global _libs
     if _libs is not None:
         return _libs
-    so, hso = LIB_DIR / os.environ.get("KDBX_LIB", "libkdbx.so"), LIB_DIR / "libkdbx_host.so"
+    so, hso = LIB_DIR / "libkdbx.so", LIB_DIR / "libkdbx_host.so"
     if not so.exists() or not hso.exists():
         raise KdbxError(f"{so} / {hso} not built: run `make -C {_PKG}` (or __graft_entry__.build()); "
                         "there is no fallback implementation")
