@@ -211,3 +211,22 @@ def test_relabel_moves_the_matrix_block(libs, oracle):
     assert np.array_equal(moved, want)
     with pytest.raises(libs.KdbxError, match="relabel"):
         t.relabel(1, 64)
+
+
+def test_partition_into_more_parts_than_patterns(libs, oracle):
+    """Empty parts are valid one-pattern tries (the sentinel) whose matrix is zero."""
+    t = libs.Trie.synth(num_samples=6, num_clusters=1, genome_kmers=40, seed=2, mutation_rate=0.05)
+    N = t.num_samples
+    full, U = ou.oracle_all2all(oracle, N, t.arrays())
+    P = t.num_patterns
+    parts = P + 5
+    acc = np.zeros_like(full)
+    owned, empty = 0, 0
+    for r in range(parts):
+        sub, u = t.partition(parts, r)
+        sub.validate()
+        tri, _ = ou.oracle_all2all(oracle, N, sub.arrays())
+        acc += tri
+        owned += u
+        empty += int(sub.num_patterns == 1)
+    assert np.array_equal(acc, full) and owned == U and empty >= 5

@@ -27,6 +27,7 @@ for step in "$@"; do
     ncu_stages2) timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:k_job_hist|k_job_fill|k_decode_locals" -s 3 -c 3 -f -o "$OUT/stages2_cfg2" python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_stages2.out" 2>&1; echo "ncu_stages2 rc=$?" | tee -a "$OUT/summary.txt";;
     bench2) timeout 900 python bench.py --no-cpu-baseline > "$OUT/bench2.json" 2> "$OUT/bench2.err"; echo "bench2 rc=$?" | tee -a "$OUT/summary.txt";;
     cli_trace) D=/tmp/kdbx_modes; ( time kmer-db_b200/bin/kmer-db-b200 new2all $D/n2a.ours.db $D/q.list $D/t.csv ) > "$OUT/cli_new2all.txt" 2>&1; ( time kmer-db_b200/bin/kmer-db-b200 all2all $D/n2a.ours.db $D/t2.csv ) > "$OUT/cli_all2all.txt" 2>&1; ( time kmer-db_b200/bin/kmer-db-b200 build $D/db.list $D/t.db ) > "$OUT/cli_build.txt" 2>&1; ( time oracle/_ref/kmer-db new2all -t 16 $D/n2a.ref.db $D/q.list $D/t3.csv ) > "$OUT/ref_new2all.txt" 2>&1; ( time python -c "import ctypes,time; t=time.time(); l=ctypes.CDLL('libcudart.so.12'); l.cudaFree(0); print('cuda init', time.time()-t)" ) > "$OUT/cuda_init.txt" 2>&1; echo "cli_trace rc=$?" | tee -a "$OUT/summary.txt";;
+    bench_2000) timeout 1200 python bench.py --samples 2000 --clusters 8 --steps 3 --warmup 3 --no-cpu-baseline > "$OUT/bench_2000.json" 2> "$OUT/bench_2000.err"; echo "bench_2000 rc=$?" | tee -a "$OUT/summary.txt";;
     test_multi) timeout 600 python -m pytest tests -m gpu -x -q -k "multi_gpu or sharding" > "$OUT/pytest_multi.log" 2>&1; echo "pytest_multi rc=$?" | tee -a "$OUT/summary.txt";;
     modes) timeout 1500 python tools/bench_modes.py --out-dir /tmp/kdbx_modes > "$OUT/modes.jsonl" 2> "$OUT/modes.err"; echo "modes rc=$?" | tee -a "$OUT/summary.txt";;
     *) echo "unknown step $step";;
