@@ -183,13 +183,46 @@ __device__ __forceinline__ uint32_t gamma_next(const uint64_t* __restrict__ w, u
 // staged in shared memory and written out with coalesced stores (a thread writing its own list
 // straight to HBM costs one 32-byte sector per 4-byte id); blocks whose lists do not fit the stage
 // write directly.
+//
+// With one column window (N <= tile_cols) a job is fully described by a run of local ids inside one
+// block of matrix rows, so the decoder — which has every id in hand — also counts the jobs per key
+// and their updates (DecodeHist): the first of the two job-enumeration passes of the bucketing
+// stage is then not needed at all.  The rule must equal enumerate_jobs' exactly: a run ends where
+// the row block changes and, for lists longer than kSmallL (taken 32 positions at a time by a
+// warp there), at every multiple of 32 positions; a job counts iff its weight and its number of
+// updates k*i + k(k-1)/2 are non-zero.
 constexpr int kDecodeThreads = 128;
 constexpr uint32_t kDecodeStage = 10240;  // ids (40 KB)
+constexpr uint32_t kSmallL = 8;           // see enumerate_jobs
+constexpr uint32_t kDecodeHistKeys = 64;
+struct DecodeHist {
+    uint32_t enabled, rb_shift, nkeys;
+    uint64_t per;                       // patterns per block of the fill pass (a multiple of kDecodeThreads)
+    uint32_t* blockhist;                // [fill block][key]
+    unsigned long long* work;           // [key]
+    unsigned long long* total_updates;
+    const uint32_t* W;
+};
 __global__ void __launch_bounds__(kDecodeThreads)
 k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __restrict__ loff,
                 const uint32_t* __restrict__ bits, const uint64_t* __restrict__ poff, const uint64_t* __restrict__ payload,
-                uint64_t payload_words, uint32_t* __restrict__ loc, uint32_t N, int* __restrict__ err) {
+                uint64_t payload_words, uint32_t* __restrict__ loc, uint32_t N, int* __restrict__ err, DecodeHist dh) {
     __shared__ uint32_t s_ids[kDecodeStage];
+    // per key: jobs in the top 12 bits, their updates in units of 1024 in the low 20 (a block's 128 patterns
+    // hold at most 128 * 32 runs per key and 128 * N * N / 2 / 1024 < 2^20 such units with N <= 1024) — ONE
+    // 32-bit shared-memory reduction per run.  The updates only size the scatter kernel's work units, so the
+    // rounding is harmless; the job counts are exact.
+    __shared__ uint32_t s_pack[kDecodeHistKeys];
+    if (dh.enabled) {
+        if (threadIdx.x < kDecodeHistKeys) s_pack[threadIdx.x] = 0;
+        __syncthreads();
+    }
+    unsigned long long my_updates = 0;
+    // closes the run of k rows that starts at list position i (all in row block rb)
+    auto close_run = [&](uint32_t rb, uint32_t i, uint32_t k, uint32_t w) {
+        const uint32_t upd = k * i + k * (k - 1u) / 2u;   // < 32 * 1024 + 496
+        if (w != 0 && upd != 0) atomicAdd(&s_pack[rb], (1u << 20) | ((upd + 512u) >> 10));
+    };
     const uint64_t p0 = (uint64_t)blockIdx.x * kDecodeThreads;
     const uint64_t p = p0 + threadIdx.x;
     const uint64_t p_end = p0 + kDecodeThreads < P ? p0 + kDecodeThreads : P;
@@ -202,9 +235,12 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
             uint32_t* out = staged ? s_ids + (nd.loff - base) : loc + nd.loff;
             // the parent's list must end before this one starts, or full lists would not ascend
             const uint32_t floor_id = nd.parent >= 0 && nodes[nd.parent].l ? nodes[nd.parent].last + 1u : 0u;
+            const uint32_t first = nd.n - nd.l;
+            if (dh.enabled) my_updates = (unsigned long long)nd.l * first + (unsigned long long)nd.l * (nd.l - 1u) / 2u;
             if (nd.l == 1) {
                 out[0] = nd.last;
                 if (nd.last < floor_id) atomicExch(err, 3);
+                if (dh.enabled) close_run(nd.last >> dh.rb_shift, first, 1u, dh.W[p]);
             } else {
                 const uint32_t nb = bits[p];
                 const uint64_t po = poff[p];
@@ -238,7 +274,22 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
                     uint32_t cur = nd.last - (uint32_t)sum;
                     if (cur < floor_id) atomicExch(err, 3);
                     out[0] = cur;
-                    for (uint32_t i = 1; i < nd.l; ++i) { cur += out[i]; out[i] = cur; }
+                    if (!dh.enabled) {
+                        for (uint32_t i = 1; i < nd.l; ++i) { cur += out[i]; out[i] = cur; }
+                    } else {
+                        const uint32_t w = dh.W[p];
+                        const bool rounds = nd.l > kSmallL;   // longer lists are enumerated 32 positions at a time
+                        uint32_t run_j = 0, run_rb = cur >> dh.rb_shift;
+                        for (uint32_t i = 1; i < nd.l; ++i) {
+                            cur += out[i]; out[i] = cur;
+                            const uint32_t rb = cur >> dh.rb_shift;
+                            if (rb != run_rb || (rounds && (i & 31u) == 0)) {
+                                close_run(run_rb, first + run_j, i - run_j, w);
+                                run_j = i; run_rb = rb;
+                            }
+                        }
+                        close_run(run_rb, first + run_j, nd.l - run_j, w);
+                    }
                 } else {
                     for (uint32_t i = 0; i < nd.l; ++i) out[i] = 0;  // never chased: the call fails on the error flag
                 }
@@ -248,6 +299,17 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
     if (staged) {
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < (uint32_t)total; i += kDecodeThreads) loc[base + i] = s_ids[i];
+    }
+    if (dh.enabled) {
+        for (int o = 16; o; o >>= 1) my_updates += __shfl_xor_sync(0xffffffffu, my_updates, o);
+        if ((threadIdx.x & 31) == 0 && my_updates) atomicAdd(dh.total_updates, my_updates);
+        __syncthreads();
+        // this block's 128 patterns lie inside one block of the fill pass (dh.per is a multiple of 128)
+        if (threadIdx.x < dh.nkeys && s_pack[threadIdx.x]) {
+            const uint32_t pk = s_pack[threadIdx.x];
+            atomicAdd(&dh.blockhist[(p0 / dh.per) * dh.nkeys + threadIdx.x], pk >> 20);
+            atomicAdd(&dh.work[threadIdx.x], ((unsigned long long)(pk & 0xFFFFFu) << 10) + (pk >> 20));  // never 0 for a used key
+        }
     }
 }
 
@@ -509,7 +571,6 @@ __device__ __forceinline__ void jobs_of_pattern_warp(const Node& nd, uint64_t ba
 // lane walks the rows of its own pattern when there are at most kSmallL of them — 32 patterns in
 // flight per warp instead of one; longer local lists are then taken one by one by the whole warp.
 // emit(key, job, updates, w) may be called by any lane; `updates` accumulates U per lane.
-constexpr uint32_t kSmallL = 8;
 template <class Emit>
 __device__ __forceinline__ void enumerate_jobs(uint64_t lo, uint64_t hi, uint32_t warp, uint32_t nwarps,
                                                const Node* __restrict__ nodes, const uint64_t* __restrict__ noff, uint64_t base0,
@@ -577,25 +638,25 @@ constexpr uint32_t kSmemKeys = 2048;
 constexpr int kBucketThreads = 256;
 #define KDBX_BUCKET_BOUNDS __launch_bounds__(kBucketThreads)
 
-__device__ __forceinline__ void block_slice(uint64_t p0, uint64_t p1, uint64_t& lo, uint64_t& hi) {
-    const uint64_t per = (p1 - p0 + gridDim.x - 1) / gridDim.x;
+__device__ __forceinline__ void block_slice(uint64_t p0, uint64_t p1, uint64_t& lo, uint64_t& hi, uint64_t per_given = 0) {
+    const uint64_t per = per_given ? per_given : (p1 - p0 + gridDim.x - 1) / gridDim.x;
     lo = p0 + (uint64_t)blockIdx.x * per;
-    hi = lo + per < p1 ? lo + per : p1;
     if (lo > p1) lo = p1;
+    hi = lo + per < p1 ? lo + per : p1;
 }
 
 __global__ void KDBX_BUCKET_BOUNDS
 k_job_hist_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
                 const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, const uint32_t* __restrict__ loc, const uint32_t* __restrict__ first_ids, uint32_t resident,
                 uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin, uint32_t row_end, uint32_t nkeys, uint32_t* __restrict__ blockhist,
-                unsigned long long* __restrict__ work, unsigned long long* __restrict__ total_updates) {
+                unsigned long long* __restrict__ work, unsigned long long* __restrict__ total_updates, uint64_t per) {
     __shared__ uint32_t s_hist[kSmemKeys];
     __shared__ unsigned long long s_work[kSmemKeys];
     for (uint32_t k = threadIdx.x; k < nkeys; k += blockDim.x) { s_hist[k] = 0; s_work[k] = 0; }
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     uint64_t lo, hi;
-    block_slice(p0, p1, lo, hi);
+    block_slice(p0, p1, lo, hi, per);
     unsigned long long updates = 0;
     const uint32_t* flat = flat_all + (resident ? noff[p0] : 0ull);  // the chunk's lists start at its first pattern
     enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, loc, first_ids, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
@@ -649,14 +710,14 @@ __global__ void KDBX_BUCKET_BOUNDS
 k_job_fill_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint64_t* __restrict__ noff,
                 const uint32_t* __restrict__ W, const uint32_t* __restrict__ flat_all, const uint32_t* __restrict__ loc, const uint32_t* __restrict__ first_ids, uint32_t resident,
                 uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t row_begin, uint32_t row_end, uint32_t nkeys, const uint32_t* __restrict__ blockbase,
-                Job* __restrict__ jobs) {
+                Job* __restrict__ jobs, uint64_t per) {
     __shared__ uint32_t s_next[kSmemKeys];
     const uint32_t* mine = blockbase + (size_t)blockIdx.x * nkeys;
     for (uint32_t k = threadIdx.x; k < nkeys; k += blockDim.x) s_next[k] = mine[k];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     uint64_t lo, hi;
-    block_slice(p0, p1, lo, hi);
+    block_slice(p0, p1, lo, hi, per);
     unsigned long long updates = 0;
     const uint32_t* flat = flat_all + (resident ? noff[p0] : 0ull);  // the chunk's lists start at its first pattern
     enumerate_jobs(lo, hi, warp, nwarps, nodes, noff, noff[p0], W, flat, loc, first_ids, T, tile_cols, rb_shift, row_begin, row_end, lane, updates,
@@ -1117,7 +1178,7 @@ int launch_level_graph(kdbx_ctx* ctx, kdbx_ctx::LevelGraph& g, std::initializer_
 }
 
 // scans + node packing + W + gamma decode.  Leaves sum_l / sum_n on the host (one sync).
-int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
+int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches, const DecodeHist* decode_hist = nullptr) {
     const uint64_t P = ctx->P;
     cudaStream_t st = ctx->stream;
     CK(ctx->loff.ensure((P + 1) * 8)); CK(ctx->noff.ensure((P + 1) * 8)); CK(ctx->coff.ensure((P + 1) * 8));
@@ -1205,9 +1266,11 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches) {
     }
     CK(ctx->loc.ensure((ctx->sum_l + 32) * 4));
     CK(cudaStreamWaitEvent(st, ctx->ev_up_payload, 0));  // the payload may still be on its way (second H2D stream)
+    DecodeHist dh{};
+    if (decode_hist) { dh = *decode_hist; dh.W = ctx->W.as<uint32_t>(); }
     k_decode_locals<<<blocks_for(P, kDecodeThreads), kDecodeThreads, 0, st>>>(P, ctx->nodes.as<Node>(), ctx->loff.as<uint64_t>(), ctx->bits.as<uint32_t>(), ctx->poff.as<uint64_t>(),
                                                          ctx->payload.as<uint64_t>(), ctx->payload_words, ctx->loc.as<uint32_t>(), ctx->N,
-                                                         ctx->err_flag.as<int>());
+                                                         ctx->err_flag.as<int>(), dh);
     launches += 1;
     CK(cudaGetLastError());
     // chunk boundaries
@@ -1275,13 +1338,34 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
 
     cudaEvent_t ev_start = ctx->event();
     if (cells) CK(cudaMemsetAsync(d_out, 0, cells * 4, st));
-    const int nchunks_or_err = prepare(ctx, pl, launches);
+    const uint32_t nkeys = pl.RB * pl.T;
+    const unsigned wide_grid = (unsigned)(ctx->sm_count * 8);
+    const bool smem_buckets = nkeys <= kSmemKeys;
+    // patterns per block of the bucketing passes: a multiple of the decoder's block, so that the decoder can
+    // count jobs per (fill block, key) itself (DecodeHist)
+    const uint64_t per_block = (((ctx->P + wide_grid - 1) / wide_grid) + kDecodeThreads - 1) / kDecodeThreads * kDecodeThreads;
+    CK(ctx->counters.ensure(64));
+    unsigned long long* d_total_updates = ctx->counters.as<unsigned long long>();
+    uint32_t* d_unit_counter = ctx->counters.as<uint32_t>() + 4;
+    CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+    // one column window, all rows, one part: the decoder counts the jobs and the first enumeration pass is skipped
+    bool hist_by_decoder = pl.T == 1 && nkeys <= kDecodeHistKeys && nkeys > 0 && cells > 0 && row_begin == 0 && row_end == ctx->N &&
+                           num_parts == 1 && !(ctx->cfg.flags & KDBX_FLAG_CHUNKED_LISTS);
+    DecodeHist dh{};
+    if (hist_by_decoder) {
+        CK(ctx->blockhist.ensure((size_t)wide_grid * nkeys * 4 + 16));
+        CK(ctx->work.ensure(((size_t)nkeys + 1) * 8));
+        CK(cudaMemsetAsync(ctx->blockhist.p, 0, (size_t)wide_grid * nkeys * 4, st));
+        CK(cudaMemsetAsync(ctx->work.p, 0, ((size_t)nkeys + 1) * 8, st));
+        dh.enabled = 1; dh.rb_shift = pl.rb_shift; dh.nkeys = nkeys; dh.per = per_block;
+        dh.blockhist = ctx->blockhist.as<uint32_t>(); dh.work = ctx->work.as<unsigned long long>(); dh.total_updates = d_total_updates;
+    }
+    const int nchunks_or_err = prepare(ctx, pl, launches, hist_by_decoder ? &dh : nullptr);
     if (nchunks_or_err < 0) return nchunks_or_err;
     const uint32_t nchunks = (uint32_t)nchunks_or_err;
     std::vector<uint64_t> bounds(nchunks + 1);
     cudaEvent_t ev_prepared = ctx->event();
 
-    const uint32_t nkeys = pl.RB * pl.T;
     if (cells == 0 || nkeys == 0) {  // N <= 1 or an empty row range: no cell exists
         CK(cudaStreamSynchronize(st));
         s.ms_prepare = elapsed(ev_start, ev_prepared);
@@ -1315,10 +1399,10 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     CK(ctx->bucket_off.ensure(((size_t)nkeys + 1) * 4)); CK(ctx->cursor.ensure(((size_t)nkeys + 1) * 4));
     CK(ctx->ucount.ensure(((size_t)nkeys + 1) * 4)); CK(ctx->uoff.ensure(((size_t)nkeys + 1) * 4));
     if (!resident) CK(ctx->units.ensure(cap * sizeof(Unit)));
-    CK(ctx->counters.ensure(64));
-    unsigned long long* d_total_updates = ctx->counters.as<unsigned long long>();
-    uint32_t* d_unit_counter = ctx->counters.as<uint32_t>() + 4;
-    CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+    if (hist_by_decoder && !resident) {   // the lists are streamed after all: count per chunk as usual
+        hist_by_decoder = false;
+        CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+    }
 
     cudaEvent_t ev_expand_a = nullptr, ev_expand_b = nullptr;
     if (resident) {
@@ -1346,8 +1430,6 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_scatter_add, (int)pl.threads, smem));
     if (blocks_per_sm < 1) return ctx->fail(KDBX_ERR_CUDA, "scatter kernel does not fit on an SM");
     const unsigned scatter_grid = (unsigned)(ctx->sm_count * blocks_per_sm);
-    const unsigned wide_grid = (unsigned)(ctx->sm_count * 8);
-    const bool smem_buckets = nkeys <= kSmemKeys;
     if (smem_buckets) CK(ctx->blockhist.ensure((size_t)wide_grid * nkeys * 4 + 16));
 
     struct ChunkEv { cudaEvent_t a, b, c, d; };
@@ -1367,19 +1449,23 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         if (!resident)
             k_expand<<<wide_grid, 256, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->loc.as<uint32_t>(), ctx->flat.as<uint32_t>());
         e.b = ctx->event();
-        CK(cudaMemsetAsync(ctx->work.p, 0, ((size_t)nkeys + 1) * 8, st));
+        if (!hist_by_decoder) CK(cudaMemsetAsync(ctx->work.p, 0, ((size_t)nkeys + 1) * 8, st));
         if (smem_buckets) {
-            k_job_hist_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                                  ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
-                                                                  ctx->blockhist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates);
+            // per-block slices of whole decoder blocks when the pass covers all patterns (then the decoder may
+            // already have counted the jobs); chunks are sliced evenly
+            const uint64_t per = (p0 == 0 && p1 == ctx->P) ? per_block : 0;
+            if (!hist_by_decoder)
+                k_job_hist_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
+                                                                      ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
+                                                                      ctx->blockhist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates, per);
             k_key_totals<<<blocks_for((uint64_t)nkeys + 1, 128), 128, 0, st>>>(nkeys, wide_grid, ctx->blockhist.as<uint32_t>(), ctx->hist.as<uint32_t>());
             if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
             if (int rc = ensure_job_slots(ctx, resident, nkeys, jobs_cap)) return rc;
             k_block_offsets<<<blocks_for((uint64_t)nkeys * 32, 256), 256, 0, st>>>(nkeys, wide_grid, ctx->bucket_off.as<uint32_t>(), ctx->blockhist.as<uint32_t>());
             k_job_fill_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
                                                                   ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
-                                                                  ctx->blockhist.as<uint32_t>(), ctx->jobs.as<Job>());
-            launches += 2;
+                                                                  ctx->blockhist.as<uint32_t>(), ctx->jobs.as<Job>(), per);
+            launches += hist_by_decoder ? 1 : 2;
         } else {
             CK(cudaMemsetAsync(ctx->hist.p, 0, ((size_t)nkeys + 1) * 4, st));
             k_job_hist<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
