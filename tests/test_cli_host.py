@@ -160,3 +160,47 @@ def test_builder_matches_set_intersections(libs, oracle, seed):
         for b in range(a):
             want[a * (a - 1) // 2 + b] = np.intersect1d(sets[a], sets[b], assume_unique=True).size
     assert np.array_equal(tri, want)
+
+
+def test_sequence_stream_carries_what_sample_stream_extracts(libs, ref_fixtures, tmp_path):
+    """The device builder and new2all take SequenceStream's symbols (records separated by NUL); extracting k-mers
+    from those symbols on the host must give exactly SampleStream's k-mers, for list files, multi-sample FASTA and
+    gzip input alike (the device-side extraction is compared with the host's in tests/test_gpu_build.py)."""
+    import subprocess
+    src = tmp_path / "seqcheck.cpp"
+    src.write_text(r'''
+#include <algorithm>
+#include <cstdio>
+#include "ingest.h"
+using namespace kdbx;
+int main(int argc, char** argv) {
+    const std::string list = argv[1]; const bool multi = std::string(argv[2]) == "1"; const uint32_t k = (uint32_t)std::atoi(argv[3]);
+    const Alphabet al = Alphabet::make(kNt); const MinHash f(1.0, 0.0, k);
+    SampleStream a(list, al, f, k, multi, 2);
+    SequenceStream b(list, multi, 2);
+    SampleKmers sa; SampleSeq sb; size_t n = 0;
+    for (;;) {
+        const bool ma = a.next(sa), mb = b.next(sb);
+        if (ma != mb) { std::printf("streams differ in length\n"); return 1; }
+        if (!ma) break;
+        if (sa.name != sb.name) { std::printf("names differ: %s %s\n", sa.name.c_str(), sb.name.c_str()); return 1; }
+        std::vector<uint64_t> km;
+        extract_kmers(sb.symbols.data(), sb.symbols.size(), k, al, f, km);   // NUL is outside the alphabet
+        std::sort(km.begin(), km.end()); km.erase(std::unique(km.begin(), km.end()), km.end());
+        if (km != sa.kmers) { std::printf("k-mers differ for %s\n", sa.name.c_str()); return 1; }
+        ++n;
+    }
+    std::printf("%zu\n", n);
+    return 0;
+}
+''')
+    exe = tmp_path / "seqcheck"
+    host = ou.ROOT / "kmer-db_b200" / "host"
+    lib = ou.ROOT / "kmer-db_b200" / "lib"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-I", str(host), str(src), "-o", str(exe), "-L", str(lib), "-lkdbx_host", "-lkdbx",
+                    f"-Wl,-rpath,{lib}"], check=True)
+    for lst, multi, k, want in (("test/virus/seqs.list", "0", 18, None), ("test/virus/multi.list", "1", 18, None),
+                                ("test/synth/synth.list", "1", 21, None), ("test/virus/seqs.part2.list", "0", 24, None)):
+        r = subprocess.run([str(exe), lst, multi, str(k)], cwd=str(ref_fixtures), capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert int(r.stdout.strip()) > 0
