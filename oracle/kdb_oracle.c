@@ -150,6 +150,79 @@ uint64_t oracle_all2all_part(uint64_t P, uint32_t N, const int64_t* num_kmers, c
 /* Independent second opinion used by the tests on small tries: M[s][t] = sum of num_kmers over
  * nodes whose full list contains both s and t (a k-mer of node p lies in exactly the samples
  * of p's full list).  O(sum n^2), no W accumulation, no job rule. */
+/* The same matrix by the column-side regrouping DESIGN.md §8 proposes as the next formulation (ours; nothing in
+ * the reference does this — it is here so that the claim "fewer updates, identical bits" is checked, and as the
+ * restatement a future kernel would be pinned on).  With W_p the subtree sums (src/similarity_calculator.cpp:64-72)
+ * and S_q(r) = sum of W_p over the STRICT descendants p of q that hold sample r locally:
+ *     M[r][c] += S_q(r)   for every c in local(q), r in supp(S_q)      (r > c: descendants' ids come later)
+ *     M[r][c] += W_q      for r, c in local(q), c < r                  (the triangle inside the node)
+ * S is carried up the trie: S_parent += S_q + W_q * 1[local(q)].  All sums are modulo 2^32, like the reference's
+ * uint32 adds.  Returns the number of matrix updates plus merge operations performed (UINT64_MAX on allocation failure). */
+uint64_t oracle_all2all_regrouped(uint64_t P, uint32_t N, const int64_t* num_kmers, const int64_t* parent_id, const uint32_t* n,
+                                  const uint32_t* l, const uint32_t* last, const uint64_t* payload_off, const uint64_t* payload,
+                                  uint32_t* tri) {
+    (void)n;
+    const uint64_t cells = N ? (uint64_t)N * (N - 1) / 2 : 0;
+    memset(tri, 0, cells * sizeof(uint32_t));
+    int64_t* W = (int64_t*)malloc(P * sizeof(int64_t));
+    uint32_t** rows = (uint32_t**)calloc(P, sizeof(uint32_t*));   /* per node: (row, weight) pairs pushed up by its children */
+    uint64_t* cnt = (uint64_t*)calloc(P, sizeof(uint64_t));
+    uint64_t* cap = (uint64_t*)calloc(P, sizeof(uint64_t));
+    uint32_t* acc = (uint32_t*)calloc((size_t)N + 1, sizeof(uint32_t));   /* dense scratch over rows */
+    uint8_t* seen = (uint8_t*)calloc((size_t)N + 1, 1);
+    uint32_t* touched = (uint32_t*)malloc(((size_t)N + 1) * sizeof(uint32_t));
+    uint32_t* loc = (uint32_t*)malloc(((size_t)N + 1) * sizeof(uint32_t));
+    uint64_t ops = 0;
+    int fail = !W || !rows || !cnt || !cap || !acc || !seen || !touched || !loc;
+    if (!fail) {
+        memcpy(W, num_kmers, P * sizeof(int64_t));
+        for (uint64_t i = P; i-- > 1;)
+            if (parent_id[i] >= 0) W[parent_id[i]] += W[i];
+    }
+    for (uint64_t q = P; !fail && q-- > 0;) {   /* children have larger ids: S_q is complete when q is reached */
+        uint32_t nt = 0;
+        for (uint64_t e = 0; e < cnt[q]; ++e) {   /* compact the pushed pairs into S_q */
+            const uint32_t r = rows[q][2 * e];
+            if (!seen[r]) { seen[r] = 1; touched[nt++] = r; }
+            acc[r] += rows[q][2 * e + 1];
+        }
+        ops += cnt[q];
+        free(rows[q]); rows[q] = NULL;
+        if (l[q]) oracle_decode_local(payload + payload_off[q], l[q], last[q], loc);
+        const uint32_t wq = (uint32_t)W[q];
+        for (uint32_t t = 0; t < nt; ++t) {       /* rectangle: rows of the strict descendants x local(q) */
+            const uint64_t r = touched[t];
+            uint32_t* row = tri + r * (r - 1) / 2;
+            for (uint32_t j = 0; j < l[q]; ++j) row[loc[j]] += acc[r];
+            ops += l[q];
+        }
+        for (uint32_t i = 1; i < l[q]; ++i) {      /* triangle inside the node */
+            const uint64_t r = loc[i];
+            uint32_t* row = tri + r * (r - 1) / 2;
+            for (uint32_t j = 0; j < i; ++j) row[loc[j]] += wq;
+            ops += i;
+        }
+        const int64_t par = parent_id[q];
+        if (par >= 0) {                            /* T_q = S_q + W_q * 1[local(q)] goes up */
+            const uint64_t need = cnt[par] + nt + l[q];
+            if (need > cap[par]) {
+                const uint64_t ncap = need * 2 + 8;
+                uint32_t* np = (uint32_t*)realloc(rows[par], ncap * 2 * sizeof(uint32_t));
+                if (!np) { fail = 1; break; }
+                rows[par] = np; cap[par] = ncap;
+            }
+            uint64_t at = cnt[par];
+            for (uint32_t t = 0; t < nt; ++t) { rows[par][2 * at] = touched[t]; rows[par][2 * at + 1] = acc[touched[t]]; ++at; }
+            for (uint32_t j = 0; j < l[q]; ++j) { rows[par][2 * at] = loc[j]; rows[par][2 * at + 1] = wq; ++at; }
+            cnt[par] = at;
+        }
+        for (uint32_t t = 0; t < nt; ++t) { acc[touched[t]] = 0; seen[touched[t]] = 0; }
+    }
+    if (rows) for (uint64_t q = 0; q < P; ++q) free(rows[q]);
+    free(W); free(rows); free(cnt); free(cap); free(acc); free(seen); free(touched); free(loc);
+    return fail ? UINT64_MAX : ops;
+}
+
 int oracle_all2all_bruteforce(uint64_t P, uint32_t N, const int64_t* num_kmers, const int64_t* parent_id, const uint32_t* n,
                               const uint32_t* l, const uint32_t* last, const uint64_t* payload_off, const uint64_t* payload,
                               uint32_t* tri) {

@@ -22,6 +22,8 @@ def load_oracle():
     lib.oracle_all2all.restype = C.c_uint64
     lib.oracle_all2all_bruteforce.argtypes = [C.c_uint64, C.c_uint32] + [vp] * 8
     lib.oracle_all2all_bruteforce.restype = C.c_int
+    lib.oracle_all2all_regrouped.argtypes = [C.c_uint64, C.c_uint32] + [vp] * 8
+    lib.oracle_all2all_regrouped.restype = C.c_uint64
     lib.oracle_all2all_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
     lib.oracle_all2all_file.restype = C.c_uint64
     lib.oracle_decode_local.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
@@ -42,6 +44,17 @@ def oracle_all2all(lib, N, a):
                            pay.ctypes.data, tri.ctypes.data)
     assert U != 2**64 - 1
     return tri[:tri_cells(N)], U
+
+
+def oracle_regrouped(lib, N, a):
+    """(tri, operations) by the column-side regrouping of DESIGN.md §8."""
+    tri = np.zeros(max(1, tri_cells(N)), dtype=np.uint32)
+    pay = a["payload"] if a["payload"].size else np.zeros(2, np.uint64)
+    ops = lib.oracle_all2all_regrouped(len(a["n"]), N, a["num_kmers"].ctypes.data, a["parent_id"].ctypes.data, a["n"].ctypes.data,
+                                       a["l"].ctypes.data, a["last"].ctypes.data, a["payload_off"].ctypes.data, pay.ctypes.data,
+                                       tri.ctypes.data)
+    assert ops != 2**64 - 1
+    return tri[:tri_cells(N)], ops
 
 
 def oracle_bruteforce(lib, N, a):

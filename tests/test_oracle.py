@@ -59,3 +59,26 @@ def test_oracle_equals_reference_binary_on_generated_db(oracle, libs, ref_bin, t
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     oracle.oracle_all2all_file(str(db).encode(), str(tmp_path / "o.csv").encode(), 0)
     assert ou.read_bytes(tmp_path / "o.csv") == ou.read_bytes(tmp_path / "ref.csv")
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_regrouped_formulation_gives_the_same_bits(oracle, libs, golden_dbs, seed):
+    """summing the weights of a node's descendants per row before touching the matrix is exact
+    (uint32 wrap-around included) and, on tries with deep sharing, needs fewer operations than U."""
+    rng = np.random.default_rng(200 + seed)
+    N = int(rng.integers(2, 80))
+    a, _ = ou.random_trie(rng, N, int(rng.integers(2, 400)), max_local=int(rng.integers(1, 12)), big_weights=(seed % 2 == 0))
+    tri, U = ou.oracle_all2all(oracle, N, a)
+    re, ops = ou.oracle_regrouped(oracle, N, a)
+    assert np.array_equal(tri, re)
+    if seed == 0:
+        for name in ("virus.k18", "synth.k21"):
+            t = libs.Trie.read_db(golden_dbs[name][0])
+            tri, U = ou.oracle_all2all(oracle, t.num_samples, t.arrays())
+            re, ops = ou.oracle_regrouped(oracle, t.num_samples, t.arrays())
+            assert np.array_equal(tri, re)
+        t = libs.Trie.synth(num_samples=120, num_clusters=2, genome_kmers=30000, seed=3)
+        tri, U = ou.oracle_all2all(oracle, 120, t.arrays())
+        re, ops = ou.oracle_regrouped(oracle, 120, t.arrays())
+        assert np.array_equal(tri, re)
+        assert ops < U   # the generated cluster tries share deeply: the regrouped form does less work
