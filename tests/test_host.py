@@ -230,3 +230,37 @@ def test_partition_into_more_parts_than_patterns(libs, oracle):
         owned += u
         empty += int(sub.num_patterns == 1)
     assert np.array_equal(acc, full) and owned == U and empty >= 5
+
+
+def test_column_window_arithmetic():
+    """The diagonal-relative column windows of the scatter kernel (win_hi / win_col0 / make_plan in
+    csrc/kdbx.cu), restated: for every row block the windows are disjoint, cover all columns below the block's
+    rows, hold at most tile_cols columns each and number at most T; window 0 ends at the block's 32-aligned end."""
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        N = int(rng.integers(2, 6000))
+        tr = int(2 ** rng.integers(0, 6))
+        tc = 32 * int(rng.integers(1, 80))
+        RB = (N + tr - 1) // tr
+        hi_max = (RB * tr + 31) & ~31
+        T = max(1, (hi_max + tc - 1) // tc)
+        for rb in {0, 1, RB // 2, RB - 1} & set(range(RB)):
+            hi = ((rb + 1) * tr + 31) & ~31
+            assert (rb + 1) * tr <= hi <= hi_max
+            covered = 0
+            prev_lo = hi
+            for t in range(T):
+                col0 = max(0, hi - (t + 1) * tc)
+                upper = hi - t * tc
+                if upper <= 0:
+                    break
+                assert upper == prev_lo and 0 < upper - col0 <= tc
+                covered += upper - col0
+                prev_lo = col0
+                if col0 == 0:
+                    break
+            assert prev_lo == 0 and covered == hi     # [0, hi) is tiled exactly
+            # the window of a column: t = (hi - 1 - c) // tile_cols, as emit_run computes it
+            for c in rng.integers(0, hi, size=5):
+                t = (hi - 1 - int(c)) // tc
+                assert t < T and max(0, hi - (t + 1) * tc) <= c < hi - t * tc
