@@ -72,6 +72,8 @@ def parse_args():
                          "'strong' = the configs[1] database cut into N sub-tries; both end in one NCCL all-reduce")
     ap.add_argument("--emulate-shard", default="", help="debug, N=1 only: 'r/w' = run the weak-scaling shard of rank r of w "
                     "ranks alone (no collective): what that rank would execute in a w-GPU run")
+    ap.add_argument("--list-form", choices=["auto", "ids", "boundaries"], default="auto",
+                    help="form of the full sample lists (kdbx.h: KDBX_FLAG_ID_LISTS / KDBX_FLAG_BOUNDARY_LISTS); auto = the library decides")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cache-dir", default=os.environ.get("KDBX_CACHE", "/tmp/kdbx_cache"))
@@ -280,7 +282,8 @@ def main():
     N0, P0, U0 = int(tot.num_samples), int(tot.num_patterns), int(tot.updates)
     chunk_ids = a.chunk_ids
     ctx = kdbx.Context(device=local_rank, chunk_ids=chunk_ids, tile_cols=a.tile_cols, unit_updates=a.unit_updates,
-                       tile_rows=a.tile_rows, scatter_threads=a.scatter_threads, flags=(kdbx.FLAG_CHUNKED_LISTS if a.chunked_lists else 0) | kdbx.FLAG_ASYNC_UPLOAD)
+                       tile_rows=a.tile_rows, scatter_threads=a.scatter_threads, flags=(kdbx.FLAG_CHUNKED_LISTS if a.chunked_lists else 0) | kdbx.FLAG_ASYNC_UPLOAD |
+                       {"auto": 0, "ids": kdbx.FLAG_ID_LISTS, "boundaries": kdbx.FLAG_BOUNDARY_LISTS}[a.list_form])
     scaling = a.scaling
     full_ref = None
     t_shard = 0.0
@@ -458,7 +461,8 @@ def main():
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "stage_ms_per_step": {k: v / a.steps for k, v in stage.items()}, "wall_ms_per_step": wall_ms / a.steps,
         "library_ms_per_step": per_step_ms,
-        "result_checksum": checksum,
+        "result_checksum": checksum, "list_form": ["ids", "run boundaries"][int(st.list_form)],
+        "physical_updates_per_step": int(st.physical_updates),
     }))
     if dist is not None:
         dist.destroy_process_group()

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define KDBX_ABI_VERSION 3
+#define KDBX_ABI_VERSION 4
 
 enum {
     KDBX_OK = 0,
@@ -69,6 +69,15 @@ typedef struct kdbx_config {
  * the next compute call overlap the tail of the transfer.  The caller's arrays must then stay
  * valid and unchanged until that compute call has returned. */
 #define KDBX_FLAG_ASYNC_UPLOAD 2u
+/* Form of the full sample lists in the dense all2all.  Default: the library looks at the decoded local lists and
+ * keeps every list as its sorted RUN BOUNDARIES (start of each run of consecutive ids, one past its end) when that
+ * holds at most 3/4 of the entries the plain id lists would — the analogue of the reference's fast path for 16
+ * consecutive ids (src/simd/row_add_avx2.cpp:38-75): a run then costs two accumulator updates whatever its length,
+ * and prefix sums along the rows restore the counts when a tile is flushed (uint32 arithmetic: same bits).
+ * KDBX_FLAG_ID_LISTS forces plain id lists, KDBX_FLAG_BOUNDARY_LISTS forces run boundaries wherever that form is
+ * implemented (one column window, all rows, lists resident in HBM). */
+#define KDBX_FLAG_ID_LISTS 4u
+#define KDBX_FLAG_BOUNDARY_LISTS 8u
 
 /* Borrowed, read-only SoA view of `std::vector<pattern_t>` (src/pattern.h:42-55) as
  * PrefixKmerDb::getPatterns() exposes it (src/prefix_kmer_db.h:87-175).  One entry per trie
@@ -119,7 +128,10 @@ typedef struct kdbx_stats {
     uint64_t hits;           /* new2all: k-mers found in the database                    */
     float ms_probe;          /* new2all: hash probe kernel                               */
     float ms_compact;        /* sparse: filter + compaction kernels                      */
-    uint64_t reserved[2];
+    uint64_t physical_updates; /* shared-memory reductions actually issued: = updates with id lists, fewer with
+                                  boundary lists (a run of consecutive ids costs two whatever its length)   */
+    uint32_t list_form;      /* 0 = sample-id lists, 1 = run-boundary lists (KDBX_FLAG_BOUNDARY_LISTS)      */
+    uint32_t _pad2;
 } kdbx_stats;
 
 /* Library / device management ---------------------------------------------------------- */
@@ -137,6 +149,15 @@ void kdbx_host_free(void* p);
 /* Stage the trie in HBM.  Replaces handing `PrefixKmerDb&` to the calculator
  * (src/console_all2all.cpp:26,34).  Only copies; all decoding happens in the compute calls. */
 int kdbx_load_patterns(kdbx_ctx* ctx, const kdbx_trie_view* view);
+
+/* Optional hint after kdbx_load_patterns: every sample id of the staged trie lies in [lo, hi).  The part of a
+ * sharded database that one GPU holds (kdbxh_partition) covers a narrow band of sample ids; with the band declared
+ * the dense all2all lays its accumulator tiles over that band only, i.e. it plans like a database of hi - lo
+ * samples (one column window up to 1536 samples).  The result is unchanged — rows and columns outside the band
+ * are zero — and an id outside the band is an error (KDBX_ERR_ARG), not silently dropped.  Reset to [0, N) by
+ * every kdbx_load_patterns.  No analogue in the reference (src/similarity_calculator.cpp:290-329 blocks by
+ * pattern count only). */
+int kdbx_set_sample_window(kdbx_ctx* ctx, uint32_t lo, uint32_t hi);
 
 /* Number of `row[col] += w` updates per matrix row (length num_samples), the quantity
  * row-block sharding is balanced on; sum = U.  Computed on the device. */

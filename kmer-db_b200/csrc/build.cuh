@@ -405,6 +405,7 @@ int new2all_sequences_impl(kdbx_ctx* ctx, const kdbx_build_params* params, const
                            uint32_t n_queries, uint32_t* out, uint64_t* unique_kmers, kdbx_stats* stats) {
     if (!ctx->loaded) return ctx->fail(KDBX_ERR_STATE, "no patterns loaded (call kdbx_load_patterns first)");
     if (!ctx->tables_loaded) return ctx->fail(KDBX_ERR_STATE, "no k-mer tables loaded (call kdbx_load_hashtables first)");
+    if (int rcw = require_full_window(ctx, "kdbx_new2all_sequences")) return rcw;
     if (n_queries && (!q_off || !out)) return ctx->fail(KDBX_ERR_ARG, "kdbx_new2all_sequences: NULL argument");
     for (uint32_t q = 0; q < n_queries; ++q)
         if (q_off[q + 1] < q_off[q]) return ctx->fail(KDBX_ERR_ARG, "kdbx_new2all_sequences: q_off must be non-decreasing");
@@ -430,6 +431,7 @@ int new2all_sequences_impl(kdbx_ctx* ctx, const kdbx_build_params* params, const
         if (rc < 0) return rc;
         if (int rc2 = check_device_error(ctx)) return rc2;
     }
+    CK(cudaMemsetAsync(ctx->err_flag.p, 0, 16, st));   // stale probe errors of earlier calls (see new2all_impl)
     cudaEvent_t ev1 = ctx->event();
     if (n_queries == 0 || N == 0) { if (stats) *stats = s; return KDBX_OK; }
     CK(ctx->counters.ensure(64));

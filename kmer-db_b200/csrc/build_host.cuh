@@ -221,6 +221,7 @@ int builder_adopt(kdbx_builder* b) {
     if (!ctx->loaded || !ctx->tables_loaded) return ctx->fail(KDBX_ERR_STATE, "kdbx_builder_adopt: stage the database first (kdbx_load_patterns + kdbx_load_hashtables)");
     if (ctx->num_tables != b->num_tables) return ctx->fail(KDBX_ERR_ARG, "kdbx_builder_adopt: the database has %llu k-mer tables, these parameters imply %llu",
                                                            (unsigned long long)ctx->num_tables, (unsigned long long)b->num_tables);
+    if (int rcw = require_full_window(ctx, "kdbx_builder_adopt")) return rcw;
     BCK(cudaSetDevice(ctx->device));
     Plan pl;
     if (int rc = make_plan(ctx, pl)) return rc;

@@ -1,0 +1,381 @@
+// Boundary ("difference") form of the dense all2all (included by kdbx.cu; shares its anonymous namespace).
+//
+// The reference's row_add has a fast path for 16 consecutive sample ids (src/simd/row_add_avx2.cpp:38-75):
+// databases built from related genomes hold long runs of consecutive ids in their sample lists — a delta of 1 is
+// a single bit of the Elias-gamma stream (src/elias_gamma.h:104-128).  This file takes that idea to its end.
+// Adding w to the cells c of a run [s, e] of one matrix row is the same as adding +w at s and -w at e + 1 to the
+// row's DIFFERENCE array and taking prefix sums once, when the accumulator tile is flushed: a run costs two
+// shared-memory reductions whatever its length.  So a pattern's full list is kept as its sorted list of run
+// boundaries  B = [s1, e1+1, s2, e2+1, ...]  (even positions open a run, odd positions close one), a row r of
+// the pattern receives the boundaries b < r (a prefix of B: the ids below r are exactly the ids of the list
+// before r; a run that contains r is left open — the cells at and above the diagonal are never read), with
+// weight +w at even and -w at odd positions, and the flush turns differences into counts.  All arithmetic is
+// uint32 modulo 2^32, so the result is bit-identical to the id form.  U stays the unit of account: the number of
+// reductions actually issued is reported next to it (kdbx_stats::physical_updates).
+//
+// B(p) = B(parent) ++ own boundaries of local(p); when local(p) starts right after the parent's last id, the
+// parent's final close and the own first open cancel and both are dropped ("joined").
+// Used when the lists are resident, there is one column window and all rows are computed (the headline path);
+// everything else runs the id form of kdbx.cu.
+#pragma once
+
+// nb[p] = entries of B(p): the parent's, minus its final close when joined, plus the own ones.  One launch per
+// num_samples level, ascending (parents first), like the level-order expansion.
+__global__ void k_pull_level(uint32_t count, const uint32_t* __restrict__ order, const Node* __restrict__ nodes,
+                             const uint32_t* __restrict__ ownb, uint32_t* __restrict__ nb) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t p = order[i];
+    const int32_t q = nodes[p].parent;
+    const uint32_t own = ownb[p];
+    nb[p] = (q >= 0 ? nb[q] : 0u) + (own >> 1) - (own & 1u);
+}
+
+struct BoundSlots {   // slots of a boundary list: 16-byte aligned like the id lists (ListSlots)
+    const uint32_t* p; uint64_t n;
+    __host__ __device__ uint64_t operator()(uint64_t i) const { return i < n ? (uint64_t)((p[i] + 3u) & ~3u) : 0ull; }
+};
+
+// B(p) = B(parent)[0 .. nb_parent - joined) ++ own boundaries, built from the decoded local ids.
+template <uint32_t kLanes>
+__global__ void k_expand_level_diff(uint32_t count, const uint32_t* __restrict__ order, const Node* __restrict__ nodes,
+                                    const uint64_t* __restrict__ boff, const uint32_t* __restrict__ nb, const uint32_t* __restrict__ ownb,
+                                    const uint32_t* __restrict__ loc, uint32_t* bflat, uint64_t capacity, int* __restrict__ err) {
+    const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / kLanes;
+    const uint32_t sub = threadIdx.x & (kLanes - 1);
+    const uint32_t group_mask = ((kLanes == 32 ? 0u : (1u << kLanes)) - 1u) << ((threadIdx.x & 31u) & ~(kLanes - 1));
+    bool have = gid < count;
+    Node nd; nd.parent = -1; nd.n = 0; nd.l = 0; nd.last = 0; nd.loff = 0; nd.up2 = nd.up3 = -1;
+    uint32_t* dst = bflat;
+    uint32_t own = 0, npar = 0;
+    if (have) {
+        const uint32_t p = order[gid];
+        nd = nodes[p];
+        own = ownb[p];
+        const uint64_t at = boff[p];
+        npar = nb[p] - (own >> 1);                 // entries taken over from the parent (its final close dropped when joined)
+        if (at + ((nb[p] + 3u) & ~3u) > capacity) { if (sub == 0) atomicExch(err, 8); have = false; }
+        dst = bflat + at;
+    }
+    if (have && nd.parent >= 0 && npar) {
+        // both lists start 16-byte aligned; the copy may run up to 3 entries past what is kept — still inside
+        // this pattern's slots, overwritten by its own entries below
+        const uint4* src = reinterpret_cast<const uint4*>(bflat + boff[nd.parent]);
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        const uint32_t n4 = (npar + 3u) >> 2;
+        for (uint32_t j = sub; j < n4; j += kLanes) d4[j] = src[j];
+    }
+    __syncwarp();
+    // own entries: id L[j] opens a run unless it continues one (the first id: unless joined), and L[j] + 1 closes
+    // the run unless L[j+1] continues it
+    const uint32_t joined = own & 1u;
+    const uint32_t* L = loc + nd.loff;
+    uint32_t run = npar;
+    const uint32_t rounds = have ? (nd.l + kLanes - 1) / kLanes : 0u;
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t j = r * kLanes + sub;
+        const bool valid = j < nd.l;
+        uint32_t cur = 0; bool s = false, e = false;
+        if (valid) {
+            cur = L[j];
+            s = j == 0 ? !joined : (L[j - 1] + 1u != cur);
+            e = j + 1 == nd.l || L[j + 1] != cur + 1u;
+        }
+        const uint32_t cnt = (uint32_t)s + (uint32_t)e;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (uint32_t o = 1; o < kLanes; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(group_mask, incl, o, kLanes);
+            if (sub >= o) incl += up;
+        }
+        uint32_t at = run + incl - cnt;
+        if (s) dst[at++] = cur;
+        if (e) dst[at] = cur + 1u;
+        run += __shfl_sync(group_mask, incl, kLanes - 1, kLanes);
+    }
+}
+
+// ---- job enumeration ------------------------------------------------------------------------------------------
+// Same jobs as the id form with one column window (a pattern x a block of matrix rows; lists longer than kSmallL
+// cut every 32 positions), described by boundary positions: the rows are the local ids loc[rows .. rows + k), all
+// of them receive the boundaries [0, c0) (those below the first row) and row j those of [c0, c0 + ext) that lie
+// below its id.  Job fields: off/off_hi = start of B(p) (40 bits), a = low 32 bits of the row offset in loc,
+// b = c0, A0 = ext | row offset high bits << 8, k, w.
+template <class Emit>
+__device__ __forceinline__ void enumerate_jobs_diff(uint64_t lo, uint64_t hi, uint32_t warp, uint32_t nwarps,
+                                                    const Node* __restrict__ nodes, const uint64_t* __restrict__ boff,
+                                                    const uint32_t* __restrict__ nb, const uint32_t* __restrict__ ownb,
+                                                    const uint32_t* __restrict__ W, const uint32_t* __restrict__ loc, uint32_t rb_shift,
+                                                    uint32_t lane, unsigned long long& updates, unsigned long long& physical, Emit emit) {
+    auto make_job = [&](uint64_t base, uint64_t rows, uint32_t c0, uint32_t ext, uint32_t k, uint32_t w) {
+        Job jb;
+        jb.off = (uint32_t)base; jb.off_hi = (uint32_t)(base >> 32);
+        jb.a = (uint32_t)rows; jb.b = c0; jb.A0 = ext | ((uint32_t)(rows >> 32) << 8);
+        jb.k = k; jb.w = w; jb.pad = 0;
+        return jb;
+    };
+    for (uint64_t b = lo + (uint64_t)warp * 32; b < hi; b += (uint64_t)nwarps * 32) {
+        const uint64_t p = b + lane;
+        Node nd; nd.parent = -1; nd.n = 0; nd.l = 0; nd.last = 0; nd.loff = 0; nd.up2 = nd.up3 = -1;
+        uint32_t w = 0, own = 0, cnt0 = 0;
+        uint64_t base = 0;
+        if (p < hi) {
+            nd = nodes[p];
+            if (nd.l) { w = W[p]; base = boff[p]; own = ownb[p]; cnt0 = nb[p] - (own >> 1); }   // boundaries below the first local id
+        }
+        // cnt_j = entries of B(p) below the local id L[j] = cnt0 + sum over i < j of (L[i] opens a run) + (a run closes
+        // after L[i]): the open L[i] and the close L[i] + 1 (present iff L[i+1] != L[i] + 1) both lie below L[j].
+        if (nd.l && nd.l <= kSmallL) {
+            const uint32_t first = nd.n - nd.l;
+            const uint32_t* rows = loc + nd.loff;
+            uint32_t cnt = cnt0, prev = 0, run_j = 0, run_rb = 0, run_c0 = 0, run_cl = 0;
+            bool starts_prev = false;
+            for (uint32_t j = 0; j < nd.l; ++j) {
+                const uint32_t row = rows[j];
+                const bool gap = j != 0 && prev + 1u != row;
+                if (j) cnt += (uint32_t)starts_prev + (uint32_t)gap;
+                const uint32_t rb = row >> rb_shift;
+                if (j == 0) { run_rb = rb; run_c0 = cnt; }
+                else if (rb != run_rb) {
+                    const uint32_t k = j - run_j, i = first + run_j;
+                    const unsigned long long upd = (unsigned long long)k * i + k * (k - 1u) / 2u;
+                    if (w != 0 && upd != 0) emit(run_rb, make_job(base, nd.loff + run_j, run_c0, run_cl - run_c0, k, w), upd);
+                    run_j = j; run_rb = rb; run_c0 = cnt;
+                }
+                run_cl = cnt;
+                updates += first + j; physical += cnt;
+                starts_prev = j == 0 ? !(own & 1u) : gap;
+                prev = row;
+            }
+            const uint32_t k = nd.l - run_j, i = first + run_j;
+            const unsigned long long upd = (unsigned long long)k * i + k * (k - 1u) / 2u;
+            if (w != 0 && upd != 0) emit(run_rb, make_job(base, nd.loff + run_j, run_c0, run_cl - run_c0, k, w), upd);
+        }
+        uint32_t big = __ballot_sync(0xffffffffu, nd.l > kSmallL);
+        while (big) {
+            const int src = __ffs((int)big) - 1;
+            big &= big - 1;
+            const uint32_t bn = __shfl_sync(0xffffffffu, nd.n, src), bl = __shfl_sync(0xffffffffu, nd.l, src);
+            const uint64_t bloff = __shfl_sync(0xffffffffu, nd.loff, src);
+            const uint32_t bw = __shfl_sync(0xffffffffu, w, src), bown = __shfl_sync(0xffffffffu, own, src);
+            const uint64_t bbase = __shfl_sync(0xffffffffu, base, src);
+            uint32_t carry = __shfl_sync(0xffffffffu, cnt0, src);   // boundaries below the first row of this round
+            const uint32_t first = bn - bl;
+            const uint32_t* rows = loc + bloff;
+            for (uint32_t r0 = 0; r0 < bl; r0 += 32) {
+                const uint32_t j = r0 + lane;
+                const bool have = j < bl;
+                uint32_t row = 0xFFFFFFFFu, prev = 0;
+                if (have) { row = rows[j]; if (j) prev = rows[j - 1]; }
+                // entries that lie below row j but not below row j-1: the open of row j-1 (if it starts a run) and the
+                // close after it (if row j does not continue the run)
+                uint32_t add = 0;
+                if (have && j) {
+                    const bool starts_prev = (j - 1 == 0) ? !(bown & 1u) : (rows[j - 2] + 1u != prev);
+                    add = (uint32_t)starts_prev + (uint32_t)(prev + 1u != row);
+                }
+                uint32_t incl = add;
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += up; }
+                const uint32_t cnt = carry + incl;   // boundaries below row j
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+                if (have) { updates += first + j; physical += cnt; }
+                const uint32_t rb = row >> rb_shift;
+                const uint32_t prev_rb = __shfl_up_sync(0xffffffffu, rb, 1);
+                const uint32_t amask = __ballot_sync(0xffffffffu, have);
+                const bool start = have && (lane == 0 || prev_rb != rb);
+                const uint32_t smask = __ballot_sync(0xffffffffu, start);
+                const uint32_t above = lane == 31 ? 0u : ((smask >> (lane + 1)) << (lane + 1));
+                const uint32_t next_start = above ? (uint32_t)__ffs((int)above) - 1u : 32u;
+                const uint32_t last_active = amask ? 32u - (uint32_t)__clz((int)amask) : 0u;
+                const uint32_t run_end = min(next_start, last_active);           // one past the run's last lane
+                const uint32_t cnt_last = __shfl_sync(0xffffffffu, cnt, (run_end > lane ? run_end : lane + 1u) - 1u);
+                if (!start) continue;
+                const uint32_t k = run_end - lane, i = first + j;
+                const unsigned long long upd = (unsigned long long)k * i + k * (k - 1u) / 2u;
+                if (bw != 0 && upd != 0) emit(rb, make_job(bbase, bloff + j, cnt, cnt_last - cnt, k, bw), upd);
+            }
+        }
+    }
+}
+
+__global__ void KDBX_BUCKET_BOUNDS
+k_job_fill_diff(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __restrict__ boff, const uint32_t* __restrict__ nb,
+                const uint32_t* __restrict__ ownb, const uint32_t* __restrict__ W, const uint32_t* __restrict__ loc, uint32_t rb_shift,
+                uint32_t nkeys, const uint32_t* __restrict__ blockbase, Job* __restrict__ jobs, uint64_t per,
+                unsigned long long* __restrict__ physical_total) {
+    __shared__ uint32_t s_next[kDecodeHistKeys];
+    const uint32_t* mine = blockbase + (size_t)blockIdx.x * nkeys;
+    for (uint32_t k = threadIdx.x; k < nkeys; k += blockDim.x) s_next[k] = mine[k];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint64_t lo, hi;
+    block_slice(0, P, lo, hi, per);
+    unsigned long long updates = 0, physical = 0;
+    enumerate_jobs_diff(lo, hi, warp, nwarps, nodes, boff, nb, ownb, W, loc, rb_shift, lane, updates, physical,
+                        [&](uint32_t key, const Job& jb, unsigned long long) {
+                            const uint32_t slot = atomicAdd(&s_next[key], 1u);
+                            jobs[slot] = jb;
+                        });
+    for (int o = 16; o; o >>= 1) physical += __shfl_xor_sync(0xffffffffu, physical, o);
+    if (lane == 0 && physical) atomicAdd(physical_total, physical);
+}
+
+// ---- the scatter-add kernel, boundary form --------------------------------------------------------------------
+// Same schedule as k_scatter_add (persistent CTAs, work units of one row block, CTA-owned accumulator tile in
+// shared memory, a warp per job, one load of a list entry feeds all k rows of the job) with three differences:
+// the list entries are run boundaries and carry the weight +w (even positions) or -w (odd positions); the rows'
+// accumulator addresses and ids sit in a small per-warp shared-memory table (one broadcast LDS.64 per row instead
+// of shuffles); the flush takes prefix sums along every row before it adds the tile into the packed triangle.
+constexpr uint32_t kDiffBatch = 8;
+
+template <uint32_t F, uint32_t G>
+__device__ __forceinline__ void last_rows_diff(uint32_t k, uint32_t rows_saddr, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t y0,
+                                               uint32_t y1, uint32_t y2, uint32_t wl) {
+#pragma unroll 2
+    for (uint32_t j = 0; j < k; ++j) {
+        uint32_t ro, lim;   // shared address of the row's accumulators, 4 * (row id): entries below it count
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(ro), "=r"(lim) : "r"(rows_saddr + j * 8u));
+        if (F > 0) red_shared_add(ro + x0, wl);
+        if (F > 1) red_shared_add(ro + x1, wl);
+        if (F > 2) red_shared_add(ro + x2, wl);
+        if (G > 0) { if (y0 < lim) red_shared_add(ro + y0, wl); }
+        if (G > 1) { if (y1 < lim) red_shared_add(ro + y1, wl); }
+        if (G > 2) { if (y2 < lim) red_shared_add(ro + y2, wl); }
+    }
+}
+
+// (64 registers = 1024 threads per SM: the accumulator tile allows one CTA per SM anyway; with __launch_bounds__
+// alone ptxas settles on 32 registers and spills)
+__global__ void __maxnreg__(64)
+k_scatter_diff(const Unit* __restrict__ units, const uint32_t* __restrict__ n_units_ptr, const Job* __restrict__ jobs,
+               const uint32_t* __restrict__ bflat, const uint32_t* __restrict__ loc, uint32_t* __restrict__ tri,
+               uint32_t id_lo, uint32_t tile_cols, uint32_t rb_shift, uint32_t* __restrict__ unit_counter) {
+    extern __shared__ uint4 tile4[];
+    uint32_t* tile = reinterpret_cast<uint32_t*>(tile4);
+    __shared__ uint32_t s_unit, s_next_job;
+    __shared__ uint2 s_rows[32][32];   // per warp: (accumulator row address, 4 * row id) of the current job's rows
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_units = *n_units_ptr;
+    const uint32_t R = 1u << rb_shift;
+    const uint32_t stride = tile_cols;
+    const uint32_t tile_saddr = (uint32_t)__cvta_generic_to_shared(tile);
+    const uint32_t rows_saddr = (uint32_t)__cvta_generic_to_shared(&s_rows[warp][0]);
+    constexpr uint32_t kNone = 0xFFFFFFFFu;
+    uint32_t cur_key = kNone;
+    for (;;) {
+        if (threadIdx.x == 0) s_unit = atomicAdd(unit_counter, 1u);
+        __syncthreads();
+        const uint32_t u = s_unit;
+        const bool done = u >= n_units;
+        Unit un; un.key = kNone; un.job_begin = un.job_end = 0; un.pad = 0;
+        if (!done) un = units[u];
+        if (un.key != cur_key) {
+            if (cur_key != kNone) {
+                // flush: prefix sums along each row (differences -> counts), then into the packed triangle.
+                // A warp per row, 32 columns at a time; only the columns below the diagonal exist.
+                const uint32_t row0 = cur_key << rb_shift;
+                for (uint32_t r = warp; r < R; r += (blockDim.x >> 5)) {
+                    const uint32_t row = row0 + r;                 // relative to id_lo, like the columns
+                    const uint32_t nc = min(tile_cols, row);
+                    const uint64_t out0 = tri_offset((uint64_t)row + id_lo) + id_lo;
+                    const uint32_t* src = tile + r * stride;
+                    uint32_t carry = 0;
+                    for (uint32_t c0 = 0; c0 < nc; c0 += 32) {
+                        const uint32_t c = c0 + lane;
+                        uint32_t v = c < nc ? src[c] : 0u;
+                        for (int o = 1; o < 32; o <<= 1) { const uint32_t up = __shfl_up_sync(0xffffffffu, v, o); if ((int)lane >= o) v += up; }
+                        v += carry;
+                        carry = __shfl_sync(0xffffffffu, v, 31);
+                        if (c < nc && v) atomicAdd(&tri[out0 + c], v);
+                    }
+                }
+                __syncthreads();
+            }
+            if (!done) {
+                const uint32_t n4 = (R * stride + 3u) >> 2;
+                for (uint32_t c = threadIdx.x; c < n4; c += blockDim.x) tile4[c] = make_uint4(0, 0, 0, 0);
+            }
+            cur_key = un.key;
+        }
+        if (done) break;
+        if (threadIdx.x == 0) s_next_job = un.job_begin;
+        __syncthreads();
+        const uint32_t row0 = un.key << rb_shift;
+        for (;;) {
+            uint32_t jb = 0;
+            if (lane == 0) jb = atomicAdd(&s_next_job, kDiffBatch);
+            jb = __shfl_sync(0xffffffffu, jb, 0);
+            if (jb >= un.job_end) break;
+            const uint32_t cnt = min(kDiffBatch, un.job_end - jb);
+            uint4 part = make_uint4(0, 0, 0, 0);  // lane 2q: (off, rows, c0, ext|rows_hi<<8) of job q; lane 2q+1: (k, w, off_hi, -)
+            if (lane < 2 * cnt) part = ldg_nc_v4(reinterpret_cast<const uint4*>(jobs + jb) + lane);
+#pragma unroll 1
+            for (uint32_t q = 0; q < cnt; ++q) {
+                const uint32_t off = __shfl_sync(0xffffffffu, part.x, 2 * q), rows_lo = __shfl_sync(0xffffffffu, part.y, 2 * q);
+                const uint32_t c0 = __shfl_sync(0xffffffffu, part.z, 2 * q), ex = __shfl_sync(0xffffffffu, part.w, 2 * q);
+                const uint32_t k = __shfl_sync(0xffffffffu, part.x, 2 * q + 1), w = __shfl_sync(0xffffffffu, part.y, 2 * q + 1);
+                const uint32_t off_hi = __shfl_sync(0xffffffffu, part.z, 2 * q + 1);
+                const uint32_t* list = bflat + (((uint64_t)off_hi << 32) | off);
+                const uint32_t e = c0 + (ex & 0xFFu);
+                __syncwarp();   // the previous job's reads of the row table are done
+                if (lane < k) {
+                    const uint32_t my_row = ldg_nc_u32(loc + (((uint64_t)(ex >> 8) << 32) | rows_lo) + lane);
+                    s_rows[warp][lane] = make_uint2(tile_saddr + (my_row - row0) * stride * 4u, my_row * 4u);
+                }
+                __syncwarp();
+                const uint32_t wl = (lane & 1u) ? 0u - w : w;   // slices start at even positions: the lane's parity is the entry's
+                // whole 128-entry slices of the boundaries every row receives ...
+                uint32_t c = 0;
+                for (; c + 128 <= c0; c += 128) {
+                    const uint32_t* p = list + c + lane;
+                    const uint32_t x0 = ldg_nc_u32(p) * 4u, x1 = ldg_nc_u32(p + 32) * 4u;
+                    const uint32_t x2 = ldg_nc_u32(p + 64) * 4u, x3 = ldg_nc_u32(p + 96) * 4u;
+                    for (uint32_t j = 0; j < k; ++j) {
+                        uint32_t ro;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ro) : "r"(rows_saddr + j * 8u));
+                        red_shared_add(ro + x0, wl); red_shared_add(ro + x1, wl);
+                        red_shared_add(ro + x2, wl); red_shared_add(ro + x3, wl);
+                    }
+                }
+                // ... then one pass over the rows for the rest: F complete 32-entry groups below c0 (unconditional)
+                // and G groups that reach into [c0, e) — entries of the job's own rows, taken by row j iff they lie
+                // below its id.  Entries past e compare as "not below" (all ones).
+                {
+                    const uint32_t full = (c0 - c) >> 5;                 // 0..3
+                    const uint32_t cg = c + full * 32;                   // first entry of the predicated groups
+                    const uint32_t rem = e - cg;                          // 0..93
+                    const uint32_t* p = list + c + lane;
+                    uint32_t x0 = 0, x1 = 0, x2 = 0;
+                    if (full > 0) x0 = ldg_nc_u32(p) * 4u;
+                    if (full > 1) x1 = ldg_nc_u32(p + 32) * 4u;
+                    if (full > 2) x2 = ldg_nc_u32(p + 64) * 4u;
+                    const uint32_t* pg = list + cg + lane;
+                    uint32_t y0 = 0xFFFFFFFFu, y1 = 0xFFFFFFFFu, y2 = 0xFFFFFFFFu;
+                    if (lane < rem) y0 = ldg_nc_u32(pg) * 4u;
+                    if (lane + 32 < rem) y1 = ldg_nc_u32(pg + 32) * 4u;
+                    if (lane + 64 < rem) y2 = ldg_nc_u32(pg + 64) * 4u;
+                    const uint32_t groups = (rem + 31u) >> 5;            // 0..3
+                    switch (full * 4 + groups) {
+                        case 0: break;
+                        case 1: last_rows_diff<0, 1>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                        case 2: last_rows_diff<0, 2>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                        case 3: last_rows_diff<0, 3>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                        case 4: last_rows_diff<1, 0>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                        case 5: last_rows_diff<1, 1>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                        case 6: last_rows_diff<1, 2>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                        case 7: last_rows_diff<1, 3>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                        case 8: last_rows_diff<2, 0>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                        case 9: last_rows_diff<2, 1>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                        case 10: last_rows_diff<2, 2>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                        case 11: last_rows_diff<2, 3>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                        case 12: last_rows_diff<3, 0>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                        case 13: last_rows_diff<3, 1>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                        case 14: last_rows_diff<3, 2>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                        default: last_rows_diff<3, 3>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}

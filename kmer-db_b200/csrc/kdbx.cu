@@ -106,8 +106,10 @@ __global__ void k_build_nodes(uint64_t P, const int64_t* __restrict__ parent, co
     if (p >= P) return;
     {   // structure every later kernel relies on: parent before child, n = n_parent + l <= N
         const int64_t q = parent[p];
+        // (a pattern with a parent holds at least one sample of its own: the level-order passes rely on
+        //  num_samples growing strictly along every parent chain)
         const bool ok = q >= -1 && q < (int64_t)p && l[p] <= n[p] && n[p] <= N &&
-                        n[p] == (q >= 0 ? n[q] : 0u) + l[p] && (l[p] == 0 || last[p] < N);
+                        n[p] == (q >= 0 ? n[q] : 0u) + l[p] && (l[p] == 0 || last[p] < N) && (l[p] != 0 || q < 0);
         if (!ok) atomicExch(err, 4);
     }
     Node nd;
@@ -132,10 +134,13 @@ __global__ void k_iota(uint64_t P, uint32_t* __restrict__ out) {
     if (p < P) out[p] = (uint32_t)p;
 }
 // level_start[v] = first index of key v in the descending-sorted key array
-__global__ void k_level_starts(uint64_t P, const uint32_t* __restrict__ keys, uint32_t* __restrict__ level_start) {
+// (keys come straight from the caller's trie: a num_samples beyond N is reported by k_build_nodes, and must
+// not be used as an index here before the host has seen that flag)
+__global__ void k_level_starts(uint64_t P, uint32_t N, const uint32_t* __restrict__ keys, uint32_t* __restrict__ level_start) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
-    if (i == 0 || keys[i] != keys[i - 1]) level_start[keys[i]] = (uint32_t)i;
+    const uint32_t v = keys[i];
+    if (v <= N && (i == 0 || v != keys[i - 1])) level_start[v] = (uint32_t)i;
 }
 __global__ void k_push_level(uint32_t count, const uint32_t* __restrict__ order, const int64_t* __restrict__ parent,
                              uint32_t* __restrict__ W) {
@@ -202,14 +207,18 @@ struct DecodeHist {
     unsigned long long* work;           // [key]
     unsigned long long* total_updates;
     const uint32_t* W;
+    // boundary form of the local lists (diff.cuh): per pattern (entries appended to the parent's boundary list) << 1 |
+    // (the list continues the parent's last run), and the sum of the appended entries over all patterns
+    uint32_t* ownb;
+    unsigned long long* sum_app;
 };
 __global__ void __launch_bounds__(kDecodeThreads)
 k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __restrict__ loff,
                 const uint32_t* __restrict__ bits, const uint64_t* __restrict__ poff, const uint64_t* __restrict__ payload,
-                uint64_t payload_words, uint32_t* __restrict__ loc, uint32_t N, int* __restrict__ err, DecodeHist dh) {
+                uint64_t payload_words, uint32_t* __restrict__ loc, uint32_t win_lo, uint32_t win_n, int* __restrict__ err, DecodeHist dh) {
     __shared__ uint32_t s_ids[kDecodeStage];
     // per key: jobs in the top 12 bits, their updates in units of 1024 in the low 20 (a block's 128 patterns
-    // hold at most 128 * 32 runs per key and 128 * N * N / 2 / 1024 < 2^20 such units with N <= 1024) — ONE
+    // hold at most 128 * 32 runs per key and 128 * N * N / 2 / 1024 < 2^20 such units with N <= 1536) — ONE
     // 32-bit shared-memory reduction per run.  The updates only size the scatter kernel's work units, so the
     // rounding is harmless; the job counts are exact.
     __shared__ uint32_t s_pack[kDecodeHistKeys];
@@ -218,10 +227,11 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
         __syncthreads();
     }
     unsigned long long my_updates = 0;
+    uint32_t my_app = 0;
     // closes the run of k rows that starts at list position i (all in row block rb)
     auto close_run = [&](uint32_t rb, uint32_t i, uint32_t k, uint32_t w) {
-        const uint32_t upd = k * i + k * (k - 1u) / 2u;   // < 32 * 1024 + 496
-        if (w != 0 && upd != 0) atomicAdd(&s_pack[rb], (1u << 20) | ((upd + 512u) >> 10));
+        const uint32_t upd = k * i + k * (k - 1u) / 2u;   // < 32 * 1536 + 496
+        if (w != 0 && upd != 0 && rb < dh.nkeys) atomicAdd(&s_pack[rb], (1u << 20) | ((upd + 512u) >> 10));   // (rb >= nkeys: id outside the window, flagged)
     };
     const uint64_t p0 = (uint64_t)blockIdx.x * kDecodeThreads;
     const uint64_t p = p0 + threadIdx.x;
@@ -231,22 +241,29 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
     const bool staged = total <= kDecodeStage;
     if (p < P) {
         const Node nd = nodes[p];
+        uint32_t own = 0;
         if (nd.l) {
             uint32_t* out = staged ? s_ids + (nd.loff - base) : loc + nd.loff;
             // the parent's list must end before this one starts, or full lists would not ascend
-            const uint32_t floor_id = nd.parent >= 0 && nodes[nd.parent].l ? nodes[nd.parent].last + 1u : 0u;
+            const bool has_par = nd.parent >= 0 && nodes[nd.parent].l;
+            const uint32_t floor_id = has_par ? nodes[nd.parent].last + 1u : 0u;
             const uint32_t first = nd.n - nd.l;
             if (dh.enabled) my_updates = (unsigned long long)nd.l * first + (unsigned long long)nd.l * (nd.l - 1u) / 2u;
+            // every id must lie in the sample window; the kernels downstream see ids relative to win_lo
+            if (nd.last - win_lo >= win_n) atomicExch(err, 7);
             if (nd.l == 1) {
-                out[0] = nd.last;
+                out[0] = nd.last - win_lo;
                 if (nd.last < floor_id) atomicExch(err, 3);
-                if (dh.enabled) close_run(nd.last >> dh.rb_shift, first, 1u, dh.W[p]);
+                if (nd.last < win_lo) atomicExch(err, 7);
+                if (dh.enabled) close_run((nd.last - win_lo) >> dh.rb_shift, first, 1u, dh.W[p]);
+                const uint32_t joined = has_par && nd.last == floor_id;
+                own = ((2u - joined) << 1) | joined;
             } else {
                 const uint32_t nb = bits[p];
                 const uint64_t po = poff[p];
                 bool ok = po + ((uint64_t)(nb + 127u) / 128u) * 2u <= payload_words;
                 if (!ok) atomicExch(err, 5);
-                uint32_t pos = 0;
+                uint32_t pos = 0, runs = 1;
                 uint64_t sum = 0;
                 if (ok) {
                     const uint64_t* w = payload + po;
@@ -263,9 +280,10 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
                             i += z; pos += z; sum += z;
                             continue;
                         }
-                        const uint32_t d = gamma_next(w, pos, nb);
+                        const uint32_t d = gamma_next(w, pos, nb);   // >= 2 (the next bit is a one), or 0 on a malformed stream
                         out[i++] = d;
                         sum += d;
+                        ++runs;
                     }
                     if (i != nd.l || pos != nb) { atomicExch(err, 1); ok = false; }
                     else if (sum > nd.last) { atomicExch(err, 2); ok = false; }
@@ -273,8 +291,14 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
                 if (ok) {
                     uint32_t cur = nd.last - (uint32_t)sum;
                     if (cur < floor_id) atomicExch(err, 3);
+                    if (cur < win_lo) { atomicExch(err, 7); ok = false; }
+                    const uint32_t joined = has_par && cur == floor_id;
+                    own = ((2u * runs - joined) << 1) | joined;
+                    cur -= win_lo;
                     out[0] = cur;
-                    if (!dh.enabled) {
+                    if (!ok) {
+                        for (uint32_t i = 1; i < nd.l; ++i) out[i] = 0;
+                    } else if (!dh.enabled) {
                         for (uint32_t i = 1; i < nd.l; ++i) { cur += out[i]; out[i] = cur; }
                     } else {
                         const uint32_t w = dh.W[p];
@@ -295,10 +319,15 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
                 }
             }
         }
+        if (dh.ownb) { dh.ownb[p] = own; my_app = own >> 1; }
     }
     if (staged) {
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < (uint32_t)total; i += kDecodeThreads) loc[base + i] = s_ids[i];
+    }
+    if (dh.ownb) {
+        for (int o = 16; o; o >>= 1) my_app += __shfl_xor_sync(0xffffffffu, my_app, o);
+        if ((threadIdx.x & 31) == 0 && my_app) atomicAdd(dh.sum_app, (unsigned long long)my_app);
     }
     if (dh.enabled) {
         for (int o = 16; o; o >>= 1) my_updates += __shfl_xor_sync(0xffffffffu, my_updates, o);
@@ -853,7 +882,7 @@ constexpr uint32_t kRowPad = 32;   // padding words after every accumulator row 
 __global__ void __launch_bounds__(1024)
 k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_units_ptr, const Job* __restrict__ jobs,
               const uint32_t* __restrict__ flat_all, const uint64_t* __restrict__ flat_shift, uint32_t* __restrict__ tri,
-              uint64_t tri_base, uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t* __restrict__ unit_counter) {
+              uint64_t tri_base, uint32_t id_lo, uint32_t T, uint32_t tile_cols, uint32_t rb_shift, uint32_t* __restrict__ unit_counter) {
     extern __shared__ uint4 tile4[];
     const uint32_t* flat = flat_all + (flat_shift ? *flat_shift : 0ull);
     uint32_t* tile = reinterpret_cast<uint32_t*>(tile4);
@@ -882,7 +911,7 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
                     const uint32_t row = row0 + r;
                     if (row <= col0) continue;
                     const uint32_t nc = min(tile_cols, row - col0);  // only columns < row exist
-                    const uint64_t out0 = tri_offset(row) - tri_base + col0;
+                    const uint64_t out0 = tri_offset((uint64_t)row + id_lo) - tri_base + col0 + id_lo;   // rows and columns are relative to the sample window
                     const uint32_t* src = tile + r * stride;
                     for (uint32_t c = threadIdx.x; c < nc; c += blockDim.x) {
                         const uint32_t v = src[c];
@@ -967,6 +996,8 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
     }
 }
 
+#include "diff.cuh"
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -985,7 +1016,7 @@ struct DevBuf {
     template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
-std::string g_open_error;
+thread_local std::string g_open_error;   // kdbx_open may run on several host threads at once (one per device)
 
 }  // namespace
 
@@ -1015,8 +1046,37 @@ struct kdbx_ctx {
     // per chunk
     DevBuf flat, jobs, hist, work, bucket_off, cursor, ucount, uoff, units, counters, blockhist;
     DevBuf tri, rowupd, first_id;
-    uint64_t sum_l = 0, sum_n = 0;
+    uint64_t sum_l = 0, sum_n = 0, sum_cost = 0;
     bool prepared = false;  // nodes / W / loc are valid for the loaded trie
+
+    // Sample window [win_lo, win_hi): every sample id of the staged trie lies inside it (kdbx_set_sample_window;
+    // default [0, N)).  The dense kernels then work on ids relative to win_lo, so the shard of a large database
+    // whose samples sit close together is planned like a database of win_hi - win_lo samples.
+    uint32_t win_lo = 0, win_hi = 0;
+
+    // What the host has to know about the staged trie to enqueue a step — sizes, the level table, the plan
+    // of the last call — is read back ONCE per staged trie (load_gen) and call signature.  Later calls with
+    // the same signature recompute everything on the device but never wait for it: one synchronisation at the
+    // end of the call, none inside.
+    uint64_t load_gen = 0;
+    struct StepMeta {
+        bool prep_valid = false;   // sum_l / sum_n / sum_cost / levels belong to load_gen
+        uint64_t prep_gen = 0;
+        bool valid = false;
+        uint64_t gen = 0;
+        uint32_t row_begin = 0, row_end = 0, part = 0, num_parts = 0, win_lo = 0, win_hi = 0;
+        uint32_t tile_cols = 0, tile_rows = 0, threads = 0, unit_updates = 0, flags = 0;
+        uint64_t chunk = 0;
+        bool resident = false, diff = false;
+        uint32_t nchunks = 0;
+        unsigned scatter_grid = 0;
+        std::vector<uint64_t> bounds;     // chunk boundaries (chunked mode)
+        std::vector<uint64_t> jobs_in_pass; // exact job counts of the passes executed
+        uint64_t diff_slots = 0;          // entries of the boundary lists (diff mode)
+    } meta;
+    // boundary lists (diff.cuh)
+    DevBuf ownb, nb, boff;
+    uint64_t* h_pinned = nullptr;          // small pinned read-back area
 
     // sparse delivery (sparse.cuh)
     DevBuf sp_cnt, sp_counts, sp_rowptr, sp_col, sp_val;
@@ -1035,10 +1095,10 @@ struct kdbx_ctx {
     // the step does not depend on how fast the host can issue launches.
     struct LevelGraph {
         cudaGraphExec_t exec = nullptr;
-        const void* ptr[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        const void* ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
         uint64_t P = 0, levels_hash = 0;
         size_t nlevels = 0;
-    } g_push, g_expand;
+    } g_push, g_expand, g_pull, g_expand_diff;
 
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -1084,17 +1144,21 @@ int scan_exclusive_u32(kdbx_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_
 
 struct Plan {
     uint32_t tile_cols = 0, tile_rows = 0, rb_shift = 0, T = 0, RB = 0, unit_updates = 0, threads = 0;
+    uint32_t lo = 0, Nw = 0;     // sample window: ids lo .. lo + Nw, the kernels see ids relative to lo
     uint64_t chunk = 0;
-    size_t smem = 0;
+    size_t smem = 0, smem_diff = 0;
 };
 
 constexpr size_t kMaxTileBytes = 200 * 1024;  // of the 227 KB a CTA may use
+constexpr uint32_t kMaxOneWindowCols = 1536;  // 32 rows x 1536 columns: the widest tile that still fits
 
 int make_plan(kdbx_ctx* ctx, Plan& pl) {
-    const uint32_t N = ctx->N;
+    pl.lo = ctx->win_lo;
+    const uint32_t N = ctx->win_hi - ctx->win_lo;
+    pl.Nw = N;
     uint32_t tc = ctx->cfg.tile_cols;
-    // default: whole rows up to 1024 samples (a 32 x 1024 tile is 128 KB: one 1024-thread CTA per SM)
-    if (tc == 0) tc = std::min<uint32_t>(1024u, std::max<uint32_t>(32u, (N + 31u) & ~31u));
+    // default: whole rows (one column window) up to 1536 samples, 1024-column windows beyond
+    if (tc == 0) tc = N <= kMaxOneWindowCols ? std::max<uint32_t>(32u, (N + 31u) & ~31u) : 1024u;
     if (tc < 32 || (tc & 31)) return ctx->fail(KDBX_ERR_ARG, "tile_cols must be a multiple of 32");
     uint32_t tr = ctx->cfg.tile_rows;
     if (tr == 0) {
@@ -1113,6 +1177,7 @@ int make_plan(kdbx_ctx* ctx, Plan& pl) {
     }
     if ((uint64_t)pl.T * pl.RB >= ((uint64_t)1 << 31)) return ctx->fail(KDBX_ERR_ARG, "too many (row block, column tile) keys");
     pl.smem = ((size_t)tr * (tc + kRowPad) * 4 + 15) & ~(size_t)15;  // padding words per row, see k_scatter_add
+    pl.smem_diff = ((size_t)tr * tc * 4 + 15) & ~(size_t)15;         // no padding in the boundary form
     pl.threads = ctx->cfg.scatter_threads ? ctx->cfg.scatter_threads : (pl.smem > 100 * 1024 ? 1024u : pl.smem > 48 * 1024 ? 512u : 256u);
     if (pl.threads < 32 || pl.threads > 1024 || (pl.threads & 31)) return ctx->fail(KDBX_ERR_ARG, "scatter_threads must be a multiple of 32 in [32, 1024]");
     // a unit flushes at most tile_rows x tile_cols cells with global reductions: keep >= 64 updates per cell
@@ -1124,18 +1189,29 @@ int make_plan(kdbx_ctx* ctx, Plan& pl) {
 }
 
 int error_from_flag(kdbx_ctx* ctx, int flag) {
+    if (flag) { ctx->prepared = false; ctx->meta.valid = false; ctx->meta.prep_valid = false; }   // nothing decoded is usable: the next call starts over
     if (flag == 1) return ctx->fail(KDBX_ERR_ARG, "malformed trie: Elias-gamma stream does not match num_bits");
     if (flag == 2) return ctx->fail(KDBX_ERR_ARG, "malformed trie: sample id out of range");
     if (flag == 3) return ctx->fail(KDBX_ERR_ARG, "malformed trie: a local list does not continue its parent's list");
     if (flag == 4) return ctx->fail(KDBX_ERR_ARG, "malformed trie: parent_id / num_samples / num_local_samples inconsistent");
     if (flag == 5) return ctx->fail(KDBX_ERR_ARG, "malformed trie: payload offset out of bounds");
     if (flag == 6) return ctx->fail(KDBX_ERR_ARG, "k-mer table points at a pattern that does not exist");
+    if (flag == 7) return ctx->fail(KDBX_ERR_ARG, "a sample id lies outside the declared sample window");
+    if (flag == 8) return ctx->fail(KDBX_ERR_STATE, "internal: boundary lists exceed their buffer");
     return KDBX_OK;
 }
 int check_device_error(kdbx_ctx* ctx) {
     int flag = 0;
     CK(cudaMemcpy(&flag, ctx->err_flag.p, sizeof flag, cudaMemcpyDeviceToHost));
     return error_from_flag(ctx, flag);
+}
+
+// entry points that hand decoded sample ids to the caller (or index per-sample arrays with them) need ids that
+// are not shifted by a sample window
+int require_full_window(kdbx_ctx* ctx, const char* what) {
+    if (ctx->win_lo != 0 || ctx->win_hi != ctx->N)
+        return ctx->fail(KDBX_ERR_STATE, "%s: a sample window is set (kdbx_set_sample_window); only the dense and sparse all2all honour it", what);
+    return KDBX_OK;
 }
 
 uint64_t levels_hash_of(const std::vector<std::pair<uint32_t, uint32_t>>& levels) {
@@ -1177,10 +1253,12 @@ int launch_level_graph(kdbx_ctx* ctx, kdbx_ctx::LevelGraph& g, std::initializer_
     return KDBX_OK;
 }
 
-// scans + node packing + W + gamma decode.  Leaves sum_l / sum_n on the host (one sync).
+// scans + node packing + W + gamma decode.  The sizes and the level table reach the host once per staged trie
+// (one synchronisation); later calls re-run every kernel but take those from the context.
 int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches, const DecodeHist* decode_hist = nullptr) {
     const uint64_t P = ctx->P;
     cudaStream_t st = ctx->stream;
+    const bool cached = ctx->meta.prep_valid && ctx->meta.prep_gen == ctx->load_gen;
     CK(ctx->loff.ensure((P + 1) * 8)); CK(ctx->noff.ensure((P + 1) * 8)); CK(ctx->coff.ensure((P + 1) * 8));
     CK(ctx->nodes.ensure(P * sizeof(Node))); CK(ctx->W.ensure(P * 4)); CK(ctx->err_flag.ensure(16));
     cub::CountingInputIterator<uint64_t> idx(0);
@@ -1214,7 +1292,6 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches, const DecodeHist*
     const uint32_t N = ctx->N;
     CK(ctx->order_in.ensure(P * 4)); CK(ctx->order.ensure(P * 4)); CK(ctx->keys_sorted.ensure(P * 4));
     CK(ctx->level_start.ensure(((size_t)N + 2) * 4));
-    ctx->h_level_start.resize((size_t)N + 2);
     {
         int end_bit = 1;
         while (end_bit < 32 && (N >> end_bit)) ++end_bit;
@@ -1225,21 +1302,24 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches, const DecodeHist*
         CK(ctx->cub_tmp.ensure(tmp));
         CK(cub::DeviceRadixSort::SortPairsDescending(ctx->cub_tmp.p, tmp, ctx->n.as<uint32_t>(), ctx->keys_sorted.as<uint32_t>(),
                                                      ctx->order_in.as<uint32_t>(), ctx->order.as<uint32_t>(), P, 0, end_bit, st));
-        CK(cudaMemsetAsync(ctx->level_start.p, 0xFF, ((size_t)N + 2) * 4, st));
-        k_level_starts<<<blocks_for(P, 256), 256, 0, st>>>(P, ctx->keys_sorted.as<uint32_t>(), ctx->level_start.as<uint32_t>());
-        launches += 4;
+        launches += 2;
     }
-    uint64_t sums[3] = {0, 0, 0};
-    CK(cudaMemcpyAsync(&sums[0], ctx->loff.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&sums[1], ctx->noff.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&sums[2], ctx->coff.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(ctx->h_level_start.data(), ctx->level_start.p, ((size_t)N + 2) * 4, cudaMemcpyDeviceToHost, st));
-    int h_flag = 0;
-    CK(cudaMemcpyAsync(&h_flag, ctx->err_flag.p, sizeof h_flag, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (int rc = error_from_flag(ctx, h_flag)) return rc;  // structural errors stop here, before any id is chased
-    ctx->sum_l = sums[0]; ctx->sum_n = sums[1];
-    {   // deepest level first; level 0 (the sentinel, n = 0) has no parent to feed
+    if (!cached) {
+        ctx->h_level_start.resize((size_t)N + 2);
+        CK(cudaMemsetAsync(ctx->level_start.p, 0xFF, ((size_t)N + 2) * 4, st));
+        k_level_starts<<<blocks_for(P, 256), 256, 0, st>>>(P, N, ctx->keys_sorted.as<uint32_t>(), ctx->level_start.as<uint32_t>());
+        launches += 2;
+        uint64_t sums[3] = {0, 0, 0};
+        CK(cudaMemcpyAsync(&sums[0], ctx->loff.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&sums[1], ctx->noff.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&sums[2], ctx->coff.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->h_level_start.data(), ctx->level_start.p, ((size_t)N + 2) * 4, cudaMemcpyDeviceToHost, st));
+        int h_flag = 0;
+        CK(cudaMemcpyAsync(&h_flag, ctx->err_flag.p, sizeof h_flag, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (int rc = error_from_flag(ctx, h_flag)) return rc;  // structural errors stop here, before any id is chased
+        ctx->sum_l = sums[0]; ctx->sum_n = sums[1]; ctx->sum_cost = sums[2];
+        // deepest level first; level 0 (the sentinel, n = 0) has no parent to feed
         uint32_t end = (uint32_t)P;
         std::vector<std::pair<uint32_t, uint32_t>>& levels = ctx->levels;  // ascending n; ranges in `order`
         levels.clear();
@@ -1249,6 +1329,10 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches, const DecodeHist*
             levels.emplace_back(b, end);   // keys are sorted descending: smaller n sits further back
             end = b;
         }
+        ctx->meta.prep_valid = true; ctx->meta.prep_gen = ctx->load_gen;
+    }
+    {
+        const std::vector<std::pair<uint32_t, uint32_t>>& levels = ctx->levels;
         // levels[k] = (begin of key v_k, end); built for ascending v, so begin decreases
         uint32_t n_launch = 0;
         for (size_t k = levels.size(); k-- > 0;) if (levels[k].second > levels[k].first) ++n_launch;
@@ -1269,12 +1353,12 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches, const DecodeHist*
     DecodeHist dh{};
     if (decode_hist) { dh = *decode_hist; dh.W = ctx->W.as<uint32_t>(); }
     k_decode_locals<<<blocks_for(P, kDecodeThreads), kDecodeThreads, 0, st>>>(P, ctx->nodes.as<Node>(), ctx->loff.as<uint64_t>(), ctx->bits.as<uint32_t>(), ctx->poff.as<uint64_t>(),
-                                                         ctx->payload.as<uint64_t>(), ctx->payload_words, ctx->loc.as<uint32_t>(), ctx->N,
-                                                         ctx->err_flag.as<int>(), dh);
+                                                         ctx->payload.as<uint64_t>(), ctx->payload_words, ctx->loc.as<uint32_t>(), ctx->win_lo,
+                                                         ctx->win_hi - ctx->win_lo, ctx->err_flag.as<int>(), dh);
     launches += 1;
     CK(cudaGetLastError());
     // chunk boundaries
-    const uint64_t total_cost = sums[2];
+    const uint64_t total_cost = ctx->sum_cost;
     const uint32_t nchunks = (uint32_t)std::max<uint64_t>(1, (total_cost + pl.chunk - 1) / pl.chunk);
     CK(ctx->bounds.ensure(((size_t)nchunks + 1) * 8));
     k_chunk_bounds<<<blocks_for(nchunks + 1, 128), 128, 0, st>>>(P, ctx->coff.as<uint64_t>(), pl.chunk, nchunks, ctx->bounds.as<uint64_t>());
@@ -1286,27 +1370,6 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches, const DecodeHist*
 
 float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 
-// With resident lists a pass may cover far more patterns than the chunk planner's worst-case bound
-// provides slots for: read the exact number of jobs of this pass (bucket_off[nkeys], just scanned)
-// and grow the job / unit arrays to it.  The chunked mode stays within its precomputed bound.
-int ensure_job_slots(kdbx_ctx* ctx, bool resident, uint32_t nkeys, uint64_t& jobs_cap) {
-    if (!resident) return KDBX_OK;
-    uint32_t total = 0;
-    int h_flag = 0;   // decode errors surface here: before any job is filled in or executed
-    CK(cudaMemcpyAsync(&total, ctx->bucket_off.as<uint32_t>() + nkeys, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(&h_flag, ctx->err_flag.p, sizeof h_flag, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (int rc = error_from_flag(ctx, h_flag)) return rc;
-    if ((uint64_t)total + 64 > jobs_cap) {
-        jobs_cap = (uint64_t)total + 64;
-        CK(ctx->jobs.ensure(jobs_cap * sizeof(Job)));
-        CK(ctx->units.ensure(jobs_cap * sizeof(Unit)));
-    }
-    return KDBX_OK;
-}
-
-// part / num_parts: only the chunks c with c % num_parts == part are executed (pattern sharding for
-// multi-GPU runs: the partial matrices of all parts sum to the full one).
 // Waits for the copies of kdbx_load_patterns and records their duration.
 int finish_upload(kdbx_ctx* ctx) {
     if (!ctx->upload_pending) return KDBX_OK;
@@ -1320,6 +1383,15 @@ int finish_upload(kdbx_ctx* ctx) {
     return KDBX_OK;
 }
 
+// One dense all2all over the staged trie: rows [row_begin, row_end) of the packed triangle into d_out.
+// part / num_parts: only the chunks c with c % num_parts == part are executed (pattern sharding: the partial
+// matrices of all parts sum to the full one).
+//
+// Host round trips.  The FIRST call for a staged trie and call signature reads back what the host needs to size
+// buffers and launches (sums and the level table in prepare(), then the job / list totals and the choice of the
+// list form) — three synchronisations.  It leaves them in ctx->meta; every later call with the same signature
+// enqueues the whole step without waiting for the device and synchronises once, at the end, for U and the error
+// flag.  Nothing of the RESULT is cached: every call decodes, expands, buckets and scatters again.
 int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uint32_t* d_out, kdbx_stats* stats,
                         uint32_t part = 0, uint32_t num_parts = 1) {
     if (!ctx->loaded) return ctx->fail(KDBX_ERR_STATE, "no patterns loaded (call kdbx_load_patterns first)");
@@ -1328,6 +1400,11 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     cudaStream_t st = ctx->stream;
     Plan pl;
     if (int rc = make_plan(ctx, pl)) return rc;
+    kdbx_ctx::StepMeta& M = ctx->meta;
+    const bool cached = M.valid && M.gen == ctx->load_gen && M.row_begin == row_begin && M.row_end == row_end && M.part == part &&
+                        M.num_parts == num_parts && M.win_lo == ctx->win_lo && M.win_hi == ctx->win_hi && M.tile_cols == pl.tile_cols &&
+                        M.tile_rows == pl.tile_rows && M.threads == pl.threads && M.unit_updates == pl.unit_updates &&
+                        M.flags == ctx->cfg.flags && M.chunk == pl.chunk;
     kdbx_stats s{};
     s.ms_upload = ctx->ms_upload;
     ctx->ev_used = 0;
@@ -1335,6 +1412,10 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     auto tri_off = [](uint64_t r) { return r == 0 ? 0ull : r * (r - 1) / 2; };
     const uint64_t tri_base = tri_off(row_begin);
     const uint64_t cells = tri_off(row_end) - tri_base;
+    // the rows that can hold anything lie inside the sample window; the kernels see them relative to it
+    const uint32_t wb = std::min(std::max(row_begin, ctx->win_lo), ctx->win_hi) - ctx->win_lo;
+    const uint32_t we = std::max(std::min(row_end, ctx->win_hi), ctx->win_lo) - ctx->win_lo;
+    const bool all_rows = row_begin <= ctx->win_lo && row_end >= ctx->win_hi;
 
     cudaEvent_t ev_start = ctx->event();
     if (cells) CK(cudaMemsetAsync(d_out, 0, cells * 4, st));
@@ -1345,12 +1426,17 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     // count jobs per (fill block, key) itself (DecodeHist)
     const uint64_t per_block = (((ctx->P + wide_grid - 1) / wide_grid) + kDecodeThreads - 1) / kDecodeThreads * kDecodeThreads;
     CK(ctx->counters.ensure(64));
+    if (!ctx->h_pinned) CK(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_pinned), 64, cudaHostAllocDefault));
     unsigned long long* d_total_updates = ctx->counters.as<unsigned long long>();
     uint32_t* d_unit_counter = ctx->counters.as<uint32_t>() + 4;
+    unsigned long long* d_sum_app = ctx->counters.as<unsigned long long>() + 3;
+    unsigned long long* d_physical = ctx->counters.as<unsigned long long>() + 4;
     CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
     // one column window, all rows, one part: the decoder counts the jobs and the first enumeration pass is skipped
-    bool hist_by_decoder = pl.T == 1 && nkeys <= kDecodeHistKeys && nkeys > 0 && cells > 0 && row_begin == 0 && row_end == ctx->N &&
+    bool hist_by_decoder = pl.T == 1 && nkeys <= kDecodeHistKeys && nkeys > 0 && cells > 0 && all_rows &&
                            num_parts == 1 && !(ctx->cfg.flags & KDBX_FLAG_CHUNKED_LISTS);
+    if (cached && !M.resident) hist_by_decoder = false;
+    const bool diff_possible = hist_by_decoder && !(ctx->cfg.flags & KDBX_FLAG_ID_LISTS);
     DecodeHist dh{};
     if (hist_by_decoder) {
         CK(ctx->blockhist.ensure((size_t)wide_grid * nkeys * 4 + 16));
@@ -1359,6 +1445,10 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         CK(cudaMemsetAsync(ctx->work.p, 0, ((size_t)nkeys + 1) * 8, st));
         dh.enabled = 1; dh.rb_shift = pl.rb_shift; dh.nkeys = nkeys; dh.per = per_block;
         dh.blockhist = ctx->blockhist.as<uint32_t>(); dh.work = ctx->work.as<unsigned long long>(); dh.total_updates = d_total_updates;
+        if (diff_possible && (!cached || M.diff)) {
+            CK(ctx->ownb.ensure(ctx->P * 4));
+            dh.ownb = ctx->ownb.as<uint32_t>(); dh.sum_app = d_sum_app;
+        }
     }
     const int nchunks_or_err = prepare(ctx, pl, launches, hist_by_decoder ? &dh : nullptr);
     if (nchunks_or_err < 0) return nchunks_or_err;
@@ -1366,7 +1456,7 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     std::vector<uint64_t> bounds(nchunks + 1);
     cudaEvent_t ev_prepared = ctx->event();
 
-    if (cells == 0 || nkeys == 0) {  // N <= 1 or an empty row range: no cell exists
+    if (cells == 0 || nkeys == 0 || we <= wb) {  // no cell of the requested rows can be non-zero
         CK(cudaStreamSynchronize(st));
         s.ms_prepare = elapsed(ev_start, ev_prepared);
         s.ms_total = s.ms_prepare;
@@ -1375,41 +1465,107 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         if (stats) *stats = s;
         return KDBX_OK;
     }
-    const uint64_t cap = pl.chunk + (uint64_t)ctx->N * (pl.T + 1) + 64;  // a chunk may overshoot by one pattern
+    const uint64_t cap = pl.chunk + (uint64_t)pl.Nw * (pl.T + 1) + 64;  // a chunk may overshoot by one pattern
     // full lists of all patterns resident (level-order expansion) when they take at most 40 % of the
     // free HBM; otherwise they are expanded chunk by chunk by walking parent chains
     // (a pattern-sharded part needs only its own chunks' lists: walking their chains is cheaper than
     // expanding everything on every GPU)
     bool resident = !(ctx->cfg.flags & KDBX_FLAG_CHUNKED_LISTS) && num_parts == 1;
-    if (resident) {
+    if (cached) resident = M.resident;
+    else if (resident) {
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
         const uint64_t have = (uint64_t)free_b + ctx->flat.bytes;
         resident = (ctx->sum_n + 64) * 4 <= have / 5 * 2;
     }
-    if (!resident) {   // chunk boundaries come from the device; decode errors stop the call before any chain is walked
-        CK(cudaMemcpyAsync(bounds.data(), ctx->bounds.p, (nchunks + 1) * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (int rc = check_device_error(ctx)) return rc;
-    }   // (resident mode: the expansion only copies by the validated sizes; the flag is read before the jobs are filled in)
-    CK(ctx->flat.ensure(resident ? (ctx->sum_n + 64) * 4 : cap * 4));
-    if (resident) CK(ctx->first_id.ensure(ctx->P * 4));
-    if (!resident) CK(ctx->jobs.ensure(cap * sizeof(Job)));
     CK(ctx->hist.ensure(((size_t)nkeys + 1) * 4)); CK(ctx->work.ensure(((size_t)nkeys + 1) * 8));
     CK(ctx->bucket_off.ensure(((size_t)nkeys + 1) * 4)); CK(ctx->cursor.ensure(((size_t)nkeys + 1) * 4));
     CK(ctx->ucount.ensure(((size_t)nkeys + 1) * 4)); CK(ctx->uoff.ensure(((size_t)nkeys + 1) * 4));
-    if (!resident) CK(ctx->units.ensure(cap * sizeof(Unit)));
     if (hist_by_decoder && !resident) {   // the lists are streamed after all: count per chunk as usual
         hist_by_decoder = false;
         CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
     }
+
+    // ---- the decoder counted the jobs: bucket offsets now; first call: totals and the list form to the host ----
+    bool diff = false;
+    uint64_t diff_slots = 0, jobs_total = 0;
+    cudaEvent_t ev_bucket0 = nullptr, ev_bucket0_end = nullptr;
+    if (hist_by_decoder) {
+        ev_bucket0 = ctx->event();
+        k_key_totals<<<blocks_for((uint64_t)nkeys + 1, 128), 128, 0, st>>>(nkeys, wide_grid, ctx->blockhist.as<uint32_t>(), ctx->hist.as<uint32_t>());
+        if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
+        k_block_offsets<<<blocks_for((uint64_t)nkeys * 32, 256), 256, 0, st>>>(nkeys, wide_grid, ctx->bucket_off.as<uint32_t>(), ctx->blockhist.as<uint32_t>());
+        launches += 3;
+        const bool want_nb = dh.ownb != nullptr;
+        if (want_nb) {   // entries per boundary list (parents first) and their offsets
+            CK(ctx->nb.ensure(ctx->P * 4)); CK(ctx->boff.ensure((ctx->P + 1) * 8));
+            uint32_t n_launch = 0;
+            for (const auto& lv : ctx->levels) if (lv.second > lv.first) ++n_launch;
+            if (n_launch) {
+                if (int rc = launch_level_graph(ctx, ctx->g_pull, {ctx->order.p, ctx->nodes.p, ctx->ownb.p, ctx->nb.p}, [&] {
+                        for (size_t k = 0; k < ctx->levels.size(); ++k) {
+                            const uint32_t b = ctx->levels[k].first, e = ctx->levels[k].second;
+                            if (e <= b) continue;
+                            k_pull_level<<<blocks_for(e - b, 256), 256, 0, st>>>(e - b, ctx->order.as<uint32_t>() + b, ctx->nodes.as<Node>(),
+                                                                                  ctx->ownb.as<uint32_t>(), ctx->nb.as<uint32_t>());
+                        }
+                    })) return rc;
+            }
+            launches += n_launch;
+            cub::CountingInputIterator<uint64_t> idx(0);
+            cub::TransformInputIterator<uint64_t, BoundSlots, cub::CountingInputIterator<uint64_t>> it(idx, BoundSlots{ctx->nb.as<uint32_t>(), ctx->P});
+            if (int rc = scan_exclusive(ctx, it, ctx->boff.as<uint64_t>(), ctx->P + 1)) return rc;
+            launches += 1;
+        }
+        ev_bucket0_end = ctx->event();
+        if (cached) { diff = M.diff; diff_slots = M.diff_slots; jobs_total = M.jobs_in_pass.empty() ? 0 : M.jobs_in_pass[0]; }
+        else {
+            uint64_t* h = ctx->h_pinned;   // [0] sum of appended entries, [1] boundary slots, [2] jobs, [3] error flag
+            h[0] = h[1] = h[2] = h[3] = 0;
+            if (want_nb) {
+                CK(cudaMemcpyAsync(&h[0], d_sum_app, 8, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(&h[1], ctx->boff.as<uint64_t>() + ctx->P, 8, cudaMemcpyDeviceToHost, st));
+            }
+            CK(cudaMemcpyAsync(&h[2], ctx->bucket_off.as<uint32_t>() + nkeys, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&h[3], ctx->err_flag.p, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (int rc = error_from_flag(ctx, (int)(uint32_t)h[3])) return rc;   // decode errors stop the call before any list is built
+            jobs_total = (uint32_t)h[2];
+            diff_slots = h[1];
+            // boundary form when it holds at most 3/4 of the entries of the id form (a run of consecutive ids costs 2
+            // entries whatever its length; a lone id costs 2 instead of 1), or when the caller insists
+            diff = want_nb && (((ctx->cfg.flags & KDBX_FLAG_BOUNDARY_LISTS) != 0) || h[0] * 4 <= ctx->sum_l * 3);
+        }
+    }
+    CK(ctx->flat.ensure(diff ? (diff_slots + 64) * 4 : resident ? (ctx->sum_n + 64) * 4 : cap * 4));
+    if (resident && !diff) CK(ctx->first_id.ensure(ctx->P * 4));
+    if (!resident) { CK(ctx->jobs.ensure(cap * sizeof(Job))); CK(ctx->units.ensure(cap * sizeof(Unit))); }
+    if (!resident) {   // chunk boundaries come from the device; decode errors stop the call before any chain is walked
+        if (cached) bounds = M.bounds;
+        else {
+            CK(cudaMemcpyAsync(bounds.data(), ctx->bounds.p, (nchunks + 1) * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (int rc = check_device_error(ctx)) return rc;
+        }
+    }   // (resident mode: the expansion only copies by the validated sizes; the flag is read before the jobs are filled in)
 
     cudaEvent_t ev_expand_a = nullptr, ev_expand_b = nullptr;
     if (resident) {
         cudaEvent_t a = ctx->event();
         uint32_t n_launch = 0;
         for (const auto& lv : ctx->levels) if (lv.second > lv.first) ++n_launch;
-        if (n_launch) {
+        if (n_launch && diff) {
+            const uint64_t capacity = ctx->flat.bytes / 4;
+            if (int rc = launch_level_graph(ctx, ctx->g_expand_diff, {ctx->order.p, ctx->nodes.p, ctx->boff.p, ctx->nb.p, ctx->ownb.p, ctx->loc.p, ctx->flat.p, ctx->err_flag.p}, [&] {
+                    for (size_t k = 0; k < ctx->levels.size(); ++k) {  // ascending num_samples: parents first
+                        const uint32_t b = ctx->levels[k].first, e = ctx->levels[k].second;
+                        if (e <= b) continue;
+                        k_expand_level_diff<kLevelLanes><<<blocks_for((uint64_t)(e - b) * kLevelLanes, 256), 256, 0, st>>>(
+                            e - b, ctx->order.as<uint32_t>() + b, ctx->nodes.as<Node>(), ctx->boff.as<uint64_t>(), ctx->nb.as<uint32_t>(),
+                            ctx->ownb.as<uint32_t>(), ctx->loc.as<uint32_t>(), ctx->flat.as<uint32_t>(), capacity, ctx->err_flag.as<int>());
+                    }
+                })) return rc;
+        } else if (n_launch) {
             if (int rc = launch_level_graph(ctx, ctx->g_expand, {ctx->order.p, ctx->nodes.p, ctx->noff.p, ctx->loc.p, ctx->flat.p, ctx->first_id.p}, [&] {
                     for (size_t k = 0; k < ctx->levels.size(); ++k) {  // ascending num_samples: parents first
                         const uint32_t b = ctx->levels[k].first, e = ctx->levels[k].second;
@@ -1424,12 +1580,20 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         ev_expand_a = a;
         ev_expand_b = ctx->event();
     }
-    const size_t smem = pl.smem;
-    CK(cudaFuncSetAttribute(k_scatter_add, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int blocks_per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_scatter_add, (int)pl.threads, smem));
-    if (blocks_per_sm < 1) return ctx->fail(KDBX_ERR_CUDA, "scatter kernel does not fit on an SM");
-    const unsigned scatter_grid = (unsigned)(ctx->sm_count * blocks_per_sm);
+    unsigned scatter_grid = M.scatter_grid;
+    const size_t smem = diff ? pl.smem_diff : pl.smem;
+    if (!cached || M.diff != diff) {
+        int blocks_per_sm = 0;
+        if (diff) {
+            CK(cudaFuncSetAttribute(k_scatter_diff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_scatter_diff, (int)pl.threads, smem));
+        } else {
+            CK(cudaFuncSetAttribute(k_scatter_add, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_scatter_add, (int)pl.threads, smem));
+        }
+        if (blocks_per_sm < 1) return ctx->fail(KDBX_ERR_CUDA, "scatter kernel does not fit on an SM");
+        scatter_grid = (unsigned)(ctx->sm_count * blocks_per_sm);
+    }
     if (smem_buckets) CK(ctx->blockhist.ensure((size_t)wide_grid * nkeys * 4 + 16));
 
     struct ChunkEv { cudaEvent_t a, b, c, d; };
@@ -1441,6 +1605,29 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     }
     const uint32_t nloops = (uint32_t)bounds.size() - 1;
     uint64_t jobs_cap = resident ? std::min<uint64_t>(ctx->jobs.bytes / sizeof(Job), ctx->units.bytes / sizeof(Unit)) : cap;  // slots allocated
+    std::vector<uint64_t> jobs_in_pass;
+    uint32_t pass = 0;
+    // grows the job / unit arrays of a resident pass to its exact job count: known from the last call, or read now
+    auto ensure_job_slots = [&](uint64_t known) -> int {
+        if (!resident) return KDBX_OK;
+        uint64_t total = known;
+        if (!cached) {
+            uint32_t h_total = 0;
+            int h_flag = 0;   // decode errors surface here: before any job is filled in or executed
+            CK(cudaMemcpyAsync(&h_total, ctx->bucket_off.as<uint32_t>() + nkeys, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&h_flag, ctx->err_flag.p, sizeof h_flag, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (int rc = error_from_flag(ctx, h_flag)) return rc;
+            total = h_total;
+        }
+        jobs_in_pass.push_back(total);
+        if (total + 64 > jobs_cap) {
+            jobs_cap = total + 64;
+            CK(ctx->jobs.ensure(jobs_cap * sizeof(Job)));
+            CK(ctx->units.ensure(jobs_cap * sizeof(Unit)));
+        }
+        return KDBX_OK;
+    };
     for (uint32_t c = 0; c < nloops; ++c) {
         const uint64_t p0 = bounds[c], p1 = bounds[c + 1];
         if (p1 <= p0 || c % num_parts != part) continue;
@@ -1450,34 +1637,52 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
             k_expand<<<wide_grid, 256, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->loc.as<uint32_t>(), ctx->flat.as<uint32_t>());
         e.b = ctx->event();
         if (!hist_by_decoder) CK(cudaMemsetAsync(ctx->work.p, 0, ((size_t)nkeys + 1) * 8, st));
-        if (smem_buckets) {
-            // per-block slices of whole decoder blocks when the pass covers all patterns (then the decoder may
-            // already have counted the jobs); chunks are sliced evenly
+        const uint64_t known = cached && pass < M.jobs_in_pass.size() ? M.jobs_in_pass[pass] : 0;
+        if (hist_by_decoder) {
+            // counted by the decoder, offsets already in place (above): the job total is known
+            jobs_in_pass.push_back(jobs_total);
+            if (jobs_total + 64 > jobs_cap) {
+                jobs_cap = jobs_total + 64;
+                CK(ctx->jobs.ensure(jobs_cap * sizeof(Job)));
+                CK(ctx->units.ensure(jobs_cap * sizeof(Unit)));
+            }
+            if (diff)
+                k_job_fill_diff<<<wide_grid, kBucketThreads, 0, st>>>(ctx->P, ctx->nodes.as<Node>(), ctx->boff.as<uint64_t>(), ctx->nb.as<uint32_t>(),
+                                                                      ctx->ownb.as<uint32_t>(), ctx->W.as<uint32_t>(), ctx->loc.as<uint32_t>(), pl.rb_shift, nkeys,
+                                                                      ctx->blockhist.as<uint32_t>(), ctx->jobs.as<Job>(), per_block, d_physical);
+            else
+                k_job_fill_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
+                                                                      ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), ctx->first_id.as<uint32_t>(), 1u, pl.T, pl.tile_cols, pl.rb_shift, wb, we, nkeys,
+                                                                      ctx->blockhist.as<uint32_t>(), ctx->jobs.as<Job>(), per_block);
+            launches += 1;
+        } else if (smem_buckets) {
+            // per-block slices of whole decoder blocks when the pass covers all patterns; chunks are sliced evenly
             const uint64_t per = (p0 == 0 && p1 == ctx->P) ? per_block : 0;
-            if (!hist_by_decoder)
-                k_job_hist_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                                      ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
-                                                                      ctx->blockhist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates, per);
+            k_job_hist_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
+                                                                  ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, wb, we, nkeys,
+                                                                  ctx->blockhist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates, per);
             k_key_totals<<<blocks_for((uint64_t)nkeys + 1, 128), 128, 0, st>>>(nkeys, wide_grid, ctx->blockhist.as<uint32_t>(), ctx->hist.as<uint32_t>());
             if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
-            if (int rc = ensure_job_slots(ctx, resident, nkeys, jobs_cap)) return rc;
+            if (int rc = ensure_job_slots(known)) return rc;
             k_block_offsets<<<blocks_for((uint64_t)nkeys * 32, 256), 256, 0, st>>>(nkeys, wide_grid, ctx->bucket_off.as<uint32_t>(), ctx->blockhist.as<uint32_t>());
             k_job_fill_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                                  ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end, nkeys,
+                                                                  ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, wb, we, nkeys,
                                                                   ctx->blockhist.as<uint32_t>(), ctx->jobs.as<Job>(), per);
-            launches += hist_by_decoder ? 1 : 2;
+            launches += 5;
         } else {
             CK(cudaMemsetAsync(ctx->hist.p, 0, ((size_t)nkeys + 1) * 4, st));
             k_job_hist<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                   ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
+                                                   ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, wb, we,
                                                    ctx->hist.as<uint32_t>(), ctx->work.as<unsigned long long>(), d_total_updates);
             if (int rc = scan_exclusive_u32(ctx, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
-            if (int rc = ensure_job_slots(ctx, resident, nkeys, jobs_cap)) return rc;
+            if (int rc = ensure_job_slots(known)) return rc;
             CK(cudaMemcpyAsync(ctx->cursor.p, ctx->bucket_off.p, ((size_t)nkeys + 1) * 4, cudaMemcpyDeviceToDevice, st));
             k_job_fill<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                   ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, row_begin, row_end,
+                                                   ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), resident ? ctx->first_id.as<uint32_t>() : nullptr, resident ? 1u : 0u, pl.T, pl.tile_cols, pl.rb_shift, wb, we,
                                                    ctx->cursor.as<uint32_t>(), ctx->jobs.as<Job>());
+            launches += 4;
         }
+        ++pass;
         k_unit_count<<<blocks_for((uint64_t)nkeys + 1, 256), 256, 0, st>>>(nkeys, ctx->hist.as<uint32_t>(), ctx->work.as<unsigned long long>(),
                                                                             pl.unit_updates, ctx->ucount.as<uint32_t>());
         if (int rc = scan_exclusive_u32(ctx, ctx->ucount.as<uint32_t>(), ctx->uoff.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
@@ -1485,36 +1690,52 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
                                                              ctx->ucount.as<uint32_t>(), ctx->uoff.as<uint32_t>(), ctx->units.as<Unit>());
         CK(cudaMemsetAsync(d_unit_counter, 0, 4, st));
         e.c = ctx->event();
-        k_scatter_add<<<scatter_grid, pl.threads, smem, st>>>(ctx->units.as<Unit>(), ctx->uoff.as<uint32_t>() + nkeys, ctx->jobs.as<Job>(),
-                                                              ctx->flat.as<uint32_t>(), resident ? ctx->noff.as<uint64_t>() + p0 : nullptr, d_out, tri_base,
-                                                              pl.T, pl.tile_cols, pl.rb_shift, d_unit_counter);
+        if (diff)
+            k_scatter_diff<<<scatter_grid, pl.threads, smem, st>>>(ctx->units.as<Unit>(), ctx->uoff.as<uint32_t>() + nkeys, ctx->jobs.as<Job>(),
+                                                                   ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), d_out, pl.lo, pl.tile_cols, pl.rb_shift,
+                                                                   d_unit_counter);
+        else
+            k_scatter_add<<<scatter_grid, pl.threads, smem, st>>>(ctx->units.as<Unit>(), ctx->uoff.as<uint32_t>() + nkeys, ctx->jobs.as<Job>(),
+                                                                  ctx->flat.as<uint32_t>(), resident ? ctx->noff.as<uint64_t>() + p0 : nullptr, d_out, tri_base, pl.lo,
+                                                                  pl.T, pl.tile_cols, pl.rb_shift, d_unit_counter);
         e.d = ctx->event();
-        launches += 8;
+        launches += 4;
         s.scatter_launches += 1;
         cev.push_back(e);
     }
     cudaEvent_t ev_end = ctx->event();
     CK(cudaGetLastError());
-    unsigned long long total_updates = 0;
-    int h_flag = 0;
-    CK(cudaMemcpyAsync(&total_updates, d_total_updates, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&h_flag, ctx->err_flag.p, sizeof h_flag, cudaMemcpyDeviceToHost, st));
+    uint64_t* h = ctx->h_pinned;
+    h[4] = h[5] = h[6] = 0;
+    CK(cudaMemcpyAsync(&h[4], d_total_updates, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h[5], d_physical, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h[6], ctx->err_flag.p, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (int rc = error_from_flag(ctx, h_flag)) return rc;
+    if (int rc = error_from_flag(ctx, (int)(uint32_t)h[6])) return rc;
     s.ms_prepare = elapsed(ev_start, ev_prepared);
     for (const ChunkEv& e : cev) {
         s.ms_expand += elapsed(e.a, e.b);
         s.ms_bucket += elapsed(e.b, e.c);
         s.ms_scatter += elapsed(e.c, e.d);
     }
+    if (ev_bucket0) s.ms_bucket += elapsed(ev_bucket0, ev_bucket0_end);
     if (int rc = finish_upload(ctx)) return rc;
     s.ms_upload = ctx->ms_upload;
     if (ev_expand_a) s.ms_expand += elapsed(ev_expand_a, ev_expand_b);
     s.ms_total = elapsed(ev_start, ev_end);
-    s.updates = total_updates;
-    s.flat_ids = ctx->sum_n; s.local_ids = ctx->sum_l;
+    s.updates = h[4];
+    s.physical_updates = diff ? h[5] : h[4];
+    s.list_form = diff ? 1u : 0u;
+    s.flat_ids = diff ? diff_slots : ctx->sum_n; s.local_ids = ctx->sum_l;
     s.chunks = nloops; s.kernel_launches = launches;
     if (stats) *stats = s;
+    // what the next call with the same signature may take for granted
+    M.valid = true; M.gen = ctx->load_gen; M.row_begin = row_begin; M.row_end = row_end; M.part = part; M.num_parts = num_parts;
+    M.win_lo = ctx->win_lo; M.win_hi = ctx->win_hi; M.tile_cols = pl.tile_cols; M.tile_rows = pl.tile_rows; M.threads = pl.threads;
+    M.unit_updates = pl.unit_updates; M.flags = ctx->cfg.flags; M.chunk = pl.chunk;
+    M.resident = resident; M.diff = diff; M.nchunks = nchunks; M.scatter_grid = scatter_grid; M.diff_slots = diff_slots;
+    if (!resident) M.bounds = bounds;
+    M.jobs_in_pass = jobs_in_pass;
     return KDBX_OK;
 }
 
@@ -1623,11 +1844,14 @@ void kdbx_close(kdbx_ctx* ctx) {
                       &ctx->ucount, &ctx->uoff, &ctx->units, &ctx->counters, &ctx->blockhist, &ctx->tri, &ctx->rowupd, &ctx->first_id,
                       &ctx->sp_cnt, &ctx->sp_counts, &ctx->sp_rowptr, &ctx->sp_col, &ctx->sp_val, &ctx->slot_off, &ctx->slots,
                       &ctx->q_off, &ctx->q_kmers, &ctx->q_keys, &ctx->q_keys2, &ctx->q_runkeys, &ctx->q_runcnt, &ctx->q_out,
-                      &ctx->qx_alpha, &ctx->qx_seq, &ctx->qx_raw, &ctx->qx_sorted, &ctx->qx_count})
+                      &ctx->qx_alpha, &ctx->qx_seq, &ctx->qx_raw, &ctx->qx_sorted, &ctx->qx_count, &ctx->ownb, &ctx->nb, &ctx->boff})
         b->release();
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->g_push.exec) cudaGraphExecDestroy(ctx->g_push.exec);
     if (ctx->g_expand.exec) cudaGraphExecDestroy(ctx->g_expand.exec);
+    if (ctx->g_pull.exec) cudaGraphExecDestroy(ctx->g_pull.exec);
+    if (ctx->g_expand_diff.exec) cudaGraphExecDestroy(ctx->g_expand_diff.exec);
     if (ctx->up_stream) { cudaStreamSynchronize(ctx->up_stream); cudaStreamDestroy(ctx->up_stream); }
     for (cudaEvent_t e : {ctx->ev_up_begin, ctx->ev_up_hdr, ctx->ev_up_payload}) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1683,7 +1907,18 @@ int kdbx_load_patterns(kdbx_ctx* ctx, const kdbx_trie_view* v) {
         if (int rc = finish_upload(ctx)) return rc;
     }
     ctx->P = P; ctx->N = v->num_samples; ctx->payload_words = v->payload_words;
+    ctx->win_lo = 0; ctx->win_hi = ctx->N;
+    ++ctx->load_gen;
     ctx->loaded = true;
+    return KDBX_OK;
+}
+
+int kdbx_set_sample_window(kdbx_ctx* ctx, uint32_t lo, uint32_t hi) {
+    if (!ctx) return KDBX_ERR_ARG;
+    if (!ctx->loaded) return ctx->fail(KDBX_ERR_STATE, "no patterns loaded (call kdbx_load_patterns first)");
+    if (lo > hi || hi > ctx->N) return ctx->fail(KDBX_ERR_ARG, "bad sample window [%u,%u) for %u samples", lo, hi, ctx->N);
+    lo &= ~31u;   // row blocks and column windows are laid on a 32-id grid
+    if (lo != ctx->win_lo || hi != ctx->win_hi) { ctx->win_lo = lo; ctx->win_hi = hi; ctx->prepared = false; ++ctx->load_gen; }
     return KDBX_OK;
 }
 
@@ -1729,6 +1964,7 @@ int kdbx_row_updates(kdbx_ctx* ctx, uint64_t* out) {
     if (!ctx) return KDBX_ERR_ARG;
     if (!ctx->loaded) return ctx->fail(KDBX_ERR_STATE, "no patterns loaded (call kdbx_load_patterns first)");
     if (!out) return ctx->fail(KDBX_ERR_ARG, "output pointer is NULL");
+    if (int rc = require_full_window(ctx, "kdbx_row_updates")) return rc;
     CK(cudaSetDevice(ctx->device));
     Plan pl;
     if (int rc = make_plan(ctx, pl)) return rc;

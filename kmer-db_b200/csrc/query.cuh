@@ -151,6 +151,7 @@ int new2all_core(kdbx_ctx* ctx, uint64_t count, uint64_t kmer_base, uint32_t q_b
 int new2all_impl(kdbx_ctx* ctx, const uint64_t* kmers, const uint64_t* q_off, uint32_t n_queries, uint32_t* out, kdbx_stats* stats) {
     if (!ctx->loaded) return ctx->fail(KDBX_ERR_STATE, "no patterns loaded (call kdbx_load_patterns first)");
     if (!ctx->tables_loaded) return ctx->fail(KDBX_ERR_STATE, "no k-mer tables loaded (call kdbx_load_hashtables first)");
+    if (int rc = require_full_window(ctx, "kdbx_new2all_batch")) return rc;
     if (n_queries && (!q_off || !out)) return ctx->fail(KDBX_ERR_ARG, "kdbx_new2all_batch: NULL argument");
     for (uint32_t q = 0; q < n_queries; ++q)
         if (q_off[q + 1] < q_off[q]) return ctx->fail(KDBX_ERR_ARG, "kdbx_new2all_batch: q_off must be non-decreasing");
@@ -169,6 +170,8 @@ int new2all_impl(kdbx_ctx* ctx, const uint64_t* kmers, const uint64_t* q_off, ui
         if (rc < 0) return rc;
         if (int rc2 = check_device_error(ctx)) return rc2;
     }
+    // errors of earlier calls (a table that pointed at a missing pattern, since reloaded) must not fail this one
+    CK(cudaMemsetAsync(ctx->err_flag.p, 0, 16, st));
     cudaEvent_t ev1 = ctx->event();
     if (n_queries == 0 || N == 0) { if (stats) *stats = s; return KDBX_OK; }
 
@@ -217,6 +220,7 @@ int load_hashtables_impl(kdbx_ctx* ctx, const kdbx_tables_view* v) {
     if (!v->slots) return ctx->fail(KDBX_ERR_ARG, "kdbx_load_hashtables: slots is NULL");
     CK(cudaSetDevice(ctx->device));
     ctx->tables_loaded = false;
+    if (ctx->err_flag.p) CK(cudaMemsetAsync(ctx->err_flag.p, 0, 16, ctx->stream));
     CK(ctx->slot_off.ensure((T + 1) * 8)); CK(ctx->slots.ensure(total * 8));
     ctx->ev_used = 0;
     cudaEvent_t a = ctx->event();

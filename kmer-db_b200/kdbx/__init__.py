@@ -44,10 +44,11 @@ class Stats(C.Structure):
                 ("ms_upload", C.c_float), ("ms_prepare", C.c_float), ("ms_expand", C.c_float), ("ms_bucket", C.c_float),
                 ("ms_scatter", C.c_float), ("ms_total", C.c_float), ("ms_download", C.c_float),
                 ("scatter_launches", C.c_uint32), ("_pad", C.c_uint32), ("probes", C.c_uint64), ("hits", C.c_uint64),
-                ("ms_probe", C.c_float), ("ms_compact", C.c_float), ("reserved", C.c_uint64 * 2)]
+                ("ms_probe", C.c_float), ("ms_compact", C.c_float), ("physical_updates", C.c_uint64),
+                ("list_form", C.c_uint32), ("_pad2", C.c_uint32)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k not in ("_pad", "reserved")}
+        return {k: getattr(self, k) for k, _ in self._fields_ if k not in ("_pad", "_pad2", "reserved")}
 
 
 class MetricBound(C.Structure):
@@ -89,6 +90,8 @@ class BuildArrays(C.Structure):
 METRICS = {"jaccard": 0, "min": 1, "max": 2, "cosine": 3}
 FLAG_CHUNKED_LISTS = 1
 FLAG_ASYNC_UPLOAD = 2
+FLAG_ID_LISTS = 4
+FLAG_BOUNDARY_LISTS = 8
 
 
 class SynthParams(C.Structure):
@@ -105,7 +108,7 @@ class Totals(C.Structure):
 
 # every symbol include/kdbx.h declares (tests check that the library exports all of them)
 KDBX_SYMBOLS = ["kdbx_abi_version", "kdbx_device_count", "kdbx_open", "kdbx_close", "kdbx_last_error",
-                "kdbx_host_alloc", "kdbx_host_free", "kdbx_load_patterns", "kdbx_row_updates", "kdbx_all2all_dense",
+                "kdbx_host_alloc", "kdbx_host_free", "kdbx_load_patterns", "kdbx_set_sample_window", "kdbx_row_updates", "kdbx_all2all_dense",
                 "kdbx_all2all_dense_rows", "kdbx_all2all_dense_rows_device", "kdbx_all2all_dense_part_device", "kdbx_all2all_sparse", "kdbx_free_csr",
                 "kdbx_load_hashtables", "kdbx_new2all_batch", "kdbx_debug_fetch",
                 "kdbx_builder_open", "kdbx_builder_close", "kdbx_builder_adopt", "kdbx_builder_add_sequence", "kdbx_builder_add_kmers",
@@ -142,6 +145,7 @@ def load():
     k.kdbx_host_free.argtypes = [C.c_void_p]
     k.kdbx_host_free.restype = None
     k.kdbx_load_patterns.argtypes = [C.c_void_p, P(TrieView)]
+    k.kdbx_set_sample_window.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
     k.kdbx_row_updates.argtypes = [C.c_void_p, C.c_void_p]
     k.kdbx_all2all_dense.argtypes = [C.c_void_p, C.c_void_p, P(Stats)]
     k.kdbx_all2all_dense_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, P(Stats)]
@@ -428,6 +432,10 @@ class Context:
         self._keep = (trie_or_view, keep)
         self._check(self._k.kdbx_load_patterns(self._p, C.byref(v)))
         self.num_samples, self.num_patterns = int(v.num_samples), int(v.num_patterns)
+
+    def set_sample_window(self, lo, hi):
+        """Declare that every sample id of the staged trie lies in [lo, hi) (kdbx_set_sample_window)."""
+        self._check(self._k.kdbx_set_sample_window(self._p, lo, hi))
 
     def all2all_dense(self, out: np.ndarray | None = None):
         n = self.num_samples

@@ -223,6 +223,55 @@ uint64_t oracle_all2all_regrouped(uint64_t P, uint32_t N, const int64_t* num_kme
     return fail ? UINT64_MAX : ops;
 }
 
+/* The same matrix by the run-boundary ("difference") form the CUDA library uses when sample lists hold runs of
+ * consecutive ids (kmer-db_b200/csrc/diff.cuh; ours — the reference's nearest relative is the 16-consecutive-id fast
+ * path of row_add, src/simd/row_add_avx2.cpp:38-75).  A pattern's full list is kept as its sorted run boundaries
+ * B = [s1, e1+1, s2, e2+1, ...]; a local row r receives +W_p at the even and -W_p at the odd entries of B that lie
+ * below r, into a difference matrix; prefix sums along every row (columns below the diagonal only) restore the
+ * counts.  All sums are modulo 2^32.  Returns the number of difference updates performed, reports U through
+ * *u_out (UINT64_MAX on allocation failure). */
+uint64_t oracle_all2all_boundary(uint64_t P, uint32_t N, const int64_t* num_kmers, const int64_t* parent_id, const uint32_t* n,
+                                 const uint32_t* l, const uint32_t* last, const uint64_t* payload_off, const uint64_t* payload,
+                                 uint32_t* tri, uint64_t* u_out) {
+    const uint64_t cells = N ? (uint64_t)N * (N - 1) / 2 : 0;
+    memset(tri, 0, cells * sizeof(uint32_t));
+    int64_t* W = (int64_t*)malloc(P * sizeof(int64_t));
+    uint32_t* full = (uint32_t*)malloc(((size_t)N + 1) * sizeof(uint32_t));
+    uint32_t* B = (uint32_t*)malloc((2 * (size_t)N + 2) * sizeof(uint32_t));
+    if (!W || !full || !B) { free(W); free(full); free(B); return UINT64_MAX; }
+    memcpy(W, num_kmers, P * sizeof(int64_t));
+    for (uint64_t i = P; i-- > 1;)
+        if (parent_id[i] >= 0) W[parent_id[i]] += W[i];
+    uint64_t U = 0, phys = 0;
+    for (uint64_t p = 0; p < P; ++p) {
+        if (l[p] == 0) continue;
+        uint32_t* out = full + n[p];
+        for (int64_t q = (int64_t)p; q >= 0; q = parent_id[q]) {
+            out -= l[q];
+            oracle_decode_local(payload + payload_off[q], l[q], last[q], out);
+        }
+        uint32_t nb = 0;   /* run boundaries of the full list */
+        for (uint32_t i = 0; i < n[p]; ++i) {
+            if (i == 0 || full[i] != full[i - 1] + 1) B[nb++] = full[i];
+            if (i + 1 == n[p] || full[i + 1] != full[i] + 1) B[nb++] = full[i] + 1;
+        }
+        const uint32_t w = (uint32_t)W[p];
+        for (uint32_t i = n[p] - l[p]; i < n[p]; ++i) {
+            const uint64_t r = full[i];
+            uint32_t* row = tri + r * (r - 1) / 2;
+            for (uint32_t e = 0; e < nb && B[e] < r; ++e) { row[B[e]] += (e & 1) ? 0u - w : w; ++phys; }
+            U += i;
+        }
+    }
+    for (uint64_t r = 1; r < N; ++r) {   /* differences -> counts */
+        uint32_t* row = tri + r * (r - 1) / 2;
+        for (uint64_t c = 1; c < r; ++c) row[c] += row[c - 1];
+    }
+    free(W); free(full); free(B);
+    if (u_out) *u_out = U;
+    return phys;
+}
+
 int oracle_all2all_bruteforce(uint64_t P, uint32_t N, const int64_t* num_kmers, const int64_t* parent_id, const uint32_t* n,
                               const uint32_t* l, const uint32_t* last, const uint64_t* payload_off, const uint64_t* payload,
                               uint32_t* tri) {

@@ -24,6 +24,8 @@ def load_oracle():
     lib.oracle_all2all_bruteforce.restype = C.c_int
     lib.oracle_all2all_regrouped.argtypes = [C.c_uint64, C.c_uint32] + [vp] * 8
     lib.oracle_all2all_regrouped.restype = C.c_uint64
+    lib.oracle_all2all_boundary.argtypes = [C.c_uint64, C.c_uint32] + [vp] * 9
+    lib.oracle_all2all_boundary.restype = C.c_uint64
     lib.oracle_all2all_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
     lib.oracle_all2all_file.restype = C.c_uint64
     lib.oracle_decode_local.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
@@ -55,6 +57,18 @@ def oracle_regrouped(lib, N, a):
                                        tri.ctypes.data)
     assert ops != 2**64 - 1
     return tri[:tri_cells(N)], ops
+
+
+def oracle_boundary(lib, N, a):
+    """(tri, U, difference updates) by the run-boundary form of kmer-db_b200/csrc/diff.cuh."""
+    tri = np.zeros(max(1, tri_cells(N)), dtype=np.uint32)
+    pay = a["payload"] if a["payload"].size else np.zeros(2, np.uint64)
+    U = C.c_uint64(0)
+    phys = lib.oracle_all2all_boundary(len(a["n"]), N, a["num_kmers"].ctypes.data, a["parent_id"].ctypes.data, a["n"].ctypes.data,
+                                       a["l"].ctypes.data, a["last"].ctypes.data, a["payload_off"].ctypes.data, pay.ctypes.data,
+                                       tri.ctypes.data, C.addressof(U))
+    assert phys != 2**64 - 1
+    return tri[:tri_cells(N)], U.value, phys
 
 
 def oracle_bruteforce(lib, N, a):

@@ -68,7 +68,9 @@ def test_random_tries_bit_exact(libs, oracle, seed):
                                  dict(tile_rows=1), dict(tile_rows=8, tile_cols=64), dict(tile_rows=16, scatter_threads=128),
                                  dict(tile_rows=2, tile_cols=160, scatter_threads=1024, chunk_ids=9000),
                                  dict(flags=1), dict(flags=1, chunk_ids=4096, tile_cols=96), dict(flags=1, tile_rows=4, unit_updates=50),
-                                 dict(flags=2), dict(flags=3, chunk_ids=4096)])
+                                 dict(flags=2), dict(flags=3, chunk_ids=4096),
+                                 dict(flags=4), dict(flags=8), dict(flags=8, unit_updates=1), dict(flags=8, tile_rows=8),
+                                 dict(flags=8, scatter_threads=256), dict(flags=10, unit_updates=3000)])
 def test_schedule_knobs_do_not_change_results(libs, oracle, cfg):
     """column tiles (T>1), row blocks of 1..32 rows, many chunks, tiny / huge work units: same bits."""
     rng = np.random.default_rng(7)
@@ -81,7 +83,93 @@ def test_schedule_knobs_do_not_change_results(libs, oracle, cfg):
     if "chunk_ids" in cfg and cfg.get("flags"):
         assert st.chunks > 1
     # flags=1 (KDBX_FLAG_CHUNKED_LISTS) forces the chunked parent-chain expansion; the default here is
-    # the resident level-ordered one
+    # the resident level-ordered one; 4 = id lists, 8 = run-boundary lists (N <= 1536: one column window)
+    if cfg.get("flags", 0) & 8:
+        assert st.list_form == 1 and st.physical_updates > 0
+    if cfg.get("flags", 0) & 4:
+        assert st.list_form == 0 and st.physical_updates == U
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_boundary_lists_bit_exact(libs, oracle, seed):
+    """Run-boundary lists (csrc/diff.cuh) against the oracle AND the oracle's restatement of that form: same
+    bits, the same number of difference updates; repeated calls on one context (the no-host-round-trip path:
+    sizes and levels cached from the first call) give the same result."""
+    rng = np.random.default_rng(500 + seed)
+    N = int(rng.integers(2, 1500))
+    a, _ = ou.random_trie(rng, N, int(rng.integers(2, 3000)), max_local=int(rng.integers(1, 60)),
+                          big_weights=(seed % 2 == 0), dense_lists=(seed % 3 != 0))
+    want, U = ou.oracle_all2all(oracle, N, a)
+    _, _, phys = ou.oracle_boundary(oracle, N, a)
+    with libs.Context(device=0, flags=libs.FLAG_BOUNDARY_LISTS) as c:
+        v, keep = libs.view_from_arrays(N, a["num_kmers"], a["parent_id"], a["n"], a["l"], a["last"], a["bits"], a["payload_off"],
+                                        a["payload"])
+        c.load_patterns(v, keep)
+        for rep in range(3):
+            got, st = c.all2all_dense()
+            assert st.updates == U and st.list_form == 1
+            assert st.physical_updates == phys
+            assert np.array_equal(got, want), f"call {rep}"
+    # the default picks the form from the decoded lists: consecutive ids -> boundaries
+    got, st = _run(libs, N, a)
+    assert np.array_equal(got, want) and st.updates == U
+    if seed % 3 != 0 and N > 64:
+        assert st.list_form == 1 and st.physical_updates < U
+
+
+def test_cached_metadata_follows_the_staged_trie(libs, oracle):
+    """Sizes, levels and the list form are remembered per staged trie: loading another trie into the same
+    context, or changing the row range, must not reuse them."""
+    rng = np.random.default_rng(77)
+    tries = []
+    for N, P, dense in ((700, 2500, True), (300, 900, False), (1200, 4000, True)):
+        a, _ = ou.random_trie(rng, N, P, max_local=30, big_weights=True, dense_lists=dense)
+        tries.append((N, a, ou.oracle_all2all(oracle, N, a)))
+    with libs.Context(device=0) as c:
+        for rnd in range(2):
+            for N, a, (want, U) in tries:
+                v, keep = libs.view_from_arrays(N, a["num_kmers"], a["parent_id"], a["n"], a["l"], a["last"], a["bits"],
+                                                a["payload_off"], a["payload"])
+                c.load_patterns(v, keep)
+                for _ in range(2):
+                    got, st = c.all2all_dense()
+                    assert st.updates == U and np.array_equal(got, want)
+                half, _ = c.all2all_dense_rows(N // 3, N)
+                assert np.array_equal(half, want[ou.tri_cells(N // 3):])
+                got, st = c.all2all_dense()
+                assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("lo,width,total", [(640, 300, 2000), (0, 1536, 4000), (2048, 1000, 3048), (100, 40, 200)])
+def test_sample_window(libs, oracle, lo, width, total):
+    """kdbx_set_sample_window: a trie whose samples lie in [lo, lo + width) of a larger sample table is planned like
+    a database of `width` samples (one column window, boundary lists) and fills exactly its block of the matrix."""
+    rng = np.random.default_rng(lo + width)
+    a, _ = ou.random_trie(rng, width, 2000, max_local=25, big_weights=True, dense_lists=True)
+    small, U = ou.oracle_all2all(oracle, width, a)
+    b = dict(a)
+    b["last"] = np.where(a["l"] > 0, a["last"] + lo, a["last"]).astype(np.uint32)
+    want, U2 = ou.oracle_all2all(oracle, total, b)
+    assert U2 == U
+    with libs.Context(device=0) as c:
+        v, keep = libs.view_from_arrays(total, b["num_kmers"], b["parent_id"], b["n"], b["l"], b["last"], b["bits"], b["payload_off"],
+                                        b["payload"])
+        c.load_patterns(v, keep)
+        plain, st0 = c.all2all_dense()
+        assert np.array_equal(plain, want) and st0.updates == U
+        c.set_sample_window(lo, lo + width)
+        for _ in range(2):
+            got, st = c.all2all_dense()
+            assert st.updates == U and np.array_equal(got, want)
+            assert st.list_form == 1
+        rows, _ = c.all2all_dense_rows(lo + 5, min(total, lo + width + 7))
+        assert np.array_equal(rows, want[ou.tri_cells(lo + 5):ou.tri_cells(min(total, lo + width + 7))])
+        if lo >= 32:
+            c.set_sample_window(lo + 32, lo + width)
+            with pytest.raises(libs.KdbxError, match="outside the declared sample window"):
+                c.all2all_dense()
+        with pytest.raises(libs.KdbxError, match="bad sample window"):
+            c.set_sample_window(5, total + 1)
 
 
 def test_edge_cases(libs, oracle):

@@ -26,7 +26,7 @@ def test_libraries_export_every_declared_symbol(libs):
         assert hasattr(h, name), name
     assert set(_declared("kdbx.h")) == set(libs.KDBX_SYMBOLS)
     assert set(_declared("kdbx_host.h")) == set(libs.KDBXH_SYMBOLS)
-    assert k.kdbx_abi_version() == 3
+    assert k.kdbx_abi_version() == 4
 
 
 def test_struct_sizes_match_header(libs, tmp_path):

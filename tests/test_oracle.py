@@ -82,3 +82,27 @@ def test_regrouped_formulation_gives_the_same_bits(oracle, libs, golden_dbs, see
         re, ops = ou.oracle_regrouped(oracle, 120, t.arrays())
         assert np.array_equal(tri, re)
         assert ops < U   # the generated cluster tries share deeply: the regrouped form does less work
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_boundary_formulation_gives_the_same_bits(oracle, libs, golden_dbs, seed):
+    """kmer-db_b200/csrc/diff.cuh: lists as run boundaries, +w / -w into a difference matrix, prefix sums along the
+    rows — exact modulo 2^32, and fewer updates than U wherever the lists hold runs of consecutive ids."""
+    rng = np.random.default_rng(300 + seed)
+    N = int(rng.integers(2, 90))
+    a, _ = ou.random_trie(rng, N, int(rng.integers(2, 400)), max_local=int(rng.integers(1, 14)), big_weights=(seed % 2 == 0),
+                          dense_lists=(seed % 3 == 0))
+    tri, U = ou.oracle_all2all(oracle, N, a)
+    bd, U2, phys = ou.oracle_boundary(oracle, N, a)
+    assert np.array_equal(tri, bd) and U2 == U
+    if seed == 0:
+        for name in ("virus.k18", "virus.k24", "synth.k21"):
+            t = libs.Trie.read_db(golden_dbs[name][0])
+            tri, U = ou.oracle_all2all(oracle, t.num_samples, t.arrays())
+            bd, U2, phys = ou.oracle_boundary(oracle, t.num_samples, t.arrays())
+            assert np.array_equal(tri, bd) and U2 == U
+        t = libs.Trie.synth(num_samples=120, num_clusters=2, genome_kmers=30000, seed=3)
+        tri, U = ou.oracle_all2all(oracle, 120, t.arrays())
+        bd, U2, phys = ou.oracle_boundary(oracle, 120, t.arrays())
+        assert np.array_equal(tri, bd) and U2 == U
+        assert phys < 0.7 * U   # cluster members sit side by side in sample order: their lists are mostly runs

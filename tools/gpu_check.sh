@@ -30,6 +30,9 @@ for step in "$@"; do
     bench_2000) timeout 1200 python bench.py --samples 2000 --clusters 8 --steps 3 --warmup 3 --no-cpu-baseline > "$OUT/bench_2000.json" 2> "$OUT/bench_2000.err"; echo "bench_2000 rc=$?" | tee -a "$OUT/summary.txt";;
     test_multi) timeout 600 python -m pytest tests -m gpu -x -q -k "multi_gpu or sharding" > "$OUT/pytest_multi.log" 2>&1; echo "pytest_multi rc=$?" | tee -a "$OUT/summary.txt";;
     modes) timeout 1500 python tools/bench_modes.py --out-dir /tmp/kdbx_modes > "$OUT/modes.jsonl" 2> "$OUT/modes.err"; echo "modes rc=$?" | tee -a "$OUT/summary.txt";;
+    bench_ids) timeout 900 python bench.py --no-cpu-baseline --no-e2e --list-form ids --steps 5 --warmup 3 > "$OUT/bench_ids.json" 2> "$OUT/bench_ids.err"; echo "bench_ids rc=$?" | tee -a "$OUT/summary.txt";;
+    sanitize) timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "random_tries or boundary_lists or sample_window or edge_cases" > "$OUT/sanitizer_memcheck.log" 2>&1; echo "memcheck rc=$?" | tee -a "$OUT/summary.txt"
+              timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "random_tries or boundary_lists" > "$OUT/sanitizer_racecheck.log" 2>&1; echo "racecheck rc=$?" | tee -a "$OUT/summary.txt";;
     *) echo "unknown step $step";;
   esac
 done
