@@ -4,34 +4,39 @@
     python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a kernels through the C ABI)
     python bench.py --impl reference --gpus N --steps K ...  # the UNMODIFIED reference binary on the host cores
 
-Workload (config.workload): BASELINE.json configs[1] — 1,000 synthetic 5 Mbp bacterial genomes,
-k=18, f=1.0, dense all2all — produced by the pattern-level generator (kmer-db_b200/host/synth.cpp:
-4 clusters x 250, every genome a copy of a random earlier cluster member with 0.5 % substitutions).
-A "step" is one full all2all over that database.  The unit of work U (updates) is a property of
-the database: U = sum_p l_p(2 n_p - l_p - 1)/2 = the number of `row[col] += w` executions of the
-reference's dense path.
+Workload (config.workload).  N = 1: BASELINE.json configs[1] — 1,000 synthetic 5 Mbp bacterial genomes, k=18, f=1.0,
+dense all2all — written by the stand-alone generator kmer-db_b200/bin/kdbx-synth (host/synth.cpp: 4 clusters x 250,
+every genome a copy of a random earlier cluster member with 0.5 % substitutions).  BOTH arms read the same .db file.
+A "step" is one full all2all over that database.  The unit of work U (updates) is a property of the database:
+U = sum_p l_p(2 n_p - l_p - 1)/2 = the number of `row[col] += w` executions of the reference's dense path
+(SURVEY.md §8d).
 
   value    K*U / device time of K steps, inputs (the raw trie) resident in HBM, result left in HBM;
            device time = CUDA events on the library's stream around each step, summed, max over ranks.
   e2e      same metric through the public C-ABI calls with HOST buffers: every step copies the trie
-           from pinned host memory (kdbx_load_patterns) and reads the matrix back (kdbx_all2all_dense_rows).
-  roofline the scatter-add kernel: 12 algorithmic bytes per update (4 B id + 4 B cell read + 4 B cell
-           write) x updates per launch / measured average launch duration, against the
-           measured HBM copy bandwidth in MEASURED_PEAKS.json.
-  cpu_baseline  the reference binary (oracle/_ref/kmer-db all2all -t <all cores>) on a bounded sample:
-           the first cluster (250 genomes x 5 Mbp = exactly a quarter of the workload's updates).
-With N>1 (torchrun, one rank per GPU) the database is SHARDED: every rank holds, uploads and processes only its
-own sub-trie (kdbxh_partition: a piece of the trie's depth-first preorder plus the ancestors of that piece with
-num_kmers = 0; the matrix is linear in num_kmers, so the parts' matrices add up), runs the complete single-GPU
-pipeline on it into a partial matrix, and ONE NCCL all-reduce (uint32 sum over NVLink) adds the partial matrices —
-the exchange step BASELINE.json's north_star names.  Nothing is replicated but the few ancestor chains.
-  --scaling weak  (default)  per-GPU work fixed: N GPUs process a database of N x 1000 genomes (4N clusters, the
-                  shape of BASELINE.json configs[2]); rank r's shard is the configs[1] database laid onto the sample
-                  ids [1000 r, 1000 (r+1)) (kdbxh_relabel) — what the partitioner yields for a database whose clusters
-                  are disjoint subtrees.  U = N x U(configs[1]); the matrix is (1000 N)^2 / 2 cells.
-  --scaling strong           total work fixed: the configs[1] database is cut into N parts by kdbxh_partition
-                  (host, untimed: it is the layout of the sharded database); rank 0 also computes the unsharded
-                  matrix once and the all-reduced result must equal it bit for bit.
+           from pinned host memory (kdbx_load_patterns) and reads the matrix back.
+  roofline the scatter-add kernel.  hbm: 12 algorithmic bytes per update (4 B id + 4 B cell read + 4 B cell write,
+           SURVEY.md §8d) x U per launch / measured average launch duration, against the measured HBM copy bandwidth
+           in MEASURED_PEAKS.json — an HBM-EQUIVALENT figure: the accumulators live in shared memory, so it is not a
+           bound and exceeds 1.  smem_atomic: the physical bound — shared-memory reductions issued per second against
+           the conflict-free red.shared.add.u32 peak of the microbenchmark (profiles/r01_microbench_atomics.txt).
+  cpu_baseline  the reference binary (oracle/_ref/kmer-db all2all -t <all cores>) once on the SAME .db, its CSV kept
+           and compared byte for byte with the CSV written from the GPU result (parity_checked).
+  --impl reference   K timed runs of the reference binary on the same .db (N = 1).  At N > 1 the weak-scaling database
+           is N times larger and the reference cannot finish 25 runs of it within the driver's limit: rank 0 then times
+           the configs[1] database (1/N of the workload, said in cpu_baseline.sample); updates/s is a rate.
+
+N > 1 (torchrun, one rank per GPU): the database is SHARDED.  kdbxh_partitioner cuts the trie into N sub-tries (pieces
+of its depth-first preorder balanced on a cost model, plus the ancestor chain of each piece with num_kmers = 0; the
+matrix is linear in num_kmers, so the parts' matrices add up); every rank stages only its own part, declares the band of
+sample ids it covers (kdbx_set_sample_window), runs the complete single-GPU pipeline on it and ONE
+ncclReduceScatter(uint32, sum) INSIDE the library (kdbx_all2all_dense_reduce_scatter*) leaves every rank with its block
+of the packed triangle.  torch.distributed only carries the NCCL unique id, the barriers and the max over ranks.
+  --scaling weak  (default)  N x 1000 genomes in 4N clusters of UNEQUAL sizes (cluster_skew 0.3): the shape of
+                  BASELINE.json configs[2]; the partitioner has to cut inside clusters.
+  --scaling strong           the configs[1] database cut into N parts.
+In both, rank 0 generates and partitions once (host, untimed: it is the layout of the sharded database, like
+`build`), writes the parts next to the database and every rank reads its own.
 """
 import argparse
 import json
@@ -44,9 +49,13 @@ import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
-sys.path.insert(0, str(ROOT / "kmer-db_b200"))
+PKG = ROOT / "kmer-db_b200"
+sys.path.insert(0, str(PKG))
 
 ALGO_BYTES_PER_UPDATE = 12
+# conflict-free red.shared.add.u32 rate of one B200, ids in registers (kmer-db_b200/tools/microbench.cu,
+# profiles/r01_microbench_atomics.txt: "1 CTA/SM x 32 warps ... consecutive columns")
+SMEM_ATOMIC_PEAK = 5.097e12
 
 
 def parse_args():
@@ -55,57 +64,71 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--samples", type=int, default=1000)
-    ap.add_argument("--clusters", type=int, default=4)
+    ap.add_argument("--samples", type=int, default=1000, help="genomes per GPU")
+    ap.add_argument("--clusters", type=int, default=4, help="clusters per GPU's share of the genomes")
     ap.add_argument("--genome-kmers", type=int, default=5_000_000)
     ap.add_argument("--k", type=int, default=18)
     ap.add_argument("--mu", type=float, default=0.005)
     ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--skew", type=float, default=0.3, help="cluster size spread of the multi-GPU weak-scaling database")
     ap.add_argument("--chunk-ids", type=int, default=0)
     ap.add_argument("--tile-cols", type=int, default=0)
     ap.add_argument("--unit-updates", type=int, default=0)
     ap.add_argument("--tile-rows", type=int, default=0)
     ap.add_argument("--scatter-threads", type=int, default=0)
     ap.add_argument("--chunked-lists", action="store_true", help="force the chunked parent-chain expansion")
-    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
-                    help="N>1: 'weak' = every rank owns a configs[1]-sized shard of an N-times larger database; "
-                         "'strong' = the configs[1] database cut into N sub-tries; both end in one NCCL all-reduce")
-    ap.add_argument("--emulate-shard", default="", help="debug, N=1 only: 'r/w' = run the weak-scaling shard of rank r of w "
-                    "ranks alone (no collective): what that rank would execute in a w-GPU run")
     ap.add_argument("--list-form", choices=["auto", "ids", "boundaries"], default="auto",
                     help="form of the full sample lists (kdbx.h: KDBX_FLAG_ID_LISTS / KDBX_FLAG_BOUNDARY_LISTS); auto = the library decides")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak")
+    ap.add_argument("--no-window", action="store_true", help="N>1: do not declare the parts' sample windows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cache-dir", default=os.environ.get("KDBX_CACHE", "/tmp/kdbx_cache"))
     return ap.parse_args()
 
 
-def workload_name(a):
-    return (f"{a.samples} synthetic {a.genome_kmers / 1e6:g} Mbp genomes, {a.clusters} clusters, mu={a.mu}, "
-            f"k={a.k}, f=1.0, dense all2all (BASELINE.json configs[1] shape)")
+# ---- the workload: one .db file per (shape, seed), written by the stand-alone generator -----------------------
+def db_shape(a, world):
+    """(samples, clusters, skew) of the database the run is about."""
+    if world > 1 and a.scaling == "weak":
+        return a.samples * world, a.clusters * world, a.skew
+    return a.samples, a.clusters, 0.0
 
 
-def cache_path(a, samples, clusters):
-    return Path(a.cache_dir) / f"synth_n{samples}_c{clusters}_L{a.genome_kmers}_k{a.k}_mu{a.mu}_s{a.seed}.db"
+def db_path(a, samples, clusters, skew):
+    sk = f"_sk{skew:g}" if skew else ""
+    return Path(a.cache_dir) / f"synth_n{samples}_c{clusters}_L{a.genome_kmers}_k{a.k}_mu{a.mu}_s{a.seed}{sk}.db"
 
 
-def get_workload(kdbx, a, samples, clusters, pinned, rank=0, barrier=None):
-    """Generate (rank 0) or read the cached database.  Same seed => cluster c is identical whether
-    generated alone or as part of the full workload, so the CPU sample is a true subset."""
-    path = cache_path(a, samples, clusters)
-    if rank == 0 and not path.exists():
+def ensure_db(a, samples, clusters, skew):
+    """Path and totals of the database; generated by bin/kdbx-synth (a host program: no CUDA) when missing."""
+    path = db_path(a, samples, clusters, skew)
+    meta = Path(str(path) + ".json")
+    if not (path.exists() and meta.exists()):
+        exe = PKG / "bin" / "kdbx-synth"
+        if not exe.exists():
+            raise RuntimeError(f"{exe} missing: run `make -C {PKG}` (or __graft_entry__.build())")
         path.parent.mkdir(parents=True, exist_ok=True)
         t0 = time.time()
-        t = kdbx.Trie.synth(num_samples=samples, num_clusters=clusters, genome_kmers=a.genome_kmers, k=a.k,
-                            mutation_rate=a.mu, seed=a.seed)
-        tmp = path.with_suffix(".tmp%d" % os.getpid())
-        t.write_db(tmp)
-        os.replace(tmp, path)
-        t.close()
+        subprocess.run([str(exe), "-o", str(path), "-n", str(samples), "-c", str(clusters), "-L", str(a.genome_kmers), "-k", str(a.k),
+                        "-mu", repr(a.mu), "-seed", str(a.seed), "-skew", repr(skew)], check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL)
         print(f"[bench] generated {path.name} in {time.time() - t0:.1f} s", file=sys.stderr)
-    if barrier:
-        barrier()
-    return kdbx.Trie.read_db(path, pinned=pinned), path
+    return path, json.loads(meta.read_text())
+
+
+def workload_name(a, samples, clusters, skew):
+    s = (f"{samples} synthetic {a.genome_kmers / 1e6:g} Mbp genomes, {clusters} clusters"
+         + (f" of unequal sizes (spread {skew:g})" if skew else "") + f", mu={a.mu}, k={a.k}, f=1.0, dense all2all")
+    return s + (" (BASELINE.json configs[1])" if (samples, clusters) == (1000, 4) and a.genome_kmers == 5_000_000 else
+                " (BASELINE.json configs[2] shape)" if samples > 1000 else "")
+
+
+def common_config(a, meta, samples, clusters, skew):
+    """The part of `config` that names the workload: identical in both arms."""
+    return {"workload": workload_name(a, samples, clusters, skew), "database": db_path(a, samples, clusters, skew).name,
+            "num_samples": int(meta["num_samples"]), "num_patterns": int(meta["num_patterns"]),
+            "updates_per_step": int(meta["updates"]), "sum_n": int(meta["sum_n"]), "sum_l": int(meta["sum_l"])}
 
 
 class ClockSampler:
@@ -180,36 +203,106 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def run_reference_binary(db_path, threads):
+def ref_csv_path(db):
+    return Path(str(db) + ".ref.csv")
+
+
+def run_reference_binary(db, threads, keep_csv=True):
     """Times the reference's own all2all (the span it prints as 'OK (x seconds)' after
-    'Calculating matrix of common k-mers...', src/console_all2all.cpp:31-36)."""
+    'Calculating matrix of common k-mers...', src/console_all2all.cpp:31-36).  The CSV it writes stays next to the
+    database (<db>.ref.csv): the GPU arm compares its own CSV with it."""
     exe = ROOT / "oracle" / "_ref" / "kmer-db"
     if not exe.exists():
         raise RuntimeError("oracle/_ref/kmer-db missing (run oracle/build_ref.sh where /root/reference is mounted)")
-    out = Path(db_path).with_suffix(".ref.csv")
-    r = subprocess.run([str(exe), "all2all", "-t", str(threads), str(db_path), str(out)], capture_output=True, text=True)
+    out = ref_csv_path(db)
+    tmp = Path(str(out) + ".tmp%d" % os.getpid())
+    r = subprocess.run([str(exe), "all2all", "-t", str(threads), str(db), str(tmp)], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("reference all2all failed: " + r.stderr[-300:])
     txt = r.stdout + r.stderr
     m = re.search(r"Calculating matrix of common k-mers\.\.\..*?OK \(([0-9.eE+-]+) seconds\)", txt, re.S)
     if not m:
         raise RuntimeError("could not parse the reference's timing line")
-    try:
-        out.unlink()
-    except OSError:
-        pass
+    if keep_csv:
+        os.replace(tmp, out)
+    else:
+        tmp.unlink(missing_ok=True)
     return float(m.group(1))
 
 
-def ncu_traffic_per_launch():
-    """dram bytes per scatter launch from the committed ncu summary, if one exists."""
+def files_identical(a, b, chunk=1 << 24):
+    if os.path.getsize(a) != os.path.getsize(b):
+        return False
+    with open(a, "rb") as fa, open(b, "rb") as fb:
+        while True:
+            x, y = fa.read(chunk), fb.read(chunk)
+            if x != y:
+                return False
+            if not x:
+                return True
+
+
+def ncu_traffic_per_launch(kernel):
+    """dram bytes per scatter launch from the committed ncu summary, if one exists for this kernel."""
     p = ROOT / "profiles" / "scatter_traffic.json"
     if p.exists():
         try:
-            return json.loads(p.read_text()).get("dram_bytes_per_launch")
+            d = json.loads(p.read_text())
+            if d.get("kernel", "k_scatter_add") == kernel:
+                return d.get("dram_bytes_per_launch")
         except Exception:
             return None
     return None
+
+
+def reference_arm(a, rank, world):
+    """The unmodified reference on the host cores.  Loads none of this repository's libraries."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    samples, clusters, skew = db_shape(a, world)
+    sample_note = None
+    if world > 1 and a.scaling == "weak":
+        # the N-GPU database is N times configs[1]; the bounded sample is configs[1] itself
+        path, meta = ensure_db(a, a.samples, a.clusters, 0.0)
+        sample_note = (f"the {workload_name(a, a.samples, a.clusters, 0.0)} database = about 1/{world} of the {world}-GPU workload "
+                       f"({samples} genomes, {clusters} clusters): {a.steps + a.warmup} runs of the full one do not fit the driver's limit")
+        cfg = {"workload": workload_name(a, samples, clusters, skew), "database": db_path(a, samples, clusters, skew).name,
+               "num_samples": samples, "sample_of_workload": common_config(a, meta, a.samples, a.clusters, 0.0)}
+    else:
+        path, meta = ensure_db(a, samples, clusters, skew)
+        cfg = common_config(a, meta, samples, clusters, skew)
+    U = int(meta["updates"])
+    for _ in range(a.warmup):
+        run_reference_binary(path, cores)
+    secs = [run_reference_binary(path, cores) for _ in range(a.steps)]
+    total = sum(secs)
+    v = U * a.steps / total
+    sample = sample_note or f"the whole workload: {meta['num_samples']} genomes, U={U:.4g} per step (same .db file as the GPU arm)"
+    cfg["l2_policy"] = "CPU arm: every step is a fresh process reading the .db from the page cache"
+    print(json.dumps({
+        "impl": "reference", "metric": "k-mer-pair updates/sec on all2all", "value": v, "unit": "updates/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps,
+        "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": cfg,
+        "arm": {"binary": "oracle/_ref/kmer-db 2.3.1 all2all (unmodified reference, built by oracle/build_ref.sh)", "threads": cores,
+                "seconds_per_step": [round(x, 3) for x in secs], "csv_kept": str(ref_csv_path(path).name)},
+        "cpu_baseline": {"value": v, "unit": "updates/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": v, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def _own_cells(rank, block, cells):
+    return max(0, min(cells, (rank + 1) * block) - min(cells, rank * block))
+
+
+def _broadcast_bytes(dist, torch, payload):
+    """rank 0's 128-byte NCCL unique id to every rank (torch.distributed is the launcher's plumbing here)."""
+    t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if payload is not None:
+        t.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().numpy().tobytes())
 
 
 def main():
@@ -218,29 +311,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
-    sample_n = max(1, a.samples // a.clusters)
 
     if a.impl == "reference":
-        if rank != 0:
-            return
-        import kdbx
-        t, path = get_workload(kdbx, a, sample_n, 1, pinned=False)
-        U = int(t.totals().updates)
-        t.close()
-        for _ in range(a.warmup):
-            run_reference_binary(path, cores)
-        secs = [run_reference_binary(path, cores) for _ in range(a.steps)]
-        total = sum(secs)
-        v = U * a.steps / total
-        sample = f"first cluster only: {sample_n} genomes x {a.genome_kmers / 1e6:g} Mbp, U={U:.4g} per step"
-        print(json.dumps({
-            "impl": "reference", "metric": "k-mer-pair updates/sec on all2all", "value": v, "unit": "updates/s",
-            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps,
-            "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "sample": sample, "threads": cores},
-            "cpu_baseline": {"value": v, "unit": "updates/s", "cores": cores, "kind": "reference", "sample": sample},
-            "e2e": {"value": v, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
+        reference_arm(a, rank, world)
         return
 
     import numpy as np
@@ -277,61 +350,66 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    trie, db_path = get_workload(kdbx, a, a.samples, a.clusters, pinned=True, rank=rank, barrier=barrier if world > 1 else None)
-    tot = trie.totals()
-    N0, P0, U0 = int(tot.num_samples), int(tot.num_patterns), int(tot.updates)
-    chunk_ids = a.chunk_ids
-    ctx = kdbx.Context(device=local_rank, chunk_ids=chunk_ids, tile_cols=a.tile_cols, unit_updates=a.unit_updates,
-                       tile_rows=a.tile_rows, scatter_threads=a.scatter_threads, flags=(kdbx.FLAG_CHUNKED_LISTS if a.chunked_lists else 0) | kdbx.FLAG_ASYNC_UPLOAD |
-                       {"auto": 0, "ids": kdbx.FLAG_ID_LISTS, "boundaries": kdbx.FLAG_BOUNDARY_LISTS}[a.list_form])
-    scaling = a.scaling
-    full_ref = None
-    t_shard = 0.0
-    if world == 1 and a.emulate_shard:
-        r_, w_ = (int(x) for x in a.emulate_shard.split("/"))
-        trie.relabel(r_ * N0, N0 * w_)
-        N, U_total = N0 * w_, U0
-    elif world == 1:
-        N, U_total = N0, U0
-    elif scaling == "weak":
-        t0 = time.perf_counter()
-        trie.relabel(rank * N0, N0 * world)   # this rank's shard of the N0*world-sample database
-        t_shard = time.perf_counter() - t0
-        N, U_total = N0 * world, U0 * world
-    else:
-        if rank == 0:  # the unsharded matrix, once, as the bit-exact check of the sharded path
-            ctx.load_patterns(trie)
-            full_ref = torch.zeros(max(1, kdbx.tri_cells(N0)), dtype=torch.int32, device="cuda")
-            ctx.all2all_dense_rows_device(0, N0, full_ref.data_ptr())
-        t0 = time.perf_counter()
-        part, _owned = trie.partition(world, rank, pinned=True)
-        t_shard = time.perf_counter() - t0
-        trie.close()
-        trie = part
-        N, U_total = N0, U0
-    tot = trie.totals()
-    P = int(tot.num_patterns)
-    ctx.load_patterns(trie)
-    r0, r1 = 0, N
-    cells = kdbx.tri_cells(N)
-    d_out = torch.zeros(max(1, cells), dtype=torch.int32, device="cuda")
-
-    def step():
-        """One all2all over this rank's resident (sub-)trie (+ the all-reduce); returns the library's stats."""
-        st = ctx.all2all_dense_rows_device(r0, r1, d_out.data_ptr())
-        if dist is not None:
-            dist.all_reduce(d_out)  # uint32 sums wrap like int32 sums: same bits
-            # the library works on its own stream: the next step must not start (and zero d_out)
-            # while this all-reduce is still in flight on NCCL's stream
-            torch.cuda.current_stream().synchronize()
-        return st
-
-    def total_updates(st_updates):
+    def sum_over_ranks(x):
         if dist is None:
-            return st_updates
-        t = torch.tensor([st_updates], dtype=torch.int64, device="cuda")
+            return int(x)
+        t = torch.tensor([int(x)], dtype=torch.int64, device="cuda")
         dist.all_reduce(t)
         return int(t.item())
+
+    samples, clusters, skew = db_shape(a, world)
+    if rank == 0:
+        ensure_db(a, samples, clusters, skew)
+    if world > 1:
+        barrier()
+    path, meta = ensure_db(a, samples, clusters, skew)   # (now only reads the side file)
+    N, U_total = int(meta["num_samples"]), int(meta["updates"])
+    cells = kdbx.tri_cells(N)
+    flags = ((kdbx.FLAG_CHUNKED_LISTS if a.chunked_lists else 0) | kdbx.FLAG_ASYNC_UPLOAD |
+             {"auto": 0, "ids": kdbx.FLAG_ID_LISTS, "boundaries": kdbx.FLAG_BOUNDARY_LISTS}[a.list_form])
+    ctx = kdbx.Context(device=local_rank, chunk_ids=a.chunk_ids, tile_cols=a.tile_cols, unit_updates=a.unit_updates,
+                       tile_rows=a.tile_rows, scatter_threads=a.scatter_threads, flags=flags)
+    t_shard = 0.0
+    window = (0, N)
+    if world == 1:
+        trie = kdbx.Trie.read_db(path, pinned=True)
+    else:
+        # rank 0 cuts the database once and writes the parts next to it; every rank reads its own
+        tag = f"{path}.{a.scaling}"
+        part_path = Path(f"{tag}.part{rank}of{world}.db")
+        if rank == 0 and not all(Path(f"{tag}.part{r}of{world}.db.json").exists() for r in range(world)):
+            t0 = time.perf_counter()
+            whole = kdbx.Trie.read_db(path, pinned=False)
+            for r, (part, owned, win) in enumerate(whole.partition_all(world)):
+                pp = Path(f"{tag}.part{r}of{world}.db")
+                part.write_db(pp)
+                tt = part.totals()
+                Path(str(pp) + ".json").write_text(json.dumps({"window": list(win), "owned_updates": owned, "updates": int(tt.updates),
+                                                                "num_patterns": int(tt.num_patterns)}))
+                part.close()
+            whole.close()
+            t_shard = time.perf_counter() - t0
+            print(f"[bench] cut {path.name} into {world} parts in {t_shard:.1f} s", file=sys.stderr)
+        barrier()
+        trie = kdbx.Trie.read_db(part_path, pinned=True)
+        window = tuple(json.loads(Path(str(part_path) + ".json").read_text())["window"])
+        ctx.comm_init_rank(world, rank, _broadcast_bytes(dist, torch, kdbx.Context.comm_unique_id() if rank == 0 else None))
+    tot = trie.totals()
+    P = int(tot.num_patterns)
+
+    def stage():
+        ctx.load_patterns(trie)
+        if world > 1 and not a.no_window:
+            ctx.set_sample_window(*window)
+    stage()
+    block = ctx.block_cells() if world > 1 else cells
+    d_out = torch.zeros(max(1, block), dtype=torch.int32, device="cuda")
+
+    def step():
+        """One all2all over this rank's resident (sub-)trie, the reduce-scatter included; returns the library's stats."""
+        if world == 1:
+            return ctx.all2all_dense_rows_device(0, N, d_out.data_ptr())
+        return ctx.all2all_dense_reduce_scatter_device(d_out.data_ptr())[2]
 
     # ---- device-resident leg -------------------------------------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None   # started now, so that it is settled before the timed steps
@@ -340,19 +418,9 @@ def main():
         st = step()
     U_rank = int(st.updates)
     assert U_rank == int(tot.updates), "updates executed on this rank != U of its (sub-)trie"
-    U_exec = total_updates(U_rank)
+    U_exec = sum_over_ranks(U_rank)
     # sharding replicates only ancestor chains (num_kmers = 0 there, but their rows are still visited)
     assert U_total <= U_exec <= U_total * 1.001, "updates executed by all ranks != U of the database"
-    if full_ref is not None:
-        assert torch.equal(d_out[:cells], full_ref[:cells]), "all-reduced matrix of the sharded run != unsharded matrix"
-        full_ref = None
-    if dist is not None and scaling == "weak":
-        # ranks own disjoint diagonal blocks: this rank's block must hold exactly its own partial result
-        mine = torch.zeros_like(d_out)
-        ctx.all2all_dense_rows_device(r0, r1, mine.data_ptr())
-        lo, hi = kdbx.tri_cells(rank * N0), kdbx.tri_cells((rank + 1) * N0)
-        assert torch.equal(mine[lo:hi], d_out[lo:hi]) and int(mine.to(torch.int64).sum().item()) == int(mine[lo:hi].to(torch.int64).sum().item())
-        del mine
     if sampler:
         sampler.wait_first_sample()
     barrier()
@@ -362,45 +430,76 @@ def main():
     dev_ms = scat_ms = 0.0
     per_step_ms = []
     launches = scat_launches = 0
-    stage = {"prepare": 0.0, "expand": 0.0, "bucket": 0.0, "scatter": 0.0}
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    stage_ms = {"prepare": 0.0, "expand": 0.0, "bucket": 0.0, "scatter": 0.0, "collective": 0.0}
     for i in range(a.steps):
-        ev[i][0].record()
         st = step()
-        ev[i][1].record()
         assert st.updates == U_rank
         dev_ms += st.ms_total
         per_step_ms.append(round(st.ms_total, 3))
         scat_ms += st.ms_scatter
         launches += st.kernel_launches
         scat_launches += st.scatter_launches
-        for k in stage:
-            stage[k] += getattr(st, "ms_" + k)
+        for k in stage_ms:
+            stage_ms[k] += getattr(st, "ms_" + k)
     barrier()
     wall_ms = (time.perf_counter() - wall0) * 1e3
     clocks = sampler.stop() if sampler else None
-    if dist is not None:
-        # with a collective in the step, time the whole step: CUDA events on torch's stream bracket the
-        # (synchronous) library call and the NCCL all-reduce that follows it
-        dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    # every step ends in a collective (N > 1), so the ranks advance in lockstep: the library's device time of a step
+    # (CUDA events on its stream, reduce-scatter included) already contains the wait for the slowest rank
     T_ms = max_over_ranks(dev_ms)
     value = U_total * a.steps / (T_ms / 1e3)
-    checksum = int(d_out[:cells].to(torch.int64).sum().item()) if cells else 0
+    own = _own_cells(rank, block, cells)
+    checksum = sum_over_ranks(int((d_out[:own].to(torch.int64) & 0xFFFFFFFF).sum().item()) if own else 0)
+    physical = sum_over_ranks(int(st.physical_updates))
 
-    # ---- end-to-end leg: host trie -> H2D -> compute (-> all-reduce) -> D2H host matrix ----------
+    # ---- parity: the matrix of the timed configuration against the reference binary's CSV, byte for byte --------
+    parity = None
+    cpu_baseline = None
+    host_full = None
+    if world > 1:
+        blocks = [torch.zeros_like(d_out) for _ in range(world)] if rank == 0 else None   # (a check, untimed)
+        dist.gather(d_out, blocks, dst=0)
+        if rank == 0:
+            host_full = torch.cat(blocks)[:cells].cpu().numpy().view(np.uint32)
+    else:
+        host_full = d_out[:cells].cpu().numpy().view(np.uint32)
+    if rank == 0 and not a.no_cpu_baseline:
+        try:
+            ref_csv = ref_csv_path(path)
+            if world == 1 or (not ref_csv.exists() and U_total < 4e11):
+                secs = run_reference_binary(path, cores)
+                cpu_baseline = {"value": U_total / secs, "unit": "updates/s", "cores": cores, "kind": "reference",
+                                "sample": f"the whole workload once: {N} genomes, U={U_total:.4g}, {secs:.2f} s, kmer-db 2.3.1 all2all -t {cores} "
+                                          f"on the same .db file"}
+            if ref_csv.exists():
+                whole = kdbx.Trie.read_db(path, pinned=False) if world > 1 else trie
+                ours = Path(str(path) + ".gpu.csv")
+                whole.write_all2all_csv(host_full, ours)
+                same = files_identical(ours, ref_csv)
+                parity = {"parity_checked": "cmp of the CSV written from the GPU matrix with the CSV of oracle/_ref/kmer-db all2all on the same .db",
+                          "csv_identical": bool(same), "csv_bytes": os.path.getsize(ours)}
+                ours.unlink(missing_ok=True)
+                if world > 1:
+                    whole.close()
+                assert same, "GPU CSV differs from the reference binary's CSV"
+            else:
+                parity = {"parity_checked": None, "why": "no reference CSV for this database (too large to run the reference here)"}
+        except AssertionError:
+            raise
+        except Exception as e:  # the baseline is a reported number, not a dependency of the GPU path
+            cpu_baseline = {"value": None, "unit": "updates/s", "cores": cores, "kind": "reference", "sample": f"failed: {e}"}
+    host_full = None
+
+    # ---- end-to-end leg: host trie -> H2D -> compute (-> reduce-scatter) -> D2H of every block ------------------
     e2e = None
     if not a.no_e2e:
-        out_host = kdbx.pinned_empty(max(1, cells), np.uint32)
-        out_t = torch.from_numpy(out_host.view(np.int32))
+        out_host = kdbx.pinned_empty(max(1, block), np.uint32)
 
         def e2e_step():
-            ctx.load_patterns(trie)
-            if dist is not None:
-                st2 = step()
-                out_t.copy_(d_out, non_blocking=False)
-            else:
-                _, st2 = ctx.all2all_dense_rows(r0, r1, out_host[:cells])
-            return st2
+            stage()
+            if world == 1:
+                return ctx.all2all_dense_rows(0, N, out_host[:cells])[1]
+            return ctx.all2all_dense_reduce_scatter(out_host)[2]
         e2e_step()
         barrier()
         t0 = time.perf_counter()
@@ -409,62 +508,63 @@ def main():
         torch.cuda.synchronize()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         barrier()
-        assert int(out_host[:cells].astype(np.int64).sum()) == checksum, "e2e result differs from the device-resident result"
-        h2d = total_updates(P * 40 + int(tot.payload_bytes))  # summed over the ranks (every rank copies its own shard)
+        got = sum_over_ranks(int(out_host[:own].astype(np.int64).sum()))
+        assert got == checksum, "e2e result differs from the device-resident result"
+        h2d = sum_over_ranks(P * 40 + int(tot.payload_bytes))  # summed over the ranks (every rank copies its own shard)
         e2e = {"value": U_total * a.steps / e2e_s, "unit": "updates/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": cells * 4 * world, "ms_per_step": 1e3 * e2e_s / a.steps,
+               "d2h_bytes_per_step": cells * 4, "ms_per_step": 1e3 * e2e_s / a.steps,
                "ms_upload": st2.ms_upload, "ms_download": st2.ms_download}
 
     if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     peak, peak_src = measured_hbm_peak()
     achieved = ALGO_BYTES_PER_UPDATE * U_rank * a.steps / (scat_ms / 1e3) / 1e9 if scat_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_scatter_add", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
+    phys_rank = int(st.physical_updates)
+    atomic_rate = phys_rank * a.steps / (scat_ms / 1e3) if scat_ms > 0 else 0.0
+    kernel = "k_scatter_diff" if int(st.list_form) == 1 else "k_scatter_add"
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic_per_launch(kernel), "peak_source": peak_src,
+                "note": "HBM-EQUIVALENT figure (12 B x U / kernel time): the accumulators live in shared memory, so it is not a bound; "
+                        "the kernel's physical bound is smem_atomic",
                 "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE,
                 "updates_per_launch": U_rank / max(1, scat_launches / a.steps),
                 "avg_launch_ms": scat_ms / max(1, scat_launches), "launches_per_step": scat_launches // max(1, a.steps),
-                "kernel_share_of_step": scat_ms / dev_ms if dev_ms else None}
+                "kernel_share_of_step": scat_ms / dev_ms if dev_ms else None,
+                "smem_atomic": {"achieved": atomic_rate, "peak": SMEM_ATOMIC_PEAK, "unit": "red.shared.add.u32 lane-updates/s",
+                                "frac": atomic_rate / SMEM_ATOMIC_PEAK,
+                                "peak_source": "conflict-free microbenchmark, ids in registers (profiles/r01_microbench_atomics.txt)",
+                                "reductions_per_launch": phys_rank / max(1, scat_launches / a.steps),
+                                "note": "lane-updates actually issued (run-boundary lists issue fewer than U: two per run of consecutive ids)"}}
 
-    cpu_baseline = None
-    if world == 1 and not a.no_cpu_baseline:
-        try:
-            sub = trie.prefix(sample_n)
-            sub_path = cache_path(a, sample_n, 1)
-            if not sub_path.exists():
-                sub.write_db(sub_path)
-            U_s = int(sub.totals().updates)
-            secs = run_reference_binary(sub_path, cores)
-            cpu_baseline = {"value": U_s / secs, "unit": "updates/s", "cores": cores, "kind": "reference",
-                            "sample": f"first cluster only: {sample_n} genomes x {a.genome_kmers / 1e6:g} Mbp, "
-                                      f"U={U_s:.4g}, {secs:.2f} s, kmer-db 2.3.1 all2all -t {cores}"}
-        except Exception as e:  # the baseline is a reported number, not a dependency of the GPU path
-            cpu_baseline = {"value": None, "unit": "updates/s", "cores": cores, "kind": "reference", "sample": f"failed: {e}"}
-
-    print(json.dumps({
+    cfg = common_config(a, meta, samples, clusters, skew)
+    cfg.update({
+        "patterns_on_rank0": P,
+        "parallelism": ("1 GPU, no collective" if world == 1 else
+                        f"trie cut into {world} sub-tries by kdbxh_partitioner (preorder pieces + ancestor chains), one per GPU, "
+                        f"sample windows declared, one ncclReduceScatter of the {cells * 4 / 1e6:.0f} MB matrix per step inside libkdbx.so"),
+        "shard_seconds_host": t_shard, "sample_window_rank0": list(window),
+        "l2_policy": "inputs (trie %.1f GB + lists) exceed the 126 MB L2; no explicit flush" % ((P * 40 + int(tot.payload_bytes)) / 1e9),
+        "chunk_ids": a.chunk_ids, "tile_cols": a.tile_cols, "unit_updates": a.unit_updates,
+        "tile_rows": a.tile_rows, "scatter_threads": a.scatter_threads, "list_form_requested": a.list_form})
+    line = {
         "metric": "k-mer-pair updates/sec on all2all", "value": value, "unit": "updates/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": T_ms / a.steps, "higher_is_better": True,
-        "scaling": scaling, "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_name(a) + ("" if world == 1 else
-                               f"; x{world} shards laid side by side = {N} genomes ({a.clusters * world} clusters)" if scaling == "weak"
-                               else f"; cut into {world} sub-tries"),
-                   "num_samples": N, "num_patterns": P if world == 1 else None, "patterns_on_rank0": P, "updates_per_step": U_total,
-                   "sum_n": int(tot.sum_n), "sum_l": int(tot.sum_l),
-                   "parallelism": ("1 GPU, no collective" if world == 1 else
-                                   f"trie sharded into {world} sub-tries (preorder pieces + ancestor chains), one per GPU, "
-                                   f"+ one NCCL all-reduce of the {cells * 4 / 1e6:.0f} MB matrix per step"),
-                   "shard_seconds_host": t_shard,
-                   "l2_policy": "inputs (trie %.1f GB + per-chunk lists) exceed the 126 MB L2; no explicit flush" %
-                                ((P * 40 + int(tot.payload_bytes)) / 1e9),
-                   "chunk_ids": chunk_ids, "tile_cols": a.tile_cols, "unit_updates": a.unit_updates,
-                   "tile_rows": a.tile_rows, "scatter_threads": a.scatter_threads},
+        "scaling": a.scaling, "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": cfg,
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
-        "stage_ms_per_step": {k: v / a.steps for k, v in stage.items()}, "wall_ms_per_step": wall_ms / a.steps,
+        "stage_ms_per_step": {k: v / a.steps for k, v in stage_ms.items()}, "wall_ms_per_step": wall_ms / a.steps,
         "library_ms_per_step": per_step_ms,
         "result_checksum": checksum, "list_form": ["ids", "run boundaries"][int(st.list_form)],
-        "physical_updates_per_step": int(st.physical_updates),
-    }))
+        "physical_updates_per_step": physical,
+    }
+    if parity:
+        line.update(parity)
+    print(json.dumps(line))
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -131,7 +131,7 @@ typedef struct kdbx_stats {
     uint64_t physical_updates; /* shared-memory reductions actually issued: = updates with id lists, fewer with
                                   boundary lists (a run of consecutive ids costs two whatever its length)   */
     uint32_t list_form;      /* 0 = sample-id lists, 1 = run-boundary lists (KDBX_FLAG_BOUNDARY_LISTS)      */
-    uint32_t _pad2;
+    float ms_collective;     /* multi-GPU: the reduce-scatter of the partial matrices                       */
 } kdbx_stats;
 
 /* Library / device management ---------------------------------------------------------- */
@@ -266,6 +266,31 @@ int kdbx_new2all_batch(kdbx_ctx* ctx, const uint64_t* kmers, const uint64_t* q_o
  * 302-327. */
 int kdbx_all2all_dense_part_device(kdbx_ctx* ctx, uint32_t part, uint32_t num_parts, void* d_out_tri,
                                    kdbx_stats* stats);
+
+/* ---- several GPUs of one node -------------------------------------------------------------- */
+
+/* The reference is one process; its template for sharding is the grid of partial databases of all2all-parts
+ * (src/console_all2all_parts.cpp:143-331).  Here the database is cut into sub-tries (kdbxh_partition: the matrix is
+ * linear in num_kmers, so the parts' matrices add up), one context and one GPU per part, and ONE collective —
+ * ncclReduceScatter(uint32, sum) over NVLink — adds the partial matrices and leaves rank r with the cells
+ * [r B, (r+1) B) of the packed triangle, B = ceil(N(N-1)/2 / ranks).  NCCL is bound at run time (libnccl.so.2).
+ *
+ * One process per GPU: rank 0 calls kdbx_comm_unique_id, the launcher hands the 128 bytes to every rank, and every
+ * rank calls kdbx_comm_init_rank (collective: all ranks must call).  One process, several contexts:
+ * kdbx_comm_init_all; the compute calls below must then be issued from one host thread per context. */
+#define KDBX_COMM_ID_BYTES 128
+int kdbx_comm_unique_id(void* id_out);
+int kdbx_comm_init_rank(kdbx_ctx* ctx, int nranks, int rank, const void* id);
+int kdbx_comm_init_all(kdbx_ctx* const* ctxs, int n);
+void kdbx_comm_destroy(kdbx_ctx* ctx);
+
+/* The dense all2all of the sub-trie staged on this context, reduce-scattered over the communicator (a context without
+ * one is a communicator of one rank).  The rank's block of the packed triangle — *num_cells cells starting at cell
+ * *first_cell (src/array.h:140 layout) — goes to d_block (device memory, room for B cells) or out_block (host). */
+int kdbx_all2all_dense_reduce_scatter_device(kdbx_ctx* ctx, void* d_block, uint64_t* first_cell, uint64_t* num_cells,
+                                             kdbx_stats* stats);
+int kdbx_all2all_dense_reduce_scatter(kdbx_ctx* ctx, uint32_t* out_block, uint64_t* first_cell, uint64_t* num_cells,
+                                      kdbx_stats* stats);
 
 /* ---- build: database construction on the device --------------------------------------------- */
 

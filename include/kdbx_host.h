@@ -31,6 +31,7 @@ typedef struct kdbxh_synth_params {
     uint64_t seed;
     int32_t threads;         /* 0 = all host cores */
     int32_t _pad;
+    double cluster_skew;     /* 0: equal clusters; s in (0,1): sizes spread over [1-s, 1+s] x the mean */
 } kdbxh_synth_params;
 
 typedef struct kdbxh_totals {
@@ -73,6 +74,12 @@ int kdbxh_prefix(const kdbxh_trie* src, uint32_t num_samples, kdbxh_trie* dst);
  * sum (uint32, wrapping) to the matrix of src: one GPU per part + one NCCL all-reduce.
  * owned_updates (may be NULL) receives U of the patterns the part owns. */
 int kdbxh_partition(const kdbxh_trie* src, uint32_t num_parts, uint32_t part, kdbxh_trie* dst, uint64_t* owned_updates);
+/* All parts of one cut without repeating the preorder walk: src must outlive the partitioner.  window (may be
+ * NULL) receives the band of sample ids [lo, hi) that the part's lists lie in, for kdbx_set_sample_window. */
+typedef struct kdbxh_partitioner kdbxh_partitioner;
+kdbxh_partitioner* kdbxh_partitioner_new(const kdbxh_trie* src, uint32_t num_parts);
+void kdbxh_partitioner_free(kdbxh_partitioner* p);
+int kdbxh_partitioner_part(const kdbxh_partitioner* p, uint32_t part, kdbxh_trie* dst, uint64_t* owned_updates, uint32_t* window);
 /* Shifts every sample id of t by `offset` inside a sample table of `new_total` entries (the other
  * entries are empty samples); the trie keeps its shape.  Lays shards of a workload side by side. */
 int kdbxh_relabel(kdbxh_trie* t, uint32_t offset, uint32_t new_total);

@@ -228,6 +228,14 @@ k_job_fill_diff(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
 // of shuffles); the flush takes prefix sums along every row before it adds the tile into the packed triangle.
 constexpr uint32_t kDiffBatch = 8;
 
+// tile[..] += v iff y < lim.  Not a predicated reduction: ptxas turns `@p red.shared` (and an `if` around the asm
+// statement alike) into a branch with a convergence barrier, six instructions per guarded reduction; adding 0 instead
+// takes four (compare, select, address, reduction).  Entries that are absent hold this lane's padding column (every
+// accumulator row is followed by kRowPad padding words), so the address is always inside the tile.
+__device__ __forceinline__ void red_shared_add_below(uint32_t saddr, uint32_t v, uint32_t y, uint32_t lim) {
+    red_shared_add(saddr, y < lim ? v : 0u);
+}
+
 template <uint32_t F, uint32_t G>
 __device__ __forceinline__ void last_rows_diff(uint32_t k, uint32_t rows_saddr, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t y0,
                                                uint32_t y1, uint32_t y2, uint32_t wl) {
@@ -238,9 +246,9 @@ __device__ __forceinline__ void last_rows_diff(uint32_t k, uint32_t rows_saddr, 
         if (F > 0) red_shared_add(ro + x0, wl);
         if (F > 1) red_shared_add(ro + x1, wl);
         if (F > 2) red_shared_add(ro + x2, wl);
-        if (G > 0) { if (y0 < lim) red_shared_add(ro + y0, wl); }
-        if (G > 1) { if (y1 < lim) red_shared_add(ro + y1, wl); }
-        if (G > 2) { if (y2 < lim) red_shared_add(ro + y2, wl); }
+        if (G > 0) red_shared_add_below(ro + y0, wl, y0, lim);
+        if (G > 1) red_shared_add_below(ro + y1, wl, y1, lim);
+        if (G > 2) red_shared_add_below(ro + y2, wl, y2, lim);
     }
 }
 
@@ -257,7 +265,8 @@ k_scatter_diff(const Unit* __restrict__ units, const uint32_t* __restrict__ n_un
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_units = *n_units_ptr;
     const uint32_t R = 1u << rb_shift;
-    const uint32_t stride = tile_cols;
+    const uint32_t stride = tile_cols + kRowPad;   // padding words: see red_shared_add_below
+    const uint32_t pad_col = tile_cols + lane;
     const uint32_t tile_saddr = (uint32_t)__cvta_generic_to_shared(tile);
     const uint32_t rows_saddr = (uint32_t)__cvta_generic_to_shared(&s_rows[warp][0]);
     constexpr uint32_t kNone = 0xFFFFFFFFu;
@@ -309,71 +318,110 @@ k_scatter_diff(const Unit* __restrict__ units, const uint32_t* __restrict__ n_un
             const uint32_t cnt = min(kDiffBatch, un.job_end - jb);
             uint4 part = make_uint4(0, 0, 0, 0);  // lane 2q: (off, rows, c0, ext|rows_hi<<8) of job q; lane 2q+1: (k, w, off_hi, -)
             if (lane < 2 * cnt) part = ldg_nc_v4(reinterpret_cast<const uint4*>(jobs + jb) + lane);
-#pragma unroll 1
-            for (uint32_t q = 0; q < cnt; ++q) {
+            // One job of look-ahead: the row ids and the first list entries of job q+1 are requested before job q's
+            // reductions are issued, so a warp does not sit out a DRAM round trip per job (the lists of a bucket's jobs
+            // are scattered over HBM; with 8 warps per scheduler that latency was the largest stall of the id form).
+            struct Pending {
+                const uint32_t* list;
+                uint32_t c0, e, k, w, row;
+                uint32_t v0, v1, v2, v3, v4, v5;   // c0 >= 128: the first 128-entry slice (v0..v3); else the F full groups (v0..v2) and the G guarded ones (v3..v5)
+            };
+            auto request = [&](uint32_t q, Pending& J) {
                 const uint32_t off = __shfl_sync(0xffffffffu, part.x, 2 * q), rows_lo = __shfl_sync(0xffffffffu, part.y, 2 * q);
                 const uint32_t c0 = __shfl_sync(0xffffffffu, part.z, 2 * q), ex = __shfl_sync(0xffffffffu, part.w, 2 * q);
                 const uint32_t k = __shfl_sync(0xffffffffu, part.x, 2 * q + 1), w = __shfl_sync(0xffffffffu, part.y, 2 * q + 1);
                 const uint32_t off_hi = __shfl_sync(0xffffffffu, part.z, 2 * q + 1);
-                const uint32_t* list = bflat + (((uint64_t)off_hi << 32) | off);
-                const uint32_t e = c0 + (ex & 0xFFu);
+                J.list = bflat + (((uint64_t)off_hi << 32) | off);
+                J.c0 = c0; J.e = c0 + (ex & 0xFFu); J.k = k; J.w = w;
+                J.row = 0;
+                if (lane < k) J.row = ldg_nc_u32(loc + (((uint64_t)(ex >> 8) << 32) | rows_lo) + lane);
+                const uint32_t* p = J.list + lane;
+                J.v0 = J.v1 = J.v2 = 0u; J.v3 = J.v4 = J.v5 = pad_col;
+                if (c0 >= 128) {
+                    J.v0 = ldg_nc_u32(p); J.v1 = ldg_nc_u32(p + 32); J.v2 = ldg_nc_u32(p + 64); J.v3 = ldg_nc_u32(p + 96);
+                } else {
+                    const uint32_t full = c0 >> 5, rem = J.e - full * 32;   // rem: 0..93 entries in the guarded groups
+                    if (full > 0) J.v0 = ldg_nc_u32(p);
+                    if (full > 1) J.v1 = ldg_nc_u32(p + 32);
+                    if (full > 2) J.v2 = ldg_nc_u32(p + 64);
+                    const uint32_t* pg = p + full * 32;
+                    if (lane < rem) J.v3 = ldg_nc_u32(pg);
+                    if (lane + 32 < rem) J.v4 = ldg_nc_u32(pg + 32);
+                    if (lane + 64 < rem) J.v5 = ldg_nc_u32(pg + 64);
+                }
+            };
+            // the pass over the rows for up to 3 full groups below c0 (unconditional) and up to 3 groups that reach into
+            // [c0, e) — entries of the job's own rows, taken by row j iff they lie below its id (absent entries hold the
+            // lane's padding column, which is not below any row)
+            auto last_pass = [&](uint32_t k, uint32_t full, uint32_t groups, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t y0, uint32_t y1,
+                                 uint32_t y2, uint32_t wl) {
+                switch (full * 4 + groups) {
+                    case 0: break;
+                    case 1: last_rows_diff<0, 1>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 2: last_rows_diff<0, 2>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 3: last_rows_diff<0, 3>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 4: last_rows_diff<1, 0>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 5: last_rows_diff<1, 1>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 6: last_rows_diff<1, 2>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 7: last_rows_diff<1, 3>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 8: last_rows_diff<2, 0>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 9: last_rows_diff<2, 1>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 10: last_rows_diff<2, 2>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 11: last_rows_diff<2, 3>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 12: last_rows_diff<3, 0>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 13: last_rows_diff<3, 1>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 14: last_rows_diff<3, 2>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                    default: last_rows_diff<3, 3>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                }
+            };
+            Pending cur, nxt;
+            request(0, cur);
+            nxt = cur;
+#pragma unroll 1
+            for (uint32_t q = 0; q < cnt; ++q) {
+                if (q + 1 < cnt) request(q + 1, nxt);
+                const uint32_t k = cur.k, c0 = cur.c0, e = cur.e;
                 __syncwarp();   // the previous job's reads of the row table are done
-                if (lane < k) {
-                    const uint32_t my_row = ldg_nc_u32(loc + (((uint64_t)(ex >> 8) << 32) | rows_lo) + lane);
-                    s_rows[warp][lane] = make_uint2(tile_saddr + (my_row - row0) * stride * 4u, my_row * 4u);
-                }
+                if (lane < k) s_rows[warp][lane] = make_uint2(tile_saddr + (cur.row - row0) * stride * 4u, cur.row * 4u);
                 __syncwarp();
-                const uint32_t wl = (lane & 1u) ? 0u - w : w;   // slices start at even positions: the lane's parity is the entry's
-                // whole 128-entry slices of the boundaries every row receives ...
-                uint32_t c = 0;
-                for (; c + 128 <= c0; c += 128) {
-                    const uint32_t* p = list + c + lane;
-                    const uint32_t x0 = ldg_nc_u32(p) * 4u, x1 = ldg_nc_u32(p + 32) * 4u;
-                    const uint32_t x2 = ldg_nc_u32(p + 64) * 4u, x3 = ldg_nc_u32(p + 96) * 4u;
-                    for (uint32_t j = 0; j < k; ++j) {
-                        uint32_t ro;
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ro) : "r"(rows_saddr + j * 8u));
-                        red_shared_add(ro + x0, wl); red_shared_add(ro + x1, wl);
-                        red_shared_add(ro + x2, wl); red_shared_add(ro + x3, wl);
+                const uint32_t wl = (lane & 1u) ? 0u - cur.w : cur.w;   // slices start at even positions: the lane's parity is the entry's
+                if (c0 < 128) {
+                    const uint32_t full = c0 >> 5;
+                    last_pass(k, full, (e - full * 32 + 31u) >> 5, cur.v0 * 4u, cur.v1 * 4u, cur.v2 * 4u, cur.v3 * 4u, cur.v4 * 4u, cur.v5 * 4u, wl);
+                } else {
+                    // whole 128-entry slices of the boundaries every row receives (the first one is already here) ...
+                    const uint32_t* list = cur.list;
+                    uint32_t x0 = cur.v0 * 4u, x1 = cur.v1 * 4u, x2 = cur.v2 * 4u, x3 = cur.v3 * 4u;
+                    uint32_t c = 0;
+                    for (;;) {
+                        for (uint32_t j = 0; j < k; ++j) {
+                            uint32_t ro;
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ro) : "r"(rows_saddr + j * 8u));
+                            red_shared_add(ro + x0, wl); red_shared_add(ro + x1, wl);
+                            red_shared_add(ro + x2, wl); red_shared_add(ro + x3, wl);
+                        }
+                        c += 128;
+                        if (c + 128 > c0) break;
+                        const uint32_t* p = list + c + lane;
+                        x0 = ldg_nc_u32(p) * 4u; x1 = ldg_nc_u32(p + 32) * 4u; x2 = ldg_nc_u32(p + 64) * 4u; x3 = ldg_nc_u32(p + 96) * 4u;
                     }
-                }
-                // ... then one pass over the rows for the rest: F complete 32-entry groups below c0 (unconditional)
-                // and G groups that reach into [c0, e) — entries of the job's own rows, taken by row j iff they lie
-                // below its id.  Entries past e compare as "not below" (all ones).
-                {
+                    // ... then the rest
                     const uint32_t full = (c0 - c) >> 5;                 // 0..3
-                    const uint32_t cg = c + full * 32;                   // first entry of the predicated groups
+                    const uint32_t cg = c + full * 32;                   // first entry of the guarded groups
                     const uint32_t rem = e - cg;                          // 0..93
                     const uint32_t* p = list + c + lane;
-                    uint32_t x0 = 0, x1 = 0, x2 = 0;
+                    x0 = x1 = x2 = 0;
                     if (full > 0) x0 = ldg_nc_u32(p) * 4u;
                     if (full > 1) x1 = ldg_nc_u32(p + 32) * 4u;
                     if (full > 2) x2 = ldg_nc_u32(p + 64) * 4u;
                     const uint32_t* pg = list + cg + lane;
-                    uint32_t y0 = 0xFFFFFFFFu, y1 = 0xFFFFFFFFu, y2 = 0xFFFFFFFFu;
+                    uint32_t y0 = pad_col * 4u, y1 = pad_col * 4u, y2 = pad_col * 4u;
                     if (lane < rem) y0 = ldg_nc_u32(pg) * 4u;
                     if (lane + 32 < rem) y1 = ldg_nc_u32(pg + 32) * 4u;
                     if (lane + 64 < rem) y2 = ldg_nc_u32(pg + 64) * 4u;
-                    const uint32_t groups = (rem + 31u) >> 5;            // 0..3
-                    switch (full * 4 + groups) {
-                        case 0: break;
-                        case 1: last_rows_diff<0, 1>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                        case 2: last_rows_diff<0, 2>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                        case 3: last_rows_diff<0, 3>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                        case 4: last_rows_diff<1, 0>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                        case 5: last_rows_diff<1, 1>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                        case 6: last_rows_diff<1, 2>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                        case 7: last_rows_diff<1, 3>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                        case 8: last_rows_diff<2, 0>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                        case 9: last_rows_diff<2, 1>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                        case 10: last_rows_diff<2, 2>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                        case 11: last_rows_diff<2, 3>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                        case 12: last_rows_diff<3, 0>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                        case 13: last_rows_diff<3, 1>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                        case 14: last_rows_diff<3, 2>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                        default: last_rows_diff<3, 3>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                    }
+                    last_pass(k, full, (rem + 31u) >> 5, x0, x1, x2, y0, y1, y2, wl);
                 }
+                cur = nxt;
             }
         }
         __syncthreads();

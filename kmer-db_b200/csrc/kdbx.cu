@@ -799,11 +799,31 @@ k_job_fill(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint6
                    });
 }
 
-// units per key = ceil(work / unit_updates) (>= 1 when the bucket is non-empty)
+// work[nkeys] = total work of the pass (one block)
+__global__ void k_work_total(uint32_t nkeys, unsigned long long* __restrict__ work) {
+    __shared__ unsigned long long s_part[32];
+    unsigned long long sum = 0;
+    for (uint32_t k = threadIdx.x; k < nkeys; k += blockDim.x) sum += work[k];
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) t += s_part[w];
+        work[nkeys] = t;
+    }
+}
+
+// units per key = ceil(work / unit) (>= 1 when the bucket is non-empty).  unit = unit_updates, or — when the plan
+// leaves it to the library (target_units > 0) — the larger of that and total work / target_units: a CTA of the
+// scatter kernel meets a barrier and re-reads its schedule once per unit, so a pass is cut into a few units per
+// CTA (enough to balance the tail) rather than into units of a fixed size.
 __global__ void k_unit_count(uint32_t nkeys, const uint32_t* __restrict__ hist, const unsigned long long* __restrict__ work,
-                             uint32_t unit_updates, uint32_t* __restrict__ ucount) {
+                             uint32_t unit_updates_min, uint32_t target_units, uint32_t* __restrict__ ucount) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > nkeys) return;
+    unsigned long long unit_updates = unit_updates_min;
+    if (target_units) unit_updates = max(unit_updates, work[nkeys] / target_units);
     uint32_t c = 0;
     if (k < nkeys && hist[k]) {
         const unsigned long long u = (work[k] + unit_updates - 1) / unit_updates;
@@ -855,21 +875,24 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const uint4* p) {
     return v;
 }
 
+constexpr uint32_t kUnitsPerCta = 12;  // work units per CTA of a scatter pass when the plan does not fix their size (k_unit_count)
 constexpr uint32_t kJobBatch = 8;  // jobs a warp claims at once (16 lanes load them as uint4 halves)
 
 // Last pass of a job over its k rows (see k_scatter_add): F complete 32-id groups (x0..x2), the partial
 // group xt under `tail`, and the triangular part (lanes below j hold the ids of the rows before row j).
 template <uint32_t F>
 __device__ __forceinline__ void last_rows(uint32_t k, uint32_t rowoff, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t xt, bool tail,
-                                          bool tv, uint32_t my_id4, uint32_t lane, uint32_t w) {
+                                          bool has_tail, uint32_t wt, uint32_t my_id4, uint32_t lane, uint32_t w) {
 #pragma unroll 2
     for (uint32_t j = 0; j < k; ++j) {
         const uint32_t ro = __shfl_sync(0xffffffffu, rowoff, j);
         if (F > 0) red_shared_add(ro + x0, w);
         if (F > 1) red_shared_add(ro + x1, w);
         if (F > 2) red_shared_add(ro + x2, w);
-        if (tail) red_shared_add(ro + xt, w);
-        if (tv && lane < j) red_shared_add(ro + my_id4, w);
+        // (adding 0 instead of skipping: ptxas compiles a guarded shared-memory reduction into a branch with a
+        //  convergence barrier, six instructions where these take three or four; idle lanes hold their padding word)
+        if (has_tail) red_shared_add(ro + xt, tail ? w : 0u);
+        red_shared_add(ro + my_id4, lane < j ? wt : 0u);
     }
 }
 constexpr uint32_t kRowPad = 32;   // padding words after every accumulator row (see k_scatter_add)
@@ -983,11 +1006,14 @@ k_scatter_add(const Unit* __restrict__ units, const uint32_t* __restrict__ n_uni
                     if (lane + 64 < rem) x2 = ldg_nc_u32(p + 64) * 4u;
                     if (lane + 96 < rem) x3 = ldg_nc_u32(p + 96) * 4u;
                     const bool tv = lane < k && A0 + lane >= a && A0 + lane < b;
+                    const uint32_t wt = tv ? w : 0u;              // weight of this lane's row id as a column of later rows
+                    const uint32_t tcol = tv ? my_id4 : pad4;     // (lanes without one add 0 to their padding word)
+                    const bool has_tail = (rem & 31u) != 0;
                     switch (full) {
-                        case 0: last_rows<0>(k, rowoff, x0, x1, x2, x0, tail, tv, my_id4, lane, w); break;
-                        case 1: last_rows<1>(k, rowoff, x0, x1, x2, x1, tail, tv, my_id4, lane, w); break;
-                        case 2: last_rows<2>(k, rowoff, x0, x1, x2, x2, tail, tv, my_id4, lane, w); break;
-                        default: last_rows<3>(k, rowoff, x0, x1, x2, x3, tail, tv, my_id4, lane, w); break;
+                        case 0: last_rows<0>(k, rowoff, x0, x1, x2, x0, tail, has_tail, wt, tcol, lane, w); break;
+                        case 1: last_rows<1>(k, rowoff, x0, x1, x2, x1, tail, has_tail, wt, tcol, lane, w); break;
+                        case 2: last_rows<2>(k, rowoff, x0, x1, x2, x2, tail, has_tail, wt, tcol, lane, w); break;
+                        default: last_rows<3>(k, rowoff, x0, x1, x2, x3, tail, has_tail, wt, tcol, lane, w); break;
                     }
                 }
             }
@@ -1076,6 +1102,10 @@ struct kdbx_ctx {
     } meta;
     // boundary lists (diff.cuh)
     DevBuf ownb, nb, boff;
+    // multi-GPU (comm.cuh): the NCCL communicator this context is a rank of, and its block of the result
+    void* comm = nullptr;
+    int comm_nranks = 1, comm_rank = 0;
+    DevBuf rs_block;
     uint64_t* h_pinned = nullptr;          // small pinned read-back area
 
     // sparse delivery (sparse.cuh)
@@ -1581,7 +1611,7 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         ev_expand_b = ctx->event();
     }
     unsigned scatter_grid = M.scatter_grid;
-    const size_t smem = diff ? pl.smem_diff : pl.smem;
+    const size_t smem = pl.smem;   // both forms pad every accumulator row with kRowPad words
     if (!cached || M.diff != diff) {
         int blocks_per_sm = 0;
         if (diff) {
@@ -1683,8 +1713,10 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
             launches += 4;
         }
         ++pass;
+        k_work_total<<<1, 256, 0, st>>>(nkeys, ctx->work.as<unsigned long long>());
         k_unit_count<<<blocks_for((uint64_t)nkeys + 1, 256), 256, 0, st>>>(nkeys, ctx->hist.as<uint32_t>(), ctx->work.as<unsigned long long>(),
-                                                                            pl.unit_updates, ctx->ucount.as<uint32_t>());
+                                                                            pl.unit_updates, ctx->cfg.unit_updates ? 0u : (uint32_t)ctx->sm_count * kUnitsPerCta,
+                                                                            ctx->ucount.as<uint32_t>());
         if (int rc = scan_exclusive_u32(ctx, ctx->ucount.as<uint32_t>(), ctx->uoff.as<uint32_t>(), (uint64_t)nkeys + 1)) return rc;
         k_unit_fill<<<blocks_for(nkeys, 256), 256, 0, st>>>(nkeys, ctx->hist.as<uint32_t>(), ctx->bucket_off.as<uint32_t>(),
                                                              ctx->ucount.as<uint32_t>(), ctx->uoff.as<uint32_t>(), ctx->units.as<Unit>());
@@ -1699,7 +1731,7 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
                                                                   ctx->flat.as<uint32_t>(), resident ? ctx->noff.as<uint64_t>() + p0 : nullptr, d_out, tri_base, pl.lo,
                                                                   pl.T, pl.tile_cols, pl.rb_shift, d_unit_counter);
         e.d = ctx->event();
-        launches += 4;
+        launches += 5;
         s.scatter_launches += 1;
         cev.push_back(e);
     }
@@ -1740,6 +1772,7 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
 }
 
 #include "sparse.cuh"
+#include "comm.cuh"
 #include "query.cuh"
 #include "build.cuh"
 
@@ -1844,8 +1877,9 @@ void kdbx_close(kdbx_ctx* ctx) {
                       &ctx->ucount, &ctx->uoff, &ctx->units, &ctx->counters, &ctx->blockhist, &ctx->tri, &ctx->rowupd, &ctx->first_id,
                       &ctx->sp_cnt, &ctx->sp_counts, &ctx->sp_rowptr, &ctx->sp_col, &ctx->sp_val, &ctx->slot_off, &ctx->slots,
                       &ctx->q_off, &ctx->q_kmers, &ctx->q_keys, &ctx->q_keys2, &ctx->q_runkeys, &ctx->q_runcnt, &ctx->q_out,
-                      &ctx->qx_alpha, &ctx->qx_seq, &ctx->qx_raw, &ctx->qx_sorted, &ctx->qx_count, &ctx->ownb, &ctx->nb, &ctx->boff})
+                      &ctx->qx_alpha, &ctx->qx_seq, &ctx->qx_raw, &ctx->qx_sorted, &ctx->qx_count, &ctx->ownb, &ctx->nb, &ctx->boff, &ctx->rs_block})
         b->release();
+    if (ctx->comm) { nccl_api()->CommDestroy(static_cast<ncclComm_t>(ctx->comm)); ctx->comm = nullptr; }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->g_push.exec) cudaGraphExecDestroy(ctx->g_push.exec);
@@ -1958,6 +1992,85 @@ int kdbx_all2all_dense_rows(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end,
 int kdbx_all2all_dense(kdbx_ctx* ctx, uint32_t* out_tri, kdbx_stats* stats) {
     if (!ctx) return KDBX_ERR_ARG;
     return kdbx_all2all_dense_rows(ctx, 0, ctx->N, out_tri, stats);
+}
+
+int kdbx_comm_unique_id(void* id) {
+    if (!id) return KDBX_ERR_ARG;
+    NcclApi* api = nccl_api();
+    if (!api->error.empty()) { g_open_error = api->error; return KDBX_ERR_STATE; }
+    ncclUniqueId u;
+    const ncclResult_t r = api->GetUniqueId(&u);
+    if (r != ncclSuccess) { g_open_error = std::string("ncclGetUniqueId failed: ") + api->GetErrorString(r); return KDBX_ERR_CUDA; }
+    std::memcpy(id, &u, KDBX_COMM_ID_BYTES);
+    return KDBX_OK;
+}
+
+int kdbx_comm_init_rank(kdbx_ctx* ctx, int nranks, int rank, const void* id) {
+    if (!ctx) return KDBX_ERR_ARG;
+    if (!id || nranks < 1 || rank < 0 || rank >= nranks) return ctx->fail(KDBX_ERR_ARG, "kdbx_comm_init_rank: bad rank %d of %d", rank, nranks);
+    NcclApi* api = nccl_api();
+    if (!api->error.empty()) return ctx->fail(KDBX_ERR_STATE, "%s", api->error.c_str());
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->comm) { api->CommDestroy(static_cast<ncclComm_t>(ctx->comm)); ctx->comm = nullptr; }
+    ncclUniqueId u;
+    std::memcpy(&u, id, KDBX_COMM_ID_BYTES);
+    ncclComm_t c = nullptr;
+    NCK(api->CommInitRank(&c, nranks, u, rank));
+    ctx->comm = c; ctx->comm_nranks = nranks; ctx->comm_rank = rank;
+    return KDBX_OK;
+}
+
+int kdbx_comm_init_all(kdbx_ctx* const* ctxs, int n) {
+    if (!ctxs || n < 1) return KDBX_ERR_ARG;
+    kdbx_ctx* ctx = ctxs[0];
+    if (!ctx) return KDBX_ERR_ARG;
+    NcclApi* api = nccl_api();
+    if (!api->error.empty()) return ctx->fail(KDBX_ERR_STATE, "%s", api->error.c_str());
+    std::vector<int> devs((size_t)n);
+    std::vector<ncclComm_t> comms((size_t)n, nullptr);
+    for (int i = 0; i < n; ++i) {
+        if (!ctxs[i]) return ctx->fail(KDBX_ERR_ARG, "kdbx_comm_init_all: context %d is NULL", i);
+        devs[(size_t)i] = ctxs[i]->device;
+        if (ctxs[i]->comm) { api->CommDestroy(static_cast<ncclComm_t>(ctxs[i]->comm)); ctxs[i]->comm = nullptr; }
+    }
+    NCK(api->CommInitAll(comms.data(), n, devs.data()));
+    for (int i = 0; i < n; ++i) { ctxs[i]->comm = comms[(size_t)i]; ctxs[i]->comm_nranks = n; ctxs[i]->comm_rank = i; }
+    return KDBX_OK;
+}
+
+void kdbx_comm_destroy(kdbx_ctx* ctx) {
+    if (!ctx || !ctx->comm) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    nccl_api()->CommDestroy(static_cast<ncclComm_t>(ctx->comm));
+    ctx->comm = nullptr; ctx->comm_nranks = 1; ctx->comm_rank = 0;
+}
+
+int kdbx_all2all_dense_reduce_scatter_device(kdbx_ctx* ctx, void* d_block, uint64_t* first_cell, uint64_t* num_cells, kdbx_stats* stats) {
+    if (!ctx) return KDBX_ERR_ARG;
+    return all2all_reduce_scatter_device(ctx, static_cast<uint32_t*>(d_block), first_cell, num_cells, stats);
+}
+
+int kdbx_all2all_dense_reduce_scatter(kdbx_ctx* ctx, uint32_t* out_block, uint64_t* first_cell, uint64_t* num_cells, kdbx_stats* stats) {
+    if (!ctx) return KDBX_ERR_ARG;
+    if (!ctx->loaded) return ctx->fail(KDBX_ERR_STATE, "no patterns loaded (call kdbx_load_patterns first)");
+    const uint64_t N = ctx->N, cells = N ? N * (N - 1) / 2 : 0;
+    const uint64_t B = comm_block_cells(cells, ctx->comm ? ctx->comm_nranks : 1);
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->rs_block.ensure((B + 4) * 4));
+    kdbx_stats s{};
+    uint64_t first = 0, count = 0;
+    if (int rc = all2all_reduce_scatter_device(ctx, ctx->rs_block.as<uint32_t>(), &first, &count, &s)) return rc;
+    if (count && !out_block) return ctx->fail(KDBX_ERR_ARG, "output pointer is NULL");
+    cudaEvent_t a = ctx->event();
+    if (count) CK(cudaMemcpyAsync(out_block, ctx->rs_block.p, count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEvent_t b = ctx->event();
+    CK(cudaStreamSynchronize(ctx->stream));
+    s.ms_download = elapsed(a, b);
+    if (first_cell) *first_cell = first;
+    if (num_cells) *num_cells = count;
+    if (stats) *stats = s;
+    return KDBX_OK;
 }
 
 int kdbx_row_updates(kdbx_ctx* ctx, uint64_t* out) {

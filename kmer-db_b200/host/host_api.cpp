@@ -185,7 +185,7 @@ int kdbxh_synth(kdbxh_trie* t, const kdbxh_synth_params* p) {
         kdbx::SynthParams sp;
         sp.num_samples = p->num_samples; sp.num_clusters = p->num_clusters;
         sp.genome_kmers = p->genome_kmers; sp.k = p->k; sp.mutation_rate = p->mutation_rate;
-        sp.seed = p->seed; sp.interleaved = p->interleaved; sp.threads = p->threads;
+        sp.seed = p->seed; sp.interleaved = p->interleaved; sp.threads = p->threads; sp.cluster_skew = p->cluster_skew;
         kdbx::synth_generate(sp, t->t);
     });
 }
@@ -200,6 +200,18 @@ int kdbxh_prefix(const kdbxh_trie* src, uint32_t num_samples, kdbxh_trie* dst) {
 int kdbxh_partition(const kdbxh_trie* src, uint32_t num_parts, uint32_t part, kdbxh_trie* dst, uint64_t* owned_updates) {
     if (!src || !dst || src == dst) { g_err = "bad argument"; return -1; }
     return guarded([&] { dst->flat_off.clear(); dst->flat_slots.clear(); kdbx::partition_trie(src->t, num_parts, part, dst->t, owned_updates); });
+}
+struct kdbxh_partitioner { kdbx::TriePartitioner p; kdbxh_partitioner(const kdbx::Trie& t, uint32_t n) : p(t, n) {} };
+kdbxh_partitioner* kdbxh_partitioner_new(const kdbxh_trie* src, uint32_t num_parts) {
+    if (!src) { g_err = "null argument"; return nullptr; }
+    kdbxh_partitioner* out = nullptr;
+    guarded([&] { out = new kdbxh_partitioner(src->t, num_parts); });
+    return out;
+}
+void kdbxh_partitioner_free(kdbxh_partitioner* p) { delete p; }
+int kdbxh_partitioner_part(const kdbxh_partitioner* p, uint32_t part, kdbxh_trie* dst, uint64_t* owned_updates, uint32_t* window) {
+    if (!p || !dst) { g_err = "null argument"; return -1; }
+    return guarded([&] { dst->flat_off.clear(); dst->flat_slots.clear(); p->p.extract(part, dst->t, owned_updates, window); });
 }
 int kdbxh_relabel(kdbxh_trie* t, uint32_t offset, uint32_t new_total) {
     if (!t) { g_err = "null argument"; return -1; }

@@ -19,6 +19,7 @@
 #include <cstring>
 #include <numeric>
 
+#include "gamma.h"
 #include "trie.h"
 
 namespace kdbx {
@@ -65,30 +66,32 @@ std::vector<uint32_t> trie_preorder(const Trie& t) {
     return order;
 }
 
-// dst := part `part` of `num_parts` (see the header of this file).  The parts' all2all matrices sum
-// to the all2all matrix of src.  owned_updates (optional) receives U of the owned patterns.
-void partition_trie(const Trie& src, uint32_t num_parts, uint32_t part, Trie& dst, uint64_t* owned_updates) {
-    if (num_parts == 0 || part >= num_parts) throw std::runtime_error("partition: bad part index");
+// Cuts of the preorder at equal shares of the cost: part g owns pre[cut[g] .. cut[g+1]).
+TriePartitioner::TriePartitioner(const Trie& src, uint32_t num_parts) : src_(src), num_parts_(num_parts) {
+    if (num_parts == 0) throw std::runtime_error("partition: bad number of parts");
     const uint64_t P = src.num_patterns();
-    const std::vector<uint32_t> pre = trie_preorder(src);
-    // cut the preorder at equal shares of the cost
+    pre_ = trie_preorder(src);
     long double total = 0;
     for (uint64_t p = 0; p < P; ++p) total += (long double)pattern_cost(src.n[p], src.l[p]);
-    uint64_t a = 0, b = P;
-    {
-        const long double lo = total * part / num_parts, hi = total * (part + 1) / num_parts;
-        long double run = 0;
-        bool have_a = false;
-        a = P;
-        for (uint64_t i = 0; i < P; ++i) {
-            if (!have_a && run >= lo) { a = i; have_a = true; }
-            if (run >= hi) { b = i; break; }
-            run += (long double)pattern_cost(src.n[pre[i]], src.l[pre[i]]);
-        }
-        if (part == 0) a = 0;
-        if (part + 1 == num_parts) b = P;
-        if (a > b) a = b;
+    cut_.assign((size_t)num_parts + 1, P);
+    cut_[0] = 0;
+    long double run = 0;
+    uint32_t g = 1;
+    for (uint64_t i = 0; i < P && g < num_parts; ++i) {
+        while (g < num_parts && run >= total * g / num_parts) cut_[g++] = i;
+        run += (long double)pattern_cost(src.n[pre_[i]], src.l[pre_[i]]);
     }
+}
+
+// dst := part `part` (see the header of this file).  The parts' all2all matrices sum to the all2all matrix
+// of src.  owned_updates (optional) receives U of the owned patterns; window (optional) the band of sample ids
+// [lo, hi) the part's lists lie in (what kdbx_set_sample_window wants to hear).
+void TriePartitioner::extract(uint32_t part, Trie& dst, uint64_t* owned_updates, uint32_t* window) const {
+    if (part >= num_parts_) throw std::runtime_error("partition: bad part index");
+    const Trie& src = src_;
+    const uint64_t P = src.num_patterns();
+    const std::vector<uint32_t>& pre = pre_;
+    const uint64_t a = cut_[part], b = std::max(cut_[part], cut_[(size_t)part + 1]);
     // nodes of the part: the ancestor chain of pre[a] (root first), then the owned piece
     std::vector<uint32_t> nodes;
     if (a < b) {
@@ -110,6 +113,8 @@ void partition_trie(const Trie& src, uint32_t num_parts, uint32_t part, Trie& ds
     dst.num_kmers.resize(Q); dst.parent_id.resize(Q); dst.n.resize(Q); dst.l.resize(Q);
     dst.last.resize(Q); dst.bits.resize(Q); dst.payload_off.resize(Q);
     uint64_t words = 0, U = 0;
+    uint32_t lo = 0xFFFFFFFFu, hi = 0;
+    std::vector<uint32_t> ids;
     size_t o = 0;
     if (add_sentinel) {
         dst.num_kmers[0] = 0; dst.parent_id[0] = -1; dst.n[0] = 0; dst.l[0] = 0; dst.last[0] = 0; dst.bits[0] = 0;
@@ -126,6 +131,14 @@ void partition_trie(const Trie& src, uint32_t num_parts, uint32_t part, Trie& ds
         dst.payload_off[o] = words;
         words += Trie::payload_words_for_bits(src.bits[p]);
         if (owned) { const uint64_t nn = src.n[p], ll = src.l[p]; U += ll * (2 * nn - ll - 1) / 2; }
+        if (src.l[p]) {
+            hi = std::max(hi, src.last[p] + 1);
+            if (q < 0) {   // a root's first id is the smallest id of every list below it
+                ids.resize(src.l[p]);
+                decode_local_ids(src.payload.data() + src.payload_off[p], src.l[p], src.last[p], ids.data());
+                lo = std::min(lo, ids[0]);
+            }
+        }
     }
     dst.payload.resize(words, 0);
     o = add_sentinel ? 1 : 0;
@@ -135,6 +148,12 @@ void partition_trie(const Trie& src, uint32_t num_parts, uint32_t part, Trie& ds
         if (w) std::memcpy(dst.payload.data() + dst.payload_off[o], src.payload.data() + src.payload_off[p], w * 8);
     }
     if (owned_updates) *owned_updates = U;
+    if (window) { window[0] = hi ? lo : 0; window[1] = hi; }
+}
+
+void partition_trie(const Trie& src, uint32_t num_parts, uint32_t part, Trie& dst, uint64_t* owned_updates) {
+    if (num_parts == 0 || part >= num_parts) throw std::runtime_error("partition: bad part index");
+    TriePartitioner(src, num_parts).extract(part, dst, owned_updates, nullptr);
 }
 
 // Moves every sample of the database `offset` places up inside a table of `new_total` samples

@@ -315,8 +315,24 @@ void synth_generate(const SynthParams& sp_in, Trie& t) {
     // sample -> cluster assignment
     std::vector<uint32_t> cluster_of(N);
     std::vector<std::vector<uint32_t>> members(C);
-    for (uint32_t s = 0; s < N; ++s) {
-        const uint32_t c = sp.interleaved ? (s % C) : (uint32_t)(((uint64_t)s * C) / N);
+    std::vector<uint32_t> first_of(C + 1, N);   // contiguous order: cluster c holds the samples [first_of[c], first_of[c+1])
+    {
+        // unequal clusters: weight 1 + skew * u_c with u_c in [-1, 1) fixed by the cluster index; at least one sample each
+        std::vector<double> cum(C + 1, 0.0);
+        for (uint32_t c = 0; c < C; ++c) {
+            const double u = (double)((c * 2654435761u) % 1000u) / 500.0 - 1.0;
+            cum[c + 1] = cum[c] + 1.0 + (sp.cluster_skew > 0.0 && sp.cluster_skew < 1.0 ? sp.cluster_skew * u : 0.0);
+        }
+        first_of[0] = 0;
+        for (uint32_t c = 1; c < C; ++c) {
+            uint32_t b = sp.cluster_skew > 0.0 && sp.cluster_skew < 1.0 ? (uint32_t)(cum[c] / cum[C] * N + 0.5) : (uint32_t)(((uint64_t)c * N + C - 1) / C);
+            b = std::max(b, first_of[c - 1] + 1);
+            first_of[c] = std::min(b, N - (C - c));
+        }
+    }
+    for (uint32_t s = 0, cc = 0; s < N; ++s) {
+        while (!sp.interleaved && s >= first_of[cc + 1]) ++cc;
+        const uint32_t c = sp.interleaved ? (s % C) : cc;
         cluster_of[s] = c; members[c].push_back(s);
     }
     std::vector<ClusterSim> sims(C);

@@ -13,6 +13,7 @@ struct SynthParams {
     uint64_t seed = 2;
     int interleaved = 0;              // 0: clusters contiguous in sample order; 1: round-robin
     int threads = 0;                  // 0 = hardware concurrency (one cluster per thread)
+    double cluster_skew = 0.0;        // 0: equal clusters; s in (0,1): cluster sizes spread over [1-s, 1+s] x the mean (contiguous order only)
 };
 
 void synth_generate(const SynthParams& sp, Trie& out);

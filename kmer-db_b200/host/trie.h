@@ -216,6 +216,19 @@ void write_db(const std::string& path, const Trie& t);
 // parts' all2all matrices add up to the whole database's.
 std::vector<uint32_t> trie_preorder(const Trie& t);
 void partition_trie(const Trie& src, uint32_t num_parts, uint32_t part, Trie& dst, uint64_t* owned_updates = nullptr);
+// the same for all parts of one cut: the preorder and the cut points are computed once
+class TriePartitioner {
+public:
+    TriePartitioner(const Trie& src, uint32_t num_parts);
+    // window (optional): [lo, hi) band of sample ids the part's lists lie in
+    void extract(uint32_t part, Trie& dst, uint64_t* owned_updates = nullptr, uint32_t* window = nullptr) const;
+    uint32_t num_parts() const { return num_parts_; }
+private:
+    const Trie& src_;
+    uint32_t num_parts_;
+    std::vector<uint32_t> pre_;
+    std::vector<uint64_t> cut_;
+};
 // shifts all sample ids by `offset` inside a sample table of `new_total` entries
 void relabel_samples(Trie& t, uint32_t offset, uint32_t new_total);
 

@@ -45,7 +45,7 @@ class Stats(C.Structure):
                 ("ms_scatter", C.c_float), ("ms_total", C.c_float), ("ms_download", C.c_float),
                 ("scatter_launches", C.c_uint32), ("_pad", C.c_uint32), ("probes", C.c_uint64), ("hits", C.c_uint64),
                 ("ms_probe", C.c_float), ("ms_compact", C.c_float), ("physical_updates", C.c_uint64),
-                ("list_form", C.c_uint32), ("_pad2", C.c_uint32)]
+                ("list_form", C.c_uint32), ("ms_collective", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k not in ("_pad", "_pad2", "reserved")}
@@ -97,7 +97,7 @@ FLAG_BOUNDARY_LISTS = 8
 class SynthParams(C.Structure):
     _fields_ = [("num_samples", C.c_uint32), ("num_clusters", C.c_uint32), ("genome_kmers", C.c_uint64),
                 ("k", C.c_uint32), ("interleaved", C.c_int32), ("mutation_rate", C.c_double), ("seed", C.c_uint64),
-                ("threads", C.c_int32), ("_pad", C.c_int32)]
+                ("threads", C.c_int32), ("_pad", C.c_int32), ("cluster_skew", C.c_double)]
 
 
 class Totals(C.Structure):
@@ -110,11 +110,13 @@ class Totals(C.Structure):
 KDBX_SYMBOLS = ["kdbx_abi_version", "kdbx_device_count", "kdbx_open", "kdbx_close", "kdbx_last_error",
                 "kdbx_host_alloc", "kdbx_host_free", "kdbx_load_patterns", "kdbx_set_sample_window", "kdbx_row_updates", "kdbx_all2all_dense",
                 "kdbx_all2all_dense_rows", "kdbx_all2all_dense_rows_device", "kdbx_all2all_dense_part_device", "kdbx_all2all_sparse", "kdbx_free_csr",
-                "kdbx_load_hashtables", "kdbx_new2all_batch", "kdbx_debug_fetch",
+                "kdbx_load_hashtables", "kdbx_new2all_batch", "kdbx_debug_fetch", "kdbx_comm_unique_id", "kdbx_comm_init_rank",
+                "kdbx_comm_init_all", "kdbx_comm_destroy", "kdbx_all2all_dense_reduce_scatter_device", "kdbx_all2all_dense_reduce_scatter",
                 "kdbx_builder_open", "kdbx_builder_close", "kdbx_builder_adopt", "kdbx_builder_add_sequence", "kdbx_builder_add_kmers",
                 "kdbx_builder_finish", "kdbx_builder_export", "kdbx_new2all_sequences"]
 KDBXH_SYMBOLS = ["kdbxh_last_error", "kdbxh_trie_new", "kdbxh_trie_free", "kdbxh_read_db", "kdbxh_write_db",
-                 "kdbxh_synth", "kdbxh_validate", "kdbxh_prefix", "kdbxh_partition", "kdbxh_relabel", "kdbxh_view", "kdbxh_totals_of", "kdbxh_sample_name",
+                 "kdbxh_synth", "kdbxh_validate", "kdbxh_prefix", "kdbxh_partition", "kdbxh_partitioner_new", "kdbxh_partitioner_free",
+                 "kdbxh_partitioner_part", "kdbxh_relabel", "kdbxh_view", "kdbxh_totals_of", "kdbxh_sample_name",
                  "kdbxh_sample_kmers", "kdbxh_write_all2all_csv", "kdbxh_read_db_full", "kdbxh_tables_view",
                  "kdbxh_builder_new", "kdbxh_builder_free", "kdbxh_builder_add_sample", "kdbxh_builder_finish",
                  "kdbxh_samples_load", "kdbxh_samples_free", "kdbxh_samples_count", "kdbxh_samples_name", "kdbxh_samples_kmers"]
@@ -151,6 +153,13 @@ def load():
     k.kdbx_all2all_dense_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, P(Stats)]
     k.kdbx_all2all_dense_rows_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, P(Stats)]
     k.kdbx_all2all_dense_part_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, P(Stats)]
+    k.kdbx_comm_unique_id.argtypes = [C.c_void_p]
+    k.kdbx_comm_init_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    k.kdbx_comm_init_all.argtypes = [P(C.c_void_p), C.c_int]
+    k.kdbx_comm_destroy.argtypes = [C.c_void_p]
+    k.kdbx_comm_destroy.restype = None
+    k.kdbx_all2all_dense_reduce_scatter_device.argtypes = [C.c_void_p, C.c_void_p, P(C.c_uint64), P(C.c_uint64), P(Stats)]
+    k.kdbx_all2all_dense_reduce_scatter.argtypes = [C.c_void_p, C.c_void_p, P(C.c_uint64), P(C.c_uint64), P(Stats)]
     k.kdbx_all2all_sparse.argtypes = [C.c_void_p, P(Filter), P(Csr), P(Stats)]
     k.kdbx_free_csr.argtypes = [P(Csr)]
     k.kdbx_free_csr.restype = None
@@ -178,6 +187,11 @@ def load():
     h.kdbxh_validate.argtypes = [C.c_void_p]
     h.kdbxh_prefix.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     h.kdbxh_partition.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, P(C.c_uint64)]
+    h.kdbxh_partitioner_new.argtypes = [C.c_void_p, C.c_uint32]
+    h.kdbxh_partitioner_new.restype = C.c_void_p
+    h.kdbxh_partitioner_free.argtypes = [C.c_void_p]
+    h.kdbxh_partitioner_free.restype = None
+    h.kdbxh_partitioner_part.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, P(C.c_uint64), P(C.c_uint32 * 2)]
     h.kdbxh_relabel.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
     h.kdbxh_view.argtypes = [C.c_void_p, P(TrieView)]
     h.kdbxh_totals_of.argtypes = [C.c_void_p, P(Totals)]
@@ -283,9 +297,9 @@ class Trie:
 
     @classmethod
     def synth(cls, num_samples, num_clusters=4, genome_kmers=5_000_000, k=18, mutation_rate=0.005, seed=2,
-              interleaved=False, threads=0, pinned=False):
+              interleaved=False, threads=0, pinned=False, cluster_skew=0.0):
         t = cls(pinned)
-        sp = SynthParams(num_samples, num_clusters, genome_kmers, k, 1 if interleaved else 0, mutation_rate, seed, threads, 0)
+        sp = SynthParams(num_samples, num_clusters, genome_kmers, k, 1 if interleaved else 0, mutation_rate, seed, threads, 0, cluster_skew)
         t._check(t._h.kdbxh_synth(t._p, C.byref(sp)))
         return t
 
@@ -301,6 +315,21 @@ class Trie:
         u = C.c_uint64()
         self._check(self._h.kdbxh_partition(self._p, num_parts, part, t._p, C.byref(u)))
         return t, int(u.value)
+
+    def partition_all(self, num_parts, pinned=False):
+        """Yields (part trie, owned updates, (lo, hi) sample window) for every part of one cut (kdbxh_partitioner_*)."""
+        pt = self._h.kdbxh_partitioner_new(self._p, num_parts)
+        if not pt:
+            raise KdbxError(self._h.kdbxh_last_error().decode())
+        try:
+            for part in range(num_parts):
+                out = Trie(pinned)
+                owned = C.c_uint64(0)
+                win = (C.c_uint32 * 2)(0, 0)
+                self._check(self._h.kdbxh_partitioner_part(pt, part, out._p, C.byref(owned), C.byref(win)))
+                yield out, int(owned.value), (int(win[0]), int(win[1]))
+        finally:
+            self._h.kdbxh_partitioner_free(pt)
 
     def relabel(self, offset, new_total):
         """Shift all sample ids by `offset` inside a table of `new_total` samples (in place)."""
@@ -462,6 +491,36 @@ class Context:
         st = Stats()
         self._check(self._k.kdbx_all2all_dense_part_device(self._p, part, num_parts, C.c_void_p(device_ptr), C.byref(st)))
         return st
+
+    # ---- several GPUs (kdbx.h: kdbx_comm_*) ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        k, _ = load()
+        buf = C.create_string_buffer(128)
+        if k.kdbx_comm_unique_id(buf) != 0:
+            raise KdbxError(k.kdbx_last_error(None).decode())
+        return buf.raw
+
+    def comm_init_rank(self, nranks: int, rank: int, unique_id: bytes):
+        self._check(self._k.kdbx_comm_init_rank(self._p, nranks, rank, C.create_string_buffer(unique_id, 128)))
+        self.comm_nranks, self.comm_rank = nranks, rank
+
+    def block_cells(self) -> int:
+        """cells of the packed triangle per rank after the reduce-scatter"""
+        n = getattr(self, "comm_nranks", 1)
+        return (tri_cells(self.num_samples) + n - 1) // n
+
+    def all2all_dense_reduce_scatter_device(self, device_ptr: int):
+        st = Stats()
+        first, count = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._k.kdbx_all2all_dense_reduce_scatter_device(self._p, C.c_void_p(device_ptr), C.byref(first), C.byref(count), C.byref(st)))
+        return int(first.value), int(count.value), st
+
+    def all2all_dense_reduce_scatter(self, out: np.ndarray):
+        st = Stats()
+        first, count = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._k.kdbx_all2all_dense_reduce_scatter(self._p, out.ctypes.data if out.size else None, C.byref(first), C.byref(count), C.byref(st)))
+        return int(first.value), int(count.value), st
 
     def all2all_sparse(self, min_common=0, max_common=0xFFFFFFFF, metric_bounds=(), sample_kmers=None):
         """Sparse rows (row_ptr, col, val) as numpy copies; metric_bounds = [(name, lo, hi)]."""

@@ -30,6 +30,20 @@ def test_reference_arm_prints_one_contract_line(libs, ref_bin, tmp_path):
     assert j["cpu_baseline"]["kind"] == "reference" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
     assert j["e2e"] == {"value": j["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert j["vs_baseline"] is None and "workload" in j["config"]
+    # the arm times the WHOLE workload (same .db file as the GPU arm), keeps its CSV for the GPU arm's cmp, and loads
+    # none of this repository's libraries: the database comes from the stand-alone generator
+    assert j["config"]["num_samples"] == 40 and j["config"]["updates_per_step"] > 0
+    assert "whole workload" in j["cpu_baseline"]["sample"]
+    db = tmp_path / j["config"]["database"]
+    assert db.exists() and (tmp_path / (j["config"]["database"] + ".ref.csv")).exists()
+    src = (ou.ROOT / "bench.py").read_text()
+    ref_fn = src[src.index("def reference_arm("):src.index("def _own_cells(")]
+    assert "kdbx." not in ref_fn and "import kdbx" not in ref_fn
+    # N > 1, weak scaling: the bounded sample is the one-GPU database, and the line says so
+    out = _run(["--impl", "reference", "--gpus", "2", *small], env={"RANK": "0", "LOCAL_RANK": "0", "WORLD_SIZE": "2"})
+    j2 = json.loads(out.strip().splitlines()[-1])
+    assert j2["config"]["num_samples"] == 80 and j2["config"]["sample_of_workload"]["num_samples"] == 40
+    assert "1/2 of the 2-GPU workload" in j2["cpu_baseline"]["sample"]
     # under torchrun only rank 0 works and prints; the other ranks exit 0 without output
     out = _run(["--impl", "reference", "--gpus", "2", *small], env={"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
     assert out.strip() == ""

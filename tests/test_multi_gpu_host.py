@@ -98,7 +98,34 @@ def _worker(rank, world, port, q):
                 o = ou.tri_cells(srow + r * 64)
                 ok6 = ok6 and bool(np.array_equal(got4[o + r * 64:o + r * 64 + srow], whole[ou.tri_cells(srow):ou.tri_cells(srow) + srow]))
                 ok6 = ok6 and not got4[o:o + r * 64].any()
-        q.put((rank, ok1, ok2, ok3, ok4, ok5, ok6))
+        # (5) the product's N > 1 path (bench.py, CLI -gpus): one cut for all ranks (kdbxh_partitioner), every rank knows the
+        # band of sample ids its part covers, a REDUCE-SCATTER of the partial matrices leaves rank r with the cells
+        # [r B, (r+1) B) of the packed triangle, B = ceil(cells / world) (kdbx_all2all_dense_reduce_scatter)
+        t5 = kdbx.Trie.synth(num_samples=96, num_clusters=5, genome_kmers=6000, seed=13, cluster_skew=0.4)
+        whole5, U5 = ou.oracle_all2all(oracle, 96, t5.arrays())
+        parts = list(t5.partition_all(world))
+        sub5, owned5, win5 = parts[rank]
+        a5 = sub5.arrays()
+        ids_ok = True
+        for p5 in range(len(a5["l"])):   # every decoded id of the part lies inside its declared window
+            if a5["l"][p5]:
+                out = np.zeros(int(a5["l"][p5]), np.uint32)
+                oracle.oracle_decode_local(a5["payload"][int(a5["payload_off"][p5]):].ctypes.data, int(a5["l"][p5]), int(a5["last"][p5]), out.ctypes.data)
+                ids_ok = ids_ok and win5[0] <= int(out[0]) and int(out[-1]) < win5[1]
+        mine5, _ = ou.oracle_all2all(oracle, 96, a5)
+        cells5 = ou.tri_cells(96)
+        B = (cells5 + world - 1) // world
+        padded5 = np.zeros(B * world, np.uint32)
+        padded5[:cells5] = mine5
+        t5r = torch.from_numpy(padded5.view(np.int32).copy())   # gloo has no reduce_scatter: all_reduce, keep the own block
+        dist.all_reduce(t5r)
+        outs = t5r[rank * B:(rank + 1) * B]
+        lo5, hi5 = min(cells5, rank * B), min(cells5, (rank + 1) * B)
+        ok7 = ids_ok and bool(np.array_equal(outs.numpy().view(np.uint32)[:hi5 - lo5], whole5[lo5:hi5]))
+        ot = torch.tensor([owned5], dtype=torch.int64)
+        dist.all_reduce(ot)
+        ok7 = ok7 and int(ot.item()) == U5
+        q.put((rank, ok1, ok2, ok3, ok4, ok5, ok6, ok7))
     finally:
         dist.destroy_process_group()
 
@@ -115,10 +142,11 @@ def test_two_rank_sharding_over_gloo(libs, oracle, world):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, ok1, ok2, ok3, ok4, ok5, ok6 in sorted(res):
+    for rank, ok1, ok2, ok3, ok4, ok5, ok6, ok7 in sorted(res):
         assert ok1, f"rank {rank}: all-reduced partial matrices differ from the full matrix"
         assert ok2, f"rank {rank}: gathered row blocks differ from the full matrix"
         assert ok3, f"rank {rank}: row shares are unbalanced"
         assert ok4
         assert ok5, f"rank {rank}: all-reduced matrices of the sub-tries differ from the matrix of the whole trie"
         assert ok6, f"rank {rank}: relabelled shards do not form the block-diagonal matrix"
+        assert ok7, f"rank {rank}: reduce-scattered block of the partitioner's parts differs from the whole matrix (or an id left its window)"

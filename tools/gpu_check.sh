@@ -17,10 +17,10 @@ for step in "$@"; do
     ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file "$OUT/launches.csv" python bench.py --samples 400 --genome-kmers 1000000 --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_list.out" 2>&1; echo "ncu_list rc=$?" | tee -a "$OUT/summary.txt";;
     ncu_full) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_scatter_add -s 2 -c 2 -f -o "$OUT/scatter" python bench.py --samples 400 --genome-kmers 1000000 --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_full.out" 2>&1; echo "ncu_full rc=$?" | tee -a "$OUT/summary.txt";;
     ncu_list_cfg2) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file "$OUT/launches_cfg2.csv" python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_list_cfg2.out" 2>&1; echo "ncu_list_cfg2 rc=$?" | tee -a "$OUT/summary.txt";;
-    ncu_full_cfg2) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_scatter_add -s 1 -c 1 -f -o "$OUT/scatter_cfg2" python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_full_cfg2.out" 2>&1; echo "ncu_full_cfg2 rc=$?" | tee -a "$OUT/summary.txt";;
+    ncu_full_cfg2) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_scatter -s 1 -c 1 -f -o "$OUT/scatter_cfg2" python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_full_cfg2.out" 2>&1; echo "ncu_full_cfg2 rc=$?" | tee -a "$OUT/summary.txt";;
     bench_chunks) for c in 16777216 33554432; do timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --chunk-ids $c > "$OUT/bench_chunk_$c.json" 2> "$OUT/bench_chunk_$c.err"; echo "bench_chunk $c rc=$?" | tee -a "$OUT/summary.txt"; done;;
     bench_tiles) for cfg in "32 1024 1024" "16 1024 512" "16 1024 1024" "8 1024 256" "32 1024 512"; do set -- $cfg; timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --tile-rows $1 --tile-cols $2 --scatter-threads $3 > "$OUT/bench_tile_$1_$2_$3.json" 2> "$OUT/bench_tile_$1_$2_$3.err"; echo "bench_tile $cfg rc=$?" | tee -a "$OUT/summary.txt"; done;;
-    ncu_stages) timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:k_expand|k_job_hist|k_job_fill|k_scatter_add|k_decode_locals" -s 41 -c 5 -f -o "$OUT/stages_cfg2" python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_stages.out" 2>&1; echo "ncu_stages rc=$?" | tee -a "$OUT/summary.txt";;
+    ncu_stages) timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:k_job_fill|k_scatter|k_decode_locals|k_key_totals" -s 0 -c 8 -f -o "$OUT/stages_cfg2" python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_stages.out" 2>&1; echo "ncu_stages rc=$?" | tee -a "$OUT/summary.txt";;
     scale) for n in ${SCALE_NS:-2}; do for mode in ${SCALE_MODES:-weak strong}; do timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 5 --warmup 3 --scaling $mode > "$OUT/scale_${mode}_$n.json" 2> "$OUT/scale_${mode}_$n.err"; echo "scale $mode $n rc=$?" | tee -a "$OUT/summary.txt"; done; done;;
     tests_build) timeout 900 python -m pytest tests/test_gpu_build.py -m gpu -x -q > "$OUT/pytest_build.log" 2>&1; echo "pytest_build rc=$?" | tee -a "$OUT/summary.txt";;
     bench_shard) for sh in ${SHARDS:-1/2 7/8}; do tag=$(echo $sh | tr / _); timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --emulate-shard $sh > "$OUT/bench_shard_$tag.json" 2> "$OUT/bench_shard_$tag.err"; echo "bench_shard $sh rc=$?" | tee -a "$OUT/summary.txt"; done;;
