@@ -228,6 +228,12 @@ typedef struct kdbx_csr {
  * N ~ 2*10^5) and compacted by a filter + prefix-sum kernel, so bubbles have no analogue.
  * `filter` may be NULL (keep every non-zero cell). */
 int kdbx_all2all_sparse(kdbx_ctx* ctx, const kdbx_filter* filter, kdbx_csr* out, kdbx_stats* stats);
+/* Rows [row_begin, row_end) of the same result (the other rows come back empty).  The unit of a multi-GPU sparse
+ * run: every device stages the whole trie, takes a block of rows balanced on kdbx_row_updates, and the caller
+ * concatenates the rows — the grid of the reference's all2all-parts (src/console_all2all_parts.cpp:143-331) with the
+ * database replicated instead of split, and no exchange between the devices. */
+int kdbx_all2all_sparse_rows(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, const kdbx_filter* filter,
+                             kdbx_csr* out, kdbx_stats* stats);
 void kdbx_free_csr(kdbx_csr* csr);
 
 /* ---- new2all: query samples against the database --------------------------------------- */

@@ -237,12 +237,13 @@ __device__ __forceinline__ void red_shared_add_below(uint32_t saddr, uint32_t v,
 }
 
 template <uint32_t F, uint32_t G>
-__device__ __forceinline__ void last_rows_diff(uint32_t k, uint32_t rows_saddr, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t y0,
-                                               uint32_t y1, uint32_t y2, uint32_t wl) {
+__device__ __forceinline__ void last_rows_diff(uint32_t k, uint32_t rows_saddr, uint32_t stride, uint32_t row_base, uint32_t x0, uint32_t x1,
+                                               uint32_t x2, uint32_t y0, uint32_t y1, uint32_t y2, uint32_t wl) {
 #pragma unroll 2
     for (uint32_t j = 0; j < k; ++j) {
-        uint32_t ro, lim;   // shared address of the row's accumulators, 4 * (row id): entries below it count
-        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(ro), "=r"(lim) : "r"(rows_saddr + j * 8u));
+        uint32_t lim;   // 4 * (row id): entries below it count; the row's accumulators start at lim * stride + row_base
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lim) : "r"(rows_saddr + j * 4u));
+        const uint32_t ro = lim * stride + row_base;
         if (F > 0) red_shared_add(ro + x0, wl);
         if (F > 1) red_shared_add(ro + x1, wl);
         if (F > 2) red_shared_add(ro + x2, wl);
@@ -261,7 +262,9 @@ k_scatter_diff(const Unit* __restrict__ units, const uint32_t* __restrict__ n_un
     extern __shared__ uint4 tile4[];
     uint32_t* tile = reinterpret_cast<uint32_t*>(tile4);
     __shared__ uint32_t s_unit, s_next_job;
-    __shared__ uint2 s_rows[32][32];   // per warp: (accumulator row address, 4 * row id) of the current job's rows
+    // per warp: 4 * (row id) of the current job's rows — one broadcast LDS per row; the address of the row's accumulators
+    // follows by one multiply-add (a 64-bit entry holding both costs two shared-memory wavefronts per row)
+    __shared__ uint32_t s_rows[32][32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_units = *n_units_ptr;
     const uint32_t R = 1u << rb_shift;
@@ -310,6 +313,7 @@ k_scatter_diff(const Unit* __restrict__ units, const uint32_t* __restrict__ n_un
         if (threadIdx.x == 0) s_next_job = un.job_begin;
         __syncthreads();
         const uint32_t row0 = un.key << rb_shift;
+        const uint32_t row_base = tile_saddr - row0 * 4u * stride;   // accumulators of row r start at (4 r) * stride + row_base
         for (;;) {
             uint32_t jb = 0;
             if (lane == 0) jb = atomicAdd(&s_next_job, kDiffBatch);
@@ -357,21 +361,21 @@ k_scatter_diff(const Unit* __restrict__ units, const uint32_t* __restrict__ n_un
                                  uint32_t y2, uint32_t wl) {
                 switch (full * 4 + groups) {
                     case 0: break;
-                    case 1: last_rows_diff<0, 1>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                    case 2: last_rows_diff<0, 2>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                    case 3: last_rows_diff<0, 3>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                    case 4: last_rows_diff<1, 0>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                    case 5: last_rows_diff<1, 1>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                    case 6: last_rows_diff<1, 2>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                    case 7: last_rows_diff<1, 3>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                    case 8: last_rows_diff<2, 0>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                    case 9: last_rows_diff<2, 1>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                    case 10: last_rows_diff<2, 2>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                    case 11: last_rows_diff<2, 3>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                    case 12: last_rows_diff<3, 0>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                    case 13: last_rows_diff<3, 1>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                    case 14: last_rows_diff<3, 2>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
-                    default: last_rows_diff<3, 3>(k, rows_saddr, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 1: last_rows_diff<0, 1>(k, rows_saddr, stride, row_base, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 2: last_rows_diff<0, 2>(k, rows_saddr, stride, row_base, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 3: last_rows_diff<0, 3>(k, rows_saddr, stride, row_base, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 4: last_rows_diff<1, 0>(k, rows_saddr, stride, row_base, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 5: last_rows_diff<1, 1>(k, rows_saddr, stride, row_base, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 6: last_rows_diff<1, 2>(k, rows_saddr, stride, row_base, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 7: last_rows_diff<1, 3>(k, rows_saddr, stride, row_base, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 8: last_rows_diff<2, 0>(k, rows_saddr, stride, row_base, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 9: last_rows_diff<2, 1>(k, rows_saddr, stride, row_base, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 10: last_rows_diff<2, 2>(k, rows_saddr, stride, row_base, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 11: last_rows_diff<2, 3>(k, rows_saddr, stride, row_base, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 12: last_rows_diff<3, 0>(k, rows_saddr, stride, row_base, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 13: last_rows_diff<3, 1>(k, rows_saddr, stride, row_base, x0, x1, x2, y0, y1, y2, wl); break;
+                    case 14: last_rows_diff<3, 2>(k, rows_saddr, stride, row_base, x0, x1, x2, y0, y1, y2, wl); break;
+                    default: last_rows_diff<3, 3>(k, rows_saddr, stride, row_base, x0, x1, x2, y0, y1, y2, wl); break;
                 }
             };
             Pending cur, nxt;
@@ -382,7 +386,7 @@ k_scatter_diff(const Unit* __restrict__ units, const uint32_t* __restrict__ n_un
                 if (q + 1 < cnt) request(q + 1, nxt);
                 const uint32_t k = cur.k, c0 = cur.c0, e = cur.e;
                 __syncwarp();   // the previous job's reads of the row table are done
-                if (lane < k) s_rows[warp][lane] = make_uint2(tile_saddr + (cur.row - row0) * stride * 4u, cur.row * 4u);
+                if (lane < k) s_rows[warp][lane] = cur.row * 4u;
                 __syncwarp();
                 const uint32_t wl = (lane & 1u) ? 0u - cur.w : cur.w;   // slices start at even positions: the lane's parity is the entry's
                 if (c0 < 128) {
@@ -395,8 +399,9 @@ k_scatter_diff(const Unit* __restrict__ units, const uint32_t* __restrict__ n_un
                     uint32_t c = 0;
                     for (;;) {
                         for (uint32_t j = 0; j < k; ++j) {
-                            uint32_t ro;
-                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ro) : "r"(rows_saddr + j * 8u));
+                            uint32_t lim;
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lim) : "r"(rows_saddr + j * 4u));
+                            const uint32_t ro = lim * stride + row_base;
                             red_shared_add(ro + x0, wl); red_shared_add(ro + x1, wl);
                             red_shared_add(ro + x2, wl); red_shared_add(ro + x3, wl);
                         }

@@ -2096,7 +2096,12 @@ int kdbx_row_updates(kdbx_ctx* ctx, uint64_t* out) {
 
 int kdbx_all2all_sparse(kdbx_ctx* ctx, const kdbx_filter* filter, kdbx_csr* out, kdbx_stats* stats) {
     if (!ctx) return KDBX_ERR_ARG;
-    return all2all_sparse_impl(ctx, filter, out, stats);
+    return all2all_sparse_impl(ctx, filter, out, stats, 0, ctx->N);
+}
+
+int kdbx_all2all_sparse_rows(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, const kdbx_filter* filter, kdbx_csr* out, kdbx_stats* stats) {
+    if (!ctx) return KDBX_ERR_ARG;
+    return all2all_sparse_impl(ctx, filter, out, stats, row_begin, row_end);
 }
 
 void kdbx_free_csr(kdbx_csr* csr) {

@@ -72,13 +72,16 @@ __global__ void k_sparse_fill(const uint32_t* __restrict__ tri, uint64_t tri_bas
     }
 }
 
-int all2all_sparse_impl(kdbx_ctx* ctx, const kdbx_filter* filter, kdbx_csr* out, kdbx_stats* stats) {
+// rows [row_begin, row_end) only (the other rows of the result are empty): the unit of work of a multi-GPU run, where
+// every device holds the whole trie and the CSR rows of the devices are concatenated by the caller
+int all2all_sparse_impl(kdbx_ctx* ctx, const kdbx_filter* filter, kdbx_csr* out, kdbx_stats* stats, uint32_t row_begin, uint32_t row_end) {
     if (!ctx->loaded) return ctx->fail(KDBX_ERR_STATE, "no patterns loaded (call kdbx_load_patterns first)");
     if (!out) return ctx->fail(KDBX_ERR_ARG, "kdbx_all2all_sparse: out is NULL");
     std::memset(out, 0, sizeof *out);
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const uint32_t N = ctx->N;
+    if (row_begin > row_end || row_end > N) return ctx->fail(KDBX_ERR_ARG, "bad row range [%u,%u) for %u samples", row_begin, row_end, N);
     FilterDev f{};
     f.lo = 0; f.hi = 0xFFFFFFFFu;
     if (filter) {
@@ -112,10 +115,10 @@ int all2all_sparse_impl(kdbx_ctx* ctx, const kdbx_filter* filter, kdbx_csr* out,
     };
     kdbx_stats total{};
     uint64_t nnz = 0;
-    uint32_t r0 = 0;
-    while (r0 < N) {
+    uint32_t r0 = row_begin;
+    while (r0 < row_end) {
         uint32_t r1 = r0 + 1;
-        while (r1 < N && tri_off(r1 + 1) - tri_off(r0) <= budget_cells) ++r1;
+        while (r1 < row_end && tri_off(r1 + 1) - tri_off(r0) <= budget_cells) ++r1;
         const uint64_t cells = tri_off(r1) - tri_off(r0);
         const uint32_t rows = r1 - r0;
         kdbx_stats s{};
@@ -166,7 +169,7 @@ int all2all_sparse_impl(kdbx_ctx* ctx, const kdbx_filter* filter, kdbx_csr* out,
         nnz += block_nnz;
         r0 = r1;
     }
-    row_ptr[N] = nnz;
+    for (size_t r = row_end; r <= N; ++r) row_ptr[r] = nnz;   // rows after the range are empty
     // hand over: row_ptr always malloc'ed; col/val are the pinned chunk itself when there was one block
     out->num_rows = N;
     out->nnz = nnz;

@@ -151,7 +151,8 @@ void run_all2all_sparse(const Params& p) {
     std::cerr << "Calculating matrix of common k-mers...";
     t0 = now();
     SparseMatrix<uint32_t> matrix;
-    calculator.all2all_sp(db, matrix, p.filters);
+    if (p.num_gpus > 1) calculator.all2all_sp_multi(db, matrix, p.filters, p.num_gpus);
+    else calculator.all2all_sp(db, matrix, p.filters);
     const double dt = now() - t0;
     std::cerr << "OK (" << dt << " seconds)" << std::endl;
     print_stats_json(calculator.last_stats(), dt);

@@ -14,6 +14,8 @@
 //     (src/main.cpp:56-59); there is no CPU fallback.
 #pragma once
 #include <cfloat>
+#include <cstdlib>
+#include <cstring>
 #include <exception>
 #include <stdexcept>
 #include <thread>
@@ -102,20 +104,23 @@ public:
         return bounds;
     }
 
-    // The dense matrix on several GPUs of one node: every device holds the whole trie and
-    // computes a contiguous block of rows straight into its slice of the caller's matrix; rows
-    // are independent, so there is no exchange.  One host thread per device.
+    // The dense matrix on several GPUs of one node.  The DATABASE is sharded: the trie is cut into one sub-trie per
+    // device (TriePartitioner: pieces of the depth-first preorder plus the ancestor chain of each piece with
+    // num_kmers = 0 — the matrix is linear in num_kmers, so the parts' matrices add up), every device stages only its
+    // own part, declares the band of sample ids it covers and runs the whole single-GPU pipeline on it; ONE
+    // ncclReduceScatter inside the library adds the partial matrices and leaves device g with block g of the packed
+    // triangle, which it copies straight into the caller's matrix.  One host thread per device.
+    // (The reference's only sharding template is the grid of partial databases of all2all-parts,
+    // src/console_all2all_parts.cpp:143-331; between threads it uses row ownership, src/similarity_calculator.cpp:371-395.)
     void all2all_multi(const Trie& db, LowerTriangularMatrix<uint32_t>& matrix, int num_gpus) const {
         const int avail = kdbx_device_count();
         if (num_gpus > avail) throw std::runtime_error("-gpus " + std::to_string(num_gpus) + " requested but only " + std::to_string(avail) + " B200 device(s) are visible");
         matrix.resize(db.num_samples());
-        const uint32_t N = db.num_samples();
-        const kdbx_trie_view v = db.view();
         const int base = device_ < 0 ? 0 : device_;
         std::vector<kdbx_ctx*> ctxs((size_t)num_gpus, nullptr);
         std::vector<std::string> errors((size_t)num_gpus);
         ctxs[0] = ctx_;
-        auto close_extra = [&]() { for (int g = 1; g < num_gpus; ++g) kdbx_close(ctxs[(size_t)g]); };
+        auto close_extra = [&]() { kdbx_comm_destroy(ctx_); for (int g = 1; g < num_gpus; ++g) kdbx_close(ctxs[(size_t)g]); };
         auto on_all = [&](auto&& fn) {
             std::vector<std::thread> th;
             for (int g = 0; g < num_gpus; ++g)
@@ -123,30 +128,36 @@ public:
             for (auto& t : th) t.join();
             for (const std::string& e : errors) if (!e.empty()) { close_extra(); throw std::runtime_error(e); }
         };
-        on_all([&](int g) {
-            if (g > 0) {
-                kdbx_config cfg{};
-                cfg.device = base + g;
-                if (kdbx_open(&cfg, &ctxs[(size_t)g]) != KDBX_OK) throw std::runtime_error(kdbx_last_error(nullptr));
-            }
-            if (kdbx_load_patterns(ctxs[(size_t)g], &v) != KDBX_OK) throw std::runtime_error(kdbx_last_error(ctxs[(size_t)g]));
-        });
-        std::vector<uint64_t> upd(N, 0);
-        if (N && kdbx_row_updates(ctx_, upd.data()) != KDBX_OK) { const std::string e = kdbx_last_error(ctx_); close_extra(); throw std::runtime_error(e); }
-        const std::vector<uint32_t> bounds = shard_rows_by_work(upd, num_gpus);
+        for (int g = 1; g < num_gpus; ++g) {   // (serially: kdbx_open reports its errors through one string per thread)
+            kdbx_config cfg{};
+            cfg.device = base + g;
+            if (kdbx_open(&cfg, &ctxs[(size_t)g]) != KDBX_OK) { const std::string e = kdbx_last_error(nullptr); close_extra(); throw std::runtime_error(e); }
+        }
+        if (kdbx_comm_init_all(ctxs.data(), num_gpus) != KDBX_OK) { const std::string e = kdbx_last_error(ctx_); close_extra(); throw std::runtime_error(e); }
+        const TriePartitioner cut(db, (uint32_t)num_gpus);
         std::vector<kdbx_stats> st((size_t)num_gpus);
         on_all([&](int g) {
-            const uint32_t r0 = bounds[(size_t)g], r1 = bounds[(size_t)g + 1];
-            uint32_t* dst = matrix.data() + (r0 == 0 ? 0 : (size_t)r0 * (r0 - 1) / 2);
-            if (kdbx_all2all_dense_rows(ctxs[(size_t)g], r0, r1, dst, &st[(size_t)g]) != KDBX_OK)
-                throw std::runtime_error(kdbx_last_error(ctxs[(size_t)g]));
+            Trie part(true);
+            uint32_t window[2] = {0, 0};
+            cut.extract((uint32_t)g, part, nullptr, window);
+            const kdbx_trie_view v = part.view();
+            kdbx_ctx* c = ctxs[(size_t)g];
+            if (kdbx_load_patterns(c, &v) != KDBX_OK || kdbx_set_sample_window(c, window[0], window[1]) != KDBX_OK)
+                throw std::runtime_error(kdbx_last_error(c));
+            const uint64_t cells = matrix.cells(), B = (cells + (uint64_t)num_gpus - 1) / (uint64_t)num_gpus;
+            uint64_t first = 0, count = 0;
+            uint32_t* dst = matrix.data() + std::min<uint64_t>(cells, (uint64_t)g * B);
+            if (kdbx_all2all_dense_reduce_scatter(c, dst, &first, &count, &st[(size_t)g]) != KDBX_OK)
+                throw std::runtime_error(kdbx_last_error(c));
         });
         stats_ = st[0];
         for (int g = 1; g < num_gpus; ++g) {  // totals; times are the slowest device's
             stats_.updates += st[(size_t)g].updates;
+            stats_.physical_updates += st[(size_t)g].physical_updates;
             stats_.kernel_launches += st[(size_t)g].kernel_launches;
             stats_.ms_total = std::max(stats_.ms_total, st[(size_t)g].ms_total);
             stats_.ms_scatter = std::max(stats_.ms_scatter, st[(size_t)g].ms_scatter);
+            stats_.ms_collective = std::max(stats_.ms_collective, st[(size_t)g].ms_collective);
         }
         close_extra();
     }
@@ -159,21 +170,77 @@ public:
         const kdbx_trie_view v = db.view();
         check(kdbx_load_patterns(ctx_, &v));
         kdbx_filter f{};
-        f.min_common = filters.kmers_lo; f.max_common = filters.kmers_hi;
         std::vector<uint32_t> counts(db.sample_kmers.begin(), db.sample_kmers.end());
-        for (const auto& m : filters.metrics) {
-            int id = -1;
-            if (m.first == "jaccard") id = KDBX_METRIC_JACCARD;
-            else if (m.first == "min") id = KDBX_METRIC_MIN;
-            else if (m.first == "max") id = KDBX_METRIC_MAX;
-            else if (m.first == "cosine") id = KDBX_METRIC_COSINE;
-            if (id < 0 || f.num_metric_bounds == 4) continue;
-            kdbx_metric_bound& b = f.metric_bounds[f.num_metric_bounds++];
-            b.metric = id; b.lo = m.second.lo; b.hi = m.second.hi;
-        }
-        f.sample_kmers = counts.data();
+        make_filter(filters, counts, f);
         kdbx_free_csr(matrix.raw());
         check(kdbx_all2all_sparse(ctx_, &f, matrix.raw(), &stats_));
+    }
+
+    // all2all_sp on several GPUs of one node: every device stages the whole trie (minhashed databases are small) and takes a
+    // block of rows balanced on the per-row update counts; the rows are independent, so there is no exchange, and the blocks'
+    // CSR rows are concatenated here.  The grid of the reference's all2all-parts (src/console_all2all_parts.cpp:143-331) with
+    // the database replicated instead of split.
+    void all2all_sp_multi(const Trie& db, SparseMatrix<uint32_t>& matrix, const OutputFilters& filters, int num_gpus) const {
+        const int avail = kdbx_device_count();
+        if (num_gpus > avail) throw std::runtime_error("-gpus " + std::to_string(num_gpus) + " requested but only " + std::to_string(avail) + " B200 device(s) are visible");
+        const uint32_t N = db.num_samples();
+        const kdbx_trie_view v = db.view();
+        kdbx_filter f{};
+        std::vector<uint32_t> counts(db.sample_kmers.begin(), db.sample_kmers.end());
+        make_filter(filters, counts, f);
+        const int base = device_ < 0 ? 0 : device_;
+        std::vector<kdbx_ctx*> ctxs((size_t)num_gpus, nullptr);
+        ctxs[0] = ctx_;
+        auto close_extra = [&]() { for (int g = 1; g < num_gpus; ++g) kdbx_close(ctxs[(size_t)g]); };
+        for (int g = 1; g < num_gpus; ++g) {
+            kdbx_config cfg{};
+            cfg.device = base + g;
+            if (kdbx_open(&cfg, &ctxs[(size_t)g]) != KDBX_OK) { const std::string e = kdbx_last_error(nullptr); close_extra(); throw std::runtime_error(e); }
+        }
+        std::vector<std::string> errors((size_t)num_gpus);
+        auto on_all = [&](auto&& fn) {
+            std::vector<std::thread> th;
+            for (int g = 0; g < num_gpus; ++g)
+                th.emplace_back([&, g] { try { fn(g); } catch (const std::exception& e) { errors[(size_t)g] = e.what(); } });
+            for (auto& t : th) t.join();
+            for (const std::string& e : errors) if (!e.empty()) { close_extra(); throw std::runtime_error(e); }
+        };
+        on_all([&](int g) { if (kdbx_load_patterns(ctxs[(size_t)g], &v) != KDBX_OK) throw std::runtime_error(kdbx_last_error(ctxs[(size_t)g])); });
+        std::vector<uint64_t> upd(N, 0);
+        if (N && kdbx_row_updates(ctx_, upd.data()) != KDBX_OK) { const std::string e = kdbx_last_error(ctx_); close_extra(); throw std::runtime_error(e); }
+        const std::vector<uint32_t> bounds = shard_rows_by_work(upd, num_gpus);
+        std::vector<kdbx_csr> parts((size_t)num_gpus, kdbx_csr{});
+        std::vector<kdbx_stats> st((size_t)num_gpus);
+        on_all([&](int g) {
+            if (kdbx_all2all_sparse_rows(ctxs[(size_t)g], bounds[(size_t)g], bounds[(size_t)g + 1], &f, &parts[(size_t)g], &st[(size_t)g]) != KDBX_OK)
+                throw std::runtime_error(kdbx_last_error(ctxs[(size_t)g]));
+        });
+        // concatenate: block g holds the rows [bounds[g], bounds[g+1]) and nothing else
+        kdbx_free_csr(matrix.raw());
+        kdbx_csr& out = *matrix.raw();
+        uint64_t nnz = 0;
+        for (const kdbx_csr& c : parts) nnz += c.nnz;
+        out.num_rows = N; out.nnz = nnz; out._pad = 0;
+        out.row_ptr = static_cast<uint64_t*>(std::malloc(((size_t)N + 1) * 8));
+        out.col = static_cast<uint32_t*>(std::malloc(std::max<uint64_t>(1, nnz) * 4));
+        out.val = static_cast<uint32_t*>(std::malloc(std::max<uint64_t>(1, nnz) * 4));
+        if (!out.row_ptr || !out.col || !out.val) { close_extra(); throw std::runtime_error("host allocation failed"); }
+        uint64_t at = 0;
+        for (int g = 0; g < num_gpus; ++g) {
+            const kdbx_csr& c = parts[(size_t)g];
+            for (uint32_t r = bounds[(size_t)g]; r < bounds[(size_t)g + 1]; ++r) out.row_ptr[r] = at + c.row_ptr[r];
+            if (c.nnz) { std::memcpy(out.col + at, c.col, c.nnz * 4); std::memcpy(out.val + at, c.val, c.nnz * 4); }
+            at += c.nnz;
+        }
+        out.row_ptr[N] = at;
+        for (kdbx_csr& c : parts) kdbx_free_csr(&c);
+        stats_ = st[0];
+        for (int g = 1; g < num_gpus; ++g) {
+            stats_.updates += st[(size_t)g].updates;
+            stats_.kernel_launches += st[(size_t)g].kernel_launches;
+            stats_.ms_total = std::max(stats_.ms_total, st[(size_t)g].ms_total);
+        }
+        close_extra();
     }
 
     // Stage the database for queries: patterns + k-mer tables (PrefixKmerDb::deserialize with
@@ -222,6 +289,21 @@ public:
     const kdbx_stats& last_stats() const { return stats_; }
 
 private:
+    // the -min/-max bounds whose arithmetic is exactly reproducible on the device (include/kdbx.h)
+    static void make_filter(const OutputFilters& filters, const std::vector<uint32_t>& counts, kdbx_filter& f) {
+        f.min_common = filters.kmers_lo; f.max_common = filters.kmers_hi;
+        for (const auto& m : filters.metrics) {
+            int id = -1;
+            if (m.first == "jaccard") id = KDBX_METRIC_JACCARD;
+            else if (m.first == "min") id = KDBX_METRIC_MIN;
+            else if (m.first == "max") id = KDBX_METRIC_MAX;
+            else if (m.first == "cosine") id = KDBX_METRIC_COSINE;
+            if (id < 0 || f.num_metric_bounds == 4) continue;
+            kdbx_metric_bound& b = f.metric_bounds[f.num_metric_bounds++];
+            b.metric = id; b.lo = m.second.lo; b.hi = m.second.hi;
+        }
+        f.sample_kmers = counts.data();
+    }
     void check(int rc) const { if (rc != KDBX_OK) throw std::runtime_error(kdbx_last_error(ctx_)); }
     int num_threads_;
     size_t cache_buffer_mb_;

@@ -109,7 +109,7 @@ class Totals(C.Structure):
 # every symbol include/kdbx.h declares (tests check that the library exports all of them)
 KDBX_SYMBOLS = ["kdbx_abi_version", "kdbx_device_count", "kdbx_open", "kdbx_close", "kdbx_last_error",
                 "kdbx_host_alloc", "kdbx_host_free", "kdbx_load_patterns", "kdbx_set_sample_window", "kdbx_row_updates", "kdbx_all2all_dense",
-                "kdbx_all2all_dense_rows", "kdbx_all2all_dense_rows_device", "kdbx_all2all_dense_part_device", "kdbx_all2all_sparse", "kdbx_free_csr",
+                "kdbx_all2all_dense_rows", "kdbx_all2all_dense_rows_device", "kdbx_all2all_dense_part_device", "kdbx_all2all_sparse", "kdbx_all2all_sparse_rows", "kdbx_free_csr",
                 "kdbx_load_hashtables", "kdbx_new2all_batch", "kdbx_debug_fetch", "kdbx_comm_unique_id", "kdbx_comm_init_rank",
                 "kdbx_comm_init_all", "kdbx_comm_destroy", "kdbx_all2all_dense_reduce_scatter_device", "kdbx_all2all_dense_reduce_scatter",
                 "kdbx_builder_open", "kdbx_builder_close", "kdbx_builder_adopt", "kdbx_builder_add_sequence", "kdbx_builder_add_kmers",
@@ -161,6 +161,7 @@ def load():
     k.kdbx_all2all_dense_reduce_scatter_device.argtypes = [C.c_void_p, C.c_void_p, P(C.c_uint64), P(C.c_uint64), P(Stats)]
     k.kdbx_all2all_dense_reduce_scatter.argtypes = [C.c_void_p, C.c_void_p, P(C.c_uint64), P(C.c_uint64), P(Stats)]
     k.kdbx_all2all_sparse.argtypes = [C.c_void_p, P(Filter), P(Csr), P(Stats)]
+    k.kdbx_all2all_sparse_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, P(Filter), P(Csr), P(Stats)]
     k.kdbx_free_csr.argtypes = [P(Csr)]
     k.kdbx_free_csr.restype = None
     k.kdbx_load_hashtables.argtypes = [C.c_void_p, P(TablesView)]
@@ -522,8 +523,9 @@ class Context:
         self._check(self._k.kdbx_all2all_dense_reduce_scatter(self._p, out.ctypes.data if out.size else None, C.byref(first), C.byref(count), C.byref(st)))
         return int(first.value), int(count.value), st
 
-    def all2all_sparse(self, min_common=0, max_common=0xFFFFFFFF, metric_bounds=(), sample_kmers=None):
-        """Sparse rows (row_ptr, col, val) as numpy copies; metric_bounds = [(name, lo, hi)]."""
+    def all2all_sparse(self, min_common=0, max_common=0xFFFFFFFF, metric_bounds=(), sample_kmers=None, rows=None):
+        """Sparse rows (row_ptr, col, val) as numpy copies; metric_bounds = [(name, lo, hi)]; rows = (begin, end) computes
+        only that block of rows (kdbx_all2all_sparse_rows)."""
         f = Filter()
         f.min_common, f.max_common = min_common, max_common
         f.num_metric_bounds = len(metric_bounds)
@@ -534,7 +536,10 @@ class Context:
             keep = np.ascontiguousarray(sample_kmers, np.uint32)
             f.sample_kmers = keep.ctypes.data
         csr, st = Csr(), Stats()
-        self._check(self._k.kdbx_all2all_sparse(self._p, C.byref(f), C.byref(csr), C.byref(st)))
+        if rows is None:
+            self._check(self._k.kdbx_all2all_sparse(self._p, C.byref(f), C.byref(csr), C.byref(st)))
+        else:
+            self._check(self._k.kdbx_all2all_sparse_rows(self._p, rows[0], rows[1], C.byref(f), C.byref(csr), C.byref(st)))
         try:
             row_ptr = _np_from(csr.row_ptr, csr.num_rows + 1, np.uint64).copy()
             col = _np_from(csr.col, csr.nnz, np.uint32).copy()

@@ -441,3 +441,14 @@ def test_reduce_scatter_two_gpus_one_process(libs, oracle):
     assert np.array_equal(got, want)
     for c in ctxs:
         c.close()
+
+
+def test_cli_all2all_on_two_gpus(libs, golden_dbs, tmp_path):
+    """kmer-db-b200 all2all -gpus 2: sub-tries + one reduce-scatter, same CSV bytes as the reference's golden file."""
+    k, _ = libs.load()
+    if k.kdbx_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    db, dense, _ = golden_dbs["virus.k18"]
+    exe = ou.ROOT / "kmer-db_b200" / "bin" / "kmer-db-b200"
+    subprocess.run([str(exe), "all2all", "-gpus", "2", str(db), str(tmp_path / "a.csv")], check=True, stderr=subprocess.DEVNULL)
+    assert ou.read_bytes(tmp_path / "a.csv") == ou.read_bytes(dense)

@@ -40,6 +40,15 @@ def test_sparse_equals_flat_clique_oracle(libs, oracle, seed):
             rp, col, val, st = c.all2all_sparse()
         assert _csr_rows(rp, col, val) == _dense_to_rows(want, N, lambda v_, s, c_: True)
         assert int(rp[-1]) == int(np.count_nonzero(want))
+    # a block of rows (kdbx_all2all_sparse_rows, the unit of the multi-GPU sparse run): those rows, the others empty
+    full_rows = _dense_to_rows(want, N, lambda v_, s, c_: True)
+    with libs.Context(device=0) as c:
+        v, keep = libs.view_from_arrays(N, a["num_kmers"], a["parent_id"], a["n"], a["l"], a["last"], a["bits"], a["payload_off"], a["payload"])
+        c.load_patterns(v, keep)
+        b, e = N // 3, max(N // 3, N - N // 4)
+        rp, col, val, st = c.all2all_sparse(rows=(b, e))
+        got = _csr_rows(rp, col, val)
+        assert got[b:e] == full_rows[b:e] and all(r == ([], []) for r in got[:b] + got[e:])
 
 
 def test_sparse_filters_on_device(libs, oracle):
@@ -214,3 +223,6 @@ def test_cli_multi_gpu_flag(cli, libs, ref_fixtures, golden_dbs, tmp_path):
         return
     cli(ref_fixtures, "all2all", "-gpus", str(min(n, 4)), golden_dbs["virus.k18"][0], tmp_path / "x.csv")
     assert ou.read_bytes(tmp_path / "x.csv") == ou.read_bytes(golden_dbs["virus.k18"][1])
+    # all2all-sp over row blocks on several devices, rows concatenated: the reference's sparse golden file
+    cli(ref_fixtures, "all2all-sp", "-gpus", str(min(n, 4)), golden_dbs["virus.k18"][0], tmp_path / "xs.csv")
+    assert ou.read_bytes(tmp_path / "xs.csv") == ou.read_bytes(golden_dbs["virus.k18"][2])

@@ -33,6 +33,7 @@ for step in "$@"; do
     bench_ids) timeout 900 python bench.py --no-cpu-baseline --no-e2e --list-form ids --steps 5 --warmup 3 > "$OUT/bench_ids.json" 2> "$OUT/bench_ids.err"; echo "bench_ids rc=$?" | tee -a "$OUT/summary.txt";;
     sanitize) timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "random_tries or boundary_lists or sample_window or edge_cases" > "$OUT/sanitizer_memcheck.log" 2>&1; echo "memcheck rc=$?" | tee -a "$OUT/summary.txt"
               timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "random_tries or boundary_lists" > "$OUT/sanitizer_racecheck.log" 2>&1; echo "racecheck rc=$?" | tee -a "$OUT/summary.txt";;
+    scale_new) for n in ${SCALE_NS:-2}; do for mode in ${SCALE_MODES:-weak strong}; do timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps ${SCALE_STEPS:-5} --warmup 3 --scaling $mode > "$OUT/scale_${mode}_$n.json" 2> "$OUT/scale_${mode}_$n.err"; echo "scale $mode $n rc=$?" | tee -a "$OUT/summary.txt"; done; done;;
     *) echo "unknown step $step";;
   esac
 done
