@@ -178,6 +178,15 @@ int kdbx_all2all_dense(kdbx_ctx* ctx, uint32_t* out_tri, kdbx_stats* stats);
 int kdbx_all2all_dense_rows(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end,
                             uint32_t* out_rows, kdbx_stats* stats);
 
+/* The step after the path, on the device: the decimal text of the dense table's cells.  For every row s in
+ * [row_begin, row_end) the s cells of the packed row, each followed by ',' — exactly what the reference prints
+ * after "<name>,<total-kmers>," (src/console_all2all.cpp:65-78 -> LowerTriangularMatrix::saveRow, src/array.h:254-258,
+ * plain decimal by src/conversion.h:99-165) — formatted from the matrix that the last kdbx_all2all_dense /
+ * kdbx_all2all_dense_rows call on this context left in device memory (the rows must lie inside that call's range).
+ * row_off receives rows + 1 byte offsets into the text; *bytes the total.  text == NULL: sizes only.  HOST pointers. */
+int kdbx_csv_dense_rows(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, char* text, uint64_t capacity,
+                        uint64_t* row_off, uint64_t* bytes);
+
 /* Same, result left in DEVICE memory (`d_out_rows` is a CUDA device pointer on ctx's
  * device, e.g. a torch tensor's data_ptr); no D2H inside the call. */
 int kdbx_all2all_dense_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end,

@@ -71,6 +71,7 @@ int all2all_reduce_scatter_device(kdbx_ctx* ctx, uint32_t* d_block, uint64_t* fi
     if (num_cells) *num_cells = std::min<uint64_t>(cells, (uint64_t)(rank + 1) * B) - std::min<uint64_t>(cells, (uint64_t)rank * B);
     if (B && !d_block) return ctx->fail(KDBX_ERR_ARG, "output pointer is NULL");
     CK(cudaSetDevice(ctx->device));
+    ctx->tri_rows_valid = false;   // ctx->tri holds a PARTIAL matrix from here on
     CK(ctx->tri.ensure(((uint64_t)nranks * B + 4) * 4));
     if ((uint64_t)nranks * B > cells)
         CK(cudaMemsetAsync(ctx->tri.as<uint32_t>() + cells, 0, ((uint64_t)nranks * B - cells) * 4, ctx->stream));

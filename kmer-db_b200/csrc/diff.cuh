@@ -258,7 +258,7 @@ __device__ __forceinline__ void last_rows_diff(uint32_t k, uint32_t rows_saddr, 
 __global__ void __maxnreg__(64)
 k_scatter_diff(const Unit* __restrict__ units, const uint32_t* __restrict__ n_units_ptr, const Job* __restrict__ jobs,
                const uint32_t* __restrict__ bflat, const uint32_t* __restrict__ loc, uint32_t* __restrict__ tri,
-               uint32_t id_lo, uint32_t tile_cols, uint32_t rb_shift, uint32_t* __restrict__ unit_counter) {
+               uint32_t id_lo, uint32_t num_rows, uint32_t tile_cols, uint32_t rb_shift, uint32_t* __restrict__ unit_counter) {
     extern __shared__ uint4 tile4[];
     uint32_t* tile = reinterpret_cast<uint32_t*>(tile4);
     __shared__ uint32_t s_unit, s_next_job;
@@ -283,23 +283,53 @@ k_scatter_diff(const Unit* __restrict__ units, const uint32_t* __restrict__ n_un
         if (!done) un = units[u];
         if (un.key != cur_key) {
             if (cur_key != kNone) {
-                // flush: prefix sums along each row (differences -> counts), then into the packed triangle.
-                // A warp per row, 32 columns at a time; only the columns below the diagonal exist.
+                // flush: prefix sums along each row (differences -> counts), then the row goes into the packed triangle as
+                // ONE bulk reduction (cp.reduce.async.bulk ... .add.u32: the TMA engine adds up to 6 KB of shared memory into
+                // global memory; the warp issues one instruction instead of 32 x nc / 32 atomics).  A bulk operation needs
+                // 16-byte aligned addresses on both sides, and a row of the packed triangle starts wherever s(s-1)/2 falls:
+                // the scanned row is therefore written back `sh` words to the right of where it was read (sh = the row's
+                // global word offset modulo 4; the reads run one 32-column chunk ahead of the writes), which gives the
+                // shared and the global address of a column the same alignment.  The up to three columns before the first
+                // and after the last aligned one go by ordinary reductions.  A warp per row; only the columns below the
+                // diagonal exist.
                 const uint32_t row0 = cur_key << rb_shift;
                 for (uint32_t r = warp; r < R; r += (blockDim.x >> 5)) {
                     const uint32_t row = row0 + r;                 // relative to id_lo, like the columns
                     const uint32_t nc = min(tile_cols, row);
+                    if (nc == 0 || row >= num_rows) continue;   // (the last row block may reach past the matrix: nothing was added there)
                     const uint64_t out0 = tri_offset((uint64_t)row + id_lo) + id_lo;
-                    const uint32_t* src = tile + r * stride;
+                    const uint32_t sh = (uint32_t)out0 & 3u;
+                    uint32_t* src = tile + r * stride;
                     uint32_t carry = 0;
+                    uint32_t v = lane < nc ? src[lane] : 0u;
                     for (uint32_t c0 = 0; c0 < nc; c0 += 32) {
-                        const uint32_t c = c0 + lane;
-                        uint32_t v = c < nc ? src[c] : 0u;
+                        const uint32_t cn = c0 + 32 + lane;
+                        const uint32_t v_next = cn < nc ? src[cn] : 0u;   // read before the shifted write below can reach it
                         for (int o = 1; o < 32; o <<= 1) { const uint32_t up = __shfl_up_sync(0xffffffffu, v, o); if ((int)lane >= o) v += up; }
                         v += carry;
                         carry = __shfl_sync(0xffffffffu, v, 31);
-                        if (c < nc && v) atomicAdd(&tri[out0 + c], v);
+                        __syncwarp();
+                        if (c0 + lane < nc) src[c0 + lane + sh] = v;
+                        v = v_next;
                     }
+                    // columns [a0, a1) are 16-byte aligned on both sides
+                    const uint32_t a0 = min(nc, (4u - sh) & 3u);
+                    const uint32_t a1 = a0 + ((nc - a0) & ~3u);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the writes above, before the TMA engine reads them
+                    __syncwarp();
+                    if (lane == 0 && a1 > a0) {
+                        const uint32_t saddr = tile_saddr + (r * stride + a0 + sh) * 4u;
+                        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u32 [%0], [%1], %2;" ::"l"(tri + out0 + a0), "r"(saddr),
+                                     "r"((a1 - a0) * 4u)
+                                     : "memory");
+                    }
+                    if (lane < a0) { const uint32_t x = src[lane + sh]; if (x) atomicAdd(&tri[out0 + lane], x); }
+                    if (a1 + lane < nc) { const uint32_t x = src[a1 + lane + sh]; if (x) atomicAdd(&tri[out0 + a1 + lane], x); }
+                }
+                // the tile is zeroed next: the bulk reductions must have read it
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 }
                 __syncthreads();
             }

@@ -263,59 +263,79 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
                 const uint64_t po = poff[p];
                 bool ok = po + ((uint64_t)(nb + 127u) / 128u) * 2u <= payload_words;
                 if (!ok) atomicExch(err, 5);
-                uint32_t pos = 0, runs = 1;
+                const uint64_t* w = payload + po;
+                // The stream holds the deltas in append order and only the LAST id is stored, so the bits are walked twice:
+                // once for the sum of the deltas (no stores; a run of zero bits = that many deltas of 1 is taken by one
+                // clz), once to write the ids.  Nothing is parked in between: the second walk writes final ids, and a run
+                // of consecutive ids is written by a loop that does nothing but store (the row-block / 32-position
+                // boundaries of the job count are stepped over arithmetically instead of being tested per id).
+                uint32_t pos = 0, runs = 1, i = 1;
                 uint64_t sum = 0;
                 if (ok) {
-                    const uint64_t* w = payload + po;
-                    uint32_t i = 1;
                     while (i < nd.l && pos < nb) {
-                        // a delta of 1 is the single bit 0 (consecutive sample ids): take a whole run of
-                        // zero bits at once — most of a cluster's lists are such runs
+                        const uint32_t off = pos & 63;
+                        const uint64_t x = w[pos >> 6] << off;
+                        uint32_t z = x ? (uint32_t)__clzll((long long)x) : 64u;
+                        z = min(min(z, 64u - off), min(nb - pos, nd.l - i));
+                        if (z) { i += z; pos += z; sum += z; continue; }
+                        const uint32_t d = gamma_next(w, pos, nb);   // >= 2 (the next bit is a one), or 0 on a malformed stream
+                        ++i; sum += d; ++runs;
+                    }
+                    if (i != nd.l || pos != nb) { atomicExch(err, 1); ok = false; }
+                    else if (sum > nd.last) { atomicExch(err, 2); ok = false; }
+                }
+                uint32_t cur = 0;
+                if (ok) {
+                    cur = nd.last - (uint32_t)sum;
+                    if (cur < floor_id) atomicExch(err, 3);
+                    if (cur < win_lo) { atomicExch(err, 7); ok = false; }
+                    const uint32_t joined = has_par && cur == floor_id;
+                    own = ((2u * runs - joined) << 1) | joined;
+                }
+                if (ok) {
+                    cur -= win_lo;
+                    out[0] = cur;
+                    const uint32_t wgt = dh.enabled ? dh.W[p] : 0u;
+                    const bool rounds = nd.l > kSmallL;   // longer lists are enumerated 32 positions at a time
+                    const uint32_t R = 1u << dh.rb_shift;
+                    uint32_t run_j = 0, run_rb = cur >> dh.rb_shift;
+                    // a job run ends before position i (id `idr`) when the row block changes or a 32-position round begins
+                    auto boundary = [&](uint32_t i, uint32_t idr) {
+                        const uint32_t rb = idr >> dh.rb_shift;
+                        if (rb != run_rb || (rounds && (i & 31u) == 0)) {
+                            close_run(run_rb, first + run_j, i - run_j, wgt);
+                            run_j = i; run_rb = rb;
+                        }
+                    };
+                    pos = 0; i = 1;
+                    while (i < nd.l) {
                         const uint32_t off = pos & 63;
                         const uint64_t x = w[pos >> 6] << off;
                         uint32_t z = x ? (uint32_t)__clzll((long long)x) : 64u;
                         z = min(min(z, 64u - off), min(nb - pos, nd.l - i));
                         if (z) {
-                            for (uint32_t t = 0; t < z; ++t) out[i + t] = 1u;
-                            i += z; pos += z; sum += z;
+                            pos += z;
+                            if (!dh.enabled) {
+                                for (uint32_t t = 0; t < z; ++t) out[i + t] = cur + 1u + t;
+                                i += z; cur += z;
+                            } else {
+                                while (z) {   // ids cur+1 .. cur+z at positions i .. i+z
+                                    boundary(i, cur + 1u);
+                                    uint32_t step = min(z, R - ((cur + 1u) & (R - 1u)));
+                                    if (rounds) step = min(step, 32u - (i & 31u));
+                                    for (uint32_t t = 0; t < step; ++t) out[i + t] = cur + 1u + t;
+                                    i += step; cur += step; z -= step;
+                                }
+                            }
                             continue;
                         }
-                        const uint32_t d = gamma_next(w, pos, nb);   // >= 2 (the next bit is a one), or 0 on a malformed stream
-                        out[i++] = d;
-                        sum += d;
-                        ++runs;
+                        cur += gamma_next(w, pos, nb);
+                        if (dh.enabled) boundary(i, cur);
+                        out[i++] = cur;
                     }
-                    if (i != nd.l || pos != nb) { atomicExch(err, 1); ok = false; }
-                    else if (sum > nd.last) { atomicExch(err, 2); ok = false; }
-                }
-                if (ok) {
-                    uint32_t cur = nd.last - (uint32_t)sum;
-                    if (cur < floor_id) atomicExch(err, 3);
-                    if (cur < win_lo) { atomicExch(err, 7); ok = false; }
-                    const uint32_t joined = has_par && cur == floor_id;
-                    own = ((2u * runs - joined) << 1) | joined;
-                    cur -= win_lo;
-                    out[0] = cur;
-                    if (!ok) {
-                        for (uint32_t i = 1; i < nd.l; ++i) out[i] = 0;
-                    } else if (!dh.enabled) {
-                        for (uint32_t i = 1; i < nd.l; ++i) { cur += out[i]; out[i] = cur; }
-                    } else {
-                        const uint32_t w = dh.W[p];
-                        const bool rounds = nd.l > kSmallL;   // longer lists are enumerated 32 positions at a time
-                        uint32_t run_j = 0, run_rb = cur >> dh.rb_shift;
-                        for (uint32_t i = 1; i < nd.l; ++i) {
-                            cur += out[i]; out[i] = cur;
-                            const uint32_t rb = cur >> dh.rb_shift;
-                            if (rb != run_rb || (rounds && (i & 31u) == 0)) {
-                                close_run(run_rb, first + run_j, i - run_j, w);
-                                run_j = i; run_rb = rb;
-                            }
-                        }
-                        close_run(run_rb, first + run_j, nd.l - run_j, w);
-                    }
+                    if (dh.enabled) close_run(run_rb, first + run_j, nd.l - run_j, wgt);
                 } else {
-                    for (uint32_t i = 0; i < nd.l; ++i) out[i] = 0;  // never chased: the call fails on the error flag
+                    for (uint32_t t = 0; t < nd.l; ++t) out[t] = 0;  // never chased: the call fails on the error flag
                 }
             }
         }
@@ -1106,6 +1126,11 @@ struct kdbx_ctx {
     void* comm = nullptr;
     int comm_nranks = 1, comm_rank = 0;
     DevBuf rs_block;
+    // dense table text (csvfmt.cuh): which rows of the matrix ctx->tri holds after a host-output all2all call
+    bool tri_rows_valid = false;
+    uint32_t tri_row_begin = 0, tri_row_end = 0;
+    DevBuf csv_text;
+    float ms_csv = 0.f;
     uint64_t* h_pinned = nullptr;          // small pinned read-back area
 
     // sparse delivery (sparse.cuh)
@@ -1466,7 +1491,8 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     bool hist_by_decoder = pl.T == 1 && nkeys <= kDecodeHistKeys && nkeys > 0 && cells > 0 && all_rows &&
                            num_parts == 1 && !(ctx->cfg.flags & KDBX_FLAG_CHUNKED_LISTS);
     if (cached && !M.resident) hist_by_decoder = false;
-    const bool diff_possible = hist_by_decoder && !(ctx->cfg.flags & KDBX_FLAG_ID_LISTS);
+    // (the boundary form flushes its tiles with 16-byte bulk reductions: the output must be aligned accordingly)
+    const bool diff_possible = hist_by_decoder && !(ctx->cfg.flags & KDBX_FLAG_ID_LISTS) && (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0;
     DecodeHist dh{};
     if (hist_by_decoder) {
         CK(ctx->blockhist.ensure((size_t)wide_grid * nkeys * 4 + 16));
@@ -1724,7 +1750,7 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         e.c = ctx->event();
         if (diff)
             k_scatter_diff<<<scatter_grid, pl.threads, smem, st>>>(ctx->units.as<Unit>(), ctx->uoff.as<uint32_t>() + nkeys, ctx->jobs.as<Job>(),
-                                                                   ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), d_out, pl.lo, pl.tile_cols, pl.rb_shift,
+                                                                   ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), d_out, pl.lo, pl.Nw, pl.tile_cols, pl.rb_shift,
                                                                    d_unit_counter);
         else
             k_scatter_add<<<scatter_grid, pl.threads, smem, st>>>(ctx->units.as<Unit>(), ctx->uoff.as<uint32_t>() + nkeys, ctx->jobs.as<Job>(),
@@ -1773,6 +1799,7 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
 
 #include "sparse.cuh"
 #include "comm.cuh"
+#include "csvfmt.cuh"
 #include "query.cuh"
 #include "build.cuh"
 
@@ -1877,7 +1904,7 @@ void kdbx_close(kdbx_ctx* ctx) {
                       &ctx->ucount, &ctx->uoff, &ctx->units, &ctx->counters, &ctx->blockhist, &ctx->tri, &ctx->rowupd, &ctx->first_id,
                       &ctx->sp_cnt, &ctx->sp_counts, &ctx->sp_rowptr, &ctx->sp_col, &ctx->sp_val, &ctx->slot_off, &ctx->slots,
                       &ctx->q_off, &ctx->q_kmers, &ctx->q_keys, &ctx->q_keys2, &ctx->q_runkeys, &ctx->q_runcnt, &ctx->q_out,
-                      &ctx->qx_alpha, &ctx->qx_seq, &ctx->qx_raw, &ctx->qx_sorted, &ctx->qx_count, &ctx->ownb, &ctx->nb, &ctx->boff, &ctx->rs_block})
+                      &ctx->qx_alpha, &ctx->qx_seq, &ctx->qx_raw, &ctx->qx_sorted, &ctx->qx_count, &ctx->ownb, &ctx->nb, &ctx->boff, &ctx->rs_block, &ctx->csv_text})
         b->release();
     if (ctx->comm) { nccl_api()->CommDestroy(static_cast<ncclComm_t>(ctx->comm)); ctx->comm = nullptr; }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -1979,7 +2006,9 @@ int kdbx_all2all_dense_rows(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end,
     CK(cudaSetDevice(ctx->device));
     CK(ctx->tri.ensure((cells + 1) * 4));
     kdbx_stats s{};
+    ctx->tri_rows_valid = false;
     if (int rc = all2all_rows_device(ctx, row_begin, row_end, ctx->tri.as<uint32_t>(), &s)) return rc;
+    ctx->tri_rows_valid = true; ctx->tri_row_begin = row_begin; ctx->tri_row_end = row_end;   // (kdbx_csv_dense_rows formats from here)
     cudaEvent_t a = ctx->event();
     if (cells) CK(cudaMemcpyAsync(out_rows, ctx->tri.p, cells * 4, cudaMemcpyDeviceToHost, ctx->stream));
     cudaEvent_t b = ctx->event();
@@ -2071,6 +2100,11 @@ int kdbx_all2all_dense_reduce_scatter(kdbx_ctx* ctx, uint32_t* out_block, uint64
     if (num_cells) *num_cells = count;
     if (stats) *stats = s;
     return KDBX_OK;
+}
+
+int kdbx_csv_dense_rows(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, char* text, uint64_t capacity, uint64_t* row_off, uint64_t* bytes) {
+    if (!ctx) return KDBX_ERR_ARG;
+    return csv_dense_rows(ctx, row_begin, row_end, text, capacity, row_off, bytes);
 }
 
 int kdbx_row_updates(kdbx_ctx* ctx, uint64_t* out) {

@@ -78,6 +78,7 @@ int all2all_sparse_impl(kdbx_ctx* ctx, const kdbx_filter* filter, kdbx_csr* out,
     if (!ctx->loaded) return ctx->fail(KDBX_ERR_STATE, "no patterns loaded (call kdbx_load_patterns first)");
     if (!out) return ctx->fail(KDBX_ERR_ARG, "kdbx_all2all_sparse: out is NULL");
     std::memset(out, 0, sizeof *out);
+    ctx->tri_rows_valid = false;   // row blocks pass through ctx->tri
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const uint32_t N = ctx->N;

@@ -27,6 +27,7 @@ struct Params {
     int gpu = -1;              // -gpu <ordinal> (ours)
     int num_gpus = 1;          // -gpus <n> (ours): row-block sharding over n devices
     bool host_build = false;   // build -host-build (ours): run the host builder explicitly (machines without a GPU)
+    bool host_csv = false;     // all2all -host-csv (ours): format the dense table on the host instead of on the device
     Alphabet alphabet = Alphabet::make(kNt);
     OutputFilters filters;
     std::string metric_name;

@@ -76,6 +76,53 @@ void write_all2all_csv(const std::string& path, const Trie& t, const uint32_t* t
     if (std::fclose(f) != 0) throw std::runtime_error("Cannot write output file " + path);
 }
 
+void write_all2all_csv_device(const std::string& path, const Trie& t, kdbx_ctx* ctx) {
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("Cannot open output file " + path);
+    const std::string head = table_header(t);
+    std::fwrite(head.data(), 1, head.size(), f);
+    const uint32_t N = t.num_samples();
+    // row blocks of at most ~256 MB of text; sizes first, then the text into a page-locked buffer
+    std::vector<uint64_t> off;
+    std::vector<char> line;
+    char* text = nullptr;
+    uint64_t cap = 0;
+    auto fail = [&](const std::string& what) { if (text) kdbx_host_free(text); std::fclose(f); throw std::runtime_error(what); };
+    uint32_t r0 = 0;
+    while (r0 < N) {
+        uint32_t r1 = r0;
+        uint64_t est = 0;
+        while (r1 < N && (r1 == r0 || est + (uint64_t)r1 * 11 <= ((uint64_t)256 << 20))) { est += (uint64_t)r1 * 11; ++r1; }
+        off.assign((size_t)(r1 - r0) + 1, 0);
+        uint64_t bytes = 0;
+        if (kdbx_csv_dense_rows(ctx, r0, r1, nullptr, 0, off.data(), &bytes) != KDBX_OK) fail(kdbx_last_error(ctx));
+        if (bytes > cap) {
+            if (text) kdbx_host_free(text);
+            text = nullptr;
+            void* v = nullptr;
+            if (kdbx_host_alloc(&v, bytes + 16) != KDBX_OK) fail("pinned allocation failed");
+            text = static_cast<char*>(v); cap = bytes;
+        }
+        if (kdbx_csv_dense_rows(ctx, r0, r1, text, cap, off.data(), &bytes) != KDBX_OK) fail(kdbx_last_error(ctx));
+        for (uint32_t s = r0; s < r1; ++s) {
+            const std::string& name = t.sample_names[s];
+            const uint64_t b = off[s - r0], e = off[s - r0 + 1];
+            line.resize(name.size() + 32 + (size_t)(e - b));
+            char* p = line.data();
+            std::memcpy(p, name.data(), name.size()); p += name.size();
+            *p++ = ',';
+            p = put_u64(p, t.sample_kmers[s]);
+            *p++ = ',';
+            if (e > b) { std::memcpy(p, text + b, (size_t)(e - b)); p += e - b; }
+            *p++ = '\n';
+            std::fwrite(line.data(), 1, (size_t)(p - line.data()), f);
+        }
+        r0 = r1;
+    }
+    if (text) kdbx_host_free(text);
+    if (std::fclose(f) != 0) throw std::runtime_error("Cannot write output file " + path);
+}
+
 // all2all-sp table (src/console_all2all_sparse.cpp:50-98): same headers, rows of `col+1:val,`
 // (SparseMatrix::saveRowSparse, src/array.h:625-637).  `filters` (may be NULL) are applied again
 // here for the bounds the device did not evaluate.

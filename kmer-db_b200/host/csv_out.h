@@ -12,6 +12,9 @@ namespace kdbx {
 
 std::string table_header(const Trie& t);
 void write_all2all_csv(const std::string& path, const Trie& t, const uint32_t* tri, bool sparse, const OutputFilters* filters = nullptr);
+// The dense table with the cells' text formatted on the device (kdbx_csv_dense_rows) from the matrix the context's last
+// kdbx_all2all_dense call left in HBM; the host adds names, k-mer counts and newlines.  Same bytes as write_all2all_csv.
+void write_all2all_csv_device(const std::string& path, const Trie& t, kdbx_ctx* ctx);
 uint64_t write_sparse_csv(const std::string& path, const Trie& t, const kdbx_csr& m, const OutputFilters* filters);
 
 class QueryTableWriter {

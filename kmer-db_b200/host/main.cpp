@@ -135,7 +135,10 @@ void run_all2all(const Params& p) {
     print_stats_json(calculator.last_stats(), dt);
     std::cerr << "Storing matrix of common k-mers in " << p.files[1] << "...";
     t0 = now();
-    write_all2all_csv(p.files[1], db, matrix.data(), p.sparse_out, p.sparse_out ? &p.filters : nullptr);
+    // the dense table's numbers are formatted on the device, from the matrix the call above left there (one GPU; the
+    // -sparse table and the multi-GPU blocks go through the host emitter)
+    if (!p.sparse_out && p.num_gpus <= 1 && !p.host_csv) write_all2all_csv_device(p.files[1], db, calculator.context());
+    else write_all2all_csv(p.files[1], db, matrix.data(), p.sparse_out, p.sparse_out ? &p.filters : nullptr);
     std::cerr << "OK (" << now() - t0 << " seconds)" << std::endl;
 }
 

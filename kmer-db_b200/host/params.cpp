@@ -79,6 +79,7 @@ bool parse_params(int argc, char** argv, Params& p) {
     if (p.num_reader_threads <= 0) p.num_reader_threads = std::max(1, p.num_threads / 2);
     find_option(a, "-gpu", p.gpu);
     find_option(a, "-gpus", p.num_gpus);
+    p.host_csv = find_switch(a, "-host-csv");
     if (p.num_gpus < 1) p.num_gpus = 1;
 
     if (p.mode == "build") {

@@ -287,6 +287,7 @@ public:
         check(kdbx_new2all_sequences(ctx_, &bp, symbols, q_off.data(), nq, similarities.data(), unique_kmers.data(), &stats_));
     }
     const kdbx_stats& last_stats() const { return stats_; }
+    kdbx_ctx* context() const { return ctx_; }   // for the emitters that format on the device (csv_out.h)
 
 private:
     // the -min/-max bounds whose arithmetic is exactly reproducible on the device (include/kdbx.h)

@@ -109,7 +109,7 @@ class Totals(C.Structure):
 # every symbol include/kdbx.h declares (tests check that the library exports all of them)
 KDBX_SYMBOLS = ["kdbx_abi_version", "kdbx_device_count", "kdbx_open", "kdbx_close", "kdbx_last_error",
                 "kdbx_host_alloc", "kdbx_host_free", "kdbx_load_patterns", "kdbx_set_sample_window", "kdbx_row_updates", "kdbx_all2all_dense",
-                "kdbx_all2all_dense_rows", "kdbx_all2all_dense_rows_device", "kdbx_all2all_dense_part_device", "kdbx_all2all_sparse", "kdbx_all2all_sparse_rows", "kdbx_free_csr",
+                "kdbx_all2all_dense_rows", "kdbx_all2all_dense_rows_device", "kdbx_all2all_dense_part_device", "kdbx_all2all_sparse", "kdbx_all2all_sparse_rows", "kdbx_csv_dense_rows", "kdbx_free_csr",
                 "kdbx_load_hashtables", "kdbx_new2all_batch", "kdbx_debug_fetch", "kdbx_comm_unique_id", "kdbx_comm_init_rank",
                 "kdbx_comm_init_all", "kdbx_comm_destroy", "kdbx_all2all_dense_reduce_scatter_device", "kdbx_all2all_dense_reduce_scatter",
                 "kdbx_builder_open", "kdbx_builder_close", "kdbx_builder_adopt", "kdbx_builder_add_sequence", "kdbx_builder_add_kmers",
@@ -153,6 +153,7 @@ def load():
     k.kdbx_all2all_dense_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, P(Stats)]
     k.kdbx_all2all_dense_rows_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, P(Stats)]
     k.kdbx_all2all_dense_part_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, P(Stats)]
+    k.kdbx_csv_dense_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, P(C.c_uint64)]
     k.kdbx_comm_unique_id.argtypes = [C.c_void_p]
     k.kdbx_comm_init_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     k.kdbx_comm_init_all.argtypes = [P(C.c_void_p), C.c_int]
@@ -492,6 +493,16 @@ class Context:
         st = Stats()
         self._check(self._k.kdbx_all2all_dense_part_device(self._p, part, num_parts, C.c_void_p(device_ptr), C.byref(st)))
         return st
+
+    def csv_dense_rows(self, row_begin, row_end):
+        """(text bytes, row offsets) of the dense table's cells for the rows of the last host-output all2all call."""
+        rows = row_end - row_begin
+        off = np.zeros(rows + 1, np.uint64)
+        total = C.c_uint64(0)
+        self._check(self._k.kdbx_csv_dense_rows(self._p, row_begin, row_end, None, 0, off.ctypes.data, C.byref(total)))
+        text = np.zeros(max(1, total.value), np.uint8)
+        self._check(self._k.kdbx_csv_dense_rows(self._p, row_begin, row_end, text.ctypes.data, total.value, off.ctypes.data, C.byref(total)))
+        return text[:total.value].tobytes(), off
 
     # ---- several GPUs (kdbx.h: kdbx_comm_*) ----
     @staticmethod

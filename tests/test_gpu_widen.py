@@ -226,3 +226,33 @@ def test_cli_multi_gpu_flag(cli, libs, ref_fixtures, golden_dbs, tmp_path):
     # all2all-sp over row blocks on several devices, rows concatenated: the reference's sparse golden file
     cli(ref_fixtures, "all2all-sp", "-gpus", str(min(n, 4)), golden_dbs["virus.k18"][0], tmp_path / "xs.csv")
     assert ou.read_bytes(tmp_path / "xs.csv") == ou.read_bytes(golden_dbs["virus.k18"][2])
+
+
+def test_dense_csv_formatted_on_the_device(libs, oracle, cli, golden_dbs, tmp_path):
+    """kdbx_csv_dense_rows: the cells' decimal text from the matrix in HBM equals the host formatter's, for values of
+    every length (0 .. 2^32-1), for row sub-ranges, and through the CLI (default) against -host-csv and the golden file."""
+    rng = np.random.default_rng(31)
+    N = 333
+    a, _ = ou.random_trie(rng, N, 3000, max_local=30, big_weights=True)
+    want, _ = ou.oracle_all2all(oracle, N, a)
+    with libs.Context(device=0) as c:
+        v, keep = libs.view_from_arrays(N, a["num_kmers"], a["parent_id"], a["n"], a["l"], a["last"], a["bits"], a["payload_off"], a["payload"])
+        c.load_patterns(v, keep)
+        tri, _ = c.all2all_dense()
+        assert np.array_equal(tri, want)
+        for r0, r1 in ((0, N), (0, 1), (1, 2), (17, 200), (N - 1, N)):
+            text, off = c.csv_dense_rows(r0, r1)
+            for s in range(r0, r1):
+                row = want[ou.tri_cells(s):ou.tri_cells(s) + s]
+                expect = "".join(f"{int(x)}," for x in row).encode()
+                assert text[int(off[s - r0]):int(off[s - r0 + 1])] == expect, (r0, r1, s)
+        assert {len(str(int(x))) for x in want} >= {1, 10}   # the input does hold one- and ten-digit numbers
+        rows, _ = c.all2all_dense_rows(100, 300)
+        text, off = c.csv_dense_rows(150, 160)
+        assert text[:int(off[1])] == "".join(f"{int(x)}," for x in want[ou.tri_cells(150):ou.tri_cells(150) + 150]).encode()
+        with pytest.raises(libs.KdbxError, match="not in the resident block"):
+            c.csv_dense_rows(50, 120)
+    db, dense, _ = golden_dbs["virus.k18"]
+    cli(tmp_path, "all2all", db, tmp_path / "dev.csv")
+    cli(tmp_path, "all2all", "-host-csv", db, tmp_path / "host.csv")
+    assert ou.read_bytes(tmp_path / "dev.csv") == ou.read_bytes(dense) == ou.read_bytes(tmp_path / "host.csv")
