@@ -129,6 +129,14 @@ __global__ void k_build_nodes(uint64_t P, const int64_t* __restrict__ parent, co
 // patterns are radix-sorted by n (descending) and every level pushes its finished sums to the
 // parents in one launch.  (A per-node walk to the root with atomics was 80 % of the prepare
 // stage: the ancestors near the roots are hit by millions of serialized L2 atomics.)
+// the 32-bit mirrors of parent_id / num_kmers (kdbx_trie_view) back to the 64-bit arrays the kernels read
+__global__ void k_widen_headers(uint64_t P, const int32_t* __restrict__ parent32, const uint32_t* __restrict__ num_kmers32,
+                                int64_t* __restrict__ parent, int64_t* __restrict__ num_kmers) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    parent[p] = (int64_t)parent32[p];
+    num_kmers[p] = (int64_t)num_kmers32[p];
+}
 __global__ void k_iota(uint64_t P, uint32_t* __restrict__ out) {
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < P) out[p] = (uint32_t)p;
@@ -263,79 +271,59 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
                 const uint64_t po = poff[p];
                 bool ok = po + ((uint64_t)(nb + 127u) / 128u) * 2u <= payload_words;
                 if (!ok) atomicExch(err, 5);
-                const uint64_t* w = payload + po;
-                // The stream holds the deltas in append order and only the LAST id is stored, so the bits are walked twice:
-                // once for the sum of the deltas (no stores; a run of zero bits = that many deltas of 1 is taken by one
-                // clz), once to write the ids.  Nothing is parked in between: the second walk writes final ids, and a run
-                // of consecutive ids is written by a loop that does nothing but store (the row-block / 32-position
-                // boundaries of the job count are stepped over arithmetically instead of being tested per id).
-                uint32_t pos = 0, runs = 1, i = 1;
+                uint32_t pos = 0, runs = 1;
                 uint64_t sum = 0;
                 if (ok) {
+                    const uint64_t* w = payload + po;
+                    uint32_t i = 1;
                     while (i < nd.l && pos < nb) {
-                        const uint32_t off = pos & 63;
-                        const uint64_t x = w[pos >> 6] << off;
-                        uint32_t z = x ? (uint32_t)__clzll((long long)x) : 64u;
-                        z = min(min(z, 64u - off), min(nb - pos, nd.l - i));
-                        if (z) { i += z; pos += z; sum += z; continue; }
-                        const uint32_t d = gamma_next(w, pos, nb);   // >= 2 (the next bit is a one), or 0 on a malformed stream
-                        ++i; sum += d; ++runs;
-                    }
-                    if (i != nd.l || pos != nb) { atomicExch(err, 1); ok = false; }
-                    else if (sum > nd.last) { atomicExch(err, 2); ok = false; }
-                }
-                uint32_t cur = 0;
-                if (ok) {
-                    cur = nd.last - (uint32_t)sum;
-                    if (cur < floor_id) atomicExch(err, 3);
-                    if (cur < win_lo) { atomicExch(err, 7); ok = false; }
-                    const uint32_t joined = has_par && cur == floor_id;
-                    own = ((2u * runs - joined) << 1) | joined;
-                }
-                if (ok) {
-                    cur -= win_lo;
-                    out[0] = cur;
-                    const uint32_t wgt = dh.enabled ? dh.W[p] : 0u;
-                    const bool rounds = nd.l > kSmallL;   // longer lists are enumerated 32 positions at a time
-                    const uint32_t R = 1u << dh.rb_shift;
-                    uint32_t run_j = 0, run_rb = cur >> dh.rb_shift;
-                    // a job run ends before position i (id `idr`) when the row block changes or a 32-position round begins
-                    auto boundary = [&](uint32_t i, uint32_t idr) {
-                        const uint32_t rb = idr >> dh.rb_shift;
-                        if (rb != run_rb || (rounds && (i & 31u) == 0)) {
-                            close_run(run_rb, first + run_j, i - run_j, wgt);
-                            run_j = i; run_rb = rb;
-                        }
-                    };
-                    pos = 0; i = 1;
-                    while (i < nd.l) {
+                        // a delta of 1 is the single bit 0 (consecutive sample ids): take a whole run of
+                        // zero bits at once — most of a cluster's lists are such runs
                         const uint32_t off = pos & 63;
                         const uint64_t x = w[pos >> 6] << off;
                         uint32_t z = x ? (uint32_t)__clzll((long long)x) : 64u;
                         z = min(min(z, 64u - off), min(nb - pos, nd.l - i));
                         if (z) {
-                            pos += z;
-                            if (!dh.enabled) {
-                                for (uint32_t t = 0; t < z; ++t) out[i + t] = cur + 1u + t;
-                                i += z; cur += z;
-                            } else {
-                                while (z) {   // ids cur+1 .. cur+z at positions i .. i+z
-                                    boundary(i, cur + 1u);
-                                    uint32_t step = min(z, R - ((cur + 1u) & (R - 1u)));
-                                    if (rounds) step = min(step, 32u - (i & 31u));
-                                    for (uint32_t t = 0; t < step; ++t) out[i + t] = cur + 1u + t;
-                                    i += step; cur += step; z -= step;
-                                }
-                            }
+                            for (uint32_t t = 0; t < z; ++t) out[i + t] = 1u;
+                            i += z; pos += z; sum += z;
                             continue;
                         }
-                        cur += gamma_next(w, pos, nb);
-                        if (dh.enabled) boundary(i, cur);
-                        out[i++] = cur;
+                        const uint32_t d = gamma_next(w, pos, nb);   // >= 2 (the next bit is a one), or 0 on a malformed stream
+                        out[i++] = d;
+                        sum += d;
+                        ++runs;
                     }
-                    if (dh.enabled) close_run(run_rb, first + run_j, nd.l - run_j, wgt);
+                    if (i != nd.l || pos != nb) { atomicExch(err, 1); ok = false; }
+                    else if (sum > nd.last) { atomicExch(err, 2); ok = false; }
+                }
+                if (ok) {
+                    uint32_t cur = nd.last - (uint32_t)sum;
+                    if (cur < floor_id) atomicExch(err, 3);
+                    if (cur < win_lo) { atomicExch(err, 7); ok = false; }
+                    const uint32_t joined = has_par && cur == floor_id;
+                    own = ((2u * runs - joined) << 1) | joined;
+                    cur -= win_lo;
+                    out[0] = cur;
+                    if (!ok) {
+                        for (uint32_t i = 1; i < nd.l; ++i) out[i] = 0;
+                    } else if (!dh.enabled) {
+                        for (uint32_t i = 1; i < nd.l; ++i) { cur += out[i]; out[i] = cur; }
+                    } else {
+                        const uint32_t w = dh.W[p];
+                        const bool rounds = nd.l > kSmallL;   // longer lists are enumerated 32 positions at a time
+                        uint32_t run_j = 0, run_rb = cur >> dh.rb_shift;
+                        for (uint32_t i = 1; i < nd.l; ++i) {
+                            cur += out[i]; out[i] = cur;
+                            const uint32_t rb = cur >> dh.rb_shift;
+                            if (rb != run_rb || (rounds && (i & 31u) == 0)) {
+                                close_run(run_rb, first + run_j, i - run_j, w);
+                                run_j = i; run_rb = rb;
+                            }
+                        }
+                        close_run(run_rb, first + run_j, nd.l - run_j, w);
+                    }
                 } else {
-                    for (uint32_t t = 0; t < nd.l; ++t) out[t] = 0;  // never chased: the call fails on the error flag
+                    for (uint32_t i = 0; i < nd.l; ++i) out[i] = 0;  // never chased: the call fails on the error flag
                 }
             }
         }
@@ -1082,7 +1070,7 @@ struct kdbx_ctx {
     uint64_t payload_words = 0;
     bool loaded = false;
     bool dense_payload = false;
-    DevBuf num_kmers, parent, n, l, last, bits, poff, payload;
+    DevBuf num_kmers, parent, n, l, last, bits, poff, payload, hdr32;
     float ms_upload = 0.f;
 
     // prepared
@@ -1904,7 +1892,7 @@ void kdbx_close(kdbx_ctx* ctx) {
                       &ctx->ucount, &ctx->uoff, &ctx->units, &ctx->counters, &ctx->blockhist, &ctx->tri, &ctx->rowupd, &ctx->first_id,
                       &ctx->sp_cnt, &ctx->sp_counts, &ctx->sp_rowptr, &ctx->sp_col, &ctx->sp_val, &ctx->slot_off, &ctx->slots,
                       &ctx->q_off, &ctx->q_kmers, &ctx->q_keys, &ctx->q_keys2, &ctx->q_runkeys, &ctx->q_runcnt, &ctx->q_out,
-                      &ctx->qx_alpha, &ctx->qx_seq, &ctx->qx_raw, &ctx->qx_sorted, &ctx->qx_count, &ctx->ownb, &ctx->nb, &ctx->boff, &ctx->rs_block, &ctx->csv_text})
+                      &ctx->qx_alpha, &ctx->qx_seq, &ctx->qx_raw, &ctx->qx_sorted, &ctx->qx_count, &ctx->ownb, &ctx->nb, &ctx->boff, &ctx->rs_block, &ctx->csv_text, &ctx->hdr32})
         b->release();
     if (ctx->comm) { nccl_api()->CommDestroy(static_cast<ncclComm_t>(ctx->comm)); ctx->comm = nullptr; }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -1950,8 +1938,17 @@ int kdbx_load_patterns(kdbx_ctx* ctx, const kdbx_trie_view* v) {
     CK(cudaMemcpyAsync(ctx->l.p, v->num_local_samples, P * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->last.p, v->last_sample_id, P * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->bits.p, v->num_bits, P * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->parent.p, v->parent_id, P * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->num_kmers.p, v->num_kmers, P * 8, cudaMemcpyHostToDevice, st));
+    if (v->parent_id32 && v->num_kmers32) {   // 8 instead of 16 bytes per pattern over PCIe, widened on the device
+        CK(ctx->hdr32.ensure(P * 8));
+        CK(cudaMemcpyAsync(ctx->hdr32.p, v->parent_id32, P * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->hdr32.as<uint32_t>() + P, v->num_kmers32, P * 4, cudaMemcpyHostToDevice, st));
+        k_widen_headers<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(P, ctx->hdr32.as<int32_t>(), ctx->hdr32.as<uint32_t>() + P,
+                                                                      ctx->parent.as<int64_t>(), ctx->num_kmers.as<int64_t>());
+        CK(cudaGetLastError());
+    } else {
+        CK(cudaMemcpyAsync(ctx->parent.p, v->parent_id, P * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->num_kmers.p, v->num_kmers, P * 8, cudaMemcpyHostToDevice, st));
+    }
     ctx->dense_payload = (v->payload_off == nullptr);
     if (!ctx->dense_payload) {
         CK(ctx->poff.ensure((P + 1) * 8));

@@ -25,6 +25,7 @@ DbBuilder::~DbBuilder() {
 
 void DbBuilder::adopt(Trie&& db) {
     if (db.tables.empty()) throw std::runtime_error("build -extend needs a database with k-mer tables");
+    db.drop_compact();   // the patterns change from here on
     for (Pattern& p : pats_) std::free(p.data);
     hdr_ = db.hdr;
     names_ = std::move(db.sample_names);

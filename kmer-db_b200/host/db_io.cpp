@@ -160,6 +160,7 @@ void read_db(const std::string& path, Trie& t, bool with_tables) {
             ++pid;
         }
     }
+    t.build_compact();
 }
 
 void write_db(const std::string& path, const Trie& t) {

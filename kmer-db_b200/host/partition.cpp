@@ -147,6 +147,7 @@ void TriePartitioner::extract(uint32_t part, Trie& dst, uint64_t* owned_updates,
         const uint64_t w = Trie::payload_words_for_bits(src.bits[p]);
         if (w) std::memcpy(dst.payload.data() + dst.payload_off[o], src.payload.data() + src.payload_off[p], w * 8);
     }
+    dst.build_compact();
     if (owned_updates) *owned_updates = U;
     if (window) { window[0] = hi ? lo : 0; window[1] = hi; }
 }

@@ -161,12 +161,28 @@ struct Trie {
     Buf<uint32_t> bits;  // num_bits
     Buf<uint64_t> payload_off;  // word offset into payload
     Buf<uint64_t> payload;      // Elias-gamma words, ceil(bits/128)*2 words per pattern
+    // 32-bit mirrors of parent_id / num_kmers for the upload (kdbx_trie_view::parent_id32 / num_kmers32): 24 instead of 40
+    // bytes of header per pattern over PCIe.  Built by build_compact() where a trie is finished (reader, partitioner);
+    // handed out by view() only while they still match the 64-bit arrays in length.
+    Buf<int32_t> parent32;
+    Buf<uint32_t> num_kmers32;
 
     explicit Trie(bool pinned = false) {
         num_kmers.set_pinned(pinned); parent_id.set_pinned(pinned); n.set_pinned(pinned);
         l.set_pinned(pinned); last.set_pinned(pinned); bits.set_pinned(pinned);
         payload_off.set_pinned(pinned); payload.set_pinned(pinned);
+        parent32.set_pinned(pinned); num_kmers32.set_pinned(pinned);
     }
+    // (re)builds the 32-bit mirrors; leaves them empty when a value does not fit
+    void build_compact() {
+        const uint64_t P = num_patterns();
+        parent32.clear(); num_kmers32.clear();
+        for (uint64_t p = 0; p < P; ++p)
+            if (num_kmers[p] < 0 || num_kmers[p] > 0xFFFFFFFFll || parent_id[p] < -1 || parent_id[p] > 0x7FFFFFFFll) return;
+        parent32.resize(P); num_kmers32.resize(P);
+        for (uint64_t p = 0; p < P; ++p) { parent32[p] = (int32_t)parent_id[p]; num_kmers32[p] = (uint32_t)num_kmers[p]; }
+    }
+    void drop_compact() { parent32.clear(); num_kmers32.clear(); }
 
     uint64_t num_patterns() const { return n.size(); }
     uint32_t num_samples() const { return (uint32_t)sample_names.size(); }
@@ -188,6 +204,9 @@ struct Trie {
         v.payload_off = payload_off.data();
         v.payload = payload.data();
         v.payload_words = payload.size();
+        if (parent32.size() == num_patterns() && num_kmers32.size() == num_patterns() && num_patterns()) {
+            v.parent_id32 = parent32.data(); v.num_kmers32 = num_kmers32.data();
+        }
         return v;
     }
 

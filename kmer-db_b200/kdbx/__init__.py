@@ -35,7 +35,8 @@ class TrieView(C.Structure):
     _fields_ = [("num_patterns", C.c_uint64), ("num_samples", C.c_uint32), ("_pad", C.c_uint32),
                 ("num_kmers", C.c_void_p), ("parent_id", C.c_void_p), ("num_samples_full", C.c_void_p),
                 ("num_local_samples", C.c_void_p), ("last_sample_id", C.c_void_p), ("num_bits", C.c_void_p),
-                ("payload_off", C.c_void_p), ("payload", C.c_void_p), ("payload_words", C.c_uint64)]
+                ("payload_off", C.c_void_p), ("payload", C.c_void_p), ("payload_words", C.c_uint64),
+                ("parent_id32", C.c_void_p), ("num_kmers32", C.c_void_p)]
 
 
 class Stats(C.Structure):

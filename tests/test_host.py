@@ -264,3 +264,58 @@ def test_column_window_arithmetic():
             for c in rng.integers(0, hi, size=5):
                 t = (hi - 1 - int(c)) // tc
                 assert t < T and max(0, hi - (t + 1) * tc) <= c < hi - t * tc
+
+
+def test_reader_builds_32_bit_header_mirrors(libs, golden_dbs):
+    """kdbx_trie_view::parent_id32 / num_kmers32: the reader and the partitioner keep 32-bit mirrors of the two 64-bit
+    header arrays (24 instead of 40 bytes per pattern to upload); they must equal the 64-bit arrays."""
+    import ctypes as C
+    t = libs.Trie.read_db(golden_dbs["virus.k18"][0])
+    v = t.view()
+    P = int(v.num_patterns)
+    assert v.parent_id32 and v.num_kmers32
+    a = t.arrays()
+    p32 = np.ctypeslib.as_array(C.cast(v.parent_id32, C.POINTER(C.c_int32)), (P,))
+    k32 = np.ctypeslib.as_array(C.cast(v.num_kmers32, C.POINTER(C.c_uint32)), (P,))
+    assert np.array_equal(p32.astype(np.int64), a["parent_id"]) and np.array_equal(k32.astype(np.int64), a["num_kmers"])
+    for part, _, _ in t.partition_all(3):
+        pv = part.view()
+        pa = part.arrays()
+        q32 = np.ctypeslib.as_array(C.cast(pv.parent_id32, C.POINTER(C.c_int32)), (int(pv.num_patterns),))
+        assert np.array_equal(q32.astype(np.int64), pa["parent_id"])
+
+
+def test_pattern_level_generator_matches_a_fasta_level_build_of_the_same_model(libs, tmp_path):
+    """host/synth.cpp simulates `build` on k-mer runs instead of sequences.  The same model at the
+    FASTA level — first genome of a cluster random, every later one a copy of a uniformly chosen earlier member with
+    i.i.d. substitutions — pushed through the real ingest + builder must give the same database STATISTICS.  The two
+    draw different random copy trees, so the comparison is between means over seeds (within 12 %; the number of distinct
+    k-mers, which does not depend on the tree, within 3 %)."""
+    def fasta_db(N, C, L, mu, seed, k=18):
+        rng = np.random.default_rng(seed)
+        acgt = np.frombuffer(b"ACGT", np.uint8)
+        members = [[] for _ in range(C)]
+        path = tmp_path / f"s{seed}.fa"
+        with open(path, "w") as f:
+            for g in range(N):
+                c = (g * C) // N
+                if not members[c]:
+                    code = rng.integers(0, 4, size=L + k - 1)
+                else:
+                    code = members[c][int(rng.integers(0, len(members[c])))].copy()
+                    pos = np.flatnonzero(rng.random(L + k - 1) < mu)
+                    code[pos] = (code[pos] + rng.integers(1, 4, size=pos.size)) % 4   # a different base
+                members[c].append(code)
+                f.write(f">g{g:04d}\n{acgt[code].tobytes().decode()}\n")
+        return libs.Trie.build(libs.load_samples(path, k=k, multisample=True, threads=4), k=k, threads=4)
+    N, C, L, seeds = 64, 2, 20000, range(1, 17)   # per-seed spread: 3 % (patterns) .. 7 % (updates); 16 seeds -> ~2 % on the means
+    fields = ("num_patterns", "sum_n", "sum_l", "updates", "kmers_count")
+    fa, sy = dict.fromkeys(fields, 0), dict.fromkeys(fields, 0)
+    for seed in seeds:
+        a = fasta_db(N, C, L, 0.005, 100 + seed).totals()
+        b = libs.Trie.synth(num_samples=N, num_clusters=C, genome_kmers=L, mutation_rate=0.005, seed=seed).totals()
+        for f in fields:
+            fa[f] += getattr(a, f); sy[f] += getattr(b, f)
+    for f in fields:
+        assert abs(sy[f] - fa[f]) <= 0.12 * fa[f], (f, fa[f] / len(seeds), sy[f] / len(seeds))
+    assert abs(sy["kmers_count"] - fa["kmers_count"]) <= 0.03 * fa["kmers_count"]
