@@ -96,110 +96,70 @@ __global__ void k_expand_level_diff(uint32_t count, const uint32_t* __restrict__
 }
 
 // ---- job enumeration ------------------------------------------------------------------------------------------
-// Same jobs as the id form with one column window (a pattern x a block of matrix rows; lists longer than kSmallL
-// cut every 32 positions), described by boundary positions: the rows are the local ids loc[rows .. rows + k), all
-// of them receive the boundaries [0, c0) (those below the first row) and row j those of [c0, c0 + ext) that lie
-// below its id.  Job fields: off/off_hi = start of B(p) (40 bits), a = low 32 bits of the row offset in loc,
-// b = c0, A0 = ext | row offset high bits << 8, k, w.
-template <class Emit>
-__device__ __forceinline__ void enumerate_jobs_diff(uint64_t lo, uint64_t hi, uint32_t warp, uint32_t nwarps,
-                                                    const Node* __restrict__ nodes, const uint64_t* __restrict__ boff,
-                                                    const uint32_t* __restrict__ nb, const uint32_t* __restrict__ ownb,
-                                                    const uint32_t* __restrict__ W, const uint32_t* __restrict__ loc, uint32_t rb_shift,
-                                                    uint32_t lane, unsigned long long& updates, unsigned long long& physical, Emit emit) {
-    auto make_job = [&](uint64_t base, uint64_t rows, uint32_t c0, uint32_t ext, uint32_t k, uint32_t w) {
-        Job jb;
-        jb.off = (uint32_t)base; jb.off_hi = (uint32_t)(base >> 32);
-        jb.a = (uint32_t)rows; jb.b = c0; jb.A0 = ext | ((uint32_t)(rows >> 32) << 8);
-        jb.k = k; jb.w = w; jb.pad = 0;
-        return jb;
-    };
-    for (uint64_t b = lo + (uint64_t)warp * 32; b < hi; b += (uint64_t)nwarps * 32) {
-        const uint64_t p = b + lane;
-        Node nd; nd.parent = -1; nd.n = 0; nd.l = 0; nd.last = 0; nd.loff = 0; nd.up2 = nd.up3 = -1;
-        uint32_t w = 0, own = 0, cnt0 = 0;
-        uint64_t base = 0;
-        if (p < hi) {
-            nd = nodes[p];
-            if (nd.l) { w = W[p]; base = boff[p]; own = ownb[p]; cnt0 = nb[p] - (own >> 1); }   // boundaries below the first local id
-        }
-        // cnt_j = entries of B(p) below the local id L[j] = cnt0 + sum over i < j of (L[i] opens a run) + (a run closes
-        // after L[i]): the open L[i] and the close L[i] + 1 (present iff L[i+1] != L[i] + 1) both lie below L[j].
-        if (nd.l && nd.l <= kSmallL) {
-            const uint32_t first = nd.n - nd.l;
-            const uint32_t* rows = loc + nd.loff;
-            uint32_t cnt = cnt0, prev = 0, run_j = 0, run_rb = 0, run_c0 = 0, run_cl = 0;
-            bool starts_prev = false;
-            for (uint32_t j = 0; j < nd.l; ++j) {
-                const uint32_t row = rows[j];
-                const bool gap = j != 0 && prev + 1u != row;
-                if (j) cnt += (uint32_t)starts_prev + (uint32_t)gap;
-                const uint32_t rb = row >> rb_shift;
-                if (j == 0) { run_rb = rb; run_c0 = cnt; }
-                else if (rb != run_rb) {
-                    const uint32_t k = j - run_j, i = first + run_j;
-                    const unsigned long long upd = (unsigned long long)k * i + k * (k - 1u) / 2u;
-                    if (w != 0 && upd != 0) emit(run_rb, make_job(base, nd.loff + run_j, run_c0, run_cl - run_c0, k, w), upd);
-                    run_j = j; run_rb = rb; run_c0 = cnt;
-                }
-                run_cl = cnt;
-                updates += first + j; physical += cnt;
-                starts_prev = j == 0 ? !(own & 1u) : gap;
-                prev = row;
+// The jobs of the headline path (one column window, all rows; their number per key was counted by the decoder): a
+// pattern x a block of matrix rows = the run of the pattern's local ids that fall into that block.  One lane walks
+// one pattern's local ids from first to last, whatever their number (a warp-cooperative walk of long lists, 32
+// positions at a time, cost four times the instructions: scans and ballots per round).
+//
+// Boundary form: the rows are the local ids loc[rows .. rows + k); all of them receive the boundaries [0, c0) (those
+// below the first row) and row j those of [c0, c0 + ext) that lie below its id.  Job fields: off/off_hi = start of
+// B(p) (40 bits), a = low 32 bits of the row offset in loc, b = c0, A0 = ext | row offset high bits << 8, k, w.
+// cnt_j = entries of B(p) below the local id L[j] = cnt0 + sum over i < j of (L[i] opens a run) + (a run closes
+// after L[i]): the open L[i] and the close L[i] + 1 (present iff L[i+1] != L[i] + 1) both lie below L[j].
+// Id form (same walk, K = false): off/off_hi = start of the full list, a = 0, b = n, A0 = position of the first row.
+template <bool kBoundary, class Emit>
+__device__ __forceinline__ void walk_runs(uint64_t lo, uint64_t hi, const Node* __restrict__ nodes, const uint64_t* __restrict__ list_off,
+                                          const uint32_t* __restrict__ nb, const uint32_t* __restrict__ ownb, const uint32_t* __restrict__ W,
+                                          const uint32_t* __restrict__ loc, uint32_t rb_shift, uint64_t stride, uint64_t first_p,
+                                          unsigned long long& physical, Emit emit) {
+    for (uint64_t p = lo + first_p; p < hi; p += stride) {
+        const Node nd = nodes[p];
+        if (nd.l == 0) continue;
+        const uint32_t w = W[p];
+        const uint64_t base = list_off[p];
+        uint32_t own = 0, cnt = 0;
+        if (kBoundary) { own = ownb[p]; cnt = nb[p] - (own >> 1); }   // boundaries below the first local id
+        const uint32_t first = nd.n - nd.l;
+        const uint32_t* rows = loc + nd.loff;
+        auto make_job = [&](uint32_t run_j, uint32_t k, uint32_t c0, uint32_t ext) {
+            Job jb;
+            jb.off = (uint32_t)base; jb.off_hi = (uint32_t)(base >> 32);
+            if (kBoundary) {
+                const uint64_t r = nd.loff + run_j;
+                jb.a = (uint32_t)r; jb.b = c0; jb.A0 = ext | ((uint32_t)(r >> 32) << 8);
+            } else {
+                jb.a = 0; jb.b = nd.n; jb.A0 = first + run_j;
             }
-            const uint32_t k = nd.l - run_j, i = first + run_j;
-            const unsigned long long upd = (unsigned long long)k * i + k * (k - 1u) / 2u;
-            if (w != 0 && upd != 0) emit(run_rb, make_job(base, nd.loff + run_j, run_c0, run_cl - run_c0, k, w), upd);
-        }
-        uint32_t big = __ballot_sync(0xffffffffu, nd.l > kSmallL);
-        while (big) {
-            const int src = __ffs((int)big) - 1;
-            big &= big - 1;
-            const uint32_t bn = __shfl_sync(0xffffffffu, nd.n, src), bl = __shfl_sync(0xffffffffu, nd.l, src);
-            const uint64_t bloff = __shfl_sync(0xffffffffu, nd.loff, src);
-            const uint32_t bw = __shfl_sync(0xffffffffu, w, src), bown = __shfl_sync(0xffffffffu, own, src);
-            const uint64_t bbase = __shfl_sync(0xffffffffu, base, src);
-            uint32_t carry = __shfl_sync(0xffffffffu, cnt0, src);   // boundaries below the first row of this round
-            const uint32_t first = bn - bl;
-            const uint32_t* rows = loc + bloff;
-            for (uint32_t r0 = 0; r0 < bl; r0 += 32) {
-                const uint32_t j = r0 + lane;
-                const bool have = j < bl;
-                uint32_t row = 0xFFFFFFFFu, prev = 0;
-                if (have) { row = rows[j]; if (j) prev = rows[j - 1]; }
-                // entries that lie below row j but not below row j-1: the open of row j-1 (if it starts a run) and the
-                // close after it (if row j does not continue the run)
-                uint32_t add = 0;
-                if (have && j) {
-                    const bool starts_prev = (j - 1 == 0) ? !(bown & 1u) : (rows[j - 2] + 1u != prev);
-                    add = (uint32_t)starts_prev + (uint32_t)(prev + 1u != row);
-                }
-                uint32_t incl = add;
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += up; }
-                const uint32_t cnt = carry + incl;   // boundaries below row j
-                carry += __shfl_sync(0xffffffffu, incl, 31);
-                if (have) { updates += first + j; physical += cnt; }
-                const uint32_t rb = row >> rb_shift;
-                const uint32_t prev_rb = __shfl_up_sync(0xffffffffu, rb, 1);
-                const uint32_t amask = __ballot_sync(0xffffffffu, have);
-                const bool start = have && (lane == 0 || prev_rb != rb);
-                const uint32_t smask = __ballot_sync(0xffffffffu, start);
-                const uint32_t above = lane == 31 ? 0u : ((smask >> (lane + 1)) << (lane + 1));
-                const uint32_t next_start = above ? (uint32_t)__ffs((int)above) - 1u : 32u;
-                const uint32_t last_active = amask ? 32u - (uint32_t)__clz((int)amask) : 0u;
-                const uint32_t run_end = min(next_start, last_active);           // one past the run's last lane
-                const uint32_t cnt_last = __shfl_sync(0xffffffffu, cnt, (run_end > lane ? run_end : lane + 1u) - 1u);
-                if (!start) continue;
-                const uint32_t k = run_end - lane, i = first + j;
-                const unsigned long long upd = (unsigned long long)k * i + k * (k - 1u) / 2u;
-                if (bw != 0 && upd != 0) emit(rb, make_job(bbase, bloff + j, cnt, cnt_last - cnt, k, bw), upd);
+            jb.k = k; jb.w = w; jb.pad = 0;
+            return jb;
+        };
+        uint32_t prev = 0, run_j = 0, run_rb = 0, run_c0 = 0, run_cl = 0;
+        bool starts_prev = false;
+        for (uint32_t j = 0; j < nd.l; ++j) {
+            const uint32_t row = rows[j];
+            const bool gap = j != 0 && prev + 1u != row;
+            if (kBoundary && j) cnt += (uint32_t)starts_prev + (uint32_t)gap;
+            const uint32_t rb = row >> rb_shift;
+            if (j == 0) { run_rb = rb; run_c0 = cnt; }
+            else if (rb != run_rb) {
+                const uint32_t k = j - run_j, i = first + run_j;
+                if (w != 0 && (unsigned long long)k * i + k * (k - 1u) / 2u != 0) emit(run_rb, make_job(run_j, k, run_c0, run_cl - run_c0));
+                run_j = j; run_rb = rb; run_c0 = cnt;
             }
+            run_cl = cnt;
+            physical += kBoundary ? cnt : first + j;
+            starts_prev = j == 0 ? !(own & 1u) : gap;
+            prev = row;
         }
+        const uint32_t k = nd.l - run_j, i = first + run_j;
+        if (w != 0 && (unsigned long long)k * i + k * (k - 1u) / 2u != 0) emit(run_rb, make_job(run_j, k, run_c0, run_cl - run_c0));
     }
 }
 
-__global__ void KDBX_BUCKET_BOUNDS
-k_job_fill_diff(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __restrict__ boff, const uint32_t* __restrict__ nb,
+// list_off = boff (boundary lists) or noff (id lists); per = patterns per block, the slices the decoder counted by
+template <bool kBoundary>
+__global__ void __launch_bounds__(kBucketThreads, 4)
+k_job_fill_runs(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __restrict__ list_off, const uint32_t* __restrict__ nb,
                 const uint32_t* __restrict__ ownb, const uint32_t* __restrict__ W, const uint32_t* __restrict__ loc, uint32_t rb_shift,
                 uint32_t nkeys, const uint32_t* __restrict__ blockbase, Job* __restrict__ jobs, uint64_t per,
                 unsigned long long* __restrict__ physical_total) {
@@ -207,17 +167,16 @@ k_job_fill_diff(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
     const uint32_t* mine = blockbase + (size_t)blockIdx.x * nkeys;
     for (uint32_t k = threadIdx.x; k < nkeys; k += blockDim.x) s_next[k] = mine[k];
     __syncthreads();
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     uint64_t lo, hi;
     block_slice(0, P, lo, hi, per);
-    unsigned long long updates = 0, physical = 0;
-    enumerate_jobs_diff(lo, hi, warp, nwarps, nodes, boff, nb, ownb, W, loc, rb_shift, lane, updates, physical,
-                        [&](uint32_t key, const Job& jb, unsigned long long) {
-                            const uint32_t slot = atomicAdd(&s_next[key], 1u);
-                            jobs[slot] = jb;
-                        });
+    unsigned long long physical = 0;
+    walk_runs<kBoundary>(lo, hi, nodes, list_off, nb, ownb, W, loc, rb_shift, blockDim.x, threadIdx.x, physical,
+                         [&](uint32_t key, const Job& jb) {
+                             const uint32_t slot = atomicAdd(&s_next[key], 1u);
+                             jobs[slot] = jb;
+                         });
     for (int o = 16; o; o >>= 1) physical += __shfl_xor_sync(0xffffffffu, physical, o);
-    if (lane == 0 && physical) atomicAdd(physical_total, physical);
+    if ((threadIdx.x & 31) == 0 && physical) atomicAdd(physical_total, physical);
 }
 
 // ---- the scatter-add kernel, boundary form --------------------------------------------------------------------

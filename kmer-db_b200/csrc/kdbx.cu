@@ -200,10 +200,9 @@ __device__ __forceinline__ uint32_t gamma_next(const uint64_t* __restrict__ w, u
 // With one column window (N <= tile_cols) a job is fully described by a run of local ids inside one
 // block of matrix rows, so the decoder — which has every id in hand — also counts the jobs per key
 // and their updates (DecodeHist): the first of the two job-enumeration passes of the bucketing
-// stage is then not needed at all.  The rule must equal enumerate_jobs' exactly: a run ends where
-// the row block changes and, for lists longer than kSmallL (taken 32 positions at a time by a
-// warp there), at every multiple of 32 positions; a job counts iff its weight and its number of
-// updates k*i + k(k-1)/2 are non-zero.
+// stage is then not needed at all.  The rule must equal the fill pass's (walk_runs) exactly: a run
+// ends where the row block changes; a job counts iff its weight and its number of updates
+// k*i + k(k-1)/2 are non-zero.
 constexpr int kDecodeThreads = 128;
 constexpr uint32_t kDecodeStage = 10240;  // ids (40 KB)
 constexpr uint32_t kSmallL = 8;           // see enumerate_jobs
@@ -238,7 +237,7 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
     uint32_t my_app = 0;
     // closes the run of k rows that starts at list position i (all in row block rb)
     auto close_run = [&](uint32_t rb, uint32_t i, uint32_t k, uint32_t w) {
-        const uint32_t upd = k * i + k * (k - 1u) / 2u;   // < 32 * 1536 + 496
+        const uint32_t upd = k * i + k * (k - 1u) / 2u;   // < 32 * 1536 + 496 (k <= 32: the rows of one block)
         if (w != 0 && upd != 0 && rb < dh.nkeys) atomicAdd(&s_pack[rb], (1u << 20) | ((upd + 512u) >> 10));   // (rb >= nkeys: id outside the window, flagged)
     };
     const uint64_t p0 = (uint64_t)blockIdx.x * kDecodeThreads;
@@ -310,12 +309,11 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
                         for (uint32_t i = 1; i < nd.l; ++i) { cur += out[i]; out[i] = cur; }
                     } else {
                         const uint32_t w = dh.W[p];
-                        const bool rounds = nd.l > kSmallL;   // longer lists are enumerated 32 positions at a time
                         uint32_t run_j = 0, run_rb = cur >> dh.rb_shift;
                         for (uint32_t i = 1; i < nd.l; ++i) {
                             cur += out[i]; out[i] = cur;
                             const uint32_t rb = cur >> dh.rb_shift;
-                            if (rb != run_rb || (rounds && (i & 31u) == 0)) {
+                            if (rb != run_rb) {
                                 close_run(run_rb, first + run_j, i - run_j, w);
                                 run_j = i; run_rb = rb;
                             }
@@ -1691,13 +1689,13 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
                 CK(ctx->units.ensure(jobs_cap * sizeof(Unit)));
             }
             if (diff)
-                k_job_fill_diff<<<wide_grid, kBucketThreads, 0, st>>>(ctx->P, ctx->nodes.as<Node>(), ctx->boff.as<uint64_t>(), ctx->nb.as<uint32_t>(),
-                                                                      ctx->ownb.as<uint32_t>(), ctx->W.as<uint32_t>(), ctx->loc.as<uint32_t>(), pl.rb_shift, nkeys,
-                                                                      ctx->blockhist.as<uint32_t>(), ctx->jobs.as<Job>(), per_block, d_physical);
+                k_job_fill_runs<true><<<wide_grid, kBucketThreads, 0, st>>>(ctx->P, ctx->nodes.as<Node>(), ctx->boff.as<uint64_t>(), ctx->nb.as<uint32_t>(),
+                                                                            ctx->ownb.as<uint32_t>(), ctx->W.as<uint32_t>(), ctx->loc.as<uint32_t>(), pl.rb_shift, nkeys,
+                                                                            ctx->blockhist.as<uint32_t>(), ctx->jobs.as<Job>(), per_block, d_physical);
             else
-                k_job_fill_smem<<<wide_grid, kBucketThreads, 0, st>>>(p0, p1, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), ctx->W.as<uint32_t>(),
-                                                                      ctx->flat.as<uint32_t>(), ctx->loc.as<uint32_t>(), ctx->first_id.as<uint32_t>(), 1u, pl.T, pl.tile_cols, pl.rb_shift, wb, we, nkeys,
-                                                                      ctx->blockhist.as<uint32_t>(), ctx->jobs.as<Job>(), per_block);
+                k_job_fill_runs<false><<<wide_grid, kBucketThreads, 0, st>>>(ctx->P, ctx->nodes.as<Node>(), ctx->noff.as<uint64_t>(), nullptr, nullptr,
+                                                                             ctx->W.as<uint32_t>(), ctx->loc.as<uint32_t>(), pl.rb_shift, nkeys,
+                                                                             ctx->blockhist.as<uint32_t>(), ctx->jobs.as<Job>(), per_block, d_physical);
             launches += 1;
         } else if (smem_buckets) {
             // per-block slices of whole decoder blocks when the pass covers all patterns; chunks are sliced evenly
