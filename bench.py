@@ -81,6 +81,9 @@ def parse_args():
                     help="form of the full sample lists (kdbx.h: KDBX_FLAG_ID_LISTS / KDBX_FLAG_BOUNDARY_LISTS); auto = the library decides")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak")
     ap.add_argument("--no-window", action="store_true", help="N>1: do not declare the parts' sample windows")
+    ap.add_argument("--check-reference", action="store_true",
+                    help="N>1: run the reference binary on the whole (N times larger) database once for the CSV cmp, however long it takes")
+    ap.add_argument("--keep-cache", action="store_true", help="N>1: keep the weak-scaling database and the parts under --cache-dir")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cache-dir", default=os.environ.get("KDBX_CACHE", "/tmp/kdbx_cache"))
@@ -396,6 +399,14 @@ def main():
         ctx.comm_init_rank(world, rank, _broadcast_bytes(dist, torch, kdbx.Context.comm_unique_id() if rank == 0 else None))
     tot = trie.totals()
     P = int(tot.num_patterns)
+    # an independent check of the whole result that costs one pass over the trie: every pattern adds num_kmers to each
+    # pair of its n samples (the flat form of the reference's sparse path), so the sum of all cells of the matrix is
+    # sum_p num_kmers_p * n_p (n_p - 1) / 2 — over the OWNED patterns of this rank's part (ancestors carry num_kmers = 0)
+    arr = trie.arrays()
+    nn = arr["n"].astype(np.uint64)
+    with np.errstate(over="ignore"):   # exact modulo 2^64 (numpy wraps), reduced to 60 bits so that the ranks' shares add without overflow
+        expected_sum = sum_over_ranks(int((arr["num_kmers"].astype(np.uint64) * (nn * (nn - np.uint64(1)) // np.uint64(2))).sum(dtype=np.uint64)) % (1 << 60)) % (1 << 60)
+    del arr, nn
 
     def stage():
         ctx.load_patterns(trie)
@@ -451,6 +462,7 @@ def main():
     own = _own_cells(rank, block, cells)
     checksum = sum_over_ranks(int((d_out[:own].to(torch.int64) & 0xFFFFFFFF).sum().item()) if own else 0)
     physical = sum_over_ranks(int(st.physical_updates))
+    assert checksum % (1 << 60) == expected_sum, "sum of the matrix != sum over patterns of num_kmers * n (n - 1) / 2"
 
     # ---- parity: the matrix of the timed configuration against the reference binary's CSV, byte for byte --------
     parity = None
@@ -466,7 +478,7 @@ def main():
     if rank == 0 and not a.no_cpu_baseline:
         try:
             ref_csv = ref_csv_path(path)
-            if world == 1 or (not ref_csv.exists() and U_total < 4e11):
+            if world == 1 or (not ref_csv.exists() and (U_total < 4e11 or a.check_reference)):
                 secs = run_reference_binary(path, cores)
                 cpu_baseline = {"value": U_total / secs, "unit": "updates/s", "cores": cores, "kind": "reference",
                                 "sample": f"the whole workload once: {N} genomes, U={U_total:.4g}, {secs:.2f} s, kmer-db 2.3.1 all2all -t {cores} "
@@ -516,6 +528,15 @@ def main():
                "d2h_bytes_per_step": cells * 4, "ms_per_step": 1e3 * e2e_s / a.steps,
                "ms_upload": st2.ms_upload, "ms_download": st2.ms_download}
 
+    if world > 1 and not a.keep_cache:
+        # the parts (and the N-times-larger weak-scaling database) are tens of GB under /tmp: do not leave them behind
+        trie.close()
+        barrier()
+        for f in (part_path, Path(str(part_path) + ".json")):
+            f.unlink(missing_ok=True)
+        if rank == 0 and a.scaling == "weak":
+            for f in (path, Path(str(path) + ".json"), ref_csv_path(path)):
+                f.unlink(missing_ok=True)
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -558,7 +579,8 @@ def main():
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "stage_ms_per_step": {k: v / a.steps for k, v in stage_ms.items()}, "wall_ms_per_step": wall_ms / a.steps,
         "library_ms_per_step": per_step_ms,
-        "result_checksum": checksum, "list_form": ["ids", "run boundaries"][int(st.list_form)],
+        "result_checksum": checksum, "checksum_identity": "sum of all cells == sum_p num_kmers_p n_p (n_p - 1) / 2 over the trie: checked",
+        "list_form": ["ids", "run boundaries"][int(st.list_form)],
         "physical_updates_per_step": physical,
     }
     if parity:

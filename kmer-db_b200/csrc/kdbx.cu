@@ -895,10 +895,8 @@ __device__ __forceinline__ void last_rows(uint32_t k, uint32_t rowoff, uint32_t 
         if (F > 0) red_shared_add(ro + x0, w);
         if (F > 1) red_shared_add(ro + x1, w);
         if (F > 2) red_shared_add(ro + x2, w);
-        // (adding 0 instead of skipping: ptxas compiles a guarded shared-memory reduction into a branch with a
-        //  convergence barrier, six instructions where these take three or four; idle lanes hold their padding word)
-        if (has_tail) red_shared_add(ro + xt, tail ? w : 0u);
-        red_shared_add(ro + my_id4, lane < j ? wt : 0u);
+        if (tail) red_shared_add(ro + xt, w);
+        if (lane < j) red_shared_add(ro + my_id4, wt);   // (wt = 0 for lanes without a row: their my_id4 is the padding word)
     }
 }
 constexpr uint32_t kRowPad = 32;   // padding words after every accumulator row (see k_scatter_add)
