@@ -245,17 +245,17 @@ def files_identical(a, b, chunk=1 << 24):
                 return True
 
 
-def ncu_traffic_per_launch(kernel):
-    """dram bytes per scatter launch from the committed ncu summary, if one exists for this kernel."""
+def ncu_capture(kernel):
+    """figures of the committed ncu --set full capture of this kernel (profiles/scatter_traffic.json), if there is one"""
     p = ROOT / "profiles" / "scatter_traffic.json"
     if p.exists():
         try:
             d = json.loads(p.read_text())
             if d.get("kernel", "k_scatter_add") == kernel:
-                return d.get("dram_bytes_per_launch")
+                return d
         except Exception:
-            return None
-    return None
+            return {}
+    return {}
 
 
 def reference_arm(a, rank, world):
@@ -383,13 +383,9 @@ def main():
         if rank == 0 and not all(Path(f"{tag}.part{r}of{world}.db.json").exists() for r in range(world)):
             t0 = time.perf_counter()
             whole = kdbx.Trie.read_db(path, pinned=False)
-            for r, (part, owned, win) in enumerate(whole.partition_all(world)):
-                pp = Path(f"{tag}.part{r}of{world}.db")
-                part.write_db(pp)
-                tt = part.totals()
-                Path(str(pp) + ".json").write_text(json.dumps({"window": list(win), "owned_updates": owned, "updates": int(tt.updates),
-                                                                "num_patterns": int(tt.num_patterns)}))
-                part.close()
+            for r, (owned, win, upd, pats) in enumerate(whole.partition_write_all(world, f"{tag}.part")):   # one host thread per part
+                Path(f"{tag}.part{r}of{world}.db.json").write_text(json.dumps({"window": list(win), "owned_updates": owned, "updates": upd,
+                                                                              "num_patterns": pats}))
             whole.close()
             t_shard = time.perf_counter() - t0
             print(f"[bench] cut {path.name} into {world} parts in {t_shard:.1f} s", file=sys.stderr)
@@ -547,8 +543,10 @@ def main():
     phys_rank = int(st.physical_updates)
     atomic_rate = phys_rank * a.steps / (scat_ms / 1e3) if scat_ms > 0 else 0.0
     kernel = "k_scatter_diff" if int(st.list_form) == 1 else "k_scatter_add"
+    cap = ncu_capture(kernel)
+    u_rate = U_rank * a.steps / (scat_ms / 1e3) if scat_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic_per_launch(kernel), "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": cap.get("dram_bytes_per_launch"), "peak_source": peak_src,
                 "note": "HBM-EQUIVALENT figure (12 B x U / kernel time): the accumulators live in shared memory, so it is not a bound; "
                         "the kernel's physical bound is smem_atomic",
                 "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE,
@@ -559,7 +557,15 @@ def main():
                                 "frac": atomic_rate / SMEM_ATOMIC_PEAK,
                                 "peak_source": "conflict-free microbenchmark, ids in registers (profiles/r01_microbench_atomics.txt)",
                                 "reductions_per_launch": phys_rank / max(1, scat_launches / a.steps),
-                                "note": "lane-updates actually issued (run-boundary lists issue fewer than U: two per run of consecutive ids)"}}
+                                "note": "lane-updates actually ISSUED (run-boundary lists issue fewer than U: two per run of consecutive ids); "
+                                        "effective_frac counts the algorithmic updates U the launch delivers against the same peak; "
+                                        "l1tex_busy_pct is the utilisation of the shared-memory pipe in the committed ncu capture "
+                                        "(a reduction takes 2.5 bank-conflict wavefronts on sorted-but-gappy columns, so the conflict-free "
+                                        "peak is not reachable by any schedule of these updates)",
+                                "effective_frac": u_rate / SMEM_ATOMIC_PEAK,
+                                "l1tex_busy_pct": cap.get("l1tex_throughput_pct_of_peak"),
+                                "wavefronts_per_reduction": (cap.get("shared_atomic_wavefronts_per_launch") / cap.get("shared_atomic_instructions_per_launch"))
+                                if cap.get("shared_atomic_instructions_per_launch") else None}}
 
     cfg = common_config(a, meta, samples, clusters, skew)
     cfg.update({

@@ -80,6 +80,11 @@ typedef struct kdbxh_partitioner kdbxh_partitioner;
 kdbxh_partitioner* kdbxh_partitioner_new(const kdbxh_trie* src, uint32_t num_parts);
 void kdbxh_partitioner_free(kdbxh_partitioner* p);
 int kdbxh_partitioner_part(const kdbxh_partitioner* p, uint32_t part, kdbxh_trie* dst, uint64_t* owned_updates, uint32_t* window);
+/* The same for all parts at once, each written to "<prefix><part>of<num_parts>.db" by its own host thread.  The
+ * arrays (may be NULL) receive per part: U of the owned patterns, the sample window (2 entries), U of the part as a
+ * database of its own (owned + ancestor chain), its number of patterns. */
+int kdbxh_partition_write_all(const kdbxh_trie* src, uint32_t num_parts, const char* prefix, uint64_t* owned_updates,
+                              uint32_t* windows, uint64_t* part_updates, uint64_t* part_patterns);
 /* Shifts every sample id of t by `offset` inside a sample table of `new_total` entries (the other
  * entries are empty samples); the trie keeps its shape.  Lays shards of a workload side by side. */
 int kdbxh_relabel(kdbxh_trie* t, uint32_t offset, uint32_t new_total);

@@ -206,7 +206,7 @@ __device__ __forceinline__ uint32_t gamma_next(const uint64_t* __restrict__ w, u
 constexpr int kDecodeThreads = 128;
 constexpr uint32_t kDecodeStage = 10240;  // ids (40 KB)
 constexpr uint32_t kSmallL = 8;           // see enumerate_jobs
-constexpr uint32_t kDecodeHistKeys = 64;
+constexpr uint32_t kDecodeHistKeys = 192;   // row blocks the decoder can count for: 1536 samples in 32-row blocks, 3072 in 16-row blocks
 struct DecodeHist {
     uint32_t enabled, rb_shift, nkeys;
     uint64_t per;                       // patterns per block of the fill pass (a multiple of kDecodeThreads)
@@ -225,19 +225,19 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
                 uint64_t payload_words, uint32_t* __restrict__ loc, uint32_t win_lo, uint32_t win_n, int* __restrict__ err, DecodeHist dh) {
     __shared__ uint32_t s_ids[kDecodeStage];
     // per key: jobs in the top 12 bits, their updates in units of 1024 in the low 20 (a block's 128 patterns
-    // hold at most 128 * 32 runs per key and 128 * N * N / 2 / 1024 < 2^20 such units with N <= 1536) — ONE
+    // hold at most 128 runs per key and 128 * 32 * N / 1024 < 2^20 such units with N <= 3072) — ONE
     // 32-bit shared-memory reduction per run.  The updates only size the scatter kernel's work units, so the
     // rounding is harmless; the job counts are exact.
     __shared__ uint32_t s_pack[kDecodeHistKeys];
     if (dh.enabled) {
-        if (threadIdx.x < kDecodeHistKeys) s_pack[threadIdx.x] = 0;
+        for (uint32_t k = threadIdx.x; k < kDecodeHistKeys; k += kDecodeThreads) s_pack[k] = 0;
         __syncthreads();
     }
     unsigned long long my_updates = 0;
     uint32_t my_app = 0;
     // closes the run of k rows that starts at list position i (all in row block rb)
     auto close_run = [&](uint32_t rb, uint32_t i, uint32_t k, uint32_t w) {
-        const uint32_t upd = k * i + k * (k - 1u) / 2u;   // < 32 * 1536 + 496 (k <= 32: the rows of one block)
+        const uint32_t upd = k * i + k * (k - 1u) / 2u;   // < 32 * 3072 + 496 (k <= 32: the rows of one block)
         if (w != 0 && upd != 0 && rb < dh.nkeys) atomicAdd(&s_pack[rb], (1u << 20) | ((upd + 512u) >> 10));   // (rb >= nkeys: id outside the window, flagged)
     };
     const uint64_t p0 = (uint64_t)blockIdx.x * kDecodeThreads;
@@ -340,10 +340,11 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
         if ((threadIdx.x & 31) == 0 && my_updates) atomicAdd(dh.total_updates, my_updates);
         __syncthreads();
         // this block's 128 patterns lie inside one block of the fill pass (dh.per is a multiple of 128)
-        if (threadIdx.x < dh.nkeys && s_pack[threadIdx.x]) {
-            const uint32_t pk = s_pack[threadIdx.x];
-            atomicAdd(&dh.blockhist[(p0 / dh.per) * dh.nkeys + threadIdx.x], pk >> 20);
-            atomicAdd(&dh.work[threadIdx.x], ((unsigned long long)(pk & 0xFFFFFu) << 10) + (pk >> 20));  // never 0 for a used key
+        for (uint32_t k = threadIdx.x; k < dh.nkeys; k += kDecodeThreads) {
+            const uint32_t pk = s_pack[k];
+            if (!pk) continue;
+            atomicAdd(&dh.blockhist[(p0 / dh.per) * dh.nkeys + k], pk >> 20);
+            atomicAdd(&dh.work[k], ((unsigned long long)(pk & 0xFFFFFu) << 10) + (pk >> 20));  // never 0 for a used key
         }
     }
 }
@@ -1189,14 +1190,14 @@ struct Plan {
 };
 
 constexpr size_t kMaxTileBytes = 200 * 1024;  // of the 227 KB a CTA may use
-constexpr uint32_t kMaxOneWindowCols = 1536;  // 32 rows x 1536 columns: the widest tile that still fits
+constexpr uint32_t kMaxOneWindowCols = 3072;  // one column window: 32-row tiles up to 1568 columns, 16-row tiles up to 3072
 
 int make_plan(kdbx_ctx* ctx, Plan& pl) {
     pl.lo = ctx->win_lo;
     const uint32_t N = ctx->win_hi - ctx->win_lo;
     pl.Nw = N;
     uint32_t tc = ctx->cfg.tile_cols;
-    // default: whole rows (one column window) up to 1536 samples, 1024-column windows beyond
+    // default: whole rows (one column window) up to 3072 samples (the rows of a tile halve beyond 1568), 1024-column windows beyond
     if (tc == 0) tc = N <= kMaxOneWindowCols ? std::max<uint32_t>(32u, (N + 31u) & ~31u) : 1024u;
     if (tc < 32 || (tc & 31)) return ctx->fail(KDBX_ERR_ARG, "tile_cols must be a multiple of 32");
     uint32_t tr = ctx->cfg.tile_rows;

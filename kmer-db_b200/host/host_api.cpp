@@ -2,6 +2,7 @@
 // exceptions into error codes.
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/kdbx_host.h"
@@ -212,6 +213,33 @@ void kdbxh_partitioner_free(kdbxh_partitioner* p) { delete p; }
 int kdbxh_partitioner_part(const kdbxh_partitioner* p, uint32_t part, kdbxh_trie* dst, uint64_t* owned_updates, uint32_t* window) {
     if (!p || !dst) { g_err = "null argument"; return -1; }
     return guarded([&] { dst->flat_off.clear(); dst->flat_slots.clear(); p->p.extract(part, dst->t, owned_updates, window); });
+}
+// All parts of one cut, extracted and written to <prefix><part>of<num_parts>.db by one host thread each.
+int kdbxh_partition_write_all(const kdbxh_trie* src, uint32_t num_parts, const char* prefix, uint64_t* owned_updates, uint32_t* windows,
+                              uint64_t* part_updates, uint64_t* part_patterns) {
+    if (!src || !prefix || num_parts == 0) { g_err = "bad argument"; return -1; }
+    return guarded([&] {
+        const kdbx::TriePartitioner cut(src->t, num_parts);
+        std::vector<std::string> errors(num_parts);
+        std::vector<std::thread> th;
+        for (uint32_t g = 0; g < num_parts; ++g)
+            th.emplace_back([&, g] {
+                try {
+                    kdbx::Trie part(false);
+                    uint64_t owned = 0;
+                    uint32_t win[2] = {0, 0};
+                    cut.extract(g, part, &owned, win);
+                    kdbx::write_db(std::string(prefix) + std::to_string(g) + "of" + std::to_string(num_parts) + ".db", part);
+                    const auto tt = part.totals();
+                    if (owned_updates) owned_updates[g] = owned;
+                    if (windows) { windows[2 * g] = win[0]; windows[2 * g + 1] = win[1]; }
+                    if (part_updates) part_updates[g] = tt.U;
+                    if (part_patterns) part_patterns[g] = part.num_patterns();
+                } catch (const std::exception& e) { errors[g] = e.what(); }
+            });
+        for (auto& t : th) t.join();
+        for (const auto& e : errors) if (!e.empty()) throw std::runtime_error(e);
+    });
 }
 int kdbxh_relabel(kdbxh_trie* t, uint32_t offset, uint32_t new_total) {
     if (!t) { g_err = "null argument"; return -1; }

@@ -117,7 +117,7 @@ KDBX_SYMBOLS = ["kdbx_abi_version", "kdbx_device_count", "kdbx_open", "kdbx_clos
                 "kdbx_builder_finish", "kdbx_builder_export", "kdbx_new2all_sequences"]
 KDBXH_SYMBOLS = ["kdbxh_last_error", "kdbxh_trie_new", "kdbxh_trie_free", "kdbxh_read_db", "kdbxh_write_db",
                  "kdbxh_synth", "kdbxh_validate", "kdbxh_prefix", "kdbxh_partition", "kdbxh_partitioner_new", "kdbxh_partitioner_free",
-                 "kdbxh_partitioner_part", "kdbxh_relabel", "kdbxh_view", "kdbxh_totals_of", "kdbxh_sample_name",
+                 "kdbxh_partitioner_part", "kdbxh_partition_write_all", "kdbxh_relabel", "kdbxh_view", "kdbxh_totals_of", "kdbxh_sample_name",
                  "kdbxh_sample_kmers", "kdbxh_write_all2all_csv", "kdbxh_read_db_full", "kdbxh_tables_view",
                  "kdbxh_builder_new", "kdbxh_builder_free", "kdbxh_builder_add_sample", "kdbxh_builder_finish",
                  "kdbxh_samples_load", "kdbxh_samples_free", "kdbxh_samples_count", "kdbxh_samples_name", "kdbxh_samples_kmers"]
@@ -195,6 +195,7 @@ def load():
     h.kdbxh_partitioner_free.argtypes = [C.c_void_p]
     h.kdbxh_partitioner_free.restype = None
     h.kdbxh_partitioner_part.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, P(C.c_uint64), P(C.c_uint32 * 2)]
+    h.kdbxh_partition_write_all.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     h.kdbxh_relabel.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
     h.kdbxh_view.argtypes = [C.c_void_p, P(TrieView)]
     h.kdbxh_totals_of.argtypes = [C.c_void_p, P(Totals)]
@@ -333,6 +334,15 @@ class Trie:
                 yield out, int(owned.value), (int(win[0]), int(win[1]))
         finally:
             self._h.kdbxh_partitioner_free(pt)
+
+    def partition_write_all(self, num_parts, prefix):
+        """Cuts the database into num_parts parts and writes them to <prefix><part>of<num_parts>.db, one host thread per part;
+        returns [(owned updates, (lo, hi) window, updates of the part, patterns of the part)]."""
+        owned = np.zeros(num_parts, np.uint64); win = np.zeros(2 * num_parts, np.uint32)
+        upd = np.zeros(num_parts, np.uint64); pats = np.zeros(num_parts, np.uint64)
+        self._check(self._h.kdbxh_partition_write_all(self._p, num_parts, os.fsencode(str(prefix)), owned.ctypes.data, win.ctypes.data,
+                                                      upd.ctypes.data, pats.ctypes.data))
+        return [(int(owned[g]), (int(win[2 * g]), int(win[2 * g + 1])), int(upd[g]), int(pats[g])) for g in range(num_parts)]
 
     def relabel(self, offset, new_total):
         """Shift all sample ids by `offset` inside a table of `new_total` samples (in place)."""

@@ -452,3 +452,30 @@ def test_cli_all2all_on_two_gpus(libs, golden_dbs, tmp_path):
     exe = ou.ROOT / "kmer-db_b200" / "bin" / "kmer-db-b200"
     subprocess.run([str(exe), "all2all", "-gpus", "2", str(db), str(tmp_path / "a.csv")], check=True, stderr=subprocess.DEVNULL)
     assert ou.read_bytes(tmp_path / "a.csv") == ou.read_bytes(dense)
+
+
+@pytest.mark.parametrize("N", [1025, 1568, 1569, 2049, 3072, 3073])
+def test_sample_counts_around_the_window_sizes(libs, oracle, N):
+    """N around the tile limits: up to 1568 columns a tile has 32 rows, up to 3072 it has 16 (still one column window:
+    boundary lists, decoder job counts), 3073 is the first size with 1024-column windows."""
+    rng = np.random.default_rng(N)
+    a, _ = ou.random_trie(rng, N, 2500, max_local=40, big_weights=True, dense_lists=(N % 2 == 1))
+    want, U = ou.oracle_all2all(oracle, N, a)
+    got, st = _run(libs, N, a)
+    assert st.updates == U and np.array_equal(got, want)
+    got, st = _run(libs, N, a, flags=libs.FLAG_BOUNDARY_LISTS)
+    assert st.updates == U and np.array_equal(got, want)
+    assert st.list_form == (1 if N <= 3072 else 0)   # beyond one window the id form runs, whatever the flag asks for
+
+
+def test_pattern_count_guard(libs):
+    """num_patterns must stay below 2^31 (pattern ids are int32 in the node records): refused before anything is copied."""
+    z = np.zeros
+    a = {"num_kmers": z(1, np.int64), "parent_id": np.full(1, -1, np.int64), "n": z(1, np.uint32), "l": z(1, np.uint32),
+         "last": z(1, np.uint32), "bits": z(1, np.uint32), "payload_off": z(1, np.uint64), "payload": z(2, np.uint64)}
+    with libs.Context(device=0) as c:
+        v, keep = libs.view_from_arrays(4, a["num_kmers"], a["parent_id"], a["n"], a["l"], a["last"], a["bits"], a["payload_off"], a["payload"])
+        for bad in (0, 2**31, 2**40):
+            v.num_patterns = bad
+            with pytest.raises(libs.KdbxError, match=r"num_patterns must be in \[1, 2\^31\)"):
+                c.load_patterns(v, keep)
