@@ -460,6 +460,34 @@ def main():
     physical = sum_over_ranks(int(st.physical_updates))
     assert checksum % (1 << 60) == expected_sum, "sum of the matrix != sum over patterns of num_kmers * n (n - 1) / 2"
 
+    # ---- end-to-end leg: host trie -> H2D -> compute (-> reduce-scatter) -> D2H of every block ------------------
+    # (right after the device-resident leg: the reference binary of the parity leg below keeps the GPU idle for half a
+    #  minute, and the first steps after that ran 15 % slower while the clocks came back)
+    e2e = None
+    if not a.no_e2e:
+        out_host = kdbx.pinned_empty(max(1, block), np.uint32)
+
+        def e2e_step():
+            stage()
+            if world == 1:
+                return ctx.all2all_dense_rows(0, N, out_host[:cells])[1]
+            return ctx.all2all_dense_reduce_scatter(out_host)[2]
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            st2 = e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        got = sum_over_ranks(int(out_host[:own].astype(np.int64).sum()))
+        assert got == checksum, "e2e result differs from the device-resident result"
+        hdr_bytes = 24 if trie.view().parent_id32 else 40   # (32-bit mirrors of parent_id / num_kmers: kdbx_trie_view)
+        h2d = sum_over_ranks(P * hdr_bytes + int(tot.payload_bytes))  # summed over the ranks (every rank copies its own shard)
+        e2e = {"value": U_total * a.steps / e2e_s, "unit": "updates/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": cells * 4, "ms_per_step": 1e3 * e2e_s / a.steps,
+               "ms_upload": st2.ms_upload, "ms_download": st2.ms_download}
+
     # ---- parity: the matrix of the timed configuration against the reference binary's CSV, byte for byte --------
     parity = None
     cpu_baseline = None
@@ -497,32 +525,6 @@ def main():
         except Exception as e:  # the baseline is a reported number, not a dependency of the GPU path
             cpu_baseline = {"value": None, "unit": "updates/s", "cores": cores, "kind": "reference", "sample": f"failed: {e}"}
     host_full = None
-
-    # ---- end-to-end leg: host trie -> H2D -> compute (-> reduce-scatter) -> D2H of every block ------------------
-    e2e = None
-    if not a.no_e2e:
-        out_host = kdbx.pinned_empty(max(1, block), np.uint32)
-
-        def e2e_step():
-            stage()
-            if world == 1:
-                return ctx.all2all_dense_rows(0, N, out_host[:cells])[1]
-            return ctx.all2all_dense_reduce_scatter(out_host)[2]
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(a.steps):
-            st2 = e2e_step()
-        torch.cuda.synchronize()
-        e2e_s = max_over_ranks(time.perf_counter() - t0)
-        barrier()
-        got = sum_over_ranks(int(out_host[:own].astype(np.int64).sum()))
-        assert got == checksum, "e2e result differs from the device-resident result"
-        hdr_bytes = 24 if trie.view().parent_id32 else 40   # (32-bit mirrors of parent_id / num_kmers: kdbx_trie_view)
-        h2d = sum_over_ranks(P * hdr_bytes + int(tot.payload_bytes))  # summed over the ranks (every rank copies its own shard)
-        e2e = {"value": U_total * a.steps / e2e_s, "unit": "updates/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": cells * 4, "ms_per_step": 1e3 * e2e_s / a.steps,
-               "ms_upload": st2.ms_upload, "ms_download": st2.ms_download}
 
     if world > 1 and not a.keep_cache:
         # the parts (and the N-times-larger weak-scaling database) are tens of GB under /tmp: do not leave them behind

@@ -206,7 +206,7 @@ __device__ __forceinline__ uint32_t gamma_next(const uint64_t* __restrict__ w, u
 constexpr int kDecodeThreads = 128;
 constexpr uint32_t kDecodeStage = 10240;  // ids (40 KB)
 constexpr uint32_t kSmallL = 8;           // see enumerate_jobs
-constexpr uint32_t kDecodeHistKeys = 192;   // row blocks the decoder can count for: 1536 samples in 32-row blocks, 3072 in 16-row blocks
+constexpr uint32_t kDecodeHistKeys = 192;   // row blocks the decoder can count for: 3072 samples in 16-row blocks
 struct DecodeHist {
     uint32_t enabled, rb_shift, nkeys;
     uint64_t per;                       // patterns per block of the fill pass (a multiple of kDecodeThreads)
@@ -1189,15 +1189,15 @@ struct Plan {
     size_t smem = 0, smem_diff = 0;
 };
 
-constexpr size_t kMaxTileBytes = 200 * 1024;  // of the 227 KB a CTA may use
-constexpr uint32_t kMaxOneWindowCols = 3072;  // one column window: 32-row tiles up to 1568 columns, 16-row tiles up to 3072
+constexpr size_t kMaxTileBytes = 220 * 1024;  // of the 227 KB a CTA may use (the boundary-form kernel adds 4 KB of static shared memory): 32 rows x 1728 columns
+constexpr uint32_t kMaxOneWindowCols = 3072;  // one column window: 32-row tiles up to 1728 columns, 16-row tiles up to 3072
 
 int make_plan(kdbx_ctx* ctx, Plan& pl) {
     pl.lo = ctx->win_lo;
     const uint32_t N = ctx->win_hi - ctx->win_lo;
     pl.Nw = N;
     uint32_t tc = ctx->cfg.tile_cols;
-    // default: whole rows (one column window) up to 3072 samples (the rows of a tile halve beyond 1568), 1024-column windows beyond
+    // default: whole rows (one column window) up to 3072 samples (the rows of a tile halve beyond 1728), 1024-column windows beyond
     if (tc == 0) tc = N <= kMaxOneWindowCols ? std::max<uint32_t>(32u, (N + 31u) & ~31u) : 1024u;
     if (tc < 32 || (tc & 31)) return ctx->fail(KDBX_ERR_ARG, "tile_cols must be a multiple of 32");
     uint32_t tr = ctx->cfg.tile_rows;

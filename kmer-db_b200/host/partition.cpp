@@ -10,7 +10,7 @@
 // To keep the replicated ancestors few, the owned sets are contiguous pieces of the trie's
 // depth-first preorder: the ancestor closure of such a piece is the piece plus ONE root-to-node
 // chain (the ancestors of its first pattern).  Pieces are balanced on a per-pattern cost model of
-// the GPU pipeline (updates of the scatter-add + ids expanded and bucketed).
+// the GPU pipeline (updates of the scatter-add + list entries expanded + local ids decoded + a constant per node).
 // A part is renumbered in preorder (parents stay before children, as kdbx_load_patterns requires),
 // keeps the whole sample table, and its Elias-gamma payload is gathered into a compact blob, so a
 // GPU uploads and decodes only its own share.
@@ -25,11 +25,12 @@
 namespace kdbx {
 
 namespace {
-// cost of a pattern in "updates": l(2n-l-1)/2 updates at ~0.42 ps each, n flat ids at ~14 ps each
-// (decode + expand + bucketing per id, profiles/r01_bench_v4_cfg2.json), a constant per node
+// cost of a pattern in "updates" of the scatter kernel (0.32 ps each at config 2, profiles/r02_bench_cfg2_v3.json):
+// l(2n-l-1)/2 updates; n list entries expanded at ~3.7 ps each (12 updates); l local ids decoded and walked by the fill
+// pass at ~18 ps each (57 updates); ~220 ps per node for packing, sorting, scans and the level passes (680 updates)
 inline uint64_t pattern_cost(uint32_t n, uint32_t l) {
     const uint64_t nn = n, ll = l;
-    return ll * (2 * nn - ll - 1) / 2 + 34 * nn + 200;
+    return ll * (2 * nn - ll - 1) / 2 + 12 * nn + 57 * ll + 680;
 }
 }  // namespace
 

@@ -454,9 +454,9 @@ def test_cli_all2all_on_two_gpus(libs, golden_dbs, tmp_path):
     assert ou.read_bytes(tmp_path / "a.csv") == ou.read_bytes(dense)
 
 
-@pytest.mark.parametrize("N", [1025, 1568, 1569, 2049, 3072, 3073])
+@pytest.mark.parametrize("N", [1025, 1728, 1729, 2049, 3072, 3073])
 def test_sample_counts_around_the_window_sizes(libs, oracle, N):
-    """N around the tile limits: up to 1568 columns a tile has 32 rows, up to 3072 it has 16 (still one column window:
+    """N around the tile limits: up to 1728 columns a tile has 32 rows, up to 3072 it has 16 (still one column window:
     boundary lists, decoder job counts), 3073 is the first size with 1024-column windows."""
     rng = np.random.default_rng(N)
     a, _ = ou.random_trie(rng, N, 2500, max_local=40, big_weights=True, dense_lists=(N % 2 == 1))
