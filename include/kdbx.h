@@ -193,6 +193,18 @@ int kdbx_all2all_dense_rows(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end,
 int kdbx_csv_dense_rows(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, char* text, uint64_t capacity,
                         uint64_t* row_off, uint64_t* bytes);
 
+/* `distance` on the device: DistanceConsole::run (src/console_distance.cpp:74-200) for a dense triangular table.  For
+ * every row s in [row_begin, row_end) the s cells measure(common, total_kmers[s], total_kmers[c]) printed with six
+ * decimals exactly as num2str(double) does (src/conversion.h:167-219,254-260: "0" for zero, else (uint64)(v * 10^6 + 0.5)
+ * as <int>.<6 digits>), each followed by ','.  Measures: KDBX_METRIC_JACCARD / MIN / MAX / COSINE / NUM_KMERS
+ * (src/params.cpp:14-42) — one or two correctly rounded IEEE operations, so the bytes are the reference's; the
+ * logarithm-based ones stay with the caller.  Works on the resident matrix: the one the last kdbx_all2all_dense[_rows]
+ * call left, or a packed triangle staged with kdbx_stage_matrix (what the `distance` mode parsed from a table).
+ * sample_kmers: uint32[row_end] "total-kmers", none of them 0.  text == NULL: sizes only.  HOST pointers. */
+int kdbx_stage_matrix(kdbx_ctx* ctx, const uint32_t* tri, uint32_t num_samples);
+int kdbx_distance_dense_rows(kdbx_ctx* ctx, int metric, const uint32_t* sample_kmers, uint32_t row_begin, uint32_t row_end,
+                             char* text, uint64_t capacity, uint64_t* row_off, uint64_t* bytes);
+
 /* Same, result left in DEVICE memory (`d_out_rows` is a CUDA device pointer on ctx's
  * device, e.g. a torch tensor's data_ptr); no D2H inside the call. */
 int kdbx_all2all_dense_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end,
@@ -207,7 +219,8 @@ int kdbx_all2all_dense_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t r
  * Only measures whose arithmetic is exactly reproducible on the GPU (one division / one sqrt,
  * round-to-nearest) are offered here; the log-based ones (mash, ani, ...) stay with the caller,
  * who filters the returned rows on the host (kmer-db_b200/host does). */
-enum { KDBX_METRIC_JACCARD = 0, KDBX_METRIC_MIN = 1, KDBX_METRIC_MAX = 2, KDBX_METRIC_COSINE = 3 };
+enum { KDBX_METRIC_JACCARD = 0, KDBX_METRIC_MIN = 1, KDBX_METRIC_MAX = 2, KDBX_METRIC_COSINE = 3,
+       KDBX_METRIC_NUM_KMERS = 4 /* kdbx_distance_dense_rows only */ };
 typedef struct kdbx_metric_bound {
     int32_t metric;     /* KDBX_METRIC_*                                                   */
     int32_t _pad;

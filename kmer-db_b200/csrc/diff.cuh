@@ -19,16 +19,28 @@
 // everything else runs the id form of kdbx.cu.
 #pragma once
 
-// nb[p] = entries of B(p): the parent's, minus its final close when joined, plus the own ones.  One launch per
-// num_samples level, ascending (parents first), like the level-order expansion.
+// nb[p] = entries of B(p): the parent's, minus its final close when joined, plus the own ones; first_id[p] = smallest id
+// of the full list (the root's first local id).  One launch per num_samples level, ascending (parents first), like the
+// level-order expansion.  slide_cols != 0 (sliding column window, make_plan): the list of p must not reach below the
+// window of the row block of p's LAST local id, i.e. first_id + slide_cols >= end of that block; flag 9 otherwise.
 __global__ void k_pull_level(uint32_t count, const uint32_t* __restrict__ order, const Node* __restrict__ nodes,
-                             const uint32_t* __restrict__ ownb, uint32_t* __restrict__ nb) {
+                             const uint32_t* __restrict__ ownb, uint32_t* __restrict__ nb, const uint32_t* __restrict__ loc,
+                             uint32_t* __restrict__ first_id, uint32_t slide_cols, uint32_t win_lo, uint32_t rb_shift,
+                             int* __restrict__ err) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const uint32_t p = order[i];
-    const int32_t q = nodes[p].parent;
+    const Node nd = nodes[p];
+    const int32_t q = nd.parent;
     const uint32_t own = ownb[p];
     nb[p] = (q >= 0 ? nb[q] : 0u) + (own >> 1) - (own & 1u);
+    if (nd.n == 0) return;
+    const uint32_t fid = q >= 0 ? first_id[q] : loc[nd.loff];
+    first_id[p] = fid;
+    if (slide_cols && nd.l) {
+        const uint32_t block_end = (((nd.last - win_lo) >> rb_shift) + 1u) << rb_shift;
+        if (fid + slide_cols < block_end) atomicExch(err, 9);
+    }
 }
 
 struct BoundSlots {   // slots of a boundary list: 16-byte aligned like the id lists (ListSlots)
@@ -228,7 +240,6 @@ k_scatter_diff(const Unit* __restrict__ units, const uint32_t* __restrict__ n_un
     const uint32_t n_units = *n_units_ptr;
     const uint32_t R = 1u << rb_shift;
     const uint32_t stride = tile_cols + kRowPad;   // padding words: see red_shared_add_below
-    const uint32_t pad_col = tile_cols + lane;
     const uint32_t tile_saddr = (uint32_t)__cvta_generic_to_shared(tile);
     const uint32_t rows_saddr = (uint32_t)__cvta_generic_to_shared(&s_rows[warp][0]);
     constexpr uint32_t kNone = 0xFFFFFFFFu;
@@ -252,11 +263,12 @@ k_scatter_diff(const Unit* __restrict__ units, const uint32_t* __restrict__ n_un
                 // and after the last aligned one go by ordinary reductions.  A warp per row; only the columns below the
                 // diagonal exist.
                 const uint32_t row0 = cur_key << rb_shift;
+                const uint32_t col0 = row0 + R > tile_cols ? row0 + R - tile_cols : 0u;   // sliding window (make_plan): the tile's first column
                 for (uint32_t r = warp; r < R; r += (blockDim.x >> 5)) {
                     const uint32_t row = row0 + r;                 // relative to id_lo, like the columns
-                    const uint32_t nc = min(tile_cols, row);
+                    const uint32_t nc = min(tile_cols, row - min(row, col0));
                     if (nc == 0 || row >= num_rows) continue;   // (the last row block may reach past the matrix: nothing was added there)
-                    const uint64_t out0 = tri_offset((uint64_t)row + id_lo) + id_lo;
+                    const uint64_t out0 = tri_offset((uint64_t)row + id_lo) + id_lo + col0;
                     const uint32_t sh = (uint32_t)out0 & 3u;
                     uint32_t* src = tile + r * stride;
                     uint32_t carry = 0;
@@ -302,7 +314,9 @@ k_scatter_diff(const Unit* __restrict__ units, const uint32_t* __restrict__ n_un
         if (threadIdx.x == 0) s_next_job = un.job_begin;
         __syncthreads();
         const uint32_t row0 = un.key << rb_shift;
-        const uint32_t row_base = tile_saddr - row0 * 4u * stride;   // accumulators of row r start at (4 r) * stride + row_base
+        const uint32_t col0 = row0 + R > tile_cols ? row0 + R - tile_cols : 0u;   // first column of the tile (sliding window; 0 when whole rows fit)
+        const uint32_t row_base = tile_saddr - row0 * 4u * stride - col0 * 4u;   // cell (r, c) sits at (4 r) * stride + 4 c + row_base
+        const uint32_t pad_col = col0 + tile_cols + lane;                          // this lane's padding word, as a column
         for (;;) {
             uint32_t jb = 0;
             if (lane == 0) jb = atomicAdd(&s_next_job, kDiffBatch);

@@ -206,7 +206,7 @@ __device__ __forceinline__ uint32_t gamma_next(const uint64_t* __restrict__ w, u
 constexpr int kDecodeThreads = 128;
 constexpr uint32_t kDecodeStage = 10240;  // ids (40 KB)
 constexpr uint32_t kSmallL = 8;           // see enumerate_jobs
-constexpr uint32_t kDecodeHistKeys = 192;   // row blocks the decoder can count for: 3072 samples in 16-row blocks
+constexpr uint32_t kDecodeHistKeys = 512;   // row blocks the decoder can count for: 16384 samples in 32-row blocks
 struct DecodeHist {
     uint32_t enabled, rb_shift, nkeys;
     uint64_t per;                       // patterns per block of the fill pass (a multiple of kDecodeThreads)
@@ -230,7 +230,7 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
     // rounding is harmless; the job counts are exact.
     __shared__ uint32_t s_pack[kDecodeHistKeys];
     if (dh.enabled) {
-        for (uint32_t k = threadIdx.x; k < kDecodeHistKeys; k += kDecodeThreads) s_pack[k] = 0;
+        for (uint32_t k = threadIdx.x; k < dh.nkeys; k += kDecodeThreads) s_pack[k] = 0;
         __syncthreads();
     }
     unsigned long long my_updates = 0;
@@ -1090,6 +1090,7 @@ struct kdbx_ctx {
     // the same signature recompute everything on the device but never wait for it: one synchronisation at the
     // end of the call, none inside.
     uint64_t load_gen = 0;
+    uint64_t no_slide_gen = ~0ull;   // load_gen of a staged trie whose lists do not fit the sliding column window (make_plan)
     struct StepMeta {
         bool prep_valid = false;   // sum_l / sum_n / sum_cost / levels belong to load_gen
         uint64_t prep_gen = 0;
@@ -1098,7 +1099,7 @@ struct kdbx_ctx {
         uint32_t row_begin = 0, row_end = 0, part = 0, num_parts = 0, win_lo = 0, win_hi = 0;
         uint32_t tile_cols = 0, tile_rows = 0, threads = 0, unit_updates = 0, flags = 0;
         uint64_t chunk = 0;
-        bool resident = false, diff = false;
+        bool resident = false, diff = false, out_aligned = true;
         uint32_t nchunks = 0;
         unsigned scatter_grid = 0;
         std::vector<uint64_t> bounds;     // chunk boundaries (chunked mode)
@@ -1185,20 +1186,34 @@ int scan_exclusive_u32(kdbx_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_
 struct Plan {
     uint32_t tile_cols = 0, tile_rows = 0, rb_shift = 0, T = 0, RB = 0, unit_updates = 0, threads = 0;
     uint32_t lo = 0, Nw = 0;     // sample window: ids lo .. lo + Nw, the kernels see ids relative to lo
+    bool slide = false;          // one SLIDING column window per row block (see make_plan)
     uint64_t chunk = 0;
     size_t smem = 0, smem_diff = 0;
 };
 
 constexpr size_t kMaxTileBytes = 220 * 1024;  // of the 227 KB a CTA may use (the boundary-form kernel adds 4 KB of static shared memory): 32 rows x 1728 columns
-constexpr uint32_t kMaxOneWindowCols = 3072;  // one column window: 32-row tiles up to 1728 columns, 16-row tiles up to 3072
+constexpr uint32_t kMaxOneWindowCols = 1728;  // the widest tile of 32 rows (one column window holding whole rows)
 
-int make_plan(kdbx_ctx* ctx, Plan& pl) {
+// allow_slide: beyond kMaxOneWindowCols samples, try ONE column window per row block that ends right above the block's rows
+// and covers the kMaxOneWindowCols columns below them (col0 = block end - tile_cols).  It holds every list entry a row of
+// the block can receive iff no pattern's full list reaches further down than that — true for databases whose related
+// samples sit close together in sample order (clusters, clades, the parts of a sharded database); k_pull_level checks it
+// per pattern, and a database that fails is re-planned with 1024-column windows and the id form.  With it the headline
+// path (decoder job counts, boundary lists, no second enumeration) is not limited to 1728 samples but to
+// 32 * kDecodeHistKeys.
+int make_plan(kdbx_ctx* ctx, Plan& pl, bool allow_slide = false) {
     pl.lo = ctx->win_lo;
     const uint32_t N = ctx->win_hi - ctx->win_lo;
     pl.Nw = N;
     uint32_t tc = ctx->cfg.tile_cols;
-    // default: whole rows (one column window) up to 3072 samples (the rows of a tile halve beyond 1728), 1024-column windows beyond
-    if (tc == 0) tc = N <= kMaxOneWindowCols ? std::max<uint32_t>(32u, (N + 31u) & ~31u) : 1024u;
+    // default: whole rows (one column window) up to 1728 samples; beyond, a sliding window of that width if allowed,
+    // else 1024-column windows
+    pl.slide = false;
+    if (tc == 0) {
+        if (N <= kMaxOneWindowCols) tc = std::max<uint32_t>(32u, (N + 31u) & ~31u);
+        else if (allow_slide && N <= 32u * kDecodeHistKeys && ctx->cfg.tile_rows == 0) { tc = kMaxOneWindowCols; pl.slide = true; }
+        else tc = 1024u;
+    }
     if (tc < 32 || (tc & 31)) return ctx->fail(KDBX_ERR_ARG, "tile_cols must be a multiple of 32");
     uint32_t tr = ctx->cfg.tile_rows;
     if (tr == 0) {
@@ -1214,6 +1229,7 @@ int make_plan(kdbx_ctx* ctx, Plan& pl) {
     {   // windows per row block: enough to reach column 0 from the end of the last block (see win_hi)
         const uint64_t hi_max = ((uint64_t)pl.RB * tr + 31u) & ~(uint64_t)31u;
         pl.T = (uint32_t)std::max<uint64_t>(1, (hi_max + tc - 1) / tc);
+        if (pl.slide) pl.T = 1;
     }
     if ((uint64_t)pl.T * pl.RB >= ((uint64_t)1 << 31)) return ctx->fail(KDBX_ERR_ARG, "too many (row block, column tile) keys");
     pl.smem = ((size_t)tr * (tc + kRowPad) * 4 + 15) & ~(size_t)15;  // padding words per row, see k_scatter_add
@@ -1238,6 +1254,7 @@ int error_from_flag(kdbx_ctx* ctx, int flag) {
     if (flag == 6) return ctx->fail(KDBX_ERR_ARG, "k-mer table points at a pattern that does not exist");
     if (flag == 7) return ctx->fail(KDBX_ERR_ARG, "a sample id lies outside the declared sample window");
     if (flag == 8) return ctx->fail(KDBX_ERR_STATE, "internal: boundary lists exceed their buffer");
+    if (flag == 9) return ctx->fail(KDBX_ERR_STATE, "internal: a sample list reaches below its sliding column window");
     return KDBX_OK;
 }
 int check_device_error(kdbx_ctx* ctx) {
@@ -1432,19 +1449,27 @@ int finish_upload(kdbx_ctx* ctx) {
 // list form) — three synchronisations.  It leaves them in ctx->meta; every later call with the same signature
 // enqueues the whole step without waiting for the device and synchronises once, at the end, for U and the error
 // flag.  Nothing of the RESULT is cached: every call decodes, expands, buckets and scatters again.
-int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uint32_t* d_out, kdbx_stats* stats,
-                        uint32_t part = 0, uint32_t num_parts = 1) {
+constexpr int kRetryWithoutSlide = 1;   // internal: the sliding column window does not hold this database's lists
+
+int all2all_rows_device_impl(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uint32_t* d_out, kdbx_stats* stats,
+                             uint32_t part, uint32_t num_parts, bool allow_slide) {
     if (!ctx->loaded) return ctx->fail(KDBX_ERR_STATE, "no patterns loaded (call kdbx_load_patterns first)");
     if (row_begin > row_end || row_end > ctx->N) return ctx->fail(KDBX_ERR_ARG, "bad row range [%u,%u) for %u samples", row_begin, row_end, ctx->N);
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     Plan pl;
-    if (int rc = make_plan(ctx, pl)) return rc;
+    {   // the sliding window serves the headline path only (all rows of the window, one part, boundary lists, aligned output)
+        const bool all_rows0 = row_begin <= ctx->win_lo && row_end >= ctx->win_hi;
+        const bool slide_ok = allow_slide && all_rows0 && num_parts == 1 && !(ctx->cfg.flags & (KDBX_FLAG_CHUNKED_LISTS | KDBX_FLAG_ID_LISTS)) &&
+                              (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0;
+        if (int rc = make_plan(ctx, pl, slide_ok)) return rc;
+    }
     kdbx_ctx::StepMeta& M = ctx->meta;
     const bool cached = M.valid && M.gen == ctx->load_gen && M.row_begin == row_begin && M.row_end == row_end && M.part == part &&
                         M.num_parts == num_parts && M.win_lo == ctx->win_lo && M.win_hi == ctx->win_hi && M.tile_cols == pl.tile_cols &&
                         M.tile_rows == pl.tile_rows && M.threads == pl.threads && M.unit_updates == pl.unit_updates &&
-                        M.flags == ctx->cfg.flags && M.chunk == pl.chunk;
+                        M.flags == ctx->cfg.flags && M.chunk == pl.chunk &&
+                        M.out_aligned == ((reinterpret_cast<uintptr_t>(d_out) & 15u) == 0);   // (the boundary form needs an aligned output)
     kdbx_stats s{};
     s.ms_upload = ctx->ms_upload;
     ctx->ev_used = 0;
@@ -1539,16 +1564,19 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
         launches += 3;
         const bool want_nb = dh.ownb != nullptr;
         if (want_nb) {   // entries per boundary list (parents first) and their offsets
-            CK(ctx->nb.ensure(ctx->P * 4)); CK(ctx->boff.ensure((ctx->P + 1) * 8));
+            CK(ctx->nb.ensure(ctx->P * 4)); CK(ctx->boff.ensure((ctx->P + 1) * 8)); CK(ctx->first_id.ensure(ctx->P * 4));
             uint32_t n_launch = 0;
             for (const auto& lv : ctx->levels) if (lv.second > lv.first) ++n_launch;
             if (n_launch) {
-                if (int rc = launch_level_graph(ctx, ctx->g_pull, {ctx->order.p, ctx->nodes.p, ctx->ownb.p, ctx->nb.p}, [&] {
+                if (int rc = launch_level_graph(ctx, ctx->g_pull, {ctx->order.p, ctx->nodes.p, ctx->ownb.p, ctx->nb.p, ctx->loc.p, ctx->first_id.p,
+                                                                  reinterpret_cast<const void*>((uintptr_t)(pl.slide ? pl.tile_cols : 0u) | ((uintptr_t)ctx->win_lo << 32))}, [&] {
                         for (size_t k = 0; k < ctx->levels.size(); ++k) {
                             const uint32_t b = ctx->levels[k].first, e = ctx->levels[k].second;
                             if (e <= b) continue;
                             k_pull_level<<<blocks_for(e - b, 256), 256, 0, st>>>(e - b, ctx->order.as<uint32_t>() + b, ctx->nodes.as<Node>(),
-                                                                                  ctx->ownb.as<uint32_t>(), ctx->nb.as<uint32_t>());
+                                                                                  ctx->ownb.as<uint32_t>(), ctx->nb.as<uint32_t>(), ctx->loc.as<uint32_t>(),
+                                                                                  ctx->first_id.as<uint32_t>(), pl.slide ? pl.tile_cols : 0u, ctx->win_lo,
+                                                                                  pl.rb_shift, ctx->err_flag.as<int>());
                         }
                     })) return rc;
             }
@@ -1570,14 +1598,20 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
             CK(cudaMemcpyAsync(&h[2], ctx->bucket_off.as<uint32_t>() + nkeys, 4, cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(&h[3], ctx->err_flag.p, 4, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
+            if (pl.slide && (uint32_t)h[3] == 9u) {   // a list reaches below its window: plan again without it
+                CK(cudaMemsetAsync(ctx->err_flag.p, 0, 16, st));
+                return kRetryWithoutSlide;
+            }
             if (int rc = error_from_flag(ctx, (int)(uint32_t)h[3])) return rc;   // decode errors stop the call before any list is built
             jobs_total = (uint32_t)h[2];
             diff_slots = h[1];
             // boundary form when it holds at most 3/4 of the entries of the id form (a run of consecutive ids costs 2
             // entries whatever its length; a lone id costs 2 instead of 1), or when the caller insists
             diff = want_nb && (((ctx->cfg.flags & KDBX_FLAG_BOUNDARY_LISTS) != 0) || h[0] * 4 <= ctx->sum_l * 3);
+            if (pl.slide && !diff) return kRetryWithoutSlide;   // (the sliding window is built for the boundary form only)
         }
     }
+    if (pl.slide && !hist_by_decoder) return kRetryWithoutSlide;   // (lists not resident after all)
     CK(ctx->flat.ensure(diff ? (diff_slots + 64) * 4 : resident ? (ctx->sum_n + 64) * 4 : cap * 4));
     if (resident && !diff) CK(ctx->first_id.ensure(ctx->P * 4));
     if (!resident) { CK(ctx->jobs.ensure(cap * sizeof(Job))); CK(ctx->units.ensure(cap * sizeof(Unit))); }
@@ -1776,10 +1810,21 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
     M.valid = true; M.gen = ctx->load_gen; M.row_begin = row_begin; M.row_end = row_end; M.part = part; M.num_parts = num_parts;
     M.win_lo = ctx->win_lo; M.win_hi = ctx->win_hi; M.tile_cols = pl.tile_cols; M.tile_rows = pl.tile_rows; M.threads = pl.threads;
     M.unit_updates = pl.unit_updates; M.flags = ctx->cfg.flags; M.chunk = pl.chunk;
+    M.out_aligned = (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0;
     M.resident = resident; M.diff = diff; M.nchunks = nchunks; M.scatter_grid = scatter_grid; M.diff_slots = diff_slots;
     if (!resident) M.bounds = bounds;
     M.jobs_in_pass = jobs_in_pass;
     return KDBX_OK;
+}
+
+int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uint32_t* d_out, kdbx_stats* stats,
+                        uint32_t part = 0, uint32_t num_parts = 1) {
+    int rc = all2all_rows_device_impl(ctx, row_begin, row_end, d_out, stats, part, num_parts, ctx->no_slide_gen != ctx->load_gen);
+    if (rc == kRetryWithoutSlide) {
+        ctx->no_slide_gen = ctx->load_gen;   // remembered for this staged trie
+        rc = all2all_rows_device_impl(ctx, row_begin, row_end, d_out, stats, part, num_parts, false);
+    }
+    return rc;
 }
 
 #include "sparse.cuh"
@@ -2099,6 +2144,17 @@ int kdbx_all2all_dense_reduce_scatter(kdbx_ctx* ctx, uint32_t* out_block, uint64
 int kdbx_csv_dense_rows(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, char* text, uint64_t capacity, uint64_t* row_off, uint64_t* bytes) {
     if (!ctx) return KDBX_ERR_ARG;
     return csv_dense_rows(ctx, row_begin, row_end, text, capacity, row_off, bytes);
+}
+
+int kdbx_stage_matrix(kdbx_ctx* ctx, const uint32_t* tri, uint32_t num_samples) {
+    if (!ctx) return KDBX_ERR_ARG;
+    return stage_matrix(ctx, tri, num_samples);
+}
+
+int kdbx_distance_dense_rows(kdbx_ctx* ctx, int metric, const uint32_t* sample_kmers, uint32_t row_begin, uint32_t row_end, char* text,
+                             uint64_t capacity, uint64_t* row_off, uint64_t* bytes) {
+    if (!ctx) return KDBX_ERR_ARG;
+    return distance_dense_rows(ctx, metric, sample_kmers, row_begin, row_end, text, capacity, row_off, bytes);
 }
 
 int kdbx_row_updates(kdbx_ctx* ctx, uint64_t* out) {

@@ -27,6 +27,7 @@ struct Params {
     int gpu = -1;              // -gpu <ordinal> (ours)
     int num_gpus = 1;          // -gpus <n> (ours): row-block sharding over n devices
     bool host_build = false;   // build -host-build (ours): run the host builder explicitly (machines without a GPU)
+    bool device_distance = false;   // distance -device (ours): measure + six-decimal text on the GPU (explicit; no fallback)
     bool host_csv = false;     // all2all -host-csv (ours): format the dense table on the host instead of on the device
     Alphabet alphabet = Alphabet::make(kNt);
     OutputFilters filters;

@@ -80,6 +80,7 @@ bool parse_params(int argc, char** argv, Params& p) {
     find_option(a, "-gpu", p.gpu);
     find_option(a, "-gpus", p.num_gpus);
     p.host_csv = find_switch(a, "-host-csv");
+    p.device_distance = find_switch(a, "-device");
     if (p.num_gpus < 1) p.num_gpus = 1;
 
     if (p.mode == "build") {

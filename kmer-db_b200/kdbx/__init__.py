@@ -110,7 +110,7 @@ class Totals(C.Structure):
 # every symbol include/kdbx.h declares (tests check that the library exports all of them)
 KDBX_SYMBOLS = ["kdbx_abi_version", "kdbx_device_count", "kdbx_open", "kdbx_close", "kdbx_last_error",
                 "kdbx_host_alloc", "kdbx_host_free", "kdbx_load_patterns", "kdbx_set_sample_window", "kdbx_row_updates", "kdbx_all2all_dense",
-                "kdbx_all2all_dense_rows", "kdbx_all2all_dense_rows_device", "kdbx_all2all_dense_part_device", "kdbx_all2all_sparse", "kdbx_all2all_sparse_rows", "kdbx_csv_dense_rows", "kdbx_free_csr",
+                "kdbx_all2all_dense_rows", "kdbx_all2all_dense_rows_device", "kdbx_all2all_dense_part_device", "kdbx_all2all_sparse", "kdbx_all2all_sparse_rows", "kdbx_csv_dense_rows", "kdbx_stage_matrix", "kdbx_distance_dense_rows", "kdbx_free_csr",
                 "kdbx_load_hashtables", "kdbx_new2all_batch", "kdbx_debug_fetch", "kdbx_comm_unique_id", "kdbx_comm_init_rank",
                 "kdbx_comm_init_all", "kdbx_comm_destroy", "kdbx_all2all_dense_reduce_scatter_device", "kdbx_all2all_dense_reduce_scatter",
                 "kdbx_builder_open", "kdbx_builder_close", "kdbx_builder_adopt", "kdbx_builder_add_sequence", "kdbx_builder_add_kmers",
@@ -155,6 +155,8 @@ def load():
     k.kdbx_all2all_dense_rows_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, P(Stats)]
     k.kdbx_all2all_dense_part_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, P(Stats)]
     k.kdbx_csv_dense_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, P(C.c_uint64)]
+    k.kdbx_stage_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    k.kdbx_distance_dense_rows.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, P(C.c_uint64)]
     k.kdbx_comm_unique_id.argtypes = [C.c_void_p]
     k.kdbx_comm_init_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     k.kdbx_comm_init_all.argtypes = [P(C.c_void_p), C.c_int]
@@ -513,6 +515,22 @@ class Context:
         self._check(self._k.kdbx_csv_dense_rows(self._p, row_begin, row_end, None, 0, off.ctypes.data, C.byref(total)))
         text = np.zeros(max(1, total.value), np.uint8)
         self._check(self._k.kdbx_csv_dense_rows(self._p, row_begin, row_end, text.ctypes.data, total.value, off.ctypes.data, C.byref(total)))
+        return text[:total.value].tobytes(), off
+
+    def stage_matrix(self, tri: np.ndarray, num_samples: int):
+        tri = np.ascontiguousarray(tri, np.uint32)
+        self._check(self._k.kdbx_stage_matrix(self._p, tri.ctypes.data if tri.size else None, num_samples))
+
+    def distance_dense_rows(self, metric: str, sample_kmers, row_begin, row_end):
+        """(text bytes, row offsets) of the six-decimal measure table for rows of the resident matrix."""
+        cnt = np.ascontiguousarray(sample_kmers, np.uint32)
+        rows = row_end - row_begin
+        off = np.zeros(rows + 1, np.uint64)
+        total = C.c_uint64(0)
+        m = {"jaccard": 0, "min": 1, "max": 2, "cosine": 3, "num-kmers": 4}[metric]
+        self._check(self._k.kdbx_distance_dense_rows(self._p, m, cnt.ctypes.data, row_begin, row_end, None, 0, off.ctypes.data, C.byref(total)))
+        text = np.zeros(max(1, total.value), np.uint8)
+        self._check(self._k.kdbx_distance_dense_rows(self._p, m, cnt.ctypes.data, row_begin, row_end, text.ctypes.data, total.value, off.ctypes.data, C.byref(total)))
         return text[:total.value].tobytes(), off
 
     # ---- several GPUs (kdbx.h: kdbx_comm_*) ----

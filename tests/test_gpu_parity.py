@@ -456,8 +456,8 @@ def test_cli_all2all_on_two_gpus(libs, golden_dbs, tmp_path):
 
 @pytest.mark.parametrize("N", [1025, 1728, 1729, 2049, 3072, 3073])
 def test_sample_counts_around_the_window_sizes(libs, oracle, N):
-    """N around the tile limits: up to 1728 columns a tile has 32 rows, up to 3072 it has 16 (still one column window:
-    boundary lists, decoder job counts), 3073 is the first size with 1024-column windows."""
+    """N around the tile limit: up to 1728 samples a tile holds whole rows (boundary lists, decoder job counts); beyond,
+    these random tries (lists reaching anywhere) fail the locality test of the sliding window and run the id form."""
     rng = np.random.default_rng(N)
     a, _ = ou.random_trie(rng, N, 2500, max_local=40, big_weights=True, dense_lists=(N % 2 == 1))
     want, U = ou.oracle_all2all(oracle, N, a)
@@ -465,7 +465,7 @@ def test_sample_counts_around_the_window_sizes(libs, oracle, N):
     assert st.updates == U and np.array_equal(got, want)
     got, st = _run(libs, N, a, flags=libs.FLAG_BOUNDARY_LISTS)
     assert st.updates == U and np.array_equal(got, want)
-    assert st.list_form == (1 if N <= 3072 else 0)   # beyond one window the id form runs, whatever the flag asks for
+    assert st.list_form == (1 if N <= 1728 else 0)   # beyond one window the id form runs, whatever the flag asks for
 
 
 def test_pattern_count_guard(libs):
@@ -479,3 +479,38 @@ def test_pattern_count_guard(libs):
             v.num_patterns = bad
             with pytest.raises(libs.KdbxError, match=r"num_patterns must be in \[1, 2\^31\)"):
                 c.load_patterns(v, keep)
+
+
+def test_unaligned_device_output_takes_the_id_form(libs, oracle):
+    """The boundary form flushes its tiles with 16-byte bulk reductions; an output pointer that is not 16-byte aligned
+    gets the id form instead (same bits), also when the aligned call before it cached the boundary form."""
+    import torch
+    rng = np.random.default_rng(91)
+    N = 500
+    a, _ = ou.random_trie(rng, N, 3000, max_local=30, big_weights=True, dense_lists=True)
+    want, U = ou.oracle_all2all(oracle, N, a)
+    cells = ou.tri_cells(N)
+    with libs.Context(device=0) as c:
+        v, keep = libs.view_from_arrays(N, a["num_kmers"], a["parent_id"], a["n"], a["l"], a["last"], a["bits"], a["payload_off"], a["payload"])
+        c.load_patterns(v, keep)
+        buf = torch.zeros(cells + 8, dtype=torch.int32, device="cuda:0")
+        for shift, form in ((0, 1), (0, 1), (1, 0), (3, 0), (4, 1)):
+            st = c.all2all_dense_rows_device(0, N, buf[shift:].data_ptr())
+            torch.cuda.synchronize()
+            assert st.list_form == form and st.updates == U
+            assert np.array_equal(buf[shift:shift + cells].cpu().numpy().view(np.uint32), want)
+
+
+@pytest.mark.parametrize("N,clusters,form", [(4000, 16, 1), (6000, 5, 1), (4000, 2, 0), (9000, 30, 1)])
+def test_sliding_column_window(libs, oracle, N, clusters, form):
+    """Beyond 1728 samples: one column window per row block that slides with the diagonal (make_plan).  Databases whose
+    lists stay within 1728 ids below their rows (clusters up to that size) keep the headline path — boundary lists, decoder
+    job counts — at any N up to 16384; a database with wider lists (two clusters of 2000) is re-planned with the id form."""
+    t = libs.Trie.synth(num_samples=N, num_clusters=clusters, genome_kmers=2500, seed=N + clusters, mutation_rate=0.01)
+    want, U = ou.oracle_all2all(oracle, N, t.arrays())
+    with libs.Context(device=0) as c:
+        c.load_patterns(t)
+        for _ in range(2):   # second call: cached sizes, no host round trips
+            got, st = c.all2all_dense()
+            assert st.updates == U and st.list_form == form
+            assert np.array_equal(got, want)
