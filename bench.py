@@ -458,6 +458,16 @@ def main():
     own = _own_cells(rank, block, cells)
     checksum = sum_over_ranks(int((d_out[:own].to(torch.int64) & 0xFFFFFFFF).sum().item()) if own else 0)
     physical = sum_over_ranks(int(st.physical_updates))
+    # what every rank did in the last step (the collective's time on a rank is mostly its wait for the slowest one)
+    per_rank = None
+    if dist is not None:
+        mine = torch.tensor([st.ms_total - st.ms_collective, st.ms_scatter, st.ms_collective, float(window[1] - window[0]), float(st.list_form),
+                             float(U_rank), float(P)], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"compute_ms": round(float(x[0]), 2), "scatter_ms": round(float(x[1]), 2), "collective_and_wait_ms": round(float(x[2]), 2),
+                     "window_ids": int(x[3]), "list_form": ["ids", "run boundaries"][int(x[4])], "updates": int(x[5]), "patterns": int(x[6])}
+                    for x in allr]
     assert checksum % (1 << 60) == expected_sum, "sum of the matrix != sum over patterns of num_kmers * n (n - 1) / 2"
 
     # ---- end-to-end leg: host trie -> H2D -> compute (-> reduce-scatter) -> D2H of every block ------------------
@@ -591,6 +601,8 @@ def main():
         "list_form": ["ids", "run boundaries"][int(st.list_form)],
         "physical_updates_per_step": physical,
     }
+    if per_rank:
+        line["per_rank_last_step"] = per_rank
     if parity:
         line.update(parity)
     print(json.dumps(line))

@@ -256,3 +256,46 @@ def test_dense_csv_formatted_on_the_device(libs, oracle, cli, golden_dbs, tmp_pa
     cli(tmp_path, "all2all", db, tmp_path / "dev.csv")
     cli(tmp_path, "all2all", "-host-csv", db, tmp_path / "host.csv")
     assert ou.read_bytes(tmp_path / "dev.csv") == ou.read_bytes(dense) == ou.read_bytes(tmp_path / "host.csv")
+
+
+def test_distance_on_the_device(libs, oracle, cli, ref_fixtures, tmp_path):
+    """kdbx_distance_dense_rows / `distance -device`: jaccard, min, max, cosine and num-kmers with six decimals from the
+    matrix in HBM — the reference's golden files for the virus table, the host formatter on a generated one, and the
+    arithmetic restated with numpy (IEEE division and square root are correctly rounded everywhere)."""
+    for m in ("jaccard", "min", "max", "cosine"):
+        cli(ref_fixtures, "distance", m, "-device", "test/virus/k18.csv", tmp_path / f"dev.{m}")
+        assert ou.read_bytes(tmp_path / f"dev.{m}") == ou.read_bytes(ref_fixtures / f"test/virus/k18.csv.{m}")
+    r = cli(ref_fixtures, "distance", "mash", "-device", "test/virus/k18.csv", tmp_path / "x", check=False)
+    assert r.returncode != 0 and "logarithm-based measures run on the host" in r.stderr
+    r = cli(ref_fixtures, "distance", "jaccard", "-device", "test/virus/k18.n2a.csv", tmp_path / "x", check=False)
+    assert r.returncode != 0 and "dense triangular table" in r.stderr
+    t = libs.Trie.synth(num_samples=300, num_clusters=3, genome_kmers=50000, seed=17)
+    N = 300
+    cnt = np.array(t.sample_kmer_counts(), np.uint32)
+    want, _ = ou.oracle_all2all(oracle, N, t.arrays())
+
+    def f6(v):
+        if v == 0:
+            return "0"
+        x = int(v * 1000000.0 + 0.5)
+        return f"{x // 1000000}.{x % 1000000:06d}"
+    with libs.Context(device=0) as c:
+        c.load_patterns(t)
+        c.all2all_dense()
+        for m in ("jaccard", "min", "max", "cosine", "num-kmers"):
+            text, off = c.distance_dense_rows(m, cnt, 0, N)
+            for s in (0, 1, 2, 57, 299):
+                row = want[ou.tri_cells(s):ou.tri_cells(s) + s].astype(np.float64)
+                a, b = np.float64(cnt[s]), cnt[:s].astype(np.float64)
+                with np.errstate(invalid="ignore", divide="ignore"):
+                    v = {"jaccard": row / ((cnt[s] + cnt[:s] - want[ou.tri_cells(s):ou.tri_cells(s) + s]).astype(np.uint32)).astype(np.float64),
+                         "min": row / np.minimum(a, b), "max": row / np.maximum(a, b),
+                         "cosine": row / np.sqrt((cnt[s] * cnt[:s]).astype(np.uint32).astype(np.float64)), "num-kmers": row}[m]
+                assert text[int(off[s]):int(off[s + 1])].decode() == "".join(f6(float(x)) + "," for x in v), (m, s)
+        c.stage_matrix(want, N)
+        text2, off2 = c.distance_dense_rows("jaccard", cnt, 10, 20)
+        text1, off1 = c.distance_dense_rows("jaccard", cnt, 0, N)
+        assert text2 == text1[int(off1[10]):int(off1[20])]
+        bad = cnt.copy(); bad[5] = 0
+        with pytest.raises(libs.KdbxError, match="has no k-mers"):
+            c.distance_dense_rows("jaccard", bad, 0, N)
