@@ -159,7 +159,7 @@ int kdbx_load_patterns(kdbx_ctx* ctx, const kdbx_trie_view* view);
 /* Optional hint after kdbx_load_patterns: every sample id of the staged trie lies in [lo, hi).  The part of a
  * sharded database that one GPU holds (kdbxh_partition) covers a narrow band of sample ids; with the band declared
  * the dense all2all lays its accumulator tiles over that band only, i.e. it plans like a database of hi - lo
- * samples (one column window up to 3072 samples).  The result is unchanged — rows and columns outside the band
+ * samples (whole rows in one accumulator tile up to 1728 samples, a sliding window beyond).  The result is unchanged — rows and columns outside the band
  * are zero — and an id outside the band is an error (KDBX_ERR_ARG), not silently dropped.  Reset to [0, N) by
  * every kdbx_load_patterns.  No analogue in the reference (src/similarity_calculator.cpp:290-329 blocks by
  * pattern count only). */
