@@ -203,6 +203,11 @@ __device__ __forceinline__ uint32_t gamma_next(const uint64_t* __restrict__ w, u
 // stage is then not needed at all.  The rule must equal the fill pass's (walk_runs) exactly: a run
 // ends where the row block changes; a job counts iff its weight and its number of updates
 // k*i + k(k-1)/2 are non-zero.
+// What a job costs the scatter kernel besides its updates (its record, two dependent loads, the row table, the dispatch),
+// in updates: without it a row block with ten million tiny jobs (the first rows of every cluster: short lists, one or two
+// updates each) weighed next to nothing, got ONE work unit, and that unit kept a single CTA busy for as long as the rest of
+// the pass took (sm__cycles_active: 55 % of elapsed at 2000 genomes, 84 % at config 2; profiles/r02_ab_notes.txt).
+constexpr unsigned long long kJobCost = 4096;
 constexpr int kDecodeThreads = 128;
 constexpr uint32_t kDecodeStage = 10240;  // ids (40 KB)
 constexpr uint32_t kSmallL = 8;           // see enumerate_jobs
@@ -344,7 +349,7 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
             const uint32_t pk = s_pack[k];
             if (!pk) continue;
             atomicAdd(&dh.blockhist[(p0 / dh.per) * dh.nkeys + k], pk >> 20);
-            atomicAdd(&dh.work[k], ((unsigned long long)(pk & 0xFFFFFu) << 10) + (pk >> 20));  // never 0 for a used key
+            atomicAdd(&dh.work[k], ((unsigned long long)(pk & 0xFFFFFu) << 10) + (unsigned long long)(pk >> 20) * kJobCost);  // never 0 for a used key
         }
     }
 }
@@ -699,7 +704,7 @@ k_job_hist_smem(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const 
                    [&](uint32_t key, const Job&, unsigned long long upd, uint32_t w) {
                        if (w == 0 || upd == 0) return;  // adds of 0 are skipped, but still counted in U
                        atomicAdd(&s_hist[key], 1u);
-                       atomicAdd(&s_work[key], upd);
+                       atomicAdd(&s_work[key], upd + kJobCost);
                    });
     for (int o = 16; o; o >>= 1) updates += __shfl_xor_sync(0xffffffffu, updates, o);
     if (lane == 0 && updates) atomicAdd(total_updates, updates);
@@ -781,7 +786,7 @@ k_job_hist(uint64_t p0, uint64_t p1, const Node* __restrict__ nodes, const uint6
                    [&](uint32_t key, const Job&, unsigned long long upd, uint32_t w) {
                        if (w == 0 || upd == 0) return;
                        atomicAdd(&hist[key], 1u);
-                       atomicAdd(&work[key], upd);
+                       atomicAdd(&work[key], upd + kJobCost);
                    });
     for (int o = 16; o; o >>= 1) updates += __shfl_xor_sync(0xffffffffu, updates, o);
     if (lane == 0 && updates) atomicAdd(total_updates, updates);
@@ -882,7 +887,7 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const uint4* p) {
     return v;
 }
 
-constexpr uint32_t kUnitsPerCta = 12;  // work units per CTA of a scatter pass when the plan does not fix their size (k_unit_count)
+constexpr uint32_t kUnitsPerCta = 24;  // work units per CTA of a scatter pass when the plan does not fix their size (k_unit_count)
 constexpr uint32_t kJobBatch = 8;  // jobs a warp claims at once (16 lanes load them as uint4 halves)
 
 // Last pass of a job over its k rows (see k_scatter_add): F complete 32-id groups (x0..x2), the partial
