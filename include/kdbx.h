@@ -290,6 +290,25 @@ int kdbx_load_hashtables(kdbx_ctx* ctx, const kdbx_tables_view* view);
 int kdbx_new2all_batch(kdbx_ctx* ctx, const uint64_t* kmers, const uint64_t* q_off, uint32_t n_queries,
                        uint32_t* out, kdbx_stats* stats);
 
+/* ---- database against database: one cell of the grid of all2all-parts ---------------------- */
+
+/* Replaces SimilarityCalculator::db2db_sp + SparseMatrix::compact2 (src/similarity_calculator.cpp:1225-1540,
+ * src/array.h:391-446) as All2AllPartsConsole::run calls them for every cell (row part i, column part j < i) of the
+ * grid of partial databases (src/console_all2all_parts.cpp:163-254): out row s1 (a sample of the ROW database) holds
+ * the ascending (s2, common) pairs of the samples s2 of the COLUMN database that share k-mers with it and pass the
+ * filter; common = number of k-mers present in both samples.  Both databases must be staged — kdbx_load_patterns
+ * AND kdbx_load_hashtables — on two contexts of the same device, with equal k-mer length and alphabet (equal numbers
+ * of prefix buckets).  The k-mers both databases hold are found by probing the column database's tables with every
+ * k-mer of the row database's tables (the reference merges the sorted buckets, :1262-1287), the (pattern, pattern)
+ * pairs are sorted and counted (:1310-1321), and every distinct pair adds its count to the cells of
+ * list(pattern1) x list(pattern2) (:1434-1517) in a dense block of rows in HBM, compacted like kdbx_all2all_sparse.
+ * filter->sample_kmers are the ROW database's "total-kmers", cols_sample_kmers the COLUMN database's (both needed iff
+ * metric bounds are given; CombinedFilter(row counts, column counts), src/console_all2all_parts.cpp:181-186).
+ * out->num_rows = samples of the row database; column ids are local to the column database.  stats->updates = number
+ * of cell updates, probes = k-mers of the row database, hits = k-mers found in both. */
+int kdbx_db2db_sparse(kdbx_ctx* rows_db, kdbx_ctx* cols_db, const kdbx_filter* filter, const uint32_t* cols_sample_kmers,
+                      kdbx_csr* out, kdbx_stats* stats);
+
 /* Pattern-sharded variant for multi-GPU runs: the trie is cut into chunks of patterns (the
  * library's unit of streaming, kdbx_config::chunk_ids); this call executes the chunks c with
  * c % num_parts == part and leaves a PARTIAL matrix (whole packed triangle, N(N-1)/2 cells) in

@@ -1128,7 +1128,7 @@ struct kdbx_ctx {
     DevBuf sp_cnt, sp_counts, sp_rowptr, sp_col, sp_val;
     // k-mer tables + query buffers (query.cuh)
     bool tables_loaded = false;
-    uint64_t num_tables = 0;
+    uint64_t num_tables = 0, total_slots = 0;
     float ms_upload_tables = 0.f;
     DevBuf slot_off, slots, q_off, q_kmers, q_keys, q_keys2, q_runkeys, q_runcnt, q_out;
     DevBuf qx_alpha, qx_seq, qx_raw, qx_sorted, qx_count;   // queries from sequences (build.cuh)
@@ -1836,6 +1836,7 @@ int all2all_rows_device(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, uin
 #include "comm.cuh"
 #include "csvfmt.cuh"
 #include "query.cuh"
+#include "db2db.cuh"
 #include "build.cuh"
 
 }  // namespace
@@ -2191,6 +2192,12 @@ int kdbx_all2all_sparse(kdbx_ctx* ctx, const kdbx_filter* filter, kdbx_csr* out,
 int kdbx_all2all_sparse_rows(kdbx_ctx* ctx, uint32_t row_begin, uint32_t row_end, const kdbx_filter* filter, kdbx_csr* out, kdbx_stats* stats) {
     if (!ctx) return KDBX_ERR_ARG;
     return all2all_sparse_impl(ctx, filter, out, stats, row_begin, row_end);
+}
+
+int kdbx_db2db_sparse(kdbx_ctx* rows_db, kdbx_ctx* cols_db, const kdbx_filter* filter, const uint32_t* cols_sample_kmers, kdbx_csr* out,
+                      kdbx_stats* stats) {
+    if (!rows_db) return KDBX_ERR_ARG;
+    return db2db_sparse_impl(rows_db, cols_db, filter, cols_sample_kmers, out, stats);
 }
 
 void kdbx_free_csr(kdbx_csr* csr) {

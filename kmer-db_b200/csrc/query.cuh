@@ -230,6 +230,7 @@ int load_hashtables_impl(kdbx_ctx* ctx, const kdbx_tables_view* v) {
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->ms_upload_tables = elapsed(a, b);
     ctx->num_tables = T;
+    ctx->total_slots = total;
     ctx->tables_loaded = true;
     return KDBX_OK;
 }

@@ -13,13 +13,14 @@ struct FilterDev {
     uint32_t lo, hi, nb;
     int32_t metric[4];
     double mlo[4], mhi[4];
-    const uint32_t* cnt;
+    const uint32_t* cnt;       // k-mer counts of the row samples
+    const uint32_t* cnt_col;   // ... of the column samples (the same array in all2all; another database's in db2db.cuh)
 };
 
 __device__ __forceinline__ bool cell_passes(const FilterDev& f, uint32_t v, uint32_t row, uint32_t col) {
     if (v == 0 || v < f.lo || v > f.hi) return false;
     for (uint32_t b = 0; b < f.nb; ++b) {
-        const uint32_t a = f.cnt[row], c = f.cnt[col];  // uint32 arithmetic wraps like the reference's num_kmers_t
+        const uint32_t a = f.cnt[row], c = f.cnt_col[col];  // uint32 arithmetic wraps like the reference's num_kmers_t
         double x;
         switch (f.metric[b]) {
             case KDBX_METRIC_JACCARD: x = __ddiv_rn((double)v, (double)(uint32_t)(a + c - v)); break;
@@ -99,6 +100,7 @@ int all2all_sparse_impl(kdbx_ctx* ctx, const kdbx_filter* filter, kdbx_csr* out,
             CK(ctx->sp_cnt.ensure(((size_t)N + 1) * 4));
             CK(cudaMemcpyAsync(ctx->sp_cnt.p, filter->sample_kmers, (size_t)N * 4, cudaMemcpyHostToDevice, st));
             f.cnt = ctx->sp_cnt.as<uint32_t>();
+            f.cnt_col = f.cnt;
         }
     }
     // row blocks: as many rows as fit the accumulator budget (free HBM minus working buffers)

@@ -43,6 +43,7 @@ void print_usage(const std::string& mode);
 void run_build(const Params& p);
 void run_all2all(const Params& p);
 void run_all2all_sparse(const Params& p);
+void run_all2all_parts(const Params& p);
 void run_new2all(const Params& p);
 void run_distance(const Params& p);
 

@@ -4,6 +4,7 @@
 //     build       BuildConsole::run            src/console_build.cpp:33-157     (host)
 //     all2all     All2AllConsole::run          src/console_all2all.cpp:7-89     (GPU)
 //     all2all-sp  All2AllSparseConsole::run    src/console_all2all_sparse.cpp:13-111 (GPU)
+//     all2all-parts All2AllPartsConsole::run   src/console_all2all_parts.cpp:11-371 (GPU)
 //     new2all     New2AllConsole::run          src/console_new2all.cpp:12-174   (GPU)
 //     distance    DistanceConsole::run         src/console_distance.cpp:7-213   (host)
 // plus two tools of ours: `synth` (pattern-level synthetic database) and `info`.
@@ -11,7 +12,14 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <fstream>
 #include <iostream>
+#include <iterator>
+#include <memory>
+#include <mutex>
+#include <thread>
 
 #include "build_device.h"
 #include "cli.h"
@@ -19,6 +27,7 @@
 #include "ingest.h"
 #include "kmer_db.h"
 #include "similarity_calculator.h"
+#include "numfmt.h"
 #include "synth.h"
 
 namespace kdbx {
@@ -166,6 +175,194 @@ void run_all2all_sparse(const Params& p) {
     std::cerr << "No. saved pairs: " << saved << std::endl;
 }
 
+// all2all-parts (src/console_all2all_parts.cpp:11-371): the input is a LIST of databases — the parts of one sample
+// collection, built separately with the same k and fraction — and the output is the sparse table of all their samples,
+// as all2all-sp would write it for one database holding all of them.  Grid row i = the samples of part i; its cells are
+// db2db_sp(part i, part j) for j < i and all2all_sp(part i) on the diagonal; a row of the table concatenates the row's
+// cells with the column ids shifted by the samples of the parts before (SparseMatrix::saveRowSparse(row, out, idx_shift),
+// src/array.h:625-637).  One grid row needs its own part and one column part at a time on the device.  With -gpus n the
+// grid rows are dealt to n devices (they are independent) and written in order.
+namespace {
+struct PartsGrid {
+    std::vector<std::string> files;
+    std::vector<uint32_t> part_samples, first_sample;   // per part
+    Trie all;                                            // header + names + k-mer counts of every sample, in order
+};
+
+// the text of grid row i_row (all lines of its samples); returns the number of pairs written
+uint64_t parts_grid_row(const Params& p, const PartsGrid& g, const SimilarityCalculator& calc, uint32_t i_row, bool row_is_staged_as_column,
+                        Trie& db_row, std::string& text, kdbx_stats& total) {
+    // the previous grid row's part (the first column part of this row) may still be on the device: keep it as the column
+    // database and stage this row's part next to it
+    if (row_is_staged_as_column) calc.swap_databases();
+    std::cerr << "Deserializing database " << i_row + 1 << " (" << g.files[i_row] << ")" << std::endl;
+    read_db(g.files[i_row], db_row, true);
+    calc.load_database(db_row);
+    const uint32_t rows = db_row.num_samples();
+    std::vector<std::unique_ptr<SparseMatrix<uint32_t>>> cells(i_row + 1);
+    std::vector<std::vector<uint32_t>> col_counts(i_row + 1);
+    auto add_stats = [&](const kdbx_stats& st) {
+        total.updates += st.updates; total.probes += st.probes; total.hits += st.hits; total.ms_probe += st.ms_probe;
+        total.ms_scatter += st.ms_scatter; total.ms_compact += st.ms_compact; total.ms_total += st.ms_total;
+        total.ms_prepare += st.ms_prepare; total.ms_download += st.ms_download; total.kernel_launches += st.kernel_launches;
+    };
+    auto cell = [&](uint32_t i_col, const Trie& db_col) {
+        std::cerr << "Processing cell (" << i_row + 1 << "," << i_col + 1 << ")" << std::endl;
+        cells[i_col] = std::make_unique<SparseMatrix<uint32_t>>();
+        calc.db2db_sp(db_row, db_col, *cells[i_col], p.filters);
+        col_counts[i_col].assign(db_col.sample_kmers.begin(), db_col.sample_kmers.end());
+        add_stats(calc.last_stats());
+    };
+    // order of the reference: (i, i-1) first — its column part is the one already in memory — then (i, 0 .. i-2)
+    for (uint32_t step = 0; step < i_row; ++step) {
+        const uint32_t i_col = step == 0 ? i_row - 1 : step - 1;
+        Trie db_col(true);
+        if (step == 0 && row_is_staged_as_column) {
+            read_db(g.files[i_col], db_col, false);   // (its k-mer counts; patterns and tables are on the device)
+        } else {
+            read_db(g.files[i_col], db_col, true);
+            calc.load_column_database(db_col);
+        }
+        cell(i_col, db_col);
+    }
+    std::cerr << "Processing cell (" << i_row + 1 << "," << i_row + 1 << ")" << std::endl;
+    cells[i_row] = std::make_unique<SparseMatrix<uint32_t>>();
+    calc.all2all_sp(db_row, *cells[i_row], p.filters, true);
+    col_counts[i_row].assign(db_row.sample_kmers.begin(), db_row.sample_kmers.end());
+    add_stats(calc.last_stats());
+
+    const OutputFilters* filters = p.filters.trivial() ? nullptr : &p.filters;   // (again: the bounds the device left to the host)
+    const int k = (int)db_row.hdr.kmer_length;
+    uint64_t saved = 0;
+    text.clear();
+    std::string line;
+    for (uint32_t r = 0; r < rows; ++r) {
+        const uint32_t s = g.first_sample[i_row] + r;
+        size_t pairs = 0;
+        for (uint32_t c = 0; c <= i_row; ++c) pairs += cells[c]->getNoInRow(r);
+        line.resize(g.all.sample_names[s].size() + 32 + pairs * 22);
+        char* q = line.data();
+        std::memcpy(q, g.all.sample_names[s].data(), g.all.sample_names[s].size()); q += g.all.sample_names[s].size();
+        *q++ = ',';
+        q = put_u64(q, g.all.sample_kmers[s]);
+        *q++ = ',';
+        for (uint32_t c = 0; c <= i_row; ++c) {
+            const SparseMatrix<uint32_t>& m = *cells[c];
+            const uint32_t* cols = m.cols(r);
+            const uint32_t* vals = m.vals(r);
+            const size_t cnt = m.getNoInRow(r);
+            for (size_t i = 0; i < cnt; ++i) {
+                if (filters && !filters->pass(vals[i], (uint32_t)db_row.sample_kmers[r], col_counts[c][cols[i]], k)) continue;
+                q = put_u64(q, (uint64_t)g.first_sample[c] + cols[i] + 1); *q++ = ':'; q = put_u64(q, vals[i]); *q++ = ',';
+                ++saved;
+            }
+        }
+        *q++ = '\n';
+        text.append(line.data(), (size_t)(q - line.data()));
+    }
+    return saved;
+}
+}  // namespace
+
+void run_all2all_parts(const Params& p) {
+    if (p.files.size() != 2) throw usage_error(p.mode);
+    std::cerr << "All versus all comparison (sparse computation)" << std::endl;
+    PartsGrid g;
+    {
+        std::ifstream ifs(p.files[0]);
+        if (!ifs) throw std::runtime_error("Cannot open: " + p.files[0]);
+        g.files.assign(std::istream_iterator<std::string>(ifs), std::istream_iterator<std::string>());
+    }
+    const uint32_t parts = (uint32_t)g.files.size();
+    std::cerr << "Processing database grid of size " << parts << " by " << parts << std::endl;
+    const double t0 = now();
+    for (uint32_t i = 0; i < parts; ++i) {   // names and k-mer counts of all samples (DeserializationMode::SamplesOnly)
+        Trie t;
+        try { read_db(g.files[i], t, false); }
+        catch (const std::runtime_error&) { throw std::runtime_error("Cannot open k-mer database: " + g.files[i]); }
+        if (i == 0) g.all.hdr = t.hdr;
+        else {
+            if (t.hdr.kmer_length != g.all.hdr.kmer_length) throw std::runtime_error("Different k - mer lengths");
+            if (t.hdr.fraction != g.all.hdr.fraction) throw std::runtime_error("Different fractions");
+        }
+        g.first_sample.push_back((uint32_t)g.all.sample_names.size());
+        g.part_samples.push_back(t.num_samples());
+        g.all.sample_names.insert(g.all.sample_names.end(), t.sample_names.begin(), t.sample_names.end());
+        g.all.sample_kmers.insert(g.all.sample_kmers.end(), t.sample_kmers.begin(), t.sample_kmers.end());
+    }
+    FILE* f = std::fopen(p.files[1].c_str(), "wb");
+    if (!f) throw std::runtime_error("Cannot open output file " + p.files[1]);
+    const std::string head = table_header(g.all);
+    std::fwrite(head.data(), 1, head.size(), f);
+
+    const int num_gpus = std::max(1, std::min<int>(p.num_gpus, (int)std::max<uint32_t>(1, parts)));
+    if (num_gpus > kdbx_device_count()) { std::fclose(f); throw std::runtime_error("-gpus " + std::to_string(num_gpus) + " requested but only " + std::to_string(kdbx_device_count()) + " B200 device(s) are visible"); }
+    uint64_t saved = 0;
+    kdbx_stats total{};
+    if (num_gpus == 1) {
+        SimilarityCalculator calc(p.num_threads, (size_t)p.cache_buffer_mb, p.gpu);
+        std::string text;
+        for (uint32_t i = 0; i < parts; ++i) {
+            Trie db_row(true);
+            saved += parts_grid_row(p, g, calc, i, i > 0, db_row, text, total);
+            std::cerr << "Saving output matrix..." << std::endl;
+            std::fwrite(text.data(), 1, text.size(), f);
+            std::cerr << " OK (no. currently saved pairs: " << saved << ")" << std::endl;
+        }
+    } else {
+        // grid rows dealt round-robin, heaviest (last) rows first on every device; the writer takes them in order
+        std::vector<std::string> texts(parts);
+        std::vector<int> ready(parts, 0);
+        std::vector<std::string> errors((size_t)num_gpus);
+        std::vector<uint64_t> saved_g((size_t)num_gpus, 0);
+        std::vector<kdbx_stats> stats_g((size_t)num_gpus, kdbx_stats{});
+        std::mutex mu;
+        std::condition_variable cv;
+        std::vector<std::thread> workers;
+        const int base = p.gpu < 0 ? 0 : p.gpu;
+        for (int d = 0; d < num_gpus; ++d)
+            workers.emplace_back([&, d] {
+                try {
+                    SimilarityCalculator calc(p.num_threads, (size_t)p.cache_buffer_mb, base + d);
+                    for (uint32_t i = (uint32_t)d; i < parts; i += (uint32_t)num_gpus) {
+                        Trie db_row(true);
+                        std::string text;
+                        saved_g[(size_t)d] += parts_grid_row(p, g, calc, i, false, db_row, text, stats_g[(size_t)d]);
+                        std::lock_guard<std::mutex> lk(mu);
+                        texts[i] = std::move(text); ready[i] = 1;
+                        cv.notify_all();
+                    }
+                } catch (const std::exception& e) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    errors[(size_t)d] = e.what();
+                    for (uint32_t i = (uint32_t)d; i < parts; i += (uint32_t)num_gpus) if (!ready[i]) ready[i] = -1;
+                    cv.notify_all();
+                }
+            });
+        bool failed = false;
+        for (uint32_t i = 0; i < parts && !failed; ++i) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return ready[i] != 0; });
+            if (ready[i] < 0) { failed = true; break; }
+            std::string text = std::move(texts[i]);
+            lk.unlock();
+            std::fwrite(text.data(), 1, text.size(), f);
+        }
+        for (auto& w : workers) w.join();
+        for (const std::string& e : errors) if (!e.empty()) { std::fclose(f); throw std::runtime_error(e); }
+        for (int d = 0; d < num_gpus; ++d) {
+            saved += saved_g[(size_t)d];
+            total.updates += stats_g[(size_t)d].updates; total.probes += stats_g[(size_t)d].probes; total.hits += stats_g[(size_t)d].hits;
+            total.kernel_launches += stats_g[(size_t)d].kernel_launches;
+            total.ms_total = std::max(total.ms_total, stats_g[(size_t)d].ms_total);
+        }
+    }
+    if (std::fclose(f) != 0) throw std::runtime_error("Cannot write output file " + p.files[1]);
+    const double dt = now() - t0;
+    std::cerr << "Database grid procesed successfully" << std::endl << "No. saved pairs: " << saved << std::endl;
+    print_stats_json(total, dt);
+}
+
 void run_new2all(const Params& p) {
     if (p.files.size() != 3) throw usage_error(p.mode);
     std::cerr << "Set of new samples  (from genomes) versus entire database comparison" << std::endl;
@@ -272,6 +469,7 @@ int main(int argc, char** argv) {
         if (p.mode == "build") run_build(p);
         else if (p.mode == "all2all") run_all2all(p);
         else if (p.mode == "all2all-sp") run_all2all_sparse(p);
+        else if (p.mode == "all2all-parts") run_all2all_parts(p);
         else if (p.mode == "new2all") run_new2all(p);
         else if (p.mode == "distance") run_distance(p);
     } catch (const usage_error& e) {

@@ -39,7 +39,7 @@ void parse_filters(std::vector<std::string>& a, OutputFilters& f, const std::str
     }
 }
 
-const char* kModes[] = {"build", "all2all", "all2all-sp", "new2all", "distance"};
+const char* kModes[] = {"build", "all2all", "all2all-sp", "all2all-parts", "new2all", "distance"};
 
 }  // namespace
 
@@ -51,13 +51,15 @@ void print_usage(const std::string& mode) {
         std::cerr << "  all2all [-sparse [-min [<crit>:]<v>]* [-max [<crit>:]<v>]*] [-gpus <n>] [-gpu <id>] [-t <n>] [-buffer <mb>] <database> <common_table>\n";
     else if (mode == "all2all-sp")
         std::cerr << "  all2all-sp [-min [<crit>:]<v>]* [-max [<crit>:]<v>]* [-gpu <id>] [-t <n>] [-buffer <mb>] [-bubble-size <n>] <database> <common_table>\n";
+    else if (mode == "all2all-parts")
+        std::cerr << "  all2all-parts [-min [<crit>:]<v>]* [-max [<crit>:]<v>]* [-gpus <n>] [-gpu <id>] [-t <n>] [-buffer <mb>] [-bubble-size <n>] <db_list> <common_table>\n";
     else if (mode == "new2all")
         std::cerr << "  new2all [-multisample-fasta] [-sparse [-min ...]* [-max ...]*] [-gpu <id>] [-t <n>] <database> <sample_list> <common_table>\n";
     else if (mode == "distance")
         std::cerr << "  distance <measure> [-sparse [-min [<crit>:]<v>]* [-max [<crit>:]<v>]*] [-phylip-out] <common_table> <output_table>\n"
                      "    measures: jaccard, min, max, cosine, mash, ani, ani-shorter, mash-query, num-kmers\n";
     else
-        std::cerr << "  modes: build, all2all, all2all-sp, new2all, distance   (kmer-db-b200 <mode> -help)\n"
+        std::cerr << "  modes: build, all2all, all2all-sp, all2all-parts, new2all, distance   (kmer-db-b200 <mode> -help)\n"
                      "  extras: synth (generate a synthetic database), info <database>\n";
 }
 
@@ -100,14 +102,14 @@ bool parse_params(int argc, char** argv, Params& p) {
             throw std::runtime_error("K-mer length for the given alphabet cannot exceed " + std::to_string(p.alphabet.max_kmer_len));
         p.extend_db = find_switch(a, "-extend");
         p.host_build = find_switch(a, "-host-build");
-    } else if (p.mode == "all2all" || p.mode == "all2all-sp") {
+    } else if (p.mode == "all2all" || p.mode == "all2all-sp" || p.mode == "all2all-parts") {
         find_option(a, "-buffer", p.cache_buffer_mb);
         if (p.cache_buffer_mb <= 0) p.cache_buffer_mb = 8;
         find_option(a, "-bubble-size", p.bubble_size);
         p.sparse_out = find_switch(a, "-sparse");
-        if (p.sparse_out || p.mode == "all2all-sp") parse_filters(a, p.filters, "num-kmers");
+        if (p.sparse_out || p.mode != "all2all") parse_filters(a, p.filters, "num-kmers");
         std::string rows;
-        if (p.mode == "all2all-sp" && find_option(a, "-sample-rows", rows))
+        if (p.mode != "all2all" && find_option(a, "-sample-rows", rows))
             throw std::runtime_error("-sample-rows is not supported by kmer-db-b200");
     } else if (p.mode == "new2all") {
         if (find_switch(a, "-from-kmers") || find_switch(a, "-from-minhash"))

@@ -2,6 +2,7 @@
 //     class SimilarityCalculator { SimilarityCalculator(int num_threads, size_t cacheBufferMb);
 //         void all2all(PrefixKmerDb& db, LowerTriangularMatrix<uint32_t>& matrix) const;
 //         void all2all_sp(PrefixKmerDb& db, SparseMatrix<uint32_t>& matrix, CBubbleHelper& bubbles) const;
+//         void db2db_sp(PrefixKmerDb& db1, PrefixKmerDb& db2, SparseMatrix<uint32_t>& matrix, CBubbleHelper& bubbles) const;
 //         template <bool parallel> void one2all(const PrefixKmerDb& db, const kmer_t* kmers, size_t kmersCount,
 //                                               std::vector<uint32_t>& similarities) const; ... }
 // (src/similarity_calculator.h:4-16).  Same names and argument meaning; the work happens in
@@ -73,7 +74,7 @@ public:
         cfg.device = device;
         if (kdbx_open(&cfg, &ctx_) != KDBX_OK) throw std::runtime_error(kdbx_last_error(nullptr));
     }
-    ~SimilarityCalculator() { kdbx_close(ctx_); }
+    ~SimilarityCalculator() { kdbx_close(ctx_); if (ctx_cols_) kdbx_close(ctx_cols_); }
     SimilarityCalculator(const SimilarityCalculator&) = delete;
     SimilarityCalculator& operator=(const SimilarityCalculator&) = delete;
 
@@ -166,9 +167,12 @@ public:
     // matrix as sparse rows.  `filters` are the -min/-max bounds; the ones whose arithmetic is
     // exactly reproducible on the device run there (include/kdbx.h), the log-based ones are left
     // to the CSV emitter, which applies `filters` again on the host.
-    void all2all_sp(const Trie& db, SparseMatrix<uint32_t>& matrix, const OutputFilters& filters) const {
-        const kdbx_trie_view v = db.view();
-        check(kdbx_load_patterns(ctx_, &v));
+    // staged = true: the database is already on the device (load_database), as for the diagonal cells of all2all-parts.
+    void all2all_sp(const Trie& db, SparseMatrix<uint32_t>& matrix, const OutputFilters& filters, bool staged = false) const {
+        if (!staged) {
+            const kdbx_trie_view v = db.view();
+            check(kdbx_load_patterns(ctx_, &v));
+        }
         kdbx_filter f{};
         std::vector<uint32_t> counts(db.sample_kmers.begin(), db.sample_kmers.end());
         make_filter(filters, counts, f);
@@ -246,20 +250,42 @@ public:
     // Stage the database for queries: patterns + k-mer tables (PrefixKmerDb::deserialize with
     // DeserializationMode::Everything, src/console_new2all.cpp:32).
     void load_database(const Trie& db) const {
-        if (db.tables.empty()) throw std::runtime_error("database was loaded without its k-mer tables");
-        const kdbx_trie_view v = db.view();
-        check(kdbx_load_patterns(ctx_, &v));
-        std::vector<uint64_t> off(db.tables.size() + 1, 0);
-        for (size_t t = 0; t < db.tables.size(); ++t) off[t + 1] = off[t] + db.tables[t].slots.size();
-        Buf<uint64_t> slots;
-        slots.set_pinned(true);
-        slots.resize(off.back());
-        for (size_t t = 0; t < db.tables.size(); ++t)
-            std::copy(db.tables[t].slots.begin(), db.tables[t].slots.end(), slots.data() + off[t]);
-        kdbx_tables_view tv{};
-        tv.num_tables = db.tables.size(); tv.slot_off = off.data(); tv.slots = slots.data();
-        check(kdbx_load_hashtables(ctx_, &tv));
+        stage(ctx_, db);
         num_samples_ = db.num_samples();
+    }
+
+    // ---- database against database: the cells below the diagonal of all2all-parts -----------------------------------
+    // The COLUMN database of db2db_sp lives on a second context of the same device (opened on first use).
+    void load_column_database(const Trie& db) const {
+        if (!ctx_cols_) {
+            kdbx_config cfg{};
+            cfg.device = device_;
+            if (kdbx_open(&cfg, &ctx_cols_) != KDBX_OK) throw std::runtime_error(kdbx_last_error(nullptr));
+        }
+        stage(ctx_cols_, db);
+    }
+    // The staged row database becomes the staged column database and vice versa: the row part of one grid row is the
+    // first column part of the next (the reference keeps it in memory for the same reason, `db_tmp`,
+    // src/console_all2all_parts.cpp:168-175,277-278).  load_database must follow before the next row call.
+    void swap_databases() const {
+        if (!ctx_cols_) {
+            kdbx_config cfg{};
+            cfg.device = device_;
+            if (kdbx_open(&cfg, &ctx_cols_) != KDBX_OK) throw std::runtime_error(kdbx_last_error(nullptr));
+        }
+        std::swap(ctx_, ctx_cols_);
+    }
+    // src/similarity_calculator.cpp:1225 + SparseMatrix::compact2: matrix row s1 (a sample of db_row) = ascending
+    // (s2, common k-mers) pairs over the samples s2 of db_col.  Both databases must be staged (load_database for the rows,
+    // load_column_database for the columns); db_row / db_col supply the k-mer counts of the output filters.
+    void db2db_sp(const Trie& db_row, const Trie& db_col, SparseMatrix<uint32_t>& matrix, const OutputFilters& filters) const {
+        if (!ctx_cols_) throw std::runtime_error("db2db_sp: no column database staged");
+        kdbx_filter f{};
+        std::vector<uint32_t> rows(db_row.sample_kmers.begin(), db_row.sample_kmers.end());
+        std::vector<uint32_t> cols(db_col.sample_kmers.begin(), db_col.sample_kmers.end());
+        make_filter(filters, rows, f);
+        kdbx_free_csr(matrix.raw());
+        check(kdbx_db2db_sparse(ctx_, ctx_cols_, &f, cols.data(), matrix.raw(), &stats_));
     }
 
     // A batch of one2all<false> calls (src/similarity_calculator.cpp:810-925): query q owns
@@ -306,10 +332,27 @@ private:
         f.sample_kmers = counts.data();
     }
     void check(int rc) const { if (rc != KDBX_OK) throw std::runtime_error(kdbx_last_error(ctx_)); }
+    // patterns + k-mer tables of `db` to the device of context c
+    static void stage(kdbx_ctx* c, const Trie& db) {
+        if (db.tables.empty()) throw std::runtime_error("database was loaded without its k-mer tables");
+        const kdbx_trie_view v = db.view();
+        if (kdbx_load_patterns(c, &v) != KDBX_OK) throw std::runtime_error(kdbx_last_error(c));
+        std::vector<uint64_t> off(db.tables.size() + 1, 0);
+        for (size_t t = 0; t < db.tables.size(); ++t) off[t + 1] = off[t] + db.tables[t].slots.size();
+        Buf<uint64_t> slots;
+        slots.set_pinned(true);
+        slots.resize(off.back());
+        for (size_t t = 0; t < db.tables.size(); ++t)
+            std::copy(db.tables[t].slots.begin(), db.tables[t].slots.end(), slots.data() + off[t]);
+        kdbx_tables_view tv{};
+        tv.num_tables = db.tables.size(); tv.slot_off = off.data(); tv.slots = slots.data();
+        if (kdbx_load_hashtables(c, &tv) != KDBX_OK) throw std::runtime_error(kdbx_last_error(c));
+    }
     int num_threads_;
     size_t cache_buffer_mb_;
     int device_ = -1;
-    kdbx_ctx* ctx_ = nullptr;
+    mutable kdbx_ctx* ctx_ = nullptr;
+    mutable kdbx_ctx* ctx_cols_ = nullptr;   // column database of db2db_sp
     mutable kdbx_stats stats_{};
     mutable uint32_t num_samples_ = 0;
 };

@@ -110,7 +110,7 @@ class Totals(C.Structure):
 # every symbol include/kdbx.h declares (tests check that the library exports all of them)
 KDBX_SYMBOLS = ["kdbx_abi_version", "kdbx_device_count", "kdbx_open", "kdbx_close", "kdbx_last_error",
                 "kdbx_host_alloc", "kdbx_host_free", "kdbx_load_patterns", "kdbx_set_sample_window", "kdbx_row_updates", "kdbx_all2all_dense",
-                "kdbx_all2all_dense_rows", "kdbx_all2all_dense_rows_device", "kdbx_all2all_dense_part_device", "kdbx_all2all_sparse", "kdbx_all2all_sparse_rows", "kdbx_csv_dense_rows", "kdbx_stage_matrix", "kdbx_distance_dense_rows", "kdbx_free_csr",
+                "kdbx_all2all_dense_rows", "kdbx_all2all_dense_rows_device", "kdbx_all2all_dense_part_device", "kdbx_all2all_sparse", "kdbx_all2all_sparse_rows", "kdbx_db2db_sparse", "kdbx_csv_dense_rows", "kdbx_stage_matrix", "kdbx_distance_dense_rows", "kdbx_free_csr",
                 "kdbx_load_hashtables", "kdbx_new2all_batch", "kdbx_debug_fetch", "kdbx_comm_unique_id", "kdbx_comm_init_rank",
                 "kdbx_comm_init_all", "kdbx_comm_destroy", "kdbx_all2all_dense_reduce_scatter_device", "kdbx_all2all_dense_reduce_scatter",
                 "kdbx_builder_open", "kdbx_builder_close", "kdbx_builder_adopt", "kdbx_builder_add_sequence", "kdbx_builder_add_kmers",
@@ -166,6 +166,7 @@ def load():
     k.kdbx_all2all_dense_reduce_scatter.argtypes = [C.c_void_p, C.c_void_p, P(C.c_uint64), P(C.c_uint64), P(Stats)]
     k.kdbx_all2all_sparse.argtypes = [C.c_void_p, P(Filter), P(Csr), P(Stats)]
     k.kdbx_all2all_sparse_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, P(Filter), P(Csr), P(Stats)]
+    k.kdbx_db2db_sparse.argtypes = [C.c_void_p, C.c_void_p, P(Filter), C.c_void_p, P(Csr), P(Stats)]
     k.kdbx_free_csr.argtypes = [P(Csr)]
     k.kdbx_free_csr.restype = None
     k.kdbx_load_hashtables.argtypes = [C.c_void_p, P(TablesView)]
@@ -580,6 +581,32 @@ class Context:
             self._check(self._k.kdbx_all2all_sparse(self._p, C.byref(f), C.byref(csr), C.byref(st)))
         else:
             self._check(self._k.kdbx_all2all_sparse_rows(self._p, rows[0], rows[1], C.byref(f), C.byref(csr), C.byref(st)))
+        try:
+            row_ptr = _np_from(csr.row_ptr, csr.num_rows + 1, np.uint64).copy()
+            col = _np_from(csr.col, csr.nnz, np.uint32).copy()
+            val = _np_from(csr.val, csr.nnz, np.uint32).copy()
+        finally:
+            self._k.kdbx_free_csr(C.byref(csr))
+        return row_ptr, col, val, st
+
+    def db2db_sparse(self, cols_db: "Context", min_common=0, max_common=0xFFFFFFFF, metric_bounds=(), row_kmers=None, col_kmers=None):
+        """One cell of the all2all-parts grid (kdbx_db2db_sparse): this context holds the ROW database, cols_db the COLUMN
+        database (patterns and k-mer tables staged on both).  Returns (row_ptr, col, val, stats); column ids are local to
+        the column database."""
+        f = Filter()
+        f.min_common, f.max_common = min_common, max_common
+        f.num_metric_bounds = len(metric_bounds)
+        for i, (name, lo, hi) in enumerate(metric_bounds):
+            f.metric_bounds[i].metric, f.metric_bounds[i].lo, f.metric_bounds[i].hi = METRICS[name], lo, hi
+        keep_r = keep_c = None
+        if row_kmers is not None:
+            keep_r = np.ascontiguousarray(row_kmers, np.uint32)
+            f.sample_kmers = keep_r.ctypes.data
+        if col_kmers is not None:
+            keep_c = np.ascontiguousarray(col_kmers, np.uint32)
+        csr, st = Csr(), Stats()
+        self._check(self._k.kdbx_db2db_sparse(self._p, cols_db._p, C.byref(f), keep_c.ctypes.data if keep_c is not None else None,
+                                              C.byref(csr), C.byref(st)))
         try:
             row_ptr = _np_from(csr.row_ptr, csr.num_rows + 1, np.uint64).copy()
             col = _np_from(csr.col, csr.nnz, np.uint32).copy()

@@ -24,10 +24,13 @@
  *   k-mer extraction       KmerHelper::extract, MinHashFilter         src/kmer_extract.h:13-97, src/filter.h:40-115
  *   FASTA records          GenomeInputFile::extractSubsequences       src/genome_input_file.h:287-337
  *   new2all CSV            New2AllConsole::run                        src/console_new2all.cpp:98-161
+ *   database vs database   db2db_sp (k-mer matching, pair counts, list x list adds)  src/similarity_calculator.cpp:1225-1540
+ *   all2all-parts          All2AllPartsConsole::run (grid of cells, shifted columns) src/console_all2all_parts.cpp:11-371
  *
  * Parity is PINNED: tests/test_oracle.py checks this file against the reference's own golden
  * CSVs (test/virus/k18.csv, k18.sparse.csv, k24.csv, k18.frac.csv, k18.n2a.csv, k18.n2a.sparse.csv,
- * test/synth/a2a, a2a-sparse, n2a, n2a-sparse; committed under tests/golden/) and against the unmodified reference binary built by
+ * test/synth/a2a, a2a-sparse, n2a, n2a-sparse; committed under tests/golden/; all2all-parts: the reference's CI check
+ * `all2all-parts(part1, part2) == k18.sparse.csv`, .github/workflows/self-hosted.yml:357-363) and against the unmodified reference binary built by
  * oracle/build_ref.sh (oracle/_ref/kmer-db) on generated databases.
  */
 #include <stdint.h>
@@ -488,6 +491,127 @@ uint64_t oracle_one2all(const oracle_db* db, const uint64_t* kmers, uint64_t cou
     }
     free(hit); free(full);
     return hits;
+}
+
+/* ---- database against database: db2db_sp (src/similarity_calculator.cpp:1225-1540) --------------------------
+ * out (N1 x N2 cells, zeroed here): out[s1 * N2 + s2] = number of k-mers present in sample s1 of db1 and in sample
+ * s2 of db2.  The reference merges the sorted (suffix, pattern) pairs of each prefix bucket of the two databases
+ * (:1262-1287; keys are unique inside a bucket, so the merge finds exactly the suffixes both buckets hold — restated
+ * here as a lookup of every used slot of db1 in db2's bucket), sorts and counts the (pattern1, pattern2) pairs
+ * (:1310-1321), and adds every distinct pair's count to the cells of list(pattern1) x list(pattern2) (:1434-1517;
+ * bubbles only defer the same additions to compact2, src/array.h:409-415).  Returns the number of cell updates, or
+ * UINT64_MAX when the databases do not fit together. */
+static int cmp_pair(const void* a, const void* b) { const uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b; return x < y ? -1 : x > y; }
+
+static void full_list(const oracle_db* db, uint64_t p, uint32_t* buf /* n[p] ids */) {
+    uint32_t* o = buf + db->n[p];
+    for (int64_t q = (int64_t)p; q >= 0; q = db->parent_id[q]) {
+        o -= db->l[q];
+        oracle_decode_local(db->payload + db->payload_off[q], db->l[q], db->last[q], o);
+    }
+}
+
+uint64_t oracle_db2db(const oracle_db* db1, const oracle_db* db2, uint32_t* out) {
+    const uint32_t N1 = db1->num_samples, N2 = db2->num_samples;
+    if (db1->num_tables != db2->num_tables || db1->kmer_length != db2->kmer_length) return UINT64_MAX;
+    memset(out, 0, (size_t)N1 * N2 * 4);
+    uint64_t cap = 1024, np = 0;
+    uint64_t* pairs = (uint64_t*)malloc(cap * 8);
+    for (uint64_t t = 0; t < db1->num_tables; ++t) {
+        for (uint64_t i = db1->table_off[t]; i < db1->table_off[t + 1]; ++i) {
+            const uint32_t pid1 = (uint32_t)(db1->slots[i] >> 32);
+            if (pid1 == 0x7FFFFFFFu) continue;
+            const int64_t pid2 = oracle_lookup(db2, (t << 32) | (uint32_t)db1->slots[i]);
+            if (pid2 < 0) continue;
+            if (np == cap) { cap *= 2; pairs = (uint64_t*)realloc(pairs, cap * 8); }
+            pairs[np++] = ((uint64_t)pid1 << 32) | (uint32_t)pid2;
+        }
+    }
+    qsort(pairs, np, 8, cmp_pair);
+    uint32_t* l1 = (uint32_t*)malloc(((size_t)N1 + 1) * 4);
+    uint32_t* l2 = (uint32_t*)malloc(((size_t)N2 + 1) * 4);
+    uint64_t updates = 0;
+    for (uint64_t i = 0; i < np;) {
+        uint64_t j = i;
+        while (j < np && pairs[j] == pairs[i]) ++j;
+        const uint64_t p1 = pairs[i] >> 32, p2 = (uint32_t)pairs[i];
+        const uint32_t cnt = (uint32_t)(j - i);
+        full_list(db1, p1, l1);
+        full_list(db2, p2, l2);
+        for (uint32_t a = 0; a < db1->n[p1]; ++a)
+            for (uint32_t b = 0; b < db2->n[p2]; ++b) out[(size_t)l1[a] * N2 + l2[b]] += cnt;
+        updates += (uint64_t)db1->n[p1] * db2->n[p2];
+        i = j;
+    }
+    free(pairs); free(l1); free(l2);
+    return updates;
+}
+
+/* all2all-parts on a list of database files (src/console_all2all_parts.cpp:11-371), no filters: header lines over the
+ * samples of all parts, then for grid row i the lines of part i's samples — the cells (i, 0..i-1) by oracle_db2db and the
+ * diagonal cell by the all2all restatement (all2all_sp yields the same matrix), non-zero cells as <global col + 1>:<val>,
+ * (SparseMatrix::saveRowSparse(row, out, idx_shift), src/array.h:625-637).  Returns the number of pairs, or -1. */
+int64_t oracle_all2all_parts_file(const char* list_path, const char* csv_path) {
+    FILE* lf = fopen(list_path, "r");
+    if (!lf) return -1;
+    char name[4096];
+    char** files = NULL;
+    uint32_t parts = 0;
+    while (fscanf(lf, "%4095s", name) == 1) {
+        files = (char**)realloc(files, (parts + 1) * sizeof(char*));
+        files[parts++] = strdup(name);
+    }
+    fclose(lf);
+    oracle_db** dbs = (oracle_db**)calloc(parts + 1, sizeof(oracle_db*));
+    int64_t saved = 0;
+    FILE* out = NULL;
+    for (uint32_t i = 0; i < parts; ++i) {
+        dbs[i] = oracle_db_read_full(files[i]);
+        if (!dbs[i] || dbs[i]->kmer_length != dbs[0]->kmer_length || dbs[i]->fraction != dbs[0]->fraction) { saved = -1; goto done; }
+    }
+    out = fopen(csv_path, "wb");
+    if (!out) { saved = -1; goto done; }
+    if (parts) {
+        fprintf(out, "kmer-length: %u fraction: %g ,db-samples ,", dbs[0]->kmer_length, dbs[0]->fraction);
+        for (uint32_t i = 0; i < parts; ++i) for (uint32_t s = 0; s < dbs[i]->num_samples; ++s) fprintf(out, "%s,", dbs[i]->names[s]);
+        fprintf(out, "\nquery-samples,total-kmers,");
+        for (uint32_t i = 0; i < parts; ++i) for (uint32_t s = 0; s < dbs[i]->num_samples; ++s) fprintf(out, "%llu,", (unsigned long long)dbs[i]->sample_kmers[s]);
+        fprintf(out, "\n");
+    }
+    for (uint32_t i = 0; i < parts; ++i) {
+        const oracle_db* r = dbs[i];
+        const uint64_t N = r->num_samples;
+        uint32_t** rect = (uint32_t**)calloc(i + 1, sizeof(uint32_t*));
+        for (uint32_t j = 0; j < i; ++j) {
+            rect[j] = (uint32_t*)malloc((size_t)N * dbs[j]->num_samples * 4 + 4);
+            if (oracle_db2db(r, dbs[j], rect[j]) == UINT64_MAX) saved = -1;
+        }
+        uint32_t* tri = (uint32_t*)calloc(N * (N ? N - 1 : 0) / 2 + 1, 4);
+        if (oracle_all2all(r->num_patterns, r->num_samples, r->num_kmers, r->parent_id, r->n, r->l, r->last, r->bits, r->payload_off, r->payload,
+                           tri) == UINT64_MAX) saved = -1;
+        for (uint64_t s = 0; s < N && saved >= 0; ++s) {
+            fprintf(out, "%s,%llu,", r->names[s], (unsigned long long)r->sample_kmers[s]);
+            uint64_t shift = 0;
+            for (uint32_t j = 0; j < i; ++j) {
+                const uint32_t N2 = dbs[j]->num_samples;
+                for (uint32_t c = 0; c < N2; ++c)
+                    if (rect[j][s * N2 + c]) { fprintf(out, "%llu:%u,", (unsigned long long)(shift + c + 1), rect[j][s * N2 + c]); ++saved; }
+                shift += N2;
+            }
+            const uint32_t* row = tri + s * (s - 1) / 2;
+            for (uint64_t c = 0; c < s; ++c)
+                if (row[c]) { fprintf(out, "%llu:%u,", (unsigned long long)(shift + c + 1), row[c]); ++saved; }
+            fprintf(out, "\n");
+        }
+        for (uint32_t j = 0; j < i; ++j) free(rect[j]);
+        free(rect); free(tri);
+        if (saved < 0) break;
+    }
+done:
+    if (out) fclose(out);
+    for (uint32_t i = 0; i < parts; ++i) { oracle_db_free(dbs[i]); free(files[i]); }
+    free(dbs); free(files);
+    return saved;
 }
 
 /* ---- k-mer extraction, written window by window (no rolling state) so that it is independent of

@@ -22,6 +22,15 @@ cp test/synth/a2a "$HERE/synth.k21.csv"
 cp test/synth/a2a-sparse "$HERE/synth.k21.sparse.csv"
 # database of the first 100 virus genomes (the CI's k18.parts.db, .github/workflows/main.yml:73) for new2all
 "$BIN" build test/virus/seqs.part1.list "$HERE/virus.k18.part1.db"
+# all2all-parts with output filters on the virus genomes split into three parts (60 / 60 / 45 samples, in list order); without
+# filters the mode reproduces test/virus/k18.sparse.csv (the reference's own CI check, .github/workflows/self-hosted.yml:357-363)
+P3="$(mktemp -d)"
+sed -n 1,60p test/virus/seqs.list > "$P3/a.list"; sed -n 61,120p test/virus/seqs.list > "$P3/b.list"; sed -n '121,$p' test/virus/seqs.list > "$P3/c.list"
+for x in a b c; do "$BIN" build "$P3/$x.list" "$P3/$x.db"; done
+printf '%s\n' "$P3/a.db" "$P3/b.db" "$P3/c.db" > "$P3/db.list"
+"$BIN" all2all-parts "$P3/db.list" "$P3/plain.csv" && cmp "$P3/plain.csv" test/virus/k18.sparse.csv
+"$BIN" all2all-parts -min jaccard:0.985 -max num-kmers:29700 -min ani:0.9995 "$P3/db.list" "$HERE/virus.k18.parts.filtered.csv"
+rm -rf "$P3"
 # the reference's test INPUTS (FASTA, lists) and every golden OUTPUT of test/virus, test/synth and the
 # amino-acid part of test/protein, verbatim, for the CLI tests (build / new2all / distance / all2all-sp)
 tar cJf "$HERE/reference_fixtures.tar.xz" test/virus test/synth test/protein/aa_100x1000.fasta test/protein/*.a2a

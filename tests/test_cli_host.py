@@ -204,3 +204,36 @@ int main(int argc, char** argv) {
         r = subprocess.run([str(exe), lst, multi, str(k)], cwd=str(ref_fixtures), capture_output=True, text=True)
         assert r.returncode == 0, r.stdout + r.stderr
         assert int(r.stdout.strip()) > 0
+
+
+def _split_virus_lists(ref_fixtures, tmp_path, cuts):
+    """List files holding consecutive slices of test/virus/seqs.list (cuts = slice boundaries)."""
+    lines = (ref_fixtures / "test/virus/seqs.list").read_text().split()
+    out = []
+    for i, (b, e) in enumerate(zip([0] + cuts, cuts + [len(lines)])):
+        f = tmp_path / f"slice{i}.list"
+        f.write_text("\n".join(lines[b:e]) + "\n")
+        out.append(f)
+    return out
+
+
+@pytest.mark.parametrize("cuts", [[100], [60, 120], [1, 164]])
+def test_oracle_all2all_parts_reproduces_reference_csv(cli, oracle, ref_fixtures, tmp_path, cuts):
+    """all2all-parts over the virus genomes split into partial databases gives the all2all-sp table of the whole
+    collection — the reference's own CI check (.github/workflows/self-hosted.yml:357-363: parts1 + parts2 -> k18.sparse.csv).
+    Pins the oracle's restatement of db2db_sp and of the grid driver; the parts are built by our host builder, and in
+    the CI's own split part 1 is also taken as the REFERENCE built it (tests/golden/virus.k18.part1.db)."""
+    oracle.oracle_all2all_parts_file.argtypes = [C.c_char_p, C.c_char_p]
+    oracle.oracle_all2all_parts_file.restype = C.c_int64
+    dbs = []
+    for i, lst in enumerate(_split_virus_lists(ref_fixtures, tmp_path, cuts)):
+        dbs.append(tmp_path / f"part{i}.db")
+        cli(ref_fixtures, "build", "-host-build", lst, dbs[-1])
+    variants = [dbs]
+    if cuts == [100]:
+        variants.append([ou.ROOT / "tests" / "golden" / "virus.k18.part1.db", dbs[1]])
+    for v in variants:
+        (tmp_path / "db.list").write_text("\n".join(map(str, v)) + "\n")
+        pairs = oracle.oracle_all2all_parts_file(str(tmp_path / "db.list").encode(), str(tmp_path / "parts.csv").encode())
+        assert pairs == 13530   # "No. saved pairs" of the reference run
+        assert ou.read_bytes(tmp_path / "parts.csv") == ou.read_bytes(ref_fixtures / "test/virus/k18.sparse.csv")

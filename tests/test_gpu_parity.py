@@ -504,14 +504,18 @@ def test_unaligned_device_output_takes_the_id_form(libs, oracle):
             assert np.array_equal(buf[shift:shift + cells].cpu().numpy().view(np.uint32), want)
 
 
-@pytest.mark.parametrize("N,clusters,form", [(4000, 16, 1), (6000, 5, 1), (4000, 2, 0), (9000, 30, 1)])
-def test_sliding_column_window(libs, oracle, N, clusters, form):
+@pytest.mark.parametrize("N,clusters,mu,flags,form", [(4000, 16, 0.002, 0, 1), (6000, 5, 0.002, 0, 1), (4000, 2, 0.002, 0, 0),
+                                                   (9000, 30, 0.002, 0, 1), (4000, 16, 0.01, 0, 0), (4000, 16, 0.01, "boundary", 1)])
+def test_sliding_column_window(libs, oracle, N, clusters, mu, flags, form):
     """Beyond 1728 samples: one column window per row block that slides with the diagonal (make_plan).  Databases whose
     lists stay within 1728 ids below their rows (clusters up to that size) keep the headline path — boundary lists, decoder
-    job counts — at any N up to 16384; a database with wider lists (two clusters of 2000) is re-planned with the id form."""
-    t = libs.Trie.synth(num_samples=N, num_clusters=clusters, genome_kmers=2500, seed=N + clusters, mutation_rate=0.01)
+    job counts — at any N up to 16384; a database with wider lists (two clusters of 2000) is re-planned with the id form,
+    and so is one whose lists are too gappy for the boundary form to pay (mu = 0.01: 1.15 boundary entries per id,
+    computed on the host from the decoded lists) unless the caller insists on it."""
+    t = libs.Trie.synth(num_samples=N, num_clusters=clusters, genome_kmers=2500, seed=N + clusters, mutation_rate=mu)
     want, U = ou.oracle_all2all(oracle, N, t.arrays())
-    with libs.Context(device=0) as c:
+    cfg = {"flags": libs.FLAG_BOUNDARY_LISTS} if flags == "boundary" else {}
+    with libs.Context(device=0, **cfg) as c:
         c.load_patterns(t)
         for _ in range(2):   # second call: cached sizes, no host round trips
             got, st = c.all2all_dense()

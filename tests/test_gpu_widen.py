@@ -299,3 +299,103 @@ def test_distance_on_the_device(libs, oracle, cli, ref_fixtures, tmp_path):
         bad = cnt.copy(); bad[5] = 0
         with pytest.raises(libs.KdbxError, match="has no k-mers"):
             c.distance_dense_rows("jaccard", bad, 0, N)
+
+
+# ---- all2all-parts / db2db_sp (src/console_all2all_parts.cpp, src/similarity_calculator.cpp:1225-1540) ----
+def _split_virus_lists(ref_fixtures, tmp_path, cuts):
+    lines = (ref_fixtures / "test/virus/seqs.list").read_text().split()
+    out = []
+    for i, (b, e) in enumerate(zip([0] + cuts, cuts + [len(lines)])):
+        f = tmp_path / f"slice{i}.list"
+        f.write_text("\n".join(lines[b:e]) + "\n")
+        out.append(f)
+    return out
+
+
+@pytest.mark.parametrize("cuts", [[100], [60, 120], [1, 164]])
+def test_cli_all2all_parts(cli, ref_fixtures, tmp_path, cuts):
+    """The reference's CI check for the mode (self-hosted.yml:357-363): parts built separately, all2all-parts over the list
+    == k18.sparse.csv; with output filters == what the reference binary wrote for the same three parts (tests/golden)."""
+    dbs = []
+    for i, lst in enumerate(_split_virus_lists(ref_fixtures, tmp_path, cuts)):
+        dbs.append(tmp_path / f"part{i}.db")
+        cli(ref_fixtures, "build", lst, dbs[-1])
+    if cuts == [100]:
+        dbs[0] = ou.ROOT / "tests" / "golden" / "virus.k18.part1.db"   # as the reference built it
+    (tmp_path / "db.list").write_text("\n".join(map(str, dbs)) + "\n")
+    r = cli(ref_fixtures, "all2all-parts", tmp_path / "db.list", tmp_path / "parts.csv")
+    assert ou.read_bytes(tmp_path / "parts.csv") == ou.read_bytes(ref_fixtures / "test/virus/k18.sparse.csv")
+    assert "No. saved pairs: 13530" in r.stderr
+    cli(ref_fixtures, "all2all-parts", "-min", "jaccard:0.985", "-max", "num-kmers:29700", "-min", "ani:0.9995", tmp_path / "db.list", tmp_path / "f.csv")
+    assert ou.read_bytes(tmp_path / "f.csv") == ou.read_bytes(ou.ROOT / "tests" / "golden" / "virus.k18.parts.filtered.csv")
+
+
+def test_cli_all2all_parts_on_two_gpus(libs, cli, ref_fixtures, tmp_path):
+    """-gpus 2: the grid rows are dealt to two devices and written in order."""
+    k, _ = libs.load()
+    if k.kdbx_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    dbs = []
+    for i, lst in enumerate(_split_virus_lists(ref_fixtures, tmp_path, [40, 80, 120])):
+        dbs.append(tmp_path / f"part{i}.db")
+        cli(ref_fixtures, "build", lst, dbs[-1])
+    (tmp_path / "db.list").write_text("\n".join(map(str, dbs)) + "\n")
+    cli(ref_fixtures, "all2all-parts", "-gpus", "2", tmp_path / "db.list", tmp_path / "parts.csv")
+    assert ou.read_bytes(tmp_path / "parts.csv") == ou.read_bytes(ref_fixtures / "test/virus/k18.sparse.csv")
+
+
+def test_db2db_cells_against_oracle(libs, oracle, cli, ref_fixtures, tmp_path):
+    """kdbx_db2db_sparse through the C ABI against the oracle's db2db restatement, cell for cell: both orientations of
+    two databases of different sizes, one row block and many, with device-side filters."""
+    oracle.oracle_db2db.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    oracle.oracle_db2db.restype = C.c_uint64
+    oracle.oracle_db_read_full.restype = C.c_void_p
+    oracle.oracle_db_read_full.argtypes = [C.c_char_p]
+    oracle.oracle_db_free.argtypes = [C.c_void_p]
+    p1 = ou.ROOT / "tests" / "golden" / "virus.k18.part1.db"
+    p2 = tmp_path / "part2.db"
+    cli(ref_fixtures, "build", "test/virus/seqs.part2.list", p2)
+    t = {1: libs.Trie.read_db_full(p1), 2: libs.Trie.read_db_full(p2)}
+    o = {1: oracle.oracle_db_read_full(str(p1).encode()), 2: oracle.oracle_db_read_full(str(p2).encode())}
+    assert o[1] and o[2]
+    for r, c in ((2, 1), (1, 2)):
+        N1, N2 = t[r].num_samples, t[c].num_samples
+        want = np.zeros(N1 * N2, np.uint32)
+        upd = oracle.oracle_db2db(o[r], o[c], want.ctypes.data)
+        assert upd != 2**64 - 1
+        want = want.reshape(N1, N2)
+        for cfg in (dict(), dict(sparse_block_cells=7 * N2)):
+            with libs.Context(device=0, **cfg) as rows, libs.Context(device=0) as cols:
+                rows.load_patterns(t[r]); rows.load_hashtables(t[r])
+                cols.load_patterns(t[c]); cols.load_hashtables(t[c])
+                for _ in range(2):   # (the second call finds both databases prepared)
+                    rp, col, val, st = rows.db2db_sparse(cols)
+                    got = np.zeros((N1, N2), np.uint32)
+                    for s in range(N1):
+                        b, e = int(rp[s]), int(rp[s + 1])
+                        assert np.all(np.diff(col[b:e].astype(np.int64)) > 0)
+                        got[s, col[b:e]] = val[b:e]
+                    assert np.array_equal(got, want)
+                    assert int(rp[-1]) == int(np.count_nonzero(want)) and st.updates == upd and st.hits > 0 and st.probes >= st.hits
+                # filters evaluated on the device: k-mer count bounds and a jaccard bound with both databases' counts
+                ca, cb = t[r].sample_kmer_counts().astype(np.uint32), t[c].sample_kmer_counts().astype(np.uint32)
+                rp, col, val, st = rows.db2db_sparse(cols, min_common=20000, max_common=29700, metric_bounds=[("jaccard", 0.9, 0.99)],
+                                                     row_kmers=ca, col_kmers=cb)
+                keep = (want >= 20000) & (want <= 29700)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    jac = want.astype(np.float64) / (ca[:, None] + cb[None, :] - want).astype(np.uint32).astype(np.float64)
+                keep &= (jac >= 0.9) & (jac <= 0.99) & (want != 0)
+                got = np.zeros((N1, N2), bool)
+                for s in range(N1):
+                    got[s, col[int(rp[s]):int(rp[s + 1])]] = True
+                assert np.array_equal(got, keep) and keep.any() and not keep.all()
+    # misuse
+    with libs.Context(device=0) as rows, libs.Context(device=0) as cols:
+        rows.load_patterns(t[1]); rows.load_hashtables(t[1])
+        cols.load_patterns(t[2])
+        with pytest.raises(libs.KdbxError, match="no k-mer tables loaded"):
+            rows.db2db_sparse(cols)
+        with pytest.raises(libs.KdbxError, match="two contexts"):
+            rows.db2db_sparse(rows)
+    for d in o.values():
+        oracle.oracle_db_free(d)
