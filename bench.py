@@ -76,6 +76,7 @@ def parse_args():
     ap.add_argument("--unit-updates", type=int, default=0)
     ap.add_argument("--tile-rows", type=int, default=0)
     ap.add_argument("--scatter-threads", type=int, default=0)
+    ap.add_argument("--upload-chunk-mb", type=int, default=0, help="payload bytes per chunk of the asynchronous upload (kdbx_config::upload_chunk_bytes); 0 = default")
     ap.add_argument("--chunked-lists", action="store_true", help="force the chunked parent-chain expansion")
     ap.add_argument("--list-form", choices=["auto", "ids", "boundaries"], default="auto",
                     help="form of the full sample lists (kdbx.h: KDBX_FLAG_ID_LISTS / KDBX_FLAG_BOUNDARY_LISTS); auto = the library decides")
@@ -371,7 +372,8 @@ def main():
     flags = ((kdbx.FLAG_CHUNKED_LISTS if a.chunked_lists else 0) | kdbx.FLAG_ASYNC_UPLOAD |
              {"auto": 0, "ids": kdbx.FLAG_ID_LISTS, "boundaries": kdbx.FLAG_BOUNDARY_LISTS}[a.list_form])
     ctx = kdbx.Context(device=local_rank, chunk_ids=a.chunk_ids, tile_cols=a.tile_cols, unit_updates=a.unit_updates,
-                       tile_rows=a.tile_rows, scatter_threads=a.scatter_threads, flags=flags)
+                       tile_rows=a.tile_rows, scatter_threads=a.scatter_threads, flags=flags,
+                       upload_chunk_bytes=a.upload_chunk_mb << 20)
     t_shard = 0.0
     window = (0, N)
     if world == 1:
@@ -496,7 +498,10 @@ def main():
         h2d = sum_over_ranks(P * hdr_bytes + int(tot.payload_bytes))  # summed over the ranks (every rank copies its own shard)
         e2e = {"value": U_total * a.steps / e2e_s, "unit": "updates/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": cells * 4, "ms_per_step": 1e3 * e2e_s / a.steps,
-               "ms_upload": st2.ms_upload, "ms_download": st2.ms_download}
+               "ms_upload": st2.ms_upload, "ms_download": st2.ms_download,
+               # device time of the compute call of the last step, from its first kernel to its last: it starts when the
+               # headers have arrived and contains the decoder's waits for the payload chunks still on the link
+               "ms_compute_after_headers": st2.ms_total, "ms_prepare": st2.ms_prepare}
 
     # ---- parity: the matrix of the timed configuration against the reference binary's CSV, byte for byte --------
     parity = None
@@ -588,7 +593,8 @@ def main():
         "shard_seconds_host": t_shard, "sample_window_rank0": list(window),
         "l2_policy": "inputs (trie %.1f GB + lists) exceed the 126 MB L2; no explicit flush" % ((P * 40 + int(tot.payload_bytes)) / 1e9),
         "chunk_ids": a.chunk_ids, "tile_cols": a.tile_cols, "unit_updates": a.unit_updates,
-        "tile_rows": a.tile_rows, "scatter_threads": a.scatter_threads, "list_form_requested": a.list_form})
+        "tile_rows": a.tile_rows, "scatter_threads": a.scatter_threads, "list_form_requested": a.list_form,
+        "upload_chunk_mb": a.upload_chunk_mb})
     line = {
         "metric": "k-mer-pair updates/sec on all2all", "value": value, "unit": "updates/s", "n_gpus": world,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": T_ms / a.steps, "higher_is_better": True,

@@ -56,7 +56,8 @@ typedef struct kdbx_config {
     uint64_t query_batch_kmers;  /* kdbx_new2all_batch: k-mers per device pass; 0 = 2^28      */
     uint32_t tile_rows;          /* matrix rows per accumulator tile (power of two <= 32); 0 = default */
     uint32_t scatter_threads;    /* threads per CTA of the scatter-add kernel; 0 = default     */
-    uint64_t reserved[1];
+    uint64_t upload_chunk_bytes; /* KDBX_FLAG_ASYNC_UPLOAD: bytes of Elias-gamma payload per chunk of the transfer (the
+                                    decoder starts on a chunk as soon as it has arrived); 0 = 96 MB, at most 8 chunks */
 } kdbx_config;
 
 #define KDBX_FLAG_NONE 0u
@@ -66,8 +67,9 @@ typedef struct kdbx_config {
 #define KDBX_FLAG_CHUNKED_LISTS 1u
 /* kdbx_load_patterns returns as soon as the copies are enqueued (headers on the compute stream, the
  * Elias-gamma payload on a second stream) instead of waiting for them, so that the first stages of
- * the next compute call overlap the tail of the transfer.  The caller's arrays must then stay
- * valid and unchanged until that compute call has returned. */
+ * the next compute call overlap the transfer: the headers travel first, the payload follows in chunks
+ * (kdbx_config::upload_chunk_bytes), and the decoder works on a chunk while the next ones are on the link.
+ * The caller's arrays must then stay valid and unchanged until that compute call has returned. */
 #define KDBX_FLAG_ASYNC_UPLOAD 2u
 /* Form of the full sample lists in the dense all2all.  Default: the library looks at the decoded local lists and
  * keeps every list as its sorted RUN BOUNDARIES (start of each run of consecutive ids, one past its end) when that

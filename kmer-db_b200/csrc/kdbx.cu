@@ -227,7 +227,16 @@ struct DecodeHist {
 __global__ void __launch_bounds__(kDecodeThreads)
 k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __restrict__ loff,
                 const uint32_t* __restrict__ bits, const uint64_t* __restrict__ poff, const uint64_t* __restrict__ payload,
-                uint64_t payload_words, uint32_t* __restrict__ loc, uint32_t win_lo, uint32_t win_n, int* __restrict__ err, DecodeHist dh) {
+                uint64_t payload_words, uint32_t* __restrict__ loc, uint32_t win_lo, uint32_t win_n, int* __restrict__ err, DecodeHist dh,
+                uint64_t w_lo, uint64_t w_hi) {
+    // Chunked launches while the payload is still arriving (prepare()): this launch takes the blocks whose payload —
+    // the words of its 128 patterns plus the two guard words the bit reader may touch — ends inside (w_lo, w_hi] words
+    // of the densely packed payload, i.e. inside the chunk that has just arrived.  (0, ~0] = every block.
+    if (w_lo != 0 || w_hi != ~0ull) {
+        const uint64_t pe = (uint64_t)blockIdx.x * kDecodeThreads + kDecodeThreads;
+        const uint64_t endw = poff[pe < P ? pe : P] + 2;
+        if (endw <= w_lo || endw > w_hi) return;
+    }
     __shared__ uint32_t s_ids[kDecodeStage];
     // per key: jobs in the top 12 bits, their updates in units of 1024 in the low 20 (a block's 128 patterns
     // hold at most 128 runs per key and 128 * 32 * N / 1024 < 2^20 such units with N <= 3072) — ONE
@@ -1063,6 +1072,10 @@ struct kdbx_ctx {
     cudaStream_t up_stream = nullptr;     // second H2D stream: the payload travels while the scans run
     cudaEvent_t ev_up_begin = nullptr, ev_up_hdr = nullptr, ev_up_payload = nullptr;
     bool upload_pending = false;          // KDBX_FLAG_ASYNC_UPLOAD: copies may still be in flight
+    // the payload travels in chunks (asynchronous uploads of a densely packed payload): chunk k = words
+    // [up_bounds[k], up_bounds[k+1]), complete when ev_up_chunk[k] is; the decoder starts on a chunk as soon as it is there
+    std::vector<uint64_t> up_bounds;
+    std::vector<cudaEvent_t> ev_up_chunk;
     kdbx_config cfg{};
     std::string err;
 
@@ -1411,13 +1424,29 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches, const DecodeHist*
         launches += n_launch;
     }
     CK(ctx->loc.ensure((ctx->sum_l + 32) * 4));
-    CK(cudaStreamWaitEvent(st, ctx->ev_up_payload, 0));  // the payload may still be on its way (second H2D stream)
     DecodeHist dh{};
     if (decode_hist) { dh = *decode_hist; dh.W = ctx->W.as<uint32_t>(); }
-    k_decode_locals<<<blocks_for(P, kDecodeThreads), kDecodeThreads, 0, st>>>(P, ctx->nodes.as<Node>(), ctx->loff.as<uint64_t>(), ctx->bits.as<uint32_t>(), ctx->poff.as<uint64_t>(),
-                                                         ctx->payload.as<uint64_t>(), ctx->payload_words, ctx->loc.as<uint32_t>(), ctx->win_lo,
-                                                         ctx->win_hi - ctx->win_lo, ctx->err_flag.as<int>(), dh);
-    launches += 1;
+    auto decode = [&](uint64_t w_lo, uint64_t w_hi) {
+        k_decode_locals<<<blocks_for(P, kDecodeThreads), kDecodeThreads, 0, st>>>(P, ctx->nodes.as<Node>(), ctx->loff.as<uint64_t>(), ctx->bits.as<uint32_t>(), ctx->poff.as<uint64_t>(),
+                                                             ctx->payload.as<uint64_t>(), ctx->payload_words, ctx->loc.as<uint32_t>(), ctx->win_lo,
+                                                             ctx->win_hi - ctx->win_lo, ctx->err_flag.as<int>(), dh, w_lo, w_hi);
+        launches += 1;
+    };
+    // the payload may still be on its way (second H2D stream).  When it travels in chunks, one launch per chunk takes
+    // the blocks whose payload that chunk completes: decoding overlaps the rest of the transfer
+    const size_t K = ctx->up_bounds.size() > 1 ? ctx->up_bounds.size() - 1 : 1;
+    bool chunked = ctx->upload_pending && ctx->dense_payload && K > 1 && ctx->ev_up_chunk.size() >= K;
+    if (chunked && cudaEventQuery(ctx->ev_up_payload) == cudaSuccess) chunked = false;   // (everything has arrived already)
+    cudaGetLastError();   // (cudaErrorNotReady of the query is not an error)
+    if (!chunked) {
+        CK(cudaStreamWaitEvent(st, ctx->ev_up_payload, 0));
+        decode(0, ~0ull);
+    } else {
+        for (size_t k = 0; k < K; ++k) {
+            CK(cudaStreamWaitEvent(st, k + 1 == K ? ctx->ev_up_payload : ctx->ev_up_chunk[k], 0));
+            decode(k == 0 ? 0 : ctx->up_bounds[k], k + 1 == K ? ~0ull : ctx->up_bounds[k + 1]);
+        }
+    }
     CK(cudaGetLastError());
     // chunk boundaries
     const uint64_t total_cost = ctx->sum_cost;
@@ -1951,6 +1980,7 @@ void kdbx_close(kdbx_ctx* ctx) {
     if (ctx->g_expand_diff.exec) cudaGraphExecDestroy(ctx->g_expand_diff.exec);
     if (ctx->up_stream) { cudaStreamSynchronize(ctx->up_stream); cudaStreamDestroy(ctx->up_stream); }
     for (cudaEvent_t e : {ctx->ev_up_begin, ctx->ev_up_hdr, ctx->ev_up_payload}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_up_chunk) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -2003,8 +2033,23 @@ int kdbx_load_patterns(kdbx_ctx* ctx, const kdbx_trie_view* v) {
         CK(cudaMemcpyAsync(ctx->poff.p, v->payload_off, P * 8, cudaMemcpyHostToDevice, st));
     }
     CK(cudaEventRecord(ctx->ev_up_hdr, st));
-    CK(cudaStreamWaitEvent(ctx->up_stream, ctx->ev_up_begin, 0));  // not before earlier work on the buffers is done
-    if (v->payload_words) CK(cudaMemcpyAsync(ctx->payload.p, v->payload, v->payload_words * 8, cudaMemcpyHostToDevice, ctx->up_stream));
+    // the payload follows the headers on the link (one copy at a time runs at link rate; sharing it would only delay the
+    // headers, which everything before the decoder waits for), in chunks when the upload is asynchronous, so that the
+    // decoder can start on the first chunk while the others travel (prepare())
+    CK(cudaStreamWaitEvent(ctx->up_stream, ctx->ev_up_hdr, 0));   // (also: not before earlier work on the buffers is done)
+    {
+        uint64_t K = 1;
+        if ((ctx->cfg.flags & KDBX_FLAG_ASYNC_UPLOAD) && ctx->dense_payload)
+            K = std::min<uint64_t>(8, std::max<uint64_t>(1, v->payload_words * 8 / (ctx->cfg.upload_chunk_bytes ? ctx->cfg.upload_chunk_bytes : ((uint64_t)96 << 20))));
+        ctx->up_bounds.assign(K + 1, 0);
+        for (uint64_t k = 0; k <= K; ++k) ctx->up_bounds[k] = k == K ? v->payload_words : (v->payload_words / K * k) & ~(uint64_t)1;
+        while (ctx->ev_up_chunk.size() < K) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->ev_up_chunk.push_back(e); }
+        for (uint64_t k = 0; k < K; ++k) {
+            const uint64_t b = ctx->up_bounds[k], e = ctx->up_bounds[k + 1];
+            if (e > b) CK(cudaMemcpyAsync(ctx->payload.as<uint64_t>() + b, v->payload + b, (e - b) * 8, cudaMemcpyHostToDevice, ctx->up_stream));
+            CK(cudaEventRecord(ctx->ev_up_chunk[k], ctx->up_stream));
+        }
+    }
     // two zero guard words: the decoder may touch word i+1 of a run that ends at a word edge
     CK(cudaMemsetAsync(ctx->payload.as<uint64_t>() + v->payload_words, 0, 16, ctx->up_stream));
     CK(cudaEventRecord(ctx->ev_up_payload, ctx->up_stream));

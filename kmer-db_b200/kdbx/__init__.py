@@ -28,7 +28,7 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("chunk_ids", C.c_uint64),
                 ("tile_cols", C.c_uint32), ("unit_updates", C.c_uint32), ("sparse_block_cells", C.c_uint64),
                 ("query_batch_kmers", C.c_uint64), ("tile_rows", C.c_uint32), ("scatter_threads", C.c_uint32),
-                ("reserved", C.c_uint64 * 1)]
+                ("upload_chunk_bytes", C.c_uint64)]
 
 
 class TrieView(C.Structure):
@@ -438,10 +438,10 @@ class Context:
 
     def __init__(self, device: int = -1, chunk_ids: int = 0, tile_cols: int = 0, unit_updates: int = 0,
                  sparse_block_cells: int = 0, query_batch_kmers: int = 0, tile_rows: int = 0, scatter_threads: int = 0,
-                 flags: int = 0):
+                 flags: int = 0, upload_chunk_bytes: int = 0):
         k, _ = load()
         self._k = k
-        cfg = Config(device, flags, chunk_ids, tile_cols, unit_updates, sparse_block_cells, query_batch_kmers, tile_rows, scatter_threads)
+        cfg = Config(device, flags, chunk_ids, tile_cols, unit_updates, sparse_block_cells, query_batch_kmers, tile_rows, scatter_threads, upload_chunk_bytes)
         p = C.c_void_p()
         rc = k.kdbx_open(C.byref(cfg), C.byref(p))
         if rc != 0:

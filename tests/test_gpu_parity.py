@@ -521,3 +521,22 @@ def test_sliding_column_window(libs, oracle, N, clusters, mu, flags, form):
             got, st = c.all2all_dense()
             assert st.updates == U and st.list_form == form
             assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("chunk_bytes", [0, 4096, 100_000])
+def test_asynchronous_chunked_upload(libs, oracle, chunk_bytes):
+    """KDBX_FLAG_ASYNC_UPLOAD: kdbx_load_patterns returns with the copies in flight — headers first, then the payload in up
+    to eight chunks — and the decoder is launched once per chunk on the blocks whose payload that chunk completes.  Same
+    bits as the synchronous path, for every chunk size, on re-staged tries of different sizes (buffers and events reused)."""
+    with libs.Context(device=0, flags=libs.FLAG_ASYNC_UPLOAD, upload_chunk_bytes=chunk_bytes) as c:
+        for N, gk, seed in ((300, 4000, 5), (700, 1500, 6), (300, 4000, 5)):
+            t = libs.Trie.synth(num_samples=N, num_clusters=3, genome_kmers=gk, seed=seed, mutation_rate=0.004, pinned=True)
+            want, U = ou.oracle_all2all(oracle, N, t.arrays())
+            c.load_patterns(t)
+            got, st = c.all2all_dense()
+            assert st.updates == U and np.array_equal(got, want)
+            got, st = c.all2all_dense()      # (resident: nothing in flight, one decoder launch)
+            assert st.updates == U and np.array_equal(got, want)
+            c.load_patterns(t)               # staged again while nothing else runs
+            rp, col, val, st = c.all2all_sparse()
+            assert int(rp[-1]) == int(np.count_nonzero(want))

@@ -36,6 +36,7 @@ for step in "$@"; do
     scale_new) for n in ${SCALE_NS:-2}; do for mode in ${SCALE_MODES:-weak strong}; do timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps ${SCALE_STEPS:-5} --warmup 3 --scaling $mode > "$OUT/scale_${mode}_$n.json" 2> "$OUT/scale_${mode}_$n.err"; echo "scale $mode $n rc=$?" | tee -a "$OUT/summary.txt"; done; done;;
     cfg4) timeout 2400 python tools/run_cfg4.py --gpus ${CFG4_GPUS:-1} > "$OUT/cfg4_g${CFG4_GPUS:-1}.json" 2> "$OUT/cfg4.err"; echo "cfg4 rc=$?" | tee -a "$OUT/summary.txt";;
     cfg5) timeout 2400 python tools/bench_modes.py --out-dir /tmp/kdbx_cfg5 --skip sp --db-genomes ${CFG5_DB:-2000} --db-clusters 40 --queries ${CFG5_Q:-1000} --len 1000000 > "$OUT/cfg5.jsonl" 2> "$OUT/cfg5.err"; echo "cfg5 rc=$?" | tee -a "$OUT/summary.txt";;
+    bench_nochunk) timeout 900 python bench.py --no-cpu-baseline --upload-chunk-mb 100000 > "$OUT/bench_nochunk.json" 2> "$OUT/bench_nochunk.err"; echo "bench_nochunk rc=$?" | tee -a "$OUT/summary.txt";;
     *) echo "unknown step $step";;
   esac
 done
