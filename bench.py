@@ -495,6 +495,8 @@ def main():
         got = sum_over_ranks(int(out_host[:own].astype(np.int64).sum()))
         assert got == checksum, "e2e result differs from the device-resident result"
         hdr_bytes = 24 if trie.view().parent_id32 else 40   # (32-bit mirrors of parent_id / num_kmers: kdbx_trie_view)
+        if trie.view().payload_off:                          # (offsets travel too unless the payload is densely packed)
+            hdr_bytes += 8
         h2d = sum_over_ranks(P * hdr_bytes + int(tot.payload_bytes))  # summed over the ranks (every rank copies its own shard)
         e2e = {"value": U_total * a.steps / e2e_s, "unit": "updates/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": cells * 4, "ms_per_step": 1e3 * e2e_s / a.steps,

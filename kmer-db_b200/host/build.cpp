@@ -275,6 +275,7 @@ void DbBuilder::finish(Trie& out) {
     pats_.emplace_back();
     hdr_ = DbHeader();
     hdr_.is_initialized = 0;
+    out.build_compact();
 }
 
 }  // namespace kdbx

@@ -102,6 +102,7 @@ public:
             ht.slots.assign(slots.begin() + (std::ptrdiff_t)slot_off[t], slots.begin() + (std::ptrdiff_t)slot_off[t + 1]);
             ht.filled = filled[t];
         }
+        out.build_compact();
     }
     const kdbx_build_result& result() const { return result_; }
     const DbHeader& header() const { return hdr_; }

@@ -410,6 +410,7 @@ void synth_generate(const SynthParams& sp_in, Trie& t) {
             }
         }
     }
+    t.build_compact();
 }
 
 }  // namespace kdbx

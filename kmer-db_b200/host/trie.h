@@ -173,16 +173,29 @@ struct Trie {
         payload_off.set_pinned(pinned); payload.set_pinned(pinned);
         parent32.set_pinned(pinned); num_kmers32.set_pinned(pinned);
     }
-    // (re)builds the 32-bit mirrors; leaves them empty when a value does not fit
+    // Is the payload densely packed in pattern order (pattern p's words start where pattern p-1's end)?  Every trie this
+    // code writes is; view() then hands out payload_off = NULL and the 8 bytes of offset per pattern stay off the link
+    // (kdbx_trie_view: "NULL = densely packed in pattern order"; the library derives the offsets from num_bits by a scan).
+    bool payload_dense = false;
+
+    // Called where a trie is finished (reader, partitioner, generator, builders): (re)builds the 32-bit mirrors — left
+    // empty when a value does not fit — and records whether the payload is densely packed.
     void build_compact() {
         const uint64_t P = num_patterns();
         parent32.clear(); num_kmers32.clear();
+        payload_dense = payload_off.size() == P;
+        uint64_t at = 0;
+        for (uint64_t p = 0; p < P && payload_dense; ++p) {
+            if (payload_off[p] != at) payload_dense = false;
+            at += payload_words_for_bits(bits[p]);
+        }
+        if (payload_dense && at != payload.size()) payload_dense = false;
         for (uint64_t p = 0; p < P; ++p)
             if (num_kmers[p] < 0 || num_kmers[p] > 0xFFFFFFFFll || parent_id[p] < -1 || parent_id[p] > 0x7FFFFFFFll) return;
         parent32.resize(P); num_kmers32.resize(P);
         for (uint64_t p = 0; p < P; ++p) { parent32[p] = (int32_t)parent_id[p]; num_kmers32[p] = (uint32_t)num_kmers[p]; }
     }
-    void drop_compact() { parent32.clear(); num_kmers32.clear(); }
+    void drop_compact() { parent32.clear(); num_kmers32.clear(); payload_dense = false; }
 
     uint64_t num_patterns() const { return n.size(); }
     uint32_t num_samples() const { return (uint32_t)sample_names.size(); }
@@ -201,7 +214,7 @@ struct Trie {
         v.num_local_samples = l.data();
         v.last_sample_id = last.data();
         v.num_bits = bits.data();
-        v.payload_off = payload_off.data();
+        v.payload_off = payload_dense ? nullptr : payload_off.data();
         v.payload = payload.data();
         v.payload_words = payload.size();
         if (parent32.size() == num_patterns() && num_kmers32.size() == num_patterns() && num_patterns()) {

@@ -379,11 +379,18 @@ class Trie:
         """Zero-copy numpy views of the SoA arrays (valid while the Trie lives)."""
         v = self.view()
         P = int(v.num_patterns)
+        bits = _np_from(v.num_bits, P, np.uint32)
+        if v.payload_off:
+            payload_off = _np_from(v.payload_off, P, np.uint64)
+        else:   # densely packed in pattern order (the view says so with NULL): ceil(bits / 128) * 2 words per pattern
+            words = ((bits.astype(np.uint64) + np.uint64(127)) // np.uint64(128)) * np.uint64(2)
+            payload_off = np.zeros(P, np.uint64)
+            np.cumsum(words[:-1], out=payload_off[1:])
         return {
             "num_kmers": _np_from(v.num_kmers, P, np.int64), "parent_id": _np_from(v.parent_id, P, np.int64),
             "n": _np_from(v.num_samples_full, P, np.uint32), "l": _np_from(v.num_local_samples, P, np.uint32),
-            "last": _np_from(v.last_sample_id, P, np.uint32), "bits": _np_from(v.num_bits, P, np.uint32),
-            "payload_off": _np_from(v.payload_off, P, np.uint64),
+            "last": _np_from(v.last_sample_id, P, np.uint32), "bits": bits,
+            "payload_off": payload_off,
             "payload": _np_from(v.payload, int(v.payload_words), np.uint64),
         }
 
