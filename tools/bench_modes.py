@@ -6,6 +6,8 @@ prints one JSON line per mode.  Inputs are synthetic and seeded:
   all2all-sp   pattern-level database (kmer-db_b200/host/synth.cpp): many small clusters -> sparse matrix
   build        FASTA-level genomes written here (clusters of mutated copies), our host `build` vs the reference's
   new2all      queries = further mutated copies; GPU probe + scatter vs the reference's one2all per query
+  all2all-parts (--parts P) the genomes dealt round-robin to P partial databases (every part holds members of every cluster, so
+               the cells off the diagonal are as full as the diagonal ones); device db2db + all2all-sp per cell vs the reference
 
     python tools/bench_modes.py [--out-dir DIR] [--sp-samples N --sp-clusters C --sp-len L] [--db-genomes G --queries Q --len L]
 """
@@ -91,6 +93,10 @@ def main():
     ap.add_argument("--db-clusters", type=int, default=8)
     ap.add_argument("--queries", type=int, default=100)
     ap.add_argument("--len", type=int, default=1000000)
+    ap.add_argument("--parts", type=int, default=0, help="all2all-parts over this many partial databases (0 = skip the mode)")
+    ap.add_argument("--parts-genomes", type=int, default=400)
+    ap.add_argument("--parts-clusters", type=int, default=8)
+    ap.add_argument("--parts-len", type=int, default=500000)
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
     ap.add_argument("--skip", default="")
     a = ap.parse_args()
@@ -174,6 +180,49 @@ def main():
             # our database must serve the reference too, and vice versa
             run([EXE, "new2all", out / "n2a.ref.db", out / "q.list", out / "n2a.cross.csv"])
             line["csv_identical_on_reference_built_db"] = same(out / "n2a.cross.csv", out / "n2a.ref.csv")
+        print(json.dumps(line), flush=True)
+
+    if a.parts > 0:
+        names, _ = make_genomes(out / "fa_parts", a.parts_genomes, a.parts_clusters, a.parts_len, 0.005, 21, "p")
+        ours_list, ref_list = [], []
+        t_build_ours = t_build_ref = 0.0
+        for j in range(a.parts):
+            lst = out / f"part{j}.list"
+            lst.write_text("\n".join(names[j::a.parts]) + "\n")
+            _, dt = run([EXE, "build", "-t", a.threads, lst, out / f"part{j}.ours.db"])
+            t_build_ours += dt
+            ours_list.append(str(out / f"part{j}.ours.db"))
+            if have_ref:
+                _, dt = run([REF, "build", "-t", a.threads, lst, out / f"part{j}.ref.db"])
+                t_build_ref += dt
+                ref_list.append(str(out / f"part{j}.ref.db"))
+        (out / "parts.ours.list").write_text("\n".join(ours_list) + "\n")
+        runs = []
+        for _ in range(2):
+            text, wall = run([EXE, "all2all-parts", out / "parts.ours.list", out / "parts.ours.csv"])
+            runs.append((stats_json(text), wall))
+        st, wall = min(runs, key=lambda r: r[1])
+        saved = re.search(r"No\. saved pairs: (\d+)", text)
+        line = {"mode": "all2all-parts",
+                "workload": f"{a.parts_genomes} genomes x {a.parts_len} bp, {a.parts_clusters} clusters, dealt round-robin to {a.parts} partial databases "
+                            f"(k=18, FASTA-level synthetic, built on the device)",
+                "cell_updates": st.get("updates"), "kmers_probed": st.get("probes"), "kmers_in_both": st.get("hits"),
+                "saved_pairs": int(saved.group(1)) if saved else None,
+                "ours_wall_seconds_incl_db_load": wall, "ours_wall_both_runs": [r[1] for r in runs],
+                "ours_device_ms": {k: st.get(k) for k in ("ms_prepare", "ms_probe", "ms_scatter", "ms_compact", "ms_total", "ms_download")},
+                "ours_build_wall_seconds_all_parts": t_build_ours}
+        if have_ref:
+            (out / "parts.ref.list").write_text("\n".join(ref_list) + "\n")
+            text, rwall = run([REF, "all2all-parts", "-t", a.threads, out / "parts.ref.list", out / "parts.ref.csv"])
+            m = re.search(r"All2All time\s*:\s*([0-9.eE+-]+)", text)
+            ml = re.search(r"Load time\s*:\s*([0-9.eE+-]+)", text)
+            line.update({"reference_wall_seconds_incl_db_load": rwall, "reference_all2all_seconds": float(m.group(1)) if m else None,
+                         "reference_load_seconds": float(ml.group(1)) if ml else None, "reference_threads": a.threads,
+                         "reference_build_wall_seconds_all_parts": t_build_ref,
+                         "csv_identical": same(out / "parts.ours.csv", out / "parts.ref.csv")})
+            # the grid over the databases the REFERENCE built must give the same table
+            run([EXE, "all2all-parts", out / "parts.ref.list", out / "parts.cross.csv"])
+            line["csv_identical_on_reference_built_parts"] = same(out / "parts.cross.csv", out / "parts.ref.csv")
         print(json.dumps(line), flush=True)
 
 

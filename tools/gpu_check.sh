@@ -37,6 +37,10 @@ for step in "$@"; do
     cfg4) timeout 2400 python tools/run_cfg4.py --gpus ${CFG4_GPUS:-1} > "$OUT/cfg4_g${CFG4_GPUS:-1}.json" 2> "$OUT/cfg4.err"; echo "cfg4 rc=$?" | tee -a "$OUT/summary.txt";;
     cfg5) timeout 2400 python tools/bench_modes.py --out-dir /tmp/kdbx_cfg5 --skip sp --db-genomes ${CFG5_DB:-2000} --db-clusters 40 --queries ${CFG5_Q:-1000} --len 1000000 > "$OUT/cfg5.jsonl" 2> "$OUT/cfg5.err"; echo "cfg5 rc=$?" | tee -a "$OUT/summary.txt";;
     bench_nochunk) timeout 900 python bench.py --no-cpu-baseline --upload-chunk-mb 100000 > "$OUT/bench_nochunk.json" 2> "$OUT/bench_nochunk.err"; echo "bench_nochunk rc=$?" | tee -a "$OUT/summary.txt";;
+    parts) timeout 1200 python tools/bench_modes.py --out-dir /tmp/kdbx_parts --skip sp,n2a --parts ${PARTS:-4} --parts-genomes ${PARTS_GENOMES:-400} --parts-len ${PARTS_LEN:-500000} > "$OUT/parts.jsonl" 2> "$OUT/parts.err"; echo "parts rc=$?" | tee -a "$OUT/summary.txt";;
+    sanitize_new) timeout 900 compute-sanitizer --tool memcheck --target-processes all --error-exitcode 9 python -m pytest tests -m gpu -x -q -k "db2db or asynchronous_chunked or cli_all2all_parts" > "$OUT/sanitizer_memcheck_new.log" 2>&1; echo "memcheck_new rc=$?" | tee -a "$OUT/summary.txt";;
+    ncu_final) timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:k_scatter_diff|k_decode_locals|k_job_fill_runs" -s 3 -c 3 -f -o "$OUT/final_cfg2" python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_final.out" 2>&1; echo "ncu_final rc=$?" | tee -a "$OUT/summary.txt";;
+    sanitize_new2) timeout 900 compute-sanitizer --tool memcheck --target-processes all --error-exitcode 9 python -m pytest tests -m gpu -x -q -k "db2db_cells or asynchronous_chunked" > "$OUT/sanitizer_memcheck_new.log" 2>&1; echo "memcheck_new rc=$?" | tee -a "$OUT/summary.txt";;
     *) echo "unknown step $step";;
   esac
 done
