@@ -169,6 +169,8 @@ __device__ __forceinline__ uint32_t gamma_field(const uint64_t* __restrict__ w, 
     return (uint32_t)(x >> (64 - cnt));
 }
 
+#include "gamma_tokens.cuh"
+
 // One Elias-gamma value at bit `pos` (format: SURVEY.md §A.1); `limit` = num_bits guards
 // against malformed streams (returns 0 and leaves pos >= limit).
 __device__ __forceinline__ uint32_t gamma_next(const uint64_t* __restrict__ w, uint32_t& pos, uint32_t limit) {
@@ -224,6 +226,7 @@ struct DecodeHist {
     uint32_t* ownb;
     unsigned long long* sum_app;
 };
+template <bool kTokens>   // kTokens: the token parser of gamma_tokens.cuh (default); false: one delta parked per id (KDBX_DECODER=deltas, for A/B)
 __global__ void __launch_bounds__(kDecodeThreads)
 k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __restrict__ loff,
                 const uint32_t* __restrict__ bits, const uint64_t* __restrict__ poff, const uint64_t* __restrict__ payload,
@@ -286,7 +289,11 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
                 if (!ok) atomicExch(err, 5);
                 uint32_t pos = 0, runs = 1;
                 uint64_t sum = 0;
-                if (ok) {
+                if (ok && kTokens) {
+                    const int rc = gamma_parse_tokens(payload + po, nb, nd.l, out, sum, runs);
+                    if (rc == 1) { atomicExch(err, 1); ok = false; }
+                    else if (rc == 2 || sum > nd.last) { atomicExch(err, 2); ok = false; }
+                } else if (ok) {
                     const uint64_t* w = payload + po;
                     uint32_t i = 1;
                     while (i < nd.l && pos < nb) {
@@ -319,6 +326,11 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
                     out[0] = cur;
                     if (!ok) {
                         for (uint32_t i = 1; i < nd.l; ++i) out[i] = 0;
+                    } else if (kTokens && !dh.enabled) {
+                        tokens_to_ids(out, nd.l, cur);
+                    } else if (kTokens) {
+                        const uint32_t w = dh.W[p];
+                        tokens_to_ids_blocks(out, nd.l, cur, dh.rb_shift, [&](uint32_t rb, uint32_t j, uint32_t k) { close_run(rb, first + j, k, w); });
                     } else if (!dh.enabled) {
                         for (uint32_t i = 1; i < nd.l; ++i) { cur += out[i]; out[i] = cur; }
                     } else {
@@ -1072,6 +1084,7 @@ struct kdbx_ctx {
     cudaStream_t up_stream = nullptr;     // second H2D stream: the payload travels while the scans run
     cudaEvent_t ev_up_begin = nullptr, ev_up_hdr = nullptr, ev_up_payload = nullptr;
     bool upload_pending = false;          // KDBX_FLAG_ASYNC_UPLOAD: copies may still be in flight
+    bool decoder_deltas = false;          // KDBX_DECODER=deltas in the environment: the previous decoder (one parked delta per id), for A/B runs
     // the payload travels in chunks (asynchronous uploads of a densely packed payload): chunk k = words
     // [up_bounds[k], up_bounds[k+1]), complete when ev_up_chunk[k] is; the decoder starts on a chunk as soon as it is there
     std::vector<uint64_t> up_bounds;
@@ -1427,7 +1440,8 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches, const DecodeHist*
     DecodeHist dh{};
     if (decode_hist) { dh = *decode_hist; dh.W = ctx->W.as<uint32_t>(); }
     auto decode = [&](uint64_t w_lo, uint64_t w_hi) {
-        k_decode_locals<<<blocks_for(P, kDecodeThreads), kDecodeThreads, 0, st>>>(P, ctx->nodes.as<Node>(), ctx->loff.as<uint64_t>(), ctx->bits.as<uint32_t>(), ctx->poff.as<uint64_t>(),
+        auto* kernel = ctx->decoder_deltas ? k_decode_locals<false> : k_decode_locals<true>;
+        kernel<<<blocks_for(P, kDecodeThreads), kDecodeThreads, 0, st>>>(P, ctx->nodes.as<Node>(), ctx->loff.as<uint64_t>(), ctx->bits.as<uint32_t>(), ctx->poff.as<uint64_t>(),
                                                              ctx->payload.as<uint64_t>(), ctx->payload_words, ctx->loc.as<uint32_t>(), ctx->win_lo,
                                                              ctx->win_hi - ctx->win_lo, ctx->err_flag.as<int>(), dh, w_lo, w_hi);
         launches += 1;
@@ -1947,6 +1961,7 @@ int kdbx_open(const kdbx_config* cfg, kdbx_ctx** out) {
     ctx->device = dev;
     ctx->sm_count = pr.multiProcessorCount;
     if (cfg) ctx->cfg = *cfg;
+    if (const char* d = std::getenv("KDBX_DECODER")) ctx->decoder_deltas = std::strcmp(d, "deltas") == 0;
     if ((e = cudaSetDevice(dev)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev_up_begin)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_up_hdr)) != cudaSuccess ||

@@ -319,3 +319,106 @@ def test_pattern_level_generator_matches_a_fasta_level_build_of_the_same_model(l
     for f in fields:
         assert abs(sy[f] - fa[f]) <= 0.12 * fa[f], (f, fa[f] / len(seeds), sy[f] / len(seeds))
     assert abs(sy["kmers_count"] - fa["kmers_count"]) <= 0.03 * fa["kmers_count"]
+
+
+# ---- the decoder's per-pattern code (kmer-db_b200/csrc/gamma_tokens.cuh), compiled for the host ----------------------------
+@pytest.fixture(scope="module")
+def gamma_tokens(tmp_path_factory):
+    so = tmp_path_factory.mktemp("native") / "libgamma_tokens_host.so"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(so), str(ROOT / "tests" / "native" / "gamma_tokens_host.cpp")], check=True)
+    lib = C.CDLL(str(so))
+    lib.kdbx_test_decode_list.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    return lib
+
+
+def _encode_gamma(deltas):
+    """(words with two guard words, number of bits) of the Elias-gamma stream of `deltas` (MSB first; 1 -> '0')."""
+    bits = []
+    for d in deltas:
+        b = int(d).bit_length()
+        bits += [1] * (b - 1) + [0] + [(int(d) >> k) & 1 for k in range(b - 2, -1, -1)]
+    nb = len(bits)
+    words = max(2, ((nb + 127) // 128) * 2) + 2
+    w = np.zeros(words, np.uint64)
+    for i, bit in enumerate(bits):
+        if bit:
+            w[i >> 6] |= np.uint64(1) << np.uint64(63 - (i & 63))
+    return w, nb
+
+
+def _decode(lib, w, nb, l, last, sh=None):
+    out = np.zeros(max(1, l), np.uint32)
+    closes = np.zeros(3 * max(1, l), np.uint32)
+    n, runs = C.c_uint32(0), C.c_uint32(0)
+    rc = lib.kdbx_test_decode_list(w.ctypes.data, nb, l, last, 0 if sh is None else 1, sh or 0, out.ctypes.data, closes.ctypes.data, C.byref(n), C.byref(runs))
+    return rc, out[:l], closes[:3 * n.value].reshape(-1, 3), runs.value
+
+
+def test_gamma_tokens_against_oracle_on_random_lists(gamma_tokens, oracle):
+    """Token parser + both second passes == the oracle's decoder (oracle_decode_local) on random ascending lists with long runs
+    of consecutive ids, lone ids, huge gaps and runs that straddle 64-bit words; the row-block stretches equal a per-id scan."""
+    rng = np.random.default_rng(5)
+    for trial in range(400):
+        l = int(rng.integers(2, 400))
+        style = trial % 4
+        if style == 0:
+            deltas = np.ones(l - 1, np.int64)
+        elif style == 1:
+            deltas = rng.integers(1, 3, size=l - 1)
+        elif style == 2:
+            deltas = np.where(rng.random(l - 1) < 0.85, 1, rng.integers(2, 5000, size=l - 1))
+        else:
+            deltas = rng.integers(1, 2**20, size=l - 1)
+        first = int(rng.integers(0, 1000))
+        ids = first + np.concatenate([[0], np.cumsum(deltas)])
+        last = int(ids[-1])
+        w, nb = _encode_gamma(deltas)
+        want = np.zeros(l, np.uint32)
+        oracle.oracle_decode_local(w.ctypes.data, l, last, want.ctypes.data)
+        assert np.array_equal(want, ids.astype(np.uint32))
+        rc, got, _, runs = _decode(gamma_tokens, w, nb, l, last)
+        assert rc == 0 and np.array_equal(got, want) and runs == 1 + int((deltas >= 2).sum())
+        for sh in (0, 3, 5):
+            rc, got, closes, _ = _decode(gamma_tokens, w, nb, l, last, sh)
+            assert rc == 0 and np.array_equal(got, want)
+            rb = ids >> sh
+            starts = np.concatenate([[0], np.nonzero(np.diff(rb))[0] + 1])
+            ends = np.concatenate([starts[1:], [l]])
+            assert np.array_equal(closes, np.stack([rb[starts], starts, ends - starts], axis=1).astype(np.uint32))
+
+
+def test_gamma_tokens_rejects_malformed_streams(gamma_tokens):
+    deltas = [1, 1, 5, 1, 300, 1, 1, 1, 2]
+    w, nb = _encode_gamma(deltas)
+    l, last = len(deltas) + 1, 1000
+    assert _decode(gamma_tokens, w, nb, l, last)[0] == 0
+    assert _decode(gamma_tokens, w, nb - 1, l, last)[0] == 1        # a bit short
+    assert _decode(gamma_tokens, w, nb + 1, l, last)[0] == 1        # a bit long
+    assert _decode(gamma_tokens, w, nb, l + 1, last)[0] == 1        # one id too many
+    assert _decode(gamma_tokens, w, nb, l - 1, last)[0] == 1        # one too few: bits left over
+    assert _decode(gamma_tokens, w, nb, l, 100)[0] == 3             # deltas sum to more than the last id
+    ones = np.full(4, np.uint64(0xFFFFFFFFFFFFFFFF))
+    assert _decode(gamma_tokens, ones, 128, 3, 10)[0] == 1           # a unary prefix longer than any code
+    w31, nb31 = _encode_gamma([2**31 + 5])
+    assert _decode(gamma_tokens, w31, nb31, 2, 2**32 - 1)[0] == 2    # a delta that no sample id can reach
+
+
+def test_gamma_tokens_on_the_reference_built_databases(gamma_tokens, oracle, libs, golden_dbs):
+    """Every pattern of the databases the reference built (tests/golden), decoded in place from the packed payload (the next
+    pattern's words follow immediately): same ids as the oracle."""
+    checked = 0
+    for name in ("virus.k18", "synth.k21", "virus.k18.f01"):
+        t = libs.Trie.read_db(golden_dbs[name][0])   # (the arrays are views into it)
+        a = t.arrays()
+        pay = np.concatenate([a["payload"], np.zeros(2, np.uint64)])
+        for p in range(len(a["n"])):
+            l = int(a["l"][p])
+            if l < 2:
+                continue
+            w = pay[int(a["payload_off"][p]):]
+            want = np.zeros(l, np.uint32)
+            oracle.oracle_decode_local(w.ctypes.data, l, int(a["last"][p]), want.ctypes.data)
+            rc, got, closes, _ = _decode(gamma_tokens, w, int(a["bits"][p]), l, int(a["last"][p]), 5)
+            assert rc == 0 and np.array_equal(got, want) and int(closes[:, 2].sum()) == l
+            checked += 1
+    assert checked > 50
