@@ -161,39 +161,14 @@ __global__ void k_push_level(uint32_t count, const uint32_t* __restrict__ order,
     if (v) atomicAdd(&W[q], v);
 }
 
-__device__ __forceinline__ uint32_t gamma_field(const uint64_t* __restrict__ w, uint32_t pos, uint32_t cnt) {
-    if (cnt == 0) return 0;
-    const uint32_t i = pos >> 6, off = pos & 63;
-    uint64_t x = w[i] << off;
-    if (off + cnt > 64) x |= w[i + 1] >> (64 - off);
-    return (uint32_t)(x >> (64 - cnt));
-}
-
-#include "gamma_tokens.cuh"
-
-// One Elias-gamma value at bit `pos` (format: SURVEY.md §A.1); `limit` = num_bits guards
-// against malformed streams (returns 0 and leaves pos >= limit).
-__device__ __forceinline__ uint32_t gamma_next(const uint64_t* __restrict__ w, uint32_t& pos, uint32_t limit) {
-    uint32_t ones = 0;
-    while (pos < limit) {
-        const uint32_t i = pos >> 6, off = pos & 63;
-        const uint64_t x = ~(w[i] << off);
-        const uint32_t avail = 64 - off;
-        const uint32_t run = x ? (uint32_t)__clzll((long long)x) : 64u;
-        if (run >= avail) { ones += avail; pos += avail; continue; }
-        ones += run; pos += run + 1;
-        if (ones > 31 || pos + ones > limit) { pos = limit + 1; return 0; }
-        const uint32_t low = gamma_field(w, pos, ones);
-        pos += ones;
-        return (1u << ones) | low;
-    }
-    pos = limit + 1;
-    return 0;
-}
+#include "gamma_tokens.cuh"   // the Elias-gamma parser: one walk of the bits, one token per run of zero bits
 
 // Decodes the LOCAL ids of every pattern into d_loc (ascending), one thread per pattern.  The
 // stream holds the deltas in append order and only the LAST id is stored (src/pattern.cpp:99-109):
-// a thread walks its bits once, parking the deltas, then turns them into ids front to back.
+// a thread walks its bits once, parking one token per delta >= 2 and per run of deltas of 1, then turns the tokens into
+// ids front to back (gamma_tokens.cuh; measured equal to parking one delta per id, 24.6 ms of prepare either way at
+// config 2 — runs average 3.4 ids there — and kept because the same code is compiled for the host and tested against the
+// oracle without a GPU).
 // The local lists of the 128 consecutive patterns of a block are contiguous in d_loc, so they are
 // staged in shared memory and written out with coalesced stores (a thread writing its own list
 // straight to HBM costs one 32-byte sector per 4-byte id); blocks whose lists do not fit the stage
@@ -226,7 +201,6 @@ struct DecodeHist {
     uint32_t* ownb;
     unsigned long long* sum_app;
 };
-template <bool kTokens>   // kTokens: the token parser of gamma_tokens.cuh (default); false: one delta parked per id (KDBX_DECODER=deltas, for A/B)
 __global__ void __launch_bounds__(kDecodeThreads)
 k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __restrict__ loff,
                 const uint32_t* __restrict__ bits, const uint64_t* __restrict__ poff, const uint64_t* __restrict__ payload,
@@ -287,34 +261,12 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
                 const uint64_t po = poff[p];
                 bool ok = po + ((uint64_t)(nb + 127u) / 128u) * 2u <= payload_words;
                 if (!ok) atomicExch(err, 5);
-                uint32_t pos = 0, runs = 1;
+                uint32_t runs = 1;
                 uint64_t sum = 0;
-                if (ok && kTokens) {
+                if (ok) {
                     const int rc = gamma_parse_tokens(payload + po, nb, nd.l, out, sum, runs);
                     if (rc == 1) { atomicExch(err, 1); ok = false; }
                     else if (rc == 2 || sum > nd.last) { atomicExch(err, 2); ok = false; }
-                } else if (ok) {
-                    const uint64_t* w = payload + po;
-                    uint32_t i = 1;
-                    while (i < nd.l && pos < nb) {
-                        // a delta of 1 is the single bit 0 (consecutive sample ids): take a whole run of
-                        // zero bits at once — most of a cluster's lists are such runs
-                        const uint32_t off = pos & 63;
-                        const uint64_t x = w[pos >> 6] << off;
-                        uint32_t z = x ? (uint32_t)__clzll((long long)x) : 64u;
-                        z = min(min(z, 64u - off), min(nb - pos, nd.l - i));
-                        if (z) {
-                            for (uint32_t t = 0; t < z; ++t) out[i + t] = 1u;
-                            i += z; pos += z; sum += z;
-                            continue;
-                        }
-                        const uint32_t d = gamma_next(w, pos, nb);   // >= 2 (the next bit is a one), or 0 on a malformed stream
-                        out[i++] = d;
-                        sum += d;
-                        ++runs;
-                    }
-                    if (i != nd.l || pos != nb) { atomicExch(err, 1); ok = false; }
-                    else if (sum > nd.last) { atomicExch(err, 2); ok = false; }
                 }
                 if (ok) {
                     uint32_t cur = nd.last - (uint32_t)sum;
@@ -326,25 +278,11 @@ k_decode_locals(uint64_t P, const Node* __restrict__ nodes, const uint64_t* __re
                     out[0] = cur;
                     if (!ok) {
                         for (uint32_t i = 1; i < nd.l; ++i) out[i] = 0;
-                    } else if (kTokens && !dh.enabled) {
-                        tokens_to_ids(out, nd.l, cur);
-                    } else if (kTokens) {
-                        const uint32_t w = dh.W[p];
-                        tokens_to_ids_blocks(out, nd.l, cur, dh.rb_shift, [&](uint32_t rb, uint32_t j, uint32_t k) { close_run(rb, first + j, k, w); });
                     } else if (!dh.enabled) {
-                        for (uint32_t i = 1; i < nd.l; ++i) { cur += out[i]; out[i] = cur; }
+                        tokens_to_ids(out, nd.l, cur);
                     } else {
                         const uint32_t w = dh.W[p];
-                        uint32_t run_j = 0, run_rb = cur >> dh.rb_shift;
-                        for (uint32_t i = 1; i < nd.l; ++i) {
-                            cur += out[i]; out[i] = cur;
-                            const uint32_t rb = cur >> dh.rb_shift;
-                            if (rb != run_rb) {
-                                close_run(run_rb, first + run_j, i - run_j, w);
-                                run_j = i; run_rb = rb;
-                            }
-                        }
-                        close_run(run_rb, first + run_j, nd.l - run_j, w);
+                        tokens_to_ids_blocks(out, nd.l, cur, dh.rb_shift, [&](uint32_t rb, uint32_t j, uint32_t k) { close_run(rb, first + j, k, w); });
                     }
                 } else {
                     for (uint32_t i = 0; i < nd.l; ++i) out[i] = 0;  // never chased: the call fails on the error flag
@@ -1084,7 +1022,6 @@ struct kdbx_ctx {
     cudaStream_t up_stream = nullptr;     // second H2D stream: the payload travels while the scans run
     cudaEvent_t ev_up_begin = nullptr, ev_up_hdr = nullptr, ev_up_payload = nullptr;
     bool upload_pending = false;          // KDBX_FLAG_ASYNC_UPLOAD: copies may still be in flight
-    bool decoder_deltas = false;          // KDBX_DECODER=deltas in the environment: the previous decoder (one parked delta per id), for A/B runs
     // the payload travels in chunks (asynchronous uploads of a densely packed payload): chunk k = words
     // [up_bounds[k], up_bounds[k+1]), complete when ev_up_chunk[k] is; the decoder starts on a chunk as soon as it is there
     std::vector<uint64_t> up_bounds;
@@ -1440,8 +1377,7 @@ int prepare(kdbx_ctx* ctx, const Plan& pl, uint32_t& launches, const DecodeHist*
     DecodeHist dh{};
     if (decode_hist) { dh = *decode_hist; dh.W = ctx->W.as<uint32_t>(); }
     auto decode = [&](uint64_t w_lo, uint64_t w_hi) {
-        auto* kernel = ctx->decoder_deltas ? k_decode_locals<false> : k_decode_locals<true>;
-        kernel<<<blocks_for(P, kDecodeThreads), kDecodeThreads, 0, st>>>(P, ctx->nodes.as<Node>(), ctx->loff.as<uint64_t>(), ctx->bits.as<uint32_t>(), ctx->poff.as<uint64_t>(),
+        k_decode_locals<<<blocks_for(P, kDecodeThreads), kDecodeThreads, 0, st>>>(P, ctx->nodes.as<Node>(), ctx->loff.as<uint64_t>(), ctx->bits.as<uint32_t>(), ctx->poff.as<uint64_t>(),
                                                              ctx->payload.as<uint64_t>(), ctx->payload_words, ctx->loc.as<uint32_t>(), ctx->win_lo,
                                                              ctx->win_hi - ctx->win_lo, ctx->err_flag.as<int>(), dh, w_lo, w_hi);
         launches += 1;
@@ -1961,7 +1897,6 @@ int kdbx_open(const kdbx_config* cfg, kdbx_ctx** out) {
     ctx->device = dev;
     ctx->sm_count = pr.multiProcessorCount;
     if (cfg) ctx->cfg = *cfg;
-    if (const char* d = std::getenv("KDBX_DECODER")) ctx->decoder_deltas = std::strcmp(d, "deltas") == 0;
     if ((e = cudaSetDevice(dev)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev_up_begin)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_up_hdr)) != cudaSuccess ||

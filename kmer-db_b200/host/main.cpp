@@ -180,59 +180,69 @@ void run_all2all_sparse(const Params& p) {
 // as all2all-sp would write it for one database holding all of them.  Grid row i = the samples of part i; its cells are
 // db2db_sp(part i, part j) for j < i and all2all_sp(part i) on the diagonal; a row of the table concatenates the row's
 // cells with the column ids shifted by the samples of the parts before (SparseMatrix::saveRowSparse(row, out, idx_shift),
-// src/array.h:625-637).  One grid row needs its own part and one column part at a time on the device.  With -gpus n the
-// grid rows are dealt to n devices (they are independent) and written in order.
+// src/array.h:625-637).  The reference keeps two parts in host memory and reads every column part again for every grid
+// row; here a part is read and staged on the device ONCE and stays there while the parts fit the HBM budget (the parts
+// with the lowest numbers first: part j is a column of every row after it), so the grid costs O(parts) loads instead of
+// O(parts^2).  With -gpus n the grid rows are dealt to n devices (they are independent) and written in order.
 namespace {
 struct PartsGrid {
     std::vector<std::string> files;
     std::vector<uint32_t> part_samples, first_sample;   // per part
+    std::vector<uint64_t> resident_bytes;                // per part: estimate of what it occupies on the device
     Trie all;                                            // header + names + k-mer counts of every sample, in order
 };
 
+// Staged parts of one device: handle per part (-1 = not on the device).
+struct PartsOnDevice {
+    const PartsGrid& g;
+    const SimilarityCalculator& calc;
+    std::vector<int> handle;
+    uint64_t budget, used = 0;
+    PartsOnDevice(const PartsGrid& grid, const SimilarityCalculator& c, uint64_t budget_bytes)
+        : g(grid), calc(c), handle(grid.files.size(), -1), budget(budget_bytes) {}
+    // stages part i if it is not there; `keep`: it may stay (it fits the budget)
+    int acquire(uint32_t i, bool& keep) {
+        keep = true;
+        if (handle[i] >= 0) return handle[i];
+        std::cerr << "Deserializing database " << i + 1 << " (" << g.files[i] << ")" << std::endl;
+        Trie db;
+        read_db(g.files[i], db, true);
+        const int h = calc.stage_part(db);
+        if (used + g.resident_bytes[i] <= budget) { handle[i] = h; used += g.resident_bytes[i]; }
+        else keep = false;
+        return h;
+    }
+};
+
 // the text of grid row i_row (all lines of its samples); returns the number of pairs written
-uint64_t parts_grid_row(const Params& p, const PartsGrid& g, const SimilarityCalculator& calc, uint32_t i_row, bool row_is_staged_as_column,
-                        Trie& db_row, std::string& text, kdbx_stats& total) {
-    // the previous grid row's part (the first column part of this row) may still be on the device: keep it as the column
-    // database and stage this row's part next to it
-    if (row_is_staged_as_column) calc.swap_databases();
-    std::cerr << "Deserializing database " << i_row + 1 << " (" << g.files[i_row] << ")" << std::endl;
-    read_db(g.files[i_row], db_row, true);
-    calc.load_database(db_row);
-    const uint32_t rows = db_row.num_samples();
+uint64_t parts_grid_row(const Params& p, const PartsGrid& g, const SimilarityCalculator& calc, PartsOnDevice& dev, uint32_t i_row,
+                        std::string& text, kdbx_stats& total) {
+    bool keep_row = true;
+    const int row = dev.acquire(i_row, keep_row);
+    const uint32_t rows = g.part_samples[i_row];
     std::vector<std::unique_ptr<SparseMatrix<uint32_t>>> cells(i_row + 1);
-    std::vector<std::vector<uint32_t>> col_counts(i_row + 1);
     auto add_stats = [&](const kdbx_stats& st) {
         total.updates += st.updates; total.probes += st.probes; total.hits += st.hits; total.ms_probe += st.ms_probe;
         total.ms_scatter += st.ms_scatter; total.ms_compact += st.ms_compact; total.ms_total += st.ms_total;
         total.ms_prepare += st.ms_prepare; total.ms_download += st.ms_download; total.kernel_launches += st.kernel_launches;
     };
-    auto cell = [&](uint32_t i_col, const Trie& db_col) {
+    for (uint32_t i_col = 0; i_col < i_row; ++i_col) {
+        bool keep_col = true;
+        const int col = dev.acquire(i_col, keep_col);
         std::cerr << "Processing cell (" << i_row + 1 << "," << i_col + 1 << ")" << std::endl;
         cells[i_col] = std::make_unique<SparseMatrix<uint32_t>>();
-        calc.db2db_sp(db_row, db_col, *cells[i_col], p.filters);
-        col_counts[i_col].assign(db_col.sample_kmers.begin(), db_col.sample_kmers.end());
+        calc.db2db_sp(row, col, *cells[i_col], p.filters);
         add_stats(calc.last_stats());
-    };
-    // order of the reference: (i, i-1) first — its column part is the one already in memory — then (i, 0 .. i-2)
-    for (uint32_t step = 0; step < i_row; ++step) {
-        const uint32_t i_col = step == 0 ? i_row - 1 : step - 1;
-        Trie db_col(true);
-        if (step == 0 && row_is_staged_as_column) {
-            read_db(g.files[i_col], db_col, false);   // (its k-mer counts; patterns and tables are on the device)
-        } else {
-            read_db(g.files[i_col], db_col, true);
-            calc.load_column_database(db_col);
-        }
-        cell(i_col, db_col);
+        if (!keep_col) calc.drop_part(col);
     }
     std::cerr << "Processing cell (" << i_row + 1 << "," << i_row + 1 << ")" << std::endl;
     cells[i_row] = std::make_unique<SparseMatrix<uint32_t>>();
-    calc.all2all_sp(db_row, *cells[i_row], p.filters, true);
-    col_counts[i_row].assign(db_row.sample_kmers.begin(), db_row.sample_kmers.end());
+    calc.all2all_sp_part(row, *cells[i_row], p.filters);
     add_stats(calc.last_stats());
+    if (!keep_row) calc.drop_part(row);
 
     const OutputFilters* filters = p.filters.trivial() ? nullptr : &p.filters;   // (again: the bounds the device left to the host)
-    const int k = (int)db_row.hdr.kmer_length;
+    const int k = (int)g.all.hdr.kmer_length;
     uint64_t saved = 0;
     text.clear();
     std::string line;
@@ -252,8 +262,9 @@ uint64_t parts_grid_row(const Params& p, const PartsGrid& g, const SimilarityCal
             const uint32_t* vals = m.vals(r);
             const size_t cnt = m.getNoInRow(r);
             for (size_t i = 0; i < cnt; ++i) {
-                if (filters && !filters->pass(vals[i], (uint32_t)db_row.sample_kmers[r], col_counts[c][cols[i]], k)) continue;
-                q = put_u64(q, (uint64_t)g.first_sample[c] + cols[i] + 1); *q++ = ':'; q = put_u64(q, vals[i]); *q++ = ',';
+                const uint32_t sc = g.first_sample[c] + cols[i];
+                if (filters && !filters->pass(vals[i], (uint32_t)g.all.sample_kmers[s], (uint32_t)g.all.sample_kmers[sc], k)) continue;
+                q = put_u64(q, (uint64_t)sc + 1); *q++ = ':'; q = put_u64(q, vals[i]); *q++ = ',';
                 ++saved;
             }
         }
@@ -261,6 +272,11 @@ uint64_t parts_grid_row(const Params& p, const PartsGrid& g, const SimilarityCal
         text.append(line.data(), (size_t)(q - line.data()));
     }
     return saved;
+}
+
+uint64_t file_bytes(const std::string& path) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    return f ? (uint64_t)f.tellg() : 0;
 }
 }  // namespace
 
@@ -287,6 +303,9 @@ void run_all2all_parts(const Params& p) {
         }
         g.first_sample.push_back((uint32_t)g.all.sample_names.size());
         g.part_samples.push_back(t.num_samples());
+        // on the device: the raw tables (allocated slots, up to 2.5x the filled ones the file holds), the trie, its decoded
+        // local lists and the working buffers of the cells — a generous multiple of the file
+        g.resident_bytes.push_back(file_bytes(g.files[i]) * 8 + ((uint64_t)64 << 20));
         g.all.sample_names.insert(g.all.sample_names.end(), t.sample_names.begin(), t.sample_names.end());
         g.all.sample_kmers.insert(g.all.sample_kmers.end(), t.sample_kmers.begin(), t.sample_kmers.end());
     }
@@ -297,20 +316,21 @@ void run_all2all_parts(const Params& p) {
 
     const int num_gpus = std::max(1, std::min<int>(p.num_gpus, (int)std::max<uint32_t>(1, parts)));
     if (num_gpus > kdbx_device_count()) { std::fclose(f); throw std::runtime_error("-gpus " + std::to_string(num_gpus) + " requested but only " + std::to_string(kdbx_device_count()) + " B200 device(s) are visible"); }
+    const uint64_t budget = (uint64_t)(p.cache_buffer_mb > 8 ? p.cache_buffer_mb : 100 * 1024) << 20;   // -buffer <mb> bounds the resident parts (default 100 GB)
     uint64_t saved = 0;
     kdbx_stats total{};
     if (num_gpus == 1) {
         SimilarityCalculator calc(p.num_threads, (size_t)p.cache_buffer_mb, p.gpu);
+        PartsOnDevice dev(g, calc, budget);
         std::string text;
         for (uint32_t i = 0; i < parts; ++i) {
-            Trie db_row(true);
-            saved += parts_grid_row(p, g, calc, i, i > 0, db_row, text, total);
+            saved += parts_grid_row(p, g, calc, dev, i, text, total);
             std::cerr << "Saving output matrix..." << std::endl;
             std::fwrite(text.data(), 1, text.size(), f);
             std::cerr << " OK (no. currently saved pairs: " << saved << ")" << std::endl;
         }
     } else {
-        // grid rows dealt round-robin, heaviest (last) rows first on every device; the writer takes them in order
+        // grid rows dealt round-robin; every device keeps its own staged parts; the writer takes the rows in order
         std::vector<std::string> texts(parts);
         std::vector<int> ready(parts, 0);
         std::vector<std::string> errors((size_t)num_gpus);
@@ -324,10 +344,10 @@ void run_all2all_parts(const Params& p) {
             workers.emplace_back([&, d] {
                 try {
                     SimilarityCalculator calc(p.num_threads, (size_t)p.cache_buffer_mb, base + d);
+                    PartsOnDevice dev(g, calc, budget);
                     for (uint32_t i = (uint32_t)d; i < parts; i += (uint32_t)num_gpus) {
-                        Trie db_row(true);
                         std::string text;
-                        saved_g[(size_t)d] += parts_grid_row(p, g, calc, i, false, db_row, text, stats_g[(size_t)d]);
+                        saved_g[(size_t)d] += parts_grid_row(p, g, calc, dev, i, text, stats_g[(size_t)d]);
                         std::lock_guard<std::mutex> lk(mu);
                         texts[i] = std::move(text); ready[i] = 1;
                         cv.notify_all();

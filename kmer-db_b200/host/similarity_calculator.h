@@ -74,7 +74,7 @@ public:
         cfg.device = device;
         if (kdbx_open(&cfg, &ctx_) != KDBX_OK) throw std::runtime_error(kdbx_last_error(nullptr));
     }
-    ~SimilarityCalculator() { kdbx_close(ctx_); if (ctx_cols_) kdbx_close(ctx_cols_); }
+    ~SimilarityCalculator() { kdbx_close(ctx_); for (Part& p : parts_) if (p.ctx) kdbx_close(p.ctx); }
     SimilarityCalculator(const SimilarityCalculator&) = delete;
     SimilarityCalculator& operator=(const SimilarityCalculator&) = delete;
 
@@ -167,12 +167,9 @@ public:
     // matrix as sparse rows.  `filters` are the -min/-max bounds; the ones whose arithmetic is
     // exactly reproducible on the device run there (include/kdbx.h), the log-based ones are left
     // to the CSV emitter, which applies `filters` again on the host.
-    // staged = true: the database is already on the device (load_database), as for the diagonal cells of all2all-parts.
-    void all2all_sp(const Trie& db, SparseMatrix<uint32_t>& matrix, const OutputFilters& filters, bool staged = false) const {
-        if (!staged) {
-            const kdbx_trie_view v = db.view();
-            check(kdbx_load_patterns(ctx_, &v));
-        }
+    void all2all_sp(const Trie& db, SparseMatrix<uint32_t>& matrix, const OutputFilters& filters) const {
+        const kdbx_trie_view v = db.view();
+        check(kdbx_load_patterns(ctx_, &v));
         kdbx_filter f{};
         std::vector<uint32_t> counts(db.sample_kmers.begin(), db.sample_kmers.end());
         make_filter(filters, counts, f);
@@ -254,38 +251,45 @@ public:
         num_samples_ = db.num_samples();
     }
 
-    // ---- database against database: the cells below the diagonal of all2all-parts -----------------------------------
-    // The COLUMN database of db2db_sp lives on a second context of the same device (opened on first use).
-    void load_column_database(const Trie& db) const {
-        if (!ctx_cols_) {
-            kdbx_config cfg{};
-            cfg.device = device_;
-            if (kdbx_open(&cfg, &ctx_cols_) != KDBX_OK) throw std::runtime_error(kdbx_last_error(nullptr));
-        }
-        stage(ctx_cols_, db);
+    // ---- all2all-parts: partial databases staged side by side on this calculator's device -----------------------------
+    // The reference holds two parts in host memory at a time and reads every column part again for every grid row
+    // (src/console_all2all_parts.cpp:209-221); 180 GB of HBM hold many parts at once, so a part is staged ONCE — patterns
+    // and raw k-mer tables, on a context of its own — and stays until it is dropped.  Returns the part's handle.
+    int stage_part(const Trie& db) const {
+        kdbx_ctx* c = nullptr;
+        kdbx_config cfg{};
+        cfg.device = device_;
+        if (kdbx_open(&cfg, &c) != KDBX_OK) throw std::runtime_error(kdbx_last_error(nullptr));
+        try { stage(c, db); } catch (...) { kdbx_close(c); throw; }
+        Part staged;
+        staged.ctx = c;
+        staged.counts.assign(db.sample_kmers.begin(), db.sample_kmers.end());
+        for (size_t h = 0; h < parts_.size(); ++h) if (!parts_[h].ctx) { parts_[h] = std::move(staged); return (int)h; }
+        parts_.push_back(std::move(staged));
+        return (int)parts_.size() - 1;
     }
-    // The staged row database becomes the staged column database and vice versa: the row part of one grid row is the
-    // first column part of the next (the reference keeps it in memory for the same reason, `db_tmp`,
-    // src/console_all2all_parts.cpp:168-175,277-278).  load_database must follow before the next row call.
-    void swap_databases() const {
-        if (!ctx_cols_) {
-            kdbx_config cfg{};
-            cfg.device = device_;
-            if (kdbx_open(&cfg, &ctx_cols_) != KDBX_OK) throw std::runtime_error(kdbx_last_error(nullptr));
-        }
-        std::swap(ctx_, ctx_cols_);
+    void drop_part(int h) const {
+        if (h < 0 || (size_t)h >= parts_.size() || !parts_[(size_t)h].ctx) return;
+        kdbx_close(parts_[(size_t)h].ctx);
+        parts_[(size_t)h] = Part();
     }
-    // src/similarity_calculator.cpp:1225 + SparseMatrix::compact2: matrix row s1 (a sample of db_row) = ascending
-    // (s2, common k-mers) pairs over the samples s2 of db_col.  Both databases must be staged (load_database for the rows,
-    // load_column_database for the columns); db_row / db_col supply the k-mer counts of the output filters.
-    void db2db_sp(const Trie& db_row, const Trie& db_col, SparseMatrix<uint32_t>& matrix, const OutputFilters& filters) const {
-        if (!ctx_cols_) throw std::runtime_error("db2db_sp: no column database staged");
+    // src/similarity_calculator.cpp:1225 + SparseMatrix::compact2: matrix row s1 (a sample of the row part) = ascending
+    // (s2, common k-mers) pairs over the samples s2 of the column part.
+    void db2db_sp(int row_part, int col_part, SparseMatrix<uint32_t>& matrix, const OutputFilters& filters) const {
+        const Part& r = part(row_part);
+        const Part& c = part(col_part);
         kdbx_filter f{};
-        std::vector<uint32_t> rows(db_row.sample_kmers.begin(), db_row.sample_kmers.end());
-        std::vector<uint32_t> cols(db_col.sample_kmers.begin(), db_col.sample_kmers.end());
-        make_filter(filters, rows, f);
+        make_filter(filters, r.counts, f);
         kdbx_free_csr(matrix.raw());
-        check(kdbx_db2db_sparse(ctx_, ctx_cols_, &f, cols.data(), matrix.raw(), &stats_));
+        if (kdbx_db2db_sparse(r.ctx, c.ctx, &f, c.counts.data(), matrix.raw(), &stats_) != KDBX_OK) throw std::runtime_error(kdbx_last_error(r.ctx));
+    }
+    // the diagonal cell: all2all_sp of a staged part
+    void all2all_sp_part(int h, SparseMatrix<uint32_t>& matrix, const OutputFilters& filters) const {
+        const Part& r = part(h);
+        kdbx_filter f{};
+        make_filter(filters, r.counts, f);
+        kdbx_free_csr(matrix.raw());
+        if (kdbx_all2all_sparse(r.ctx, &f, matrix.raw(), &stats_) != KDBX_OK) throw std::runtime_error(kdbx_last_error(r.ctx));
     }
 
     // A batch of one2all<false> calls (src/similarity_calculator.cpp:810-925): query q owns
@@ -332,27 +336,34 @@ private:
         f.sample_kmers = counts.data();
     }
     void check(int rc) const { if (rc != KDBX_OK) throw std::runtime_error(kdbx_last_error(ctx_)); }
-    // patterns + k-mer tables of `db` to the device of context c
+    // patterns + k-mer tables of `db` to the device of context c.  (The tables go through one contiguous pageable copy:
+    // page-locking a buffer that is used once costs more than the slower copy.)
     static void stage(kdbx_ctx* c, const Trie& db) {
         if (db.tables.empty()) throw std::runtime_error("database was loaded without its k-mer tables");
         const kdbx_trie_view v = db.view();
         if (kdbx_load_patterns(c, &v) != KDBX_OK) throw std::runtime_error(kdbx_last_error(c));
         std::vector<uint64_t> off(db.tables.size() + 1, 0);
         for (size_t t = 0; t < db.tables.size(); ++t) off[t + 1] = off[t] + db.tables[t].slots.size();
-        Buf<uint64_t> slots;
-        slots.set_pinned(true);
-        slots.resize(off.back());
+        std::vector<uint64_t> slots(off.back());
         for (size_t t = 0; t < db.tables.size(); ++t)
             std::copy(db.tables[t].slots.begin(), db.tables[t].slots.end(), slots.data() + off[t]);
         kdbx_tables_view tv{};
         tv.num_tables = db.tables.size(); tv.slot_off = off.data(); tv.slots = slots.data();
         if (kdbx_load_hashtables(c, &tv) != KDBX_OK) throw std::runtime_error(kdbx_last_error(c));
     }
+    struct Part {
+        kdbx_ctx* ctx = nullptr;
+        std::vector<uint32_t> counts;   // "total-kmers" of the part's samples
+    };
+    const Part& part(int h) const {
+        if (h < 0 || (size_t)h >= parts_.size() || !parts_[(size_t)h].ctx) throw std::runtime_error("all2all-parts: no such staged part");
+        return parts_[(size_t)h];
+    }
     int num_threads_;
     size_t cache_buffer_mb_;
     int device_ = -1;
-    mutable kdbx_ctx* ctx_ = nullptr;
-    mutable kdbx_ctx* ctx_cols_ = nullptr;   // column database of db2db_sp
+    kdbx_ctx* ctx_ = nullptr;
+    mutable std::vector<Part> parts_;        // all2all-parts: the partial databases staged on this device
     mutable kdbx_stats stats_{};
     mutable uint32_t num_samples_ = 0;
 };

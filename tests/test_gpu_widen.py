@@ -326,6 +326,9 @@ def test_cli_all2all_parts(cli, ref_fixtures, tmp_path, cuts):
     r = cli(ref_fixtures, "all2all-parts", tmp_path / "db.list", tmp_path / "parts.csv")
     assert ou.read_bytes(tmp_path / "parts.csv") == ou.read_bytes(ref_fixtures / "test/virus/k18.sparse.csv")
     assert "No. saved pairs: 13530" in r.stderr
+    # -buffer <mb> bounds the parts kept on the device: with 9 MB none stays, every cell stages its column part again
+    cli(ref_fixtures, "all2all-parts", "-buffer", "9", tmp_path / "db.list", tmp_path / "parts.small.csv")
+    assert ou.read_bytes(tmp_path / "parts.small.csv") == ou.read_bytes(ref_fixtures / "test/virus/k18.sparse.csv")
     cli(ref_fixtures, "all2all-parts", "-min", "jaccard:0.985", "-max", "num-kmers:29700", "-min", "ani:0.9995", tmp_path / "db.list", tmp_path / "f.csv")
     assert ou.read_bytes(tmp_path / "f.csv") == ou.read_bytes(ou.ROOT / "tests" / "golden" / "virus.k18.parts.filtered.csv")
 
