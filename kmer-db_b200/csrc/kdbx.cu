@@ -167,8 +167,8 @@ __global__ void k_push_level(uint32_t count, const uint32_t* __restrict__ order,
 // stream holds the deltas in append order and only the LAST id is stored (src/pattern.cpp:99-109):
 // a thread walks its bits once, parking one token per delta >= 2 and per run of deltas of 1, then turns the tokens into
 // ids front to back (gamma_tokens.cuh; measured equal to parking one delta per id, 24.6 ms of prepare either way at
-// config 2 — runs average 3.4 ids there — and kept because the same code is compiled for the host and tested against the
-// oracle without a GPU).
+// config 2 — runs average 3.4 ids there — and kept because the same code is compiled for the host and unit-tested
+// without a GPU, tests/test_host.py).
 // The local lists of the 128 consecutive patterns of a block are contiguous in d_loc, so they are
 // staged in shared memory and written out with coalesced stores (a thread writing its own list
 // straight to HBM costs one 32-byte sector per 4-byte id); blocks whose lists do not fit the stage
