@@ -22,9 +22,13 @@ U = sum_p l_p(2 n_p - l_p - 1)/2 = the number of `row[col] += w` executions of t
            the conflict-free red.shared.add.u32 peak of the microbenchmark (profiles/r01_microbench_atomics.txt).
   cpu_baseline  the reference binary (oracle/_ref/kmer-db all2all -t <all cores>) once on the SAME .db, its CSV kept
            and compared byte for byte with the CSV written from the GPU result (parity_checked).
-  --impl reference   K timed runs of the reference binary on the same .db (N = 1).  At N > 1 the weak-scaling database
-           is N times larger and the reference cannot finish 25 runs of it within the driver's limit: rank 0 then times
-           the configs[1] database (1/N of the workload, said in cpu_baseline.sample); updates/s is a rate.
+  --impl reference   the unmodified reference binary on the host cores.  The whole configs[1] database runs once in every
+           invocation (full_config_run; its CSV is kept for the GPU arm's cmp).  If warmup + steps such runs fit
+           --ref-budget-s (420 s; the driver gives a run of this script 870 s and asks for 25 runs of 30 s) they all are
+           runs of the whole database (same_config: true); otherwise every step is a bounded sample — the same generator,
+           genomes and clusters at 1/5 (1/10 ...) of the genome length — and the line carries both rates and their quotient
+           (steps_rate_over_full_config_rate).  At N > 1 the weak-scaling database is N times larger: rank 0 then times the
+           configs[1] database (1/N of the workload, said in cpu_baseline.sample); updates/s is a rate.
 
 N > 1 (torchrun, one rank per GPU): the database is SHARDED.  kdbxh_partitioner cuts the trie into N sub-tries (pieces
 of its depth-first preorder balanced on a cost model, plus the ancestor chain of each piece with num_kmers = 0; the
@@ -39,6 +43,7 @@ In both, rank 0 generates and partitions once (host, untimed: it is the layout o
 `build`), writes the parts next to the database and every rank reads its own.
 """
 import argparse
+import datetime
 import json
 import os
 import re
@@ -85,6 +90,8 @@ def parse_args():
     ap.add_argument("--check-reference", action="store_true",
                     help="N>1: run the reference binary on the whole (N times larger) database once for the CSV cmp, however long it takes")
     ap.add_argument("--keep-cache", action="store_true", help="N>1: keep the weak-scaling database and the parts under --cache-dir")
+    ap.add_argument("--ref-budget-s", type=float, default=float(os.environ.get("KDBX_REF_BUDGET_S", "420")),
+                    help="--impl reference: wall-clock budget of the whole invocation; steps become bounded samples when runs of the whole database do not fit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cache-dir", default=os.environ.get("KDBX_CACHE", "/tmp/kdbx_cache"))
@@ -99,14 +106,14 @@ def db_shape(a, world):
     return a.samples, a.clusters, 0.0
 
 
-def db_path(a, samples, clusters, skew):
+def db_path(a, samples, clusters, skew, genome_kmers=None):
     sk = f"_sk{skew:g}" if skew else ""
-    return Path(a.cache_dir) / f"synth_n{samples}_c{clusters}_L{a.genome_kmers}_k{a.k}_mu{a.mu}_s{a.seed}{sk}.db"
+    return Path(a.cache_dir) / f"synth_n{samples}_c{clusters}_L{genome_kmers or a.genome_kmers}_k{a.k}_mu{a.mu}_s{a.seed}{sk}.db"
 
 
-def ensure_db(a, samples, clusters, skew):
+def ensure_db(a, samples, clusters, skew, genome_kmers=None):
     """Path and totals of the database; generated by bin/kdbx-synth (a host program: no CUDA) when missing."""
-    path = db_path(a, samples, clusters, skew)
+    path = db_path(a, samples, clusters, skew, genome_kmers)
     meta = Path(str(path) + ".json")
     if not (path.exists() and meta.exists()):
         exe = PKG / "bin" / "kdbx-synth"
@@ -114,23 +121,24 @@ def ensure_db(a, samples, clusters, skew):
             raise RuntimeError(f"{exe} missing: run `make -C {PKG}` (or __graft_entry__.build())")
         path.parent.mkdir(parents=True, exist_ok=True)
         t0 = time.time()
-        subprocess.run([str(exe), "-o", str(path), "-n", str(samples), "-c", str(clusters), "-L", str(a.genome_kmers), "-k", str(a.k),
+        subprocess.run([str(exe), "-o", str(path), "-n", str(samples), "-c", str(clusters), "-L", str(genome_kmers or a.genome_kmers), "-k", str(a.k),
                         "-mu", repr(a.mu), "-seed", str(a.seed), "-skew", repr(skew)], check=True, stdout=subprocess.DEVNULL,
                        stderr=subprocess.DEVNULL)
         print(f"[bench] generated {path.name} in {time.time() - t0:.1f} s", file=sys.stderr)
     return path, json.loads(meta.read_text())
 
 
-def workload_name(a, samples, clusters, skew):
-    s = (f"{samples} synthetic {a.genome_kmers / 1e6:g} Mbp genomes, {clusters} clusters"
+def workload_name(a, samples, clusters, skew, genome_kmers=None):
+    L = genome_kmers or a.genome_kmers
+    s = (f"{samples} synthetic {L / 1e6:g} Mbp genomes, {clusters} clusters"
          + (f" of unequal sizes (spread {skew:g})" if skew else "") + f", mu={a.mu}, k={a.k}, f=1.0, dense all2all")
-    return s + (" (BASELINE.json configs[1])" if (samples, clusters) == (1000, 4) and a.genome_kmers == 5_000_000 else
+    return s + (" (BASELINE.json configs[1])" if (samples, clusters) == (1000, 4) and L == 5_000_000 else
                 " (BASELINE.json configs[2] shape)" if samples > 1000 else "")
 
 
-def common_config(a, meta, samples, clusters, skew):
+def common_config(a, meta, samples, clusters, skew, genome_kmers=None):
     """The part of `config` that names the workload: identical in both arms."""
-    return {"workload": workload_name(a, samples, clusters, skew), "database": db_path(a, samples, clusters, skew).name,
+    return {"workload": workload_name(a, samples, clusters, skew, genome_kmers), "database": db_path(a, samples, clusters, skew, genome_kmers).name,
             "num_samples": int(meta["num_samples"]), "num_patterns": int(meta["num_patterns"]),
             "updates_per_step": int(meta["updates"]), "sum_n": int(meta["sum_n"]), "sum_l": int(meta["sum_l"])}
 
@@ -259,38 +267,85 @@ def ncu_capture(kernel):
     return {}
 
 
+REF_SAMPLE_FRACTIONS = (5, 10, 20, 50, 100)   # the bounded sample of a step: the same database shape at 1/5 ... 1/100 of the genome length
+
+
 def reference_arm(a, rank, world):
-    """The unmodified reference on the host cores.  Loads none of this repository's libraries."""
+    """The unmodified reference on the host cores.  Loads none of this repository's libraries.
+
+    The whole database runs ONCE in every invocation (full_config_run; its CSV is what the GPU arm compares with).  When
+    warmup + steps runs of the whole database fit --ref-budget-s they all are such runs (same_config: true).  Otherwise —
+    the driver's 25 runs of configs[1] take a quarter of an hour on 16 cores and its limit per run of this script is
+    870 s — every step is a bounded sample: the same generator, the same number of genomes and clusters (so the same row
+    lengths and list shapes) at a fraction of the genome length, i.e. a fraction of the patterns; the line then carries
+    both rates (the steps' and the whole database's) and their quotient."""
     if rank != 0:
         return
+    t_begin = time.perf_counter()
     cores = os.cpu_count() or 1
     samples, clusters, skew = db_shape(a, world)
-    sample_note = None
+    scale_note = ""
     if world > 1 and a.scaling == "weak":
-        # the N-GPU database is N times configs[1]; the bounded sample is configs[1] itself
-        path, meta = ensure_db(a, a.samples, a.clusters, 0.0)
-        sample_note = (f"the {workload_name(a, a.samples, a.clusters, 0.0)} database = about 1/{world} of the {world}-GPU workload "
-                       f"({samples} genomes, {clusters} clusters): {a.steps + a.warmup} runs of the full one do not fit the driver's limit")
+        # the N-GPU database is N times configs[1]; the reference runs configs[1] itself
+        base = (a.samples, a.clusters, 0.0)
+        path, meta = ensure_db(a, *base)
+        scale_note = (f"the {workload_name(a, *base)} database = about 1/{world} of the {world}-GPU workload "
+                      f"({samples} genomes, {clusters} clusters): runs of the full one do not fit the driver's limit; ")
         cfg = {"workload": workload_name(a, samples, clusters, skew), "database": db_path(a, samples, clusters, skew).name,
-               "num_samples": samples, "sample_of_workload": common_config(a, meta, a.samples, a.clusters, 0.0)}
+               "num_samples": samples, "sample_of_workload": common_config(a, meta, *base)}
     else:
-        path, meta = ensure_db(a, samples, clusters, skew)
-        cfg = common_config(a, meta, samples, clusters, skew)
-    U = int(meta["updates"])
-    for _ in range(a.warmup):
-        run_reference_binary(path, cores)
-    secs = [run_reference_binary(path, cores) for _ in range(a.steps)]
+        base = (samples, clusters, skew)
+        path, meta = ensure_db(a, *base)
+        cfg = common_config(a, meta, *base)
+    t_gen = time.perf_counter() - t_begin
+    U_full = int(meta["updates"])
+    w0 = time.perf_counter()
+    secs_full = run_reference_binary(path, cores)          # keeps <db>.ref.csv
+    wall_full = time.perf_counter() - w0
+    full_run = {"value": U_full / secs_full, "unit": "updates/s", "seconds": round(secs_full, 3), "wall_seconds": round(wall_full, 3),
+                "updates": U_full, "database": path.name}
+    more_full = max(0, a.warmup - 1) + a.steps             # (the run above is the first warm-up)
+    elapsed = time.perf_counter() - t_begin
+    same_config = elapsed + more_full * wall_full * 1.05 <= a.ref_budget_s
+    if same_config:
+        for _ in range(max(0, a.warmup - 1)):
+            run_reference_binary(path, cores)
+        secs = [run_reference_binary(path, cores) for _ in range(a.steps)]
+        U = U_full
+        sample = scale_note + f"the whole workload: {meta['num_samples']} genomes, U={U:.4g} per step (same .db file as the GPU arm)"
+        step_db = path.name
+    else:
+        gen_full = max(t_gen, 2.0 * wall_full)             # (the database may have come from the cache)
+        den = REF_SAMPLE_FRACTIONS[-1]
+        for d in REF_SAMPLE_FRACTIONS:
+            if elapsed + gen_full / d + (a.warmup + a.steps) * wall_full * 1.3 / d <= a.ref_budget_s:
+                den = d
+                break
+        L = max(min(1000, a.genome_kmers), a.genome_kmers // den)
+        spath, smeta = ensure_db(a, *base, genome_kmers=L)
+        for _ in range(a.warmup):
+            run_reference_binary(spath, cores, keep_csv=False)
+        secs = [run_reference_binary(spath, cores, keep_csv=False) for _ in range(a.steps)]
+        U = int(smeta["updates"])
+        cfg["step_sample"] = dict(common_config(a, smeta, *base, genome_kmers=L), genome_length_fraction=f"1/{a.genome_kmers // L}" if a.genome_kmers % L == 0 else L / a.genome_kmers)
+        sample = (scale_note + f"every step = the same generator and shape at {L / 1e6:g} Mbp per genome instead of {a.genome_kmers / 1e6:g} "
+                  f"({smeta['num_samples']} genomes, {base[1]} clusters, U={U:.4g} per step): {a.warmup + a.steps} runs of the whole database "
+                  f"({wall_full:.1f} s each) do not fit the arm's budget of {a.ref_budget_s:g} s; the whole database ran once in this "
+                  f"invocation: {secs_full:.2f} s = {U_full / secs_full:.4g} updates/s (full_config_run)")
+        step_db = spath.name
     total = sum(secs)
     v = U * a.steps / total
-    sample = sample_note or f"the whole workload: {meta['num_samples']} genomes, U={U:.4g} per step (same .db file as the GPU arm)"
     cfg["l2_policy"] = "CPU arm: every step is a fresh process reading the .db from the page cache"
     print(json.dumps({
         "impl": "reference", "metric": "k-mer-pair updates/sec on all2all", "value": v, "unit": "updates/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps,
         "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": cfg,
+        "config": cfg, "same_config": bool(same_config), "full_config_run": full_run,
+        "steps_rate_over_full_config_rate": v / full_run["value"],
         "arm": {"binary": "oracle/_ref/kmer-db 2.3.1 all2all (unmodified reference, built by oracle/build_ref.sh)", "threads": cores,
-                "seconds_per_step": [round(x, 3) for x in secs], "csv_kept": str(ref_csv_path(path).name)},
+                "step_database": step_db, "updates_per_step": U, "seconds_per_step": [round(x, 3) for x in secs],
+                "csv_kept": str(ref_csv_path(path).name), "budget_s": a.ref_budget_s,
+                "wall_s": round(time.perf_counter() - t_begin, 1)},
         "cpu_baseline": {"value": v, "unit": "updates/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -333,7 +388,8 @@ def main():
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            # (rank 0 generates and cuts the database while the others wait at a barrier: minutes on a box with few cores)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(minutes=40))
             warm = torch.zeros(1, device="cuda")
             dist.all_reduce(warm)
             torch.cuda.synchronize()

@@ -33,7 +33,8 @@ def test_reference_arm_prints_one_contract_line(libs, ref_bin, tmp_path):
     # the arm times the WHOLE workload (same .db file as the GPU arm), keeps its CSV for the GPU arm's cmp, and loads
     # none of this repository's libraries: the database comes from the stand-alone generator
     assert j["config"]["num_samples"] == 40 and j["config"]["updates_per_step"] > 0
-    assert "whole workload" in j["cpu_baseline"]["sample"]
+    assert "whole workload" in j["cpu_baseline"]["sample"] and j["same_config"] is True
+    assert j["full_config_run"]["updates"] == j["config"]["updates_per_step"] == j["arm"]["updates_per_step"]
     db = tmp_path / j["config"]["database"]
     assert db.exists() and (tmp_path / (j["config"]["database"] + ".ref.csv")).exists()
     src = (ou.ROOT / "bench.py").read_text()
@@ -44,6 +45,17 @@ def test_reference_arm_prints_one_contract_line(libs, ref_bin, tmp_path):
     j2 = json.loads(out.strip().splitlines()[-1])
     assert j2["config"]["num_samples"] == 80 and j2["config"]["sample_of_workload"]["num_samples"] == 40
     assert "1/2 of the 2-GPU workload" in j2["cpu_baseline"]["sample"]
+    # runs of the whole database that do not fit the arm's budget: the whole database still runs once (its CSV is kept for
+    # the GPU arm's cmp), the steps are the same shape at a fraction of the genome length, and the line carries both rates
+    out = _run(["--impl", "reference", "--gpus", "1", "--ref-budget-s", "0", *small])
+    j3 = json.loads(out.strip().splitlines()[-1])
+    assert j3["same_config"] is False and j3["steps"] == 2 and j3["warmup"] == 1 and len(j3["arm"]["seconds_per_step"]) == 2
+    assert j3["config"]["num_samples"] == 40 and j3["config"]["database"] == j["config"]["database"]
+    assert j3["config"]["step_sample"]["num_samples"] == 40 and j3["config"]["step_sample"]["database"] == j3["arm"]["step_database"] != j["config"]["database"]
+    assert 0 < j3["arm"]["updates_per_step"] == j3["config"]["step_sample"]["updates_per_step"] < j["config"]["updates_per_step"]
+    assert j3["full_config_run"]["updates"] == j["config"]["updates_per_step"] and j3["full_config_run"]["value"] > 0
+    assert j3["cpu_baseline"]["value"] == j3["value"] == j3["e2e"]["value"] and "full_config_run" in j3["cpu_baseline"]["sample"]
+    assert abs(j3["steps_rate_over_full_config_rate"] - j3["value"] / j3["full_config_run"]["value"]) < 1e-9
     # under torchrun only rank 0 works and prints; the other ranks exit 0 without output
     out = _run(["--impl", "reference", "--gpus", "2", *small], env={"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
     assert out.strip() == ""
