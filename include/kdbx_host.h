@@ -125,6 +125,17 @@ const uint64_t* kdbxh_samples_kmers(const kdbxh_samples* s, uint32_t i, uint64_t
 /* tri: packed lower-triangular uint32 matrix, N(N-1)/2 cells (src/array.h:140). */
 int kdbxh_write_all2all_csv(const kdbxh_trie* t, const uint32_t* tri, const char* path, int sparse);
 
+/* The all2all-sp / all2all-parts table from sparse rows (src/console_all2all_sparse.cpp:50-98, SparseMatrix::saveRowSparse
+ * src/array.h:625-637), with the reference's output options evaluated on the host:
+ *   filters      the command-line words of -min / -max, e.g. "-min jaccard:0.9 -max 100" (NULL = none; src/params.cpp:418-455)
+ *   sample_rows  "<criterion>:<count>" of -sample-rows (NULL = off; src/sampler.h, src/array.h:451-541): every sample keeps
+ *                its <count> best neighbours of the symmetric matrix
+ * The matrix comes as a grid of cells: rows of cells[i] are the samples row_shifts[i] + r of `t`, its columns the samples
+ * col_shifts[i] + c (one cell with both shifts 0 = all2all-sp; the cells of all2all-parts otherwise, which needs
+ * sample_rows: without it that mode writes its rows as they are computed).  saved (optional) = pairs written. */
+int kdbxh_write_sparse_csv(const kdbxh_trie* t, const kdbx_csr* cells, const uint32_t* row_shifts, const uint32_t* col_shifts,
+                           uint32_t num_cells, const char* filters, const char* sample_rows, const char* path, uint64_t* saved);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,8 @@ struct Params {
     bool host_csv = false;     // all2all -host-csv (ours): format the dense table on the host instead of on the device
     Alphabet alphabet = Alphabet::make(kNt);
     OutputFilters filters;
+    int sampling_size = 0;               // -sample-rows [criterion:]count of all2all-sp / all2all-parts (0 = off)
+    metric_fn sampling_criterion = nullptr;
     std::string metric_name;
     std::vector<std::string> files;
 };

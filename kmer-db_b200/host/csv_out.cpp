@@ -4,6 +4,7 @@
 // is plain decimal like NumericConversions::Int2PChar (src/conversion.h:99-165) — written
 // independently (two-digit table), rows formatted in parallel and written in order.
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <thread>
 
@@ -151,6 +152,79 @@ uint64_t write_sparse_csv(const std::string& path, const Trie& t, const kdbx_csr
         *p++ = '\n';
         std::fwrite(row.data(), 1, (size_t)(p - row.data()), f);
     }
+    if (std::fclose(f) != 0) throw std::runtime_error("Cannot write output file " + path);
+    return saved;
+}
+
+// ---- -sample-rows (csv_out.h) ---------------------------------------------------------------------------------------
+RowSampler::RowSampler(size_t num_samples, uint32_t max_items, metric_fn criterion)
+    : rows_(num_samples), max_items_(max_items), criterion_(criterion) {
+    if (max_items == 0 || !criterion) throw std::runtime_error("Sampling parameters error - a criterion and a positive count are needed");
+}
+
+// Bounded like the reference's (src/sampler.h:98-122): a row holds at most max_items; once full it is a heap whose top
+// is the worst kept item, and a new item replaces the top iff it is better.
+void RowSampler::add(size_t row, uint32_t item, uint32_t value, double score) {
+    std::vector<Item>& v = rows_[row];
+    const Item it{item, value, score};
+    if (v.size() < max_items_) {
+        v.push_back(it);
+        if (v.size() == max_items_) std::make_heap(v.begin(), v.end(), heap_order);
+        return;
+    }
+    if (!heap_order(it, v.front())) return;   // not better than the worst kept
+    std::pop_heap(v.begin(), v.end(), heap_order);
+    v.back() = it;
+    std::push_heap(v.begin(), v.end(), heap_order);
+}
+
+void RowSampler::add_cell(const kdbx_csr& m, const OutputFilters* filters, const uint64_t* row_kmers, const uint64_t* col_kmers,
+                          uint32_t row_shift, uint32_t col_shift, int k) {
+    if (filters && filters->trivial()) filters = nullptr;
+    if (!m.row_ptr) return;
+    for (uint32_t r = 0; r < m.num_rows; ++r) {
+        const uint32_t rc = (uint32_t)row_kmers[r];
+        for (uint64_t i = m.row_ptr[r]; i < m.row_ptr[r + 1]; ++i) {
+            const uint32_t c = m.col[i], v = m.val[i], cc = (uint32_t)col_kmers[c];
+            if (v == 0 || (filters && !filters->pass(v, rc, cc, k))) continue;
+            const double score = criterion_(v, rc, cc, k);
+            const size_t a = (size_t)row_shift + r, b = (size_t)col_shift + c;
+            if (a >= rows_.size() || b >= rows_.size()) throw std::runtime_error("sampler: sample id out of range");
+            add(a, (uint32_t)b, v, score);
+            add(b, (uint32_t)a, v, score);
+        }
+    }
+}
+
+uint64_t RowSampler::write_rows(FILE* f, const std::vector<std::string>& names, const std::vector<uint64_t>& kmers) {
+    uint64_t saved = 0;
+    std::string row;
+    for (size_t s = 0; s < rows_.size(); ++s) {
+        std::vector<Item>& v = rows_[s];
+        std::sort(v.begin(), v.end(), [](const Item& x, const Item& y) { return x.item < y.item; });
+        row.resize(names[s].size() + 32 + v.size() * 22);
+        char* p = row.data();
+        std::memcpy(p, names[s].data(), names[s].size()); p += names[s].size();
+        *p++ = ',';
+        p = put_u64(p, kmers[s]);
+        *p++ = ',';
+        for (const Item& x : v) { p = put_u64(p, (uint64_t)x.item + 1); *p++ = ':'; p = put_u64(p, x.value); *p++ = ','; }
+        *p++ = '\n';
+        std::fwrite(row.data(), 1, (size_t)(p - row.data()), f);
+        saved += v.size();
+    }
+    return saved;
+}
+
+uint64_t write_sparse_csv_sampled(const std::string& path, const Trie& t, const kdbx_csr& m, const OutputFilters* filters,
+                                  uint32_t max_items, metric_fn criterion) {
+    RowSampler sampler(t.num_samples(), max_items, criterion);
+    sampler.add_cell(m, filters, t.sample_kmers.data(), t.sample_kmers.data(), 0, 0, (int)t.hdr.kmer_length);
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("Cannot open output file " + path);
+    const std::string head = table_header(t);
+    std::fwrite(head.data(), 1, head.size(), f);
+    const uint64_t saved = sampler.write_rows(f, t.sample_names, t.sample_kmers);
     if (std::fclose(f) != 0) throw std::runtime_error("Cannot write output file " + path);
     return saved;
 }

@@ -1,6 +1,7 @@
 // extern "C" surface of libkdbx_host.so (include/kdbx_host.h): thin wrappers that translate
 // exceptions into error codes.
 #include <cstring>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <vector>
@@ -269,6 +270,51 @@ uint64_t kdbxh_sample_kmers(const kdbxh_trie* t, uint32_t i) {
 int kdbxh_write_all2all_csv(const kdbxh_trie* t, const uint32_t* tri, const char* path, int sparse) {
     if (!t || !path || (!tri && t->t.num_samples() > 1)) { g_err = "null argument"; return -1; }
     return guarded([&] { kdbx::write_all2all_csv(path, t->t, tri, sparse != 0); });
+}
+
+int kdbxh_write_sparse_csv(const kdbxh_trie* t, const kdbx_csr* cells, const uint32_t* row_shifts, const uint32_t* col_shifts,
+                           uint32_t num_cells, const char* filters, const char* sample_rows, const char* path, uint64_t* saved) {
+    if (!t || !path || (num_cells && !cells)) { g_err = "null argument"; return -1; }
+    return guarded([&] {
+        kdbx::OutputFilters f;
+        if (filters) {
+            std::istringstream words(filters);
+            std::string w, v;
+            while (words >> w) {
+                if ((w != "-min" && w != "-max") || !(words >> v)) throw std::runtime_error("filters: expected -min <v> / -max <v>");
+                f.add(w == "-min" ? 0 : 1, v, "num-kmers");
+            }
+        }
+        const kdbx::Trie& db = t->t;
+        const uint32_t N = db.num_samples();
+        for (uint32_t i = 0; i < num_cells; ++i) {
+            const uint32_t rs = row_shifts ? row_shifts[i] : 0, cs = col_shifts ? col_shifts[i] : 0;
+            if ((uint64_t)rs + cells[i].num_rows > N || cs > N) throw std::runtime_error("cell outside the sample table");
+        }
+        uint64_t n = 0;
+        if (!sample_rows) {
+            if (num_cells != 1 || (row_shifts && row_shifts[0]) || (col_shifts && col_shifts[0]))
+                throw std::runtime_error("a grid of cells needs sample_rows");
+            n = kdbx::write_sparse_csv(path, db, cells[0], &f);
+        } else {
+            kdbx::metric_fn crit = nullptr;
+            int count = 0;
+            kdbx::parse_sample_rows(sample_rows, crit, count);
+            if (count <= 0 || !crit) throw std::runtime_error("Sampling parameters error - a criterion and a positive count are needed");
+            kdbx::RowSampler sampler(N, (uint32_t)count, crit);
+            for (uint32_t i = 0; i < num_cells; ++i) {
+                const uint32_t rs = row_shifts ? row_shifts[i] : 0, cs = col_shifts ? col_shifts[i] : 0;
+                sampler.add_cell(cells[i], &f, db.sample_kmers.data() + rs, db.sample_kmers.data() + cs, rs, cs, (int)db.hdr.kmer_length);
+            }
+            FILE* out = std::fopen(path, "wb");
+            if (!out) throw std::runtime_error(std::string("Cannot open output file ") + path);
+            const std::string head = kdbx::table_header(db);
+            std::fwrite(head.data(), 1, head.size(), out);
+            n = sampler.write_rows(out, db.sample_names, db.sample_kmers);
+            if (std::fclose(out) != 0) throw std::runtime_error(std::string("Cannot write output file ") + path);
+        }
+        if (saved) *saved = n;
+    });
 }
 
 }  // extern "C"

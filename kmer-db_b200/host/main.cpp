@@ -170,7 +170,9 @@ void run_all2all_sparse(const Params& p) {
     print_stats_json(calculator.last_stats(), dt);
     std::cerr << "Storing matrix of common k-mers in " << p.files[1] << "...";
     t0 = now();
-    const uint64_t saved = write_sparse_csv(p.files[1], db, *matrix.raw(), &p.filters);
+    const uint64_t saved = p.sampling_size > 0
+        ? write_sparse_csv_sampled(p.files[1], db, *matrix.raw(), &p.filters, (uint32_t)p.sampling_size, p.sampling_criterion)
+        : write_sparse_csv(p.files[1], db, *matrix.raw(), &p.filters);
     std::cerr << "OK (" << now() - t0 << " seconds)" << std::endl;
     std::cerr << "No. saved pairs: " << saved << std::endl;
 }
@@ -214,9 +216,19 @@ struct PartsOnDevice {
     }
 };
 
-// the text of grid row i_row (all lines of its samples); returns the number of pairs written
+// -sample-rows: the rows are chosen from the whole grid (a sample's neighbours sit in its row's cells AND in the cells of
+// the rows below it), so the cells go into one sampler and the table is written after the last of them
+// (src/console_all2all_parts.cpp:188-191,272-275,333-345)
+struct GridSampler {
+    RowSampler sampler;
+    std::mutex mu;   // (-gpus n: the devices' rows arrive concurrently)
+    GridSampler(size_t samples, uint32_t count, metric_fn criterion) : sampler(samples, count, criterion) {}
+};
+
+// the text of grid row i_row (all lines of its samples); returns the number of pairs written.  With a sampler the cells
+// are handed to it instead and the text stays empty.
 uint64_t parts_grid_row(const Params& p, const PartsGrid& g, const SimilarityCalculator& calc, PartsOnDevice& dev, uint32_t i_row,
-                        std::string& text, kdbx_stats& total) {
+                        std::string& text, kdbx_stats& total, GridSampler* sampling) {
     bool keep_row = true;
     const int row = dev.acquire(i_row, keep_row);
     const uint32_t rows = g.part_samples[i_row];
@@ -245,6 +257,13 @@ uint64_t parts_grid_row(const Params& p, const PartsGrid& g, const SimilarityCal
     const int k = (int)g.all.hdr.kmer_length;
     uint64_t saved = 0;
     text.clear();
+    if (sampling) {
+        std::lock_guard<std::mutex> lk(sampling->mu);
+        for (uint32_t c = 0; c <= i_row; ++c)
+            sampling->sampler.add_cell(*cells[c]->raw(), filters, g.all.sample_kmers.data() + g.first_sample[i_row],
+                                       g.all.sample_kmers.data() + g.first_sample[c], g.first_sample[i_row], g.first_sample[c], k);
+        return 0;
+    }
     std::string line;
     for (uint32_t r = 0; r < rows; ++r) {
         const uint32_t s = g.first_sample[i_row] + r;
@@ -319,12 +338,14 @@ void run_all2all_parts(const Params& p) {
     const uint64_t budget = (uint64_t)(p.cache_buffer_mb > 8 ? p.cache_buffer_mb : 100 * 1024) << 20;   // -buffer <mb> bounds the resident parts (default 100 GB)
     uint64_t saved = 0;
     kdbx_stats total{};
+    std::unique_ptr<GridSampler> sampling;
+    if (p.sampling_size > 0) sampling = std::make_unique<GridSampler>(g.all.sample_names.size(), (uint32_t)p.sampling_size, p.sampling_criterion);
     if (num_gpus == 1) {
         SimilarityCalculator calc(p.num_threads, (size_t)p.cache_buffer_mb, p.gpu);
         PartsOnDevice dev(g, calc, budget);
         std::string text;
         for (uint32_t i = 0; i < parts; ++i) {
-            saved += parts_grid_row(p, g, calc, dev, i, text, total);
+            saved += parts_grid_row(p, g, calc, dev, i, text, total, sampling.get());
             std::cerr << "Saving output matrix..." << std::endl;
             std::fwrite(text.data(), 1, text.size(), f);
             std::cerr << " OK (no. currently saved pairs: " << saved << ")" << std::endl;
@@ -347,7 +368,7 @@ void run_all2all_parts(const Params& p) {
                     PartsOnDevice dev(g, calc, budget);
                     for (uint32_t i = (uint32_t)d; i < parts; i += (uint32_t)num_gpus) {
                         std::string text;
-                        saved_g[(size_t)d] += parts_grid_row(p, g, calc, dev, i, text, stats_g[(size_t)d]);
+                        saved_g[(size_t)d] += parts_grid_row(p, g, calc, dev, i, text, stats_g[(size_t)d], sampling.get());
                         std::lock_guard<std::mutex> lk(mu);
                         texts[i] = std::move(text); ready[i] = 1;
                         cv.notify_all();
@@ -377,6 +398,7 @@ void run_all2all_parts(const Params& p) {
             total.ms_total = std::max(total.ms_total, stats_g[(size_t)d].ms_total);
         }
     }
+    if (sampling) saved = sampling->sampler.write_rows(f, g.all.sample_names, g.all.sample_kmers);
     if (std::fclose(f) != 0) throw std::runtime_error("Cannot write output file " + p.files[1]);
     const double dt = now() - t0;
     std::cerr << "Database grid procesed successfully" << std::endl << "No. saved pairs: " << saved << std::endl;

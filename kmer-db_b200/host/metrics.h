@@ -40,6 +40,22 @@ inline metric_fn find_metric(const std::string& name) {
     return it == table.end() ? nullptr : it->second;
 }
 
+// "-sample-rows [criterion:]count" (src/params.cpp:533-556).  criterion stays null when none is named (the reference's
+// random selection, which kmer-db-b200 does not offer: csv_out.h).
+inline void parse_sample_rows(const std::string& text, metric_fn& criterion, int& count) {
+    std::string num = text;
+    criterion = nullptr;
+    const size_t sep = text.rfind(':');
+    if (sep != std::string::npos) {
+        const std::string name = text.substr(0, sep);
+        criterion = find_metric(name);
+        if (!criterion) throw std::runtime_error("Sampling parameters error - unknown measure: " + name);
+        num = text.substr(sep + 1);
+    }
+    std::istringstream iss(num);
+    if (!(iss >> count)) throw std::runtime_error("Sampling parameters error - unable to parse numerical value: " + text);
+}
+
 struct MetricBound {
     double lo = std::numeric_limits<double>::lowest(), hi = std::numeric_limits<double>::max();
     metric_fn fn = nullptr;

@@ -50,9 +50,9 @@ void print_usage(const std::string& mode) {
     else if (mode == "all2all")
         std::cerr << "  all2all [-sparse [-min [<crit>:]<v>]* [-max [<crit>:]<v>]*] [-gpus <n>] [-gpu <id>] [-t <n>] [-buffer <mb>] <database> <common_table>\n";
     else if (mode == "all2all-sp")
-        std::cerr << "  all2all-sp [-min [<crit>:]<v>]* [-max [<crit>:]<v>]* [-gpu <id>] [-t <n>] [-buffer <mb>] [-bubble-size <n>] <database> <common_table>\n";
+        std::cerr << "  all2all-sp [-min [<crit>:]<v>]* [-max [<crit>:]<v>]* [-sample-rows <crit>:<count>] [-gpu <id>] [-t <n>] [-buffer <mb>] [-bubble-size <n>] <database> <common_table>\n";
     else if (mode == "all2all-parts")
-        std::cerr << "  all2all-parts [-min [<crit>:]<v>]* [-max [<crit>:]<v>]* [-gpus <n>] [-gpu <id>] [-t <n>] [-buffer <mb>] [-bubble-size <n>] <db_list> <common_table>\n";
+        std::cerr << "  all2all-parts [-min [<crit>:]<v>]* [-max [<crit>:]<v>]* [-sample-rows <crit>:<count>] [-gpus <n>] [-gpu <id>] [-t <n>] [-buffer <mb>] [-bubble-size <n>] <db_list> <common_table>\n";
     else if (mode == "new2all")
         std::cerr << "  new2all [-multisample-fasta] [-sparse [-min ...]* [-max ...]*] [-gpu <id>] [-t <n>] <database> <sample_list> <common_table>\n";
     else if (mode == "distance")
@@ -109,8 +109,13 @@ bool parse_params(int argc, char** argv, Params& p) {
         p.sparse_out = find_switch(a, "-sparse");
         if (p.sparse_out || p.mode != "all2all") parse_filters(a, p.filters, "num-kmers");
         std::string rows;
-        if (p.mode != "all2all" && find_option(a, "-sample-rows", rows))
-            throw std::runtime_error("-sample-rows is not supported by kmer-db-b200");
+        if (p.mode != "all2all" && find_option(a, "-sample-rows", rows)) {
+            parse_sample_rows(rows, p.sampling_criterion, p.sampling_size);
+            if (p.sampling_size < 0) throw std::runtime_error("Sampling parameters error - unable to parse numerical value: " + rows);
+            if (p.sampling_size > 0 && !p.sampling_criterion)
+                throw std::runtime_error("-sample-rows without a criterion (random selection) is not supported by kmer-db-b200: "
+                                         "name one, e.g. -sample-rows jaccard:" + std::to_string(p.sampling_size));
+        }
     } else if (p.mode == "new2all") {
         if (find_switch(a, "-from-kmers") || find_switch(a, "-from-minhash"))
             throw std::runtime_error("-from-kmers / -from-minhash inputs are not supported by kmer-db-b200 (FASTA only)");

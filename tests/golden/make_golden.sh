@@ -34,3 +34,16 @@ rm -rf "$P3"
 # the reference's test INPUTS (FASTA, lists) and every golden OUTPUT of test/virus, test/synth and the
 # amino-acid part of test/protein, verbatim, for the CLI tests (build / new2all / distance / all2all-sp)
 tar cJf "$HERE/reference_fixtures.tar.xz" test/virus test/synth test/protein/aa_100x1000.fasta test/protein/*.a2a
+# -sample-rows <criterion>:<count> of all2all-sp on the virus database (the best <count> neighbours of every sample);
+# all2all-parts with the same option writes the same bytes for the genomes split into parts (checked here, not stored)
+for c in jaccard:3 num-kmers:5 ani:2 mash-query:4; do
+  "$BIN" all2all-sp -sample-rows "$c" "$HERE/virus.k18.db" "$HERE/virus.k18.sampled.${c/:/_}.csv"
+done
+"$BIN" all2all-sp -min jaccard:0.99 -max num-kmers:29800 -sample-rows cosine:2 "$HERE/virus.k18.db" "$HERE/virus.k18.sampled.filtered.cosine_2.csv"
+P2="$(mktemp -d)"
+sed -n 1,100p test/virus/seqs.list > "$P2/a.list"; sed -n '101,$p' test/virus/seqs.list > "$P2/b.list"
+for x in a b; do "$BIN" build "$P2/$x.list" "$P2/$x.db"; done
+printf '%s\n' "$P2/a.db" "$P2/b.db" > "$P2/db.list"
+"$BIN" all2all-parts -sample-rows jaccard:3 "$P2/db.list" "$P2/s.csv" && cmp "$P2/s.csv" "$HERE/virus.k18.sampled.jaccard_3.csv"
+"$BIN" all2all-parts -min jaccard:0.99 -max num-kmers:29800 -sample-rows cosine:2 "$P2/db.list" "$P2/f.csv" && cmp "$P2/f.csv" "$HERE/virus.k18.sampled.filtered.cosine_2.csv"
+rm -rf "$P2"

@@ -132,6 +132,12 @@ def test_cli_errors(cli, ref_fixtures, tmp_path):
     assert r.returncode != 0 and "Unable to open input file" in r.stderr
     r = cli(ref_fixtures, "build", "only-one-file", check=False)
     assert r.returncode != 0
+    # -sample-rows: the options are parsed before any device is opened (src/params.cpp:533-556)
+    for words, msg in ((["-sample-rows", "3"], "random selection"), (["-sample-rows", "nosuch:3"], "unknown measure"),
+                       (["-sample-rows", "jaccard:x"], "unable to parse numerical value")):
+        for mode in ("all2all-sp", "all2all-parts"):
+            r = cli(ref_fixtures, mode, *words, "in", tmp_path / "o.csv", check=False)
+            assert r.returncode != 0 and msg in r.stderr, (mode, words, r.stderr)
     assert cli(ref_fixtures, "-version").stdout.startswith("kmer-db-b200")
 
 

@@ -402,3 +402,28 @@ def test_db2db_cells_against_oracle(libs, oracle, cli, ref_fixtures, tmp_path):
             rows.db2db_sparse(rows)
     for d in o.values():
         oracle.oracle_db_free(d)
+
+
+def test_cli_sample_rows(cli, ref_fixtures, golden_dbs, tmp_path):
+    """-sample-rows <criterion>:<count> in all2all-sp and all2all-parts (host/csv_out.h::RowSampler over the rows the device
+    delivers): the bytes the reference binary wrote for the same options (tests/golden/make_golden.sh); the parts mode
+    writes the same table for the genomes split into parts.  (The selection itself is also pinned on CPU:
+    tests/test_host.py::test_sparse_table_with_sample_rows_equals_reference_output.)"""
+    G = ou.ROOT / "tests" / "golden"
+    db = golden_dbs["virus.k18"][0]
+    dbs = []
+    for i, lst in enumerate(_split_virus_lists(ref_fixtures, tmp_path, [60, 120])):
+        dbs.append(tmp_path / f"part{i}.db")
+        cli(ref_fixtures, "build", lst, dbs[-1])
+    (tmp_path / "db.list").write_text("\n".join(map(str, dbs)) + "\n")
+    for words, golden in ((["-sample-rows", "jaccard:3"], "virus.k18.sampled.jaccard_3.csv"),
+                          (["-sample-rows", "mash-query:4"], "virus.k18.sampled.mash-query_4.csv"),
+                          (["-min", "jaccard:0.99", "-max", "num-kmers:29800", "-sample-rows", "cosine:2"], "virus.k18.sampled.filtered.cosine_2.csv")):
+        want = ou.read_bytes(G / golden)
+        pairs = sum(len([x for x in ln.split(b",")[2:] if x]) for ln in want.splitlines()[2:])
+        r = cli(ref_fixtures, "all2all-sp", *words, db, tmp_path / "sp.csv")
+        assert ou.read_bytes(tmp_path / "sp.csv") == want, words
+        assert f"No. saved pairs: {pairs}" in r.stderr
+        r = cli(ref_fixtures, "all2all-parts", *words, tmp_path / "db.list", tmp_path / "parts.csv")
+        assert ou.read_bytes(tmp_path / "parts.csv") == want, words
+        assert f"No. saved pairs: {pairs}" in r.stderr

@@ -487,3 +487,60 @@ def test_parallel_mapped_reader_equals_streaming_reader(libs, golden_dbs, tmp_pa
         f.write_bytes(bytes(bad))
         a, b = _read_both_ways(libs, f, monkeypatch)
         assert a[0] == b[0] == "error", what
+
+
+def _csr_of_block(tri, r0, r1, c0, c1):
+    """rows [r0, r1) x columns [c0, c1) of the packed lower-triangular matrix as (row_ptr, col, val): non-zero cells below
+    the diagonal, columns ascending and relative to c0 — what kdbx_all2all_sparse / kdbx_db2db_sparse hand to the host"""
+    ptr, cols, vals = [0], [], []
+    for r in range(r0, r1):
+        row = tri[ou.tri_cells(r):ou.tri_cells(r) + r]
+        hi = min(c1, r)
+        if hi > c0:
+            seg = row[c0:hi]
+            nz = np.nonzero(seg)[0]
+            cols.append(nz.astype(np.uint32)); vals.append(seg[nz])
+        ptr.append(ptr[-1] + (len(cols[-1]) if hi > c0 else 0))
+    cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, np.uint32)
+    return np.array(ptr, np.uint64), cat(cols), cat(vals)
+
+
+@pytest.mark.parametrize("golden,filters,sample_rows", [
+    ("virus.k18.sparse.csv", None, None),
+    ("virus.k18.sampled.jaccard_3.csv", None, "jaccard:3"),
+    ("virus.k18.sampled.num-kmers_5.csv", None, "num-kmers:5"),
+    ("virus.k18.sampled.ani_2.csv", None, "ani:2"),
+    ("virus.k18.sampled.mash-query_4.csv", None, "mash-query:4"),
+    ("virus.k18.sampled.filtered.cosine_2.csv", "-min jaccard:0.99 -max num-kmers:29800", "cosine:2"),
+])
+def test_sparse_table_with_sample_rows_equals_reference_output(libs, oracle, golden_dbs, tmp_path, golden, filters, sample_rows):
+    """-sample-rows <criterion>:<count> (host/csv_out.h::RowSampler): the oracle computes the matrix, the product filters,
+    samples and formats it — as one matrix (all2all-sp) and as the grid of cells of all2all-parts with the samples split
+    60 / 60 / 44 and 1 / 163 — and the bytes must be what the reference binary wrote (tests/golden/make_golden.sh)."""
+    t = libs.Trie.read_db(golden_dbs["virus.k18"][0])
+    N = t.num_samples
+    tri, _ = ou.oracle_all2all(oracle, N, t.arrays())
+    want = ou.read_bytes(ou.ROOT / "tests" / "golden" / golden)
+    out = tmp_path / "o.csv"
+    saved = t.write_sparse_csv([(0, 0, *_csr_of_block(tri, 0, N, 0, N))], out, filters=filters, sample_rows=sample_rows)
+    assert ou.read_bytes(out) == want
+    assert saved == sum(len([x for x in ln.split(b",")[2:] if x]) for ln in want.splitlines()[2:])
+    if sample_rows is None:
+        return
+    for cuts in ([60, 120], [1]):
+        edges = [0, *cuts, N]
+        cells = [(edges[i], edges[j], *_csr_of_block(tri, edges[i], edges[i + 1], edges[j], edges[j + 1]))
+                 for i in range(len(edges) - 1) for j in range(i + 1)]
+        # (any order of the cells gives the same rows: the selection is a total order on (criterion, sample id))
+        t.write_sparse_csv(cells[::-1], out, filters=filters, sample_rows=sample_rows)
+        assert ou.read_bytes(out) == want, cuts
+
+
+def test_sample_rows_argument_errors(libs, golden_dbs, tmp_path):
+    t = libs.Trie.read_db(golden_dbs["virus.k18"][0])
+    empty = [(0, 0, np.zeros(t.num_samples + 1, np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.uint32))]
+    for bad in ("3", "nosuch:3", "jaccard:x", "jaccard:0"):   # no criterion = the reference's random selection: not offered
+        with pytest.raises(libs.KdbxError):
+            t.write_sparse_csv(empty, tmp_path / "e.csv", sample_rows=bad)
+    with pytest.raises(libs.KdbxError):   # a grid of cells is only meaningful with a sampler
+        t.write_sparse_csv(empty + empty, tmp_path / "e.csv")
