@@ -125,6 +125,10 @@ const uint64_t* kdbxh_samples_kmers(const kdbxh_samples* s, uint32_t i, uint64_t
 /* tri: packed lower-triangular uint32 matrix, N(N-1)/2 cells (src/array.h:140). */
 int kdbxh_write_all2all_csv(const kdbxh_trie* t, const uint32_t* tri, const char* path, int sparse);
 
+/* The one2all table (src/console_one2all.cpp:82-92): the database's two header lines and one row
+ * `<sample>,<kmers>,<sims[0]>,...,<sims[N-1]>,` without a newline after it. */
+int kdbxh_write_one2all_csv(const kdbxh_trie* t, const char* sample, uint64_t kmers, const uint32_t* sims, const char* path);
+
 /* The all2all-sp / all2all-parts table from sparse rows (src/console_all2all_sparse.cpp:50-98, SparseMatrix::saveRowSparse
  * src/array.h:625-637), with the reference's output options evaluated on the host:
  *   filters      the command-line words of -min / -max, e.g. "-min jaccard:0.9 -max 100" (NULL = none; src/params.cpp:418-455)

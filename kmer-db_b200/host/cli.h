@@ -47,6 +47,7 @@ void run_all2all(const Params& p);
 void run_all2all_sparse(const Params& p);
 void run_all2all_parts(const Params& p);
 void run_new2all(const Params& p);
+void run_one2all(const Params& p);
 void run_distance(const Params& p);
 
 }  // namespace kdbx

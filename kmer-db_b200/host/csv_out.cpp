@@ -229,6 +229,23 @@ uint64_t write_sparse_csv_sampled(const std::string& path, const Trie& t, const 
     return saved;
 }
 
+void write_one2all_csv(const std::string& path, const Trie& db, const std::string& sample, uint64_t kmers, const uint32_t* sims) {
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("Cannot open output file " + path);
+    const std::string head = table_header(db);
+    std::fwrite(head.data(), 1, head.size(), f);
+    const size_t N = db.num_samples();
+    std::string row(sample.size() + 32 + N * 11, '\0');
+    char* p = row.data();
+    std::memcpy(p, sample.data(), sample.size()); p += sample.size();
+    *p++ = ',';
+    p = put_u64(p, kmers);
+    *p++ = ',';
+    for (size_t c = 0; c < N; ++c) { p = put_u64(p, sims[c]); *p++ = ','; }
+    std::fwrite(row.data(), 1, (size_t)(p - row.data()), f);
+    if (std::fclose(f) != 0) throw std::runtime_error("Cannot write output file " + path);
+}
+
 // new2all table (src/console_new2all.cpp:98-161): database headers, then one row per query in
 // input order: `<name>,<unique k-mers>,` + N dense cells, or `col+1:val,` pairs for non-zero cells
 // passing the filters (evaluated with the QUERY's k-mer count as the row count).

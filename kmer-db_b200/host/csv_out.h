@@ -47,6 +47,10 @@ private:
 uint64_t write_sparse_csv_sampled(const std::string& path, const Trie& t, const kdbx_csr& m, const OutputFilters* filters,
                                   uint32_t max_items, metric_fn criterion);
 
+// one2all table (src/console_one2all.cpp:82-92): the two database header lines, then ONE row `<sample as given>,<its unique
+// k-mers>,` + N dense cells — and no newline after it
+void write_one2all_csv(const std::string& path, const Trie& db, const std::string& sample, uint64_t kmers, const uint32_t* sims);
+
 class QueryTableWriter {
 public:
     QueryTableWriter(const std::string& path, const Trie& db, bool sparse, const OutputFilters* filters);

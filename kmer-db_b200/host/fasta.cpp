@@ -157,6 +157,8 @@ namespace kdbx {
 
 SequenceStream::SequenceStream(const std::string& list_arg, bool multisample, int threads)
     : files_(read_sample_list(list_arg)), multisample_(multisample), ahead_((size_t)std::max(1, threads)) {}
+SequenceStream::SequenceStream(std::vector<std::string> entries, bool multisample, int threads)
+    : files_(std::move(entries)), multisample_(multisample), ahead_((size_t)std::max(1, threads)) {}
 
 std::vector<SampleSeq> SequenceStream::load_file(size_t idx) const {
     std::vector<SampleSeq> out;

@@ -272,6 +272,11 @@ int kdbxh_write_all2all_csv(const kdbxh_trie* t, const uint32_t* tri, const char
     return guarded([&] { kdbx::write_all2all_csv(path, t->t, tri, sparse != 0); });
 }
 
+int kdbxh_write_one2all_csv(const kdbxh_trie* t, const char* sample, uint64_t kmers, const uint32_t* sims, const char* path) {
+    if (!t || !sample || !path || (!sims && t->t.num_samples())) { g_err = "null argument"; return -1; }
+    return guarded([&] { kdbx::write_one2all_csv(path, t->t, sample, kmers, sims); });
+}
+
 int kdbxh_write_sparse_csv(const kdbxh_trie* t, const kdbx_csr* cells, const uint32_t* row_shifts, const uint32_t* col_shifts,
                            uint32_t num_cells, const char* filters, const char* sample_rows, const char* path, uint64_t* saved) {
     if (!t || !path || (num_cells && !cells)) { g_err = "null argument"; return -1; }

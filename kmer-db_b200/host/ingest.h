@@ -43,6 +43,8 @@ struct SampleSeq {
 class SequenceStream {
 public:
     SequenceStream(const std::string& list_arg, bool multisample, int threads);
+    // the entries themselves (one2all: a single sample file, with or without its extension)
+    SequenceStream(std::vector<std::string> entries, bool multisample, int threads);
     bool next(SampleSeq& out);
     size_t num_files() const { return files_.size(); }
 

@@ -462,6 +462,41 @@ void run_new2all(const Params& p) {
     print_stats_json(total, dt);
 }
 
+// one2all (src/console_one2all.cpp:12-96): ONE sample file against the database — new2all's device path with a single
+// query (k-mer extraction, minhash, sort/unique, probe, scatter), the table in the mode's own layout (csv_out.h).
+void run_one2all(const Params& p) {
+    if (p.files.size() != 3) throw usage_error(p.mode);
+    std::cerr << "One new sample  (from genomes) versus entire database comparison" << std::endl;
+    SimilarityCalculator calculator(p.num_threads, (size_t)p.cache_buffer_mb, p.gpu);
+    Trie db(true);
+    std::cerr << "Loading k-mer database " << p.files[0] << ":" << std::endl;
+    double t0 = now();
+    read_db(p.files[0], db, true);
+    std::cerr << "OK (" << now() - t0 << " seconds)" << std::endl;
+    calculator.load_database(db);
+    std::cerr << "Loading sample kmers..." << std::endl;
+    SequenceStream stream(std::vector<std::string>{p.files[1]}, false, 1);
+    SampleSeq s;
+    if (!stream.next(s)) throw std::runtime_error("Cannot open sample file: " + p.files[1]);
+    Buf<char> symbols;
+    symbols.set_pinned(true);
+    symbols.resize(s.symbols.size());
+    std::copy(s.symbols.begin(), s.symbols.end(), symbols.data());
+    const std::vector<uint64_t> q_off = {0, (uint64_t)symbols.size()};
+    std::vector<uint64_t> unique;
+    std::vector<uint32_t> sims;
+    std::cerr << "Calculating similarity vector..." << std::endl;
+    t0 = now();
+    calculator.one2all_sequences(db.hdr, symbols.data(), q_off, sims, unique);
+    const double dt = now() - t0;
+    std::cerr << "OK (" << dt << " seconds)" << std::endl << "Number of k-mers: " << unique[0] << std::endl
+              << "Minhash fraction: " << db.hdr.fraction << std::endl;
+    print_stats_json(calculator.last_stats(), dt);
+    std::cerr << "Storing similarity vector in " << p.files[2] << "..." << std::endl;
+    write_one2all_csv(p.files[2], db, p.files[1], unique[0], sims.data());
+    std::cerr << "OK" << std::endl;
+}
+
 namespace {
 int run_synth(std::vector<std::string> args) {
     SynthParams sp; std::vector<std::string> files;
@@ -513,6 +548,7 @@ int main(int argc, char** argv) {
         else if (p.mode == "all2all-sp") run_all2all_sparse(p);
         else if (p.mode == "all2all-parts") run_all2all_parts(p);
         else if (p.mode == "new2all") run_new2all(p);
+        else if (p.mode == "one2all") run_one2all(p);
         else if (p.mode == "distance") run_distance(p);
     } catch (const usage_error& e) {
         print_usage(e.what());

@@ -39,7 +39,7 @@ void parse_filters(std::vector<std::string>& a, OutputFilters& f, const std::str
     }
 }
 
-const char* kModes[] = {"build", "all2all", "all2all-sp", "all2all-parts", "new2all", "distance"};
+const char* kModes[] = {"build", "all2all", "all2all-sp", "all2all-parts", "new2all", "one2all", "distance"};
 
 }  // namespace
 
@@ -55,11 +55,13 @@ void print_usage(const std::string& mode) {
         std::cerr << "  all2all-parts [-min [<crit>:]<v>]* [-max [<crit>:]<v>]* [-sample-rows <crit>:<count>] [-gpus <n>] [-gpu <id>] [-t <n>] [-buffer <mb>] [-bubble-size <n>] <db_list> <common_table>\n";
     else if (mode == "new2all")
         std::cerr << "  new2all [-multisample-fasta] [-sparse [-min ...]* [-max ...]*] [-gpu <id>] [-t <n>] <database> <sample_list> <common_table>\n";
+    else if (mode == "one2all")
+        std::cerr << "  one2all [-gpu <id>] [-t <n>] <database> <sample> <common_table>\n";
     else if (mode == "distance")
         std::cerr << "  distance <measure> [-sparse [-min [<crit>:]<v>]* [-max [<crit>:]<v>]*] [-phylip-out] <common_table> <output_table>\n"
                      "    measures: jaccard, min, max, cosine, mash, ani, ani-shorter, mash-query, num-kmers\n";
     else
-        std::cerr << "  modes: build, all2all, all2all-sp, all2all-parts, new2all, distance   (kmer-db-b200 <mode> -help)\n"
+        std::cerr << "  modes: build, all2all, all2all-sp, all2all-parts, new2all, one2all, distance   (kmer-db-b200 <mode> -help)\n"
                      "  extras: synth (generate a synthetic database), info <database>\n";
 }
 
@@ -122,6 +124,9 @@ bool parse_params(int argc, char** argv, Params& p) {
         p.multisample_fasta = find_switch(a, "-multisample-fasta");
         p.sparse_out = find_switch(a, "-sparse");
         if (p.sparse_out) parse_filters(a, p.filters, "num-kmers");
+    } else if (p.mode == "one2all") {
+        if (find_switch(a, "-from-kmers") || find_switch(a, "-from-minhash"))
+            throw std::runtime_error("-from-kmers / -from-minhash inputs are not supported by kmer-db-b200 (FASTA only)");
     } else if (p.mode == "distance") {
         p.sparse_out = find_switch(a, "-sparse");
         p.phylip_out = find_switch(a, "-phylip-out");

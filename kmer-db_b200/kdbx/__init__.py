@@ -118,7 +118,7 @@ KDBX_SYMBOLS = ["kdbx_abi_version", "kdbx_device_count", "kdbx_open", "kdbx_clos
 KDBXH_SYMBOLS = ["kdbxh_last_error", "kdbxh_trie_new", "kdbxh_trie_free", "kdbxh_read_db", "kdbxh_write_db",
                  "kdbxh_synth", "kdbxh_validate", "kdbxh_prefix", "kdbxh_partition", "kdbxh_partitioner_new", "kdbxh_partitioner_free",
                  "kdbxh_partitioner_part", "kdbxh_partition_write_all", "kdbxh_relabel", "kdbxh_view", "kdbxh_totals_of", "kdbxh_sample_name",
-                 "kdbxh_sample_kmers", "kdbxh_write_all2all_csv", "kdbxh_write_sparse_csv", "kdbxh_read_db_full", "kdbxh_tables_view",
+                 "kdbxh_sample_kmers", "kdbxh_write_all2all_csv", "kdbxh_write_sparse_csv", "kdbxh_write_one2all_csv", "kdbxh_read_db_full", "kdbxh_tables_view",
                  "kdbxh_builder_new", "kdbxh_builder_free", "kdbxh_builder_add_sample", "kdbxh_builder_finish",
                  "kdbxh_samples_load", "kdbxh_samples_free", "kdbxh_samples_count", "kdbxh_samples_name", "kdbxh_samples_kmers"]
 
@@ -207,6 +207,7 @@ def load():
     h.kdbxh_sample_kmers.argtypes = [C.c_void_p, C.c_uint32]
     h.kdbxh_sample_kmers.restype = C.c_uint64
     h.kdbxh_write_all2all_csv.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+    h.kdbxh_write_one2all_csv.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_void_p, C.c_char_p]
     h.kdbxh_write_sparse_csv.argtypes = [C.c_void_p, P(Csr), C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p, C.c_char_p, C.c_char_p, P(C.c_uint64)]
     h.kdbxh_read_db_full.argtypes = [C.c_void_p, C.c_char_p]
     h.kdbxh_tables_view.argtypes = [C.c_void_p, P(TablesView)]
@@ -403,6 +404,12 @@ class Trie:
         if tri.size != tri_cells(self.num_samples):
             raise KdbxError("matrix size does not match the sample count")
         self._check(self._h.kdbxh_write_all2all_csv(self._p, tri.ctypes.data, os.fsencode(str(path)), 1 if sparse else 0))
+
+    def write_one2all_csv(self, sample, kmers, sims, path):
+        sims = np.ascontiguousarray(sims, dtype=np.uint32)
+        if sims.size != self.num_samples:
+            raise KdbxError("one similarity per database sample is needed")
+        self._check(self._h.kdbxh_write_one2all_csv(self._p, os.fsencode(str(sample)), int(kmers), sims.ctypes.data, os.fsencode(str(path))))
 
     def write_sparse_csv(self, cells, path, filters=None, sample_rows=None):
         """The all2all-sp / all2all-parts table from sparse rows (kdbxh_write_sparse_csv).  cells: [(row_shift, col_shift,

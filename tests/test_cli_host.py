@@ -243,3 +243,19 @@ def test_oracle_all2all_parts_reproduces_reference_csv(cli, oracle, ref_fixtures
         pairs = oracle.oracle_all2all_parts_file(str(tmp_path / "db.list").encode(), str(tmp_path / "parts.csv").encode())
         assert pairs == 13530   # "No. saved pairs" of the reference run
         assert ou.read_bytes(tmp_path / "parts.csv") == ou.read_bytes(ref_fixtures / "test/virus/k18.sparse.csv")
+
+
+def test_one2all_table_reproduces_reference_csv(cli, libs, oracle, ref_fixtures, tmp_path):
+    """The reference's CI step `build -k 25 -f 0.1 seqs.part1.list` + `one2all k25.db data/MT159713` == test/virus/MT159713.csv
+    (.github/workflows/main.yml:156-160).  CPU: our host builder writes the database, the oracle's new2all supplies the
+    similarity vector of that one query, the product's one2all emitter (host/csv_out.cpp::write_one2all_csv) formats it."""
+    db = tmp_path / "k25.db"
+    cli(ref_fixtures, "build", "-host-build", "-k", "25", "-f", "0.1", "test/virus/seqs.part1.list", db)
+    (tmp_path / "q.list").write_text("./test/virus/data/MT159713\n")
+    n2a = _oracle_new2all_csv(oracle, db, tmp_path / "q.list", tmp_path / "n2a.csv", cwd=ref_fixtures).decode().splitlines()
+    assert len(n2a) == 3
+    row = n2a[2].split(",")
+    assert row[0] == "MT159713" and row[-1] == ""
+    t = libs.Trie.read_db(db)
+    t.write_one2all_csv("./test/virus/data/MT159713", int(row[1]), np.array(row[2:-1], dtype=np.uint32), tmp_path / "o.csv")
+    assert ou.read_bytes(tmp_path / "o.csv") == ou.read_bytes(ref_fixtures / "test/virus/MT159713.csv")

@@ -427,3 +427,13 @@ def test_cli_sample_rows(cli, ref_fixtures, golden_dbs, tmp_path):
         r = cli(ref_fixtures, "all2all-parts", *words, tmp_path / "db.list", tmp_path / "parts.csv")
         assert ou.read_bytes(tmp_path / "parts.csv") == want, words
         assert f"No. saved pairs: {pairs}" in r.stderr
+
+
+def test_cli_one2all(cli, ref_fixtures, tmp_path):
+    """The reference's CI step for the mode (.github/workflows/main.yml:156-160): build -k 25 -f 0.1 from the first 100 genomes,
+    one2all with one more genome given without its extension, cmp with test/virus/MT159713.csv."""
+    cli(ref_fixtures, "build", "-k", "25", "-f", "0.1", "test/virus/seqs.part1.list", tmp_path / "k25.db")
+    cli(ref_fixtures, "one2all", tmp_path / "k25.db", "./test/virus/data/MT159713", tmp_path / "MT159713.csv")
+    assert ou.read_bytes(tmp_path / "MT159713.csv") == ou.read_bytes(ref_fixtures / "test/virus/MT159713.csv")
+    r = cli(ref_fixtures, "one2all", tmp_path / "k25.db", "./test/virus/data/no-such-genome", tmp_path / "x.csv", check=False)
+    assert r.returncode != 0 and "Cannot open sample file" in r.stderr
