@@ -36,8 +36,8 @@ public:
 
     void reserve(size_t n) {
         if (n <= cap_) return;
-        size_t ncap = cap_ ? cap_ : 1024;
-        while (ncap < n) ncap += ncap / 2 + 1;
+        size_t ncap = cap_ ? cap_ : (n < 1024 ? 1024 : n);   // a first request is met exactly (the readers size every array once;
+        while (ncap < n) ncap += ncap / 2 + 1;                //  page-locked memory is too dear to over-allocate by half)
         T* np = nullptr;
         if (pinned_) {
             void* v = nullptr;
