@@ -103,6 +103,40 @@ void fill_block(BlockRef& b, uint64_t pid, uint64_t at, Trie& t, int32_t* parent
     }
 }
 
+// a read-only mapping of the file from byte `from` on (data() = the byte at `from`)
+class MappedTail {
+public:
+    MappedTail(const std::string& path, uint64_t from) {
+        const int fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) return;
+        struct stat st;
+        if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && (uint64_t)st.st_size > from) {
+            const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE);
+            const uint64_t map_off = from / page * page;
+            len_ = (size_t)((uint64_t)st.st_size - map_off);
+            void* m = mmap(nullptr, len_, PROT_READ, MAP_PRIVATE, fd, (off_t)map_off);
+            if (m != MAP_FAILED) {
+                map_ = m;
+                madvise(m, len_, MADV_WILLNEED);
+                data_ = static_cast<const char*>(m) + (from - map_off);
+                avail_ = (uint64_t)st.st_size - from;
+            }
+        }
+        ::close(fd);
+    }
+    ~MappedTail() { if (map_) munmap(map_, len_); }
+    MappedTail(const MappedTail&) = delete;
+    MappedTail& operator=(const MappedTail&) = delete;
+    bool ok() const { return map_ != nullptr; }
+    const char* data() const { return data_; }
+    uint64_t size() const { return avail_; }
+private:
+    void* map_ = nullptr;
+    size_t len_ = 0;
+    const char* data_ = nullptr;
+    uint64_t avail_ = 0;
+};
+
 template <class F>
 void for_each_block(size_t count, F&& f) {
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
@@ -115,24 +149,72 @@ void for_each_block(size_t count, F&& f) {
     for (auto& x : th) x.join();
 }
 
+// The raw k-mer tables (hash_map_lp::serialize, src/hashmap_lp.h:481-528: 64 bytes of fields, the occupancy bit vector,
+// the filled items in slot order), expanded to slot arrays in parallel: the headers are walked once for the tables'
+// places in the file, then the tables are dealt to the threads.  Returns false when the file cannot be mapped;
+// `end` = file offset right after the last table.
+bool read_tables_mapped(const std::string& path, uint64_t here, uint64_t num_tables, std::vector<HashTable>& tables, uint64_t& end) {
+    MappedTail map(path, here);
+    if (!map.ok()) return false;
+    const char* base = map.data();
+    const uint64_t avail = map.size();
+    const auto corrupt = [&] { return std::runtime_error("Corrupt k-mer database " + path); };
+    const auto truncated = [&] { return std::runtime_error("Cannot open k-mer database " + path + " (truncated)"); };
+    std::vector<uint64_t> at(num_tables);
+    uint64_t o = 0;
+    for (uint64_t i = 0; i < num_tables; ++i) {
+        if (avail - o < 64) throw truncated();
+        uint64_t filled, allocated;
+        std::memcpy(&filled, base + o + 8, 8);
+        std::memcpy(&allocated, base + o + 16, 8);
+        if (allocated == 0 || (allocated & (allocated - 1)) || filled > allocated) throw corrupt();
+        const uint64_t body = (allocated + 63) / 64 * 8 + filled * 8;
+        if (avail - o - 64 < body) throw truncated();
+        at[i] = o;
+        o += 64 + body;
+    }
+    end = here + o;
+    tables.clear();
+    tables.resize(num_tables);
+    std::atomic<bool> bad{false};
+    const size_t group = 64;   // tables per grab (k = 25 means 2^18 tables of 16 slots)
+    for_each_block((size_t)((num_tables + group - 1) / group), [&](size_t g) {
+        for (uint64_t i = g * group; i < std::min<uint64_t>(num_tables, (g + 1) * group); ++i) {
+            const char* p = base + at[i];
+            HashTable& ht = tables[i];
+            uint64_t allocated;
+            std::memcpy(&ht.max_fill, p, 8); std::memcpy(&ht.filled, p + 8, 8); std::memcpy(&allocated, p + 16, 8);
+            std::memcpy(&ht.ht_total, p + 48, 8); std::memcpy(&ht.ht_match, p + 56, 8);
+            const uint64_t bv_words = (allocated + 63) / 64;
+            const char* bv = p + 64;
+            const char* items = bv + bv_words * 8;
+            ht.slots.assign(allocated, HashTable::kEmptySlot);
+            uint64_t next = 0;
+            for (uint64_t w = 0; w < bv_words; ++w) {
+                uint64_t bits;
+                std::memcpy(&bits, bv + w * 8, 8);
+                while (bits) {
+                    const uint64_t slot = w * 64 + (uint64_t)__builtin_ctzll(bits);
+                    bits &= bits - 1;
+                    if (slot >= allocated || next >= ht.filled) { bad = true; return; }
+                    std::memcpy(&ht.slots[slot], items + next * 8, 8);   // {u32 key; i32 val}
+                    ++next;
+                }
+            }
+            if (next != ht.filled) { bad = true; return; }
+        }
+    });
+    if (bad) throw corrupt();
+    return true;
+}
+
 // Reads the P patterns that start at file offset `here` (right after the pattern count) through a mapping of the file.
 // Returns false when the file cannot be mapped (the caller then streams it); throws on a corrupt pattern section.
 bool read_patterns_mapped(const std::string& path, uint64_t here, uint64_t P, Trie& t) {
-    const int fd = ::open(path.c_str(), O_RDONLY);
-    if (fd < 0) return false;
-    struct stat st;
-    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || (uint64_t)st.st_size <= here) { ::close(fd); return false; }
-    const uint64_t file_size = (uint64_t)st.st_size;
-    const long page = sysconf(_SC_PAGESIZE);
-    const uint64_t map_off = here / (uint64_t)page * (uint64_t)page;
-    const size_t map_len = (size_t)(file_size - map_off);
-    void* m = mmap(nullptr, map_len, PROT_READ, MAP_PRIVATE, fd, (off_t)map_off);
-    ::close(fd);
-    if (m == MAP_FAILED) return false;
-    struct Unmap { void* p; size_t n; ~Unmap() { munmap(p, n); } } unmap{m, map_len};
-    madvise(m, map_len, MADV_WILLNEED);
-    const char* base = static_cast<const char*>(m) + (here - map_off);
-    const uint64_t avail = file_size - here;
+    MappedTail map(path, here);
+    if (!map.ok()) return false;
+    const char* base = map.data();
+    const uint64_t avail = map.size();
     const auto corrupt = [&] { return std::runtime_error("Corrupt k-mer database " + path); };
     const auto truncated = [&] { return std::runtime_error("Cannot open k-mer database " + path + " (truncated)"); };
 
@@ -209,8 +291,19 @@ void read_db(const std::string& path, Trie& t, bool with_tables) {
         if (!raw) throw std::runtime_error("Cannot open k-mer database " + path + " (non-raw hashtables are not supported)");
         t.tables.resize(h.num_hashtables);
     }
+    const char* force_reader = std::getenv("KDBX_DB_READER");   // "stream": the sequential readers (tests compare the two)
+    const bool stream_only = force_reader && std::strcmp(force_reader, "stream") == 0;
+    uint64_t tables_done = 0;
+    if (with_tables && !stream_only && h.num_hashtables) {
+        const off_t here = ftello(in.f);
+        uint64_t end = 0;
+        if (here >= 0 && read_tables_mapped(path, (uint64_t)here, h.num_hashtables, t.tables, end)) {
+            if (fseeko(in.f, (off_t)end, SEEK_SET) != 0) throw std::runtime_error("Cannot open k-mer database " + path + " (seek)");
+            tables_done = h.num_hashtables;
+        }
+    }
     std::vector<uint64_t> bv, items;
-    for (uint64_t i = 0; i < h.num_hashtables; ++i) {
+    for (uint64_t i = tables_done; i < h.num_hashtables; ++i) {
         if (raw) {
             const double max_fill = in.get<double>();
             const uint64_t filled = in.get<uint64_t>();
@@ -255,8 +348,7 @@ void read_db(const std::string& path, Trie& t, bool with_tables) {
     const uint64_t P = in.get<uint64_t>();
     {
         const off_t here = ftello(in.f);
-        const char* force = std::getenv("KDBX_DB_READER");   // "stream": the sequential reader (tests compare the two)
-        if (here >= 0 && !(force && std::strcmp(force, "stream") == 0) && read_patterns_mapped(path, (uint64_t)here, P, t)) return;
+        if (here >= 0 && !stream_only && read_patterns_mapped(path, (uint64_t)here, P, t)) return;
     }
     t.num_kmers.resize(P); t.parent_id.resize(P); t.n.resize(P); t.l.resize(P);
     t.last.resize(P); t.bits.resize(P); t.payload_off.resize(P);

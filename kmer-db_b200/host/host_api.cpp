@@ -137,8 +137,10 @@ int kdbxh_tables_view(kdbxh_trie* t, kdbx_tables_view* out) {
             for (size_t i = 0; i < tabs.size(); ++i) t->flat_off[i + 1] = t->flat_off[i] + tabs[i].slots.size();
             t->flat_slots.clear();
             t->flat_slots.resize(t->flat_off.back());
-            for (size_t i = 0; i < tabs.size(); ++i)
-                std::memcpy(t->flat_slots.data() + t->flat_off[i], tabs[i].slots.data(), tabs[i].slots.size() * 8);
+            kdbx::parallel_ranges(tabs.size(), 64, [&](size_t b, size_t e) {
+                for (size_t i = b; i < e; ++i)
+                    std::memcpy(t->flat_slots.data() + t->flat_off[i], tabs[i].slots.data(), tabs[i].slots.size() * 8);
+            });
         }
         out->num_tables = tabs.size(); out->slot_off = t->flat_off.data(); out->slots = t->flat_slots.data();
     });

@@ -344,11 +344,12 @@ private:
         if (kdbx_load_patterns(c, &v) != KDBX_OK) throw std::runtime_error(kdbx_last_error(c));
         std::vector<uint64_t> off(db.tables.size() + 1, 0);
         for (size_t t = 0; t < db.tables.size(); ++t) off[t + 1] = off[t] + db.tables[t].slots.size();
-        std::vector<uint64_t> slots(off.back());
-        for (size_t t = 0; t < db.tables.size(); ++t)
-            std::copy(db.tables[t].slots.begin(), db.tables[t].slots.end(), slots.data() + off[t]);
+        std::unique_ptr<uint64_t[]> slots(new uint64_t[off.back() + 1]);   // (not value-initialised: every slot is copied below)
+        parallel_ranges(db.tables.size(), 64, [&](size_t b, size_t e) {
+            for (size_t t = b; t < e; ++t) std::copy(db.tables[t].slots.begin(), db.tables[t].slots.end(), slots.get() + off[t]);
+        });
         kdbx_tables_view tv{};
-        tv.num_tables = db.tables.size(); tv.slot_off = off.data(); tv.slots = slots.data();
+        tv.num_tables = db.tables.size(); tv.slot_off = off.data(); tv.slots = slots.get();
         if (kdbx_load_hashtables(c, &tv) != KDBX_OK) throw std::runtime_error(kdbx_last_error(c));
     }
     struct Part {

@@ -7,7 +7,10 @@
 #include <cstdint>
 #include <cstdlib>
 #include <stdexcept>
+#include <algorithm>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/kdbx.h"
@@ -83,6 +86,17 @@ private:
     size_t size_ = 0, cap_ = 0;
     bool pinned_ = false;
 };
+
+// f(begin, end) over [0, n) in contiguous ranges on up to 16 host threads (bulk copies of table slots, headers, ...)
+template <class F>
+inline void parallel_ranges(size_t n, size_t min_range, F&& f) {
+    const size_t hw = std::max<size_t>(1, std::thread::hardware_concurrency());
+    const size_t nt = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(hw, 16), n / std::max<size_t>(1, min_range)));
+    if (nt <= 1) { if (n) f((size_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < nt; ++k) th.emplace_back([&, k] { f(n * k / nt, n * (k + 1) / nt); });
+    for (auto& x : th) x.join();
+}
 
 // Database header fields in file order (src/prefix_kmer_db.cpp:449-455).
 struct DbHeader {

@@ -544,3 +544,55 @@ def test_sample_rows_argument_errors(libs, golden_dbs, tmp_path):
             t.write_sparse_csv(empty, tmp_path / "e.csv", sample_rows=bad)
     with pytest.raises(libs.KdbxError):   # a grid of cells is only meaningful with a sampler
         t.write_sparse_csv(empty + empty, tmp_path / "e.csv")
+
+
+def _tables_of(t):
+    """(slot offsets, slots) of a trie read with its k-mer tables, as numpy copies"""
+    v = t.tables_view()
+    T = int(v.num_tables)
+    off = np.ctypeslib.as_array(C.cast(v.slot_off, C.POINTER(C.c_uint64)), shape=(T + 1,)).copy()
+    slots = np.ctypeslib.as_array(C.cast(v.slots, C.POINTER(C.c_uint64)), shape=(int(off[-1]),)).copy()
+    return off, slots
+
+
+def test_parallel_mapped_table_reader_equals_streaming_reader(libs, cli, golden_dbs, ref_fixtures, tmp_path, monkeypatch):
+    """The raw k-mer tables of a database (new2all, all2all-parts, build -extend) are expanded to slot arrays in parallel
+    from a mapping of the file; same slots, same patterns after them and same refusals as the sequential reader — on the
+    reference-built fixtures (256 and 65 536 tables) and on a k = 25 database of ours (262 144 tables)."""
+    ours = tmp_path / "k25.db"
+    cli(ref_fixtures, "build", "-host-build", "-k", "25", "-f", "0.1", "test/virus/seqs.part1.list", ours)
+    for db in (golden_dbs["virus.k18"][0], golden_dbs["virus.k24"][0], golden_dbs["synth.k21"][0], ours):
+        got = {}
+        for mode in ("mapped", "stream"):
+            if mode == "stream":
+                monkeypatch.setenv("KDBX_DB_READER", "stream")
+            else:
+                monkeypatch.delenv("KDBX_DB_READER", raising=False)
+            t = libs.Trie.read_db_full(db)
+            got[mode] = (_tables_of(t), {k: np.array(x, copy=True) for k, x in t.arrays().items()})
+            t.close()
+        monkeypatch.delenv("KDBX_DB_READER", raising=False)
+        (oa, sa), pa = got["mapped"]
+        (ob, sb), pb = got["stream"]
+        assert np.array_equal(oa, ob) and np.array_equal(sa, sb), db
+        assert int((sa >> np.uint64(32) != np.uint64(0x7FFFFFFF)).sum()) > 0
+        for k in pa:
+            assert np.array_equal(pa[k], pb[k]), (db, k)
+    # a table section cut short or with an impossible header: both readers refuse
+    raw = golden_dbs["virus.k18"][0].read_bytes()
+    probe = libs.Trie.read_db(golden_dbs["virus.k18"][0])
+    names = sum(16 + len(n) for n in probe.sample_names())
+    first_table = 8 + 4 + 8 + 8 + 4 + 1 + 8 + 8 + names + 8      # header fields, sample table, table count
+    assert raw[first_table - 8:first_table] == np.uint64(256).tobytes()
+    for what, data in (("cut inside the tables", raw[:first_table + 1000]),
+                       ("allocated is not a power of two", raw[:first_table + 16] + np.uint64(48).tobytes() + raw[first_table + 24:])):
+        f = tmp_path / "bad.db"
+        f.write_bytes(data)
+        for mode in ("mapped", "stream"):
+            if mode == "stream":
+                monkeypatch.setenv("KDBX_DB_READER", "stream")
+            else:
+                monkeypatch.delenv("KDBX_DB_READER", raising=False)
+            with pytest.raises(libs.KdbxError):
+                libs.Trie.read_db_full(f)
+        monkeypatch.delenv("KDBX_DB_READER", raising=False)
