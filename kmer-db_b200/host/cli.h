@@ -26,6 +26,8 @@ struct Params {
     bool multisample_fasta = false, sparse_out = false, extend_db = false, phylip_out = false;
     int gpu = -1;              // -gpu <ordinal> (ours)
     int num_gpus = 1;          // -gpus <n> (ours): row-block sharding over n devices
+    bool from_minhash = false; // -from-minhash: samples / queries are <entry>.minhash files written by the `minhash` mode
+    bool fraction_given = false;
     bool host_build = false;   // build -host-build (ours): run the host builder explicitly (machines without a GPU)
     bool device_distance = false;   // distance -device (ours): measure + six-decimal text on the GPU (explicit; no fallback)
     bool host_csv = false;     // all2all -host-csv (ours): format the dense table on the host instead of on the device
@@ -43,6 +45,7 @@ bool parse_params(int argc, char** argv, Params& out);
 void print_usage(const std::string& mode);
 
 void run_build(const Params& p);
+void run_minhash(const Params& p);
 void run_all2all(const Params& p);
 void run_all2all_sparse(const Params& p);
 void run_all2all_parts(const Params& p);

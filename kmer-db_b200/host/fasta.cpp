@@ -95,8 +95,60 @@ SampleStream::SampleStream(const std::string& list_arg, const Alphabet& alphabet
     : files_(read_sample_list(list_arg)), alphabet_(alphabet), filter_(filter), k_(k), multisample_(multisample),
       ahead_((size_t)std::max(1, threads)) {}
 
+SampleStream::SampleStream(const std::string& list_arg, FromMinhash, int threads)
+    : files_(read_sample_list(list_arg)), alphabet_(Alphabet::make(kNt)), filter_(1.0, 0.0, 18), k_(0), multisample_(false),
+      from_minhash_(true), ahead_((size_t)std::max(1, threads)) {}
+SampleStream::SampleStream(std::vector<std::string> entries, FromMinhash, int threads)
+    : files_(std::move(entries)), alphabet_(Alphabet::make(kNt)), filter_(1.0, 0.0, 18), k_(0), multisample_(false),
+      from_minhash_(true), ahead_((size_t)std::max(1, threads)) {}
+
+namespace {
+constexpr uint32_t kMinhashSignature = 0xfedcba98u;
+}
+
+void store_minhash(const std::string& entry, const uint64_t* kmers, size_t count, uint32_t k, double fraction) {
+    const std::string path = entry + ".minhash";
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("Cannot write " + path);
+    const uint64_t n = count;
+    bool ok = std::fwrite(&kMinhashSignature, 4, 1, f) == 1 && std::fwrite(&n, 8, 1, f) == 1;
+    if (ok && count) ok = std::fwrite(kmers, 8, count, f) == count;
+    ok = ok && std::fwrite(&k, 4, 1, f) == 1 && std::fwrite(&fraction, 8, 1, f) == 1;
+    if (std::fclose(f) != 0 || !ok) throw std::runtime_error("Cannot write " + path);
+}
+
+bool load_minhash(const std::string& entry, SampleKmers& out) {
+    const std::string path = entry + ".minhash";
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    uint32_t sig = 0;
+    uint64_t n = 0;
+    bool ok = std::fread(&sig, 4, 1, f) == 1 && sig == kMinhashSignature && std::fread(&n, 8, 1, f) == 1;
+    if (ok) {   // the count must fit the file
+        const long at = std::ftell(f);
+        ok = std::fseek(f, 0, SEEK_END) == 0;
+        const long end = ok ? std::ftell(f) : 0;
+        ok = ok && at >= 0 && end >= at && (uint64_t)(end - at) >= 12 && n == ((uint64_t)(end - at) - 12) / 8 && std::fseek(f, at, SEEK_SET) == 0;
+    }
+    if (ok) {
+        out.kmers.resize(n);
+        ok = (n == 0 || std::fread(out.kmers.data(), 8, n, f) == n) && std::fread(&out.k, 4, 1, f) == 1 && std::fread(&out.fraction, 8, 1, f) == 1;
+    }
+    std::fclose(f);
+    if (!ok) { out.kmers.clear(); return false; }
+    out.name = sample_name_of(entry);
+    out.entry = entry;
+    return true;
+}
+
 std::vector<SampleKmers> SampleStream::load_file(size_t idx) const {
     std::vector<SampleKmers> out;
+    if (from_minhash_) {
+        SampleKmers s;
+        if (!load_minhash(files_[idx], s)) std::fprintf(stderr, "failed:%s\n", files_[idx].c_str());
+        else out.push_back(std::move(s));
+        return out;
+    }
     std::string data;
     if (!load_sequence_file(files_[idx], data)) {
         std::fprintf(stderr, "failed:%s\n", files_[idx].c_str());
@@ -119,6 +171,7 @@ std::vector<SampleKmers> SampleStream::load_file(size_t idx) const {
     } else {
         SampleKmers s;
         s.name = sample_name_of(files_[idx]);
+        s.entry = files_[idx];
         size_t total = 0;
         for (const FastaRecord& r : recs) total += r.len;
         s.kmers.reserve(total);

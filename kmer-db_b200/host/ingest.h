@@ -24,7 +24,15 @@ struct FastaRecord {
 struct SampleKmers {
     std::string name;
     std::vector<uint64_t> kmers;  // ascending, unique
+    std::string entry;            // the list entry the sample came from (where `minhash` stores <entry>.minhash)
+    uint32_t k = 0;               // from a .minhash file: the k-mer length and the fraction recorded there (0 otherwise)
+    double fraction = 0.0;
 };
+
+// <entry>.minhash, the reference's minhashed-sample file (MihashedInputFile::store / open, src/minhashed_input_file.h:56-121):
+// u32 0xfedcba98, u64 count, u64 kmers[count] (ascending, unique, already filtered), u32 k-mer length, f64 fraction.
+void store_minhash(const std::string& entry, const uint64_t* kmers, size_t count, uint32_t k, double fraction);
+bool load_minhash(const std::string& entry, SampleKmers& out);
 
 std::vector<std::string> read_sample_list(const std::string& arg);
 bool load_sequence_file(const std::string& entry, std::string& data);  // plain or gzip
@@ -63,6 +71,10 @@ class SampleStream {
 public:
     SampleStream(const std::string& list_arg, const Alphabet& alphabet, const MinHash& filter, uint32_t k, bool multisample,
                  int threads);
+    // -from-minhash: every list entry names <entry>.minhash (k-mer length and fraction come from the files)
+    struct FromMinhash {};
+    SampleStream(const std::string& list_arg, FromMinhash, int threads);
+    SampleStream(std::vector<std::string> entries, FromMinhash, int threads);
     // Next sample in input order; false when the input is exhausted.
     bool next(SampleKmers& out);
     size_t num_files() const { return files_.size(); }
@@ -75,6 +87,7 @@ private:
     MinHash filter_;
     uint32_t k_;
     bool multisample_;
+    bool from_minhash_ = false;
     size_t ahead_;
     size_t next_file_ = 0;
     std::deque<std::future<std::vector<SampleKmers>>> inflight_;

@@ -62,16 +62,37 @@ static void run_build_device(const Params& p) {
         if (old.hdr.alphabet_type != p.alphabet.id)
             throw std::runtime_error("Error in AbstractKmerDb::addKmers(): adding samples from different alphabet");
     }
+    // -from-minhash: the k-mer length and the fraction are the ones the `minhash` mode recorded in the samples' files
+    // (src/minhashed_input_file.h:62-84, src/console_build.cpp:105-118), so the first sample is read before the builder opens
+    std::unique_ptr<SampleStream> minhashed;
+    SampleKmers first;
+    bool have_first = false;
+    if (p.from_minhash) {
+        minhashed = std::make_unique<SampleStream>(p.files[0], SampleStream::FromMinhash{}, p.num_reader_threads);
+        have_first = minhashed->next(first);
+        if (have_first && !p.extend_db) { k = first.k; fraction = first.fraction; start = 0.0; }
+    }
     DeviceDbBuilder builder(p.gpu, alphabet, k, fraction, start);
     if (p.extend_db) { builder.adopt(old); old = Trie(); }
     std::cerr << "Processing samples..." << std::endl;
     const double t0 = now();
-    SequenceStream stream(p.files[0], p.multisample_fasta, p.num_reader_threads);
-    SampleSeq s;
     size_t n = 0;
-    while (stream.next(s)) {
-        if (builder.add_sample(s.name, s.symbols.data(), s.symbols.size()) == 0) std::cerr << "Empty sample: " << s.name << std::endl;
-        if (++n % 10 == 0) std::cerr << "\r" << n << "/" << stream.num_files() << "..." << std::flush;
+    size_t num_files = 0;
+    if (p.from_minhash) {
+        num_files = minhashed->num_files();
+        for (bool more = have_first; more; more = minhashed->next(first)) {
+            if (first.k != k) throw std::runtime_error("Error in AbstractKmerDb::addKmers(): adding kmers of different length");
+            if (first.fraction != fraction) throw std::runtime_error("Error in AbstractKmerDb::addKmers(): adding kmers of different minhash fraction");
+            if (builder.add_sample_kmers(first.name, first.kmers.data(), first.kmers.size()) == 0) std::cerr << "Empty sample: " << first.name << std::endl;
+            if (++n % 10 == 0) std::cerr << "\r" << n << "/" << num_files << "..." << std::flush;
+        }
+    } else {
+        SequenceStream stream(p.files[0], p.multisample_fasta, p.num_reader_threads);
+        SampleSeq s;
+        while (stream.next(s)) {
+            if (builder.add_sample(s.name, s.symbols.data(), s.symbols.size()) == 0) std::cerr << "Empty sample: " << s.name << std::endl;
+            if (++n % 10 == 0) std::cerr << "\r" << n << "/" << stream.num_files() << "..." << std::flush;
+        }
     }
     std::cerr << "\r" << n << "/" << n << "                      " << std::endl;
     std::cerr << "Database update time: " << now() - t0 << std::endl;
@@ -107,13 +128,15 @@ void run_build(const Params& p) {
     }
     std::cerr << "Processing samples..." << std::endl;
     const double t0 = now();
-    SampleStream stream(p.files[0], alphabet, filter, k, p.multisample_fasta, p.num_reader_threads);
+    SampleStream stream = p.from_minhash ? SampleStream(p.files[0], SampleStream::FromMinhash{}, p.num_reader_threads)
+                                         : SampleStream(p.files[0], alphabet, filter, k, p.multisample_fasta, p.num_reader_threads);
     SampleKmers s;
     size_t n = 0;
     // the alphabet recorded with every sample is the command line's one (src/console_build.cpp:117)
     const int32_t alphabet_id = p.extend_db ? p.alphabet.id : alphabet.id;
     while (stream.next(s)) {
         if (s.kmers.empty()) std::cerr << "Empty sample: " << s.name << std::endl;
+        if (p.from_minhash) { k = s.k; fraction = s.fraction; }   // (the builder refuses a sample whose k or fraction differs from the database's)
         builder.add_sample(s.name, s.kmers.data(), s.kmers.size(), k, fraction, alphabet_id, alphabet.bits_per_symbol);
         if (++n % 10 == 0) std::cerr << "\r" << n << "/" << stream.num_files() << "..." << std::flush;
     }
@@ -123,6 +146,24 @@ void run_build(const Params& p) {
     Trie db;
     builder.finish(db);
     write_db(p.files[1], db);
+}
+
+// minhash (src/console_minhash.cpp:6-60): every sample's k-mers — extracted, filtered to the fraction, sorted, unique —
+// are stored next to the sample as <entry>.minhash, to be read back by build / new2all / one2all -from-minhash.
+// Host work (file in, file out); the device enters where those modes consume the files.
+void run_minhash(const Params& p) {
+    if (p.files.size() != 1) throw usage_error(p.mode);
+    std::cerr << "Minhashing samples..." << std::endl;
+    const double t0 = now();
+    SampleStream stream(p.files[0], p.alphabet, MinHash(p.fraction, 0.0, p.kmer_length), p.kmer_length, false, p.num_reader_threads);
+    SampleKmers s;
+    size_t n = 0;
+    while (stream.next(s)) {
+        store_minhash(s.entry, s.kmers.data(), s.kmers.size(), p.kmer_length, p.fraction);
+        ++n;
+    }
+    if (n != stream.num_files()) throw std::runtime_error("Cannot open some of the samples of " + p.files[0]);
+    std::cerr << n << " samples, " << now() - t0 << " seconds" << std::endl;
 }
 
 void run_all2all(const Params& p) {
@@ -415,10 +456,42 @@ void run_new2all(const Params& p) {
     read_db(p.files[0], db, true);
     std::cerr << "OK (" << now() - t0 << " seconds)" << std::endl;
     calculator.load_database(db);
-    SequenceStream stream(p.files[1], p.multisample_fasta, p.num_reader_threads);
     std::cerr << "Processing queries..." << std::endl;
     t0 = now();
     QueryTableWriter writer(p.files[2], db, p.sparse_out, &p.filters);
+    if (p.from_minhash) {
+        // the queries are k-mer sets already (<entry>.minhash): batches of them go to kdbx_new2all_batch as they are
+        SampleStream queries(p.files[1], SampleStream::FromMinhash{}, p.num_reader_threads);
+        const size_t N = db.num_samples();
+        std::vector<std::string> names;
+        std::vector<uint64_t> kmers, q_off;
+        std::vector<uint32_t> sims;
+        kdbx_stats total{};
+        SampleKmers q;
+        bool more = true;
+        size_t done = 0;
+        while (more) {
+            names.clear(); kmers.clear(); q_off.assign(1, 0);
+            while (names.size() < 4096 && kmers.size() < ((size_t)1 << 27) && (more = queries.next(q))) {
+                if (q.k != db.hdr.kmer_length) throw std::runtime_error("Sample and database k-mer length differ");
+                kmers.insert(kmers.end(), q.kmers.begin(), q.kmers.end());
+                q_off.push_back(kmers.size());
+                names.push_back(std::move(q.name));
+            }
+            if (names.empty()) break;
+            calculator.one2all_batch(kmers.data(), q_off, sims);
+            const kdbx_stats& st = calculator.last_stats();
+            total.probes += st.probes; total.hits += st.hits; total.ms_probe += st.ms_probe; total.ms_scatter += st.ms_scatter; total.ms_total += st.ms_total;
+            for (size_t i = 0; i < names.size(); ++i) writer.write_row(names[i], q_off[i + 1] - q_off[i], sims.data() + i * N);
+            done += names.size();
+        }
+        writer.close();
+        const double dt = now() - t0;
+        std::cerr << std::endl << "EXECUTION TIMES" << std::endl << "Total: " << dt << std::endl;
+        print_stats_json(total, dt);
+        return;
+    }
+    SequenceStream stream(p.files[1], p.multisample_fasta, p.num_reader_threads);
     // the queries' SEQUENCES go to the device in batches (bounded symbols); k-mer extraction, sort and unique
     // happen there; rows are written in input order
     const uint64_t batch_symbols = (uint64_t)1 << 27;
@@ -475,6 +548,20 @@ void run_one2all(const Params& p) {
     std::cerr << "OK (" << now() - t0 << " seconds)" << std::endl;
     calculator.load_database(db);
     std::cerr << "Loading sample kmers..." << std::endl;
+    if (p.from_minhash) {
+        SampleKmers q;
+        if (!load_minhash(p.files[1], q)) throw std::runtime_error("Cannot open sample file: " + p.files[1]);
+        if (q.k != db.hdr.kmer_length) throw std::runtime_error("Sample and database k-mer length differ");
+        std::vector<uint32_t> sims;
+        std::cerr << "Calculating similarity vector..." << std::endl;
+        t0 = now();
+        calculator.one2all_batch(q.kmers.data(), {0, (uint64_t)q.kmers.size()}, sims);
+        const double dt = now() - t0;
+        std::cerr << "OK (" << dt << " seconds)" << std::endl << "Number of k-mers: " << q.kmers.size() << std::endl;
+        print_stats_json(calculator.last_stats(), dt);
+        write_one2all_csv(p.files[2], db, p.files[1], q.kmers.size(), sims.data());
+        return;
+    }
     SequenceStream stream(std::vector<std::string>{p.files[1]}, false, 1);
     SampleSeq s;
     if (!stream.next(s)) throw std::runtime_error("Cannot open sample file: " + p.files[1]);
@@ -544,6 +631,7 @@ int main(int argc, char** argv) {
         Params p;
         if (!parse_params(argc, argv, p)) return 0;
         if (p.mode == "build") run_build(p);
+        else if (p.mode == "minhash") run_minhash(p);
         else if (p.mode == "all2all") run_all2all(p);
         else if (p.mode == "all2all-sp") run_all2all_sparse(p);
         else if (p.mode == "all2all-parts") run_all2all_parts(p);

@@ -39,14 +39,17 @@ void parse_filters(std::vector<std::string>& a, OutputFilters& f, const std::str
     }
 }
 
-const char* kModes[] = {"build", "all2all", "all2all-sp", "all2all-parts", "new2all", "one2all", "distance"};
+const char* kModes[] = {"build", "minhash", "all2all", "all2all-sp", "all2all-parts", "new2all", "one2all", "distance"};
 
 }  // namespace
 
 void print_usage(const std::string& mode) {
     std::cerr << "kmer-db-b200: B200-native common k-mer counting (kmer-db compatible command line)\n";
     if (mode == "build")
-        std::cerr << "  build [-k <len>] [-f <fraction>] [-multisample-fasta] [-extend] [-alphabet <name>] [-preserve-strand] [-t <n>] <sample_list> <database>\n";
+        std::cerr << "  build [-k <len>] [-f <fraction>] [-multisample-fasta] [-extend] [-alphabet <name>] [-preserve-strand] [-t <n>] <sample_list> <database>\n"
+                     "  build -from-minhash [-extend] [-t <n>] <sample_list> <database>\n";
+    else if (mode == "minhash")
+        std::cerr << "  minhash [-f <fraction>] [-k <len>] [-alphabet <name>] [-preserve-strand] [-t <n>] <sample_list>     (writes <sample>.minhash)\n";
     else if (mode == "all2all")
         std::cerr << "  all2all [-sparse [-min [<crit>:]<v>]* [-max [<crit>:]<v>]*] [-gpus <n>] [-gpu <id>] [-t <n>] [-buffer <mb>] <database> <common_table>\n";
     else if (mode == "all2all-sp")
@@ -54,14 +57,14 @@ void print_usage(const std::string& mode) {
     else if (mode == "all2all-parts")
         std::cerr << "  all2all-parts [-min [<crit>:]<v>]* [-max [<crit>:]<v>]* [-sample-rows <crit>:<count>] [-gpus <n>] [-gpu <id>] [-t <n>] [-buffer <mb>] [-bubble-size <n>] <db_list> <common_table>\n";
     else if (mode == "new2all")
-        std::cerr << "  new2all [-multisample-fasta] [-sparse [-min ...]* [-max ...]*] [-gpu <id>] [-t <n>] <database> <sample_list> <common_table>\n";
+        std::cerr << "  new2all [-multisample-fasta | -from-minhash] [-sparse [-min ...]* [-max ...]*] [-gpu <id>] [-t <n>] <database> <sample_list> <common_table>\n";
     else if (mode == "one2all")
-        std::cerr << "  one2all [-gpu <id>] [-t <n>] <database> <sample> <common_table>\n";
+        std::cerr << "  one2all [-from-minhash] [-gpu <id>] [-t <n>] <database> <sample> <common_table>\n";
     else if (mode == "distance")
         std::cerr << "  distance <measure> [-sparse [-min [<crit>:]<v>]* [-max [<crit>:]<v>]*] [-phylip-out] <common_table> <output_table>\n"
                      "    measures: jaccard, min, max, cosine, mash, ani, ani-shorter, mash-query, num-kmers\n";
     else
-        std::cerr << "  modes: build, all2all, all2all-sp, all2all-parts, new2all, one2all, distance   (kmer-db-b200 <mode> -help)\n"
+        std::cerr << "  modes: build, minhash, all2all, all2all-sp, all2all-parts, new2all, one2all, distance   (kmer-db-b200 <mode> -help)\n"
                      "  extras: synth (generate a synthetic database), info <database>\n";
 }
 
@@ -87,10 +90,12 @@ bool parse_params(int argc, char** argv, Params& p) {
     p.device_distance = find_switch(a, "-device");
     if (p.num_gpus < 1) p.num_gpus = 1;
 
-    if (p.mode == "build") {
-        if (find_switch(a, "-from-kmers") || find_switch(a, "-from-minhash"))
-            throw std::runtime_error("-from-kmers / -from-minhash inputs are not supported by kmer-db-b200 (FASTA only)");
-        find_option(a, "-f", p.fraction);
+    if (p.mode == "build" || p.mode == "minhash") {
+        if (find_switch(a, "-from-kmers")) throw std::runtime_error("-from-kmers (KMC databases) is not supported by kmer-db-b200");
+        p.from_minhash = find_switch(a, "-from-minhash");
+        if (p.from_minhash && p.mode == "minhash") throw std::runtime_error("minhash -from-minhash: the samples are minhashed already");
+        p.fraction_given = find_option(a, "-f", p.fraction);
+        if (p.mode == "minhash" && !p.fraction_given) p.fraction = 0.01;   // src/params.cpp:130-133
         find_option(a, "-f-start", p.fraction_start);
         p.multisample_fasta = find_switch(a, "-multisample-fasta");
         std::string name;
@@ -104,6 +109,8 @@ bool parse_params(int argc, char** argv, Params& p) {
             throw std::runtime_error("K-mer length for the given alphabet cannot exceed " + std::to_string(p.alphabet.max_kmer_len));
         p.extend_db = find_switch(a, "-extend");
         p.host_build = find_switch(a, "-host-build");
+        if (p.mode == "minhash" && p.multisample_fasta)
+            throw std::runtime_error("minhash -multisample-fasta is not supported by kmer-db-b200 (one .minhash file per sample file)");
     } else if (p.mode == "all2all" || p.mode == "all2all-sp" || p.mode == "all2all-parts") {
         find_option(a, "-buffer", p.cache_buffer_mb);
         if (p.cache_buffer_mb <= 0) p.cache_buffer_mb = 8;
@@ -119,14 +126,14 @@ bool parse_params(int argc, char** argv, Params& p) {
                                          "name one, e.g. -sample-rows jaccard:" + std::to_string(p.sampling_size));
         }
     } else if (p.mode == "new2all") {
-        if (find_switch(a, "-from-kmers") || find_switch(a, "-from-minhash"))
-            throw std::runtime_error("-from-kmers / -from-minhash inputs are not supported by kmer-db-b200 (FASTA only)");
+        if (find_switch(a, "-from-kmers")) throw std::runtime_error("-from-kmers (KMC databases) is not supported by kmer-db-b200");
+        p.from_minhash = find_switch(a, "-from-minhash");
         p.multisample_fasta = find_switch(a, "-multisample-fasta");
         p.sparse_out = find_switch(a, "-sparse");
         if (p.sparse_out) parse_filters(a, p.filters, "num-kmers");
     } else if (p.mode == "one2all") {
-        if (find_switch(a, "-from-kmers") || find_switch(a, "-from-minhash"))
-            throw std::runtime_error("-from-kmers / -from-minhash inputs are not supported by kmer-db-b200 (FASTA only)");
+        if (find_switch(a, "-from-kmers")) throw std::runtime_error("-from-kmers (KMC databases) is not supported by kmer-db-b200");
+        p.from_minhash = find_switch(a, "-from-minhash");
     } else if (p.mode == "distance") {
         p.sparse_out = find_switch(a, "-sparse");
         p.phylip_out = find_switch(a, "-phylip-out");

@@ -47,3 +47,9 @@ printf '%s\n' "$P2/a.db" "$P2/b.db" > "$P2/db.list"
 "$BIN" all2all-parts -sample-rows jaccard:3 "$P2/db.list" "$P2/s.csv" && cmp "$P2/s.csv" "$HERE/virus.k18.sampled.jaccard_3.csv"
 "$BIN" all2all-parts -min jaccard:0.99 -max num-kmers:29800 -sample-rows cosine:2 "$P2/db.list" "$P2/f.csv" && cmp "$P2/f.csv" "$HERE/virus.k18.sampled.filtered.cosine_2.csv"
 rm -rf "$P2"
+# `minhash -f 0.1` on the virus genomes: digests of the 165 <sample>.minhash files the reference writes (the CI then builds
+# from them and expects test/virus/k18.frac.csv, .github/workflows/main.yml:143-148)
+M="$(mktemp -d)"; cp -r test/virus "$M/virus"
+( cd "$M" && sed 's#\./test/virus/#./virus/#' virus/seqs.list > seqs.list && "$BIN" minhash -f 0.1 seqs.list \
+  && sha256sum virus/data/*.minhash | sed 's#  virus/data/#  #' > "$HERE/virus.minhash.f01.sha256" )
+rm -rf "$M"

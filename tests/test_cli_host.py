@@ -259,3 +259,44 @@ def test_one2all_table_reproduces_reference_csv(cli, libs, oracle, ref_fixtures,
     t = libs.Trie.read_db(db)
     t.write_one2all_csv("./test/virus/data/MT159713", int(row[1]), np.array(row[2:-1], dtype=np.uint32), tmp_path / "o.csv")
     assert ou.read_bytes(tmp_path / "o.csv") == ou.read_bytes(ref_fixtures / "test/virus/MT159713.csv")
+
+
+def _virus_copy(ref_fixtures, tmp_path):
+    """a private copy of the virus inputs (the minhash mode writes next to the samples)"""
+    work = tmp_path / "w"
+    shutil.copytree(ref_fixtures / "test" / "virus", work / "test" / "virus")
+    return work
+
+
+def test_minhash_mode_and_build_from_minhash(cli, oracle, ref_bin, ref_fixtures, tmp_path):
+    """The reference's CI step `minhash -f 0.1 seqs.list; build -from-minhash seqs.list db; all2all` == test/virus/k18.frac.csv
+    (.github/workflows/main.yml:143-148).  The .minhash files must be the reference's byte for byte (digests of what the
+    reference binary wrote: tests/golden/virus.minhash.f01.sha256); CPU: the host builder reads them back, the oracle runs
+    all2all."""
+    import hashlib
+    work = _virus_copy(ref_fixtures, tmp_path)
+    cli(work, "minhash", "-f", "0.1", "test/virus/seqs.list")
+    want = dict(reversed(ln.split()) for ln in (ou.ROOT / "tests" / "golden" / "virus.minhash.f01.sha256").read_text().splitlines())
+    got = {f.name: hashlib.sha256(f.read_bytes()).hexdigest() for f in (work / "test/virus/data").glob("*.minhash")}
+    assert got == want and len(got) == 165
+    cli(work, "build", "-host-build", "-from-minhash", "test/virus/seqs.list", tmp_path / "mh.db")
+    assert _oracle_all2all_csv(oracle, tmp_path / "mh.db", tmp_path / "mh.csv") == ou.read_bytes(ref_fixtures / "test/virus/k18.frac.csv")
+    if ref_bin is not None:   # the unmodified reference builds the same database from OUR files
+        import subprocess
+        subprocess.run([str(ref_bin), "build", "-from-minhash", "test/virus/seqs.list", str(tmp_path / "ref.db")], cwd=work, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        assert _oracle_all2all_csv(oracle, tmp_path / "ref.db", tmp_path / "ref.csv") == ou.read_bytes(ref_fixtures / "test/virus/k18.frac.csv")
+    # default fraction of the mode is 0.01 (src/params.cpp:130-133); k and fraction travel in the files
+    cli(work, "minhash", "-k", "20", "test/virus/seqs.part2.list")
+    raw = (work / "test/virus/data/MT159713.minhash").read_bytes()
+    n = int.from_bytes(raw[4:12], "little")
+    assert raw[:4] == bytes.fromhex("98badcfe") and len(raw) == 4 + 8 + 8 * n + 4 + 8
+    assert int.from_bytes(raw[12 + 8 * n:16 + 8 * n], "little") == 20 and np.frombuffer(raw[16 + 8 * n:], np.float64)[0] == 0.01
+    # a database cannot take samples of another k-mer length or fraction; a missing or damaged file is an error
+    r = cli(work, "build", "-host-build", "-from-minhash", "test/virus/seqs.list", tmp_path / "bad.db", check=False)
+    assert r.returncode != 0
+    (work / "test/virus/data/NC_045512.minhash").write_bytes(b"\x98\xba\xdc\xfe" + (5).to_bytes(8, "little") + b"\0" * 8)
+    r = cli(work, "build", "-host-build", "-from-minhash", "test/virus/seqs.part1.list", tmp_path / "bad.db", check=False)
+    assert "failed:./test/virus/data/NC_045512" in r.stderr
+    r = cli(work, "minhash", "-from-kmers", "test/virus/seqs.list", check=False)
+    assert r.returncode != 0 and "not supported" in r.stderr

@@ -437,3 +437,24 @@ def test_cli_one2all(cli, ref_fixtures, tmp_path):
     assert ou.read_bytes(tmp_path / "MT159713.csv") == ou.read_bytes(ref_fixtures / "test/virus/MT159713.csv")
     r = cli(ref_fixtures, "one2all", tmp_path / "k25.db", "./test/virus/data/no-such-genome", tmp_path / "x.csv", check=False)
     assert r.returncode != 0 and "Cannot open sample file" in r.stderr
+
+
+def test_cli_minhash_inputs(cli, ref_fixtures, tmp_path):
+    """-from-minhash through the device paths: the CI step `minhash -f 0.1; build -from-minhash; all2all` == k18.frac.csv
+    (.github/workflows/main.yml:143-148) with the k-mer sets going to kdbx_builder_add_kmers; new2all / one2all
+    -from-minhash (kdbx_new2all_batch) give the tables of the same queries read from FASTA against that database."""
+    import shutil
+    work = tmp_path / "w"
+    shutil.copytree(ref_fixtures / "test" / "virus", work / "test" / "virus")
+    cli(work, "minhash", "-f", "0.1", "test/virus/seqs.list")
+    cli(work, "build", "-from-minhash", "test/virus/seqs.list", tmp_path / "mh.db")
+    cli(work, "all2all", tmp_path / "mh.db", tmp_path / "mh.csv")
+    assert ou.read_bytes(tmp_path / "mh.csv") == ou.read_bytes(ref_fixtures / "test/virus/k18.frac.csv")
+    cli(work, "build", "-from-minhash", "test/virus/seqs.part1.list", tmp_path / "p1.db")
+    for extra in ([], ["-sparse"]):
+        cli(work, "new2all", *extra, tmp_path / "p1.db", "test/virus/seqs.part2.list", tmp_path / "fasta.csv")
+        cli(work, "new2all", "-from-minhash", *extra, tmp_path / "p1.db", "test/virus/seqs.part2.list", tmp_path / "minhash.csv")
+        assert ou.read_bytes(tmp_path / "minhash.csv") == ou.read_bytes(tmp_path / "fasta.csv")
+    cli(work, "one2all", tmp_path / "p1.db", "./test/virus/data/MT159713", tmp_path / "o.fasta.csv")
+    cli(work, "one2all", "-from-minhash", tmp_path / "p1.db", "./test/virus/data/MT159713", tmp_path / "o.minhash.csv")
+    assert ou.read_bytes(tmp_path / "o.minhash.csv") == ou.read_bytes(tmp_path / "o.fasta.csv")
