@@ -23,7 +23,7 @@ U = sum_p l_p(2 n_p - l_p - 1)/2 = the number of `row[col] += w` executions of t
   cpu_baseline  the reference binary (oracle/_ref/kmer-db all2all -t <all cores>) once on the SAME .db, its CSV kept
            and compared byte for byte with the CSV written from the GPU result (parity_checked).
   --impl reference   the unmodified reference binary on the host cores.  The whole configs[1] database runs once in every
-           invocation (full_config_run; its CSV is kept for the GPU arm's cmp).  If warmup + steps such runs fit
+           invocation (full_config_run; its CSV is kept for the GPU arm's cmp).  If warmup + steps such runs fit 60 % of
            --ref-budget-s (420 s; the driver gives a run of this script 870 s and asks for 25 runs of 30 s) they all are
            runs of the whole database (same_config: true); otherwise every step is a bounded sample — the same generator,
            genomes and clusters at 1/5 (1/10 ...) of the genome length — and the line carries both rates and their quotient
@@ -306,7 +306,9 @@ def reference_arm(a, rank, world):
                 "updates": U_full, "database": path.name}
     more_full = max(0, a.warmup - 1) + a.steps             # (the run above is the first warm-up)
     elapsed = time.perf_counter() - t_begin
-    same_config = elapsed + more_full * wall_full * 1.05 <= a.ref_budget_s
+    # (runs of the whole database only when they fit with a wide margin — 60 % of the budget — so that boxes of different core
+    #  counts, and the N = 1 .. 8 runs of one box, do not end up on different sides of the line)
+    same_config = elapsed + more_full * wall_full * 1.05 <= 0.6 * a.ref_budget_s
     if same_config:
         for _ in range(max(0, a.warmup - 1)):
             run_reference_binary(path, cores)
