@@ -41,8 +41,8 @@ for step in "$@"; do
     sanitize_new) timeout 900 compute-sanitizer --tool memcheck --target-processes all --error-exitcode 9 python -m pytest tests -m gpu -x -q -k "db2db or asynchronous_chunked or cli_all2all_parts" > "$OUT/sanitizer_memcheck_new.log" 2>&1; echo "memcheck_new rc=$?" | tee -a "$OUT/summary.txt";;
     ncu_final) timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:k_scatter_diff|k_decode_locals|k_job_fill_runs" -s 3 -c 3 -f -o "$OUT/final_cfg2" python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > "$OUT/ncu_final.out" 2>&1; echo "ncu_final rc=$?" | tee -a "$OUT/summary.txt";;
     sanitize_new2) timeout 900 compute-sanitizer --tool memcheck --target-processes all --error-exitcode 9 python -m pytest tests -m gpu -x -q -k "db2db_cells or asynchronous_chunked" > "$OUT/sanitizer_memcheck_new.log" 2>&1; echo "memcheck_new rc=$?" | tee -a "$OUT/summary.txt";;
-    bench_deltas) KDBX_DECODER=deltas timeout 900 python bench.py --no-cpu-baseline --no-e2e > "$OUT/bench_deltas.json" 2> "$OUT/bench_deltas.err"; echo "bench_deltas rc=$?" | tee -a "$OUT/summary.txt";;
     tests_new) timeout 900 python -m pytest tests -m gpu -x -q -k "parts or db2db or asynchronous or sliding or golden" > "$OUT/pytest_new.log" 2>&1; echo "pytest_new rc=$?" | tee -a "$OUT/summary.txt";;
+    tests_cli_new) timeout 900 python -m pytest tests/test_gpu_widen.py -m gpu -x -q -k "sample_rows or one2all or minhash" > "$OUT/pytest_cli_new.log" 2>&1; echo "pytest_cli_new rc=$?" | tee -a "$OUT/summary.txt";;
     tests_2gpu) timeout 900 python -m pytest tests -m gpu -x -q -k "two_gpus or multi_gpu" > "$OUT/pytest_2gpu.log" 2>&1; echo "pytest_2gpu rc=$?" | tee -a "$OUT/summary.txt";;
     *) echo "unknown step $step";;
   esac
