@@ -185,11 +185,12 @@ void RowSampler::add_cell(const kdbx_csr& m, const OutputFilters* filters, const
     for (uint32_t r = 0; r < m.num_rows; ++r) {
         const uint32_t rc = (uint32_t)row_kmers[r];
         for (uint64_t i = m.row_ptr[r]; i < m.row_ptr[r + 1]; ++i) {
-            const uint32_t c = m.col[i], v = m.val[i], cc = (uint32_t)col_kmers[c];
-            if (v == 0 || (filters && !filters->pass(v, rc, cc, k))) continue;
-            const double score = criterion_(v, rc, cc, k);
+            const uint32_t c = m.col[i], v = m.val[i];
             const size_t a = (size_t)row_shift + r, b = (size_t)col_shift + c;
             if (a >= rows_.size() || b >= rows_.size()) throw std::runtime_error("sampler: sample id out of range");
+            const uint32_t cc = (uint32_t)col_kmers[c];
+            if (v == 0 || (filters && !filters->pass(v, rc, cc, k))) continue;
+            const double score = criterion_(v, rc, cc, k);
             add(a, (uint32_t)b, v, score);
             add(b, (uint32_t)a, v, score);
         }

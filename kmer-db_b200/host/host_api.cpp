@@ -297,12 +297,18 @@ int kdbxh_write_sparse_csv(const kdbxh_trie* t, const kdbx_csr* cells, const uin
         for (uint32_t i = 0; i < num_cells; ++i) {
             const uint32_t rs = row_shifts ? row_shifts[i] : 0, cs = col_shifts ? col_shifts[i] : 0;
             if ((uint64_t)rs + cells[i].num_rows > N || cs > N) throw std::runtime_error("cell outside the sample table");
+            if (cells[i].num_rows && (!cells[i].row_ptr || (cells[i].row_ptr[cells[i].num_rows] && (!cells[i].col || !cells[i].val))))
+                throw std::runtime_error("cell with rows but no arrays");
         }
         uint64_t n = 0;
         if (!sample_rows) {
             if (num_cells != 1 || (row_shifts && row_shifts[0]) || (col_shifts && col_shifts[0]))
                 throw std::runtime_error("a grid of cells needs sample_rows");
-            n = kdbx::write_sparse_csv(path, db, cells[0], &f);
+            const kdbx_csr& m = cells[0];
+            if (m.num_rows != N || !m.row_ptr || (m.row_ptr[N] && (!m.col || !m.val))) throw std::runtime_error("the matrix must have one row per sample");
+            for (uint64_t i = 0; i < m.row_ptr[N]; ++i)
+                if (m.col[i] >= N) throw std::runtime_error("column id outside the sample table");
+            n = kdbx::write_sparse_csv(path, db, m, &f);
         } else {
             kdbx::metric_fn crit = nullptr;
             int count = 0;
